@@ -1,0 +1,150 @@
+/*
+ * include/psolver.h — C ABI of libpsolver.so, the B200-native unified particle solver step.
+ *
+ * Drop-in boundary.  In the reference (ebirenbaum/ParticleSolver) the solver step sits behind the
+ * extern "C" wrapper layer declared in gpu/src/cuda/wrappers.cuh:12-97, gpu/src/cuda/util.cuh:6-25 and
+ * gpu/src/cuda/shared_variables.cuh:13-36 and is called only from ParticleSystem
+ * (gpu/src/particlesystem.cpp).  This library exports
+ *   (1) a context-based interface (ps_*): opaque context, 64-bit sizes, error codes, one CUDA stream per
+ *       context, whole-step entry point ps_step() == ParticleSystem::update (particlesystem.cpp:144-246)
+ *       plus one entry point per stage for parity checks; and
+ *   (2) the reference's own wrapper names and argument orders (include/ps_reference_abi.h), implemented
+ *       on the same kernels, so the reference's ParticleSystem links against it unchanged.
+ * Plain pointers and sizes only; no torch / thrust / C++ types cross this boundary.
+ * There is no CPU fallback: every entry point returns PS_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef PSOLVER_H
+#define PSOLVER_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* phase codes — gpu/src/cuda/shared_variables.cuh:4-9 */
+#define PS_PHASE_NO_COLLIDE (-1)
+#define PS_PHASE_FLUID 0
+#define PS_PHASE_GAS 1
+#define PS_PHASE_CLOTH 2
+#define PS_PHASE_SOLID 3
+#define PS_PHASE_RIGID 4 /* + body id */
+
+enum {
+    PS_OK = 0,
+    PS_ERR_INVALID = 1,  /* bad argument (null, non power-of-two grid, ...) */
+    PS_ERR_CUDA = 2,     /* CUDA runtime / cuRAND failure; see ps_last_error() */
+    PS_ERR_CAPACITY = 3, /* append beyond max_particles (the reference silently drops: particlesystem.cpp:311,335) */
+    PS_ERR_STATE = 4     /* call order violated (e.g. neighbour solve before a grid build) */
+};
+
+/* Superset of SimParams (gpu/src/cuda/kernel.cuh:9-22) + what ParticleSystem keeps beside it
+ * (bounds, iteration count: gpu/src/particlesystem.h:113-116).  Defaults: ps_default_params(). */
+typedef struct PsParams {
+    float gravity[3];            /* (0,-9.8,0)  particlesystem.cpp:65 */
+    float global_damping;        /* 1.0, unused by the reference's live kernels */
+    float particle_radius;       /* 0.25        particleapp.cpp:24 */
+    uint32_t grid_size[3];       /* powers of two; 64^3 in the reference (particleapp.cpp:25) */
+    float world_origin[3];       /* 0           particlesystem.cpp:61 */
+    float cell_size[3];          /* 2*radius    particlesystem.cpp:62-63 */
+    int32_t min_bounds[3];       /* scene box, integer like the reference's int3 */
+    int32_t max_bounds[3];
+    uint32_t solver_iterations;  /* 5           particleapp.cpp:38 */
+    float omega;                 /* SOR factor on the Jacobi-averaged deltas; 1.0 == reference */
+    uint32_t flags;              /* PS_FLAG_* */
+} PsParams;
+
+#define PS_FLAG_NONE 0u
+#define PS_FLAG_ZERO_NONFLUID_LAMBDA 1u /* deviation: lambda of non-fluid slots reads 0 instead of a stale value */
+
+typedef struct PsCtx PsCtx;
+
+/* array selectors for ps_download / ps_upload / ps_device_ptr */
+enum {
+    PS_ARR_POS = 0,          /* float4[n]  current positions (the reference's VBO) */
+    PS_ARR_VEL = 1,          /* float4[n]  V            integration.cu:23 */
+    PS_ARR_PREV = 2,         /* float4[n]  Xstar        shared_variables.cu:8 */
+    PS_ARR_INV_MASS = 3,     /* float[n]   W            shared_variables.cu:9 */
+    PS_ARR_PHASE = 4,        /* int[n]     phase        shared_variables.cu:10 */
+    PS_ARR_REST_DENSITY = 5, /* float[n]   ros          integration.cu:27 */
+    PS_ARR_HASH = 6,         /* uint[n]    sorted cell keys      m_dGridParticleHash */
+    PS_ARR_INDEX = 7,        /* uint[n]    sorted order          m_dGridParticleIndex */
+    PS_ARR_CELL_START = 8,   /* uint[cells] 0xffffffff = empty   m_dCellStart */
+    PS_ARR_CELL_END = 9,     /* uint[cells] valid where start != 0xffffffff  m_dCellEnd */
+    PS_ARR_SORTED_POS = 10,  /* float4[n] */
+    PS_ARR_SORTED_INV_MASS = 11,
+    PS_ARR_SORTED_PHASE = 12,
+    PS_ARR_LAMBDA = 13,      /* float[n] by sorted slot  integration.cu:24 */
+    PS_ARR_NUM_NEIGHBORS = 14, /* uint[n] by sorted slot integration.cu:30 */
+    PS_ARR_RANDS = 15,       /* float[iterations*6] wall-jitter uniforms of the last step */
+    PS_ARR_OCCURRENCES = 16, /* uint[n]    solver.cu:41 */
+    PS_ARR_CELL_BEGIN = 17   /* uint[cells+1] dense lower-bound table (internal; exposed for tests) */
+};
+
+void ps_default_params(PsParams *p);
+const char *ps_last_error(void);
+const char *ps_version(void);
+
+int ps_create(int device, const PsParams *params, uint64_t max_particles, PsCtx **out);
+int ps_destroy(PsCtx *ctx);
+int ps_set_params(PsCtx *ctx, const PsParams *params);   /* setParameters, integration.cu:96-100 */
+int ps_get_params(PsCtx *ctx, PsParams *out);
+uint64_t ps_num_particles(PsCtx *ctx);
+uint64_t ps_num_cells(PsCtx *ctx);
+
+/* host pointers, copied.  pos4/vel4: float[4n]; inv_mass, rest_density: float[n]; phase: int[n].
+ * == the VBO write + appendIntegrationParticle + appendPhaseAndMass + appendSolverParticle of
+ * ParticleSystem::addParticleMultiple (particlesystem.cpp:333-348). */
+int ps_append_particles(PsCtx *ctx, const float *pos4, const float *vel4, const float *inv_mass,
+                        const float *rest_density, const int32_t *phase, uint64_t n);
+/* addDistanceConstraint (solver.cu:125-156): idx_pairs uint[2m], rest float[m] */
+int ps_add_distance_constraints(PsCtx *ctx, const uint32_t *idx_pairs, const float *rest, uint64_t m);
+/* addPointConstraint (solver.cu:108-123): idx uint[p], xyz float[3p] */
+int ps_add_point_constraints(PsCtx *ctx, const uint32_t *idx, const float *xyz, uint64_t p);
+
+/* constraint lists as held by the context, in insertion order (host copies; any pointer may be NULL) */
+uint64_t ps_num_distance_constraints(PsCtx *ctx);
+uint64_t ps_num_point_constraints(PsCtx *ctx);
+int ps_copy_distance_constraints(PsCtx *ctx, uint32_t *idx_pairs, float *rest);
+int ps_copy_point_constraints(PsCtx *ctx, uint32_t *idx, float *xyz);
+
+/* One whole step == ParticleSystem::update(dt) (particlesystem.cpp:144-246), asynchronous on the context's
+ * stream, replayed from a CUDA graph after the first call.  dt is clamped to 0.05 like the reference (:149). */
+int ps_step(PsCtx *ctx, float dt);
+int ps_sync(PsCtx *ctx);
+/* milliseconds of device time of the last ps_step (CUDA events on the context's stream); syncs. */
+int ps_last_step_ms(PsCtx *ctx, float *ms);
+
+/* Per-stage entry points, in the order update() calls them; each is asynchronous on the context's stream. */
+int ps_begin_step(PsCtx *ctx);               /* draws this step's wall-jitter uniforms (cuRAND XORWOW, seed 1234) */
+int ps_predict(PsCtx *ctx, float dt);        /* K1  integrateSystem               integration.cu:122-135 */
+int ps_build_grid(PsCtx *ctx);               /* K2-K4 calcHash, sortParticles, reorderDataAndFindCellStart */
+int ps_solve_contacts(PsCtx *ctx);           /* K5  collide                       integration.cu:338-386 */
+int ps_solve_fluid(PsCtx *ctx);              /* K6+K7 solveFluids                 integration.cu:453-508 */
+int ps_collide_world(PsCtx *ctx, uint32_t iteration); /* K8 collideWorld          integration.cu:319-336 */
+int ps_solve_distance(PsCtx *ctx);           /* K9  solveDistanceConstraints      solver.cu:196-231 */
+int ps_solve_point(PsCtx *ctx);              /* K10 solvePointConstraints         solver.cu:180-194 */
+int ps_update_velocity(PsCtx *ctx, float dt);/* K11 calcVelocity                  integration.cu:416-426 */
+
+/* Synchronous copies (they sync the context's stream first). count is in elements of the array's type
+ * (float4 counts as 4 floats: pass 4*n). */
+int ps_download(PsCtx *ctx, int which, void *host, uint64_t offset_elems, uint64_t count_elems);
+int ps_upload(PsCtx *ctx, int which, const void *host, uint64_t offset_elems, uint64_t count_elems);
+/* asynchronous variants on the context's stream; host memory should be pinned */
+int ps_download_async(PsCtx *ctx, int which, void *host, uint64_t offset_elems, uint64_t count_elems);
+int ps_upload_async(PsCtx *ctx, int which, const void *host, uint64_t offset_elems, uint64_t count_elems);
+/* raw device pointer of an array (for zero-copy interop with a viewer or torch); NULL if unknown */
+void *ps_device_ptr(PsCtx *ctx, int which);
+/* the context's cudaStream_t, as an opaque pointer */
+void *ps_stream(PsCtx *ctx);
+
+/* number of kernel launches issued by the last ps_step (counted at capture time) */
+uint32_t ps_launches_per_step(PsCtx *ctx);
+
+/* ---- spatial slab decomposition (multi-GPU; one context per GPU, exchange done by the caller over NCCL) ----
+ * A context holds `owned` particles followed by `ghost` particles (copies of neighbours' particles within the
+ * halo of the slab faces).  Ghosts take part in grid build and as neighbours, but are never moved. */
+int ps_set_ghost_count(PsCtx *ctx, uint64_t ghosts);
+uint64_t ps_num_owned(PsCtx *ctx);
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSOLVER_H */

@@ -1,0 +1,357 @@
+"""particlesolver_b200 — B200-native unified particle solver step (PBF fluids, contacts, cloth/rope constraints).
+
+Python here is plumbing only: it loads the in-tree `libpsolver.so` (hand-written sm_100a CUDA kernels + the C++
+host class) through its C ABI (include/psolver.h) with ctypes.  There is NO CPU path: importing works without a
+GPU (so that symbols can be checked), but creating a solver without an sm_100 device raises.
+
+Mirrors the reference's host interface (ebirenbaum/ParticleSolver gpu/src/particlesystem.h:22-52):
+`ParticleSystem(radius, grid, max_particles, min_bounds, max_bounds, iterations)` with `addFluid`,
+`addParticleGrid`, `addHorizCloth`, `addRope`, `addStaticSphere`, `update(dt)`, ... implemented by the C++ class
+in csrc/particle_system.cpp (this module only forwards).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsolver.so")
+
+# phase codes, reference gpu/src/cuda/shared_variables.cuh:4-9
+NO_COLLIDE, FLUID, GAS, CLOTH, SOLID, RIGID = -1, 0, 1, 2, 3, 4
+
+PS_OK, PS_ERR_INVALID, PS_ERR_CUDA, PS_ERR_CAPACITY, PS_ERR_STATE = 0, 1, 2, 3, 4
+FLAG_ZERO_NONFLUID_LAMBDA = 1
+
+(ARR_POS, ARR_VEL, ARR_PREV, ARR_INV_MASS, ARR_PHASE, ARR_REST_DENSITY, ARR_HASH, ARR_INDEX, ARR_CELL_START, ARR_CELL_END,
+ ARR_SORTED_POS, ARR_SORTED_INV_MASS, ARR_SORTED_PHASE, ARR_LAMBDA, ARR_NUM_NEIGHBORS, ARR_RANDS, ARR_OCCURRENCES,
+ ARR_CELL_BEGIN) = range(18)
+_ARR_DTYPE = {ARR_POS: np.float32, ARR_VEL: np.float32, ARR_PREV: np.float32, ARR_INV_MASS: np.float32, ARR_PHASE: np.int32,
+              ARR_REST_DENSITY: np.float32, ARR_HASH: np.uint32, ARR_INDEX: np.uint32, ARR_CELL_START: np.uint32,
+              ARR_CELL_END: np.uint32, ARR_SORTED_POS: np.float32, ARR_SORTED_INV_MASS: np.float32, ARR_SORTED_PHASE: np.int32,
+              ARR_LAMBDA: np.float32, ARR_NUM_NEIGHBORS: np.uint32, ARR_RANDS: np.float32, ARR_OCCURRENCES: np.uint32,
+              ARR_CELL_BEGIN: np.uint32}
+_ARR_WIDTH = {ARR_POS: 4, ARR_VEL: 4, ARR_PREV: 4, ARR_SORTED_POS: 4}
+
+
+class PsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpsolver error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    """PsParams (include/psolver.h) — superset of the reference's SimParams (gpu/src/cuda/kernel.cuh:9-22)."""
+    _fields_ = [("gravity", C.c_float * 3), ("global_damping", C.c_float), ("particle_radius", C.c_float),
+                ("grid_size", C.c_uint32 * 3), ("world_origin", C.c_float * 3), ("cell_size", C.c_float * 3),
+                ("min_bounds", C.c_int32 * 3), ("max_bounds", C.c_int32 * 3), ("solver_iterations", C.c_uint32),
+                ("omega", C.c_float), ("flags", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded libpsolver.so.  Raises if the extension has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m particlesolver_b200.build` "
+                              "(sm_100a CUDA extension; there is no CPU or PyTorch fallback)")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        vp, u64, u32, i32, f32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_float
+        L.ps_last_error.restype = C.c_char_p
+        L.ps_version.restype = C.c_char_p
+        L.ps_default_params.argtypes = [C.POINTER(Params)]
+        L.ps_default_params.restype = None
+        L.ps_create.argtypes = [i32, C.POINTER(Params), u64, C.POINTER(vp)]
+        L.ps_destroy.argtypes = [vp]
+        L.ps_set_params.argtypes = [vp, C.POINTER(Params)]
+        L.ps_get_params.argtypes = [vp, C.POINTER(Params)]
+        for f in ("ps_num_particles", "ps_num_cells", "ps_num_owned"):
+            getattr(L, f).argtypes = [vp]
+            getattr(L, f).restype = u64
+        L.ps_launches_per_step.argtypes = [vp]
+        L.ps_launches_per_step.restype = u32
+        L.ps_append_particles.argtypes = [vp, vp, vp, vp, vp, vp, u64]
+        L.ps_add_distance_constraints.argtypes = [vp, vp, vp, u64]
+        L.ps_add_point_constraints.argtypes = [vp, vp, vp, u64]
+        L.ps_num_distance_constraints.argtypes = [vp]
+        L.ps_num_distance_constraints.restype = u64
+        L.ps_num_point_constraints.argtypes = [vp]
+        L.ps_num_point_constraints.restype = u64
+        L.ps_copy_distance_constraints.argtypes = [vp, vp, vp]
+        L.ps_copy_point_constraints.argtypes = [vp, vp, vp]
+        L.ps_step.argtypes = [vp, f32]
+        L.ps_sync.argtypes = [vp]
+        L.ps_last_step_ms.argtypes = [vp, C.POINTER(f32)]
+        for f in ("ps_begin_step", "ps_build_grid", "ps_solve_contacts", "ps_solve_fluid", "ps_solve_distance", "ps_solve_point"):
+            getattr(L, f).argtypes = [vp]
+        L.ps_predict.argtypes = [vp, f32]
+        L.ps_update_velocity.argtypes = [vp, f32]
+        L.ps_collide_world.argtypes = [vp, u32]
+        for f in ("ps_download", "ps_upload", "ps_download_async", "ps_upload_async"):
+            getattr(L, f).argtypes = [vp, i32, vp, u64, u64]
+        L.ps_device_ptr.argtypes = [vp, i32]
+        L.ps_device_ptr.restype = vp
+        L.ps_stream.argtypes = [vp]
+        L.ps_stream.restype = vp
+        L.ps_set_ghost_count.argtypes = [vp, u64]
+        # C++ host class (csrc/particle_system.cpp)
+        L.pshost_create.argtypes = [f32, u32, u32, u32, u32, vp, vp, i32]
+        L.pshost_create.restype = vp
+        L.pshost_build_scene.argtypes = [C.c_char_p, i32, u32, i32, i32, i32]
+        L.pshost_build_scene.restype = vp
+        L.pshost_destroy.argtypes = [vp]
+        L.pshost_destroy.restype = None
+        L.pshost_ctx.argtypes = [vp]
+        L.pshost_ctx.restype = vp
+        L.pshost_error.argtypes = [vp]
+        L.pshost_error.restype = C.c_char_p
+        L.pshost_num_particles.argtypes = [vp]
+        L.pshost_num_particles.restype = u32
+        L.pshost_update.argtypes = [vp, f32]
+        L.pshost_update.restype = None
+        L.pshost_add_fluid.argtypes = [vp, vp, vp, f32, f32]
+        L.pshost_add_particle_grid.argtypes = [vp, vp, vp, f32, i32]
+        L.pshost_add_horiz_cloth.argtypes = [vp, vp, vp, vp, vp, f32, i32]
+        L.pshost_add_rope.argtypes = [vp, vp, vp, f32, i32, f32, i32]
+        L.pshost_add_static_sphere.argtypes = [vp, vp, vp, f32]
+        L.pshost_set_particle_to_add.argtypes = [vp, vp, vp, f32]
+        L.pshost_set_fluid_to_add.argtypes = [vp, vp, vp, f32, f32]
+        L.pshost_make_point_constraint.argtypes = [vp, u32, vp]
+        L.pshost_make_distance_constraint.argtypes = [vp, u32, u32, f32]
+        L.pshost_get_positions.argtypes = [vp, vp]
+        L.pshost_get_velocities.argtypes = [vp, vp]
+        for f in ("pshost_add_fluid", "pshost_add_particle_grid", "pshost_add_horiz_cloth", "pshost_add_rope", "pshost_add_static_sphere",
+                  "pshost_set_particle_to_add", "pshost_set_fluid_to_add", "pshost_make_point_constraint",
+                  "pshost_make_distance_constraint", "pshost_get_positions", "pshost_get_velocities"):
+            getattr(L, f).restype = None
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != PS_OK:
+        raise PsError(rc, lib().ps_last_error().decode())
+
+
+def default_params():
+    p = Params()
+    lib().ps_default_params(C.byref(p))
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Solver:
+    """Thin handle on a PsCtx: raw SoA access + whole-step and per-stage entry points (include/psolver.h)."""
+
+    def __init__(self, params=None, max_particles=1 << 20, device=0, _borrowed=None):
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self._h = C.c_void_p(_borrowed)
+            return
+        p = params if params is not None else default_params()
+        h = C.c_void_p()
+        _check(lib().ps_create(device, C.byref(p), max_particles, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and self._owned:
+            lib().ps_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    # --- state ---
+    @property
+    def n(self):
+        return int(lib().ps_num_particles(self._h))
+
+    @property
+    def num_cells(self):
+        return int(lib().ps_num_cells(self._h))
+
+    @property
+    def params(self):
+        p = Params()
+        _check(lib().ps_get_params(self._h, C.byref(p)))
+        return p
+
+    def set_params(self, p):
+        _check(lib().ps_set_params(self._h, C.byref(p)))
+
+    def append(self, pos4, vel4, inv_mass, rest_density, phase):
+        pos4, vel4 = _arr(pos4, np.float32).reshape(-1, 4), _arr(vel4, np.float32).reshape(-1, 4)
+        n = pos4.shape[0]
+        w, ro, ph = _arr(inv_mass, np.float32).reshape(-1), _arr(rest_density, np.float32).reshape(-1), _arr(phase, np.int32).reshape(-1)
+        assert vel4.shape[0] == n and w.size == n and ro.size == n and ph.size == n
+        _check(lib().ps_append_particles(self._h, _ptr(pos4), _ptr(vel4), _ptr(w), _ptr(ro), _ptr(ph), n))
+
+    def add_distance_constraints(self, idx_pairs, rest):
+        idx, rest = _arr(idx_pairs, np.uint32).reshape(-1), _arr(rest, np.float32).reshape(-1)
+        assert idx.size == 2 * rest.size
+        _check(lib().ps_add_distance_constraints(self._h, _ptr(idx), _ptr(rest), rest.size))
+
+    def add_point_constraints(self, idx, xyz):
+        idx, xyz = _arr(idx, np.uint32).reshape(-1), _arr(xyz, np.float32).reshape(-1)
+        assert xyz.size == 3 * idx.size
+        _check(lib().ps_add_point_constraints(self._h, _ptr(idx), _ptr(xyz), idx.size))
+
+    def distance_constraints(self):
+        m = int(lib().ps_num_distance_constraints(self._h))
+        idx, rest = np.zeros(2 * m, np.uint32), np.zeros(m, np.float32)
+        _check(lib().ps_copy_distance_constraints(self._h, _ptr(idx), _ptr(rest)))
+        return idx, rest
+
+    def point_constraints(self):
+        k = int(lib().ps_num_point_constraints(self._h))
+        idx, xyz = np.zeros(k, np.uint32), np.zeros(3 * k, np.float32)
+        _check(lib().ps_copy_point_constraints(self._h, _ptr(idx), _ptr(xyz)))
+        return idx, xyz
+
+    # --- stepping ---
+    def step(self, dt):
+        _check(lib().ps_step(self._h, dt))
+
+    def sync(self):
+        _check(lib().ps_sync(self._h))
+
+    def last_step_ms(self):
+        ms = C.c_float()
+        _check(lib().ps_last_step_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    @property
+    def launches_per_step(self):
+        return int(lib().ps_launches_per_step(self._h))
+
+    def begin_step(self): _check(lib().ps_begin_step(self._h))
+    def predict(self, dt): _check(lib().ps_predict(self._h, dt))
+    def build_grid(self): _check(lib().ps_build_grid(self._h))
+    def solve_contacts(self): _check(lib().ps_solve_contacts(self._h))
+    def solve_fluid(self): _check(lib().ps_solve_fluid(self._h))
+    def collide_world(self, iteration): _check(lib().ps_collide_world(self._h, iteration))
+    def solve_distance(self): _check(lib().ps_solve_distance(self._h))
+    def solve_point(self): _check(lib().ps_solve_point(self._h))
+    def update_velocity(self, dt): _check(lib().ps_update_velocity(self._h, dt))
+
+    # --- data ---
+    def _count(self, which):
+        if which in (ARR_CELL_START, ARR_CELL_END):
+            return self.num_cells
+        if which == ARR_CELL_BEGIN:
+            return self.num_cells + 1
+        if which == ARR_RANDS:
+            return int(self.params.solver_iterations) * 6
+        return self.n * _ARR_WIDTH.get(which, 1)
+
+    def download(self, which, out=None):
+        cnt = self._count(which)
+        a = out if out is not None else np.empty(cnt, dtype=_ARR_DTYPE[which])
+        _check(lib().ps_download(self._h, which, _ptr(a), 0, cnt))
+        w = _ARR_WIDTH.get(which, 1)
+        return a.reshape(-1, w) if w > 1 else a
+
+    def upload(self, which, data, offset_elems=0):
+        a = _arr(data, _ARR_DTYPE[which]).reshape(-1)
+        _check(lib().ps_upload(self._h, which, _ptr(a), offset_elems, a.size))
+
+    def device_ptr(self, which):
+        return lib().ps_device_ptr(self._h, which)
+
+    @property
+    def stream(self):
+        return lib().ps_stream(self._h)
+
+    def set_ghost_count(self, g):
+        _check(lib().ps_set_ghost_count(self._h, g))
+
+
+class ParticleSystem:
+    """The reference's host class (gpu/src/particlesystem.h:22-52), forwarded to the C++ implementation."""
+
+    def __init__(self, particleRadius=0.25, gridSize=(64, 64, 64), maxParticles=15000, minBounds=(-50, 0, -50),
+                 maxBounds=(50, 200, 50), iterations=5, _handle=None):
+        L = lib()
+        if _handle is None:
+            mn, mx = (C.c_int * 3)(*minBounds), (C.c_int * 3)(*maxBounds)
+            _handle = L.pshost_create(particleRadius, gridSize[0], gridSize[1], gridSize[2], maxParticles, mn, mx, iterations)
+        self._h = C.c_void_p(_handle)
+        self._raise()
+
+    @classmethod
+    def scene(cls, name, grid=64, max_particles=15000, iterations=5, side=100, seed=1):
+        """One of the reference's demo scenes ("1".."9", particleapp.cpp:141-215) or the scaled configs "c2"/"c3"."""
+        h = lib().pshost_build_scene(str(name).encode(), grid, max_particles, iterations, side, seed)
+        if not h:
+            raise ValueError(f"unknown scene {name!r}")
+        return cls(_handle=h)
+
+    def _raise(self):
+        e = lib().pshost_error(self._h).decode()
+        if e and not e.startswith("addParticleMultiple: batch dropped"):
+            raise PsError(PS_ERR_CUDA, e)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pshost_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    @property
+    def solver(self):
+        return Solver(_borrowed=lib().pshost_ctx(self._h))
+
+    def getNumParticles(self):
+        return int(lib().pshost_num_particles(self._h))
+
+    def update(self, deltaTime):
+        lib().pshost_update(self._h, deltaTime)
+        self._raise()
+
+    def addFluid(self, ll, ur, mass, density, color=(0, 0, 1)):
+        lib().pshost_add_fluid(self._h, (C.c_int * 3)(*ll), (C.c_int * 3)(*ur), mass, density); self._raise()
+
+    def addParticleGrid(self, ll, ur, mass, addJitter):
+        lib().pshost_add_particle_grid(self._h, (C.c_int * 3)(*ll), (C.c_int * 3)(*ur), mass, int(addJitter)); self._raise()
+
+    def addHorizCloth(self, ll, ur, spacing, dist, mass, holdEdges):
+        lib().pshost_add_horiz_cloth(self._h, (C.c_int * 2)(*ll), (C.c_int * 2)(*ur), (C.c_float * 3)(*spacing), (C.c_float * 2)(*dist), mass,
+                                     int(holdEdges)); self._raise()
+
+    def addRope(self, start, spacing, dist, numLinks, mass, constrainStart):
+        lib().pshost_add_rope(self._h, (C.c_float * 3)(*start), (C.c_float * 3)(*spacing), dist, numLinks, mass, int(constrainStart)); self._raise()
+
+    def addStaticSphere(self, ll, ur, spacing):
+        lib().pshost_add_static_sphere(self._h, (C.c_int * 3)(*ll), (C.c_int * 3)(*ur), spacing); self._raise()
+
+    def setParticleToAdd(self, pos, vel, mass):
+        lib().pshost_set_particle_to_add(self._h, (C.c_float * 3)(*pos), (C.c_float * 3)(*vel), mass)
+
+    def setFluidToAdd(self, pos, color, mass, density):
+        lib().pshost_set_fluid_to_add(self._h, (C.c_float * 3)(*pos), (C.c_float * 3)(*color), mass, density)
+
+    def makePointConstraint(self, index, point):
+        lib().pshost_make_point_constraint(self._h, index, (C.c_float * 3)(*point)); self._raise()
+
+    def makeDistanceConstraint(self, index, distance):
+        lib().pshost_make_distance_constraint(self._h, index[0], index[1], distance); self._raise()
+
+    def getPositions(self):
+        a = np.empty((self.getNumParticles(), 4), np.float32)
+        lib().pshost_get_positions(self._h, _ptr(a))
+        return a
+
+    def getVelocities(self):
+        a = np.empty((self.getNumParticles(), 4), np.float32)
+        lib().pshost_get_velocities(self._h, _ptr(a))
+        return a

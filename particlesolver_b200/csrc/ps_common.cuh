@@ -1,0 +1,117 @@
+// particlesolver_b200/csrc/ps_common.cuh — shared device/host declarations of libpsolver (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libpsolver is written for sm_100a (B200) only"
+#endif
+
+typedef uint32_t u32;
+
+// phase codes (reference gpu/src/cuda/shared_variables.cuh:4-9)
+#define PH_FLUID 0
+#define PH_CLOTH 2
+#define PH_SOLID 3
+
+// solver constants (reference gpu/src/cuda/integration_kernel.cuh:20-40)
+#define PS_EPS 0.001f
+#define PS_MAX_NEIGHBORS 500u
+#define PS_H 2.f
+#define PS_H2 4.f
+#define PS_H6 64.f
+#define PS_POLY6 0.00305992474f
+#define PS_SPIKY 0.22381163872f
+#define PS_RELAX .01f
+#define PS_K_P .1f
+#define PS_DQ_P .2f
+#define PS_S_FRICTION .005f
+#define PS_K_FRICTION .0002f
+
+#define PS_MAX_RAD 8
+
+// uniform grid descriptor, passed by value (kernel parameter space == constant bank, one per launch, so
+// several contexts can coexist; the reference uses a single __constant__ SimParams, integration_kernel.cuh:55)
+struct GridDesc {
+    float ox, oy, oz;  // worldOrigin
+    float cx, cy, cz;  // cellSize
+    u32 gx, gy, gz;    // gridSize (powers of two)
+    u32 mx, my, mz;    // gridSize-1
+    u32 num_cells;
+};
+
+// Row stencil: for each (dz,dy) the largest |dx| whose cell can still hold a particle within the support
+// radius, or -1 if the whole row is out of reach.  rad = ceil(H/cell) as in integration_kernel.cuh:546.
+struct StencilDesc {
+    int rad;
+    signed char xr[(2 * PS_MAX_RAD + 1) * (2 * PS_MAX_RAD + 1)];
+};
+
+struct WorldDesc {
+    float radius;
+    int min_x, min_y, min_z;
+    int max_x, max_y, max_z;
+};
+
+// ---- calcGridPos / calcGridHash semantics (reference integration_kernel.cuh:187-203) ----
+// floor((p-origin)/cell) with the approximate divide the reference's -use_fast_math build emits
+// (exact for power-of-two cell sizes), then '&' wrap and x-fastest linearisation.
+__device__ __forceinline__ int3 ps_grid_pos(const GridDesc &g, float x, float y, float z) {
+    int3 gp;
+    gp.x = (int)floorf(__fdividef(x - g.ox, g.cx));
+    gp.y = (int)floorf(__fdividef(y - g.oy, g.cy));
+    gp.z = (int)floorf(__fdividef(z - g.oz, g.cz));
+    return gp;
+}
+__device__ __forceinline__ u32 ps_grid_hash(const GridDesc &g, int3 gp) {
+    u32 x = (u32)gp.x & g.mx, y = (u32)gp.y & g.my, z = (u32)gp.z & g.mz;
+    return (z * g.gy + y) * g.gx + x;
+}
+
+// streaming (read-once / write-once) 128-bit accesses that do not pollute L1
+__device__ __forceinline__ float4 ld_stream4(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream4(float4 *p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---------------- launchers (host side, all asynchronous on `s`) ----------------
+// ps_stream_kernels.cu
+void ps_launch_predict(float4 *pos, const float4 *vel, float4 *prev, u32 n, float dt, float3 g, cudaStream_t s);
+void ps_launch_velocity(const float4 *pos, const float4 *prev, float4 *vel, u32 n, float dt, cudaStream_t s);
+void ps_launch_collide_world(float4 *pos, const float4 *prev, const int *phase, u32 n, const float *rands6, WorldDesc w, cudaStream_t s);
+void ps_launch_point(float4 *pos, const u32 *pidx, const float *pxyz, u32 np, cudaStream_t s);
+void ps_launch_distance(float4 *pos, float4 *scratch, const u32 *csr_particle, const u32 *csr_off, const u32 *csr_other,
+                        const float *csr_rest, const u32 *occ, u32 num_constrained, float omega, cudaStream_t s);
+// ps_grid_kernels.cu
+void ps_launch_calc_hash(u32 *hash, u32 *index, const float4 *pos, u32 n, GridDesc g, cudaStream_t s);
+void ps_launch_reorder(u32 *cell_start, u32 *cell_end, float4 *spos, float *sw, int *sphase, const u32 *hash, const u32 *index,
+                       const float4 *pos, const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s);
+// dense lower-bound table cell_begin[c] = #particles with key < c, c in [0,num_cells]; from cell_start
+void ps_launch_cell_begin(u32 *cell_begin, const u32 *cell_start, u32 *block_min, u32 n, u32 num_cells, cudaStream_t s);
+size_t ps_cell_begin_scratch_elems(u32 num_cells);
+// ps_sort_kernels.cu
+struct SortScratch {
+    u32 *hist;    // [4][256] global digit histograms
+    u32 *status;  // [passes][tiles][256] decoupled look-back words
+    u32 *ticket;  // [4] dynamic tile ids
+};
+size_t ps_sort_status_elems(u32 n, int passes);
+int ps_sort_passes(u32 num_cells);
+// Stable LSD radix sort of (key,val) pairs on the low 8*passes key bits, ping-ponging between (kA,vA) and
+// (kB,vB): input in A, result in A when `passes` is even and in B when it is odd (the caller picks where the
+// unsorted keys are written so that the result lands where it wants it).  3 + passes launches + 3 memsets.
+// identity_vals: vals[i]==i on entry is assumed and vA is never read (saves one 4 B/particle read).
+void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool identity_vals, SortScratch sc, cudaStream_t s);
+// ps_neighbor_kernels.cu
+void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
+                       const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, cudaStream_t s);
+void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
+                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st,
+                            bool zero_nonfluid, cudaStream_t s);
+void ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
+                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
+                            cudaStream_t s);

@@ -1,0 +1,624 @@
+// particlesolver_b200/csrc/ps_context.cu — context, memory, step orchestration and the ps_* C ABI
+// (include/psolver.h).  Host-side equivalent of the reference's wrapper layer
+// (gpu/src/cuda/{integration,solver,shared_variables,util}.cu) + ParticleSystem::update
+// (gpu/src/particlesystem.cpp:144-246), without process-global state: everything lives in a PsCtx.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include "ps_context.h"
+
+// ------------------------------------------------------------------ errors ------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void ps_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+#define CU(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) {                                                                      \
+            ps_set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);    \
+            return PS_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+#define CR(x)                                                                                         \
+    do {                                                                                              \
+        curandStatus_t e_ = (x);                                                                      \
+        if (e_ != CURAND_STATUS_SUCCESS) {                                                            \
+            ps_set_error("%s failed: curand status %d (%s:%d)", #x, (int)e_, __FILE__, __LINE__);     \
+            return PS_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+#define NEED(c)                                  \
+    do {                                         \
+        if (!(c)) {                              \
+            ps_set_error("null context");        \
+            return PS_ERR_INVALID;               \
+        }                                        \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+extern "C" const char *ps_last_error(void) { return g_err; }
+extern "C" const char *ps_version(void) { return "particlesolver_b200 0.1 (sm_100a)"; }
+
+extern "C" void ps_default_params(PsParams *p) {
+    if (!p) return;
+    memset(p, 0, sizeof *p);
+    p->gravity[0] = 0.f; p->gravity[1] = -9.8f; p->gravity[2] = 0.f;  // particlesystem.cpp:65
+    p->global_damping = 1.0f;
+    p->particle_radius = 0.25f;                                        // particleapp.cpp:24
+    p->grid_size[0] = p->grid_size[1] = p->grid_size[2] = 64;          // particleapp.cpp:25
+    p->cell_size[0] = p->cell_size[1] = p->cell_size[2] = 0.5f;        // 2 * radius, particlesystem.cpp:62
+    p->min_bounds[0] = -50; p->min_bounds[1] = 0; p->min_bounds[2] = -50;  // particleapp.cpp:38
+    p->max_bounds[0] = 50; p->max_bounds[1] = 200; p->max_bounds[2] = 50;
+    p->solver_iterations = 5;
+    p->omega = 1.0f;
+    p->flags = PS_FLAG_NONE;
+}
+
+static bool is_pow2(u32 v) { return v && !(v & (v - 1)); }
+
+static int validate_params(const PsParams *p) {
+    for (int c = 0; c < 3; c++) {
+        if (!is_pow2(p->grid_size[c])) { ps_set_error("grid_size[%d]=%u is not a power of two (the hash wraps with '&')", c, p->grid_size[c]); return PS_ERR_INVALID; }
+        if (!(p->cell_size[c] > 0.f)) { ps_set_error("cell_size[%d] must be positive", c); return PS_ERR_INVALID; }
+        if (p->grid_size[c] >= (1u << 24)) { ps_set_error("grid_size[%d] must stay below 2^24 (reference hash uses __umul24)", c); return PS_ERR_INVALID; }
+    }
+    uint64_t cells = (uint64_t)p->grid_size[0] * p->grid_size[1] * p->grid_size[2];
+    if (cells > (1ull << 31)) { ps_set_error("grid has %llu cells; the 32-bit cell key allows 2^31", (unsigned long long)cells); return PS_ERR_INVALID; }
+    if ((uint64_t)p->grid_size[2] * p->grid_size[1] >= (1ull << 24) && p->grid_size[0] > 1) {
+        // (z&mask)*gy must fit the 24-bit multiplier of the reference's __umul24 to stay bit-identical
+        ps_set_error("grid_size y*z must stay below 2^24 for a hash identical to the reference's __umul24 form");
+        return PS_ERR_INVALID;
+    }
+    int rad = (int)ceilf(PS_H / p->cell_size[0]);
+    if (rad > PS_MAX_RAD) { ps_set_error("cell_size %.4g gives a fluid stencil radius %d > %d", p->cell_size[0], rad, PS_MAX_RAD); return PS_ERR_INVALID; }
+    for (int c = 0; c < 3; c++)
+        if (p->grid_size[c] < (u32)(2 * rad + 2)) { ps_set_error("grid_size[%d]=%u is smaller than the fluid stencil (%d cells)", c, p->grid_size[c], 2 * rad + 2); return PS_ERR_INVALID; }
+    if (p->solver_iterations > 64) { ps_set_error("solver_iterations > 64"); return PS_ERR_INVALID; }
+    return PS_OK;
+}
+
+void ps_ctx_refresh_descs(PsCtx *c) {
+    const PsParams &p = c->params;
+    GridDesc &g = c->grid;
+    g.ox = p.world_origin[0]; g.oy = p.world_origin[1]; g.oz = p.world_origin[2];
+    g.cx = p.cell_size[0]; g.cy = p.cell_size[1]; g.cz = p.cell_size[2];
+    g.gx = p.grid_size[0]; g.gy = p.grid_size[1]; g.gz = p.grid_size[2];
+    g.mx = g.gx - 1; g.my = g.gy - 1; g.mz = g.gz - 1;
+    g.num_cells = g.gx * g.gy * g.gz;
+    c->num_cells = g.num_cells;
+    c->sort_passes = ps_sort_passes(g.num_cells);
+    c->world.radius = p.particle_radius;
+    c->world.min_x = p.min_bounds[0]; c->world.min_y = p.min_bounds[1]; c->world.min_z = p.min_bounds[2];
+    c->world.max_x = p.max_bounds[0]; c->world.max_y = p.max_bounds[1]; c->world.max_z = p.max_bounds[2];
+    // Row stencil of the fluid kernels.  rad follows the reference (integration_kernel.cuh:546).  A cell at offset
+    // d along an axis is at least (|d|-1)*cell away, so a (dy,dz) row with ay^2+az^2 > H^2 holds no neighbour
+    // and within a kept row only |dx| <= 1 + sqrt(H^2-ay^2-az^2)/cell can.  Margins keep borderline cells.
+    StencilDesc &st = c->stencil;
+    memset(&st, 0, sizeof st);
+    st.rad = (int)ceilf(PS_H / g.cx);
+    const int w = 2 * st.rad + 1;
+    for (int dz = -st.rad; dz <= st.rad; dz++)
+        for (int dy = -st.rad; dy <= st.rad; dy++) {
+            double ay = std::max(abs(dy) - 1, 0) * (double)g.cy, az = std::max(abs(dz) - 1, 0) * (double)g.cz;
+            double rem = (double)PS_H2 * (1.0 + 1e-4) - ay * ay - az * az;
+            int xr = -1;
+            if (rem >= 0.0) xr = std::min(st.rad, 1 + (int)floor(sqrt(rem) / g.cx + 1e-4));
+            st.xr[(dz + st.rad) * w + (dy + st.rad)] = (signed char)xr;
+        }
+}
+
+// ------------------------------------------------------------------ memory ------------------------------------------------------------------
+template <class T>
+static int grow(T **p, uint64_t old_n, uint64_t new_n, cudaStream_t s, bool zero_new) {
+    T *np = nullptr;
+    CU(cudaMalloc((void **)&np, std::max<uint64_t>(new_n, 1) * sizeof(T)));
+    if (*p && old_n) CU(cudaMemcpyAsync(np, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (zero_new && new_n > old_n) CU(cudaMemsetAsync(np + old_n, 0, (new_n - old_n) * sizeof(T), s));
+    if (*p) { CU(cudaStreamSynchronize(s)); CU(cudaFree(*p)); }
+    *p = np;
+    return PS_OK;
+}
+
+int ps_ctx_ensure_capacity(PsCtx *c, uint64_t want) {
+    if (want <= c->capacity) return PS_OK;
+    uint64_t cap = std::max<uint64_t>(want, c->capacity ? c->capacity * 2 : 1024);
+    if (c->limit && cap > c->limit) cap = std::max<uint64_t>(want, c->limit);
+    cap = (cap + 3) & ~3ull;
+    const uint64_t o = c->capacity;
+    cudaStream_t s = c->stream;
+    int r;
+#define G(arr, zero) if ((r = grow(&c->arr, o, cap, s, zero)) != PS_OK) return r;
+    G(pos, true) G(vel, true) G(prev, true) G(spos, true)
+    G(w, true) G(ros, true) G(sw, true) G(lambda, true)   // lambda zero-initialised like the reference's resize (integration.cu:68)
+    G(phase, true) G(sphase, true)
+    G(hash, true) G(index, true) G(hash_tmp, true) G(index_tmp, true) G(num_neighbors, true) G(occ, true)
+#undef G
+    c->capacity = cap;
+    // sort look-back status words for the largest n this capacity allows
+    size_t need = ps_sort_status_elems((u32)cap, 4);
+    if (need > c->sort_status_elems) {
+        if (c->sort_status) CU(cudaFree(c->sort_status));
+        CU(cudaMalloc((void **)&c->sort_status, need * sizeof(u32)));
+        c->sort_status_elems = need;
+    }
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    return PS_OK;
+}
+
+int ps_ctx_ensure_cells(PsCtx *c) {
+    uint64_t cells = c->num_cells;
+    if (cells <= c->cell_capacity && c->cell_start) return PS_OK;
+    if (c->cell_start) { CU(cudaFree(c->cell_start)); CU(cudaFree(c->cell_end)); CU(cudaFree(c->cell_begin)); CU(cudaFree(c->cell_block_min)); }
+    CU(cudaMalloc((void **)&c->cell_start, cells * sizeof(u32)));
+    CU(cudaMalloc((void **)&c->cell_end, cells * sizeof(u32)));
+    CU(cudaMalloc((void **)&c->cell_begin, (cells + 8) * sizeof(u32)));
+    CU(cudaMalloc((void **)&c->cell_block_min, ps_cell_begin_scratch_elems((u32)cells) * sizeof(u32)));
+    CU(cudaMemsetAsync(c->cell_start, 0xff, cells * sizeof(u32), c->stream));
+    CU(cudaMemsetAsync(c->cell_end, 0, cells * sizeof(u32), c->stream));
+    c->cell_capacity = cells;
+    return PS_OK;
+}
+
+SortScratch ps_ctx_sort_scratch(PsCtx *c, u32) {
+    SortScratch sc;
+    sc.hist = c->sort_hist;
+    sc.status = c->sort_status;
+    sc.ticket = c->sort_ticket;
+    return sc;
+}
+
+// ------------------------------------------------------------------ lifetime ------------------------------------------------------------------
+extern "C" int ps_create(int device, const PsParams *params, uint64_t max_particles, PsCtx **out) {
+    return ps_create_internal(device, params, max_particles, false, out);
+}
+
+// legacy_default_stream: the reference-ABI shim issues everything on stream 0 so that the caller's own blocking
+// cudaMemcpy calls keep the ordering they have with the reference's default-stream wrappers.
+int ps_create_internal(int device, const PsParams *params, uint64_t max_particles, bool legacy_default_stream, PsCtx **out) {
+    if (!params || !out) { ps_set_error("ps_create: null argument"); return PS_ERR_INVALID; }
+    *out = nullptr;
+    int r = validate_params(params);
+    if (r != PS_OK) return r;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { ps_set_error("ps_create: device %d of %d", device, ndev); return PS_ERR_INVALID; }
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { ps_set_error("ps_create: device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor); return PS_ERR_CUDA; }
+    if (max_particles >= (1ull << 31)) { ps_set_error("ps_create: max_particles must be < 2^31 per context"); return PS_ERR_INVALID; }
+    const uint64_t initial = max_particles ? max_particles : 1024;  // 0 = unlimited, grows on demand (reference-ABI shim)
+    DeviceGuard dg(device);
+    PsCtx *c = new PsCtx();
+    c->device = device;
+    c->params = *params;
+    c->limit = max_particles;
+    ps_ctx_refresh_descs(c);
+    auto fail = [&](int code) { ps_destroy(c); return code; };
+    c->own_stream = !legacy_default_stream;
+    if (c->own_stream && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { ps_set_error("cudaStreamCreate failed"); return fail(PS_ERR_CUDA); }
+    if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) { ps_set_error("cudaEventCreate failed"); return fail(PS_ERR_CUDA); }
+    if (cudaMalloc((void **)&c->sort_hist, 4 * 256 * sizeof(u32)) != cudaSuccess || cudaMalloc((void **)&c->sort_ticket, 4 * sizeof(u32)) != cudaSuccess) {
+        ps_set_error("cudaMalloc failed"); return fail(PS_ERR_CUDA);
+    }
+    c->rands_iters = 64;
+    if (cudaMalloc((void **)&c->rands, c->rands_iters * 6 * sizeof(float)) != cudaSuccess) { ps_set_error("cudaMalloc failed"); return fail(PS_ERR_CUDA); }
+    cudaMemsetAsync(c->rands, 0, c->rands_iters * 6 * sizeof(float), c->stream);
+    // same generator the reference creates in initIntegration (integration.cu:46-47): XORWOW, seed 1234
+    if (curandCreateGenerator(&c->gen, CURAND_RNG_PSEUDO_DEFAULT) != CURAND_STATUS_SUCCESS ||
+        curandSetPseudoRandomGeneratorSeed(c->gen, 1234ULL) != CURAND_STATUS_SUCCESS || curandSetStream(c->gen, c->stream) != CURAND_STATUS_SUCCESS) {
+        ps_set_error("curand generator setup failed"); return fail(PS_ERR_CUDA);
+    }
+    if ((r = ps_ctx_ensure_cells(c)) != PS_OK) return fail(r);
+    if ((r = ps_ctx_ensure_capacity(c, initial)) != PS_OK) return fail(r);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { ps_set_error("stream sync failed"); return fail(PS_ERR_CUDA); }
+    *out = c;
+    return PS_OK;
+}
+
+extern "C" int ps_destroy(PsCtx *c) {
+    if (!c) return PS_OK;
+    DeviceGuard dg(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->gen) curandDestroyGenerator(c->gen);
+    void *ptrs[] = {c->pos, c->vel, c->prev, c->spos, c->w, c->ros, c->sw, c->lambda, c->phase, c->sphase, c->hash, c->index, c->hash_tmp,
+                    c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->cell_block_min, c->sort_hist,
+                    c->sort_status, c->sort_ticket, c->rands, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
+                    c->d_point_xyz, c->dist_scratch};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return PS_OK;
+}
+
+extern "C" int ps_set_params(PsCtx *c, const PsParams *p) {
+    NEED(c);
+    if (!p) { ps_set_error("ps_set_params: null params"); return PS_ERR_INVALID; }
+    int r = validate_params(p);
+    if (r != PS_OK) return r;
+    DeviceGuard dg(c->device);
+    c->params = *p;
+    ps_ctx_refresh_descs(c);
+    if ((r = ps_ctx_ensure_cells(c)) != PS_OK) return r;
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    c->grid_valid = false;
+    return PS_OK;
+}
+extern "C" int ps_get_params(PsCtx *c, PsParams *out) { NEED(c); if (!out) return PS_ERR_INVALID; *out = c->params; return PS_OK; }
+extern "C" uint64_t ps_num_particles(PsCtx *c) { return c ? c->n : 0; }
+extern "C" uint64_t ps_num_owned(PsCtx *c) { return c ? c->n - c->n_ghost : 0; }
+extern "C" uint64_t ps_num_cells(PsCtx *c) { return c ? c->num_cells : 0; }
+extern "C" uint32_t ps_launches_per_step(PsCtx *c) { return c ? c->launches_per_step : 0; }
+extern "C" void *ps_stream(PsCtx *c) { return c ? (void *)c->stream : nullptr; }
+
+// ------------------------------------------------------------------ scene building ------------------------------------------------------------------
+extern "C" int ps_append_particles(PsCtx *c, const float *pos4, const float *vel4, const float *inv_mass, const float *rest_density,
+                                   const int32_t *phase, uint64_t n) {
+    NEED(c);
+    if (n == 0) return PS_OK;
+    if (!pos4 || !vel4 || !inv_mass || !rest_density || !phase) { ps_set_error("ps_append_particles: null array"); return PS_ERR_INVALID; }
+    if (c->n_ghost) { ps_set_error("ps_append_particles: drop ghosts first (ps_set_ghost_count(ctx,0))"); return PS_ERR_STATE; }
+    if (c->limit && (uint64_t)c->n + n > c->limit) {
+        ps_set_error("ps_append_particles: %llu + %llu exceeds max_particles %llu", (unsigned long long)c->n, (unsigned long long)n, (unsigned long long)c->limit);
+        return PS_ERR_CAPACITY;
+    }
+    DeviceGuard dg(c->device);
+    int r = ps_ctx_ensure_capacity(c, (uint64_t)c->n + n);
+    if (r != PS_OK) return r;
+    cudaStream_t s = c->stream;
+    CU(cudaMemcpyAsync(c->pos + c->n, pos4, n * 16, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->vel + c->n, vel4, n * 16, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->w + c->n, inv_mass, n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->ros + c->n, rest_density, n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(c->phase + c->n, phase, n * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));  // host buffers may be stack arrays of the caller (the reference's builders are)
+    c->n += (u32)n;
+    c->h_occ.resize(c->n, 0u);
+    c->constraints_dirty = true;
+    c->grid_valid = false;
+    return PS_OK;
+}
+
+extern "C" int ps_add_distance_constraints(PsCtx *c, const uint32_t *idx, const float *rest, uint64_t m) {
+    NEED(c);
+    if (m == 0) return PS_OK;
+    if (!idx || !rest) { ps_set_error("ps_add_distance_constraints: null array"); return PS_ERR_INVALID; }
+    for (uint64_t k = 0; k < 2 * m; k++)
+        if (idx[k] >= c->n) { ps_set_error("distance constraint endpoint %u >= %u particles", idx[k], c->n); return PS_ERR_INVALID; }
+    c->h_dist_idx.insert(c->h_dist_idx.end(), idx, idx + 2 * m);
+    c->h_dist_rest.insert(c->h_dist_rest.end(), rest, rest + m);
+    for (uint64_t k = 0; k < 2 * m; k++) c->h_occ[idx[k]]++;  // updateOccurences, solver.cu:72-106,149
+    c->constraints_dirty = true;
+    return PS_OK;
+}
+
+extern "C" int ps_add_point_constraints(PsCtx *c, const uint32_t *idx, const float *xyz, uint64_t p) {
+    NEED(c);
+    if (p == 0) return PS_OK;
+    if (!idx || !xyz) { ps_set_error("ps_add_point_constraints: null array"); return PS_ERR_INVALID; }
+    for (uint64_t k = 0; k < p; k++)
+        if (idx[k] >= c->n) { ps_set_error("point constraint index %u >= %u particles", idx[k], c->n); return PS_ERR_INVALID; }
+    c->h_point_idx.insert(c->h_point_idx.end(), idx, idx + p);
+    c->h_point_xyz.insert(c->h_point_xyz.end(), xyz, xyz + 3 * p);
+    for (uint64_t k = 0; k < p; k++) c->h_occ[idx[k]]++;  // solver.cu:122
+    c->constraints_dirty = true;
+    return PS_OK;
+}
+
+extern "C" uint64_t ps_num_distance_constraints(PsCtx *c) { return c ? c->h_dist_rest.size() : 0; }
+extern "C" uint64_t ps_num_point_constraints(PsCtx *c) { return c ? c->h_point_idx.size() : 0; }
+extern "C" int ps_copy_distance_constraints(PsCtx *c, uint32_t *idx, float *rest) {
+    NEED(c);
+    if (idx) memcpy(idx, c->h_dist_idx.data(), c->h_dist_idx.size() * sizeof(u32));
+    if (rest) memcpy(rest, c->h_dist_rest.data(), c->h_dist_rest.size() * sizeof(float));
+    return PS_OK;
+}
+extern "C" int ps_copy_point_constraints(PsCtx *c, uint32_t *idx, float *xyz) {
+    NEED(c);
+    if (idx) memcpy(idx, c->h_point_idx.data(), c->h_point_idx.size() * sizeof(u32));
+    if (xyz) memcpy(xyz, c->h_point_xyz.data(), c->h_point_xyz.size() * sizeof(float));
+    return PS_OK;
+}
+
+template <class T>
+static int upload_vec(T **d, const std::vector<T> &h, cudaStream_t s) {
+    if (*d) { CU(cudaFree(*d)); *d = nullptr; }
+    if (h.empty()) return PS_OK;
+    CU(cudaMalloc((void **)d, h.size() * sizeof(T)));
+    CU(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return PS_OK;
+}
+
+// Build the gather CSR of the distance constraints (see K9 note in ps_stream_kernels.cu) and upload pins / counts.
+int ps_ctx_sync_constraints(PsCtx *c) {
+    if (!c->constraints_dirty) return PS_OK;
+    cudaStream_t s = c->stream;
+    CU(cudaStreamSynchronize(s));
+    const size_t m = c->h_dist_rest.size();
+    std::vector<u32> deg(c->n, 0u);
+    for (size_t k = 0; k < 2 * m; k++) deg[c->h_dist_idx[k]]++;
+    std::vector<u32> particle, off, other;
+    std::vector<float> rest;
+    std::vector<u32> slot(c->n, 0xffffffffu);
+    for (u32 i = 0; i < c->n; i++)
+        if (deg[i]) { slot[i] = (u32)particle.size(); particle.push_back(i); }
+    const u32 K = (u32)particle.size();
+    c->dist_prefix_ok = true;
+    for (u32 k = 0; k < K; k++) if (particle[k] != k) { c->dist_prefix_ok = false; break; }
+    off.assign(K + 1, 0u);
+    for (u32 k = 0; k < K; k++) off[k + 1] = off[k] + deg[particle[k]];
+    other.assign(2 * m, 0u);
+    rest.assign(2 * m, 0.f);
+    std::vector<u32> fill(off.begin(), off.end() - (K ? 1 : 0));
+    if (K == 0) fill.clear();
+    // order inside a particle's list == order of its entries after the reference's stable sort_by_key of
+    // [all first endpoints..., all second endpoints...] (solver.cu:203-219): "a" roles first, then "b" roles
+    for (size_t k = 0; k < m; k++) { u32 a = c->h_dist_idx[2 * k], b = c->h_dist_idx[2 * k + 1]; u32 t = fill[slot[a]]++; other[t] = b; rest[t] = c->h_dist_rest[k]; }
+    for (size_t k = 0; k < m; k++) { u32 a = c->h_dist_idx[2 * k], b = c->h_dist_idx[2 * k + 1]; u32 t = fill[slot[b]]++; other[t] = a | 0x80000000u; rest[t] = c->h_dist_rest[k]; }
+    int r;
+    if ((r = upload_vec(&c->csr_particle, particle, s)) != PS_OK) return r;
+    if ((r = upload_vec(&c->csr_off, off, s)) != PS_OK) return r;
+    if ((r = upload_vec(&c->csr_other, other, s)) != PS_OK) return r;
+    if ((r = upload_vec(&c->csr_rest, rest, s)) != PS_OK) return r;
+    if ((r = upload_vec(&c->d_point_idx, c->h_point_idx, s)) != PS_OK) return r;
+    if ((r = upload_vec(&c->d_point_xyz, c->h_point_xyz, s)) != PS_OK) return r;
+    if (c->dist_scratch) { CU(cudaFree(c->dist_scratch)); c->dist_scratch = nullptr; }
+    if (K) CU(cudaMalloc((void **)&c->dist_scratch, (size_t)K * sizeof(float4)));
+    if (c->n) CU(cudaMemcpyAsync(c->occ, c->h_occ.data(), (size_t)c->n * sizeof(u32), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    c->num_constrained = K;
+    c->num_points = (u32)c->h_point_idx.size();
+    c->constraints_dirty = false;
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    return PS_OK;
+}
+
+// ------------------------------------------------------------------ stages ------------------------------------------------------------------
+// K2 -> K3 -> K4 (+ dense table).  When the pass count is odd the unsorted keys are written straight into the
+// scratch pair so that the last pass lands in (hash,index); values are implicit (identity) in the first pass.
+u32 ps_issue_build_grid(PsCtx *c, const float4 *pos) {
+    cudaStream_t s = c->stream;
+    const u32 n = c->n;
+    const bool odd = (c->sort_passes & 1) != 0;
+    u32 *kA = odd ? c->hash_tmp : c->hash, *vA = odd ? c->index_tmp : c->index;
+    u32 *kB = odd ? c->hash : c->hash_tmp, *vB = odd ? c->index : c->index_tmp;
+    ps_launch_calc_hash(kA, nullptr, pos, n, c->grid, s);
+    ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s);
+    ps_launch_reorder(c->cell_start, c->cell_end, c->spos, c->sw, c->sphase, c->hash, c->index, pos, c->w, c->phase, n, c->num_cells, s);
+    ps_launch_cell_begin(c->cell_begin, c->cell_start, c->cell_block_min, n, c->num_cells, s);
+    c->grid_valid = true;
+    // calc_hash 1 + sort (3 memsets + hist + passes) + reorder (memset + kernel) + cell_begin 3
+    return 1 + 4 + (u32)c->sort_passes + 2 + 3;
+}
+
+static int ready(PsCtx *c) {
+    NEED(c);
+    if (c->n == 0) return PS_OK;
+    return ps_ctx_sync_constraints(c);
+}
+static int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ps_set_error("%s: %s", what, cudaGetErrorString(e)); return PS_ERR_CUDA; }
+    return PS_OK;
+}
+
+extern "C" int ps_begin_step(PsCtx *c) {
+    NEED(c);
+    DeviceGuard dg(c->device);
+    const u32 iters = c->params.solver_iterations;
+    // one curandGenerateUniform(gen, rands, 6) per solver iteration, exactly like collideWorld (integration.cu:326)
+    for (u32 it = 0; it < iters; it++) CR(curandGenerateUniform(c->gen, c->rands + 6 * it, 6));
+    return PS_OK;
+}
+
+extern "C" int ps_predict(PsCtx *c, float dt) {
+    int r = ready(c); if (r != PS_OK) return r;
+    DeviceGuard dg(c->device);
+    dt = std::min(dt, .05f);
+    const PsParams &p = c->params;
+    ps_launch_predict(c->pos, c->vel, c->prev, c->n - c->n_ghost, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), c->stream);
+    return check_launch("ps_predict");
+}
+extern "C" int ps_build_grid(PsCtx *c) {
+    int r = ready(c); if (r != PS_OK) return r;
+    DeviceGuard dg(c->device);
+    if (c->n) ps_issue_build_grid(c, c->pos);
+    return check_launch("ps_build_grid");
+}
+extern "C" int ps_solve_contacts(PsCtx *c) {
+    int r = ready(c); if (r != PS_OK) return r;
+    if (c->n && !c->grid_valid) { ps_set_error("ps_solve_contacts: no grid (call ps_build_grid)"); return PS_ERR_STATE; }
+    DeviceGuard dg(c->device);
+    ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, c->n, c->n - c->n_ghost, c->grid,
+                      c->params.particle_radius, c->stream);
+    return check_launch("ps_solve_contacts");
+}
+extern "C" int ps_solve_fluid(PsCtx *c) {
+    int r = ready(c); if (r != PS_OK) return r;
+    if (c->n && !c->grid_valid) { ps_set_error("ps_solve_fluid: no grid (call ps_build_grid)"); return PS_ERR_STATE; }
+    DeviceGuard dg(c->device);
+    // lambda is needed for ghosts too (their owners are on another GPU): n_owned = n for K6
+    ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n, c->grid,
+                           c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->stream);
+    ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost, c->grid, c->stencil,
+                           c->params.omega, c->stream);
+    return check_launch("ps_solve_fluid");
+}
+extern "C" int ps_collide_world(PsCtx *c, uint32_t iteration) {
+    int r = ready(c); if (r != PS_OK) return r;
+    if (iteration >= c->rands_iters) { ps_set_error("ps_collide_world: iteration %u out of range", iteration); return PS_ERR_INVALID; }
+    DeviceGuard dg(c->device);
+    ps_launch_collide_world(c->pos, c->prev, c->phase, c->n - c->n_ghost, c->rands + 6 * iteration, c->world, c->stream);
+    return check_launch("ps_collide_world");
+}
+extern "C" int ps_solve_distance(PsCtx *c) {
+    int r = ready(c); if (r != PS_OK) return r;
+    DeviceGuard dg(c->device);
+    ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained,
+                       c->params.omega, c->stream);
+    return check_launch("ps_solve_distance");
+}
+extern "C" int ps_solve_point(PsCtx *c) {
+    int r = ready(c); if (r != PS_OK) return r;
+    DeviceGuard dg(c->device);
+    ps_launch_point(c->pos, c->d_point_idx, c->d_point_xyz, c->num_points, c->stream);
+    return check_launch("ps_solve_point");
+}
+extern "C" int ps_update_velocity(PsCtx *c, float dt) {
+    int r = ready(c); if (r != PS_OK) return r;
+    DeviceGuard dg(c->device);
+    dt = std::min(dt, .05f);
+    ps_launch_velocity(c->pos, c->prev, c->vel, c->n - c->n_ghost, dt, c->stream);
+    return check_launch("ps_update_velocity");
+}
+
+// issue the whole step on the context's stream (either eagerly or under stream capture); returns #launches
+static u32 issue_step(PsCtx *c, float dt) {
+    const PsParams &p = c->params;
+    cudaStream_t s = c->stream;
+    const u32 n = c->n, n_owned = c->n - c->n_ghost;
+    u32 launches = 0;
+    ps_launch_predict(c->pos, c->vel, c->prev, n_owned, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), s);
+    launches++;
+    for (u32 it = 0; it < p.solver_iterations; it++) {
+        launches += ps_issue_build_grid(c, c->pos);
+        ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n_owned, c->grid,
+                          p.particle_radius, s);
+        ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil,
+                               (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s);
+        ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned, c->grid, c->stencil, p.omega, s);
+        ps_launch_collide_world(c->pos, c->prev, c->phase, n_owned, c->rands + 6 * it, c->world, s);
+        launches += 4;
+        if (c->num_constrained) { ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained, p.omega, s); launches += 2; }
+        if (c->num_points) { ps_launch_point(c->pos, c->d_point_idx, c->d_point_xyz, c->num_points, s); launches++; }
+    }
+    ps_launch_velocity(c->pos, c->prev, c->vel, n_owned, dt, s);
+    launches++;
+    return launches;
+}
+
+extern "C" int ps_step(PsCtx *c, float dt) {
+    int r = ready(c); if (r != PS_OK) return r;
+    if (c->n == 0) return PS_OK;  // the reference returns early too (particlesystem.cpp:151-155)
+    if (c->n_ghost) { ps_set_error("ps_step: slab contexts with ghosts are stepped stage by stage (halo refresh between stages)"); return PS_ERR_STATE; }
+    DeviceGuard dg(c->device);
+    dt = std::min(dt, .05f);  // particlesystem.cpp:149
+    if ((r = ps_begin_step(c)) != PS_OK) return r;
+    static const bool no_graph = getenv("PS_NO_GRAPH") != nullptr;
+    cudaStream_t s = c->stream;
+    CU(cudaEventRecord(c->ev0, s));
+    if (no_graph) {
+        c->launches_per_step = issue_step(c, dt);
+    } else {
+        PsCtx::GraphKey key{c->n, c->n_ghost, (u32)c->h_dist_rest.size(), c->num_points, c->params.solver_iterations, c->params.flags, dt, c->params.omega};
+        if (!c->graph_exec || !(key == c->graph_key)) {
+            if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            u32 launches = issue_step(c, dt);
+            cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (e != cudaSuccess) { ps_set_error("stream capture of the step failed: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
+            e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { ps_set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); c->graph_exec = nullptr; return PS_ERR_CUDA; }
+            c->graph_key = key;
+            c->launches_per_step = launches;
+        }
+        CU(cudaGraphLaunch(c->graph_exec, s));
+    }
+    CU(cudaEventRecord(c->ev1, s));
+    return check_launch("ps_step");
+}
+
+extern "C" int ps_sync(PsCtx *c) {
+    NEED(c);
+    DeviceGuard dg(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    return PS_OK;
+}
+extern "C" int ps_last_step_ms(PsCtx *c, float *ms) {
+    NEED(c);
+    if (!ms) return PS_ERR_INVALID;
+    DeviceGuard dg(c->device);
+    CU(cudaEventSynchronize(c->ev1));
+    CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return PS_OK;
+}
+
+// ------------------------------------------------------------------ data access ------------------------------------------------------------------
+struct ArrInfo { void *ptr; size_t esz; uint64_t count; };
+static ArrInfo arr_info(PsCtx *c, int which) {
+    const uint64_t n = c->n, cells = c->num_cells;
+    switch (which) {
+        case PS_ARR_POS: return {c->pos, 4, 4 * n};
+        case PS_ARR_VEL: return {c->vel, 4, 4 * n};
+        case PS_ARR_PREV: return {c->prev, 4, 4 * n};
+        case PS_ARR_INV_MASS: return {c->w, 4, n};
+        case PS_ARR_PHASE: return {c->phase, 4, n};
+        case PS_ARR_REST_DENSITY: return {c->ros, 4, n};
+        case PS_ARR_HASH: return {c->hash, 4, n};
+        case PS_ARR_INDEX: return {c->index, 4, n};
+        case PS_ARR_CELL_START: return {c->cell_start, 4, cells};
+        case PS_ARR_CELL_END: return {c->cell_end, 4, cells};
+        case PS_ARR_SORTED_POS: return {c->spos, 4, 4 * n};
+        case PS_ARR_SORTED_INV_MASS: return {c->sw, 4, n};
+        case PS_ARR_SORTED_PHASE: return {c->sphase, 4, n};
+        case PS_ARR_LAMBDA: return {c->lambda, 4, n};
+        case PS_ARR_NUM_NEIGHBORS: return {c->num_neighbors, 4, n};
+        case PS_ARR_RANDS: return {c->rands, 4, (uint64_t)c->params.solver_iterations * 6};
+        case PS_ARR_OCCURRENCES: return {c->occ, 4, n};
+        case PS_ARR_CELL_BEGIN: return {c->cell_begin, 4, cells + 1};
+        default: return {nullptr, 0, 0};
+    }
+}
+static int copy_common(PsCtx *c, int which, void *host, uint64_t off, uint64_t cnt, bool to_host, bool sync) {
+    NEED(c);
+    ArrInfo a = arr_info(c, which);
+    if (!a.ptr && a.count == 0 && cnt == 0) return PS_OK;
+    if (!a.ptr) { ps_set_error("unknown array selector %d", which); return PS_ERR_INVALID; }
+    if (!host && cnt) { ps_set_error("null host pointer"); return PS_ERR_INVALID; }
+    if (off + cnt > a.count) { ps_set_error("range [%llu,%llu) exceeds array %d of %llu elements", (unsigned long long)off, (unsigned long long)(off + cnt), which, (unsigned long long)a.count); return PS_ERR_INVALID; }
+    if (cnt == 0) return PS_OK;
+    DeviceGuard dg(c->device);
+    if (which == PS_ARR_OCCURRENCES) { int r = ps_ctx_sync_constraints(c); if (r != PS_OK) return r; }
+    char *d = (char *)a.ptr + off * a.esz;
+    if (to_host) CU(cudaMemcpyAsync(host, d, cnt * a.esz, cudaMemcpyDeviceToHost, c->stream));
+    else CU(cudaMemcpyAsync(d, host, cnt * a.esz, cudaMemcpyHostToDevice, c->stream));
+    if (sync) CU(cudaStreamSynchronize(c->stream));
+    if (!to_host && (which == PS_ARR_POS || which == PS_ARR_INV_MASS || which == PS_ARR_PHASE)) c->grid_valid = false;
+    return PS_OK;
+}
+extern "C" int ps_download(PsCtx *c, int which, void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, host, off, cnt, true, true); }
+extern "C" int ps_upload(PsCtx *c, int which, const void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, (void *)host, off, cnt, false, true); }
+extern "C" int ps_download_async(PsCtx *c, int which, void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, host, off, cnt, true, false); }
+extern "C" int ps_upload_async(PsCtx *c, int which, const void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, (void *)host, off, cnt, false, false); }
+extern "C" void *ps_device_ptr(PsCtx *c, int which) { return c ? arr_info(c, which).ptr : nullptr; }
+
+// ------------------------------------------------------------------ slabs ------------------------------------------------------------------
+extern "C" int ps_set_ghost_count(PsCtx *c, uint64_t ghosts) {
+    NEED(c);
+    const uint64_t owned = c->n - c->n_ghost;
+    if (c->limit && owned + ghosts > c->limit) { ps_set_error("ps_set_ghost_count: %llu owned + %llu ghosts exceeds max_particles", (unsigned long long)owned, (unsigned long long)ghosts); return PS_ERR_CAPACITY; }
+    DeviceGuard dg(c->device);
+    int r = ps_ctx_ensure_capacity(c, owned + ghosts);
+    if (r != PS_OK) return r;
+    c->n = (u32)(owned + ghosts);
+    c->n_ghost = (u32)ghosts;
+    c->h_occ.resize(c->n, 0u);
+    c->grid_valid = false;
+    return PS_OK;
+}

@@ -1,0 +1,75 @@
+// particlesolver_b200/csrc/ps_context.h — internal definition of the opaque PsCtx (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <curand.h>
+#include <string>
+#include <vector>
+#include "../../include/psolver.h"
+#include "ps_common.cuh"
+
+struct PsCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    PsParams params{};
+    GridDesc grid{};
+    StencilDesc stencil{};
+    WorldDesc world{};
+    u32 num_cells = 0;
+    int sort_passes = 0;
+
+    uint64_t limit = 0;     // hard particle limit (ps_create's max_particles)
+    uint64_t capacity = 0;  // allocated slots
+    u32 n = 0;              // owned + ghosts
+    u32 n_ghost = 0;
+
+    // per-particle state (SoA).  pos may be caller-owned in the reference-ABI shim, hence the indirection.
+    float4 *pos = nullptr, *vel = nullptr, *prev = nullptr, *spos = nullptr;
+    float *w = nullptr, *ros = nullptr, *sw = nullptr, *lambda = nullptr;
+    int *phase = nullptr, *sphase = nullptr;
+    u32 *hash = nullptr, *index = nullptr, *hash_tmp = nullptr, *index_tmp = nullptr, *num_neighbors = nullptr, *occ = nullptr;
+    // per-cell state
+    u32 *cell_start = nullptr, *cell_end = nullptr, *cell_begin = nullptr, *cell_block_min = nullptr;
+    uint64_t cell_capacity = 0;
+    // sort scratch
+    u32 *sort_hist = nullptr, *sort_status = nullptr, *sort_ticket = nullptr;
+    size_t sort_status_elems = 0;
+    // wall jitter uniforms, [iterations][6]
+    float *rands = nullptr;
+    u32 rands_iters = 0;
+    curandGenerator_t gen = nullptr;
+
+    // constraints: host mirror + device arrays
+    std::vector<u32> h_dist_idx;    // 2 per constraint
+    std::vector<float> h_dist_rest;
+    std::vector<u32> h_point_idx;
+    std::vector<float> h_point_xyz;  // 3 per pin
+    std::vector<u32> h_occ;
+    bool constraints_dirty = false;
+    u32 num_constrained = 0, num_points = 0;
+    u32 *csr_particle = nullptr, *csr_off = nullptr, *csr_other = nullptr, *d_point_idx = nullptr;
+    float *csr_rest = nullptr, *d_point_xyz = nullptr;
+    float4 *dist_scratch = nullptr;
+    bool dist_prefix_ok = true;  // constrained particles are the index prefix [0,K) (see K9 note)
+
+    // CUDA graph of one whole step
+    cudaGraphExec_t graph_exec = nullptr;
+    struct GraphKey { u32 n, n_ghost, m, p, iters, flags; float dt, omega; bool operator==(const GraphKey &o) const {
+        return n == o.n && n_ghost == o.n_ghost && m == o.m && p == o.p && iters == o.iters && flags == o.flags && dt == o.dt && omega == o.omega; } } graph_key{};
+    u32 launches_per_step = 0;
+    u32 launch_counter = 0;  // counts launches while a step is being issued
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool grid_valid = false;
+};
+
+// internal helpers shared with the reference-ABI shim
+int ps_create_internal(int device, const PsParams *params, uint64_t max_particles, bool legacy_default_stream, PsCtx **out);
+int ps_ctx_ensure_capacity(PsCtx *c, uint64_t want);
+int ps_ctx_ensure_cells(PsCtx *c);
+int ps_ctx_sync_constraints(PsCtx *c);
+void ps_ctx_refresh_descs(PsCtx *c);
+void ps_set_error(const char *fmt, ...);
+SortScratch ps_ctx_sort_scratch(PsCtx *c, u32 n);
+
+// stage issue functions on explicit arrays (used by both ABIs); each returns the number of launches issued
+u32 ps_issue_build_grid(PsCtx *c, const float4 *pos);
