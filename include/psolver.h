@@ -113,6 +113,17 @@ int ps_sync(PsCtx *ctx);
 /* milliseconds of device time of the last ps_step (CUDA events on the context's stream); syncs. */
 int ps_last_step_ms(PsCtx *ctx, float *ms);
 
+/* Device-time a region of work on the context's stream with CUDA events (stop synchronises). */
+int ps_timer_start(PsCtx *ctx);
+int ps_timer_stop(PsCtx *ctx, float *ms);
+
+/* Instrumented step for roofline reporting: the same launches as ps_step, issued eagerly with a CUDA event after
+ * every stage.  stage_ms[PS_NUM_STAGES] receives the device time of each stage summed over the step's solver
+ * iterations, stage_launches[PS_NUM_STAGES] (may be NULL) the number of kernel launches behind it. */
+#define PS_NUM_STAGES 12
+int ps_step_profiled(PsCtx *ctx, float dt, float *stage_ms, uint32_t *stage_launches);
+const char *ps_stage_name(int stage); /* "predict","hash","sort","reorder","cell_table","contacts","lambda","delta_p","world","distance","point","velocity" */
+
 /* Per-stage entry points, in the order update() calls them; each is asynchronous on the context's stream. */
 int ps_begin_step(PsCtx *ctx);               /* draws this step's wall-jitter uniforms (cuRAND XORWOW, seed 1234) */
 int ps_predict(PsCtx *ctx, float dt);        /* K1  integrateSystem               integration.cu:122-135 */

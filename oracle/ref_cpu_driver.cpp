@@ -1,0 +1,90 @@
+// Headless driver around the reference's UNMODIFIED 2-D CPU solver (cpu/src/simulation.cpp + constraint/*.cpp,
+// compiled from /root/reference by oracle/Makefile into oracle/_ref/ref_cpu).  TEST INFRASTRUCTURE ONLY.
+//   ref_cpu --scene 6 --ticks N [--dump dir] [--json]
+// Builds a scene exactly as the Qt app does (Simulation() runs init(WRECKING_BALL) first, then the key handler
+// calls init(type): cpu/src/simulation.cpp:11-16, cpu/src/view.cpp:121-179), runs tick(.01) N times
+// (cpu/src/view.cpp:185-202) and reports kinetic energy / timing; --dump writes particle state after chosen ticks.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+// every system / third-party header first, so that the access hack below only touches the reference's classes
+#include <algorithm>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <QList>
+#include <QHash>
+#include <QSet>
+#include "includes.h"
+#define private public
+#include "simulation.h"
+#undef private
+
+static SimulationType scene_of(const std::string &k) {
+    // key bindings of cpu/src/view.cpp:121-179
+    if (k == "1") return FRICTION_TEST;
+    if (k == "2") return GRANULAR_TEST;
+    if (k == "3") return STACKS_TEST;
+    if (k == "4") return WALL_TEST;
+    if (k == "5") return PENDULUM_TEST;
+    if (k == "6") return FLUID_TEST;
+    if (k == "7") return FLUID_SOLID_TEST;
+    if (k == "8") return ROPE_TEST;
+    if (k == "9") return GAS_ROPE_TEST;
+    if (k == "0") return WATER_BALLOON_TEST;
+    return FLUID_TEST;
+}
+
+static void dump_state(Simulation &sim, const std::string &dir, int tick) {
+    char name[256];
+    snprintf(name, sizeof name, "%s/tick%05d.bin", dir.c_str(), tick);
+    FILE *f = fopen(name, "wb");
+    if (!f) { perror("fopen"); exit(1); }
+    int n = sim.m_particles.size();
+    fwrite(&n, sizeof n, 1, f);
+    for (int i = 0; i < n; i++) {
+        Particle *p = sim.m_particles[i];
+        double rec[8] = {p->p.x, p->p.y, p->v.x, p->v.y, p->imass, (double)p->ph, (double)p->bod, 0.0};
+        fwrite(rec, sizeof rec, 1, f);
+    }
+    fclose(f);
+}
+
+int main(int argc, char **argv) {
+    std::string scene = "6", dump;
+    int ticks = 100, dump_every = 0;
+    bool json = false;
+    for (int i = 1; i < argc; i++) {
+        std::string k = argv[i];
+        if (k == "--scene" && i + 1 < argc) scene = argv[++i];
+        else if (k == "--ticks" && i + 1 < argc) ticks = atoi(argv[++i]);
+        else if (k == "--dump" && i + 1 < argc) dump = argv[++i];
+        else if (k == "--dump-every" && i + 1 < argc) dump_every = atoi(argv[++i]);
+        else if (k == "--json") json = true;
+    }
+    Simulation sim;  // constructor builds WRECKING_BALL first, consuming rand() like the app does
+    sim.init(scene_of(scene));
+    int n = sim.getNumParticles();
+    if (!dump.empty()) { std::string c = "mkdir -p '" + dump + "'"; if (system(c.c_str())) return 1; dump_state(sim, dump, 0); }
+    std::vector<double> ke;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int t = 1; t <= ticks; t++) {
+        sim.tick(.01);  // cpu/src/view.cpp:197
+        if (t == 1 || t == 100 || t == 1000 || t == ticks) ke.push_back(sim.getKineticEnergy());
+        if (!dump.empty() && (t == 1 || (dump_every > 0 && t % dump_every == 0) || t == ticks)) dump_state(sim, dump, t);
+    }
+    double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (json) {
+        printf("{\"impl\": \"reference_cpu_unmodified\", \"scene\": \"%s\", \"n\": %d, \"ticks\": %d, \"ms_per_tick\": %.4f, "
+               "\"particle_steps_per_s\": %.1f, \"solver_iterations\": %d, \"cores\": 1, \"ke_last\": %.17g}\n",
+               scene.c_str(), n, ticks, 1e3 * sec / ticks, n * (double)ticks / sec, SOLVER_ITERATIONS, ke.empty() ? 0.0 : ke.back());
+    } else {
+        printf("scene %s: %d particles, %d ticks in %.3f s\n", scene.c_str(), n, ticks, sec);
+        for (double k : ke) printf("KE %.17g\n", k);
+    }
+    return 0;
+}

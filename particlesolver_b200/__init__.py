@@ -22,6 +22,7 @@ NO_COLLIDE, FLUID, GAS, CLOTH, SOLID, RIGID = -1, 0, 1, 2, 3, 4
 
 PS_OK, PS_ERR_INVALID, PS_ERR_CUDA, PS_ERR_CAPACITY, PS_ERR_STATE = 0, 1, 2, 3, 4
 FLAG_ZERO_NONFLUID_LAMBDA = 1
+NUM_STAGES = 12
 
 (ARR_POS, ARR_VEL, ARR_PREV, ARR_INV_MASS, ARR_PHASE, ARR_REST_DENSITY, ARR_HASH, ARR_INDEX, ARR_CELL_START, ARR_CELL_END,
  ARR_SORTED_POS, ARR_SORTED_INV_MASS, ARR_SORTED_PHASE, ARR_LAMBDA, ARR_NUM_NEIGHBORS, ARR_RANDS, ARR_OCCURRENCES,
@@ -82,6 +83,11 @@ def lib():
         L.ps_num_point_constraints.restype = u64
         L.ps_copy_distance_constraints.argtypes = [vp, vp, vp]
         L.ps_copy_point_constraints.argtypes = [vp, vp, vp]
+        L.ps_timer_start.argtypes = [vp]
+        L.ps_timer_stop.argtypes = [vp, C.POINTER(f32)]
+        L.ps_step_profiled.argtypes = [vp, f32, vp, vp]
+        L.ps_stage_name.argtypes = [i32]
+        L.ps_stage_name.restype = C.c_char_p
         L.ps_step.argtypes = [vp, f32]
         L.ps_sync.argtypes = [vp]
         L.ps_last_step_ms.argtypes = [vp, C.POINTER(f32)]
@@ -228,6 +234,28 @@ class Solver:
         ms = C.c_float()
         _check(lib().ps_last_step_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def timer_start(self):
+        _check(lib().ps_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        _check(lib().ps_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def step_profiled(self, dt):
+        """One eager step with an event after every stage -> ({stage: ms}, {stage: kernel launches})."""
+        ms = np.zeros(NUM_STAGES, np.float32)
+        ln = np.zeros(NUM_STAGES, np.uint32)
+        _check(lib().ps_step_profiled(self._h, dt, _ptr(ms), _ptr(ln)))
+        names = [lib().ps_stage_name(k).decode() for k in range(NUM_STAGES)]
+        return dict(zip(names, ms.tolist())), dict(zip(names, ln.tolist()))
+
+    def download_async(self, which, host_ptr, count_elems, offset_elems=0):
+        _check(lib().ps_download_async(self._h, which, host_ptr, offset_elems, count_elems))
+
+    def upload_async(self, which, host_ptr, count_elems, offset_elems=0):
+        _check(lib().ps_upload_async(self._h, which, host_ptr, offset_elems, count_elems))
 
     @property
     def launches_per_step(self):

@@ -238,6 +238,7 @@ extern "C" int ps_destroy(PsCtx *c) {
                     c->sort_status, c->sort_ticket, c->rands, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
                     c->d_point_xyz, c->dist_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
@@ -401,8 +402,8 @@ u32 ps_issue_build_grid(PsCtx *c, const float4 *pos) {
     ps_launch_reorder(c->cell_start, c->cell_end, c->spos, c->sw, c->sphase, c->hash, c->index, pos, c->w, c->phase, n, c->num_cells, s);
     ps_launch_cell_begin(c->cell_begin, c->cell_start, c->cell_block_min, n, c->num_cells, s);
     c->grid_valid = true;
-    // calc_hash 1 + sort (3 memsets + hist + passes) + reorder (memset + kernel) + cell_begin 3
-    return 1 + 4 + (u32)c->sort_passes + 2 + 3;
+    // kernels only (the 4 memset nodes are not counted): calc_hash 1 + hist 1 + passes + reorder 1 + cell_begin 3
+    return 1 + 1 + (u32)c->sort_passes + 1 + 3;
 }
 
 static int ready(PsCtx *c) {
@@ -542,6 +543,77 @@ extern "C" int ps_step(PsCtx *c, float dt) {
     }
     CU(cudaEventRecord(c->ev1, s));
     return check_launch("ps_step");
+}
+
+// ---- instrumented step: same launches as ps_step, issued eagerly with a CUDA event after every stage ----
+static const char *const kStageNames[PS_NUM_STAGES] = {"predict", "hash", "sort", "reorder", "cell_table", "contacts", "lambda", "delta_p",
+                                                       "world", "distance", "point", "velocity"};
+extern "C" const char *ps_stage_name(int stage) { return (stage >= 0 && stage < PS_NUM_STAGES) ? kStageNames[stage] : ""; }
+
+extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *stage_launches) {
+    int r = ready(c); if (r != PS_OK) return r;
+    if (!stage_ms) { ps_set_error("ps_step_profiled: null output"); return PS_ERR_INVALID; }
+    for (int k = 0; k < PS_NUM_STAGES; k++) { stage_ms[k] = 0.f; if (stage_launches) stage_launches[k] = 0; }
+    if (c->n == 0) return PS_OK;
+    if (c->n_ghost) { ps_set_error("ps_step_profiled: not for slab contexts"); return PS_ERR_STATE; }
+    DeviceGuard dg(c->device);
+    dt = std::min(dt, .05f);
+    if ((r = ps_begin_step(c)) != PS_OK) return r;
+    const PsParams &p = c->params;
+    cudaStream_t s = c->stream;
+    const u32 n = c->n;
+    const u32 iters = p.solver_iterations;
+    const int max_marks = 2 + (int)iters * 16;
+    std::vector<cudaEvent_t> ev(max_marks);
+    std::vector<int> tag(max_marks, -1);
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    int m = 0;
+    auto mark = [&](int stage, u32 launches) { cudaEventRecord(ev[m], s); tag[m] = stage; if (stage >= 0 && stage_launches) stage_launches[stage] += launches; m++; };
+    mark(-1, 0);
+    ps_launch_predict(c->pos, c->vel, c->prev, n, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), s); mark(0, 1);
+    const bool odd = (c->sort_passes & 1) != 0;
+    u32 *kA = odd ? c->hash_tmp : c->hash, *vA = odd ? c->index_tmp : c->index;
+    u32 *kB = odd ? c->hash : c->hash_tmp, *vB = odd ? c->index : c->index_tmp;
+    for (u32 it = 0; it < iters; it++) {
+        ps_launch_calc_hash(kA, nullptr, c->pos, n, c->grid, s); mark(1, 1);
+        ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s); mark(2, 1 + c->sort_passes);
+        ps_launch_reorder(c->cell_start, c->cell_end, c->spos, c->sw, c->sphase, c->hash, c->index, c->pos, c->w, c->phase, n, c->num_cells, s); mark(3, 1);
+        ps_launch_cell_begin(c->cell_begin, c->cell_start, c->cell_block_min, n, c->num_cells, s); mark(4, 3);
+        c->grid_valid = true;
+        ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, s); mark(5, 1);
+        ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil,
+                               (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s); mark(6, 1);
+        ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil, p.omega, s); mark(7, 1);
+        ps_launch_collide_world(c->pos, c->prev, c->phase, n, c->rands + 6 * it, c->world, s); mark(8, 1);
+        if (c->num_constrained) { ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained, p.omega, s); mark(9, 2); }
+        if (c->num_points) { ps_launch_point(c->pos, c->d_point_idx, c->d_point_xyz, c->num_points, s); mark(10, 1); }
+    }
+    ps_launch_velocity(c->pos, c->prev, c->vel, n, dt, s); mark(11, 1);
+    CU(cudaStreamSynchronize(s));
+    for (int k = 1; k < m; k++) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ev[k - 1], ev[k]));
+        stage_ms[tag[k]] += ms;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return check_launch("ps_step_profiled");
+}
+
+extern "C" int ps_timer_start(PsCtx *c) {
+    NEED(c);
+    DeviceGuard dg(c->device);
+    if (!c->tm0) { CU(cudaEventCreate(&c->tm0)); CU(cudaEventCreate(&c->tm1)); }
+    CU(cudaEventRecord(c->tm0, c->stream));
+    return PS_OK;
+}
+extern "C" int ps_timer_stop(PsCtx *c, float *ms) {
+    NEED(c);
+    if (!ms || !c->tm0) { ps_set_error("ps_timer_stop without ps_timer_start"); return PS_ERR_STATE; }
+    DeviceGuard dg(c->device);
+    CU(cudaEventRecord(c->tm1, c->stream));
+    CU(cudaEventSynchronize(c->tm1));
+    CU(cudaEventElapsedTime(ms, c->tm0, c->tm1));
+    return PS_OK;
 }
 
 extern "C" int ps_sync(PsCtx *c) {

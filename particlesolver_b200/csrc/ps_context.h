@@ -58,7 +58,7 @@ struct PsCtx {
         return n == o.n && n_ghost == o.n_ghost && m == o.m && p == o.p && iters == o.iters && flags == o.flags && dt == o.dt && omega == o.omega; } } graph_key{};
     u32 launches_per_step = 0;
     u32 launch_counter = 0;  // counts launches while a step is being issued
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     bool grid_valid = false;
 };
 
