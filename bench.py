@@ -38,7 +38,7 @@ GRID = 256
 ITERS = 5
 
 # algorithmic (compulsory) HBM bytes per particle per launch of each stage — SURVEY.md §8(d) / BASELINE.md §5.
-# sort: 4 + 16 P with P = radix passes (3 for 2^24 cells); cell_table: 16 B per CELL (memset 4 + scan 12).
+# sort: 4 + 16 P with P = radix passes (3 for 2^24 cells); cell_table: 4 B per CELL (one write of the dense table) + 4 B per key.
 STAGE_BYTES = {"predict": 64, "hash": 24, "sort": 52, "reorder": 56, "contacts": 60, "lambda": 36, "delta_p": 64, "world": 52,
                "velocity": 48}
 
@@ -269,7 +269,7 @@ def run_ours(args, rank, world, local_rank):
             continue
         calls = 1 if k in ("predict", "velocity") else ITERS
         if k == "cell_table":
-            b = 16.0 * cells
+            b = 4.0 * cells + 4.0 * n  # write the dense table once, read the sorted keys once
         elif k in STAGE_BYTES:
             b = STAGE_BYTES[k] * n
         else:

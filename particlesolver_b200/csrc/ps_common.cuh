@@ -88,11 +88,14 @@ void ps_launch_distance(float4 *pos, float4 *scratch, const u32 *csr_particle, c
                         const float *csr_rest, const u32 *occ, u32 num_constrained, float omega, cudaStream_t s);
 // ps_grid_kernels.cu
 void ps_launch_calc_hash(u32 *hash, u32 *index, const float4 *pos, u32 n, GridDesc g, cudaStream_t s);
-void ps_launch_reorder(u32 *cell_start, u32 *cell_end, float4 *spos, float *sw, int *sphase, const u32 *hash, const u32 *index,
-                       const float4 *pos, const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s);
-// dense lower-bound table cell_begin[c] = #particles with key < c, c in [0,num_cells]; from cell_start
-void ps_launch_cell_begin(u32 *cell_begin, const u32 *cell_start, u32 *block_min, u32 n, u32 num_cells, cudaStream_t s);
-size_t ps_cell_begin_scratch_elems(u32 num_cells);
+// K4: gather into sorted order + per-chunk lower bounds (chunk_lb[ps_chunk_table_elems(num_cells)])
+void ps_launch_reorder(float4 *spos, float *sw, int *sphase, u32 *chunk_lb, const u32 *hash, const u32 *index, const float4 *pos,
+                       const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s);
+size_t ps_chunk_table_elems(u32 num_cells);
+// dense lower-bound table cell_begin[c] = #particles with key < c, c in [0,num_cells]; from the sorted keys + chunk_lb
+void ps_launch_cell_begin(u32 *cell_begin, const u32 *hash, const u32 *chunk_lb, u32 n, u32 num_cells, cudaStream_t s);
+// the reference's cellStart/cellEnd pair, derived from cell_begin (cellEnd of empty cells reads 0)
+void ps_launch_emit_reference_tables(u32 *cell_start, u32 *cell_end, const u32 *cell_begin, u32 num_cells, cudaStream_t s);
 // ps_sort_kernels.cu
 struct SortScratch {
     u32 *hist;    // [4][256] global digit histograms

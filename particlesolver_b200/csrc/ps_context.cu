@@ -159,15 +159,29 @@ int ps_ctx_ensure_capacity(PsCtx *c, uint64_t want) {
 
 int ps_ctx_ensure_cells(PsCtx *c) {
     uint64_t cells = c->num_cells;
-    if (cells <= c->cell_capacity && c->cell_start) return PS_OK;
-    if (c->cell_start) { CU(cudaFree(c->cell_start)); CU(cudaFree(c->cell_end)); CU(cudaFree(c->cell_begin)); CU(cudaFree(c->cell_block_min)); }
-    CU(cudaMalloc((void **)&c->cell_start, cells * sizeof(u32)));
-    CU(cudaMalloc((void **)&c->cell_end, cells * sizeof(u32)));
+    if (cells <= c->cell_capacity && c->cell_begin) return PS_OK;
+    if (c->cell_begin) { CU(cudaFree(c->cell_begin)); CU(cudaFree(c->chunk_lb)); c->cell_begin = c->chunk_lb = nullptr; }
+    if (c->cell_start) { CU(cudaFree(c->cell_start)); CU(cudaFree(c->cell_end)); c->cell_start = c->cell_end = nullptr; }
     CU(cudaMalloc((void **)&c->cell_begin, (cells + 8) * sizeof(u32)));
-    CU(cudaMalloc((void **)&c->cell_block_min, ps_cell_begin_scratch_elems((u32)cells) * sizeof(u32)));
-    CU(cudaMemsetAsync(c->cell_start, 0xff, cells * sizeof(u32), c->stream));
-    CU(cudaMemsetAsync(c->cell_end, 0, cells * sizeof(u32), c->stream));
+    CU(cudaMalloc((void **)&c->chunk_lb, ps_chunk_table_elems((u32)cells) * sizeof(u32)));
     c->cell_capacity = cells;
+    c->ref_tables_valid = false;
+    return PS_OK;
+}
+
+// cellStart / cellEnd in the reference's format (m_dCellStart / m_dCellEnd), derived from the dense table of the
+// last grid build.  Not on the step's path: only parity checks and foreign consumers ask for them.
+int ps_ctx_emit_reference_tables(PsCtx *c) {
+    if (c->ref_tables_valid) return PS_OK;
+    if (!c->grid_valid) { ps_set_error("cellStart/cellEnd requested before a grid build"); return PS_ERR_STATE; }
+    const uint64_t cells = c->num_cells;
+    if (!c->cell_start) {
+        CU(cudaMalloc((void **)&c->cell_start, cells * sizeof(u32)));
+        CU(cudaMalloc((void **)&c->cell_end, cells * sizeof(u32)));
+    }
+    ps_launch_emit_reference_tables(c->cell_start, c->cell_end, c->cell_begin, (u32)cells, c->stream);
+    CU(cudaGetLastError());
+    c->ref_tables_valid = true;
     return PS_OK;
 }
 
@@ -234,7 +248,7 @@ extern "C" int ps_destroy(PsCtx *c) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->gen) curandDestroyGenerator(c->gen);
     void *ptrs[] = {c->pos, c->vel, c->prev, c->spos, c->w, c->ros, c->sw, c->lambda, c->phase, c->sphase, c->hash, c->index, c->hash_tmp,
-                    c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->cell_block_min, c->sort_hist,
+                    c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->chunk_lb, c->sort_hist,
                     c->sort_status, c->sort_ticket, c->rands, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
                     c->d_point_xyz, c->dist_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -287,6 +301,7 @@ extern "C" int ps_append_particles(PsCtx *c, const float *pos4, const float *vel
     CU(cudaMemcpyAsync(c->ros + c->n, rest_density, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(c->phase + c->n, phase, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));  // host buffers may be stack arrays of the caller (the reference's builders are)
+    for (uint64_t k = 0; k < n; k++) { c->n_fluid += phase[k] == PH_FLUID; c->n_contact += phase[k] >= PH_CLOTH; }
     c->n += (u32)n;
     c->h_occ.resize(c->n, 0u);
     c->constraints_dirty = true;
@@ -399,11 +414,12 @@ u32 ps_issue_build_grid(PsCtx *c, const float4 *pos) {
     u32 *kB = odd ? c->hash : c->hash_tmp, *vB = odd ? c->index : c->index_tmp;
     ps_launch_calc_hash(kA, nullptr, pos, n, c->grid, s);
     ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s);
-    ps_launch_reorder(c->cell_start, c->cell_end, c->spos, c->sw, c->sphase, c->hash, c->index, pos, c->w, c->phase, n, c->num_cells, s);
-    ps_launch_cell_begin(c->cell_begin, c->cell_start, c->cell_block_min, n, c->num_cells, s);
+    ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, pos, c->w, c->phase, n, c->num_cells, s);
+    ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s);
     c->grid_valid = true;
-    // kernels only (the 4 memset nodes are not counted): calc_hash 1 + hist 1 + passes + reorder 1 + cell_begin 3
-    return 1 + 1 + (u32)c->sort_passes + 1 + 3;
+    c->ref_tables_valid = false;
+    // kernels only (the 3 memset nodes of the sort are not counted): calc_hash 1 + hist 1 + passes + reorder 1 + cell_begin 1
+    return 1 + 1 + (u32)c->sort_passes + 1 + 1;
 }
 
 static int ready(PsCtx *c) {
@@ -493,17 +509,27 @@ static u32 issue_step(PsCtx *c, float dt) {
     cudaStream_t s = c->stream;
     const u32 n = c->n, n_owned = c->n - c->n_ghost;
     u32 launches = 0;
+    // the phase census lets an all-fluid scene skip the contact pass and a fluid-free scene the two PBF passes
+    // (both kernels would only read every phase and return)
+    const bool has_contact = !c->census_known || c->n_contact > 0, has_fluid = !c->census_known || c->n_fluid > 0;
     ps_launch_predict(c->pos, c->vel, c->prev, n_owned, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), s);
     launches++;
     for (u32 it = 0; it < p.solver_iterations; it++) {
         launches += ps_issue_build_grid(c, c->pos);
-        ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n_owned, c->grid,
-                          p.particle_radius, s);
-        ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil,
-                               (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s);
-        ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned, c->grid, c->stencil, p.omega, s);
+        if (has_contact) {
+            ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n_owned, c->grid,
+                              p.particle_radius, s);
+            launches++;
+        }
+        if (has_fluid) {
+            ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid,
+                                   c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s);
+            ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned, c->grid, c->stencil,
+                                   p.omega, s);
+            launches += 2;
+        }
         ps_launch_collide_world(c->pos, c->prev, c->phase, n_owned, c->rands + 6 * it, c->world, s);
-        launches += 4;
+        launches++;
         if (c->num_constrained) { ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained, p.omega, s); launches += 2; }
         if (c->num_points) { ps_launch_point(c->pos, c->d_point_idx, c->d_point_xyz, c->num_points, s); launches++; }
     }
@@ -563,6 +589,7 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
     cudaStream_t s = c->stream;
     const u32 n = c->n;
     const u32 iters = p.solver_iterations;
+    const bool has_contact = !c->census_known || c->n_contact > 0, has_fluid = !c->census_known || c->n_fluid > 0;
     const int max_marks = 2 + (int)iters * 16;
     std::vector<cudaEvent_t> ev(max_marks);
     std::vector<int> tag(max_marks, -1);
@@ -577,13 +604,16 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
     for (u32 it = 0; it < iters; it++) {
         ps_launch_calc_hash(kA, nullptr, c->pos, n, c->grid, s); mark(1, 1);
         ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s); mark(2, 1 + c->sort_passes);
-        ps_launch_reorder(c->cell_start, c->cell_end, c->spos, c->sw, c->sphase, c->hash, c->index, c->pos, c->w, c->phase, n, c->num_cells, s); mark(3, 1);
-        ps_launch_cell_begin(c->cell_begin, c->cell_start, c->cell_block_min, n, c->num_cells, s); mark(4, 3);
+        ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, c->pos, c->w, c->phase, n, c->num_cells, s); mark(3, 1);
+        ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s); mark(4, 1);
         c->grid_valid = true;
-        ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, s); mark(5, 1);
-        ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil,
-                               (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s); mark(6, 1);
-        ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil, p.omega, s); mark(7, 1);
+        c->ref_tables_valid = false;
+        if (has_contact) { ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, s); mark(5, 1); }
+        if (has_fluid) {
+            ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil,
+                                   (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s); mark(6, 1);
+            ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil, p.omega, s); mark(7, 1);
+        }
         ps_launch_collide_world(c->pos, c->prev, c->phase, n, c->rands + 6 * it, c->world, s); mark(8, 1);
         if (c->num_constrained) { ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained, p.omega, s); mark(9, 2); }
         if (c->num_points) { ps_launch_point(c->pos, c->d_point_idx, c->d_point_xyz, c->num_points, s); mark(10, 1); }
@@ -661,24 +691,37 @@ static int copy_common(PsCtx *c, int which, void *host, uint64_t off, uint64_t c
     NEED(c);
     ArrInfo a = arr_info(c, which);
     if (!a.ptr && a.count == 0 && cnt == 0) return PS_OK;
-    if (!a.ptr) { ps_set_error("unknown array selector %d", which); return PS_ERR_INVALID; }
+    if (!a.ptr && !(which == PS_ARR_CELL_START || which == PS_ARR_CELL_END)) { ps_set_error("unknown array selector %d", which); return PS_ERR_INVALID; }
     if (!host && cnt) { ps_set_error("null host pointer"); return PS_ERR_INVALID; }
     if (off + cnt > a.count) { ps_set_error("range [%llu,%llu) exceeds array %d of %llu elements", (unsigned long long)off, (unsigned long long)(off + cnt), which, (unsigned long long)a.count); return PS_ERR_INVALID; }
     if (cnt == 0) return PS_OK;
     DeviceGuard dg(c->device);
     if (which == PS_ARR_OCCURRENCES) { int r = ps_ctx_sync_constraints(c); if (r != PS_OK) return r; }
+    if (which == PS_ARR_CELL_START || which == PS_ARR_CELL_END) {
+        if (!to_host) { ps_set_error("cellStart/cellEnd are derived outputs"); return PS_ERR_INVALID; }
+        int r = ps_ctx_emit_reference_tables(c); if (r != PS_OK) return r;
+        a = arr_info(c, which);
+    }
     char *d = (char *)a.ptr + off * a.esz;
     if (to_host) CU(cudaMemcpyAsync(host, d, cnt * a.esz, cudaMemcpyDeviceToHost, c->stream));
     else CU(cudaMemcpyAsync(d, host, cnt * a.esz, cudaMemcpyHostToDevice, c->stream));
     if (sync) CU(cudaStreamSynchronize(c->stream));
     if (!to_host && (which == PS_ARR_POS || which == PS_ARR_INV_MASS || which == PS_ARR_PHASE)) c->grid_valid = false;
+    if (!to_host && which == PS_ARR_PHASE) { c->census_known = false; if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; } }
     return PS_OK;
 }
 extern "C" int ps_download(PsCtx *c, int which, void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, host, off, cnt, true, true); }
 extern "C" int ps_upload(PsCtx *c, int which, const void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, (void *)host, off, cnt, false, true); }
 extern "C" int ps_download_async(PsCtx *c, int which, void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, host, off, cnt, true, false); }
 extern "C" int ps_upload_async(PsCtx *c, int which, const void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, (void *)host, off, cnt, false, false); }
-extern "C" void *ps_device_ptr(PsCtx *c, int which) { return c ? arr_info(c, which).ptr : nullptr; }
+extern "C" void *ps_device_ptr(PsCtx *c, int which) {
+    if (!c) return nullptr;
+    if (which == PS_ARR_CELL_START || which == PS_ARR_CELL_END) {  // derived tables: filled for the grid of the last build
+        DeviceGuard dg(c->device);
+        if (ps_ctx_emit_reference_tables(c) != PS_OK) return nullptr;
+    }
+    return arr_info(c, which).ptr;
+}
 
 // ------------------------------------------------------------------ slabs ------------------------------------------------------------------
 extern "C" int ps_set_ghost_count(PsCtx *c, uint64_t ghosts) {

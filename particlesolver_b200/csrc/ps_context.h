@@ -22,6 +22,10 @@ struct PsCtx {
     uint64_t capacity = 0;  // allocated slots
     u32 n = 0;              // owned + ghosts
     u32 n_ghost = 0;
+    // phase census of the appended particles, so that a step skips the contact pass of an all-fluid scene and the
+    // fluid passes of a scene without fluid; unknown after a raw phase upload (then nothing is skipped)
+    bool census_known = true;
+    u32 n_fluid = 0, n_contact = 0;  // phase == FLUID, phase >= CLOTH
 
     // per-particle state (SoA).  pos may be caller-owned in the reference-ABI shim, hence the indirection.
     float4 *pos = nullptr, *vel = nullptr, *prev = nullptr, *spos = nullptr;
@@ -29,7 +33,9 @@ struct PsCtx {
     int *phase = nullptr, *sphase = nullptr;
     u32 *hash = nullptr, *index = nullptr, *hash_tmp = nullptr, *index_tmp = nullptr, *num_neighbors = nullptr, *occ = nullptr;
     // per-cell state
-    u32 *cell_start = nullptr, *cell_end = nullptr, *cell_begin = nullptr, *cell_block_min = nullptr;
+    u32 *cell_begin = nullptr, *chunk_lb = nullptr;
+    u32 *cell_start = nullptr, *cell_end = nullptr;  // the reference's table format: allocated and filled on demand
+    bool ref_tables_valid = false;
     uint64_t cell_capacity = 0;
     // sort scratch
     u32 *sort_hist = nullptr, *sort_status = nullptr, *sort_ticket = nullptr;
@@ -66,6 +72,7 @@ struct PsCtx {
 int ps_create_internal(int device, const PsParams *params, uint64_t max_particles, bool legacy_default_stream, PsCtx **out);
 int ps_ctx_ensure_capacity(PsCtx *c, uint64_t want);
 int ps_ctx_ensure_cells(PsCtx *c);
+int ps_ctx_emit_reference_tables(PsCtx *c);
 int ps_ctx_sync_constraints(PsCtx *c);
 void ps_ctx_refresh_descs(PsCtx *c);
 void ps_set_error(const char *fmt, ...);

@@ -48,48 +48,141 @@ __device__ __forceinline__ void for_each_candidate(const GridDesc &g, const Sten
     }
 }
 
+// ------------------------------------------------------------------ fluid neighbour walk ------------------------------------------------------------------
+// Shared by K6 and K7.  One thread per sorted slot, one warp = 32 consecutive slots (= a run of x-adjacent
+// particles of one or two grid rows).  Two things keep the warp's issue slots busy:
+//   (1) per-particle row pruning: for stencil row (dy,dz) the x-extent that can hold a neighbour follows from the
+//       particle's own position inside its cell, ext = sqrt(H^2 - dymin^2 - dzmin^2) — ~200 candidates per
+//       particle instead of the ~370 of the full 9^3 stencil.  The pruning is conservative (eps margin), so the
+//       accepted neighbour sequence — and with it the 500-cap and the summation order — is exactly the reference's;
+//   (2) accept/interact split: the distance test runs over all candidates, accepted neighbours (~40 % of them) are
+//       staged in a per-thread shared-memory queue of Q float4 entries (r.x, r.y, r.z, r2 | j) and the expensive
+//       interaction body runs over full queues with every lane active, instead of under a divergent branch.
+// The row loop is warp-uniform (all lanes walk the same (dz,dy) sequence; the inner loop runs to the warp's longest
+// range), which keeps the vote that triggers a queue flush legal.
+constexpr int kQ = 8;
+constexpr unsigned kFull = 0xffffffffu;
+
+template <bool STORE_J, class Body>
+__device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const StencilDesc &st, const u32 *__restrict__ cell_begin,
+                                                     const float4 *__restrict__ spos, bool act, u32 i, float4 pi, float4 (*q)[kBlock],
+                                                     Body &&body) {
+    const int tid = threadIdx.x;
+    const int rad = st.rad, w = 2 * st.rad + 1;
+    const float relx = pi.x - g.ox, rely = pi.y - g.oy, relz = pi.z - g.oz;
+    const int3 gp = ps_grid_pos(g, pi.x, pi.y, pi.z);
+    // margin: covers the approximate divide of the cell assignment and coordinate rounding (ulp(1000) = 6e-5)
+    const float eps = 1e-3f + 2e-6f * fmaxf(fabsf(relx), fmaxf(fabsf(rely), fabsf(relz)));
+    const float inv_cx = __fdividef(1.f, g.cx);
+    // distance from the particle to the lower / upper face of its own cell (clamped: the divide is approximate)
+    const float fy0 = fmaxf(rely - (float)gp.y * g.cy, 0.f), fy1 = fmaxf((float)(gp.y + 1) * g.cy - rely, 0.f);
+    const float fz0 = fmaxf(relz - (float)gp.z * g.cz, 0.f), fz1 = fmaxf((float)(gp.z + 1) * g.cz - relz, 0.f);
+    u32 nn = 0;
+    int cnt = 0;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < kQ; k++)
+            if (k < cnt) body(q[k][tid]);
+        cnt = 0;
+    };
+
+    for (int dz = -rad; dz <= rad; dz++) {
+        const u32 zrow = ((u32)(gp.z + dz) & g.mz) * g.gy;
+        float dzmin = dz == 0 ? 0.f : (dz > 0 ? fz1 + (float)(dz - 1) * g.cz : fz0 + (float)(-dz - 1) * g.cz);
+        dzmin = fmaxf(dzmin - eps, 0.f);
+        const float remz = PS_H2 - dzmin * dzmin;
+        for (int dy = -rad; dy <= rad; dy++) {
+            if (st.xr[(dz + rad) * w + (dy + rad)] < 0) continue;  // uniform: row out of reach for every particle
+            float dymin = dy == 0 ? 0.f : (dy > 0 ? fy1 + (float)(dy - 1) * g.cy : fy0 + (float)(-dy - 1) * g.cy);
+            dymin = fmaxf(dymin - eps, 0.f);
+            const float rem = remz - dymin * dymin;
+            u32 b0 = 0, len0 = 0, b1 = 0, len1 = 0;
+            if (act && rem >= 0.f) {
+                const float ext = sqrtf(rem) + eps;
+                int lo = (int)floorf((relx - ext) * inv_cx), hi = (int)floorf((relx + ext) * inv_cx);
+                lo = max(min(lo, gp.x), gp.x - rad);
+                hi = min(max(hi, gp.x), gp.x + rad);
+                const u32 row = (zrow + ((u32)(gp.y + dy) & g.my)) * g.gx;
+                const u32 lw = (u32)lo & g.mx, hw = (u32)hi & g.mx;
+                if (lw <= hw) {
+                    b0 = __ldg(cell_begin + row + lw);
+                    len0 = __ldg(cell_begin + row + hw + 1) - b0;
+                } else {  // the row wraps around the power-of-two grid: [lw, gx) then [0, hw]
+                    b0 = __ldg(cell_begin + row + lw);
+                    len0 = __ldg(cell_begin + row + g.mx + 1) - b0;
+                    b1 = __ldg(cell_begin + row);
+                    len1 = __ldg(cell_begin + row + hw + 1) - b1;
+                }
+            }
+#pragma unroll 1
+            for (int seg = 0; seg < 2; seg++) {
+                const u32 b = seg ? b1 : b0, len = seg ? len1 : len0;
+                const u32 maxlen = __reduce_max_sync(kFull, len);
+#pragma unroll 1
+                for (u32 t = 0; t < maxlen; t++) {
+                    if (t < len) {
+                        const u32 j = b + t;
+                        const float4 pj = __ldg(spos + j);
+                        const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
+                        const float r2 = rx * rx + ry * ry + rz * rz;
+                        if (r2 < PS_H2 && j != i && nn < PS_MAX_NEIGHBORS) {
+                            q[cnt][tid] = make_float4(rx, ry, rz, STORE_J ? __uint_as_float(j) : r2);
+                            cnt++;
+                            nn++;
+                        }
+                    }
+                    if (__any_sync(kFull, cnt == kQ)) flush();
+                }
+            }
+        }
+    }
+    flush();
+    return nn;
+}
+
 // ------------------------------------------------------------------ K6: lambda ------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lambda, u32 *__restrict__ num_neighbors,
                                                          const float4 *__restrict__ spos, const float *__restrict__ sw,
                                                          const int *__restrict__ sphase, const u32 *__restrict__ index,
                                                          const u32 *__restrict__ cell_begin, const float *__restrict__ ros, u32 n,
                                                          u32 n_owned, GridDesc g, StencilDesc st, int zero_nonfluid) {
+    __shared__ float4 q[kQ][kBlock];
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    if (sphase[i] != PH_FLUID) {
-        if (zero_nonfluid) lambda[i] = 0.f;
-        return;
+    bool act = i < n;
+    u32 orig = 0;
+    if (act) {
+        if (sphase[i] != PH_FLUID) {
+            if (zero_nonfluid) lambda[i] = 0.f;
+            act = false;
+        } else {
+            orig = index[i];
+            act = orig < n_owned;  // ghost copy of a neighbour slab's particle: its owner computes it
+        }
     }
-    const u32 orig = index[i];
-    if (orig >= n_owned) return;  // ghost copy of a neighbour slab's particle: its owner computes it
-    const float4 pi = spos[i];
-    const float inv_w = __fdividef(1.f, sw[i]);
-    const float ro0 = ros[orig];
+    if (!__any_sync(kFull, act)) return;
+    const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
+    const float ro0 = act ? ros[orig] : 1.f;
     const float inv_ro0 = __fdividef(1.f, ro0);
-    const int3 gp = ps_grid_pos(g, pi.x, pi.y, pi.z);
+    const float cs = -PS_SPIKY * inv_ro0;
 
-    u32 nn = 0;
     float ro = 0.f, denom = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-    for_each_candidate(g, st, cell_begin, gp, [&](u32 j) {
-        const float4 pj = __ldg(spos + j);
-        const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-        const float r2 = rx * rx + ry * ry + rz * rz;
-        if (r2 < PS_H2 && j != i && nn < PS_MAX_NEIGHBORS) {
-            nn++;
-            const float inv_r = rsqrtf(r2);
-            const float rlen = r2 * inv_r;  // sqrt(r2); r2 == 0 gives NaN here and is handled below
-            const float hm2 = PS_H2 - r2;
-            ro += (PS_POLY6 * hm2 * hm2 * hm2) * inv_w;
-            if (rlen >= 0.0001f) {  // false for NaN as well: coincident particles contribute no gradient
-                const float hm = PS_H - rlen;
-                const float c = (-PS_SPIKY * hm * hm) * inv_r * inv_ro0;  // spikyGrad = r * c
-                const float sx = rx * c, sy = ry * c, sz = rz * c;
-                gx -= sx; gy -= sy; gz -= sz;
-                denom += sx * sx + sy * sy + sz * sz;
-            }
+    const u32 nn = walk_fluid_neighbours<false>(g, st, cell_begin, spos, act, i, pi, q, [&](const float4 e) {
+        const float r2 = e.w;
+        const float inv_r = rsqrtf(r2);
+        const float rlen = r2 * inv_r;  // sqrt(r2); r2 == 0 gives NaN here and is handled below
+        const float hm2 = PS_H2 - r2;
+        ro += hm2 * hm2 * hm2;
+        if (rlen >= 0.0001f) {  // false for NaN as well: coincident particles contribute no gradient
+            const float hm = PS_H - rlen;
+            const float c = (cs * hm * hm) * inv_r;  // spikyGrad / rho0 = r * c
+            gx += e.x * c; gy += e.y * c; gz += e.z * c;
+            denom += (c * c) * r2;
         }
     });
-    ro += (PS_POLY6 * PS_H6) * inv_w;
+    if (!act) return;
+    const float inv_w = __fdividef(1.f, sw[i]);
+    ro = (ro + PS_H6) * (PS_POLY6 * inv_w);  // + self term poly6(0) = POLY6 * H^6 (integration_kernel.cuh:589)
     denom += gx * gx + gy * gy + gz * gz;
     lambda[i] = -__fdividef(ro * inv_ro0 - 1.f, denom + PS_RELAX);
     num_neighbors[i] = nn;
@@ -101,44 +194,42 @@ __global__ void __launch_bounds__(kBlock) k_solve_fluids(float4 *__restrict__ po
                                                          const u32 *__restrict__ index, const u32 *__restrict__ cell_begin,
                                                          const float *__restrict__ ros, u32 n, u32 n_owned, GridDesc g, StencilDesc st,
                                                          float omega) {
+    __shared__ float4 q[kQ][kBlock];
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    if (sphase[i] != PH_FLUID) return;
-    const u32 orig = index[i];
-    if (orig >= n_owned) return;
-    const float4 pi = spos[i];
-    const float li = lambda[i];
-    const int3 gp = ps_grid_pos(g, pi.x, pi.y, pi.z);
+    bool act = i < n && sphase[i] == PH_FLUID;
+    u32 orig = 0;
+    if (act) {
+        orig = index[i];
+        act = orig < n_owned;
+    }
+    if (!__any_sync(kFull, act)) return;
+    const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
+    const float li = act ? lambda[i] : 0.f;
     // s_corr = -K_P * (poly6(r) / poly6(dq*H))^4 ; the POLY6 factors cancel (integration_kernel.cuh:630-634)
     const float term2 = PS_H2 - (PS_DQ_P * PS_DQ_P * PS_H2);
     const float inv_den = __fdividef(1.f, term2 * term2 * term2);
 
-    u32 nn = 0;
     float dx = 0.f, dy = 0.f, dz = 0.f;
-    for_each_candidate(g, st, cell_begin, gp, [&](u32 j) {
-        const float4 pj = __ldg(spos + j);
-        const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-        const float r2 = rx * rx + ry * ry + rz * rz;
-        if (r2 < PS_H2 && j != i && nn < PS_MAX_NEIGHBORS) {
-            nn++;
-            const float lj = __ldg(lambda + j);
-            const float inv_r = rsqrtf(r2);
-            const float rlen = r2 * inv_r;
-            const float hm2 = PS_H2 - r2;
-            const float q = (hm2 * hm2 * hm2) * inv_den;
-            const float q2 = q * q;
-            const float s = li + lj + (-PS_K_P * q2 * q2);
-            if (rlen >= 0.0001f) {
-                const float hm = PS_H - rlen;
-                const float c = s * ((-PS_SPIKY * hm * hm) * inv_r);
-                dx += rx * c; dy += ry * c; dz += rz * c;
-            } else {  // coincident: the reference nudges along +y, (0,EPS,0,0) * -SPIKY * (H-r)^2 (:625-626)
-                const float rl = (r2 > 0.f) ? rlen : 0.f;
-                const float hm = PS_H - rl;
-                dy += s * (PS_EPS * -PS_SPIKY * hm * hm);
-            }
+    const u32 nn = walk_fluid_neighbours<true>(g, st, cell_begin, spos, act, i, pi, q, [&](const float4 e) {
+        const float lj = __ldg(lambda + __float_as_uint(e.w));
+        const float r2 = e.x * e.x + e.y * e.y + e.z * e.z;
+        const float inv_r = rsqrtf(r2);
+        const float rlen = r2 * inv_r;
+        const float hm2 = PS_H2 - r2;
+        const float qq = (hm2 * hm2 * hm2) * inv_den;
+        const float q2 = qq * qq;
+        const float s = li + lj + (-PS_K_P * q2 * q2);
+        if (rlen >= 0.0001f) {
+            const float hm = PS_H - rlen;
+            const float c = s * ((-PS_SPIKY * hm * hm) * inv_r);
+            dx += e.x * c; dy += e.y * c; dz += e.z * c;
+        } else {  // coincident: the reference nudges along +y, (0,EPS,0,0) * -SPIKY * (H-r)^2 (:625-626)
+            const float rl = (r2 > 0.f) ? rlen : 0.f;
+            const float hm = PS_H - rl;
+            dy += s * (PS_EPS * -PS_SPIKY * hm * hm);
         }
     });
+    if (!act) return;
     const float inv_div = __fdividef(omega, ros[orig] + (float)nn);
     float4 P = pos[orig];
     P.x += dx * inv_div; P.y += dy * inv_div; P.z += dz * inv_div;

@@ -13,8 +13,7 @@ PsCtx *g = nullptr;            // the one live system (the reference keeps file-
 u32 g_n_integ = 0;             // sizes of the three independently appended groups
 u32 g_n_shared = 0;            //   V/ros (integration.cu:50-72), W/phase (shared_variables.cu:32-50),
 u32 g_n_solver = 0;            //   occurences (solver.cu:64-70)
-const u32 *g_dense_for = nullptr;  // cellStart pointer the dense table was last built from
-bool g_dense_fresh = false;
+const u32 *g_dense_for = nullptr;  // cellStart pointer handed out by the last reorderDataAndFindCellStart
 
 [[noreturn]] void die(const char *where) {
     // reference behaviour: checkCudaErrors prints and exit(EXIT_FAILURE)s (helper_cuda.h:981-1008)
@@ -42,14 +41,14 @@ void maybe_destroy() {
     // the reference frees its three groups of vectors with three calls (particlesystem.cpp:131-133)
     if (g && g_n_integ == 0 && g_n_shared == 0 && g_n_solver == 0) { ps_destroy(g); g = nullptr; g_dense_for = nullptr; }
 }
-void ensure_dense(const u32 *cell_start, u32 n, u32 num_cells) {
+// collide / solveFluids receive the caller's cellStart/cellEnd; the kernels walk the dense table that
+// reorderDataAndFindCellStart built beside them, so the two must come from the same call.
+void need_dense(const u32 *cell_start, u32 num_cells, const char *where) {
     PsCtx *c = ctx();
-    if (g_dense_fresh && g_dense_for == cell_start) return;
-    if (num_cells != c->num_cells) { ps_set_error("numCells %u does not match setParameters' grid (%u)", num_cells, c->num_cells); die("cell table"); }
-    ps_launch_cell_begin(c->cell_begin, cell_start, c->cell_block_min, n, num_cells, c->stream);
-    ck_launch("cell table");
-    g_dense_for = cell_start;
-    g_dense_fresh = true;
+    if (!g_dense_for || g_dense_for != cell_start || num_cells != c->num_cells) {
+        ps_set_error("cell tables were not produced by the preceding reorderDataAndFindCellStart call");
+        die(where);
+    }
 }
 }  // namespace
 
@@ -79,7 +78,7 @@ void setParameters(PsRefSimParams *h) {
     memcpy(p.cell_size, h->cellSize, 12);
     if (memcmp(&p, &c->params, sizeof p) == 0) return;  // the reference re-uploads every frame (particlesystem.cpp:163)
     ck(ps_set_params(c, &p), "setParameters");
-    g_dense_fresh = false;
+    g_dense_for = nullptr;
 }
 
 void integrateSystem(float *pos, float dt, uint n) {
@@ -110,18 +109,25 @@ void sortParticles(uint *hash, uint *index, uint n) {
 void reorderDataAndFindCellStart(uint *cellStart, uint *cellEnd, float *sortedPos, float *sortedW, int *sortedPhase, uint *hash,
                                  uint *index, float *oldPos, uint n, uint numCells) {
     PsCtx *c = ctx();
-    ps_launch_reorder(cellStart, cellEnd, (float4 *)sortedPos, sortedW, sortedPhase, hash, index, (const float4 *)oldPos, c->w, c->phase, n,
-                      numCells, c->stream);
+    if (numCells != c->num_cells) { ps_set_error("numCells %u does not match setParameters' grid (%u)", numCells, c->num_cells); die("reorderDataAndFindCellStart"); }
+    ps_launch_reorder((float4 *)sortedPos, sortedW, sortedPhase, c->chunk_lb, hash, index, (const float4 *)oldPos, c->w, c->phase, n, numCells,
+                      c->stream);
+    if (n) {
+        ps_launch_cell_begin(c->cell_begin, hash, c->chunk_lb, n, numCells, c->stream);
+        // the caller's tables in the reference's format (cellEnd of empty cells: 0; the reference leaves them stale)
+        ps_launch_emit_reference_tables(cellStart, cellEnd, c->cell_begin, numCells, c->stream);
+    } else {
+        ck_cuda(cudaMemsetAsync(cellStart, 0xff, (size_t)numCells * sizeof(uint), c->stream), "reorderDataAndFindCellStart");
+    }
     ck_launch("reorderDataAndFindCellStart");
-    g_dense_fresh = false;
-    ensure_dense(cellStart, n, numCells);
+    g_dense_for = cellStart;
 }
 
 void collide(float *particles, float *sortedPos, float *sortedW, int *sortedPhase, uint *index, uint *cellStart, uint *cellEnd, uint n,
              uint numCells) {
     (void)cellEnd;
     PsCtx *c = ctx();
-    ensure_dense(cellStart, n, numCells);
+    need_dense(cellStart, numCells, "collide");
     ps_launch_collide((float4 *)particles, c->prev, (const float4 *)sortedPos, sortedW, sortedPhase, index, c->cell_begin, c->num_neighbors, n,
                       n, c->grid, c->params.particle_radius, c->stream);
     ck_launch("collide");
@@ -131,7 +137,7 @@ void solveFluids(float *sortedPos, float *sortedW, int *sortedPhase, uint *index
                  uint numCells) {
     (void)cellEnd;
     PsCtx *c = ctx();
-    ensure_dense(cellStart, n, numCells);
+    need_dense(cellStart, numCells, "solveFluids");
     ps_launch_find_lambdas(c->lambda, c->num_neighbors, (const float4 *)sortedPos, sortedW, sortedPhase, index, c->cell_begin, c->ros, n, n,
                            c->grid, c->stencil, false, c->stream);
     ps_launch_solve_fluids((float4 *)particles, c->lambda, (const float4 *)sortedPos, sortedPhase, index, c->cell_begin, c->ros, n, n, c->grid,

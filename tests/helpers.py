@@ -1,8 +1,12 @@
 """Shared helpers of the parity tests: scene -> oracle mirror, comparison with stated tolerances."""
+import os
+
 import numpy as np
 
 import oracle_py as orc
 import particlesolver_b200 as psb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # Tolerances.  Integer grid output: exact.  Positions after a stage / a step: the CUDA
 # path uses approximate divide / rsqrt / FMA contraction (the reference's own -use_fast_math build does too),

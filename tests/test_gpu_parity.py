@@ -146,3 +146,53 @@ def test_empty_and_tiny_systems():
     with pytest.raises(psb.PsError):
         sol.append(np.ones((32, 4)), np.zeros((32, 4)), np.ones(32), np.ones(32), np.zeros(32, np.int32))
     sol.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Drop-in check: the reference's UNMODIFIED host class (gpu/src/particlesystem.cpp) linked against libpsolver.so
+# through the reference's own wrapper names (include/ps_reference_abi.h) — oracle/_ref/ref_host_on_psolver, built in
+# the dev container by `make -C oracle ref` — replayed call by call and compared with the golden dumps of the
+# reference's own CUDA sources.
+# ---------------------------------------------------------------------------------------------------------------
+def _run_ref_binary(name, scene, out, mode="staged", steps=1, extra=()):
+    import os
+    import subprocess
+    exe = os.path.join(H.ROOT, "oracle", "_ref", name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "--scene", scene, "--mode", mode, "--steps", str(steps), "--out", out, *extra], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+@pytest.mark.parametrize("scene", ["7", "8", "5", "3"])
+def test_reference_host_on_libpsolver_matches_reference_gpu_golden(scene, tmp_path):
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(H.ROOT, "tests", "golden"))
+    import pack_golden
+    import golden_io as G
+    out = str(tmp_path / f"scene{scene}")
+    _run_ref_binary("ref_host_on_psolver", scene, out)
+    got, _ = pack_golden.load_dump(out)
+    g = G.load(scene)
+    iters = int(g["meta_iters"])
+    assert np.array_equal(got["init_pos"], g["init_pos"]) and np.array_equal(got["occurences"], g["occurences"])
+    assert H.max_abs(got["s0_predict_pos"], g["s0_predict_pos"]) <= 1e-6
+    T = "s0_i0_"
+    # iteration 0 starts from (practically) identical positions: the integer grid must agree bit for bit
+    if np.array_equal(got["s0_predict_pos"], g["s0_predict_pos"]):
+        for k in ("hash_unsorted", "hash", "index", "cell_start"):
+            assert np.array_equal(got[T + k], g[T + k]), k
+        valid = g[T + "cell_start"] != 0xFFFFFFFF
+        assert np.array_equal(got[T + "cell_end"][valid], g[T + "cell_end"][valid])
+        fl = g[T + "sorted_phase"] == psb.FLUID
+        assert np.array_equal(got[T + "fluid_nn"][fl], g[T + "fluid_nn"][fl])
+        assert H.max_abs(got[T + "lambda"][fl], g[T + "lambda"][fl]) <= 2e-4
+    # the wall jitter comes from the same cuRAND stream (XORWOW, seed 1234)
+    for it in range(iters):
+        assert np.array_equal(got[f"s0_i{it}_rands"], g[f"s0_i{it}_rands"])
+    d = H.max_abs(got["s0_final_pos"], g["s0_final_pos"])
+    assert d <= 10 * H.POS_ATOL, f"scene {scene}: reference host on libpsolver vs reference GPU after one step: {d:.3e}"
+    assert H.max_abs(got["s0_final_vel"], g["s0_final_vel"]) <= 10 * H.VEL_ATOL
