@@ -216,8 +216,15 @@ def run_ours(args, rank, world, local_rank):
 
     if args.quick:
         if rank == 0:
+            stages = {}
+            if not os.environ.get("PS_NO_GRAPH"):  # under ncu (PS_NO_GRAPH=1) keep the launch list to the plain steps
+                for _ in range(3):
+                    st, _ln = sol.step_profiled(DT)
+                    for k, v in st.items():
+                        stages[k] = round(stages.get(k, 0.0) + v / 3 / (1 if k in ("predict", "velocity") else ITERS), 4)
             print(json.dumps({"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True, "clocks": clocks}), flush=True)
+                              "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True, "lib": os.environ.get("PS_LIBRARY", "default"),
+                              "stage_ms_per_launch": stages, "clocks": clocks}), flush=True)
         ps.close()
         if dist is not None:
             dist.destroy_process_group()

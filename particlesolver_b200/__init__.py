@@ -56,10 +56,11 @@ def lib():
     """The loaded libpsolver.so.  Raises if the extension has not been built: there is no fallback."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m particlesolver_b200.build` "
+        path = os.environ.get("PS_LIBRARY", LIB_PATH)  # tuning builds (build.build_variant); always a libpsolver build
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: build it with `python -m particlesolver_b200.build` "
                               "(sm_100a CUDA extension; there is no CPU or PyTorch fallback)")
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
         vp, u64, u32, i32, f32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_float
         L.ps_last_error.restype = C.c_char_p
         L.ps_version.restype = C.c_char_p

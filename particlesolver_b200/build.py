@@ -28,6 +28,19 @@ def _newer(src, dst, extra=()):
     return any(os.path.getmtime(p) > t for p in (src, *extra) if os.path.exists(p))
 
 
+def build_variant(name, defines, verbose=False):
+    """Tuning aid: libpsolver_<name>.so with extra -D flags (loaded through PS_LIBRARY, see __init__.lib)."""
+    global OUT, OBJ, NVCC_FLAGS
+    saved = (OUT, OBJ, NVCC_FLAGS)
+    try:
+        OUT = os.path.join(HERE, f"libpsolver_{name}.so")
+        OBJ = os.path.join(HERE, "build", "variant_" + name)
+        NVCC_FLAGS = NVCC_FLAGS + ["-D" + d for d in defines]
+        return build_all(force=False, verbose=verbose)
+    finally:
+        OUT, OBJ, NVCC_FLAGS = saved
+
+
 def build_all(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
@@ -66,4 +79,7 @@ def build_all(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_all(force="--force" in sys.argv, verbose=True))
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":  # python -m particlesolver_b200.build --variant q16 PS_KQ=16 ...
+        print(build_variant(sys.argv[2], sys.argv[3:], verbose=False))
+    else:
+        print(build_all(force="--force" in sys.argv, verbose=True))

@@ -45,6 +45,7 @@ struct GridDesc {
 struct StencilDesc {
     int rad;
     signed char xr[(2 * PS_MAX_RAD + 1) * (2 * PS_MAX_RAD + 1)];
+    u32 rowmask[2 * PS_MAX_RAD + 1];  // per dz: bit (dy+rad) set when xr >= 0
 };
 
 struct WorldDesc {

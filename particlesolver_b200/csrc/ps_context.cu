@@ -116,6 +116,7 @@ void ps_ctx_refresh_descs(PsCtx *c) {
             int xr = -1;
             if (rem >= 0.0) xr = std::min(st.rad, 1 + (int)floor(sqrt(rem) / g.cx + 1e-4));
             st.xr[(dz + st.rad) * w + (dy + st.rad)] = (signed char)xr;
+            if (xr >= 0) st.rowmask[dz + st.rad] |= 1u << (dy + st.rad);
         }
 }
 

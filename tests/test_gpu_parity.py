@@ -196,3 +196,55 @@ def test_reference_host_on_libpsolver_matches_reference_gpu_golden(scene, tmp_pa
     d = H.max_abs(got["s0_final_pos"], g["s0_final_pos"])
     assert d <= 10 * H.POS_ATOL, f"scene {scene}: reference host on libpsolver vs reference GPU after one step: {d:.3e}"
     assert H.max_abs(got["s0_final_vel"], g["s0_final_vel"]) <= 10 * H.VEL_ATOL
+
+
+def _random_fluid(n, box, seed, lo=(0.0, 0.0, 0.0)):
+    rng = np.random.default_rng(seed)
+    pos = np.ones((n, 4), np.float32)
+    pos[:, :3] = (np.asarray(lo) + rng.uniform(0, 1, size=(n, 3)) * np.asarray(box)).astype(np.float32)
+    return pos
+
+
+@pytest.mark.parametrize("cell,grid,lo", [
+    (0.5, 64, (-6.0, 1.0, -6.0)),     # reference geometry, block straddling x = 0 / z = 0: rows wrap around the '&' grid
+    (1.0, 32, (-5.0, 1.0, -5.0)),     # stencil radius 2 (generic, non-unrolled walk)
+    (0.4, 64, (-5.0, 1.0, -5.0)),     # non-power-of-two cell: approximate divide in the cell assignment, radius 5
+    (0.25, 128, (1.0, 1.0, 1.0)),     # radius 8 (largest supported)
+])
+def test_fluid_walk_other_cell_sizes_and_wrap(cell, grid, lo):
+    """K6/K7 against the oracle on a jittered random fluid for stencil radii other than the reference's 4, for a
+    non-power-of-two cell size and for rows that wrap around the grid: identical neighbour counts (the per-particle
+    pruning must never drop a neighbour), lambda and positions within tolerance."""
+    n = 6000
+    p = psb.default_params()
+    p.grid_size[:] = (grid, grid, grid)
+    p.cell_size[:] = (cell, cell, cell)
+    sol = psb.Solver(p, max_particles=n)
+    pos = _random_fluid(n, (10.0, 6.0, 10.0), seed=int(cell * 100), lo=lo)  # ~10 particles per unit^3 -> ~330 neighbours
+    sol.append(pos, np.zeros((n, 4), np.float32), np.ones(n, np.float32), np.full(n, 8.0, np.float32), np.zeros(n, np.int32))
+    o = H.oracle_from_solver(sol)
+    sol.build_grid(); o.build_grid()
+    H.assert_grid_equal(sol, o, f"cell {cell}")
+    sol.solve_fluid(); o.solve_fluids()
+    assert np.array_equal(sol.download(psb.ARR_NUM_NEIGHBORS), o.nn)
+    assert o.nn.max() > 100
+    np.testing.assert_allclose(sol.download(psb.ARR_LAMBDA), o.lam, rtol=H.LAMBDA_RTOL, atol=1e-5)
+    assert H.max_abs(sol.download(psb.ARR_POS), o.pos) <= H.POS_ATOL
+    sol.close()
+
+
+def test_fluid_neighbour_cap_500():
+    """More than 500 particles inside H: the first 500 in the reference's traversal order count (integration_kernel.cuh:508-513)."""
+    n = 3000
+    p = psb.default_params()
+    sol = psb.Solver(p, max_particles=n)
+    pos = _random_fluid(n, (3.0, 3.0, 3.0), seed=5, lo=(2.0, 2.0, 2.0))  # ~110 per unit^3 -> thousands within H
+    sol.append(pos, np.zeros((n, 4), np.float32), np.ones(n, np.float32), np.full(n, 100.0, np.float32), np.zeros(n, np.int32))
+    o = H.oracle_from_solver(sol)
+    sol.build_grid(); o.build_grid()
+    sol.solve_fluid(); o.solve_fluids()
+    nn = sol.download(psb.ARR_NUM_NEIGHBORS)
+    assert nn.max() == 500 and np.array_equal(nn, o.nn)
+    np.testing.assert_allclose(sol.download(psb.ARR_LAMBDA), o.lam, rtol=H.LAMBDA_RTOL, atol=1e-5)
+    assert H.max_abs(sol.download(psb.ARR_POS), o.pos) <= H.POS_ATOL
+    sol.close()
