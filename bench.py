@@ -8,6 +8,11 @@ Workload (config.workload): "c3" = the reference's GPU scene 7 (fluid blob with 
 tension", gpu/src/particleapp.cpp:172-176) scaled to 100^3 = 1,000,000 PBF particles on a 256^3 grid, 5 solver
 iterations, dt = 1/60 — BASELINE.json configs[2], SURVEY.md §8 C3.  One "step" = one ParticleSystem::update.
 
+N > 1 (torchrun, one rank per GPU): "c5" = synthetic PBF dam break, 64,000,000 particles in total (640 x 250 x 400
+lattice, spacing 2.5 r, rho0 4.1), slab-decomposed along x over the N GPUs (particlesolver_b200/slab.py): ghost halo
+refreshed every solver iteration and particle migration every step, both as neighbour send/recv over NCCL —
+BASELINE.json configs[4], SURVEY.md §8 C5.  --particles scales the block in x (total = nx x 250 x 400).
+
 Own arm (default):
   value     whole-job particle-steps/s, state resident in HBM, K steps timed with CUDA events on the solver's
             stream (CUDA-graph replay), max over ranks.
@@ -320,12 +325,184 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+C5_NY, C5_NZ = 250, 400          # lattice sites in y and z: 100,000 particles per x-plane
+C5_SPACING, C5_RHO0 = 0.625, 4.1
+
+
+def run_slabs(args, rank, world, local_rank):
+    """Config C5: dam break, slab-decomposed over the ranks (one GPU each).  Also runs on one GPU (--workload c5)."""
+    import math
+    import torch
+    import particlesolver_b200 as psb
+    from particlesolver_b200 import slab
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the solver has no CPU path")
+    torch.cuda.set_device(local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    plane = C5_NY * C5_NZ
+    nx = max(world, int(round(args.particles / plane / world)) * world)
+    total = nx * plane
+    ix0, ix1 = rank * nx // world, (rank + 1) * nx // world
+    n_mine = (ix1 - ix0) * plane
+    cuts = slab.uniform_cuts(0.0, nx * C5_SPACING, world)
+    drift = 0.25
+    halo_cells = int(math.ceil((2 * slab.H + 2 * drift) / 0.5)) + 1
+    slab_cells = int(math.ceil((ix1 - ix0) * C5_SPACING / 0.5))
+    gx = 1 << int(math.ceil(math.log2(slab_cells + 2 * halo_cells + 8)))  # no aliasing inside a slab + its halo
+    p = psb.default_params()
+    p.grid_size[:] = (gx, 512, 512)
+    p.min_bounds[:] = (0, 0, 0)
+    p.max_bounds[:] = (int(2 * nx * C5_SPACING), 256, int(C5_NZ * C5_SPACING))
+    p.solver_iterations = ITERS
+    halo_cap = int(plane * (2 * slab.H + 2 * drift + 2.0) / C5_SPACING)      # particles within the halo width of a face, with slack
+    cap = n_mine + 2 * halo_cap + n_mine // 8
+    sol = psb.Solver(p, max_particles=cap, device=local_rank)
+    step_planes = max(1, (4_000_000 // plane))
+    for a in range(ix0, ix1, step_planes):  # host generation in chunks of ~4M particles
+        pos, vel, w, ros, phase = slab.dam_break_block(nx, C5_NY, C5_NZ, ix0=a, ix1=min(a + step_planes, ix1), spacing=C5_SPACING,
+                                                       rest_density=C5_RHO0)
+        sol.append(pos, vel, w, ros, phase)
+    assert sol.n == n_mine
+    eng = slab.CtxEngine(sol, halo_capacity=halo_cap, migrant_capacity=max(plane * 2, 1 << 16))
+    comm = slab.DistComm(eng) if world > 1 else None
+    dom = slab.SlabDomain(eng, rank, world, cuts, drift=drift, comm=comm)
+
+    def step():
+        if world > 1:
+            dom.step(DT)
+        else:  # one slab: no neighbours, no ghosts
+            dom.begin(DT)
+            for it in range(ITERS):
+                dom.solve(it)
+            dom.finish(DT)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sol.sync()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    sent0 = comm.bytes_sent if comm else 0
+    sol.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms = sol.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = reduce(ms, dist.ReduceOp.MAX)
+    value = total * args.steps / (ms * 1e-3)
+    sent = reduce((comm.bytes_sent - sent0) if comm else 0, dist.ReduceOp.SUM) / max(args.steps, 1)
+    ghosts = reduce(dom.stats["ghosts"], dist.ReduceOp.SUM)
+    owned_min, owned_max = reduce(sol.n_owned, dist.ReduceOp.MIN), reduce(sol.n_owned, dist.ReduceOp.MAX)
+    # kernels launched per step and rank: predict 1 + iterations x (grid build 4 + passes, lambda, delta_p, world, halo select/pack/unpack 4)
+    # + migration (select 2 [+ pack 1 + compaction 6 + append 1 when particles leave / arrive]) + velocity 1
+    passes = 4 if gx * 512 * 512 > (1 << 24) else 3
+    launches_per_step = 1 + ITERS * (4 + passes + 3 + (4 if world > 1 else 0)) + (2 if world > 1 else 0) + 1
+
+    # ---- end to end: the step's inputs come from pinned host memory, its result goes back to it ----
+    n_cap = cap
+    hpos = torch.empty((n_cap, 4), dtype=torch.float32).pin_memory()
+    hvel = torch.empty((n_cap, 4), dtype=torch.float32).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        k = sol.n_owned
+        sol.upload_async(psb.ARR_POS, hpos.data_ptr(), 4 * k)
+        sol.upload_async(psb.ARR_VEL, hvel.data_ptr(), 4 * k)
+        step()
+        k = sol.n_owned
+        sol.download_async(psb.ARR_POS, hpos.data_ptr(), 4 * k)
+        sol.download_async(psb.ARR_VEL, hvel.data_ptr(), 4 * k)
+        sol.sync()
+
+    k0 = sol.n_owned
+    sol.download_async(psb.ARR_POS, hpos.data_ptr(), 4 * k0)
+    sol.download_async(psb.ARR_VEL, hvel.data_ptr(), 4 * k0)
+    sol.sync()
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = reduce(e2e_ms, dist.ReduceOp.MAX)
+    e2e_value = total * e2e_steps / (e2e_ms * 1e-3)
+
+    # ---- per-stage device times on this rank (events around every stage call of a few extra steps) ----
+    acc = {}
+
+    class Timed:
+        def __init__(self, e): self.e = e
+        def __getattr__(self, name):
+            f = getattr(self.e, name)
+            if name not in ("predict", "build_grid", "solve_contacts", "solve_fluid", "collide_world", "update_velocity", "pack_halo",
+                            "set_ghosts", "pack_migrants", "append_migrants"):
+                return f
+            def g(*a, **k):
+                sol.timer_start(); r = f(*a, **k); acc[name] = acc.get(name, 0.0) + sol.timer_stop(); return r
+            return g
+    prof_steps = 2
+    dom.eng = Timed(eng)
+    for _ in range(prof_steps):
+        step()
+    dom.eng = eng
+    peak, peak_kind = measured_peaks()
+    n_local = sol.n  # owned + ghosts: what the kernels process
+    fluid_ms = acc.get("solve_fluid", 0.0) / prof_steps / ITERS
+    fluid_bytes = (36 + 64) * n_local  # K6 + K7, SURVEY 8(d)
+    stage_ms = {k: round(v / prof_steps, 4) for k, v in acc.items()}
+    roofline = {"kernel": "lambda+delta_p (solve_fluid stage: k_find_lambdas + k_solve_fluids)", "bound": "hbm",
+                "achieved": round(fluid_bytes / (fluid_ms * 1e-3) / 1e9, 1) if fluid_ms else None, "peak": peak, "unit": "GB/s",
+                "frac": round(fluid_bytes / (fluid_ms * 1e-3) / 1e9 / peak, 4) if fluid_ms else None, "traffic": None, "peak_kind": peak_kind,
+                "note": "rank 0, owned + ghost particles; the neighbour kernels are FP32-issue bound, not HBM bound (DESIGN.md section 4)"}
+    if rank == 0:
+        line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"c5: synthetic PBF dam break, {total} particles ({nx} x {C5_NY} x {C5_NZ} lattice, spacing 2.5 r, rho0 4.1), "
+                                       f"{world} x-slab(s), ghost halo {2 * slab.H + 2 * drift} wide refreshed every solver iteration, migration every step, "
+                                       f"per-rank grid {gx} x 512 x 512, 5 solver iterations, dt=1/60",
+                           "particles_total": total, "particles_per_gpu": [int(owned_min), int(owned_max)], "ghosts_total": int(ghosts),
+                           "exchange": "torch.distributed send/recv over NCCL between neighbouring ranks" if world > 1 else "none",
+                           "exchange_bytes_per_step": int(sent), "l2": "per-rank working set >> 126 MB L2; no flush"},
+                "particle_iterations_per_s": value * ITERS,
+                "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 32 * total, "d2h_bytes_per_step": 32 * total,
+                        "ms_per_step": e2e_ms / e2e_steps},
+                "gpu_launches": launches_per_step * args.steps * world,
+                "roofline": roofline, "stage_ms_per_step_rank0": stage_ms,
+                "cpu_baseline": None if world > 1 else "see the c3 line (bench.py without --workload)",
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    sol.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c5"], help="auto: c3 on one GPU, c5 (slabs) on several")
+    ap.add_argument("--particles", type=int, default=64_000_000, help="c5: total particle count over all ranks (rounded to whole lattice planes)")
     ap.add_argument("--quick", action="store_true", help="resident timing only (for runs under ncu): no e2e, no per-stage pass, no CPU baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -333,6 +510,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif world > 1 or args.workload == "c5":
+        run_slabs(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

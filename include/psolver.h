@@ -150,9 +150,29 @@ void *ps_stream(PsCtx *ctx);
 /* number of kernel launches issued by the last ps_step (counted at capture time) */
 uint32_t ps_launches_per_step(PsCtx *ctx);
 
-/* ---- spatial slab decomposition (multi-GPU; one context per GPU, exchange done by the caller over NCCL) ----
- * A context holds `owned` particles followed by `ghost` particles (copies of neighbours' particles within the
- * halo of the slab faces).  Ghosts take part in grid build and as neighbours, but are never moved. */
+/* ---- spatial slab decomposition (multi-GPU; one context per GPU; the exchange itself is the caller's: NCCL
+ * send/recv of the record buffers between neighbouring ranks, see particlesolver_b200/slab.py) ----
+ * A context owns the particles whose x lies in its slab [x_lo, x_hi) and holds them first in every array, followed by
+ * `ghost` copies of the neighbours' particles near the two faces.  Ghosts take part in the grid build and are read as
+ * neighbours (their lambda is computed locally, which is exact for ghosts within H of a face when the halo is 2H wide),
+ * but they are never moved and never written back.  Use +-INFINITY for the outer faces of the first / last slab.
+ * All buffers are DEVICE pointers of `capacity_records` records; counts are returned on the host (the calls
+ * synchronise the context's stream).  Record order is ascending particle index, so runs are reproducible.
+ * Slab contexts hold no distance / point constraints (PS_ERR_STATE otherwise) and are stepped stage by stage. */
+#define PS_HALO_RECORD_BYTES 32u    /* float4 pos | float inv_mass | float rest_density | int32 phase | pad */
+#define PS_MIGRANT_RECORD_BYTES 64u /* float4 pos | float4 prev | float4 vel | float inv_mass | float rest_density | int32 phase | pad */
+/* records of the OWNED particles with x < x_lo + width (-> left_buf) and with x >= x_hi - width (-> right_buf) */
+int ps_slab_pack_halo(PsCtx *ctx, float x_lo, float x_hi, float width, void *left_buf, void *right_buf, uint64_t capacity_records,
+                      uint32_t counts[2]);
+/* replaces the ghosts by the records received from the left and right neighbours (left first) */
+int ps_slab_set_ghosts(PsCtx *ctx, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right);
+/* removes the owned particles with x < x_lo (-> left_buf) or x >= x_hi (-> right_buf), keeping the order of the rest;
+ * drops the ghosts.  Call it after ps_predict: prev / vel travel with the particle. */
+int ps_slab_pack_migrants(PsCtx *ctx, float x_lo, float x_hi, void *left_buf, void *right_buf, uint64_t capacity_records, uint32_t counts[2]);
+/* appends received migrants as owned particles (left neighbour's first) */
+int ps_slab_append_migrants(PsCtx *ctx, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right);
+/* lambda is computed for owned particles and for ghosts with x in [x_min, x_max] only (default: everywhere) */
+int ps_slab_set_lambda_range(PsCtx *ctx, float x_min, float x_max);
 int ps_set_ghost_count(PsCtx *ctx, uint64_t ghosts);
 uint64_t ps_num_owned(PsCtx *ctx);
 #ifdef __cplusplus

@@ -104,6 +104,11 @@ def lib():
         L.ps_stream.argtypes = [vp]
         L.ps_stream.restype = vp
         L.ps_set_ghost_count.argtypes = [vp, u64]
+        L.ps_slab_pack_halo.argtypes = [vp, f32, f32, f32, vp, vp, u64, C.POINTER(u32 * 2)]
+        L.ps_slab_set_ghosts.argtypes = [vp, vp, u64, vp, u64]
+        L.ps_slab_pack_migrants.argtypes = [vp, f32, f32, vp, vp, u64, C.POINTER(u32 * 2)]
+        L.ps_slab_append_migrants.argtypes = [vp, vp, u64, vp, u64]
+        L.ps_slab_set_lambda_range.argtypes = [vp, f32, f32]
         # C++ host class (csrc/particle_system.cpp)
         L.pshost_create.argtypes = [f32, u32, u32, u32, u32, vp, vp, i32]
         L.pshost_create.restype = vp
@@ -302,6 +307,38 @@ class Solver:
 
     def set_ghost_count(self, g):
         _check(lib().ps_set_ghost_count(self._h, g))
+
+    # --- slab decomposition (device pointers in, counts out; see particlesolver_b200/slab.py) ---
+    @property
+    def n_owned(self):
+        return int(lib().ps_num_owned(self._h))
+
+    def slab_pack_halo(self, x_lo, x_hi, width, left_ptr, right_ptr, capacity):
+        c = (C.c_uint32 * 2)()
+        _check(lib().ps_slab_pack_halo(self._h, x_lo, x_hi, width, left_ptr, right_ptr, capacity, C.byref(c)))
+        return int(c[0]), int(c[1])
+
+    def slab_set_ghosts(self, left_ptr, n_left, right_ptr, n_right):
+        _check(lib().ps_slab_set_ghosts(self._h, left_ptr, n_left, right_ptr, n_right))
+
+    def slab_pack_migrants(self, x_lo, x_hi, left_ptr, right_ptr, capacity):
+        c = (C.c_uint32 * 2)()
+        _check(lib().ps_slab_pack_migrants(self._h, x_lo, x_hi, left_ptr, right_ptr, capacity, C.byref(c)))
+        return int(c[0]), int(c[1])
+
+    def slab_append_migrants(self, left_ptr, n_left, right_ptr, n_right):
+        _check(lib().ps_slab_append_migrants(self._h, left_ptr, n_left, right_ptr, n_right))
+
+    def slab_set_lambda_range(self, x_min, x_max):
+        _check(lib().ps_slab_set_lambda_range(self._h, max(x_min, -3.0e38), min(x_max, 3.0e38)))
+
+    def download_owned(self, which):
+        """The owned particles' part of a per-particle array (ghosts follow them)."""
+        n = self.n_owned * _ARR_WIDTH.get(which, 1)
+        a = np.empty(n, dtype=_ARR_DTYPE[which])
+        _check(lib().ps_download(self._h, which, _ptr(a), 0, n))
+        w = _ARR_WIDTH.get(which, 1)
+        return a.reshape(-1, w) if w > 1 else a
 
 
 class ParticleSystem:

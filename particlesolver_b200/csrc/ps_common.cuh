@@ -114,8 +114,23 @@ void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool 
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                        const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, cudaStream_t s);
 void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
-                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st,
-                            bool zero_nonfluid, cudaStream_t s);
+                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
+                            const StencilDesc &st, bool zero_nonfluid, cudaStream_t s);
 void ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
                             const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
                             cudaStream_t s);
+// ps_slab_kernels.cu — slab decomposition: ordered selection / packing / compaction
+size_t ps_slab_scratch_elems(u32 n);
+void ps_launch_slab_select(const float4 *pos, u32 n, float left_below, float right_from, u32 *scratch, cudaStream_t s);
+void ps_launch_slab_pack_halo(const float4 *pos, const float *w, const float *ros, const int *phase, u32 n, float left_below, float right_from,
+                              const u32 *scratch, void *left, void *right, u32 cap, cudaStream_t s);
+void ps_launch_slab_unpack_halo(float4 *pos, float *w, float *ros, int *phase, u32 first, const void *from_left, u32 n_left, const void *from_right,
+                                u32 n_right, cudaStream_t s);
+void ps_launch_slab_pack_migrants(const float4 *pos, const float4 *prev, const float4 *vel, const float *w, const float *ros, const int *phase, u32 n,
+                                  float left_below, float right_from, const u32 *scratch, void *left, void *right, u32 cap, cudaStream_t s);
+void ps_launch_slab_compact4(const float4 *pos, const float4 *src, float4 *dst, u32 n, float left_below, float right_from, const u32 *scratch,
+                             cudaStream_t s);
+void ps_launch_slab_compact1(const float4 *pos, const u32 *src, u32 *dst, u32 n, float left_below, float right_from, const u32 *scratch,
+                             cudaStream_t s);
+void ps_launch_slab_append_migrants(float4 *pos, float4 *prev, float4 *vel, float *w, float *ros, int *phase, u32 first, const void *from_left,
+                                    u32 n_left, const void *from_right, u32 n_right, cudaStream_t s);

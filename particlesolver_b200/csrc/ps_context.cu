@@ -250,9 +250,10 @@ extern "C" int ps_destroy(PsCtx *c) {
     if (c->gen) curandDestroyGenerator(c->gen);
     void *ptrs[] = {c->pos, c->vel, c->prev, c->spos, c->w, c->ros, c->sw, c->lambda, c->phase, c->sphase, c->hash, c->index, c->hash_tmp,
                     c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->chunk_lb, c->sort_hist,
-                    c->sort_status, c->sort_ticket, c->rands, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
+                    c->sort_status, c->sort_ticket, c->rands, c->slab_scratch, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
                     c->d_point_xyz, c->dist_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->slab_counts_host) cudaFreeHost(c->slab_counts_host);
     if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -469,9 +470,9 @@ extern "C" int ps_solve_fluid(PsCtx *c) {
     int r = ready(c); if (r != PS_OK) return r;
     if (c->n && !c->grid_valid) { ps_set_error("ps_solve_fluid: no grid (call ps_build_grid)"); return PS_ERR_STATE; }
     DeviceGuard dg(c->device);
-    // lambda is needed for ghosts too (their owners are on another GPU): n_owned = n for K6
-    ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n, c->grid,
-                           c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->stream);
+    // lambda is needed for the ghosts next to a face too (their owners are on another GPU): see ps_slab_set_lambda_range
+    ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost,
+                           c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->stream);
     ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost, c->grid, c->stencil,
                            c->params.omega, c->stream);
     return check_launch("ps_solve_fluid");
@@ -523,8 +524,8 @@ static u32 issue_step(PsCtx *c, float dt) {
             launches++;
         }
         if (has_fluid) {
-            ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid,
-                                   c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s);
+            ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned,
+                                   c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s);
             ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned, c->grid, c->stencil,
                                    p.omega, s);
             launches += 2;
@@ -611,8 +612,8 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
         c->ref_tables_valid = false;
         if (has_contact) { ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, s); mark(5, 1); }
         if (has_fluid) {
-            ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil,
-                                   (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s); mark(6, 1);
+            ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->lambda_xmin,
+                                   c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s); mark(6, 1);
             ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil, p.omega, s); mark(7, 1);
         }
         ps_launch_collide_world(c->pos, c->prev, c->phase, n, c->rands + 6 * it, c->world, s); mark(8, 1);
@@ -736,5 +737,102 @@ extern "C" int ps_set_ghost_count(PsCtx *c, uint64_t ghosts) {
     c->n_ghost = (u32)ghosts;
     c->h_occ.resize(c->n, 0u);
     c->grid_valid = false;
+    return PS_OK;
+}
+
+static int slab_ready(PsCtx *c, const char *what) {
+    NEED(c);
+    if (!c->h_dist_rest.empty() || !c->h_point_idx.empty()) { ps_set_error("%s: slab contexts cannot hold distance / point constraints (particle indices change)", what); return PS_ERR_STATE; }
+    const size_t need = ps_slab_scratch_elems((u32)c->capacity);
+    if (need > c->slab_scratch_elems) {
+        if (c->slab_scratch) CU(cudaFree(c->slab_scratch));
+        CU(cudaMalloc((void **)&c->slab_scratch, need * sizeof(u32)));
+        c->slab_scratch_elems = need;
+    }
+    if (!c->slab_counts_host) CU(cudaMallocHost((void **)&c->slab_counts_host, 2 * sizeof(u32)));
+    return PS_OK;
+}
+static int slab_fetch_counts(PsCtx *c, u32 n, uint32_t counts[2]) {
+    const size_t tiles = (ps_slab_scratch_elems(n) - 2) / 2;
+    CU(cudaMemcpyAsync(c->slab_counts_host, c->slab_scratch + 2 * tiles, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    counts[0] = c->slab_counts_host[0];
+    counts[1] = c->slab_counts_host[1];
+    return PS_OK;
+}
+
+extern "C" int ps_slab_pack_halo(PsCtx *c, float x_lo, float x_hi, float width, void *left_buf, void *right_buf, uint64_t cap, uint32_t counts[2]) {
+    int r = slab_ready(c, "ps_slab_pack_halo"); if (r != PS_OK) return r;
+    if (!counts || ((!left_buf || !right_buf) && cap)) { ps_set_error("ps_slab_pack_halo: null argument"); return PS_ERR_INVALID; }
+    DeviceGuard dg(c->device);
+    const u32 owned = c->n - c->n_ghost;
+    const float left_below = x_lo + width, right_from = x_hi - width;
+    ps_launch_slab_select(c->pos, owned, left_below, right_from, c->slab_scratch, c->stream);
+    ps_launch_slab_pack_halo(c->pos, c->w, c->ros, c->phase, owned, left_below, right_from, c->slab_scratch, left_buf, right_buf, (u32)std::min<uint64_t>(cap, 0xffffffffu), c->stream);
+    if ((r = check_launch("ps_slab_pack_halo")) != PS_OK) return r;
+    if ((r = slab_fetch_counts(c, owned, counts)) != PS_OK) return r;
+    if (counts[0] > cap || counts[1] > cap) { ps_set_error("ps_slab_pack_halo: %u / %u records exceed the buffer capacity %llu", counts[0], counts[1], (unsigned long long)cap); return PS_ERR_CAPACITY; }
+    return PS_OK;
+}
+
+extern "C" int ps_slab_set_ghosts(PsCtx *c, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right) {
+    int r = slab_ready(c, "ps_slab_set_ghosts"); if (r != PS_OK) return r;
+    if ((n_left && !from_left) || (n_right && !from_right)) { ps_set_error("ps_slab_set_ghosts: null buffer"); return PS_ERR_INVALID; }
+    if ((r = ps_set_ghost_count(c, n_left + n_right)) != PS_OK) return r;
+    DeviceGuard dg(c->device);
+    ps_launch_slab_unpack_halo(c->pos, c->w, c->ros, c->phase, c->n - c->n_ghost, from_left, (u32)n_left, from_right, (u32)n_right, c->stream);
+    c->census_known = false;  // ghosts may carry any phase
+    return check_launch("ps_slab_set_ghosts");
+}
+
+extern "C" int ps_slab_pack_migrants(PsCtx *c, float x_lo, float x_hi, void *left_buf, void *right_buf, uint64_t cap, uint32_t counts[2]) {
+    int r = slab_ready(c, "ps_slab_pack_migrants"); if (r != PS_OK) return r;
+    if (!counts || ((!left_buf || !right_buf) && cap)) { ps_set_error("ps_slab_pack_migrants: null argument"); return PS_ERR_INVALID; }
+    if (!(x_lo < x_hi)) { ps_set_error("ps_slab_pack_migrants: empty slab [%g, %g)", x_lo, x_hi); return PS_ERR_INVALID; }
+    if ((r = ps_set_ghost_count(c, 0)) != PS_OK) return r;
+    DeviceGuard dg(c->device);
+    cudaStream_t s = c->stream;
+    const u32 n = c->n;
+    ps_launch_slab_select(c->pos, n, x_lo, x_hi, c->slab_scratch, s);
+    if ((r = check_launch("ps_slab_pack_migrants")) != PS_OK) return r;
+    if ((r = slab_fetch_counts(c, n, counts)) != PS_OK) return r;
+    if (counts[0] > cap || counts[1] > cap) { ps_set_error("ps_slab_pack_migrants: %u / %u records exceed the buffer capacity %llu", counts[0], counts[1], (unsigned long long)cap); return PS_ERR_CAPACITY; }
+    const u32 gone = counts[0] + counts[1];
+    if (!gone) return PS_OK;
+    ps_launch_slab_pack_migrants(c->pos, c->prev, c->vel, c->w, c->ros, c->phase, n, x_lo, x_hi, c->slab_scratch, left_buf, right_buf, (u32)std::min<uint64_t>(cap, 0xffffffffu), s);
+    // stable compaction of the stayers, array by array through the sorted-copy scratch (rebuilt by the next grid build);
+    // pos classifies every pass, so it goes last
+    const size_t keep = n - gone;
+    auto c4 = [&](float4 *arr) { ps_launch_slab_compact4(c->pos, arr, c->spos, n, x_lo, x_hi, c->slab_scratch, s); return cudaMemcpyAsync(arr, c->spos, keep * sizeof(float4), cudaMemcpyDeviceToDevice, s); };
+    auto c1 = [&](void *arr) { ps_launch_slab_compact1(c->pos, (const u32 *)arr, c->hash_tmp, n, x_lo, x_hi, c->slab_scratch, s); return cudaMemcpyAsync(arr, c->hash_tmp, keep * sizeof(u32), cudaMemcpyDeviceToDevice, s); };
+    CU(c4(c->prev)); CU(c4(c->vel)); CU(c1(c->w)); CU(c1(c->ros)); CU(c1(c->phase)); CU(c4(c->pos));
+    c->n = (u32)keep;
+    c->h_occ.resize(c->n, 0u);
+    c->census_known = false;
+    c->grid_valid = false;
+    return check_launch("ps_slab_pack_migrants");
+}
+
+extern "C" int ps_slab_append_migrants(PsCtx *c, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right) {
+    int r = slab_ready(c, "ps_slab_append_migrants"); if (r != PS_OK) return r;
+    if ((n_left && !from_left) || (n_right && !from_right)) { ps_set_error("ps_slab_append_migrants: null buffer"); return PS_ERR_INVALID; }
+    if ((r = ps_set_ghost_count(c, 0)) != PS_OK) return r;
+    const uint64_t add = n_left + n_right;
+    if (!add) return PS_OK;
+    if (c->limit && (uint64_t)c->n + add > c->limit) { ps_set_error("ps_slab_append_migrants: %llu + %llu exceeds max_particles", (unsigned long long)c->n, (unsigned long long)add); return PS_ERR_CAPACITY; }
+    DeviceGuard dg(c->device);
+    if ((r = ps_ctx_ensure_capacity(c, (uint64_t)c->n + add)) != PS_OK) return r;
+    ps_launch_slab_append_migrants(c->pos, c->prev, c->vel, c->w, c->ros, c->phase, c->n, from_left, (u32)n_left, from_right, (u32)n_right, c->stream);
+    c->n += (u32)add;
+    c->h_occ.resize(c->n, 0u);
+    c->census_known = false;
+    c->grid_valid = false;
+    return check_launch("ps_slab_append_migrants");
+}
+
+extern "C" int ps_slab_set_lambda_range(PsCtx *c, float x_min, float x_max) {
+    NEED(c);
+    c->lambda_xmin = x_min;
+    c->lambda_xmax = x_max;
     return PS_OK;
 }

@@ -66,6 +66,11 @@ struct PsCtx {
     u32 launch_counter = 0;  // counts launches while a step is being issued
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     bool grid_valid = false;
+    // slab decomposition
+    u32 *slab_scratch = nullptr;
+    size_t slab_scratch_elems = 0;
+    u32 *slab_counts_host = nullptr;  // pinned, 2 words
+    float lambda_xmin = -3.0e38f, lambda_xmax = 3.0e38f;
 };
 
 // internal helpers shared with the reference-ABI shim

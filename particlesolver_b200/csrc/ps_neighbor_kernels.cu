@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
                                                          const float4 *__restrict__ spos, const float *__restrict__ sw,
                                                          const int *__restrict__ sphase, const u32 *__restrict__ index,
                                                          const u32 *__restrict__ cell_begin, const float *__restrict__ ros, u32 n,
-                                                         u32 n_owned, GridDesc g, StencilDesc st, int zero_nonfluid) {
+                                                         u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g, StencilDesc st,
+                                                         int zero_nonfluid) {
     extern __shared__ float4 fluid_smem[];
     for_each_slot(g, cell_begin, n, [&](const u32 i, bool act) {
         u32 orig = 0;
@@ -321,11 +322,15 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
                 act = false;
             } else {
                 orig = index[i];
-                act = orig < n_owned;  // ghost copy of a neighbour slab's particle: its owner computes it
             }
         }
+        float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
+        // ghost copies of a neighbour slab's particles: their lambda is needed by the owned particles next to the face
+        // (K7 reads lambda_j), and it is exact when the halo holds the ghost's whole neighbourhood, i.e. for ghosts
+        // within [ghost_xmin, ghost_xmax]; ghosts further out are never read
+        if (act && orig >= n_owned && !(pi.x >= ghost_xmin && pi.x <= ghost_xmax)) act = false;
         if (!__any_sync(kFull, act)) return;
-        const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
+        if (!act) pi = make_float4(g.ox, g.oy, g.oz, 0.f);
         const float ro0 = act ? ros[orig] : 1.f;
         const float inv_ro0 = __fdividef(1.f, ro0);
         const float cs = -PS_SPIKY * inv_ro0;
@@ -513,8 +518,8 @@ void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, cons
 }
 
 void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
-                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st,
-                            bool zero_nonfluid, cudaStream_t s) {
+                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
+                            const StencilDesc &st, bool zero_nonfluid, cudaStream_t s) {
     if (!n) return;
     const size_t sm = fluid_smem_bytes(st.rad);
     static const cudaError_t optin = cudaFuncSetAttribute(k_find_lambdas<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
@@ -524,10 +529,10 @@ void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spo
     (void)carve;
 #endif
     if (st.rad == 4)  // the reference's configuration (H = 2, cell = 2r = 0.5): stencil loops fully unrolled
-        k_find_lambdas<4><<<fluid_grid(n, g), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, g, st,
+        k_find_lambdas<4><<<fluid_grid(n, g), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin, ghost_xmax, g, st,
                                                              zero_nonfluid ? 1 : 0);
     else
-        k_find_lambdas<0><<<fluid_grid(n, g), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, g, st,
+        k_find_lambdas<0><<<fluid_grid(n, g), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin, ghost_xmax, g, st,
                                                              zero_nonfluid ? 1 : 0);
 }
 

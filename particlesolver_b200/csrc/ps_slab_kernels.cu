@@ -1,0 +1,247 @@
+// particlesolver_b200/csrc/ps_slab_kernels.cu — spatial slab decomposition: ghost-halo packing, particle migration.
+//
+// New work (the reference is single-GPU).  A context owns the particles whose x lies in its slab
+// [x_lo, x_hi) and keeps ghost copies of its neighbours' particles near the two faces behind them in the same SoA
+// arrays (indices [n_owned, n)).  Ghosts take part in the grid build and are read as neighbours; they are never moved.
+// Everything here is ORDERED (a stable stream compaction: flags -> exclusive scan -> scatter), so a run is
+// reproducible and the in-cell neighbour order (ascending original index) does not depend on scheduling.
+//
+//   halo record    32 B : pos4 | w | rest density | phase | pad          (what a neighbour needs of a ghost)
+//   migrant record 64 B : pos4 | prev4 | vel4 | w | rest density | phase | pad   (the full state of a particle)
+#include "ps_common.cuh"
+
+namespace {
+constexpr int kBlock = 256;
+constexpr int kItems = 8;
+constexpr int kTile = kBlock * kItems;  // 2048 particles per CTA
+
+struct HaloRec { float4 pos; float w, ros; int phase; u32 pad; };
+struct MigrantRec { float4 pos, prev, vel; float w, ros; int phase; u32 pad; };
+static_assert(sizeof(HaloRec) == 32 && sizeof(MigrantRec) == 64, "record sizes are part of the wire format");
+
+// class of a particle: 0 = stays / not selected, 1 = left buffer, 2 = right buffer (3 = both, halo of a thin slab)
+__device__ __forceinline__ u32 classify(float x, float left_below, float right_from) { return (x < left_below ? 1u : 0u) | (x >= right_from ? 2u : 0u); }
+
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *sm, u32 &total) {  // exclusive scan over the CTA's threads
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sm[wid] = incl;
+    __syncthreads();
+    u32 base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; w++) {
+        const u32 c = sm[w];
+        if (w < wid) base += c;
+        tot += c;
+    }
+    __syncthreads();
+    total = tot;
+    return base + incl - v;
+}
+
+// pass 1: per-tile counts of class-1 (left) and class-2 (right) particles -> tile_counts[2*tile + {0,1}]
+__global__ void __launch_bounds__(kBlock) k_slab_count(const float4 *__restrict__ pos, u32 n, float left_below, float right_from,
+                                                       u32 *__restrict__ tile_counts) {
+    __shared__ u32 sm[kBlock / 32];
+    const u32 base = blockIdx.x * kTile + threadIdx.x * kItems;
+    u32 cl = 0, cr = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        const u32 i = base + k;
+        if (i < n) {
+            const u32 c = classify(__ldg(&pos[i].x), left_below, right_from);
+            cl += c & 1u;
+            cr += c >> 1;
+        }
+    }
+    u32 tl, tr;
+    block_excl_scan(cl, sm, tl);
+    block_excl_scan(cr, sm, tr);
+    if (threadIdx.x == 0) { tile_counts[2 * blockIdx.x] = tl; tile_counts[2 * blockIdx.x + 1] = tr; }
+}
+
+// pass 2 (one CTA): exclusive scan of the tile counts in place; totals[0..1] = number of left / right records
+__global__ void __launch_bounds__(1024) k_slab_scan_tiles(u32 *__restrict__ tile_counts, u32 tiles, u32 *__restrict__ totals) {
+    __shared__ u32 sm[2][32];
+    __shared__ u32 carry[2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x < 2) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 t0 = 0; t0 < tiles; t0 += 1024) {
+        const u32 t = t0 + threadIdx.x;
+        u32 v[2] = {t < tiles ? tile_counts[2 * t] : 0u, t < tiles ? tile_counts[2 * t + 1] : 0u};
+        u32 incl[2] = {v[0], v[1]};
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 a = __shfl_up_sync(0xffffffffu, incl[0], o), b = __shfl_up_sync(0xffffffffu, incl[1], o);
+            if (lane >= o) { incl[0] += a; incl[1] += b; }
+        }
+        if (lane == 31) { sm[0][wid] = incl[0]; sm[1][wid] = incl[1]; }
+        __syncthreads();
+        u32 base[2] = {carry[0], carry[1]}, tot[2] = {0, 0};
+        for (int w = 0; w < 32; w++) {
+            if (w < wid) { base[0] += sm[0][w]; base[1] += sm[1][w]; }
+            tot[0] += sm[0][w]; tot[1] += sm[1][w];
+        }
+        if (t < tiles) { tile_counts[2 * t] = base[0] + incl[0] - v[0]; tile_counts[2 * t + 1] = base[1] + incl[1] - v[1]; }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry[0] += tot[0]; carry[1] += tot[1]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { totals[0] = carry[0]; totals[1] = carry[1]; }
+}
+
+// pass 3a: halo records of the selected particles, in ascending particle index
+__global__ void __launch_bounds__(kBlock) k_slab_pack_halo(const float4 *__restrict__ pos, const float *__restrict__ w, const float *__restrict__ ros,
+                                                           const int *__restrict__ phase, u32 n, float left_below, float right_from,
+                                                           const u32 *__restrict__ tile_offsets, HaloRec *__restrict__ left, HaloRec *__restrict__ right,
+                                                           u32 cap) {
+    __shared__ u32 sm[kBlock / 32];
+    const u32 base = blockIdx.x * kTile + threadIdx.x * kItems;
+    u32 cls[kItems], cl = 0, cr = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        const u32 i = base + k;
+        cls[k] = i < n ? classify(__ldg(&pos[i].x), left_below, right_from) : 0u;
+        cl += cls[k] & 1u;
+        cr += cls[k] >> 1;
+    }
+    u32 dummy;
+    u32 ol = tile_offsets[2 * blockIdx.x] + block_excl_scan(cl, sm, dummy);
+    u32 orr = tile_offsets[2 * blockIdx.x + 1] + block_excl_scan(cr, sm, dummy);
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        if (!cls[k]) continue;
+        const u32 i = base + k;
+        HaloRec r;
+        r.pos = pos[i]; r.w = w[i]; r.ros = ros[i]; r.phase = phase[i]; r.pad = 0;
+        if (cls[k] & 1u) { if (ol < cap) left[ol] = r; ol++; }
+        if (cls[k] & 2u) { if (orr < cap) right[orr] = r; orr++; }
+    }
+}
+
+// ghosts received from the two neighbours -> the tails of the SoA arrays, left neighbour's first
+__global__ void __launch_bounds__(kBlock) k_slab_unpack_halo(float4 *__restrict__ pos, float *__restrict__ w, float *__restrict__ ros, int *__restrict__ phase,
+                                                             u32 first, const HaloRec *__restrict__ from_left, u32 n_left,
+                                                             const HaloRec *__restrict__ from_right, u32 n_right) {
+    const u32 k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= n_left + n_right) return;
+    const HaloRec r = k < n_left ? from_left[k] : from_right[k - n_left];
+    const u32 i = first + k;
+    pos[i] = r.pos; w[i] = r.w; ros[i] = r.ros; phase[i] = r.phase;
+}
+
+// pass 3b: migrant records (class 1 -> left, class 2 -> right; a particle cannot be both: x_lo < x_hi)
+__global__ void __launch_bounds__(kBlock) k_slab_pack_migrants(const float4 *__restrict__ pos, const float4 *__restrict__ prev, const float4 *__restrict__ vel,
+                                                               const float *__restrict__ w, const float *__restrict__ ros, const int *__restrict__ phase,
+                                                               u32 n, float left_below, float right_from, const u32 *__restrict__ tile_offsets,
+                                                               MigrantRec *__restrict__ left, MigrantRec *__restrict__ right, u32 cap) {
+    __shared__ u32 sm[kBlock / 32];
+    const u32 base = blockIdx.x * kTile + threadIdx.x * kItems;
+    u32 cls[kItems], cl = 0, cr = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        const u32 i = base + k;
+        cls[k] = i < n ? classify(__ldg(&pos[i].x), left_below, right_from) : 0u;
+        cl += cls[k] & 1u;
+        cr += cls[k] >> 1;
+    }
+    u32 dummy;
+    u32 ol = tile_offsets[2 * blockIdx.x] + block_excl_scan(cl, sm, dummy);
+    u32 orr = tile_offsets[2 * blockIdx.x + 1] + block_excl_scan(cr, sm, dummy);
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        if (!cls[k]) continue;
+        const u32 i = base + k;
+        MigrantRec r;
+        r.pos = pos[i]; r.prev = prev[i]; r.vel = vel[i]; r.w = w[i]; r.ros = ros[i]; r.phase = phase[i]; r.pad = 0;
+        if (cls[k] & 1u) { if (ol < cap) left[ol] = r; ol++; }
+        else { if (orr < cap) right[orr] = r; orr++; }
+    }
+}
+
+// stable compaction of the stayers: element i moves to i - (#migrants before i).  tile_offsets holds the exclusive
+// left/right migrant counts per tile, so the destination is known without another scan.
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_slab_compact(const float4 *__restrict__ pos, const T *__restrict__ src, T *__restrict__ dst, u32 n,
+                                                         float left_below, float right_from, const u32 *__restrict__ tile_offsets) {
+    __shared__ u32 sm[kBlock / 32];
+    const u32 base = blockIdx.x * kTile + threadIdx.x * kItems;
+    u32 cls[kItems], gone = 0;
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        const u32 i = base + k;
+        cls[k] = i < n ? classify(__ldg(&pos[i].x), left_below, right_from) : 0u;
+        gone += cls[k] ? 1u : 0u;
+    }
+    u32 dummy;
+    u32 before = tile_offsets[2 * blockIdx.x] + tile_offsets[2 * blockIdx.x + 1] + block_excl_scan(gone, sm, dummy);
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        const u32 i = base + k;
+        if (i >= n) break;
+        if (cls[k]) { before++; continue; }
+        dst[i - before] = src[i];
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_slab_append_migrants(float4 *__restrict__ pos, float4 *__restrict__ prev, float4 *__restrict__ vel, float *__restrict__ w,
+                                                                 float *__restrict__ ros, int *__restrict__ phase, u32 first,
+                                                                 const MigrantRec *__restrict__ from_left, u32 n_left,
+                                                                 const MigrantRec *__restrict__ from_right, u32 n_right) {
+    const u32 k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= n_left + n_right) return;
+    const MigrantRec r = k < n_left ? from_left[k] : from_right[k - n_left];
+    const u32 i = first + k;
+    pos[i] = r.pos; prev[i] = r.prev; vel[i] = r.vel; w[i] = r.w; ros[i] = r.ros; phase[i] = r.phase;
+}
+}  // namespace
+
+static inline u32 cdiv(u32 a, u32 b) { return (a + b - 1) / b; }
+
+size_t ps_slab_scratch_elems(u32 n) { return 2 * (size_t)cdiv(n ? n : 1, kTile) + 2; }
+
+// counts + exclusive tile offsets for the split (x < left_below | x >= right_from); totals land in scratch[2*tiles .. +1]
+void ps_launch_slab_select(const float4 *pos, u32 n, float left_below, float right_from, u32 *scratch, cudaStream_t s) {
+    const u32 tiles = cdiv(n ? n : 1, kTile);
+    k_slab_count<<<tiles, kBlock, 0, s>>>(pos, n, left_below, right_from, scratch);
+    k_slab_scan_tiles<<<1, 1024, 0, s>>>(scratch, tiles, scratch + 2 * tiles);
+}
+void ps_launch_slab_pack_halo(const float4 *pos, const float *w, const float *ros, const int *phase, u32 n, float left_below, float right_from,
+                              const u32 *scratch, void *left, void *right, u32 cap, cudaStream_t s) {
+    if (!n) return;
+    k_slab_pack_halo<<<cdiv(n, kTile), kBlock, 0, s>>>(pos, w, ros, phase, n, left_below, right_from, scratch, (HaloRec *)left, (HaloRec *)right, cap);
+}
+void ps_launch_slab_unpack_halo(float4 *pos, float *w, float *ros, int *phase, u32 first, const void *from_left, u32 n_left, const void *from_right,
+                                u32 n_right, cudaStream_t s) {
+    if (!(n_left + n_right)) return;
+    k_slab_unpack_halo<<<cdiv(n_left + n_right, kBlock), kBlock, 0, s>>>(pos, w, ros, phase, first, (const HaloRec *)from_left, n_left,
+                                                                        (const HaloRec *)from_right, n_right);
+}
+void ps_launch_slab_pack_migrants(const float4 *pos, const float4 *prev, const float4 *vel, const float *w, const float *ros, const int *phase, u32 n,
+                                  float left_below, float right_from, const u32 *scratch, void *left, void *right, u32 cap, cudaStream_t s) {
+    if (!n) return;
+    k_slab_pack_migrants<<<cdiv(n, kTile), kBlock, 0, s>>>(pos, prev, vel, w, ros, phase, n, left_below, right_from, scratch, (MigrantRec *)left,
+                                                          (MigrantRec *)right, cap);
+}
+void ps_launch_slab_compact4(const float4 *pos, const float4 *src, float4 *dst, u32 n, float left_below, float right_from, const u32 *scratch,
+                             cudaStream_t s) {
+    if (!n) return;
+    k_slab_compact<float4><<<cdiv(n, kTile), kBlock, 0, s>>>(pos, src, dst, n, left_below, right_from, scratch);
+}
+void ps_launch_slab_compact1(const float4 *pos, const u32 *src, u32 *dst, u32 n, float left_below, float right_from, const u32 *scratch,
+                             cudaStream_t s) {
+    if (!n) return;
+    k_slab_compact<u32><<<cdiv(n, kTile), kBlock, 0, s>>>(pos, src, dst, n, left_below, right_from, scratch);
+}
+void ps_launch_slab_append_migrants(float4 *pos, float4 *prev, float4 *vel, float *w, float *ros, int *phase, u32 first, const void *from_left,
+                                    u32 n_left, const void *from_right, u32 n_right, cudaStream_t s) {
+    if (!(n_left + n_right)) return;
+    k_slab_append_migrants<<<cdiv(n_left + n_right, kBlock), kBlock, 0, s>>>(pos, prev, vel, w, ros, phase, first, (const MigrantRec *)from_left,
+                                                                            n_left, (const MigrantRec *)from_right, n_right);
+}

@@ -1,0 +1,267 @@
+"""Spatial slab decomposition of one particle system over several GPUs (new work — the reference is
+single-GPU).
+
+One process per GPU.  Rank r owns the particles with x in [cuts[r], cuts[r+1]) and keeps, behind them in the same
+arrays, ghost copies of its neighbours' particles within `halo` of the two faces.  Per step:
+
+    begin      : predict (K1) on the owned particles
+    migrate    : owned particles whose predicted x left the slab move to the neighbour with their full state
+    5 x        : refresh the ghost halo (positions change every solver iteration, and the reference rebuilds its grid
+                 every iteration too), then K2-K8 on owned + ghosts, writing owned particles only
+    finish     : velocity update (K11)
+
+Only the exchange itself happens here (torch.distributed send/recv between neighbouring ranks: NCCL over NVLink on
+the GPU box, gloo in the CPU tests); selection, packing, compaction and unpacking are CUDA kernels behind the C ABI
+(ps_slab_* in include/psolver.h).  There is no data-path collective besides that neighbour exchange.
+
+Halo width.  K7 reads lambda_j of every neighbour j of an owned particle i.  Ghost lambdas are computed locally instead
+of being exchanged: a ghost within H (+ drift) of the face has its whole neighbourhood inside a 2H-wide halo, so its
+local lambda equals its owner's up to summation order.  halo = 2H + 2*drift, lambda range = face +- (H + drift), where
+`drift` bounds how far a particle moves inside the solver iterations of one step (migration runs once per step, right
+after the predict, which is where velocities move particles).
+"""
+import math
+
+import numpy as np
+
+H = 2.0  # PBF support radius, reference gpu/src/cuda/integration_kernel.cuh:25
+HALO_RECORD_BYTES = 32
+MIGRANT_RECORD_BYTES = 64
+
+
+def uniform_cuts(x_min, x_max, nranks):
+    """nranks+1 cut planes: equal-width slabs over [x_min, x_max], outer faces at +-inf."""
+    c = [x_min + (x_max - x_min) * r / nranks for r in range(nranks + 1)]
+    c[0], c[-1] = -math.inf, math.inf
+    return c
+
+
+def quantile_cuts(x, nranks):
+    """Equal-count cut planes from the x coordinates of the initial particle set."""
+    q = np.quantile(np.asarray(x, np.float64), [r / nranks for r in range(1, nranks)]) if nranks > 1 else []
+    return [-math.inf, *[float(v) for v in q], math.inf]
+
+
+class CtxEngine:
+    """GPU engine: a libpsolver context + torch-owned device buffers for the records (so that torch.distributed can
+    send them as they are)."""
+
+    def __init__(self, solver, halo_capacity, migrant_capacity, device=None):
+        import torch
+        self.torch = torch
+        self.sol = solver
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.ExternalStream(solver.stream, device=self.device)  # NCCL ops are ordered against the solver's stream
+        mk = lambda n, b: torch.empty((max(int(n), 1), b), dtype=torch.uint8, device=self.device)
+        self.halo_cap, self.migr_cap = int(halo_capacity), int(migrant_capacity)
+        self.halo_send = (mk(halo_capacity, HALO_RECORD_BYTES), mk(halo_capacity, HALO_RECORD_BYTES))
+        self.migr_send = (mk(migrant_capacity, MIGRANT_RECORD_BYTES), mk(migrant_capacity, MIGRANT_RECORD_BYTES))
+
+    # records in, records out (torch uint8 tensors [count, record_bytes] on the engine's device)
+    def empty_records(self, count, record_bytes):
+        return self.torch.empty((int(count), record_bytes), dtype=self.torch.uint8, device=self.device)
+
+    def pack_halo(self, x_lo, x_hi, width):
+        nl, nr = self.sol.slab_pack_halo(x_lo, x_hi, width, self.halo_send[0].data_ptr(), self.halo_send[1].data_ptr(), self.halo_cap)
+        return self.halo_send[0][:nl], self.halo_send[1][:nr]
+
+    def set_ghosts(self, from_left, from_right):
+        self._keep = (from_left, from_right)  # the unpack kernel is asynchronous: keep the buffers alive
+        self.sol.slab_set_ghosts(from_left.data_ptr() if from_left.shape[0] else None, from_left.shape[0],
+                                 from_right.data_ptr() if from_right.shape[0] else None, from_right.shape[0])
+
+    def pack_migrants(self, x_lo, x_hi):
+        nl, nr = self.sol.slab_pack_migrants(x_lo, x_hi, self.migr_send[0].data_ptr(), self.migr_send[1].data_ptr(), self.migr_cap)
+        return self.migr_send[0][:nl], self.migr_send[1][:nr]
+
+    def append_migrants(self, from_left, from_right):
+        self._keep_m = (from_left, from_right)
+        self.sol.slab_append_migrants(from_left.data_ptr() if from_left.shape[0] else None, from_left.shape[0],
+                                      from_right.data_ptr() if from_right.shape[0] else None, from_right.shape[0])
+
+    def set_lambda_range(self, x_min, x_max):
+        self.sol.slab_set_lambda_range(x_min, x_max)
+
+    # stages
+    def begin_step(self): self.sol.begin_step()
+    def predict(self, dt): self.sol.predict(dt)
+    def build_grid(self): self.sol.build_grid()
+    def solve_contacts(self): self.sol.solve_contacts()
+    def solve_fluid(self): self.sol.solve_fluid()
+    def collide_world(self, it): self.sol.collide_world(it)
+    def update_velocity(self, dt): self.sol.update_velocity(dt)
+    def sync(self): self.sol.sync()
+
+    @property
+    def n_owned(self): return self.sol.n_owned
+
+    @property
+    def iterations(self): return int(self.sol.params.solver_iterations)
+
+
+class DistComm:
+    """Neighbour exchange over torch.distributed (backend nccl on GPUs, gloo on CPU)."""
+
+    def __init__(self, engine, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.eng, self.group = torch, dist, engine, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.count_device = getattr(engine, "device", torch.device("cpu"))
+        self.bytes_sent = 0
+
+    def exchange(self, to_left, to_right, record_bytes):
+        """Send `to_left` to rank-1 and `to_right` to rank+1; returns (from_left, from_right)."""
+        torch, dist = self.torch, self.dist
+        mine = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=self.count_device)
+        allc = torch.empty((self.world, 2), dtype=torch.int64, device=self.count_device)
+        dist.all_gather_into_tensor(allc, mine, group=self.group) if self.count_device.type == "cuda" else \
+            dist.all_gather(list(allc.unbind(0)), mine, group=self.group)
+        counts = allc.cpu().tolist()
+        r, w = self.rank, self.world
+        n_from_left = counts[r - 1][1] if r > 0 else 0
+        n_from_right = counts[r + 1][0] if r < w - 1 else 0
+        from_left = self.eng.empty_records(n_from_left, record_bytes)
+        from_right = self.eng.empty_records(n_from_right, record_bytes)
+        ops = []
+        if r > 0 and to_left.shape[0]:
+            ops.append(dist.P2POp(dist.isend, to_left, r - 1, self.group))
+        if r < w - 1 and to_right.shape[0]:
+            ops.append(dist.P2POp(dist.isend, to_right, r + 1, self.group))
+        if n_from_left:
+            ops.append(dist.P2POp(dist.irecv, from_left, r - 1, self.group))
+        if n_from_right:
+            ops.append(dist.P2POp(dist.irecv, from_right, r + 1, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        self.bytes_sent += (to_left.shape[0] * (r > 0) + to_right.shape[0] * (r < w - 1)) * record_bytes
+        return from_left, from_right
+
+
+class SlabDomain:
+    """Host logic of one rank's slab.  Backend-agnostic: `engine` is a CtxEngine (GPU) or, in the CPU tests, an engine
+    over the oracle with the same methods."""
+
+    def __init__(self, engine, rank, nranks, cuts, drift=0.25, comm=None):
+        assert len(cuts) == nranks + 1 and all(cuts[k] < cuts[k + 1] for k in range(nranks))
+        self.eng, self.rank, self.nranks, self.comm = engine, rank, nranks, comm
+        self.x_lo, self.x_hi = float(cuts[rank]), float(cuts[rank + 1])
+        self.halo = 2.0 * H + 2.0 * drift
+        self.lambda_ext = H + drift
+        engine.set_lambda_range(self.x_lo - self.lambda_ext, self.x_hi + self.lambda_ext)
+        self.stats = {"migrated_out": 0, "ghosts": 0}
+
+    # ---- phases (a LocalCluster drives them in lock-step; step() strings them together over a communicator) ----
+    def begin(self, dt):
+        self.eng.begin_step()
+        self.eng.predict(dt)
+
+    def pack_migrants(self):
+        l, r = self.eng.pack_migrants(self.x_lo, self.x_hi)
+        self.stats["migrated_out"] += int(l.shape[0]) + int(r.shape[0])
+        return l, r
+
+    def apply_migrants(self, from_left, from_right):
+        self.eng.append_migrants(from_left, from_right)
+
+    def pack_halo(self):
+        return self.eng.pack_halo(self.x_lo, self.x_hi, self.halo)
+
+    def apply_halo(self, from_left, from_right):
+        self.stats["ghosts"] = int(from_left.shape[0]) + int(from_right.shape[0])
+        self.eng.set_ghosts(from_left, from_right)
+
+    def solve(self, it):
+        e = self.eng
+        e.build_grid()
+        e.solve_contacts()
+        e.solve_fluid()
+        e.collide_world(it)
+
+    def finish(self, dt):
+        self.eng.update_velocity(dt)
+
+    # ---- one whole step over the communicator ----
+    def _on_stream(self):
+        s = getattr(self.eng, "stream", None)
+        if s is None:
+            import contextlib
+            return contextlib.nullcontext()
+        return self.eng.torch.cuda.stream(s)
+
+    def migrate(self):
+        l, r = self.pack_migrants()
+        with self._on_stream():
+            fl, fr = self.comm.exchange(l, r, MIGRANT_RECORD_BYTES)
+        self.apply_migrants(fl, fr)
+
+    def refresh_halo(self):
+        l, r = self.pack_halo()
+        with self._on_stream():
+            fl, fr = self.comm.exchange(l, r, HALO_RECORD_BYTES)
+        self.apply_halo(fl, fr)
+
+    def step(self, dt):
+        self.begin(dt)
+        self.migrate()
+        for it in range(self.eng.iterations):
+            self.refresh_halo()
+            self.solve(it)
+        self.finish(dt)
+
+
+class LocalCluster:
+    """All slabs in one process, stepped in lock-step with in-process hand-over of the record buffers (tests; also a way
+    to run several slabs on one GPU)."""
+
+    def __init__(self, engines, cuts, drift=0.25):
+        n = len(engines)
+        self.doms = [SlabDomain(e, r, n, cuts, drift) for r, e in enumerate(engines)]
+
+    def _hand_over(self, sends, apply, record_bytes):
+        n = len(self.doms)
+        for r, d in enumerate(self.doms):
+            fl = sends[r - 1][1] if r > 0 else d.eng.empty_records(0, record_bytes)
+            fr = sends[r + 1][0] if r < n - 1 else d.eng.empty_records(0, record_bytes)
+            apply(d, fl, fr)
+        for d in self.doms:
+            d.eng.sync()  # the send buffers are reused by the next pack
+
+    def step(self, dt):
+        for d in self.doms:
+            d.begin(dt)
+        self._hand_over([d.pack_migrants() for d in self.doms], lambda d, a, b: d.apply_migrants(a, b), MIGRANT_RECORD_BYTES)
+        for it in range(self.doms[0].eng.iterations):
+            self._hand_over([d.pack_halo() for d in self.doms], lambda d, a, b: d.apply_halo(a, b), HALO_RECORD_BYTES)
+            for d in self.doms:
+                d.solve(it)
+        for d in self.doms:
+            d.finish(dt)
+
+
+# ---------------------------------------------------------------- synthetic dam break ----------------------------------------------------------------
+def _hash_uniform(idx, stream, seed=1234):
+    """Counter-based uniforms in [0,1): a splitmix64 finaliser of (global lattice index, stream, seed), so that any rank
+    count generates the identical particle set."""
+    z = (idx.astype(np.uint64) * np.uint64(3) + np.uint64(stream)) * np.uint64(0x9E3779B97F4A7C15) + np.uint64(seed)
+    z ^= z >> np.uint64(30); z *= np.uint64(0xBF58476D1CE4E5B9)
+    z ^= z >> np.uint64(27); z *= np.uint64(0x94D049BB133111EB)
+    z ^= z >> np.uint64(31)
+    return (z >> np.uint64(40)).astype(np.float64) / float(1 << 24)
+
+
+def dam_break_block(nx, ny, nz, ix0=0, ix1=None, origin=(0.3125, 0.3125, 0.3125), spacing=0.625, jitter=0.0025, rest_density=4.1):
+    """Particles of lattice columns ix0 <= ix < ix1 of an nx x ny x nz fluid block (x fastest, then y, then z):
+    spacing 2.5 r, jitter +-0.01 r from a counter-based hash of the GLOBAL lattice index, mass 1, rho0 = 4.1 (the
+    lattice's own density, so the block starts near equilibrium).  Returns pos4, vel4, inv_mass, rest_density, phase."""
+    ix1 = nx if ix1 is None else ix1
+    ix = np.arange(ix0, ix1, dtype=np.int64)
+    z, y, x = np.meshgrid(np.arange(nz, dtype=np.int64), np.arange(ny, dtype=np.int64), ix, indexing="ij")
+    gid = ((z * ny + y) * nx + x).ravel()
+    n = gid.size
+    pos = np.ones((n, 4), np.float32)
+    for c, lat in enumerate((x.ravel(), y.ravel(), z.ravel())):
+        j = (_hash_uniform(gid, c) * 2.0 - 1.0) * jitter
+        pos[:, c] = (origin[c] + lat * spacing + j).astype(np.float32)
+    return pos, np.zeros((n, 4), np.float32), np.ones(n, np.float32), np.full(n, rest_density, np.float32), np.zeros(n, np.int32)

@@ -1,0 +1,114 @@
+"""Slab decomposition on the GPU: the ps_slab_* kernels (ordered halo packing, ghost unpacking, migration with stable
+compaction) driven by particlesolver_b200.slab, several slabs as several contexts on one B200 (in-process hand-over of
+the record buffers), against (a) one undecomposed context and (b) the CPU oracle engine doing the same decomposition.
+The multi-process NCCL path is in test_gpu_slab_nccl.py."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import oracle_py as orc
+import particlesolver_b200 as psb
+from particlesolver_b200 import slab
+from slab_oracle_engine import HALO_DT, MIGR_DT, OracleEngine
+from test_slab_cpu import _match, _scene, _split
+
+pytestmark = pytest.mark.gpu
+DT = 1.0 / 60.0
+
+
+def _params(p_or):
+    p = psb.default_params()
+    p.grid_size[:] = tuple(p_or.grid)
+    p.min_bounds[:] = tuple(p_or.min_b)
+    p.max_bounds[:] = tuple(p_or.max_b)
+    return p
+
+
+def _ctx_engine(p, arrays, cap=20000):
+    pos, vel, w, phase, ros = arrays
+    sol = psb.Solver(p, max_particles=cap)
+    sol.append(pos, vel, w, ros, phase)
+    return slab.CtxEngine(sol, halo_capacity=cap, migrant_capacity=cap)
+
+
+def _records(t, dt):
+    return np.ascontiguousarray(t.cpu().numpy()).reshape(-1).view(dt)
+
+
+def test_pack_kernels_match_the_cpu_engine():
+    """halo and migrant records: same particles, same order, same bytes as the numpy restatement"""
+    p_or, pos, vel, w, phase, ros = _scene()
+    rng = np.random.default_rng(0)
+    pos[:, 0] += rng.uniform(-0.3, 0.3, pos.shape[0]).astype(np.float32)  # ragged faces
+    eng = _ctx_engine(_params(p_or), (pos, vel, w, phase, ros))
+    ref = OracleEngine(p_or, pos, vel, w, phase, ros)
+    x_lo, x_hi = 8.0, 15.0
+    for width in (0.7, 4.5):
+        gl, gr = eng.pack_halo(x_lo, x_hi, width)
+        rl, rr = ref.pack_halo(x_lo, x_hi, width)
+        assert gl.shape[0] > 0 and gr.shape[0] > 0
+        assert np.array_equal(gl.cpu().numpy(), rl.numpy()) and np.array_equal(gr.cpu().numpy(), rr.numpy())
+    # migration: prev/vel travel, the stayers keep their order
+    eng.sol.predict(DT)
+    ref.pos, ref.prev = eng.sol.download(psb.ARR_POS).copy(), eng.sol.download(psb.ARR_PREV).copy()  # identical inputs for the split
+    gl, gr = eng.pack_migrants(x_lo, x_hi)
+    rl, rr = ref.pack_migrants(x_lo, x_hi)
+    assert gl.shape[0] > 0 and gr.shape[0] > 0
+    assert np.array_equal(gl.cpu().numpy(), rl.numpy()) and np.array_equal(gr.cpu().numpy(), rr.numpy())
+    assert eng.n_owned == ref.n_owned < pos.shape[0]
+    assert np.array_equal(eng.sol.download_owned(psb.ARR_POS), ref.pos)
+    assert np.array_equal(eng.sol.download_owned(psb.ARR_PREV), ref.prev)
+    assert np.array_equal(eng.sol.download_owned(psb.ARR_VEL), ref.vel)
+    # and back in: appended behind the stayers, left neighbour's first
+    eng.append_migrants(gr, gl); ref.append_migrants(rr, rl)
+    assert eng.n_owned == pos.shape[0]
+    assert np.array_equal(eng.sol.download_owned(psb.ARR_VEL), ref.vel)
+    assert np.array_equal(eng.sol.download_owned(psb.ARR_PHASE), ref.phase)
+    eng.sol.close()
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slabs_on_one_gpu_match_one_context(nranks):
+    p_or, pos, vel, w, phase, ros = _scene()
+    p = _params(p_or)
+    steps = 4
+    whole = psb.Solver(p, max_particles=pos.shape[0] + 16)
+    whole.append(pos, vel, w, ros, phase)
+    for _ in range(steps):
+        whole.step(DT)
+    cuts = slab.quantile_cuts(pos[:, 0], nranks)
+    engines = [_ctx_engine(p, part) for part in _split(cuts, pos, vel, w, phase, ros)]
+    cl = slab.LocalCluster(engines, cuts)
+    for _ in range(steps):
+        cl.step(DT)
+    got_pos = np.concatenate([e.sol.download_owned(psb.ARR_POS) for e in engines])
+    got_vel = np.concatenate([e.sol.download_owned(psb.ARR_VEL) for e in engines])
+    assert got_pos.shape[0] == pos.shape[0]
+    assert sum(d.stats["migrated_out"] for d in cl.doms) > 0 and all(d.stats["ghosts"] > 0 for d in cl.doms)
+    # the same wall-jitter stream on every rank (each context seeds XORWOW with 1234 like the reference)
+    assert np.array_equal(engines[0].sol.download(psb.ARR_RANDS), whole.download(psb.ARR_RANDS))
+    _match(whole.download(psb.ARR_POS), whole.download(psb.ARR_VEL), got_pos, got_vel, tol=5e-5)
+    for e in engines:
+        e.sol.close()
+    whole.close()
+
+
+def test_slab_context_rejects_constraints():
+    ps = psb.ParticleSystem.scene("2")  # cloth: distance + point constraints
+    sol = ps.solver
+    buf = torch.empty((1024, 32), dtype=torch.uint8, device="cuda")
+    with pytest.raises(psb.PsError) as e:
+        sol.slab_pack_halo(0.0, 1.0, 0.5, buf.data_ptr(), buf.data_ptr(), 1024)
+    assert e.value.code == psb.PS_ERR_STATE
+    ps.close()
+
+
+def test_record_buffer_overflow_is_reported():
+    p_or, pos, vel, w, phase, ros = _scene()
+    eng = _ctx_engine(_params(p_or), (pos, vel, w, phase, ros))
+    buf = torch.empty((8, 32), dtype=torch.uint8, device="cuda")
+    with pytest.raises(psb.PsError) as e:
+        eng.sol.slab_pack_halo(8.0, 15.0, 4.5, buf.data_ptr(), buf.data_ptr(), 8)
+    assert e.value.code == psb.PS_ERR_CAPACITY
+    eng.sol.close()

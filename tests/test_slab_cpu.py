@@ -1,0 +1,121 @@
+"""Slab decomposition, host side (CPU): cuts, halo selection, ghost bookkeeping, migration and the neighbour exchange of
+particlesolver_b200.slab, with the oracle as the compute engine.  In-process lock-step (LocalCluster, 2 and 3 slabs) and
+two real processes over gloo (DistComm); each must reproduce the single-domain oracle run."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_py as orc
+from particlesolver_b200 import slab
+from slab_oracle_engine import OracleEngine
+
+DT = 1.0 / 60.0
+
+
+def _scene(nx=30, ny=8, nz=8):
+    """A fluid block moving in +x at 6 units/s (0.1 per step: particles cross the cut planes) on a 64^3 grid."""
+    pos, vel, w, ros, phase = slab.dam_break_block(nx, ny, nz, origin=(2.3, 1.3, 2.3))
+    vel[:, 0] = 6.0
+    p = orc.make_params(grid=(64, 64, 64), min_b=(0, 0, 0), max_b=(40, 30, 12))
+    return p, pos, vel, w, phase, ros
+
+
+def _single(p, pos, vel, w, phase, ros, steps):
+    o = orc.OracleSystem(p, pos, vel, w, phase, ros, iterations=5)
+    rands = np.full((5, 6), 0.5, np.float32)
+    for _ in range(steps):
+        o.step(DT, rands)
+    return o.pos, o.vel
+
+
+def _match(pos_a, vel_a, pos_b, vel_b, tol):
+    """same particle SET: nearest-neighbour bijection within tol"""
+    from scipy.spatial import cKDTree
+    assert pos_a.shape == pos_b.shape
+    d, idx = cKDTree(pos_b[:, :3]).query(pos_a[:, :3])
+    assert d.max() <= tol, f"max position mismatch {d.max():.3e}"
+    assert np.unique(idx).size == idx.size
+    assert np.abs(vel_a[:, :3] - vel_b[idx, :3]).max() <= tol * 60 * 1.5
+
+
+def _split(cuts, pos, *arrays):
+    out = []
+    for r in range(len(cuts) - 1):
+        sel = (pos[:, 0] >= cuts[r]) & (pos[:, 0] < cuts[r + 1])
+        out.append(tuple(a[sel] for a in (pos, *arrays)))
+    return out
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_local_cluster_matches_single_domain(nranks):
+    p, pos, vel, w, phase, ros = _scene()
+    steps = 4
+    ref_pos, ref_vel = _single(p, pos, vel, w, phase, ros, steps)
+    cuts = slab.quantile_cuts(pos[:, 0], nranks)
+    engines = [OracleEngine(p, a, b, c, d, e) for a, b, c, d, e in _split(cuts, pos, vel, w, phase, ros)]
+    n0 = [e.n_owned for e in engines]
+    cl = slab.LocalCluster(engines, cuts)
+    for _ in range(steps):
+        cl.step(DT)
+    got_pos = np.concatenate([e.pos[:e.n_owned] for e in engines])
+    got_vel = np.concatenate([e.vel for e in engines])
+    assert got_pos.shape[0] == pos.shape[0]                       # nothing lost, nothing duplicated
+    assert sum(d.stats["migrated_out"] for d in cl.doms) > 0      # the block moves: particles did change owner
+    assert [e.n_owned for e in engines] != n0
+    assert all(d.stats["ghosts"] > 0 for d in cl.doms)
+    # owned particles stay inside their slab (up to the drift allowance of one step)
+    for d in cl.doms:
+        x = d.eng.pos[:d.eng.n_owned, 0]
+        assert (x >= d.x_lo - 0.25).all() and (x < d.x_hi + 0.25).all()
+    _match(ref_pos, ref_vel, got_pos, got_vel, tol=2e-5)
+
+
+def test_cuts():
+    c = slab.uniform_cuts(0.0, 80.0, 4)
+    assert c[0] == -np.inf and c[-1] == np.inf and c[1:-1] == [20.0, 40.0, 60.0]
+    x = np.linspace(0, 1, 1001)
+    q = slab.quantile_cuts(x, 4)
+    assert np.allclose(q[1:-1], [0.25, 0.5, 0.75])
+    assert slab.quantile_cuts(x, 1) == [-np.inf, np.inf]
+
+
+def test_dam_break_block_is_rank_count_independent():
+    whole = slab.dam_break_block(12, 3, 4)[0]
+    parts = [slab.dam_break_block(12, 3, 4, ix0=a, ix1=b)[0] for a, b in ((0, 5), (5, 12))]
+    a = whole[np.lexsort(whole[:, :3].T)]
+    b = np.concatenate(parts); b = b[np.lexsort(b[:, :3].T)]
+    assert np.array_equal(a, b)
+    assert np.abs(whole[:, :3] - np.round((whole[:, :3] - 0.3125) / 0.625) * 0.625 - 0.3125).max() <= 0.0025 + 1e-6
+
+
+def _gloo_worker(rank, world, port, steps, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p, pos, vel, w, phase, ros = _scene()
+    cuts = slab.quantile_cuts(pos[:, 0], world)
+    mine = _split(cuts, pos, vel, w, phase, ros)[rank]
+    eng = OracleEngine(p, *mine)
+    dom = slab.SlabDomain(eng, rank, world, cuts, comm=slab.DistComm(eng))
+    for _ in range(steps):
+        dom.step(DT)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), pos=eng.pos[:eng.n_owned], vel=eng.vel, migrated=dom.stats["migrated_out"],
+             sent=dom.comm.bytes_sent)
+    dist.destroy_process_group()
+
+
+def test_two_processes_over_gloo_match_single_domain(tmp_path):
+    import torch.multiprocessing as mp
+    steps, world = 5, 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(world, port, steps, str(tmp_path)), nprocs=world, join=True)
+    p, pos, vel, w, phase, ros = _scene()
+    ref_pos, ref_vel = _single(p, pos, vel, w, phase, ros, steps)
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    got_pos = np.concatenate([z["pos"] for z in parts])
+    got_vel = np.concatenate([z["vel"] for z in parts])
+    assert sum(int(z["migrated"]) for z in parts) > 0 and all(int(z["sent"]) > 0 for z in parts)
+    _match(ref_pos, ref_vel, got_pos, got_vel, tol=2e-5)
