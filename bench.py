@@ -496,6 +496,16 @@ def run_slabs(args, rank, world, local_rank):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner) are sent to stderr
+    global print
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):  # noqa: A001
+        k.setdefault("file", real_stdout)
+        _print(*a, **k)
+        real_stdout.flush()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -50,6 +50,9 @@ typedef struct PsParams {
     uint32_t solver_iterations;  /* 5           particleapp.cpp:38 */
     float omega;                 /* SOR factor on the Jacobi-averaged deltas; 1.0 == reference */
     uint32_t flags;              /* PS_FLAG_* */
+    uint32_t neighbor_list_rows; /* rows (of 32 interleaved lists) per warp kept between the two PBF passes: 128 B x rows per 32
+                                    particles; 256 holds ~210 neighbours per particle, a warp that needs more falls back to a second
+                                    grid walk (results identical); 0 = keep no lists.  Multiple of 8. */
 } PsParams;
 
 #define PS_FLAG_NONE 0u

@@ -46,7 +46,7 @@ class Params(C.Structure):
     _fields_ = [("gravity", C.c_float * 3), ("global_damping", C.c_float), ("particle_radius", C.c_float),
                 ("grid_size", C.c_uint32 * 3), ("world_origin", C.c_float * 3), ("cell_size", C.c_float * 3),
                 ("min_bounds", C.c_int32 * 3), ("max_bounds", C.c_int32 * 3), ("solver_iterations", C.c_uint32),
-                ("omega", C.c_float), ("flags", C.c_uint32)]
+                ("omega", C.c_float), ("flags", C.c_uint32), ("neighbor_list_rows", C.c_uint32)]
 
 
 _lib = None

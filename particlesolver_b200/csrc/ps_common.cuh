@@ -113,12 +113,14 @@ void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool 
 // ps_neighbor_kernels.cu
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                        const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, cudaStream_t s);
+// nbr_list / nbr_rows: interleaved per-warp neighbour lists written by K6 and consumed by K7 (nullptr: K7 re-walks the grid)
+size_t ps_neighbor_list_elems(unsigned long long capacity, u32 max_rows);
 void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                             const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
-                            const StencilDesc &st, bool zero_nonfluid, cudaStream_t s);
-void ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
-                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
-                            cudaStream_t s);
+                            const StencilDesc &st, bool zero_nonfluid, u32 *nbr_list, u32 *nbr_rows, u32 max_rows, cudaStream_t s);
+u32 ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
+                           const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
+                           const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s);  // returns the number of launches
 // ps_slab_kernels.cu — slab decomposition: ordered selection / packing / compaction
 size_t ps_slab_scratch_elems(u32 n);
 void ps_launch_slab_select(const float4 *pos, u32 n, float left_below, float right_from, u32 *scratch, cudaStream_t s);

@@ -64,6 +64,7 @@ extern "C" void ps_default_params(PsParams *p) {
     p->solver_iterations = 5;
     p->omega = 1.0f;
     p->flags = PS_FLAG_NONE;
+    p->neighbor_list_rows = 256;
 }
 
 static bool is_pow2(u32 v) { return v && !(v & (v - 1)); }
@@ -86,6 +87,7 @@ static int validate_params(const PsParams *p) {
     for (int c = 0; c < 3; c++)
         if (p->grid_size[c] < (u32)(2 * rad + 2)) { ps_set_error("grid_size[%d]=%u is smaller than the fluid stencil (%d cells)", c, p->grid_size[c], 2 * rad + 2); return PS_ERR_INVALID; }
     if (p->solver_iterations > 64) { ps_set_error("solver_iterations > 64"); return PS_ERR_INVALID; }
+    if (p->neighbor_list_rows % 8 || p->neighbor_list_rows > 4096) { ps_set_error("neighbor_list_rows must be a multiple of 8, at most 4096"); return PS_ERR_INVALID; }
     return PS_OK;
 }
 
@@ -147,6 +149,12 @@ int ps_ctx_ensure_capacity(PsCtx *c, uint64_t want) {
     G(hash, true) G(index, true) G(hash_tmp, true) G(index_tmp, true) G(num_neighbors, true) G(occ, true)
 #undef G
     c->capacity = cap;
+    if (c->nbr_list) { CU(cudaFree(c->nbr_list)); CU(cudaFree(c->nbr_rows)); c->nbr_list = c->nbr_rows = nullptr; }
+    c->nbr_max_rows = c->params.neighbor_list_rows;
+    if (c->nbr_max_rows) {
+        CU(cudaMalloc((void **)&c->nbr_list, ps_neighbor_list_elems(cap, c->nbr_max_rows) * sizeof(u32)));
+        CU(cudaMalloc((void **)&c->nbr_rows, ((cap + 31) / 32) * sizeof(u32)));
+    }
     // sort look-back status words for the largest n this capacity allows
     size_t need = ps_sort_status_elems((u32)cap, 4);
     if (need > c->sort_status_elems) {
@@ -250,7 +258,7 @@ extern "C" int ps_destroy(PsCtx *c) {
     if (c->gen) curandDestroyGenerator(c->gen);
     void *ptrs[] = {c->pos, c->vel, c->prev, c->spos, c->w, c->ros, c->sw, c->lambda, c->phase, c->sphase, c->hash, c->index, c->hash_tmp,
                     c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->chunk_lb, c->sort_hist,
-                    c->sort_status, c->sort_ticket, c->rands, c->slab_scratch, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
+                    c->sort_status, c->sort_ticket, c->rands, c->slab_scratch, c->nbr_list, c->nbr_rows, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
                     c->d_point_xyz, c->dist_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->slab_counts_host) cudaFreeHost(c->slab_counts_host);
@@ -268,9 +276,19 @@ extern "C" int ps_set_params(PsCtx *c, const PsParams *p) {
     int r = validate_params(p);
     if (r != PS_OK) return r;
     DeviceGuard dg(c->device);
+    const bool rows_changed = p->neighbor_list_rows != c->params.neighbor_list_rows;
     c->params = *p;
     ps_ctx_refresh_descs(c);
     if ((r = ps_ctx_ensure_cells(c)) != PS_OK) return r;
+    if (rows_changed) {
+        CU(cudaStreamSynchronize(c->stream));
+        if (c->nbr_list) { CU(cudaFree(c->nbr_list)); CU(cudaFree(c->nbr_rows)); c->nbr_list = c->nbr_rows = nullptr; }
+        c->nbr_max_rows = p->neighbor_list_rows;
+        if (c->nbr_max_rows) {
+            CU(cudaMalloc((void **)&c->nbr_list, ps_neighbor_list_elems(c->capacity, c->nbr_max_rows) * sizeof(u32)));
+            CU(cudaMalloc((void **)&c->nbr_rows, ((c->capacity + 31) / 32) * sizeof(u32)));
+        }
+    }
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     c->grid_valid = false;
     return PS_OK;
@@ -472,9 +490,10 @@ extern "C" int ps_solve_fluid(PsCtx *c) {
     DeviceGuard dg(c->device);
     // lambda is needed for the ghosts next to a face too (their owners are on another GPU): see ps_slab_set_lambda_range
     ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost,
-                           c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->stream);
+                           c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list,
+                           c->nbr_rows, c->nbr_max_rows, c->stream);
     ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost, c->grid, c->stencil,
-                           c->params.omega, c->stream);
+                           c->params.omega, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
     return check_launch("ps_solve_fluid");
 }
 extern "C" int ps_collide_world(PsCtx *c, uint32_t iteration) {
@@ -525,10 +544,10 @@ static u32 issue_step(PsCtx *c, float dt) {
         }
         if (has_fluid) {
             ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned,
-                                   c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s);
-            ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned, c->grid, c->stencil,
-                                   p.omega, s);
-            launches += 2;
+                                   c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list,
+                                   c->nbr_rows, c->nbr_max_rows, s);
+            launches += 1 + ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned, c->grid,
+                                                   c->stencil, p.omega, c->nbr_list, c->nbr_rows, c->nbr_max_rows, s);
         }
         ps_launch_collide_world(c->pos, c->prev, c->phase, n_owned, c->rands + 6 * it, c->world, s);
         launches++;
@@ -613,8 +632,10 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
         if (has_contact) { ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, s); mark(5, 1); }
         if (has_fluid) {
             ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->lambda_xmin,
-                                   c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, s); mark(6, 1);
-            ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil, p.omega, s); mark(7, 1);
+                                   c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list, c->nbr_rows,
+                                   c->nbr_max_rows, s); mark(6, 1);
+            const u32 k7 = ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil, p.omega,
+                                                  c->nbr_list, c->nbr_rows, c->nbr_max_rows, s); mark(7, k7);
         }
         ps_launch_collide_world(c->pos, c->prev, c->phase, n, c->rands + 6 * it, c->world, s); mark(8, 1);
         if (c->num_constrained) { ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained, p.omega, s); mark(9, 2); }

@@ -32,6 +32,9 @@ struct PsCtx {
     float *w = nullptr, *ros = nullptr, *sw = nullptr, *lambda = nullptr;
     int *phase = nullptr, *sphase = nullptr;
     u32 *hash = nullptr, *index = nullptr, *hash_tmp = nullptr, *index_tmp = nullptr, *num_neighbors = nullptr, *occ = nullptr;
+    // neighbour lists between K6 and K7 (ps_neighbor_kernels.cu); nbr_rows[warp] = rows used or overflow mark
+    u32 *nbr_list = nullptr, *nbr_rows = nullptr;
+    u32 nbr_max_rows = 0;
     // per-cell state
     u32 *cell_begin = nullptr, *chunk_lb = nullptr;
     u32 *cell_start = nullptr, *cell_end = nullptr;  // the reference's table format: allocated and filled on demand

@@ -26,6 +26,7 @@ namespace {
 #ifndef PS_KQ
 #define PS_KQ 8
 #endif
+typedef unsigned long long u64;
 constexpr int kBlock = PS_FBLOCK;  // tuning knobs of the neighbour kernels (build variants: scripts/bench_variants.sh)
 
 // Visit, in the reference's order, every sorted slot j whose cell lies in the stencil rows around gp.
@@ -56,8 +57,8 @@ __device__ __forceinline__ void for_each_candidate(const GridDesc &g, const Sten
 }
 
 // ------------------------------------------------------------------ fluid neighbour walk ------------------------------------------------------------------
-// Shared by K6 and K7.  One thread per sorted slot, one warp = 32 consecutive slots (= a run of x-adjacent
-// particles of one or two grid rows).  Three things keep the warp's issue slots busy:
+// The neighbour search of the PBF passes.  One thread per sorted slot, one warp = 32 consecutive slots (= a run of
+// x-adjacent particles of one or two grid rows).  What keeps the warp's issue slots busy:
 //   (1) per-particle row pruning: for stencil row (dy,dz) the x-extent that can hold a neighbour follows from the
 //       particle's own position inside its cell, ext = sqrt(H^2 - dymin^2 - dzmin^2) — ~200 candidates per
 //       particle instead of the ~370 of the full 9^3 stencil.  The pruning is conservative (eps margin), so the
@@ -66,40 +67,47 @@ __device__ __forceinline__ void for_each_candidate(const GridDesc &g, const Sten
 //       lane to lane, so walking them row by row in lock-step leaves 45 % of the lanes idle (profiles/r1b).  Instead
 //       each lane first writes the non-empty ranges of one z-slab of the stencil (<= 9 rows) to a small list in
 //       shared memory, then all lanes walk their own lists in one flat loop whose trip count is the warp's largest
-//       candidate total;
+//       candidate total, with a 2-deep software pipeline on the position gather;
 //   (3) accept/interact split: the distance test runs over all candidates, accepted neighbours (~65 % of them) are
-//       staged in a per-thread shared-memory queue of kQ float4 entries (r.x, r.y, r.z, r2 | j) and the expensive
-//       interaction body runs over full queues with (nearly) every lane active, instead of under a divergent branch.
-// All loops that contain a vote are warp-uniform.
+//       staged in a per-thread shared-memory queue of kQ slots and the expensive interaction body runs over full
+//       queues with (nearly) every lane active, instead of under a divergent branch;
+//   (4) K6 leaves the accepted neighbours behind as a compact list (below), so K7 does not search again.
+// All loops that contain a vote are warp-uniform.  Shared memory is carved out of the same 256 KB as L1, and the
+// candidate gather lives on L1 hits, so the per-thread footprint is kept small: kQ 4-byte queue slots (the neighbour's
+// sorted slot; its position is re-read, an L1 hit) + 2*(2*rad+1) list entries of (u32 begin, u16 length).
+//
+// Neighbour lists.  NOT the reference's (500 slots = 2 KB per particle, 4x over-allocated, strided by thread,
+// integration.cu:70): a warp's 32 lists are interleaved, row r of warp w is the 128-byte line
+// list[(w * max_rows + r) * 32 + lane], and the warp appends in lock-step — every queue flush writes kQ full rows, lanes
+// with fewer accepted neighbours pad with kNoNeighbor.  Writes and K7's reads are therefore fully coalesced, ~170 rows
+// (21 KB per warp, 0.7 KB per particle) for ~140 neighbours.  A warp that would need more than max_rows rows marks itself
+// overflowed and K7 re-walks the grid for it (k_solve_fluids below), so the result never depends on max_rows.
 constexpr int kQ = PS_KQ;
 constexpr unsigned kFull = 0xffffffffu;
-
-// Shared memory is carved out of the same 256 KB as L1, and the candidate gather lives on L1 hits: every byte counts.
-// Per thread: the queue (kQ entries of 16 B, or of 4 B when only the neighbour's slot is staged, PS_QJ) + the segment
-// list of one stencil slab: 2*(2*rad+1) entries of (u32 begin, u16 length).
-#ifndef PS_QJ
-#define PS_QJ 1  // measured on B200 (1M-particle fluid): 4-byte queue entries + reload beat 16-byte entries by 10 % (occupancy, L1)
-#endif
+constexpr u32 kNoNeighbor = 0xffffffffu, kListOverflow = 0xffffffffu;
 typedef unsigned short u16;
+
 static inline size_t fluid_smem_bytes(int rad) {
-    return (size_t)kQ * kBlock * (PS_QJ ? sizeof(u32) : sizeof(float4)) + (size_t)2 * (2 * rad + 1) * kBlock * (sizeof(u32) + sizeof(u16));
+    return (size_t)kQ * kBlock * sizeof(u32) + (size_t)2 * (2 * rad + 1) * kBlock * (sizeof(u32) + sizeof(u16));
 }
 
-template <int RAD, bool STORE_J, class Body>
+struct NeighborListWriter {  // per-warp view of the list being written by K6 (list == nullptr: no list)
+    u32 *list;               // this lane's column of the warp's block: row r at list[r * 32]
+    u32 max_rows, rows;
+    bool overflow;
+};
+
+// body(rx, ry, rz, j) is called for every accepted neighbour, in the reference's traversal order.
+template <int RAD, class Body>
 __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const StencilDesc &st, const u32 *__restrict__ cell_begin,
-                                                     const float4 *__restrict__ spos, bool act, u32 i, float4 pi, float4 *smem,
-                                                     Body &&body) {
+                                                     const float4 *__restrict__ spos, bool act, u32 i, float4 pi, u32 *smem,
+                                                     NeighborListWriter &nl, Body &&body) {
     const int tid = threadIdx.x;
     const int rad = RAD ? RAD : st.rad;
     const int nseg = 2 * (2 * rad + 1);  // list capacity per slab: every row may wrap into two ranges
-#if PS_QJ
     u32(*q)[kBlock] = reinterpret_cast<u32(*)[kBlock]>(smem);
-    u32 *seg_b = reinterpret_cast<u32 *>(smem) + kQ * kBlock + tid;  // entry s of this lane at seg_b[s * kBlock]
-#else
-    float4(*q)[kBlock] = reinterpret_cast<float4(*)[kBlock]>(smem);
-    u32 *seg_b = reinterpret_cast<u32 *>(smem + kQ * kBlock) + tid;  // entry s of this lane at seg_b[s * kBlock]
-#endif
-    u16 *seg_len = reinterpret_cast<u16 *>(seg_b - tid + nseg * kBlock) + tid;
+    u32 *seg_b = smem + kQ * kBlock + tid;  // entry s of this lane at seg_b[s * kBlock]
+    u16 *seg_len = reinterpret_cast<u16 *>(smem + kQ * kBlock + nseg * kBlock) + tid;
     const float relx = pi.x - g.ox, rely = pi.y - g.oy, relz = pi.z - g.oz;
     const int3 gp = ps_grid_pos(g, pi.x, pi.y, pi.z);
     // margin: covers the approximate divide of the cell assignment and coordinate rounding (ulp(1000) = 6e-5)
@@ -122,17 +130,21 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
     int cnt = 0;
 
     auto flush = [&]() {
+        if (nl.list) {  // kQ full rows of the warp's interleaved list (uniform branch)
+            if (nl.rows + kQ <= nl.max_rows) {
+#pragma unroll
+                for (int k = 0; k < kQ; k++) nl.list[(nl.rows + k) * 32] = k < cnt ? q[k][tid] : kNoNeighbor;
+                nl.rows += kQ;
+            } else {
+                nl.overflow = true;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < kQ; k++)
             if (k < cnt) {
-#if PS_QJ
                 const u32 j = q[k][tid];
                 const float4 pj = __ldg(spos + j);  // an L1 hit: the line was gathered a few instructions ago
-                const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-                body(make_float4(rx, ry, rz, STORE_J ? __uint_as_float(j) : rx * rx + ry * ry + rz * rz));
-#else
-                body(q[k][tid]);
-#endif
+                body(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z, j);
             }
         cnt = 0;
     };
@@ -213,11 +225,7 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
                 const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
                 const float r2 = rx * rx + ry * ry + rz * rz;
                 if (r2 < PS_H2 && j != i && (!decltype(capped_c)::value || nn < PS_MAX_NEIGHBORS)) {
-#if PS_QJ
                     q[cnt][tid] = j;
-#else
-                    q[cnt][tid] = make_float4(rx, ry, rz, STORE_J ? __uint_as_float(j) : r2);
-#endif
                     cnt++;
                     nn++;
                 }
@@ -243,169 +251,169 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
         if (capped) walk(cuda::std::true_type{});
         else walk(cuda::std::false_type{});
     }
-    flush();
+    if (__any_sync(kFull, cnt > 0)) flush();
     return nn;
 }
 
-// ------------------------------------------------------------------ slot mapping ------------------------------------------------------------------
-// Which sorted slot a thread works on.  The sorted order is x-fastest, so a CTA of consecutive slots is a 60-unit-long
-// pencil of particles whose stencil footprint (~110 KB of positions) thrashes L1 (profiles/r1c: 63 % hit rate, 33 % of
-// all stall samples waiting on the candidate gather).  The brick mapping gives each CTA the particles of a compact
-// brick of kBrickX x kBrickY x kBrickZ CELLS instead (16 x 2 x 2 world units at the reference's cell size): the brick's
-// kBrickY*kBrickZ grid rows are kBrickY*kBrickZ contiguous slices of the sorted arrays, enumerated row by row.  The
-// footprint per thread drops ~4x and the working set of one stencil slab fits L1.  Every lane is independent in the
-// walk (per-lane segment lists), so any slot -> lane assignment is legal; results do not depend on it.
-#ifndef PS_FMAP
-#define PS_FMAP 0
-#endif
-constexpr int kBrickX = 32, kBrickY = 4, kBrickZ = 4, kBrickRows = kBrickY * kBrickZ;
-
-// calls f(slot, have) for every slot of the calling CTA's share, warp-uniformly (have == false pads the last warp)
-template <class F>
-__device__ __forceinline__ void for_each_slot(const GridDesc &g, const u32 *__restrict__ cell_begin, u32 n, F &&f) {
-#if PS_FMAP == 0
-    const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    f(i, i < n);
-#else
-    __shared__ u32 s_b[kBrickRows], s_pre[kBrickRows + 1];
-    const int tid = threadIdx.x;
-    const u32 bw = min((u32)kBrickX, g.gx);
-    if (tid < 32) {  // one warp: the brick's rows, their slices of the sorted arrays and an exclusive scan of the slice lengths
-        u32 b = 0, len = 0;
-        if (tid < kBrickRows) {
-            const u32 cy = blockIdx.y * kBrickY + (tid % kBrickY), cz = blockIdx.z * kBrickZ + (tid / kBrickY);
-            const u32 row = (cz * g.gy + cy) * g.gx + blockIdx.x * bw;
-            b = __ldg(cell_begin + row);
-            len = __ldg(cell_begin + row + bw) - b;
-        }
-        u32 incl = len;
-#pragma unroll
-        for (int o = 1; o < kBrickRows; o <<= 1) {
-            const u32 t = __shfl_up_sync(kFull, incl, o);
-            if (tid >= o) incl += t;
-        }
-        if (tid < kBrickRows) {
-            s_b[tid] = b;
-            s_pre[tid + 1] = incl;
-        }
-        if (tid == 0) s_pre[0] = 0;
-    }
-    __syncthreads();
-    const u32 total = s_pre[kBrickRows];
-    for (u32 base = (u32)(tid & ~31); base < total; base += kBlock) {  // warp-uniform trip count
-        const u32 item = base + (tid & 31);
-        const bool have = item < total;
-        u32 r = 0;
-#pragma unroll
-        for (int k = 1; k < kBrickRows; k++) r += (have && item >= s_pre[k]) ? 1u : 0u;
-        const u32 slot = have ? s_b[r] + (item - s_pre[r]) : 0u;
-        f(slot, have);
-    }
-    (void)n;
-#endif
-}
-
-// ------------------------------------------------------------------ K6: lambda ------------------------------------------------------------------
+// ------------------------------------------------------------------ K6: lambda (+ neighbour lists) ------------------------------------------------------------------
 template <int RAD>
 __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lambda, u32 *__restrict__ num_neighbors,
                                                          const float4 *__restrict__ spos, const float *__restrict__ sw,
                                                          const int *__restrict__ sphase, const u32 *__restrict__ index,
                                                          const u32 *__restrict__ cell_begin, const float *__restrict__ ros, u32 n,
                                                          u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g, StencilDesc st,
-                                                         int zero_nonfluid) {
-    extern __shared__ float4 fluid_smem[];
-    for_each_slot(g, cell_begin, n, [&](const u32 i, bool act) {
-        u32 orig = 0;
-        if (act) {
-            if (sphase[i] != PH_FLUID) {
-                if (zero_nonfluid) lambda[i] = 0.f;
-                act = false;
-            } else {
-                orig = index[i];
-            }
+                                                         int zero_nonfluid, u32 *__restrict__ nbr_list, u32 *__restrict__ nbr_rows, u32 max_rows) {
+    extern __shared__ u32 fluid_smem[];
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    const u32 warp = i >> 5;
+    const int lane = threadIdx.x & 31;
+    bool act = i < n;
+    u32 orig = 0;
+    if (act) {
+        if (sphase[i] != PH_FLUID) {
+            if (zero_nonfluid) lambda[i] = 0.f;
+            act = false;
+        } else {
+            orig = index[i];
         }
-        float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
-        // ghost copies of a neighbour slab's particles: their lambda is needed by the owned particles next to the face
-        // (K7 reads lambda_j), and it is exact when the halo holds the ghost's whole neighbourhood, i.e. for ghosts
-        // within [ghost_xmin, ghost_xmax]; ghosts further out are never read
-        if (act && orig >= n_owned && !(pi.x >= ghost_xmin && pi.x <= ghost_xmax)) act = false;
-        if (!__any_sync(kFull, act)) return;
-        if (!act) pi = make_float4(g.ox, g.oy, g.oz, 0.f);
-        const float ro0 = act ? ros[orig] : 1.f;
-        const float inv_ro0 = __fdividef(1.f, ro0);
-        const float cs = -PS_SPIKY * inv_ro0;
+    }
+    float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
+    // ghost copies of a neighbour slab's particles: their lambda is needed by the owned particles next to the face
+    // (K7 reads lambda_j), and it is exact when the halo holds the ghost's whole neighbourhood, i.e. for ghosts
+    // within [ghost_xmin, ghost_xmax]; ghosts further out are never read
+    const bool ghost = act && orig >= n_owned;
+    if (ghost && !(pi.x >= ghost_xmin && pi.x <= ghost_xmax)) act = false;
+    if (!__any_sync(kFull, act)) {
+        if (nbr_rows && lane == 0 && (u64)warp * 32 < n) nbr_rows[warp] = 0;
+        return;
+    }
+    if (!act) pi = make_float4(g.ox, g.oy, g.oz, 0.f);
+    const float ro0 = act ? ros[orig] : 1.f;
+    const float inv_ro0 = __fdividef(1.f, ro0);
+    const float cs = -PS_SPIKY * inv_ro0;
+    NeighborListWriter nl;
+    nl.list = nbr_list ? nbr_list + ((size_t)warp * max_rows) * 32 + lane : nullptr;
+    nl.max_rows = max_rows; nl.rows = 0; nl.overflow = false;
 
-        float ro = 0.f, denom = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-        const u32 nn = walk_fluid_neighbours<RAD, false>(g, st, cell_begin, spos, act, i, pi, fluid_smem, [&](const float4 e) {
-            const float r2 = e.w;
-            const float inv_r = rsqrtf(r2);
-            const float rlen = r2 * inv_r;  // sqrt(r2); r2 == 0 gives NaN here and is handled below
-            const float hm2 = PS_H2 - r2;
-            ro += hm2 * hm2 * hm2;
-            if (rlen >= 0.0001f) {  // false for NaN as well: coincident particles contribute no gradient
-                const float hm = PS_H - rlen;
-                const float c = (cs * hm * hm) * inv_r;  // spikyGrad / rho0 = r * c
-                gx += e.x * c; gy += e.y * c; gz += e.z * c;
-                denom += (c * c) * r2;
-            }
-        });
-        if (!act) return;
-        const float inv_w = __fdividef(1.f, sw[i]);
-        ro = (ro + PS_H6) * (PS_POLY6 * inv_w);  // + self term poly6(0) = POLY6 * H^6 (integration_kernel.cuh:589)
-        denom += gx * gx + gy * gy + gz * gz;
-        lambda[i] = -__fdividef(ro * inv_ro0 - 1.f, denom + PS_RELAX);
-        num_neighbors[i] = nn;
+    float ro = 0.f, denom = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+    const u32 nn = walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, nl, [&](float rx, float ry, float rz, u32) {
+        const float r2 = rx * rx + ry * ry + rz * rz;
+        const float inv_r = rsqrtf(r2);
+        const float rlen = r2 * inv_r;  // sqrt(r2); r2 == 0 gives NaN here and is handled below
+        const float hm2 = PS_H2 - r2;
+        ro += hm2 * hm2 * hm2;
+        const float hm = PS_H - rlen;
+        // coincident particles contribute no gradient (the comparison is false for NaN as well)
+        const float c = rlen >= 0.0001f ? (cs * hm * hm) * inv_r : 0.f;  // spikyGrad / rho0 = r * c
+        gx += rx * c; gy += ry * c; gz += rz * c;
+        denom += (c * c) * r2;
     });
+    if (nbr_rows && lane == 0) nbr_rows[warp] = nl.overflow ? kListOverflow : nl.rows;
+    if (!act) return;
+    const float inv_w = __fdividef(1.f, sw[i]);
+    ro = (ro + PS_H6) * (PS_POLY6 * inv_w);  // + self term poly6(0) = POLY6 * H^6 (integration_kernel.cuh:589)
+    denom += gx * gx + gy * gy + gz * gz;
+    lambda[i] = -__fdividef(ro * inv_ro0 - 1.f, denom + PS_RELAX);
+    num_neighbors[i] = nn;
 }
 
 // ------------------------------------------------------------------ K7: delta p ------------------------------------------------------------------
+// s_corr = -K_P * (poly6(r) / poly6(dq*H))^4 ; the POLY6 factors cancel (integration_kernel.cuh:630-634)
+struct DeltaP {
+    float li, inv_den, dx, dy, dz;
+    const float *__restrict__ lambda;
+    __device__ __forceinline__ void operator()(float rx, float ry, float rz, u32 j) {
+        const float lj = __ldg(lambda + j);
+        const float r2 = rx * rx + ry * ry + rz * rz;
+        const float inv_r = rsqrtf(r2);
+        const float rlen = r2 * inv_r;
+        const float hm2 = PS_H2 - r2;
+        const float qq = (hm2 * hm2 * hm2) * inv_den;
+        const float q2 = qq * qq;
+        const float s = li + lj + (-PS_K_P * q2 * q2);
+        if (rlen >= 0.0001f) {
+            const float hm = PS_H - rlen;
+            const float c = s * ((-PS_SPIKY * hm * hm) * inv_r);
+            dx += rx * c; dy += ry * c; dz += rz * c;
+        } else {  // coincident: the reference nudges along +y, (0,EPS,0,0) * -SPIKY * (H-r)^2 (:625-626)
+            const float rl = (r2 > 0.f) ? rlen : 0.f;
+            const float hm = PS_H - rl;
+            dy += s * (PS_EPS * -PS_SPIKY * hm * hm);
+        }
+    }
+};
+__device__ __forceinline__ float delta_p_inv_den() {
+    const float term2 = PS_H2 - (PS_DQ_P * PS_DQ_P * PS_H2);
+    return __fdividef(1.f, term2 * term2 * term2);
+}
+
+// K7 from the neighbour lists K6 left behind: no search, no shared memory; rows are read 4 at a time so that four
+// position / lambda gathers are in flight per lane.
+constexpr int kListBlock = 256;
+__global__ void __launch_bounds__(kListBlock) k_solve_fluids_list(float4 *__restrict__ pos, const float *__restrict__ lambda,
+                                                                  const float4 *__restrict__ spos, const int *__restrict__ sphase,
+                                                                  const u32 *__restrict__ index, const float *__restrict__ ros,
+                                                                  const u32 *__restrict__ nbr_list, const u32 *__restrict__ nbr_rows, u32 max_rows,
+                                                                  u32 n, u32 n_owned, float omega) {
+    const u32 i = blockIdx.x * kListBlock + threadIdx.x;
+    if (i >= n) return;
+    const u32 warp = i >> 5;
+    const u32 rows = nbr_rows[warp];
+    if (rows == kListOverflow || rows == 0) return;  // overflowed warps are redone by k_solve_fluids
+    if (sphase[i] != PH_FLUID) return;
+    const u32 orig = index[i];
+    if (orig >= n_owned) return;
+    const float4 pi = spos[i];
+    DeltaP f{lambda[i], delta_p_inv_den(), 0.f, 0.f, 0.f, lambda};
+    const u32 *L = nbr_list + ((size_t)warp * max_rows) * 32 + (threadIdx.x & 31);
+    u32 nn = 0;
+    for (u32 r = 0; r < rows; r += 4) {  // rows is a multiple of kQ (4 or 8 ...)
+        u32 j[4];
+        float4 pj[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) j[k] = __ldg(L + (r + k) * 32);
+#pragma unroll
+        for (int k = 0; k < 4; k++) pj[k] = __ldg(spos + (j[k] != kNoNeighbor ? j[k] : i));
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (j[k] != kNoNeighbor) {
+                f(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z, j[k]);
+                nn++;
+            }
+    }
+    const float inv_div = __fdividef(omega, ros[orig] + (float)nn);
+    float4 P = pos[orig];
+    P.x += f.dx * inv_div; P.y += f.dy * inv_div; P.z += f.dz * inv_div;
+    pos[orig] = P;
+}
+
+// K7 by walking the grid again: the whole pass when no lists are kept, else only the warps whose list overflowed
 template <int RAD>
 __global__ void __launch_bounds__(kBlock) k_solve_fluids(float4 *__restrict__ pos, const float *__restrict__ lambda,
                                                          const float4 *__restrict__ spos, const int *__restrict__ sphase,
                                                          const u32 *__restrict__ index, const u32 *__restrict__ cell_begin,
                                                          const float *__restrict__ ros, u32 n, u32 n_owned, GridDesc g, StencilDesc st,
-                                                         float omega) {
-    extern __shared__ float4 fluid_smem[];
-    // s_corr = -K_P * (poly6(r) / poly6(dq*H))^4 ; the POLY6 factors cancel (integration_kernel.cuh:630-634)
-    const float term2 = PS_H2 - (PS_DQ_P * PS_DQ_P * PS_H2);
-    const float inv_den = __fdividef(1.f, term2 * term2 * term2);
-    for_each_slot(g, cell_begin, n, [&](const u32 i, bool act) {
-        act = act && sphase[i] == PH_FLUID;
-        u32 orig = 0;
-        if (act) {
-            orig = index[i];
-            act = orig < n_owned;
-        }
-        if (!__any_sync(kFull, act)) return;
-        const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
-        const float li = act ? lambda[i] : 0.f;
-
-        float dx = 0.f, dy = 0.f, dz = 0.f;
-        const u32 nn = walk_fluid_neighbours<RAD, true>(g, st, cell_begin, spos, act, i, pi, fluid_smem, [&](const float4 e) {
-            const float lj = __ldg(lambda + __float_as_uint(e.w));
-            const float r2 = e.x * e.x + e.y * e.y + e.z * e.z;
-            const float inv_r = rsqrtf(r2);
-            const float rlen = r2 * inv_r;
-            const float hm2 = PS_H2 - r2;
-            const float qq = (hm2 * hm2 * hm2) * inv_den;
-            const float q2 = qq * qq;
-            const float s = li + lj + (-PS_K_P * q2 * q2);
-            if (rlen >= 0.0001f) {
-                const float hm = PS_H - rlen;
-                const float c = s * ((-PS_SPIKY * hm * hm) * inv_r);
-                dx += e.x * c; dy += e.y * c; dz += e.z * c;
-            } else {  // coincident: the reference nudges along +y, (0,EPS,0,0) * -SPIKY * (H-r)^2 (:625-626)
-                const float rl = (r2 > 0.f) ? rlen : 0.f;
-                const float hm = PS_H - rl;
-                dy += s * (PS_EPS * -PS_SPIKY * hm * hm);
-            }
-        });
-        if (!act) return;
-        const float inv_div = __fdividef(omega, ros[orig] + (float)nn);
-        float4 P = pos[orig];
-        P.x += dx * inv_div; P.y += dy * inv_div; P.z += dz * inv_div;
-        pos[orig] = P;
-    });
+                                                         float omega, const u32 *__restrict__ nbr_rows) {
+    extern __shared__ u32 fluid_smem[];
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    if (nbr_rows && ((u64)(i >> 5) * 32 >= n || nbr_rows[i >> 5] != kListOverflow)) return;  // warp-uniform
+    bool act = i < n && sphase[i] == PH_FLUID;
+    u32 orig = 0;
+    if (act) {
+        orig = index[i];
+        act = orig < n_owned;
+    }
+    if (!__any_sync(kFull, act)) return;
+    const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
+    DeltaP f{act ? lambda[i] : 0.f, delta_p_inv_den(), 0.f, 0.f, 0.f, lambda};
+    NeighborListWriter nl;
+    nl.list = nullptr; nl.max_rows = 0; nl.rows = 0; nl.overflow = false;
+    const u32 nn = walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, nl, f);
+    if (!act) return;
+    const float inv_div = __fdividef(omega, ros[orig] + (float)nn);
+    float4 P = pos[orig];
+    P.x += f.dx * inv_div; P.y += f.dy * inv_div; P.z += f.dz * inv_div;
+    pos[orig] = P;
 }
 
 // ------------------------------------------------------------------ K5: contacts + friction ------------------------------------------------------------------
@@ -498,15 +506,6 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
 }  // namespace
 
 static inline u32 cdiv(u32 a, u32 b) { return (a + b - 1) / b; }
-static inline dim3 fluid_grid(u32 n, const GridDesc &g) {
-#if PS_FMAP == 0
-    (void)g;
-    return dim3(cdiv(n, kBlock));
-#else
-    (void)n;  // one CTA per brick of cells; bricks without particles (most of a sparse grid) exit after two loads
-    return dim3(cdiv(g.gx, kBrickX), g.gy / kBrickY, g.gz / kBrickZ);
-#endif
-}
 
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                        const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, cudaStream_t s) {
@@ -517,38 +516,42 @@ void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, cons
     k_collide<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, prev, spos, sw, sphase, index, cell_begin, num_neighbors, n, n_owned, g, st, radius);
 }
 
+size_t ps_neighbor_list_elems(u64 capacity, u32 max_rows) { return (size_t)((capacity + 31) / 32) * max_rows * 32; }
+
 void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                             const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
-                            const StencilDesc &st, bool zero_nonfluid, cudaStream_t s) {
+                            const StencilDesc &st, bool zero_nonfluid, u32 *nbr_list, u32 *nbr_rows, u32 max_rows, cudaStream_t s) {
     if (!n) return;
     const size_t sm = fluid_smem_bytes(st.rad);
     static const cudaError_t optin = cudaFuncSetAttribute(k_find_lambdas<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
     (void)optin;
-#ifdef PS_CARVEOUT
-    static const cudaError_t carve = cudaFuncSetAttribute(k_find_lambdas<4>, cudaFuncAttributePreferredSharedMemoryCarveout, PS_CARVEOUT);
-    (void)carve;
-#endif
+    if (!nbr_list) nbr_rows = nullptr;
     if (st.rad == 4)  // the reference's configuration (H = 2, cell = 2r = 0.5): stencil loops fully unrolled
-        k_find_lambdas<4><<<fluid_grid(n, g), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin, ghost_xmax, g, st,
-                                                             zero_nonfluid ? 1 : 0);
+        k_find_lambdas<4><<<cdiv(n, kBlock), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin,
+                                                             ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, max_rows);
     else
-        k_find_lambdas<0><<<fluid_grid(n, g), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin, ghost_xmax, g, st,
-                                                             zero_nonfluid ? 1 : 0);
+        k_find_lambdas<0><<<cdiv(n, kBlock), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin,
+                                                             ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, max_rows);
 }
 
-void ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
-                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
-                            cudaStream_t s) {
-    if (!n) return;
+// nbr_list != nullptr: K7 from the lists K6 wrote, then the grid walk for overflowed warps only; else the grid walk for all
+u32 ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
+                           const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
+                           const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s) {
+    if (!n) return 0;
     const size_t sm = fluid_smem_bytes(st.rad);
     static const cudaError_t optin = cudaFuncSetAttribute(k_solve_fluids<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
     (void)optin;
-#ifdef PS_CARVEOUT
-    static const cudaError_t carve = cudaFuncSetAttribute(k_solve_fluids<4>, cudaFuncAttributePreferredSharedMemoryCarveout, PS_CARVEOUT);
-    (void)carve;
-#endif
+    u32 launches = 1;
+    if (nbr_list) {
+        k_solve_fluids_list<<<cdiv(n, kListBlock), kListBlock, 0, s>>>(pos, lambda, spos, sphase, index, ros, nbr_list, nbr_rows, max_rows, n, n_owned, omega);
+        launches++;
+    } else {
+        nbr_rows = nullptr;
+    }
     if (st.rad == 4)
-        k_solve_fluids<4><<<fluid_grid(n, g), kBlock, sm, s>>>(pos, lambda, spos, sphase, index, cell_begin, ros, n, n_owned, g, st, omega);
+        k_solve_fluids<4><<<cdiv(n, kBlock), kBlock, sm, s>>>(pos, lambda, spos, sphase, index, cell_begin, ros, n, n_owned, g, st, omega, nbr_rows);
     else
-        k_solve_fluids<0><<<fluid_grid(n, g), kBlock, sm, s>>>(pos, lambda, spos, sphase, index, cell_begin, ros, n, n_owned, g, st, omega);
+        k_solve_fluids<0><<<cdiv(n, kBlock), kBlock, sm, s>>>(pos, lambda, spos, sphase, index, cell_begin, ros, n, n_owned, g, st, omega, nbr_rows);
+    return launches;
 }

@@ -139,9 +139,9 @@ void solveFluids(float *sortedPos, float *sortedW, int *sortedPhase, uint *index
     PsCtx *c = ctx();
     need_dense(cellStart, numCells, "solveFluids");
     ps_launch_find_lambdas(c->lambda, c->num_neighbors, (const float4 *)sortedPos, sortedW, sortedPhase, index, c->cell_begin, c->ros, n, n,
-                           -3.0e38f, 3.0e38f, c->grid, c->stencil, false, c->stream);
+                           -3.0e38f, 3.0e38f, c->grid, c->stencil, false, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
     ps_launch_solve_fluids((float4 *)particles, c->lambda, (const float4 *)sortedPos, sortedPhase, index, c->cell_begin, c->ros, n, n, c->grid,
-                           c->stencil, 1.0f, c->stream);
+                           c->stencil, 1.0f, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
     ck_launch("solveFluids");
 }
 

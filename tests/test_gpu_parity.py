@@ -248,3 +248,22 @@ def test_fluid_neighbour_cap_500():
     np.testing.assert_allclose(sol.download(psb.ARR_LAMBDA), o.lam, rtol=H.LAMBDA_RTOL, atol=1e-5)
     assert H.max_abs(sol.download(psb.ARR_POS), o.pos) <= H.POS_ATOL
     sol.close()
+
+
+def test_neighbour_list_paths_agree_bit_for_bit():
+    """K7 from K6's neighbour lists, K7 re-walking the grid (no lists kept), and the overflow fallback (lists too short for
+    every warp) take the same neighbours in the same order: identical bits."""
+    results = []
+    for rows in (256, 0, 8, 64):
+        ps = psb.ParticleSystem.scene("3")  # two fluids, walls
+        sol = ps.solver
+        p = sol.params
+        p.neighbor_list_rows = rows
+        sol.set_params(p)
+        for _ in range(2):
+            ps.update(DT)
+        results.append((sol.download(psb.ARR_POS).copy(), sol.download(psb.ARR_LAMBDA).copy(), sol.download(psb.ARR_NUM_NEIGHBORS).copy()))
+        ps.close()
+    for pos, lam, nn in results[1:]:
+        assert np.array_equal(nn, results[0][2]) and np.array_equal(lam, results[0][1]) and np.array_equal(pos, results[0][0])
+    assert results[0][2].max() > 64  # 64 rows cannot hold every warp's lists: that run mixed list warps and fallback warps
