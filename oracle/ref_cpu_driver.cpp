@@ -22,7 +22,15 @@
 #include "includes.h"
 #define private public
 #include "simulation.h"
+#include "totalfluidconstraint.h"
 #undef private
+
+// The reference draws glibc rand() for scene jitter and, every solver iteration, for the wall jitter of fluid particles
+// (cpu/src/constraint/boundaryconstraint.cpp:19).  rand() is random() under the hood (same state, same algorithm), so this
+// definition — which takes precedence over libc's for every translation unit of the executable — keeps the stream bit
+// for bit and counts the draws: a parity run must start at the same position of the stream.
+static long g_rand_calls = 0;
+extern "C" int rand(void) { g_rand_calls++; return (int)random(); }
 
 static SimulationType scene_of(const std::string &k) {
     // key bindings of cpu/src/view.cpp:121-179
@@ -46,11 +54,29 @@ static void dump_state(Simulation &sim, const std::string &dir, int tick) {
     if (!f) { perror("fopen"); exit(1); }
     int n = sim.m_particles.size();
     fwrite(&n, sizeof n, 1, f);
+    // which TotalFluidConstraint (in m_globalConstraints[STANDARD] order) a particle belongs to, -1 if none
+    std::vector<int> fluid(n, -1);
+    QList<Constraint *> &glob = sim.m_globalConstraints[STANDARD];
+    int nf = 0;
+    for (int c = 0; c < glob.size(); c++)
+        if (TotalFluidConstraint *t = dynamic_cast<TotalFluidConstraint *>(glob[c])) {
+            for (int k = 0; k < t->ps.size(); k++) fluid[t->ps[k]] = nf;
+            nf++;
+        }
     for (int i = 0; i < n; i++) {
         Particle *p = sim.m_particles[i];
-        double rec[8] = {p->p.x, p->p.y, p->v.x, p->v.y, p->imass, (double)p->ph, (double)p->bod, 0.0};
+        double rec[8] = {p->p.x, p->p.y, p->v.x, p->v.y, p->imass, (double)p->ph, (double)p->bod, (double)fluid[i]};
         fwrite(rec, sizeof rec, 1, f);
     }
+    fclose(f);
+    snprintf(name, sizeof name, "%s/tick%05d.txt", dir.c_str(), tick);
+    f = fopen(name, "w");
+    fprintf(f, "n %d\nrand_calls %ld\nke %.17g\nxbounds %.17g %.17g\nybounds %.17g %.17g\ngravity %.17g %.17g\nfluids %d", n, g_rand_calls,
+            sim.getKineticEnergy(), sim.m_xBoundaries.x, sim.m_xBoundaries.y, sim.m_yBoundaries.x, sim.m_yBoundaries.y, sim.m_gravity.x,
+            sim.m_gravity.y, nf);
+    for (int c = 0; c < glob.size(); c++)
+        if (TotalFluidConstraint *t = dynamic_cast<TotalFluidConstraint *>(glob[c])) fprintf(f, " %.17g", t->p0);
+    fprintf(f, "\n");
     fclose(f);
 }
 

@@ -49,6 +49,11 @@ class Params(C.Structure):
                 ("omega", C.c_float), ("flags", C.c_uint32), ("neighbor_list_rows", C.c_uint32)]
 
 
+class Params2D(C.Structure):
+    """Ps2dParams (include/psolver2d.h): bounds, gravity and iteration count of the reference's CPU Simulation."""
+    _fields_ = [("x_bounds", C.c_double * 2), ("y_bounds", C.c_double * 2), ("gravity", C.c_double * 2), ("solver_iterations", C.c_uint32)]
+
+
 _lib = None
 
 
@@ -139,6 +144,24 @@ def lib():
                   "pshost_set_particle_to_add", "pshost_set_fluid_to_add", "pshost_make_point_constraint",
                   "pshost_make_distance_constraint", "pshost_get_positions", "pshost_get_velocities"):
             getattr(L, f).restype = None
+        # 2-D double-precision path (include/psolver2d.h)
+        L.ps2d_default_params.argtypes = [C.POINTER(Params2D)]
+        L.ps2d_default_params.restype = None
+        L.ps2d_create.argtypes = [i32, C.POINTER(Params2D), u64, C.POINTER(vp)]
+        L.ps2d_destroy.argtypes = [vp]
+        L.ps2d_create_fluid.argtypes = [vp, vp, vp, vp, u64, C.c_double]
+        L.ps2d_seed_rand.argtypes = [vp, u32, u64]
+        L.ps2d_rand_calls.argtypes = [vp]
+        L.ps2d_rand_calls.restype = u64
+        L.ps2d_tick.argtypes = [vp, C.c_double]
+        L.ps2d_num_particles.argtypes = [vp]
+        L.ps2d_num_particles.restype = u64
+        L.ps2d_last_num_boundary_constraints.argtypes = [vp]
+        L.ps2d_last_num_boundary_constraints.restype = u32
+        L.ps2d_launches_per_tick.argtypes = [vp]
+        L.ps2d_launches_per_tick.restype = u32
+        L.ps2d_download.argtypes = [vp, i32, vp]
+        L.ps2d_kinetic_energy.argtypes = [vp, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -421,3 +444,66 @@ class ParticleSystem:
         a = np.empty((self.getNumParticles(), 4), np.float32)
         lib().pshost_get_velocities(self._h, _ptr(a))
         return a
+
+
+class Simulation2D:
+    """The 2-D double-precision path: the reference CPU application's Simulation::tick (cpu/src/simulation.cpp:115-369) on
+    the GPU for all-fluid scenes; `createFluid`, `tick`, `getNumParticles`, `getKineticEnergy` keep the reference's names."""
+
+    def __init__(self, x_bounds=(-8.0, 8.0), y_bounds=(-8.0, 40.0), gravity=(0.0, -9.8), iterations=3, max_particles=1 << 16, device=0):
+        p = Params2D()
+        lib().ps2d_default_params(C.byref(p))
+        p.x_bounds[:], p.y_bounds[:], p.gravity[:] = tuple(x_bounds), tuple(y_bounds), tuple(gravity)
+        p.solver_iterations = iterations
+        h = C.c_void_p()
+        _check(lib().ps2d_create(device, C.byref(p), max_particles, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ps2d_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def createFluid(self, positions, density, velocities=None, inv_mass=None):
+        p = _arr(positions, np.float64).reshape(-1, 2)
+        v = _arr(velocities if velocities is not None else np.zeros_like(p), np.float64).reshape(-1, 2)
+        w = _arr(inv_mass if inv_mass is not None else np.ones(p.shape[0]), np.float64).reshape(-1)
+        _check(lib().ps2d_create_fluid(self._h, _ptr(p), _ptr(v), _ptr(w), p.shape[0], density))
+
+    def seedRand(self, seed=1, skip=0):
+        _check(lib().ps2d_seed_rand(self._h, seed, skip))
+
+    @property
+    def rand_calls(self):
+        return int(lib().ps2d_rand_calls(self._h))
+
+    def tick(self, seconds=0.01):
+        _check(lib().ps2d_tick(self._h, seconds))
+
+    def getNumParticles(self):
+        return int(lib().ps2d_num_particles(self._h))
+
+    def getKineticEnergy(self):
+        e = C.c_double()
+        _check(lib().ps2d_kinetic_energy(self._h, C.byref(e)))
+        return e.value
+
+    @property
+    def num_boundary_constraints(self):
+        return int(lib().ps2d_last_num_boundary_constraints(self._h))
+
+    @property
+    def launches_per_tick(self):
+        return int(lib().ps2d_launches_per_tick(self._h))
+
+    def _get(self, which, width):
+        a = np.empty((self.getNumParticles(), width) if width > 1 else self.getNumParticles(), np.float64)
+        _check(lib().ps2d_download(self._h, which, _ptr(a)))
+        return a
+
+    def positions(self): return self._get(0, 2)
+    def velocities(self): return self._get(1, 2)
+    def estimates(self): return self._get(2, 2)
+    def lambdas(self): return self._get(3, 1)

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpsolver.so")
 OBJ = os.path.join(HERE, "build")
 CU_SOURCES = ["ps_stream_kernels.cu", "ps_grid_kernels.cu", "ps_sort_kernels.cu", "ps_neighbor_kernels.cu", "ps_slab_kernels.cu", "ps_context.cu",
-              "ps_reference_abi.cu"]
+              "ps_reference_abi.cu", "ps2d.cu"]
 CPP_SOURCES = ["particle_system.cpp"]
 # -use_fast_math mirrors the reference's own build flags (gpu/particles_cuda.pro:153-158): div.approx / sqrt.approx /
 # ftz are parity-relevant, see SURVEY Appendix A.1
@@ -58,7 +58,10 @@ def build_all(force=False, verbose=False):
         o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _newer(s, o, headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(HERE, "..", "include"), "-c", s, "-o", o]
+            flags = list(NVCC_FLAGS)
+            if src == "ps2d.cu":  # double-precision parity path: IEEE arithmetic without contraction, like the x86-64 reference
+                flags = [f for f in flags if f != "-use_fast_math"] + ["-fmad=false"]
+            cmd = [nvcc, *flags, "-I", os.path.join(HERE, "..", "include"), "-c", s, "-o", o]
             if src.endswith(".cpp"):  # host class: plain g++, IEEE arithmetic without contraction (scene parity)
                 cuda_inc = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc))), "include")
                 cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-I",

@@ -29,6 +29,14 @@ def test_psolver_h_symbols_exported():
     assert not missing, f"declared in include/psolver.h but not exported: {missing}"
 
 
+def test_psolver2d_h_symbols_exported():
+    L = psb.lib()
+    names = _declared("psolver2d.h", r"\b(ps2d_[a-z_0-9]+)\s*\(")
+    assert len(names) >= 12
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, f"declared in include/psolver2d.h but not exported: {missing}"
+
+
 def test_reference_abi_symbols_exported():
     """Same names as the reference's wrappers.cuh:12-97 and shared_variables.cuh:13-36."""
     L = psb.lib()
@@ -71,6 +79,8 @@ def test_no_cpu_fallback():
         psb.Solver(psb.default_params(), max_particles=16)
     with pytest.raises(psb.PsError):
         psb.ParticleSystem()
+    with pytest.raises(psb.PsError):
+        psb.Simulation2D()
 
 
 def test_bad_params_rejected_before_touching_the_device():
@@ -87,4 +97,4 @@ def test_product_never_touches_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
-                assert "oracle_py" not in src and "libpsoracle" not in src and "gpu_step_oracle" not in src, f
+                assert "oracle_py" not in src and "libpsoracle" not in src and "gpu_step_oracle" not in src and "cpu2d_oracle" not in src, f

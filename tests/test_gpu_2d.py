@@ -1,0 +1,91 @@
+"""Config C1 on the GPU: the 2-D double-precision path (include/psolver2d.h) against the reference's own unmodified CPU
+solver on its scene 6 (golden states tests/golden/ref_cpu_scene6.npz) and against the numpy oracle tick by tick.
+Tolerance: |dp| <= 1e-9 after 1, 2, 3 ticks, 1e-8 after 10 (double precision; the only differences are libm vs CUDA
+pow/sqrt rounding); kinetic energy after 1 tick to 1e-9 relative, after 100 ticks to 1e-4 relative."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import particlesolver_b200 as psb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import cpu2d_oracle as c2d  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(ROOT, "tests", "golden", "ref_cpu_scene6.npz"))
+
+
+def build_scene6():
+    sim = psb.Simulation2D(tuple(G["xbounds"]), tuple(G["ybounds"]), tuple(G["gravity"]), iterations=3, max_particles=1024)
+    for f, rho0 in enumerate(G["rho0"]):
+        m = G["fluid"] == f
+        assert np.array_equal(np.nonzero(m)[0], np.arange(m.sum()) + (0 if f == 0 else (G["fluid"] < f).sum()))  # fluids are index ranges
+        sim.createFluid(G["p0"][m], float(rho0), G["v0"][m], G["imass"][m])
+    sim.seedRand(1, int(G["rand_calls0"]))
+    return sim
+
+
+def test_scene6_ticks_match_reference_cpu_solver():
+    sim = build_scene6()
+    assert sim.getNumParticles() == 432
+    dt = float(G["dt"])
+    for t in range(1, 11):
+        sim.tick(dt)
+        if f"p{t}" in G.files:
+            dp = np.abs(sim.positions() - G[f"p{t}"]).max()
+            dv = np.abs(sim.velocities() - G[f"v{t}"]).max()
+            tol = 1e-9 if t <= 3 else 1e-8
+            assert dp <= tol and dv <= tol * 100, f"tick {t}: |dp| {dp:.3e} |dv| {dv:.3e}"
+            assert sim.rand_calls == int(G[f"rand_calls{t}"]), "wall-jitter draws per tick differ from the reference"
+        if t == 1:
+            assert abs(sim.getKineticEnergy() - float(G["ke1"])) <= 1e-9 * float(G["ke1"])
+            assert sim.num_boundary_constraints == (int(G["rand_calls1"]) - int(G["rand_calls0"])) // 3
+    assert sim.launches_per_tick > 0
+    sim.close()
+
+
+def test_scene6_100_ticks_energy_and_oracle_lockstep():
+    sim = build_scene6()
+    o = c2d.Cpu2dOracle(G["p0"], G["v0"], G["imass"], G["fluid"], G["rho0"], G["xbounds"], G["ybounds"], G["gravity"], rand_skip=int(G["rand_calls0"]))
+    dt = float(G["dt"])
+    worst = 0.0
+    for t in range(1, 101):
+        sim.tick(dt)
+        if t <= 20:  # the oracle tick by tick (after that both follow the same, slowly diverging, chaotic trajectory)
+            o.tick(dt)
+            worst = max(worst, np.abs(sim.positions() - o.p).max())
+    assert worst <= 1e-8, worst
+    ke = sim.getKineticEnergy()
+    assert abs(ke - float(G["ke_every_100"][0])) <= 1e-4 * ke, (ke, float(G["ke_every_100"][0]))
+    assert np.abs(sim.positions() - G["p100"]).max() <= 1e-4
+    sim.close()
+
+
+def test_scene6_1000_ticks_energy_statistics():
+    """long run: kinetic energy every 100 ticks inside a band around the reference CPU solver's series"""
+    sim = build_scene6()
+    dt = float(G["dt"])
+    ke = []
+    for t in range(1, 1001):
+        sim.tick(dt)
+        if t % 100 == 0:
+            ke.append(sim.getKineticEnergy())
+    ref = G["ke_every_100"]
+    assert np.isfinite(sim.positions()).all()
+    for k, (a, b) in enumerate(zip(ke, ref)):
+        assert 0.5 * b <= a <= 2.0 * b, f"tick {(k + 1) * 100}: KE {a:.1f} vs reference {b:.1f}"
+    x, y = sim.positions().T
+    assert x.min() >= -8 and x.max() <= 8 and y.min() >= -8  # inside the box (a fluid projection may undo part of a wall clamp)
+
+
+def test_2d_rejects_what_is_out_of_scope():
+    sim = psb.Simulation2D(max_particles=8)
+    with pytest.raises(psb.PsError):
+        sim.createFluid(np.zeros((2, 2)), 1.0, inv_mass=[1.0, 0.0])   # "A fluid cannot have a point of infinite mass."
+    with pytest.raises(psb.PsError):
+        sim.createFluid(np.zeros((20, 2)), 1.0)                        # capacity
+    sim.tick(0.01)  # empty: no-op
+    sim.close()
