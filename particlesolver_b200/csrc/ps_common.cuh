@@ -103,11 +103,12 @@ struct SortScratch {
     u32 *status;  // [passes][tiles][256] decoupled look-back words
     u32 *ticket;  // [4] dynamic tile ids
 };
-size_t ps_sort_status_elems(u32 n, int passes);
+size_t ps_sort_status_elems(u32 n, int passes);  // whole scratch: histograms + tickets + status words
+SortScratch ps_sort_scratch_layout(u32 *base);
 int ps_sort_passes(u32 num_cells);
 // Stable LSD radix sort of (key,val) pairs on the low 8*passes key bits, ping-ponging between (kA,vA) and
 // (kB,vB): input in A, result in A when `passes` is even and in B when it is odd (the caller picks where the
-// unsorted keys are written so that the result lands where it wants it).  3 + passes launches + 3 memsets.
+// unsorted keys are written so that the result lands where it wants it).  1 + passes launches + 1 memset.
 // identity_vals: vals[i]==i on entry is assumed and vA is never read (saves one 4 B/particle read).
 void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool identity_vals, SortScratch sc, cudaStream_t s);
 // ps_neighbor_kernels.cu

@@ -196,9 +196,7 @@ int ps_ctx_emit_reference_tables(PsCtx *c) {
 
 SortScratch ps_ctx_sort_scratch(PsCtx *c, u32) {
     SortScratch sc;
-    sc.hist = c->sort_hist;
-    sc.status = c->sort_status;
-    sc.ticket = c->sort_ticket;
+    sc = ps_sort_scratch_layout(c->sort_status);
     return sc;
 }
 
@@ -232,9 +230,6 @@ int ps_create_internal(int device, const PsParams *params, uint64_t max_particle
     c->own_stream = !legacy_default_stream;
     if (c->own_stream && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { ps_set_error("cudaStreamCreate failed"); return fail(PS_ERR_CUDA); }
     if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) { ps_set_error("cudaEventCreate failed"); return fail(PS_ERR_CUDA); }
-    if (cudaMalloc((void **)&c->sort_hist, 4 * 256 * sizeof(u32)) != cudaSuccess || cudaMalloc((void **)&c->sort_ticket, 4 * sizeof(u32)) != cudaSuccess) {
-        ps_set_error("cudaMalloc failed"); return fail(PS_ERR_CUDA);
-    }
     c->rands_iters = 64;
     if (cudaMalloc((void **)&c->rands, c->rands_iters * 6 * sizeof(float)) != cudaSuccess) { ps_set_error("cudaMalloc failed"); return fail(PS_ERR_CUDA); }
     cudaMemsetAsync(c->rands, 0, c->rands_iters * 6 * sizeof(float), c->stream);
@@ -257,8 +252,8 @@ extern "C" int ps_destroy(PsCtx *c) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->gen) curandDestroyGenerator(c->gen);
     void *ptrs[] = {c->pos, c->vel, c->prev, c->spos, c->w, c->ros, c->sw, c->lambda, c->phase, c->sphase, c->hash, c->index, c->hash_tmp,
-                    c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->chunk_lb, c->sort_hist,
-                    c->sort_status, c->sort_ticket, c->rands, c->slab_scratch, c->nbr_list, c->nbr_rows, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
+                    c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->chunk_lb,
+                    c->sort_status, c->rands, c->slab_scratch, c->nbr_list, c->nbr_rows, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
                     c->d_point_xyz, c->dist_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->slab_counts_host) cudaFreeHost(c->slab_counts_host);
@@ -438,7 +433,7 @@ u32 ps_issue_build_grid(PsCtx *c, const float4 *pos) {
     ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s);
     c->grid_valid = true;
     c->ref_tables_valid = false;
-    // kernels only (the 3 memset nodes of the sort are not counted): calc_hash 1 + hist 1 + passes + reorder 1 + cell_begin 1
+    // kernels only (the memset node of the sort is not counted): calc_hash 1 + hist 1 + passes + reorder 1 + cell_begin 1
     return 1 + 1 + (u32)c->sort_passes + 1 + 1;
 }
 

@@ -41,7 +41,7 @@ struct PsCtx {
     bool ref_tables_valid = false;
     uint64_t cell_capacity = 0;
     // sort scratch
-    u32 *sort_hist = nullptr, *sort_status = nullptr, *sort_ticket = nullptr;
+    u32 *sort_status = nullptr;  // histograms | tickets | look-back status words (ps_sort_scratch_layout)
     size_t sort_status_elems = 0;
     // wall jitter uniforms, [iterations][6]
     float *rands = nullptr;

@@ -146,6 +146,7 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
                 const float4 pj = __ldg(spos + j);  // an L1 hit: the line was gathered a few instructions ago
                 body(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z, j);
             }
+        nn += cnt;  // accepted neighbours are counted when they leave the queue
         cnt = 0;
     };
 
@@ -203,7 +204,7 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
         // ---- phase 2: flat walk over the list; the trip count is the warp's largest candidate total ----
         const u32 maxtotal = __reduce_max_sync(kFull, total);
         if (maxtotal == 0) continue;
-        const bool capped = __any_sync(kFull, nn + total > PS_MAX_NEIGHBORS);  // the 500-neighbour cap can bite in this slab
+        const bool capped = __any_sync(kFull, nn + (u32)cnt + total > PS_MAX_NEIGHBORS);  // the 500-neighbour cap can bite in this slab
         // Software pipeline: the positions of candidates t+1 and t+2 are requested before candidate t is tested, so each
         // lane keeps two gathers in flight (at 8 warps per scheduler one was not enough to cover an L2 hit).
         u32 jb = 0, rem_seg = 0, li = 0;
@@ -216,33 +217,32 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
             rem_seg--;
             return jb++;
         };
-        u32 j0 = 0, j1 = 0;
-        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        // A lane that has run out of candidates keeps re-testing its own slot, which is never accepted (j != i): the loop
+        // body then needs no per-lane guard, only the refill is predicated.
+        u32 j0 = i, j1 = i;
+        float4 p0 = pi, p1 = pi;
         if (total > 0) { j0 = next_j(); p0 = __ldg(spos + j0); }
         if (total > 1) { j1 = next_j(); p1 = __ldg(spos + j1); }
         auto walk = [&](auto capped_c) {
+            constexpr bool kCapped = decltype(capped_c)::value;
             auto test = [&](const u32 j, const float4 pj) {
                 const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
                 const float r2 = rx * rx + ry * ry + rz * rz;
-                if (r2 < PS_H2 && j != i && (!decltype(capped_c)::value || nn < PS_MAX_NEIGHBORS)) {
-                    q[cnt][tid] = j;
-                    cnt++;
-                    nn++;
-                }
+                if (r2 < PS_H2 && j != i && (!kCapped || nn + cnt < PS_MAX_NEIGHBORS)) q[cnt++][tid] = j;
             };
 #pragma unroll 1
             for (u32 t = 0; t < maxtotal; t += 2) {
-                if (t < total) {
+                {
                     const u32 j = j0;
                     const float4 pj = p0;
-                    if (t + 2 < total) { j0 = next_j(); p0 = __ldg(spos + j0); }
+                    if (t + 2 < total) { j0 = next_j(); p0 = __ldg(spos + j0); } else { j0 = i; }
                     test(j, pj);
                 }
                 if (__any_sync(kFull, cnt == kQ)) flush();
-                if (t + 1 < total) {
+                {
                     const u32 j = j1;
                     const float4 pj = p1;
-                    if (t + 3 < total) { j1 = next_j(); p1 = __ldg(spos + j1); }
+                    if (t + 3 < total) { j1 = next_j(); p1 = __ldg(spos + j1); } else { j1 = i; }
                     test(j, pj);
                 }
                 if (__any_sync(kFull, cnt == kQ)) flush();

@@ -37,16 +37,25 @@ __global__ void __launch_bounds__(kThreads) k_radix_hist(const u32 *__restrict__
         } else {
             for (int j = 0; j < 4; j++) k[j] = (i + j < n) ? keys[i + j] : 0xffffffffu;
         }
-        // warp-aggregated shared atomics: cell-sorted-ish keys share their high digits across the whole warp
+        // Cell keys of consecutive particles share their high digits: when a digit is uniform across the warp one lane
+        // adds 32, otherwise plain shared atomics (few conflicts: the digit varies).  No match.any, which is slow.
         const u32 active = __activemask();
         const u32 lane = threadIdx.x & 31;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            bool ok = i + j < n;
+            const bool ok = i + j < n;
             for (int p = 0; p < passes; p++) {
-                u32 d = ok ? ((k[j] >> (8 * p)) & 255u) : 256u;
-                u32 grp = __match_any_sync(active, d);
-                if (ok && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&sh[p * 256 + d], (u32)__popc(grp));
+                const u32 d = (k[j] >> (8 * p)) & 255u;
+                bool uniform = false;
+                if (active == 0xffffffffu) {  // whole warp in the loop (always, except in the last grid-stride round)
+                    const u32 d0 = __shfl_sync(0xffffffffu, d, 0);
+                    uniform = __all_sync(0xffffffffu, ok && d == d0);
+                }
+                if (uniform) {
+                    if (lane == 0) atomicAdd(&sh[p * 256 + d], 32u);
+                } else if (ok) {
+                    atomicAdd(&sh[p * 256 + d], 1u);
+                }
             }
         }
     }
@@ -95,7 +104,17 @@ __global__ void __launch_bounds__(kThreads) k_radix_pass(const u32 *__restrict__
     for (int k = 0; k < kItems; k++) {
         u32 loc = wbase + k * 32 + lane;
         bool ok = loc < nt;
-        u32 d = (key[k] >> shift) & 255u;
+        const u32 d = (key[k] >> shift) & 255u;
+        // uniform digit across the warp (the rule for the high digits of nearly sorted cell keys): rank = lane, no match.any
+        const u32 d0 = __shfl_sync(0xffffffffu, d, 0);
+        if (__all_sync(0xffffffffu, ok && d == d0)) {
+            const u32 prev = s_warp_cnt[wid][d0];
+            __syncwarp();
+            if (lane == 0) s_warp_cnt[wid][d0] = prev + 32u;
+            __syncwarp();
+            rank[k] = prev + lane;
+            continue;
+        }
         u32 grp = __match_any_sync(0xffffffffu, ok ? d : 256u);
         u32 prev = 0;
         if (ok) prev = s_warp_cnt[wid][d];
@@ -187,17 +206,24 @@ int ps_sort_passes(u32 num_cells) {
     return p < 1 ? 1 : p;
 }
 
+constexpr size_t kSortHeaderElems = 4 * 256 + 8;  // [4][256] histograms, 4 tickets (+4 pad)
 size_t ps_sort_status_elems(u32 n, int passes) {
     size_t tiles = ((size_t)n + kTile - 1) / kTile;
-    return tiles * 256 * (size_t)passes;
+    return kSortHeaderElems + tiles * 256 * (size_t)passes;
+}
+SortScratch ps_sort_scratch_layout(u32 *base) {
+    SortScratch sc;
+    sc.hist = base;
+    sc.ticket = base + 4 * 256;
+    sc.status = base + kSortHeaderElems;
+    return sc;
 }
 
 void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool identity_vals, SortScratch sc, cudaStream_t s) {
     if (!n) return;
     const u32 tiles = (n + kTile - 1) / kTile;
-    cudaMemsetAsync(sc.hist, 0, 4 * 256 * sizeof(u32), s);
-    cudaMemsetAsync(sc.ticket, 0, 4 * sizeof(u32), s);
-    cudaMemsetAsync(sc.status, 0, (size_t)tiles * 256 * passes * sizeof(u32), s);
+    // hist | tickets | status words are one allocation (ps_sort_scratch_layout): one memset node per sort
+    cudaMemsetAsync(sc.hist, 0, (kSortHeaderElems + (size_t)tiles * 256 * passes) * sizeof(u32), s);
     u32 hist_blocks = (n + kThreads * 4 * 4 - 1) / (kThreads * 4 * 4);
     if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
     k_radix_hist<<<hist_blocks, kThreads, 0, s>>>(kA, n, passes, sc.hist);
