@@ -299,8 +299,10 @@ def run_ours(args, rank, world, local_rank):
             traffic = None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac_hbm"], "traffic": traffic, "peak_kind": peak_kind,
-                "note": "neighbour kernels (contacts/lambda/delta_p) are FP32-issue/L1 bound, ~370 candidate tests per particle against "
-                        "36-64 compulsory bytes (SURVEY 8d); streaming kernels are the HBM-bound ones, see 'kernels'"}
+                "note": "the PBF kernels are FP32-issue bound, not HBM bound: ~200 candidate tests + ~140 interactions per particle against "
+                        "36-64 compulsory bytes (SURVEY 8d, DESIGN.md 4).  'traffic' exceeds the algorithmic bytes on purpose: K6 leaves "
+                        "~0.7 KB/particle of neighbour lists in HBM so that K7 does not search again (idle bandwidth traded for issue slots); "
+                        "the HBM-bound streaming kernels are in 'kernels'"}
 
     if rank == 0:
         cpu_v, cpu_n, cpu_sec = time_oracle_port(46, 1)

@@ -17,7 +17,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__throughput.avg.pct_of_peak_sustained_active",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
-STAGE_OF = {"k_find_lambdas": "lambda", "k_solve_fluids": "delta_p", "k_radix_pass": "sort", "k_radix_hist": "sort", "k_reorder": "reorder",
+STAGE_OF = {"k_find_lambdas": "lambda", "k_solve_fluids": "delta_p", "k_solve_fluids_list": "delta_p", "k_radix_pass": "sort", "k_radix_hist": "sort", "k_reorder": "reorder",
             "k_cell_begin": "cell_table", "k_cell_fill": "cell_table", "k_collide_world": "world", "k_collide": "contacts", "k_calc_hash": "hash",
             "k_predict": "predict", "k_velocity": "velocity", "k_lambda": "lambda", "k_delta": "delta_p"}
 
@@ -76,12 +76,13 @@ def traffic(rep):
         k = short(r[ni]).split("<")[0]
         b = to_float(r[ri], units[ri], "B") + to_float(r[wi], units[wi], "B")
         acc[STAGE_OF.get(k, k)][k].append(b)
-    # per stage: sum over the stage's kernels of the mean bytes per launch of that kernel x its launches per stage call is not
-    # recoverable here, so report the mean per launch of each kernel and, for single-kernel stages, the stage value
+    # per stage call: sum over the stage's kernels of (mean bytes per launch) x (launches of that kernel per stage call); the
+    # multiplicity is taken from the launch counts in the capture (e.g. k_radix_pass runs P times per k_radix_hist)
     out = {}
     for stage, ks in acc.items():
-        per_kernel = {k: sum(v) / len(v) for k, v in ks.items()}
-        out[stage] = sum(per_kernel.values()) if len(per_kernel) == 1 else None
+        fewest = min(len(v) for v in ks.values())
+        per_kernel = {k: {"bytes_per_launch": sum(v) / len(v), "launches_per_stage_call": round(len(v) / fewest, 2)} for k, v in ks.items()}
+        out[stage] = sum(d["bytes_per_launch"] * d["launches_per_stage_call"] for d in per_kernel.values())
         out[stage + "__kernels"] = per_kernel
     print(json.dumps(out, indent=1))
 
