@@ -1,6 +1,6 @@
 // Headless driver around the reference's UNMODIFIED 2-D CPU solver (cpu/src/simulation.cpp + constraint/*.cpp,
 // compiled from /root/reference by oracle/Makefile into oracle/_ref/ref_cpu).  TEST INFRASTRUCTURE ONLY.
-//   ref_cpu --scene 6 --ticks N [--dump dir] [--json]
+//   ref_cpu --scene KEY --ticks N [--dump dir [--dump-every K] [--scene-at T]] [--json]
 // Builds a scene exactly as the Qt app does (Simulation() runs init(WRECKING_BALL) first, then the key handler
 // calls init(type): cpu/src/simulation.cpp:11-16, cpu/src/view.cpp:121-179), runs tick(.01) N times
 // (cpu/src/view.cpp:185-202) and reports kinetic energy / timing; --dump writes particle state after chosen ticks.
@@ -21,8 +21,14 @@
 #include <QSet>
 #include "includes.h"
 #define private public
+#define protected public
 #include "simulation.h"
 #include "totalfluidconstraint.h"
+#include "gasconstraint.h"
+#include "distanceconstraint.h"
+#include "totalshapeconstraint.h"
+#include "opensmokeemitter.h"
+#undef protected
 #undef private
 
 // The reference draws glibc rand() for scene jitter and, every solver iteration, for the wall jitter of fluid particles
@@ -33,18 +39,85 @@ static long g_rand_calls = 0;
 extern "C" int rand(void) { g_rand_calls++; return (int)random(); }
 
 static SimulationType scene_of(const std::string &k) {
-    // key bindings of cpu/src/view.cpp:121-179
-    if (k == "1") return FRICTION_TEST;
-    if (k == "2") return GRANULAR_TEST;
-    if (k == "3") return STACKS_TEST;
-    if (k == "4") return WALL_TEST;
-    if (k == "5") return PENDULUM_TEST;
+    // key bindings of cpu/src/view.cpp:129-177
+    if (k == "1") return GRANULAR_TEST;
+    if (k == "2") return STACKS_TEST;
+    if (k == "3") return WALL_TEST;
+    if (k == "4") return PENDULUM_TEST;
+    if (k == "5") return ROPE_TEST;
     if (k == "6") return FLUID_TEST;
     if (k == "7") return FLUID_SOLID_TEST;
-    if (k == "8") return ROPE_TEST;
-    if (k == "9") return GAS_ROPE_TEST;
+    if (k == "8") return GAS_ROPE_TEST;
+    if (k == "9") return FRICTION_TEST;
     if (k == "0") return WATER_BALLOON_TEST;
-    return FLUID_TEST;
+    if (k == "n") return CRADLE_TEST;
+    if (k == "s") return SMOKE_OPEN_TEST;
+    if (k == "d") return SMOKE_CLOSED_TEST;
+    if (k == ".") return SDF_TEST;
+    if (k == "v") return VOLCANO_TEST;
+    if (k == "w") return WRECKING_BALL;
+    fprintf(stderr, "unknown scene key '%s'\n", k.c_str());
+    exit(2);
+}
+
+// Everything a tick depends on besides the per-particle state of dump_state: friction coefficients, rigid bodies
+// (member range, r vectors, SDF, centre, angle, inverse mass, stiffness), the STANDARD constraint list in order
+// (fluid / gas / distance) and the smoke emitters.  JSON, 17 significant digits.
+static void dump_scene(Simulation &sim, const std::string &dir, int tick) {
+    char nm[64];
+    snprintf(nm, sizeof nm, tick ? "/scene_t%05d.json" : "/scene.json", tick);
+    std::string name = dir + nm;
+    FILE *f = fopen(name.c_str(), "w");
+    if (!f) { perror("fopen"); exit(1); }
+    int n = sim.m_particles.size();
+    fprintf(f, "{\"n\": %d, \"rand_calls\": %ld,\n \"xbounds\": [%.17g, %.17g], \"ybounds\": [%.17g, %.17g], \"gravity\": [%.17g, %.17g],\n", n, g_rand_calls,
+            sim.m_xBoundaries.x, sim.m_xBoundaries.y, sim.m_yBoundaries.x, sim.m_yBoundaries.y, sim.m_gravity.x, sim.m_gravity.y);
+    fprintf(f, " \"particles\": [");  // [px, py, vx, vy, imass, phase, bod, sFriction, kFriction, fx, fy]
+    for (int i = 0; i < n; i++) {
+        Particle *p = sim.m_particles[i];
+        fprintf(f, "%s[%.17g, %.17g, %.17g, %.17g, %.17g, %d, %d, %.17g, %.17g, %.17g, %.17g]", i ? ",\n  " : "", p->p.x, p->p.y, p->v.x, p->v.y, p->imass,
+                (int)p->ph, p->bod, p->sFriction, p->kFriction, p->f.x, p->f.y);
+    }
+    fprintf(f, "],\n \"bodies\": [");
+    for (int b = 0; b < sim.m_bodies.size(); b++) {
+        Body *B = sim.m_bodies[b];
+        fprintf(f, "%s{\"imass\": %.17g, \"center\": [%.17g, %.17g], \"angle\": %.17g, \"stiffness\": %.17g, \"particles\": [", b ? ",\n  " : "", B->imass,
+                B->center.x, B->center.y, B->angle, B->shape->stiffness);
+        for (int k = 0; k < B->particles.size(); k++) fprintf(f, "%s%d", k ? ", " : "", B->particles[k]);
+        fprintf(f, "], \"rs\": [");
+        for (int k = 0; k < B->particles.size(); k++) { glm::dvec2 r = B->rs[B->particles[k]]; fprintf(f, "%s[%.17g, %.17g]", k ? ", " : "", r.x, r.y); }
+        fprintf(f, "], \"sdf\": [");
+        for (int k = 0; k < B->particles.size(); k++) { SDFData d = B->sdf[B->particles[k]]; fprintf(f, "%s[%.17g, %.17g, %.17g]", k ? ", " : "", d.gradient.x, d.gradient.y, d.distance); }
+        fprintf(f, "]}");
+    }
+    fprintf(f, "],\n \"standard\": [");
+    QList<Constraint *> &glob = sim.m_globalConstraints[STANDARD];
+    for (int c = 0; c < glob.size(); c++) {
+        fprintf(f, "%s", c ? ",\n  " : "");
+        if (TotalFluidConstraint *t = dynamic_cast<TotalFluidConstraint *>(glob[c])) {
+            fprintf(f, "{\"type\": \"fluid\", \"p0\": %.17g, \"ps\": [", t->p0);
+            for (int k = 0; k < t->ps.size(); k++) fprintf(f, "%s%d", k ? ", " : "", t->ps[k]);
+            fprintf(f, "]}");
+        } else if (GasConstraint *g = dynamic_cast<GasConstraint *>(glob[c])) {
+            fprintf(f, "{\"type\": \"gas\", \"p0\": %.17g, \"open\": %d, \"ps\": [", g->p0, g->m_open ? 1 : 0);
+            for (int k = 0; k < g->ps.size(); k++) fprintf(f, "%s%d", k ? ", " : "", g->ps[k]);
+            fprintf(f, "]}");
+        } else if (DistanceConstraint *d = dynamic_cast<DistanceConstraint *>(glob[c])) {
+            fprintf(f, "{\"type\": \"distance\", \"i1\": %d, \"i2\": %d, \"d\": %.17g}", d->i1, d->i2, d->d);
+        } else {
+            fprintf(f, "{\"type\": \"unknown\"}");
+        }
+    }
+    fprintf(f, "],\n \"smoke_emitters\": [");
+    for (int e = 0; e < sim.m_smokeEmitters.size(); e++) {
+        OpenSmokeEmitter *E = sim.m_smokeEmitters[e];
+        int gi = -1;
+        for (int c = 0; c < glob.size(); c++) if ((Constraint *)E->m_gs == glob[c]) gi = c;
+        fprintf(f, "%s{\"posn\": [%.17g, %.17g], \"rate\": %.17g, \"timer\": %.17g, \"standard_index\": %d}", e ? ", " : "", E->m_posn.x, E->m_posn.y,
+                E->m_particlesPerSec, E->timer, gi);
+    }
+    fprintf(f, "], \"fluid_emitters\": %d}\n", (int)sim.m_fluidEmitters.size());
+    fclose(f);
 }
 
 static void dump_state(Simulation &sim, const std::string &dir, int tick) {
@@ -82,7 +155,7 @@ static void dump_state(Simulation &sim, const std::string &dir, int tick) {
 
 int main(int argc, char **argv) {
     std::string scene = "6", dump;
-    int ticks = 100, dump_every = 0;
+    int ticks = 100, dump_every = 0, scene_at = -1;
     bool json = false;
     for (int i = 1; i < argc; i++) {
         std::string k = argv[i];
@@ -90,17 +163,19 @@ int main(int argc, char **argv) {
         else if (k == "--ticks" && i + 1 < argc) ticks = atoi(argv[++i]);
         else if (k == "--dump" && i + 1 < argc) dump = argv[++i];
         else if (k == "--dump-every" && i + 1 < argc) dump_every = atoi(argv[++i]);
+        else if (k == "--scene-at" && i + 1 < argc) scene_at = atoi(argv[++i]);  // full restart state after that tick
         else if (k == "--json") json = true;
     }
     Simulation sim;  // constructor builds WRECKING_BALL first, consuming rand() like the app does
     sim.init(scene_of(scene));
     int n = sim.getNumParticles();
-    if (!dump.empty()) { std::string c = "mkdir -p '" + dump + "'"; if (system(c.c_str())) return 1; dump_state(sim, dump, 0); }
+    if (!dump.empty()) { std::string c = "mkdir -p '" + dump + "'"; if (system(c.c_str())) return 1; dump_scene(sim, dump, 0); dump_state(sim, dump, 0); }
     std::vector<double> ke;
     auto t0 = std::chrono::steady_clock::now();
     for (int t = 1; t <= ticks; t++) {
         sim.tick(.01);  // cpu/src/view.cpp:197
         if (t == 1 || t == 100 || t == 1000 || t == ticks) ke.push_back(sim.getKineticEnergy());
+        if (!dump.empty() && t == scene_at) dump_scene(sim, dump, t);
         if (!dump.empty() && (t == 1 || (dump_every > 0 && t % dump_every == 0) || t == ticks)) dump_state(sim, dump, t);
     }
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
