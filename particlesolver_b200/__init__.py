@@ -150,6 +150,22 @@ def lib():
         L.ps2d_create.argtypes = [i32, C.POINTER(Params2D), u64, C.POINTER(vp)]
         L.ps2d_destroy.argtypes = [vp]
         L.ps2d_create_fluid.argtypes = [vp, vp, vp, vp, u64, C.c_double]
+        L.ps2d_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u64, C.POINTER(u64)]
+        L.ps2d_add_distance_constraint.argtypes = [vp, u32, u32, C.c_double]
+        L.ps2d_add_fluid_constraint.argtypes = [vp, vp, u64, C.c_double, C.POINTER(u32)]
+        L.ps2d_add_gas_constraint.argtypes = [vp, vp, u64, C.c_double, i32, C.POINTER(u32)]
+        L.ps2d_restore_rigid_body.argtypes = [vp, u32, u32, vp, vp, C.c_double, vp, C.c_double, C.c_double, C.POINTER(u32)]
+        L.ps2d_create_rigid_body.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64, C.POINTER(u32)]
+        L.ps2d_create_gas.argtypes = [vp, vp, vp, vp, u64, C.c_double, i32, C.POINTER(u32)]
+        L.ps2d_create_smoke_emitter.argtypes = [vp, vp, C.c_double, u32, C.c_double]
+        L.ps2d_set_forces.argtypes = [vp, vp]
+        L.ps2d_body_state.argtypes = [vp, u32, vp, C.POINTER(C.c_double)]
+        L.ps2d_num_bodies.argtypes = [vp]
+        L.ps2d_num_bodies.restype = u32
+        L.ps2d_last_num_contact_constraints.argtypes = [vp]
+        L.ps2d_last_num_contact_constraints.restype = u32
+        L.ps2d_last_num_levels.argtypes = [vp]
+        L.ps2d_last_num_levels.restype = u32
         L.ps2d_seed_rand.argtypes = [vp, u32, u64]
         L.ps2d_rand_calls.argtypes = [vp]
         L.ps2d_rand_calls.restype = u64
@@ -448,7 +464,11 @@ class ParticleSystem:
 
 class Simulation2D:
     """The 2-D double-precision path: the reference CPU application's Simulation::tick (cpu/src/simulation.cpp:115-369) on
-    the GPU for all-fluid scenes; `createFluid`, `tick`, `getNumParticles`, `getKineticEnergy` keep the reference's names."""
+    the GPU with all its constraint groups; `createRigidBody`, `createFluid`, `createGas`, `createSmokeEmitter`, `tick`,
+    `getNumParticles`, `getKineticEnergy` keep the reference's names (simulation.h:66-99); `addParticles`,
+    `addDistanceConstraint`, `addFluidConstraint`, `addGasConstraint`, `restoreRigidBody` correspond to its Particle /
+    DistanceConstraint / TotalFluidConstraint / GasConstraint / Body constructors."""
+    SOLID, FLUID, GAS = 0, 1, 2
 
     def __init__(self, x_bounds=(-8.0, 8.0), y_bounds=(-8.0, 40.0), gravity=(0.0, -9.8), iterations=3, max_particles=1 << 16, device=0):
         p = Params2D()
@@ -471,6 +491,127 @@ class Simulation2D:
         v = _arr(velocities if velocities is not None else np.zeros_like(p), np.float64).reshape(-1, 2)
         w = _arr(inv_mass if inv_mass is not None else np.ones(p.shape[0]), np.float64).reshape(-1)
         _check(lib().ps2d_create_fluid(self._h, _ptr(p), _ptr(v), _ptr(w), p.shape[0], density))
+
+    @staticmethod
+    def _opt(a, dtype, shape):
+        return None if a is None else _arr(a, dtype).reshape(shape)
+
+    def addParticles(self, positions, velocities=None, inv_mass=None, phase=None, bod=None, s_friction=None, k_friction=None):
+        p = _arr(positions, np.float64).reshape(-1, 2)
+        n = p.shape[0]
+        v = self._opt(velocities, np.float64, (-1, 2))
+        w = _arr(inv_mass if inv_mass is not None else np.ones(n), np.float64).reshape(-1)
+        ph = _arr(phase if phase is not None else np.zeros(n), np.int32).reshape(-1)
+        bd, sf, kf = self._opt(bod, np.int32, -1), self._opt(s_friction, np.float64, -1), self._opt(k_friction, np.float64, -1)
+        first = C.c_uint64()
+        _check(lib().ps2d_add_particles(self._h, _ptr(p), _ptr(v) if v is not None else None, _ptr(w), _ptr(ph), _ptr(bd) if bd is not None else None,
+                                        _ptr(sf) if sf is not None else None, _ptr(kf) if kf is not None else None, n, C.byref(first)))
+        return int(first.value)
+
+    def addDistanceConstraint(self, i1, i2, d=-1.0):
+        _check(lib().ps2d_add_distance_constraint(self._h, int(i1), int(i2), float(d)))
+
+    def addFluidConstraint(self, indices, density):
+        idx = _arr(indices, np.uint32).reshape(-1)
+        k = C.c_uint32()
+        _check(lib().ps2d_add_fluid_constraint(self._h, _ptr(idx), idx.shape[0], density, C.byref(k)))
+        return int(k.value)
+
+    def addGasConstraint(self, indices, density, open=False):
+        idx = _arr(indices, np.uint32).reshape(-1)
+        k = C.c_uint32()
+        _check(lib().ps2d_add_gas_constraint(self._h, _ptr(idx), idx.shape[0], density, 1 if open else 0, C.byref(k)))
+        return int(k.value)
+
+    def restoreRigidBody(self, first, count, rs, sdf, inv_mass, center, angle, stiffness=1.0):
+        rs, sdf, cen = _arr(rs, np.float64).reshape(-1, 2), _arr(sdf, np.float64).reshape(-1, 3), _arr(center, np.float64).reshape(2)
+        assert rs.shape[0] == count and sdf.shape[0] == count
+        b = C.c_uint32()
+        _check(lib().ps2d_restore_rigid_body(self._h, int(first), int(count), _ptr(rs), _ptr(sdf), inv_mass, _ptr(cen), angle, stiffness, C.byref(b)))
+        return int(b.value)
+
+    def createRigidBody(self, positions, sdf, velocities=None, inv_mass=None, s_friction=None, k_friction=None):
+        p = _arr(positions, np.float64).reshape(-1, 2)
+        n = p.shape[0]
+        v = self._opt(velocities, np.float64, (-1, 2))
+        w = _arr(inv_mass if inv_mass is not None else np.ones(n), np.float64).reshape(-1)
+        sd = _arr(sdf, np.float64).reshape(-1, 3)
+        sf, kf = self._opt(s_friction, np.float64, -1), self._opt(k_friction, np.float64, -1)
+        b = C.c_uint32()
+        _check(lib().ps2d_create_rigid_body(self._h, _ptr(p), _ptr(v) if v is not None else None, _ptr(w), _ptr(sf) if sf is not None else None,
+                                            _ptr(kf) if kf is not None else None, _ptr(sd), n, C.byref(b)))
+        return int(b.value)
+
+    def createGas(self, positions, density, open=False, velocities=None, inv_mass=None):
+        p = _arr(positions, np.float64).reshape(-1, 2)
+        v = self._opt(velocities, np.float64, (-1, 2))
+        w = _arr(inv_mass if inv_mass is not None else np.ones(p.shape[0]), np.float64).reshape(-1)
+        k = C.c_uint32()
+        _check(lib().ps2d_create_gas(self._h, _ptr(p), _ptr(v) if v is not None else None, _ptr(w), p.shape[0], density, 1 if open else 0, C.byref(k)))
+        return int(k.value)
+
+    def createSmokeEmitter(self, posn, particles_per_sec, gas_index=None, timer=0.0):
+        q = _arr(posn, np.float64).reshape(2)
+        _check(lib().ps2d_create_smoke_emitter(self._h, _ptr(q), particles_per_sec, 0xFFFFFFFF if gas_index is None else int(gas_index), timer))
+
+    def setForces(self, f):
+        f = _arr(f, np.float64).reshape(-1, 2)
+        assert f.shape[0] == self.getNumParticles()
+        _check(lib().ps2d_set_forces(self._h, _ptr(f)))
+
+    def bodyState(self, body):
+        cen = np.zeros(2, np.float64)
+        ang = C.c_double()
+        _check(lib().ps2d_body_state(self._h, int(body), _ptr(cen), C.byref(ang)))
+        return cen, ang.value
+
+    def getNumBodies(self):
+        return int(lib().ps2d_num_bodies(self._h))
+
+    @property
+    def num_contact_constraints(self):
+        return int(lib().ps2d_last_num_contact_constraints(self._h))
+
+    @property
+    def num_levels(self):
+        return int(lib().ps2d_last_num_levels(self._h))
+
+    def forces(self): return self._get(4, 2)
+    def tmass(self): return self._get(6, 1)
+
+    def counts(self):
+        a = np.empty(self.getNumParticles(), np.uint32)
+        _check(lib().ps2d_download(self._h, 5, _ptr(a)))
+        return a
+
+    @classmethod
+    def from_state(cls, scene, max_particles=None, device=0):
+        """Builds a simulation from a full restart state: the dict layout written by the reference driver
+        (oracle/ref_cpu_driver.cpp dump_scene; tests/golden/ref_cpu_scenes.npz) — particles [px, py, vx, vy, imass, phase,
+        bod, sFriction, kFriction(, fx, fy)], bodies, the STANDARD constraint list in order, smoke emitters, rand() position."""
+        P = np.array(scene["particles"], np.float64).reshape(-1, 11 if scene["particles"] and len(scene["particles"][0]) > 9 else 9)
+        n = P.shape[0]
+        sim = cls(scene["xbounds"], scene["ybounds"], scene["gravity"], max_particles=max_particles or max(1024, 2 * n), device=device)
+        sim.addParticles(P[:, 0:2], P[:, 2:4], P[:, 4], P[:, 5].astype(np.int32), P[:, 6].astype(np.int32), P[:, 7], P[:, 8])
+        for b in scene["bodies"]:
+            idx = np.array(b["particles"])
+            assert np.array_equal(idx, np.arange(idx[0], idx[0] + idx.shape[0])), "body members are a contiguous index range"
+            sim.restoreRigidBody(idx[0], idx.shape[0], b["rs"], b["sdf"], b["imass"], b["center"], b["angle"], b["stiffness"])
+        for k, c in enumerate(scene["standard"]):
+            if c["type"] == "fluid":
+                assert sim.addFluidConstraint(c["ps"], c["p0"]) == k
+            elif c["type"] == "gas":
+                assert sim.addGasConstraint(c["ps"], c["p0"], bool(c["open"])) == k
+            elif c["type"] == "distance":
+                sim.addDistanceConstraint(c["i1"], c["i2"], c["d"])
+            else:
+                raise ValueError(c["type"])
+        for e in scene.get("smoke_emitters", []):
+            sim.createSmokeEmitter(e["posn"], e["rate"], e["standard_index"] if e["standard_index"] >= 0 else None, e.get("timer", 0.0))
+        if P.shape[1] > 9:
+            sim.setForces(P[:, 9:11])
+        sim.seedRand(1, int(scene["rand_calls"]))
+        return sim
 
     def seedRand(self, seed=1, skip=0):
         _check(lib().ps2d_seed_rand(self._h, seed, skip))

@@ -1,8 +1,19 @@
 // particlesolver_b200/csrc/ps2d.cu — the 2-D double-precision path (include/psolver2d.h): one Simulation::tick of the
-// reference's CPU application on the GPU, for all-fluid scenes (config C1).  Compiled WITHOUT -use_fast_math and with
-// -fmad=false: the reference is plain x86-64 double arithmetic without contraction, and a tick is compared with it
-// to 1e-9.  Sums over neighbours run sequentially in ascending particle index, like the reference's O(N^2) loops
-// (cpu/src/constraint/totalfluidconstraint.cpp:52-76), with the other particles staged through shared memory in tiles.
+// reference's CPU application on the GPU, every constraint group of its ITERATIVE solver.
+// Compiled WITHOUT -use_fast_math and with -fmad=false: the reference is plain x86-64 double arithmetic without
+// contraction, and a tick is compared with it to 1e-9.
+//
+// How a sequential (Gauss-Seidel) constraint list runs on the GPU without changing its result: LEVEL SCHEDULING.
+// Two constraints commute unless they share a particle, so only the per-particle order of updates matters.  Each
+// particle's constraints, in list order, form its sequence; level(c) = 1 + max over c's particles of the level of the
+// constraint before c in that particle's sequence (0 if none).  Constraints of one level touch disjoint particles: they are
+// projected in parallel, and levels are executed in ascending order.  For the per-tick CONTACT list (pairs found by
+// an all-pairs test, then the walls, particle by particle — simulation.cpp:165-225) a particle's sequence is simply its
+// contact partners in ascending index followed by its walls, so the levels are the least fixpoint of a local rule and are
+// found by parallel relaxation (k2d_contact_levels).  Distance constraints are static: their schedule is built once on
+// the host when the list changes.  Fluid / gas constraints are Jacobi inside and run as whole kernels at their place in
+// the STANDARD list; sums over neighbours run sequentially in ascending particle index, like the reference's O(N^2)
+// loops (totalfluidconstraint.cpp:52-76), with the other particles staged through shared memory in tiles.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -18,55 +29,114 @@ namespace {
 typedef uint32_t u32;
 constexpr int kBlock = 128;
 constexpr int kTile = 128;
-constexpr double kRad = 0.25;    // PARTICLE_RAD, cpu/src/particle.h:6
-constexpr double kEps = 1e-4;    // EPSILON, cpu/src/includes.h:34
-constexpr double kH = 2., kH2 = 4., kH6 = 64., kH9 = 512.;  // totalfluidconstraint.h:16-19
-constexpr double kRelax = .01, kKP = .1, kEP = 4., kDQ = .2;   // totalfluidconstraint.h:22-27
+constexpr int kSerialBlock = 1024;                   // the level-scheduled kernels run as one CTA (scenes of 10^1..10^4 particles)
+constexpr int kMaxC = PS2D_MAX_CONTACTS;             // pair slots per particle
+constexpr int kEntries = kMaxC + 2;                  // + at most one x wall and one y wall
+constexpr u32 kRigidBit = 0x80000000u;
+constexpr double kRad = 0.25, kDiam = 0.5;           // PARTICLE_RAD / PARTICLE_DIAM, cpu/src/particle.h:6-7
+constexpr double kEps = 1e-4;                        // EPSILON, cpu/src/includes.h:34
+constexpr double kAlpha = -.2;                       // ALPHA, simulation.h:21
+constexpr double kH = 2., kH2 = 4., kH6 = 64., kH9 = 512.;  // totalfluidconstraint.h:16-19, gasconstraint.h:4-7
+constexpr double kRelax = .01;                       // RELAXATION
 constexpr double kPi = 3.14159265358979323846;
+
+struct FluidConsts {  // totalfluidconstraint.h:22-30 / gasconstraint.h:12-20
+    double k_p, dq_p, s_solid;
+    int gas, open;
+};
 
 __device__ __forceinline__ double poly6(double r2) {  // totalfluidconstraint.cpp:121-127
     if (r2 >= kH2) return 0.;
     const double term2 = kH2 - r2;
     return (315. / (64. * kPi * kH9)) * (term2 * term2 * term2);
 }
-// spikyGrad(r, rlen) = -normalize(r) * (45 / (pi H^6)) * (H - rlen)^2, zero outside the support and at r = 0 (:129-135);
+// spikyGrad(r, x) = -normalize(r) * (45 / (pi H^6)) * (H - x)^2, zero for x >= H and x == 0 (:129-135); x is the length
+// of r at every call site but the gas vorticity term, which passes dot(r, r) (gasconstraint.cpp:100);
 // glm::normalize(v) = v * (1 / sqrt(dot(v, v)))
-__device__ __forceinline__ double2 spiky_grad(double rx, double ry, double rlen) {
-    if (rlen >= kH || rlen == 0.) return make_double2(0., 0.);
-    const double inv = 1. / rlen;
-    const double c = 45. / (kPi * kH6), hm = kH - rlen;
+__device__ __forceinline__ double2 spiky_grad(double rx, double ry, double x) {
+    if (x >= kH || x == 0.) return make_double2(0., 0.);
+    const double inv = 1. / sqrt(rx * rx + ry * ry);
+    const double c = 45. / (kPi * kH6), hm = kH - x;
     return make_double2((-(rx * inv) * c) * hm * hm, (-(ry * inv) * c) * hm * hm);
 }
 
-// (1)-(4): v += dt g; ep = p + dt v (fixed particles stay); simulation.cpp:139-161, particle.h:56-58
-__global__ void k2d_predict(double2 *__restrict__ v, double2 *__restrict__ ep, const double2 *__restrict__ p, const double *__restrict__ imass, u32 n,
-                            double dt, double gx, double gy) {
+// (1)-(4): v += dt g (gas: ALPHA g) + dt f; f = 0; ep = p + dt v (fixed particles stay); tmass = height-scaled inverse
+// mass; simulation.cpp:139-161, particle.h:56-58,67-73
+__global__ void k2d_predict(double2 *__restrict__ v, double2 *__restrict__ ep, double2 *__restrict__ f, double *__restrict__ tmass,
+                            const double2 *__restrict__ p, const double *__restrict__ imass, const int *__restrict__ phase, u32 n, double dt, double gx,
+                            double gy) {
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
+    if (phase[i] == PS2D_PHASE_GAS) { gx = gx * kAlpha; gy = gy * kAlpha; }
     double2 vi = v[i];
-    vi.x = vi.x + dt * gx;
-    vi.y = vi.y + dt * gy;
+    const double2 fi = f[i];
+    vi.x = vi.x + dt * gx + dt * fi.x;
+    vi.y = vi.y + dt * gy + dt * fi.y;
     v[i] = vi;
+    f[i] = make_double2(0., 0.);
     const double2 pi = p[i];
-    ep[i] = imass[i] == 0. ? pi : make_double2(pi.x + dt * vi.x, pi.y + dt * vi.y);
+    const double im = imass[i];
+    ep[i] = im == 0. ? pi : make_double2(pi.x + dt * vi.x, pi.y + dt * vi.y);
+    tmass[i] = im != 0. ? 1. / ((1. / im) * exp(-pi.y)) : 0.;
 }
 
-// (8): which walls a predicted position violates — at most one constraint per axis, x before y (simulation.cpp:202-224).
-// flags: bit0 x-low, bit1 x-high, bit2 y-low, bit3 y-high; counts[i] = number of constraints (BoundaryConstraint::updateCounts).
-__global__ void k2d_boundary_flags(const double2 *__restrict__ ep, u32 n, double x0, double x1, double y0, double y1, u32 *__restrict__ flags,
-                                   u32 *__restrict__ counts) {
+// (6)-(8): the CONTACT list of a tick, stored per particle.  nb[i*kMaxC + r], r < cnt[i]: i's contact partners in
+// ascending index (bit 31: both SOLID -> RigidContactConstraint, else ContactConstraint); flags: walls violated by the
+// predicted position, at most one per axis, x before y (bit0 x-low, bit1 x-high, bit2 y-low, bit3 y-high).  The
+// reference's list is [pairs (i, j > i) by j, wall x, wall y] for i = 0, 1, ...; particle i's own sequence in that list
+// is therefore [nb ascending, wall x, wall y].  counts[i] = constraints on i in all groups (Constraint::updateCounts);
+// draws[i] = wall constraints of i that draw jitter (fluid / gas particles only, boundaryconstraint.cpp:19).
+__global__ void __launch_bounds__(kBlock) k2d_find_contacts(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ phase,
+                                                            const int *__restrict__ bod, const u32 *__restrict__ static_counts, u32 n, double x0, double x1,
+                                                            double y0, double y1, u32 *__restrict__ nb, u32 *__restrict__ cnt, u32 *__restrict__ flags,
+                                                            u32 *__restrict__ counts, u32 *__restrict__ draws, u32 *__restrict__ overflow, int any_solid) {
+    __shared__ double2 s_ep[kTile];
+    __shared__ double s_im[kTile];
+    __shared__ int s_ph[kTile], s_bod[kTile];
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    const double2 e = ep[i];
-    u32 f = 0;
-    if (e.x < x0 + kRad) f |= 1u; else if (e.x > x1 - kRad) f |= 2u;
-    if (e.y < y0 + kRad) f |= 4u; else if (e.y > y1 - kRad) f |= 8u;
-    flags[i] = f;
-    counts[i] = __popc(f);
+    const bool act = i < n;
+    const double2 e = act ? ep[i] : make_double2(0., 0.);
+    const double im = act ? imass[i] : 0.;
+    const int ph = act ? phase[i] : -1, bd = act ? bod[i] : -1;
+    u32 c = 0;
+    if (any_solid) {  // no SOLID particle: no particle-particle contact constraint (simulation.cpp:188-196)
+        for (u32 base = 0; base < n; base += kTile) {
+            __syncthreads();
+            if (base + threadIdx.x < n) {
+                const u32 j = base + threadIdx.x;
+                s_ep[threadIdx.x] = ep[j]; s_im[threadIdx.x] = imass[j]; s_ph[threadIdx.x] = phase[j]; s_bod[threadIdx.x] = bod[j];
+            }
+            __syncthreads();
+            if (!act) continue;
+            const u32 m = min((u32)kTile, n - base);
+            for (u32 t = 0; t < m; t++) {
+                const u32 j = base + t;
+                if (j == i) continue;
+                const bool solid2 = ph == PS2D_PHASE_SOLID && s_ph[t] == PS2D_PHASE_SOLID;
+                if (!solid2 && ph != PS2D_PHASE_SOLID && s_ph[t] != PS2D_PHASE_SOLID) continue;
+                if (im == 0. && s_im[t] == 0.) continue;
+                if (solid2 && bd == s_bod[t] && bd != -1) continue;
+                const double dx = s_ep[t].x - e.x, dy = s_ep[t].y - e.y;
+                if (sqrt(dx * dx + dy * dy) < kDiam - kEps) {
+                    if (c < (u32)kMaxC) nb[(size_t)i * kMaxC + c] = j | (solid2 ? kRigidBit : 0u);
+                    c++;
+                }
+            }
+        }
+    }
+    if (!act) return;
+    if (c > (u32)kMaxC) { atomicMax(overflow, c); c = kMaxC; }
+    u32 fl = 0;
+    if (e.x < x0 + kRad) fl |= 1u; else if (e.x > x1 - kRad) fl |= 2u;
+    if (e.y < y0 + kRad) fl |= 4u; else if (e.y > y1 - kRad) fl |= 8u;
+    cnt[i] = c;
+    flags[i] = fl;
+    counts[i] = static_counts[i] + c + __popc(fl);
+    draws[i] = (ph == PS2D_PHASE_FLUID || ph == PS2D_PHASE_GAS) ? __popc(fl) : 0u;
 }
 
-// rank[i] = number of boundary constraints of particles before i = position of i's first constraint in the reference's
-// constraint list (and so in the rand() stream of an iteration); total -> *num.  One CTA, sequential over chunks.
+// rank[i] = sum of counts before i (the position of i's first jitter draw in the rand() stream of an iteration);
+// total -> *num.  One CTA, sequential over chunks.
 __global__ void __launch_bounds__(1024) k2d_scan_counts(const u32 *__restrict__ counts, u32 *__restrict__ rank, u32 n, u32 *__restrict__ num) {
     __shared__ u32 sm[32];
     __shared__ u32 carry;
@@ -97,53 +167,306 @@ __global__ void __launch_bounds__(1024) k2d_scan_counts(const u32 *__restrict__ 
     if (threadIdx.x == 0) *num = carry;
 }
 
-// BoundaryConstraint::project for every constraint of one solver iteration (boundaryconstraint.cpp:14-93).  A constraint
-// touches one coordinate of one particle, so the list order only decides which draw of the stream it gets:
-// draw = raw[iteration * num + position in the list], extra = (double)(float)(draw / RAND_MAX) * .003 (frand() is
-// float-typed, includes.h:25), consumed before the early-out.  Friction is a no-op for fluids (sFriction = kFriction = 0).
-__global__ void k2d_boundary_project(double2 *__restrict__ ep, const u32 *__restrict__ flags, const u32 *__restrict__ rank, u32 n, const int *__restrict__ raw,
-                                     u32 draw_base, double x0, double x1, double y0, double y1) {
-    const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
-    const u32 f = flags[i];
-    if (!f) return;
-    double2 e = ep[i];
-    u32 k = draw_base + rank[i];
-    auto extra = [&](u32 idx) { return (double)(float)((double)raw[idx] / 2147483647.0) * .003; };
-    if (f & 3u) {
-        const double d = kRad + extra(k++);
-        if (f & 1u) { if (!(e.x >= x0 + kRad)) e.x = x0 + d; }
-        else { if (!(e.x <= x1 - kRad)) e.x = x1 - d; }
+// Level schedule of the CONTACT list (see the file header).  Entry (i, r) is the r-th constraint of particle i's
+// sequence; a pair constraint appears in both particles' sequences, q = its position in the partner's.  The rule
+//     lvl(i, r) = 1 + max(lvl(i, r - 1), lvl(j, q - 1))      (pair with j; walls: the first term only)
+// is monotone, so relaxing it from 0 in any order converges to its least fixpoint — the levels of the sequential list.
+// info[0] = number of levels, info[1] = number of constraints in the list.
+__global__ void __launch_bounds__(kSerialBlock) k2d_contact_levels(const u32 *__restrict__ nb, const u32 *__restrict__ cnt, const u32 *__restrict__ flags,
+                                                                   u32 n, unsigned char *__restrict__ nbq, u32 *__restrict__ lvl, u32 *__restrict__ info) {
+    __shared__ u32 s_max, s_pairs, s_walls;
+    if (threadIdx.x == 0) { s_max = 0; s_pairs = 0; s_walls = 0; }
+    u32 pairs = 0, walls = 0;
+    for (u32 i = threadIdx.x; i < n; i += kSerialBlock) {
+        const u32 c = cnt[i], len = c + __popc(flags[i]);
+        for (u32 r = 0; r < c; r++) {
+            const u32 j = nb[(size_t)i * kMaxC + r] & ~kRigidBit, cj = cnt[j];
+            u32 q = 0;
+            while (q < cj && (nb[(size_t)j * kMaxC + q] & ~kRigidBit) != i) q++;
+            nbq[(size_t)i * kMaxC + r] = (unsigned char)q;  // found by symmetry of the contact test
+        }
+        for (u32 r = 0; r < len; r++) lvl[(size_t)i * kEntries + r] = 0;
+        pairs += c;
+        walls += len - c;
     }
-    if (f & 12u) {
-        const double d = kRad + extra(k++);
-        if (f & 4u) { if (!(e.y >= y0 + kRad)) e.y = y0 + d; }
-        else { if (!(e.y <= y1 - kRad)) e.y = y1 - d; }
+    atomicAdd(&s_pairs, pairs);
+    atomicAdd(&s_walls, walls);
+    __syncthreads();
+    for (;;) {
+        int changed = 0;
+        for (u32 i = threadIdx.x; i < n; i += kSerialBlock) {
+            const u32 c = cnt[i], len = c + __popc(flags[i]);
+            u32 prev = 0;
+            for (u32 r = 0; r < len; r++) {
+                u32 other = 0;
+                if (r < c) {
+                    const u32 j = nb[(size_t)i * kMaxC + r] & ~kRigidBit, q = nbq[(size_t)i * kMaxC + r];
+                    if (q > 0) other = *((volatile u32 *)&lvl[(size_t)j * kEntries + q - 1]);
+                }
+                const u32 v = 1 + max(prev, other);
+                if (v != lvl[(size_t)i * kEntries + r]) { lvl[(size_t)i * kEntries + r] = v; changed = 1; }
+                prev = v;
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
     }
-    ep[i] = e;
+    u32 m = 0;
+    for (u32 i = threadIdx.x; i < n; i += kSerialBlock) {
+        const u32 len = cnt[i] + __popc(flags[i]);
+        if (len) m = max(m, lvl[(size_t)i * kEntries + len - 1]);
+    }
+    atomicMax(&s_max, m);
+    __syncthreads();
+    if (threadIdx.x == 0) { info[0] = s_max; info[1] = s_pairs / 2 + s_walls; }
 }
 
-// TotalFluidConstraint::project, first loop (totalfluidconstraint.cpp:45-93): lambda of every particle of fluid `f`,
-// 0 for everybody else (the constraint's lambdas is a QHash cleared per call: the other fluid reads 0, :106).
-__global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ fluid,
-                                                           u32 n, int f, double p0, double *__restrict__ lambda, u32 *__restrict__ nbcount) {
+struct Particles2D {  // device views used by the projection kernels
+    double2 *ep;
+    const double2 *p;
+    const double *tmass, *sfric, *kfric;
+    const int *phase, *bod;
+    const u32 *counts;
+    const double2 *sdf_grad;
+    const double *sdf_dist;
+    const double *body_angle;
+};
+
+// Particle::getSDFData (solver/particle.cpp:3-13): the body's SDF sample rotated by the body's current angle
+__device__ __forceinline__ double3 sdf_data(const Particles2D &P, u32 i) {
+    const int b = P.bod[i];
+    if (P.phase[i] != PS2D_PHASE_SOLID || b < 0) return make_double3(0., 0., -1.);
+    const double2 g = P.sdf_grad[i];
+    const double a = P.body_angle[b];
+    const double c = cos(a), s = sin(a);
+    return make_double3(g.x * c - g.y * s, g.x * s + g.y * c, P.sdf_dist[i]);
+}
+
+// ContactConstraint::project (contactconstraint.cpp:13-42)
+__device__ void project_contact(const Particles2D &P, u32 i1, u32 i2) {
+    const double t1 = P.tmass[i1], t2 = P.tmass[i2];
+    if (t1 == 0. && t2 == 0.) return;
+    double2 e1 = P.ep[i1], e2 = P.ep[i2];
+    const double dx = e1.x - e2.x, dy = e1.y - e2.y;
+    const double wsum = t1 + t2, dist = sqrt(dx * dx + dy * dy), mag = dist - kDiam;
+    if (mag > 0.) return;
+    const double sd = (mag / wsum) / dist;
+    const double dpx = sd * dx, dpy = sd * dy;
+    const double c1 = (double)P.counts[i1], c2 = (double)P.counts[i2];
+    e1.x += ((-t1) * dpx) / c1; e1.y += ((-t1) * dpy) / c1;
+    e2.x += (t2 * dpx) / c2;    e2.y += (t2 * dpy) / c2;
+    P.ep[i1] = e1; P.ep[i2] = e2;
+}
+
+// RigidContactConstraint::project (rigidcontactconstraint.cpp:29-96), stabile == false
+__device__ void project_rigid_contact(const Particles2D &P, u32 i1, u32 i2) {
+    double2 e1 = P.ep[i1], e2 = P.ep[i2];
+    const double3 s1 = sdf_data(P, i1), s2 = sdf_data(P, i2);
+    double d, nx, ny;
+    if (s1.z < 0. || s2.z < 0.) {
+        const double x = e2.x - e1.x, y = e2.y - e1.y;
+        const double len = sqrt(x * x + y * y);
+        d = kDiam - len;
+        if (d < kEps) return;
+        nx = x / len; ny = y / len;
+    } else {
+        if (s1.z < s2.z) { d = s1.z; nx = s1.x; ny = s1.y; }
+        else { d = s2.z; nx = -s2.x; ny = -s2.y; }
+        if (d < kDiam + kEps) {  // initBoundary (:13-27)
+            double x = e1.x - e2.x, y = e1.y - e2.y;
+            const double len = sqrt(x * x + y * y);
+            d = kDiam - len;
+            if (d < kEps) return;
+            if (len > kEps) { x = x / len; y = y / len; } else { x = 0.; y = 1.; }
+            const double dp = x * nx + y * ny;
+            if (dp < 0.) { nx = x - (2.0 * dp) * nx; ny = y - (2.0 * dp) * ny; }
+            else { nx = x; ny = y; }
+        }
+    }
+    const double t1 = P.tmass[i1], t2 = P.tmass[i2];
+    const double wsum = t1 + t2;
+    const double s = (1.0 / wsum) * d;
+    const double dpx = s * nx, dpy = s * ny;
+    const double c1 = (double)P.counts[i1], c2 = (double)P.counts[i2];
+    e1.x += ((-t1) * dpx) / c1; e1.y += ((-t1) * dpy) / c1;
+    e2.x += (t2 * dpx) / c2;    e2.y += (t2 * dpy) / c2;
+    // friction (:68-95)
+    const double inv = 1. / sqrt(nx * nx + ny * ny);
+    const double nfx = nx * inv, nfy = ny * inv;
+    const double2 p1 = P.p[i1], p2 = P.p[i2];
+    const double fx = (e1.x - p1.x) - (e2.x - p2.x), fy = (e1.y - p1.y) - (e2.y - p2.y);
+    const double dn = fx * nfx + fy * nfy;
+    double tx = fx - dn * nfx, ty = fy - dn * nfy;
+    const double ldpt = sqrt(tx * tx + ty * ty);
+    if (!(ldpt < kEps)) {
+        const double sfric = sqrt(P.sfric[i1] * P.sfric[i2]), kfric = sqrt(P.kfric[i1] * P.kfric[i2]);
+        if (!(ldpt < sfric * d)) {
+            const double m = fmin(kfric * d / ldpt, 1.);
+            tx = tx * m; ty = ty * m;
+        }
+        e1.x -= (tx * t1) / wsum; e1.y -= (ty * t1) / wsum;
+        e2.x += (tx * t2) / wsum; e2.y += (ty * t2) / wsum;
+    }
+    P.ep[i1] = e1; P.ep[i2] = e2;
+}
+
+// BoundaryConstraint::project (boundaryconstraint.cpp:14-93), stabile == false.  raw < 0: no jitter draw (solids)
+__device__ void project_boundary(const Particles2D &P, u32 i, double value, bool is_x, bool greater, int raw) {
+    double2 e = P.ep[i];
+    const double extra = raw >= 0 ? (double)(float)((double)raw / 2147483647.0) * .003 : 0.;  // frand() is float-typed, includes.h:25
+    const double d = kRad + extra;
+    double nx, ny;
+    if (greater) {
+        if (is_x) { if (e.x >= value + kRad) return; e.x = value + d; nx = 1.; ny = 0.; }
+        else { if (e.y >= value + kRad) return; e.y = value + d; nx = 0.; ny = 1.; }
+    } else {
+        if (is_x) { if (e.x <= value - kRad) return; e.x = value - d; nx = -1.; ny = 0.; }
+        else { if (e.y <= value - kRad) return; e.y = value - d; nx = 0.; ny = -1.; }
+    }
+    // friction: walls have a coefficient of friction of 1 (:72-92)
+    const double2 p = P.p[i];
+    const double cn = (double)P.counts[i];
+    const double dpx = (e.x - p.x) / cn, dpy = (e.y - p.y) / cn;
+    const double dn = dpx * nx + dpy * ny;
+    const double tx = dpx - dn * nx, ty = dpy - dn * ny;
+    const double ldpt = sqrt(tx * tx + ty * ty);
+    if (!(ldpt < kEps)) {
+        if (ldpt < sqrt(P.sfric[i]) * d) { e.x -= tx; e.y -= ty; }
+        else {
+            const double m = fmin(sqrt(P.kfric[i]) * d / ldpt, 1.);
+            e.x -= tx * m; e.y -= ty * m;
+        }
+    }
+    P.ep[i] = e;
+}
+
+// One solver iteration over the CONTACT list, level by level.  Thread t owns particles t, t + 1024, ...; cur[i] walks
+// particle i's sequence (levels strictly increase along it).  A pair constraint is projected by its lower-index owner
+// (it is at the same level in both sequences); the partner just steps over it.
+__global__ void __launch_bounds__(kSerialBlock) k2d_contact_project(Particles2D P, const u32 *__restrict__ nb, const u32 *__restrict__ cnt,
+                                                                    const u32 *__restrict__ flags, const u32 *__restrict__ lvl, const u32 *__restrict__ rank,
+                                                                    const u32 *__restrict__ info, u32 *__restrict__ cur, u32 n, const int *__restrict__ raw,
+                                                                    u32 draw_base, double x0, double x1, double y0, double y1) {
+    const u32 levels = info[0];
+    for (u32 i = threadIdx.x; i < n; i += kSerialBlock) cur[i] = 0;
+    for (u32 l = 1; l <= levels; l++) {
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < n; i += kSerialBlock) {
+            const u32 c = cnt[i], fl = flags[i], len = c + __popc(fl), r = cur[i];
+            if (r >= len || lvl[(size_t)i * kEntries + r] != l) continue;
+            cur[i] = r + 1;
+            if (r < c) {
+                const u32 w = nb[(size_t)i * kMaxC + r], j = w & ~kRigidBit;
+                if (i < j) {
+                    if (w & kRigidBit) project_rigid_contact(P, i, j);
+                    else project_contact(P, i, j);
+                }
+            } else {
+                const bool second = r > c, is_x = !second && (fl & 3u);
+                const int ph = P.phase[i];
+                int draw = -1;
+                if (ph == PS2D_PHASE_FLUID || ph == PS2D_PHASE_GAS) draw = raw[draw_base + rank[i] + (second ? 1u : 0u)];
+                if (is_x) project_boundary(P, i, (fl & 1u) ? x0 : x1, true, (fl & 1u) != 0, draw);
+                else project_boundary(P, i, (fl & 4u) ? y0 : y1, false, (fl & 4u) != 0, draw);
+            }
+        }
+    }
+}
+
+// DistanceConstraint::project (distanceconstraint.cpp:20-40) for one run of consecutive distance constraints of the
+// STANDARD list, stored level by level (level_off[l] .. level_off[l + 1]); the schedule is built on the host when the
+// list changes (constraints are static).
+__global__ void __launch_bounds__(kSerialBlock) k2d_distance_run(double2 *__restrict__ ep, const double *__restrict__ imass, const u32 *__restrict__ counts,
+                                                                 const u32 *__restrict__ i1s, const u32 *__restrict__ i2s, const double *__restrict__ rest,
+                                                                 const u32 *__restrict__ level_off, u32 levels) {
+    for (u32 l = 0; l < levels; l++) {
+        if (l) __syncthreads();
+        const u32 b = level_off[l], e = level_off[l + 1];
+        for (u32 k = b + threadIdx.x; k < e; k += kSerialBlock) {
+            const u32 i1 = i1s[k], i2 = i2s[k];
+            const double w1 = imass[i1], w2 = imass[i2];
+            if (w1 == 0. && w2 == 0.) continue;
+            double2 e1 = ep[i1], e2 = ep[i2];
+            const double dx = e1.x - e2.x, dy = e1.y - e2.y;
+            const double wsum = w1 + w2, dist = sqrt(dx * dx + dy * dy), mag = dist - rest[k];
+            const double sd = (mag / wsum) / dist;
+            const double dpx = sd * dx, dpy = sd * dy;
+            const double c1 = (double)counts[i1], c2 = (double)counts[i2];
+            e1.x += ((-w1) * dpx) / c1; e1.y += ((-w1) * dpy) / c1;
+            e2.x += (w2 * dpx) / c2;    e2.y += (w2 * dpy) / c2;
+            ep[i1] = e1; ep[i2] = e2;
+        }
+    }
+}
+
+// TotalShapeConstraint::project for every body (totalshapeconstraint.cpp:14-24): Body::updateCOM (centre of mass and the
+// mass-weighted mean angle, with the reference's sequential unwrapping of consecutive angles, solver/particle.cpp:15-57),
+// then every member moves to its rotated rest position.  Bodies own disjoint particles, so they run in parallel; one
+// thread per body keeps the reference's summation order (bodies are a dozen particles).
+__global__ void __launch_bounds__(kBlock) k2d_shape(double2 *__restrict__ ep, const double *__restrict__ imass, const double2 *__restrict__ rs,
+                                                    const u32 *__restrict__ b_first, const u32 *__restrict__ b_count, const double *__restrict__ b_imass,
+                                                    const double *__restrict__ b_stiff, double2 *__restrict__ b_center, double *__restrict__ b_angle, u32 nb) {
+    const u32 b = blockIdx.x * kBlock + threadIdx.x;
+    if (b >= nb) return;
+    const u32 first = b_first[b], count = b_count[b];
+    const double bim = b_imass[b];
+    double tx = 0., ty = 0.;
+    for (u32 k = 0; k < count; k++) {
+        const double2 e = ep[first + k];
+        const double im = imass[first + k];
+        tx += e.x / im; ty += e.y / im;
+    }
+    const double cx = tx * bim, cy = ty * bim;
+    double angle = 0., prev = 0.;
+    for (u32 k = 0; k < count; k++) {
+        const double2 q = rs[first + k];
+        if (q.x * q.x + q.y * q.y == 0.) continue;
+        const double2 e = ep[first + k];
+        const double rx = e.x - cx, ry = e.y - cy;
+        const double co = rx * q.x + ry * q.y, si = ry * q.x - rx * q.y;
+        double next = atan2(si, co);
+        if (k > 0) { if (prev - next >= kPi) next += 2 * kPi; }
+        else { if (next < 0.) next += 2 * kPi; }
+        prev = next;
+        next /= imass[first + k];
+        angle += next;
+    }
+    angle *= bim;
+    b_center[b] = make_double2(cx, cy);
+    b_angle[b] = angle;
+    const double c = cos(angle), s = sin(angle), stiff = b_stiff[b];
+    for (u32 k = 0; k < count; k++) {
+        const double2 q = rs[first + k];
+        const double gx = (c * q.x - s * q.y) + cx, gy = (s * q.x + c * q.y) + cy;
+        double2 e = ep[first + k];
+        e.x += (gx - e.x) * stiff; e.y += (gy - e.y) * stiff;
+        ep[first + k] = e;
+    }
+}
+
+// TotalFluidConstraint / GasConstraint::project, first loop (totalfluidconstraint.cpp:45-93, gasconstraint.cpp:33-85): lambda
+// of every particle of STANDARD constraint `op`, 0 for everybody else (the constraint's lambdas is a QHash cleared per
+// call: any other particle reads 0, :106).  SOLID neighbours count S_SOLID-fold, immovable ones not at all.
+__global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ phase,
+                                                           const int *__restrict__ group, u32 n, int op, double p0, FluidConsts K, double *__restrict__ lambda,
+                                                           u32 *__restrict__ nbcount, const double2 *__restrict__ v, double2 *__restrict__ f) {
     __shared__ double2 s_ep[kTile];
     __shared__ double s_im[kTile];
+    __shared__ int s_ph[kTile];
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    const bool mine = i < n && fluid[i] == f;
+    const bool mine = i < n && group[i] == op;
     const double2 pi = i < n ? ep[i] : make_double2(0., 0.);
     double rho = 0., denom = 0., ox = 0., oy = 0.;
-    u32 nb = 0;
+    u32 nbc = 0;
     for (u32 base = 0; base < n; base += kTile) {
         __syncthreads();
-        if (base + threadIdx.x < n && threadIdx.x < kTile) { s_ep[threadIdx.x] = ep[base + threadIdx.x]; s_im[threadIdx.x] = imass[base + threadIdx.x]; }
+        if (base + threadIdx.x < n) { s_ep[threadIdx.x] = ep[base + threadIdx.x]; s_im[threadIdx.x] = imass[base + threadIdx.x]; s_ph[threadIdx.x] = phase[base + threadIdx.x]; }
         __syncthreads();
         if (!mine) continue;
-        const u32 cnt = min((u32)kTile, n - base);
-        for (u32 t = 0; t < cnt; t++) {
+        const u32 m = min((u32)kTile, n - base);
+        for (u32 t = 0; t < m; t++) {
             const u32 j = base + t;
             if (j == i) {  // the particle itself, at its place in the index order (:78-81)
-                nb++;
+                nbc++;
                 rho += poly6(0.) / s_im[t];
                 continue;
             }
@@ -151,12 +474,16 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__rest
             const double rx = pi.x - s_ep[t].x, ry = pi.y - s_ep[t].y;
             const double r2 = rx * rx + ry * ry;
             if (r2 < kH2) {
-                nb++;
-                rho += poly6(r2) / s_im[t];
+                nbc++;
+                double incr = poly6(r2) / s_im[t];
+                const bool solid = s_ph[t] == PS2D_PHASE_SOLID;
+                if (solid) incr *= K.s_solid;
+                rho += incr;
                 const double2 sg = spiky_grad(rx, ry, sqrt(r2));
                 const double gx = -sg.x / p0, gy = -sg.y / p0;  // grad(k, j) = -spikyGrad / p0 (:137-144)
                 denom += gx * gx + gy * gy;
-                ox += sg.x; oy += sg.y;                         // grad(k, i) = sum_j spikyGrad / p0 (:146-157)
+                const double w = solid ? K.s_solid : 1.;       // grad(k, i) = sum_j w_j spikyGrad / p0 (:146-157)
+                ox += w * sg.x; oy += w * sg.y;
             }
         }
     }
@@ -164,32 +491,43 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__rest
     if (!mine) { lambda[i] = 0.; return; }
     ox = ox / p0; oy = oy / p0;
     denom += ox * ox + oy * oy;
-    lambda[i] = -((rho / p0) - 1.) / (denom + kRelax);
-    nbcount[i] = nb;
+    const double p_rat = rho / p0;
+    if (K.gas && K.open) {  // open-boundary drag, gasconstraint.cpp:80
+        const double2 vi = v[i];
+        double2 fi = f[i];
+        const double s = 1. - p_rat;
+        fi.x += (vi.x * s) * -50.; fi.y += (vi.y * s) * -50.;
+        f[i] = fi;
+    }
+    lambda[i] = -(p_rat - 1.) / (denom + kRelax);
+    nbcount[i] = nbc;
 }
 
 // second loop (:95-111): delta_i = sum_j (lambda_i + lambda_j + s_corr) spikyGrad / p0, divided by (#neighbours incl. self +
-// boundary count) (:113-115).  Written to `delta`, applied by k2d_fluid_apply: all deltas of a fluid come from the same ep.
-__global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ fluid,
-                                                          u32 n, int f, double p0, const double *__restrict__ lambda, const u32 *__restrict__ nbcount,
-                                                          const u32 *__restrict__ counts, double2 *__restrict__ delta) {
-    __shared__ double2 s_ep[kTile];
+// constraint count) (:113-115).  Written to `delta`, applied by k2d_fluid_apply: all deltas of a constraint come from the
+// same ep.  Gas: the pseudo-vorticity force of gasconstraint.cpp:99-107 goes to the force accumulator.
+__global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ group, u32 n,
+                                                          int op, double p0, FluidConsts K, const double *__restrict__ lambda, const u32 *__restrict__ nbcount,
+                                                          const u32 *__restrict__ counts, double2 *__restrict__ delta, const double2 *__restrict__ v,
+                                                          double2 *__restrict__ f) {
+    __shared__ double2 s_ep[kTile], s_v[kTile];
     __shared__ double s_im[kTile], s_lam[kTile];
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    const bool mine = i < n && fluid[i] == f;
+    const bool mine = i < n && group[i] == op;
     const double2 pi = i < n ? ep[i] : make_double2(0., 0.);
     const double li = mine ? lambda[i] : 0.;
-    const double base6 = poly6(kDQ * kDQ * kH * kH);
-    double dx = 0., dy = 0.;
+    const double base6 = poly6(K.dq_p * K.dq_p * kH * kH);
+    double dx = 0., dy = 0., fvx = 0., fvy = 0.;
     for (u32 base = 0; base < n; base += kTile) {
         __syncthreads();
-        if (base + threadIdx.x < n && threadIdx.x < kTile) {
+        if (base + threadIdx.x < n) {
             s_ep[threadIdx.x] = ep[base + threadIdx.x]; s_im[threadIdx.x] = imass[base + threadIdx.x]; s_lam[threadIdx.x] = lambda[base + threadIdx.x];
+            if (K.gas) s_v[threadIdx.x] = v[base + threadIdx.x];
         }
         __syncthreads();
         if (!mine) continue;
-        const u32 cnt = min((u32)kTile, n - base);
-        for (u32 t = 0; t < cnt; t++) {
+        const u32 m = min((u32)kTile, n - base);
+        for (u32 t = 0; t < m; t++) {
             const u32 j = base + t;
             if (j == i || s_im[t] == 0.) continue;
             const double rx = pi.x - s_ep[t].x, ry = pi.y - s_ep[t].y;
@@ -197,19 +535,32 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restr
             if (r2 < kH2) {
                 const double rlen = sqrt(r2);
                 const double2 sg = spiky_grad(rx, ry, rlen);
-                const double corr = -kKP * pow(poly6(rlen * rlen) / base6, kEP);
+                const double corr = -K.k_p * pow(poly6(rlen * rlen) / base6, 4.);  // E_P 4
                 const double s = (li + s_lam[t]) + corr;
                 dx += s * sg.x; dy += s * sg.y;
+                if (K.gas) {
+                    const double2 g = spiky_grad(rx, ry, r2);  // [sic] the squared length as the length
+                    const double wx = g.x * s_v[t].x, wy = g.y * s_v[t].y;
+                    const double L = sqrt(wx * wx + wy * wy);
+                    const double cx = 0. * 0. - ry * L, cy = L * rx - 0. * 0.;  // cross((0,0,L), (rx,ry,0))
+                    const double p6 = poly6(r2);
+                    fvx += cx * p6; fvy += cy * p6;
+                }
             }
         }
     }
     if (!mine) return;
     const double div = (double)nbcount[i] + (double)counts[i];
     delta[i] = make_double2((dx / p0) / div, (dy / p0) / div);
+    if (K.gas) {
+        double2 fi = f[i];
+        fi.x += fvx; fi.y += fvy;
+        f[i] = fi;
+    }
 }
-__global__ void k2d_fluid_apply(double2 *__restrict__ ep, const double2 *__restrict__ delta, const int *__restrict__ fluid, u32 n, int f) {
+__global__ void k2d_fluid_apply(double2 *__restrict__ ep, const double2 *__restrict__ delta, const int *__restrict__ group, u32 n, int op) {
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n || fluid[i] != f) return;
+    if (i >= n || group[i] != op) return;
     double2 e = ep[i];
     const double2 d = delta[i];
     e.x += d.x; e.y += d.y;
@@ -230,7 +581,6 @@ __global__ void k2d_finish(double2 *__restrict__ p, double2 *__restrict__ v, con
 // glibc rand() = random(), TYPE_3: r[i] = r[i-31] + r[i-3], output r[i] >> 1 (after 310 discarded words)
 struct GlibcRand {
     std::vector<uint32_t> r;
-    size_t pos = 0;
     uint64_t calls = 0;
     void seed(uint32_t s) {
         r.assign(344, 0);
@@ -254,6 +604,20 @@ struct GlibcRand {
         return (int)(v >> 1);
     }
 };
+
+enum StdKind { STD_FLUID, STD_GAS, STD_DISTANCE };
+struct StdOp {  // one entry of m_globalConstraints[STANDARD]
+    StdKind kind;
+    double p0 = 0.;  // fluid / gas rest density
+    int open = 0;
+    u32 i1 = 0, i2 = 0;
+    double d = 0.;
+};
+struct DistanceRun {  // consecutive distance constraints [begin, end) of the STANDARD list, as uploaded level by level
+    size_t begin, end;
+    u32 dev_first, dev_level_first, levels;
+};
+struct Emitter { double x, y, rate, timer; u32 standard_index; };
 }  // namespace
 
 struct Ps2dCtx {
@@ -262,15 +626,33 @@ struct Ps2dCtx {
     Ps2dParams params{};
     uint64_t cap = 0;
     u32 n = 0;
-    double2 *p = nullptr, *v = nullptr, *ep = nullptr, *delta = nullptr;
-    double *imass = nullptr, *lambda = nullptr;
-    int *fluid = nullptr, *raw = nullptr;
-    u32 *flags = nullptr, *counts = nullptr, *rank = nullptr, *nbcount = nullptr, *num_dev = nullptr, *num_host = nullptr;
+    double2 *p = nullptr, *v = nullptr, *ep = nullptr, *f = nullptr, *delta = nullptr, *rs = nullptr, *sdf_grad = nullptr;
+    double *imass = nullptr, *tmass = nullptr, *sfric = nullptr, *kfric = nullptr, *lambda = nullptr, *sdf_dist = nullptr;
+    int *phase = nullptr, *bod = nullptr, *group = nullptr, *raw = nullptr;
+    u32 *static_counts = nullptr, *flags = nullptr, *counts = nullptr, *draws = nullptr, *rank = nullptr, *nbcount = nullptr, *nb = nullptr, *cnt = nullptr,
+        *lvl = nullptr, *cur = nullptr, *scalars = nullptr, *scalars_host = nullptr;  // scalars: [0] draws, [1] levels, [2] constraints, [3] overflow
+    unsigned char *nbq = nullptr;
+    // rigid bodies
+    u32 nbodies = 0, bodies_cap = 0;
+    u32 *b_first = nullptr, *b_count = nullptr;
+    double *b_imass = nullptr, *b_stiff = nullptr, *b_angle = nullptr;
+    double2 *b_center = nullptr;
+    // distance constraints, level-sorted per run
+    u32 *dc_i1 = nullptr, *dc_i2 = nullptr, *dc_level_off = nullptr;
+    double *dc_rest = nullptr;
+    size_t dc_cap = 0, dc_level_cap = 0;
+    std::vector<DistanceRun> runs;
+    bool standard_dirty = true;
+    std::vector<StdOp> standard;
+    std::vector<u32> h_static_counts;
+    std::vector<double> h_imass;  // host mirror: constraint constructors validate against it
+    std::vector<int> h_phase;
+    std::vector<Emitter> emitters;
     size_t raw_cap = 0;
-    std::vector<double> rho0;
     std::vector<int> h_raw;
     GlibcRand rng;
-    u32 last_num_boundary = 0, launches = 0;
+    int any_solid = 0, any_jitter = 0;
+    u32 last_num_boundary = 0, last_contacts = 0, last_levels = 0, launches = 0;
 };
 
 #define CU2(x)                                                                                        \
@@ -290,12 +672,16 @@ extern "C" void ps2d_default_params(Ps2dParams *p) {
     p->solver_iterations = 3;                     // simulation.h:11
 }
 
+template <class T>
+static bool dev_alloc(T **ptr, size_t count) { return cudaMalloc((void **)ptr, std::max<size_t>(count, 1) * sizeof(T)) == cudaSuccess; }
+
 extern "C" int ps2d_create(int device, const Ps2dParams *params, uint64_t max_particles, Ps2dCtx **out) {
     if (!params || !out || !max_particles) { ps_set_error("ps2d_create: bad argument"); return PS_ERR_INVALID; }
     *out = nullptr;
     if (!(params->x_bounds[0] < params->x_bounds[1]) || !(params->y_bounds[0] < params->y_bounds[1]) || params->solver_iterations > 64) {
         ps_set_error("ps2d_create: bad bounds or iteration count"); return PS_ERR_INVALID;
     }
+    if (max_particles > (1u << 28)) { ps_set_error("ps2d_create: max_particles too large"); return PS_ERR_INVALID; }
     int ndev = 0;
     CU2(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { ps_set_error("ps2d_create: device %d of %d", device, ndev); return PS_ERR_INVALID; }
@@ -307,11 +693,16 @@ extern "C" int ps2d_create(int device, const Ps2dParams *params, uint64_t max_pa
     c->device = device; c->params = *params; c->cap = max_particles;
     c->rng.seed(1);
     const size_t n = max_particles;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&c->p, n * 16) != cudaSuccess ||
-        cudaMalloc(&c->v, n * 16) != cudaSuccess || cudaMalloc(&c->ep, n * 16) != cudaSuccess || cudaMalloc(&c->delta, n * 16) != cudaSuccess ||
-        cudaMalloc(&c->imass, n * 8) != cudaSuccess || cudaMalloc(&c->lambda, n * 8) != cudaSuccess || cudaMalloc(&c->fluid, n * 4) != cudaSuccess ||
-        cudaMalloc(&c->flags, n * 4) != cudaSuccess || cudaMalloc(&c->counts, n * 4) != cudaSuccess || cudaMalloc(&c->rank, n * 4) != cudaSuccess ||
-        cudaMalloc(&c->nbcount, n * 4) != cudaSuccess || cudaMalloc(&c->num_dev, 4) != cudaSuccess || cudaMallocHost(&c->num_host, 4) != cudaSuccess) {
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && dev_alloc(&c->p, n) && dev_alloc(&c->v, n) && dev_alloc(&c->ep, n) && dev_alloc(&c->f, n) && dev_alloc(&c->delta, n) && dev_alloc(&c->rs, n) &&
+         dev_alloc(&c->sdf_grad, n) && dev_alloc(&c->imass, n) && dev_alloc(&c->tmass, n) && dev_alloc(&c->sfric, n) && dev_alloc(&c->kfric, n) &&
+         dev_alloc(&c->lambda, n) && dev_alloc(&c->sdf_dist, n) && dev_alloc(&c->phase, n) && dev_alloc(&c->bod, n) && dev_alloc(&c->group, n) &&
+         dev_alloc(&c->static_counts, n) && dev_alloc(&c->flags, n) && dev_alloc(&c->counts, n) && dev_alloc(&c->draws, n) && dev_alloc(&c->rank, n) &&
+         dev_alloc(&c->nbcount, n) && dev_alloc(&c->nb, n * kMaxC) && dev_alloc(&c->cnt, n) && dev_alloc(&c->lvl, n * kEntries) && dev_alloc(&c->cur, n) &&
+         dev_alloc(&c->nbq, n * kMaxC) && dev_alloc(&c->scalars, 4) && cudaMallocHost((void **)&c->scalars_host, 16) == cudaSuccess;
+    if (ok) ok = cudaMemsetAsync(c->f, 0, n * 16, c->stream) == cudaSuccess && cudaMemsetAsync(c->lambda, 0, n * 8, c->stream) == cudaSuccess &&
+                 cudaMemsetAsync(c->scalars, 0, 16, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    if (!ok) {
         ps_set_error("ps2d_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         ps2d_destroy(c);
         return PS_ERR_CUDA;
@@ -324,32 +715,251 @@ extern "C" int ps2d_destroy(Ps2dCtx *c) {
     if (!c) return PS_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void *ptrs[] = {c->p, c->v, c->ep, c->delta, c->imass, c->lambda, c->fluid, c->raw, c->flags, c->counts, c->rank, c->nbcount, c->num_dev};
+    void *ptrs[] = {c->p, c->v, c->ep, c->f, c->delta, c->rs, c->sdf_grad, c->imass, c->tmass, c->sfric, c->kfric, c->lambda, c->sdf_dist, c->phase, c->bod,
+                    c->group, c->raw, c->static_counts, c->flags, c->counts, c->draws, c->rank, c->nbcount, c->nb, c->cnt, c->lvl, c->cur, c->nbq, c->scalars,
+                    c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center, c->dc_i1, c->dc_i2, c->dc_level_off, c->dc_rest};
     for (void *q : ptrs) if (q) cudaFree(q);
-    if (c->num_host) cudaFreeHost(c->num_host);
+    if (c->scalars_host) cudaFreeHost(c->scalars_host);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return PS_OK;
 }
 
+template <class T>
+static cudaError_t upload(Ps2dCtx *c, T *dst, const T *src, size_t count) {
+    if (!count) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(c->stream);  // callers pass temporaries
+}
+
+extern "C" int ps2d_add_particles(Ps2dCtx *c, const double *p2, const double *v2, const double *inv_mass, const int32_t *phase, const int32_t *bod,
+                                  const double *s_friction, const double *k_friction, uint64_t n, uint64_t *first) {
+    if (!c || !p2 || !inv_mass || !phase) { ps_set_error("ps2d_add_particles: null argument"); return PS_ERR_INVALID; }
+    if (c->n + n > c->cap) { ps_set_error("ps2d_add_particles: %llu + %llu exceeds max_particles", (unsigned long long)c->n, (unsigned long long)n); return PS_ERR_CAPACITY; }
+    for (uint64_t k = 0; k < n; k++) {
+        if (phase[k] < PS2D_PHASE_SOLID || phase[k] > PS2D_PHASE_GAS) { ps_set_error("ps2d_add_particles: unknown phase %d", phase[k]); return PS_ERR_INVALID; }
+        if (!(inv_mass[k] >= 0.)) { ps_set_error("ps2d_add_particles: negative inverse mass"); return PS_ERR_INVALID; }
+    }
+    CU2(cudaSetDevice(c->device));
+    const u32 at = c->n;
+    std::vector<double> zeros2(2 * n, 0.), zeros(n, 0.), minus(n, -1.);
+    std::vector<int> none(n, -1);
+    std::vector<u32> zc(n, 0u);
+    CU2(upload(c, (double *)(c->p + at), p2, 2 * n));
+    CU2(upload(c, (double *)(c->ep + at), p2, 2 * n));
+    CU2(upload(c, (double *)(c->v + at), v2 ? v2 : zeros2.data(), 2 * n));
+    CU2(upload(c, (double *)(c->f + at), zeros2.data(), 2 * n));
+    CU2(upload(c, (double *)(c->rs + at), zeros2.data(), 2 * n));
+    CU2(upload(c, (double *)(c->sdf_grad + at), zeros2.data(), 2 * n));
+    CU2(upload(c, c->sdf_dist + at, minus.data(), n));
+    CU2(upload(c, c->imass + at, inv_mass, n));
+    CU2(upload(c, c->tmass + at, inv_mass, n));
+    CU2(upload(c, c->sfric + at, s_friction ? s_friction : zeros.data(), n));
+    CU2(upload(c, c->kfric + at, k_friction ? k_friction : zeros.data(), n));
+    CU2(upload(c, c->lambda + at, zeros.data(), n));
+    CU2(upload(c, c->phase + at, (const int *)phase, n));
+    CU2(upload(c, c->bod + at, bod ? (const int *)bod : none.data(), n));
+    CU2(upload(c, c->group + at, none.data(), n));
+    CU2(upload(c, c->static_counts + at, zc.data(), n));
+    for (uint64_t k = 0; k < n; k++) {
+        c->h_imass.push_back(inv_mass[k]);
+        c->h_phase.push_back(phase[k]);
+        c->h_static_counts.push_back(0);
+        if (phase[k] == PS2D_PHASE_SOLID) c->any_solid = 1; else c->any_jitter = 1;
+    }
+    c->n += (u32)n;
+    if (first) *first = at;
+    return PS_OK;
+}
+
+static int bump_static_counts(Ps2dCtx *c, u32 i) {
+    c->h_static_counts[i]++;
+    CU2(upload(c, c->static_counts + i, &c->h_static_counts[i], 1));
+    return PS_OK;
+}
+
+extern "C" int ps2d_add_distance_constraint(Ps2dCtx *c, uint32_t i1, uint32_t i2, double d) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    if (i1 >= c->n || i2 >= c->n || i1 == i2) { ps_set_error("ps2d_add_distance_constraint: bad particle indices %u, %u", i1, i2); return PS_ERR_INVALID; }
+    CU2(cudaSetDevice(c->device));
+    if (d < 0.) {  // DistanceConstraint(first, second, particles): d = length(p1 - p2)
+        double a[2], b[2];
+        CU2(cudaMemcpy(a, c->p + i1, 16, cudaMemcpyDeviceToHost));
+        CU2(cudaMemcpy(b, c->p + i2, 16, cudaMemcpyDeviceToHost));
+        const double x = a[0] - b[0], y = a[1] - b[1];
+        d = std::sqrt(x * x + y * y);
+    }
+    StdOp op;
+    op.kind = STD_DISTANCE; op.i1 = i1; op.i2 = i2; op.d = d;
+    c->standard.push_back(op);
+    c->standard_dirty = true;
+    int r = bump_static_counts(c, i1);
+    if (r == PS_OK) r = bump_static_counts(c, i2);
+    return r;
+}
+
+static int add_group(Ps2dCtx *c, const uint32_t *indices, uint64_t n, double density, int want_phase, int open, uint32_t *standard_index, const char *who) {
+    if (!c || (!indices && n)) { ps_set_error("%s: null argument", who); return PS_ERR_INVALID; }
+    if (!(density > 0.)) { ps_set_error("%s: density must be positive", who); return PS_ERR_INVALID; }
+    for (uint64_t k = 0; k < n; k++) {
+        if (indices[k] >= c->n) { ps_set_error("%s: particle index %u out of range", who, indices[k]); return PS_ERR_INVALID; }
+        if (c->h_phase[indices[k]] != want_phase) { ps_set_error("%s: particle %u has phase %d", who, indices[k], c->h_phase[indices[k]]); return PS_ERR_INVALID; }
+        if (c->h_imass[indices[k]] == 0.) { ps_set_error("A fluid cannot have a point of infinite mass."); return PS_ERR_INVALID; }  // simulation.cpp:419-422,441-444
+    }
+    CU2(cudaSetDevice(c->device));
+    const int id = (int)c->standard.size();
+    for (uint64_t k = 0; k < n; k++) CU2(upload(c, c->group + indices[k], &id, 1));
+    StdOp op;
+    op.kind = want_phase == PS2D_PHASE_GAS ? STD_GAS : STD_FLUID; op.p0 = density; op.open = open;
+    c->standard.push_back(op);
+    c->standard_dirty = true;
+    if (standard_index) *standard_index = (u32)id;
+    return PS_OK;
+}
+extern "C" int ps2d_add_fluid_constraint(Ps2dCtx *c, const uint32_t *indices, uint64_t n, double density, uint32_t *standard_index) {
+    return add_group(c, indices, n, density, PS2D_PHASE_FLUID, 0, standard_index, "ps2d_add_fluid_constraint");
+}
+extern "C" int ps2d_add_gas_constraint(Ps2dCtx *c, const uint32_t *indices, uint64_t n, double density, int open, uint32_t *standard_index) {
+    return add_group(c, indices, n, density, PS2D_PHASE_GAS, open, standard_index, "ps2d_add_gas_constraint");
+}
+
+static int grow_bodies(Ps2dCtx *c) {
+    if (c->nbodies < c->bodies_cap) return PS_OK;
+    const u32 cap = std::max<u32>(64, c->bodies_cap * 2);
+    u32 *bf = nullptr, *bc = nullptr;
+    double *bi = nullptr, *bs = nullptr, *ba = nullptr;
+    double2 *bcen = nullptr;
+    if (!dev_alloc(&bf, cap) || !dev_alloc(&bc, cap) || !dev_alloc(&bi, cap) || !dev_alloc(&bs, cap) || !dev_alloc(&ba, cap) || !dev_alloc(&bcen, cap)) {
+        ps_set_error("ps2d: body table allocation failed"); return PS_ERR_CUDA;
+    }
+    if (c->nbodies) {
+        CU2(cudaMemcpy(bf, c->b_first, c->nbodies * 4, cudaMemcpyDeviceToDevice)); CU2(cudaMemcpy(bc, c->b_count, c->nbodies * 4, cudaMemcpyDeviceToDevice));
+        CU2(cudaMemcpy(bi, c->b_imass, c->nbodies * 8, cudaMemcpyDeviceToDevice)); CU2(cudaMemcpy(bs, c->b_stiff, c->nbodies * 8, cudaMemcpyDeviceToDevice));
+        CU2(cudaMemcpy(ba, c->b_angle, c->nbodies * 8, cudaMemcpyDeviceToDevice)); CU2(cudaMemcpy(bcen, c->b_center, c->nbodies * 16, cudaMemcpyDeviceToDevice));
+    }
+    void *old[] = {c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center};
+    for (void *q : old) if (q) cudaFree(q);
+    c->b_first = bf; c->b_count = bc; c->b_imass = bi; c->b_stiff = bs; c->b_angle = ba; c->b_center = bcen; c->bodies_cap = cap;
+    return PS_OK;
+}
+
+extern "C" int ps2d_restore_rigid_body(Ps2dCtx *c, uint32_t first, uint32_t n, const double *rs2, const double *sdf3, double inv_mass, const double *center2,
+                                       double angle, double stiffness, uint32_t *body_index) {
+    if (!c || !rs2 || !sdf3 || !center2) { ps_set_error("ps2d_restore_rigid_body: null argument"); return PS_ERR_INVALID; }
+    if (n <= 1) { ps_set_error("Rigid bodies must be at least 2 points."); return PS_ERR_INVALID; }  // simulation.cpp:371-374
+    if ((uint64_t)first + n > c->n) { ps_set_error("ps2d_restore_rigid_body: particles [%u, %u) out of range", first, first + n); return PS_ERR_INVALID; }
+    for (u32 k = 0; k < n; k++) {
+        if (c->h_phase[first + k] != PS2D_PHASE_SOLID) { ps_set_error("ps2d_restore_rigid_body: particle %u is not SOLID", first + k); return PS_ERR_INVALID; }
+        if (c->h_imass[first + k] == 0.) { ps_set_error("A rigid body cannot have a point of infinite mass."); return PS_ERR_INVALID; }  // simulation.cpp:386-389
+    }
+    CU2(cudaSetDevice(c->device));
+    int r = grow_bodies(c);
+    if (r != PS_OK) return r;
+    const u32 b = c->nbodies;
+    std::vector<double> grad(2 * (size_t)n), dist(n);
+    std::vector<int> bods(n, (int)b);
+    for (u32 k = 0; k < n; k++) { grad[2 * k] = sdf3[3 * k]; grad[2 * k + 1] = sdf3[3 * k + 1]; dist[k] = sdf3[3 * k + 2]; }
+    CU2(upload(c, (double *)(c->rs + first), rs2, 2 * (size_t)n));
+    CU2(upload(c, (double *)(c->sdf_grad + first), grad.data(), 2 * (size_t)n));
+    CU2(upload(c, c->sdf_dist + first, dist.data(), n));
+    CU2(upload(c, c->bod + first, bods.data(), n));
+    CU2(upload(c, c->b_first + b, &first, 1));
+    CU2(upload(c, c->b_count + b, &n, 1));
+    CU2(upload(c, c->b_imass + b, &inv_mass, 1));
+    CU2(upload(c, c->b_stiff + b, &stiffness, 1));
+    CU2(upload(c, c->b_angle + b, &angle, 1));
+    CU2(upload(c, (double *)(c->b_center + b), center2, 2));
+    for (u32 k = 0; k < n; k++) c->h_static_counts[first + k]++;  // TotalShapeConstraint::updateCounts
+    CU2(upload(c, c->static_counts + first, &c->h_static_counts[first], n));
+    c->nbodies++;
+    if (body_index) *body_index = b;
+    return PS_OK;
+}
+
+extern "C" int ps2d_create_rigid_body(Ps2dCtx *c, const double *p2, const double *v2, const double *inv_mass, const double *s_friction,
+                                      const double *k_friction, const double *sdf3, uint64_t n, uint32_t *body_index) {
+    if (!c || !p2 || !inv_mass || !sdf3) { ps_set_error("ps2d_create_rigid_body: null argument"); return PS_ERR_INVALID; }
+    if (n <= 1) { ps_set_error("Rigid bodies must be at least 2 points."); return PS_ERR_INVALID; }
+    double total_mass = 0.;
+    for (uint64_t k = 0; k < n; k++) {
+        if (inv_mass[k] == 0.) { ps_set_error("A rigid body cannot have a point of infinite mass."); return PS_ERR_INVALID; }
+        total_mass += 1.0 / inv_mass[k];
+    }
+    // body->imass = 1 / totalMass; updateCOM(particles, false): centre from p (the angle loop sees no r vectors yet: 0);
+    // computeRs: r_i = p_i - centre, imass recomputed over the particles with r != 0 (simulation.cpp:398-402, particle.cpp:59-73)
+    double bim = 1.0 / total_mass, tx = 0., ty = 0.;
+    for (uint64_t k = 0; k < n; k++) { tx += p2[2 * k] / inv_mass[k]; ty += p2[2 * k + 1] / inv_mass[k]; }
+    const double center[2] = {tx * bim, ty * bim};
+    std::vector<double> rs(2 * n);
+    double m = 0.;
+    for (uint64_t k = 0; k < n; k++) {
+        const double rx = p2[2 * k] - center[0], ry = p2[2 * k + 1] - center[1];
+        rs[2 * k] = rx; rs[2 * k + 1] = ry;
+        if (rx * rx + ry * ry != 0.) m += 1.0 / inv_mass[k];
+    }
+    bim = 1.0 / m;
+    std::vector<int32_t> ph(n, PS2D_PHASE_SOLID);
+    uint64_t first = 0;
+    int r = ps2d_add_particles(c, p2, v2, inv_mass, ph.data(), nullptr, s_friction, k_friction, n, &first);
+    if (r != PS_OK) return r;
+    return ps2d_restore_rigid_body(c, (u32)first, (u32)n, rs.data(), sdf3, bim, center, 0., 1., body_index);
+}
+
 extern "C" int ps2d_create_fluid(Ps2dCtx *c, const double *p2, const double *v2, const double *inv_mass, uint64_t n, double density) {
     if (!c || !p2 || !v2 || !inv_mass) { ps_set_error("ps2d_create_fluid: null argument"); return PS_ERR_INVALID; }
-    if (c->n + n > c->cap) { ps_set_error("ps2d_create_fluid: %llu + %llu exceeds max_particles", (unsigned long long)c->n, (unsigned long long)n); return PS_ERR_CAPACITY; }
     if (!(density > 0.)) { ps_set_error("ps2d_create_fluid: density must be positive"); return PS_ERR_INVALID; }
     for (uint64_t k = 0; k < n; k++)
         if (inv_mass[k] == 0.0) { ps_set_error("A fluid cannot have a point of infinite mass."); return PS_ERR_INVALID; }  // simulation.cpp:441-444
-    CU2(cudaSetDevice(c->device));
-    std::vector<int> fl(n, (int)c->rho0.size());
-    CU2(cudaMemcpyAsync(c->p + c->n, p2, n * 16, cudaMemcpyHostToDevice, c->stream));
-    CU2(cudaMemcpyAsync(c->v + c->n, v2, n * 16, cudaMemcpyHostToDevice, c->stream));
-    CU2(cudaMemcpyAsync(c->ep + c->n, p2, n * 16, cudaMemcpyHostToDevice, c->stream));
-    CU2(cudaMemcpyAsync(c->imass + c->n, inv_mass, n * 8, cudaMemcpyHostToDevice, c->stream));
-    CU2(cudaMemcpyAsync(c->fluid + c->n, fl.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
-    CU2(cudaStreamSynchronize(c->stream));
-    c->n += (u32)n;
-    c->rho0.push_back(density);
+    std::vector<int32_t> ph(n, PS2D_PHASE_FLUID);
+    uint64_t first = 0;
+    int r = ps2d_add_particles(c, p2, v2, inv_mass, ph.data(), nullptr, nullptr, nullptr, n, &first);
+    if (r != PS_OK) return r;
+    std::vector<u32> idx(n);
+    for (uint64_t k = 0; k < n; k++) idx[k] = (u32)(first + k);
+    return ps2d_add_fluid_constraint(c, idx.data(), n, density, nullptr);
+}
+
+extern "C" int ps2d_create_gas(Ps2dCtx *c, const double *p2, const double *v2, const double *inv_mass, uint64_t n, double density, int open,
+                               uint32_t *standard_index) {
+    if (!c || !p2 || !inv_mass) { ps_set_error("ps2d_create_gas: null argument"); return PS_ERR_INVALID; }
+    if (!(density > 0.)) { ps_set_error("ps2d_create_gas: density must be positive"); return PS_ERR_INVALID; }
+    for (uint64_t k = 0; k < n; k++)
+        if (inv_mass[k] == 0.0) { ps_set_error("A fluid cannot have a point of infinite mass."); return PS_ERR_INVALID; }  // simulation.cpp:419-422
+    std::vector<int32_t> ph(n, PS2D_PHASE_GAS);
+    uint64_t first = 0;
+    int r = ps2d_add_particles(c, p2, v2, inv_mass, ph.data(), nullptr, nullptr, nullptr, n, &first);
+    if (r != PS_OK) return r;
+    std::vector<u32> idx(n);
+    for (uint64_t k = 0; k < n; k++) idx[k] = (u32)(first + k);
+    return ps2d_add_gas_constraint(c, idx.data(), n, density, open, standard_index);
+}
+
+extern "C" int ps2d_create_smoke_emitter(Ps2dCtx *c, const double *posn2, double rate, uint32_t standard_index, double timer) {
+    if (!c || !posn2) { ps_set_error("ps2d_create_smoke_emitter: null argument"); return PS_ERR_INVALID; }
+    if (!(rate > 0.)) { ps_set_error("ps2d_create_smoke_emitter: rate must be positive"); return PS_ERR_INVALID; }
+    if (standard_index != UINT32_MAX && (standard_index >= c->standard.size() || c->standard[standard_index].kind != STD_GAS)) {
+        ps_set_error("ps2d_create_smoke_emitter: STANDARD constraint %u is not a gas", standard_index); return PS_ERR_INVALID;
+    }
+    c->emitters.push_back(Emitter{posn2[0], posn2[1], rate, timer, standard_index});
     return PS_OK;
 }
+
+extern "C" int ps2d_set_forces(Ps2dCtx *c, const double *f2) {
+    if (!c || !f2) { ps_set_error("ps2d_set_forces: null argument"); return PS_ERR_INVALID; }
+    CU2(cudaSetDevice(c->device));
+    CU2(upload(c, (double *)c->f, f2, 2 * (size_t)c->n));
+    return PS_OK;
+}
+extern "C" int ps2d_body_state(Ps2dCtx *c, uint32_t body, double *center2, double *angle) {
+    if (!c || body >= c->nbodies) { ps_set_error("ps2d_body_state: no body %u", body); return PS_ERR_INVALID; }
+    CU2(cudaSetDevice(c->device));
+    CU2(cudaStreamSynchronize(c->stream));
+    if (center2) CU2(cudaMemcpy(center2, c->b_center + body, 16, cudaMemcpyDeviceToHost));
+    if (angle) CU2(cudaMemcpy(angle, c->b_angle + body, 8, cudaMemcpyDeviceToHost));
+    return PS_OK;
+}
+extern "C" uint32_t ps2d_num_bodies(Ps2dCtx *c) { return c ? c->nbodies : 0; }
 
 extern "C" int ps2d_seed_rand(Ps2dCtx *c, uint32_t seed, uint64_t skip) {
     if (!c) return PS_ERR_INVALID;
@@ -360,47 +970,134 @@ extern "C" int ps2d_seed_rand(Ps2dCtx *c, uint32_t seed, uint64_t skip) {
 extern "C" uint64_t ps2d_rand_calls(Ps2dCtx *c) { return c ? c->rng.calls : 0; }
 extern "C" uint64_t ps2d_num_particles(Ps2dCtx *c) { return c ? c->n : 0; }
 extern "C" uint32_t ps2d_last_num_boundary_constraints(Ps2dCtx *c) { return c ? c->last_num_boundary : 0; }
+extern "C" uint32_t ps2d_last_num_contact_constraints(Ps2dCtx *c) { return c ? c->last_contacts : 0; }
+extern "C" uint32_t ps2d_last_num_levels(Ps2dCtx *c) { return c ? c->last_levels : 0; }
 extern "C" uint32_t ps2d_launches_per_tick(Ps2dCtx *c) { return c ? c->launches : 0; }
+
+// Level schedule of the static distance constraints: every maximal run of consecutive distance constraints of the
+// STANDARD list is sorted (stably) by level and uploaded with its level offsets.
+static int rebuild_standard(Ps2dCtx *c) {
+    c->runs.clear();
+    std::vector<u32> i1, i2, level_off;
+    std::vector<double> rest;
+    std::vector<u32> last(c->n, 0);
+    const size_t m = c->standard.size();
+    size_t k = 0;
+    while (k < m) {
+        if (c->standard[k].kind != STD_DISTANCE) { k++; continue; }
+        size_t e = k;
+        while (e < m && c->standard[e].kind == STD_DISTANCE) e++;
+        std::vector<u32> lv(e - k);
+        u32 levels = 0;
+        for (size_t q = k; q < e; q++) {
+            const StdOp &o = c->standard[q];
+            const u32 l = std::max(last[o.i1], last[o.i2]) + 1;
+            last[o.i1] = last[o.i2] = l;
+            lv[q - k] = l;
+            levels = std::max(levels, l);
+        }
+        for (size_t q = k; q < e; q++) last[c->standard[q].i1] = last[c->standard[q].i2] = 0;
+        DistanceRun run{k, e, (u32)i1.size(), (u32)level_off.size(), levels};
+        for (u32 l = 1; l <= levels; l++) {
+            level_off.push_back((u32)i1.size());
+            for (size_t q = k; q < e; q++)
+                if (lv[q - k] == l) { i1.push_back(c->standard[q].i1); i2.push_back(c->standard[q].i2); rest.push_back(c->standard[q].d); }
+        }
+        level_off.push_back((u32)i1.size());
+        c->runs.push_back(run);
+        k = e;
+    }
+    if (i1.size() > c->dc_cap) {
+        for (void *q : {(void *)c->dc_i1, (void *)c->dc_i2, (void *)c->dc_rest}) if (q) cudaFree(q);
+        c->dc_i1 = c->dc_i2 = nullptr; c->dc_rest = nullptr;
+        c->dc_cap = i1.size() * 2;
+        if (!dev_alloc(&c->dc_i1, c->dc_cap) || !dev_alloc(&c->dc_i2, c->dc_cap) || !dev_alloc(&c->dc_rest, c->dc_cap)) { ps_set_error("ps2d: distance table allocation failed"); return PS_ERR_CUDA; }
+    }
+    if (level_off.size() > c->dc_level_cap) {
+        if (c->dc_level_off) cudaFree(c->dc_level_off);
+        c->dc_level_off = nullptr;
+        c->dc_level_cap = level_off.size() * 2;
+        if (!dev_alloc(&c->dc_level_off, c->dc_level_cap)) { ps_set_error("ps2d: distance table allocation failed"); return PS_ERR_CUDA; }
+    }
+    CU2(upload(c, c->dc_i1, i1.data(), i1.size()));
+    CU2(upload(c, c->dc_i2, i2.data(), i2.size()));
+    CU2(upload(c, c->dc_rest, rest.data(), rest.size()));
+    CU2(upload(c, c->dc_level_off, level_off.data(), level_off.size()));
+    c->standard_dirty = false;
+    return PS_OK;
+}
 
 extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
     if (!c->n) return PS_OK;
     CU2(cudaSetDevice(c->device));
+    if (c->standard_dirty) {
+        int r = rebuild_standard(c);
+        if (r != PS_OK) return r;
+    }
     cudaStream_t s = c->stream;
     const u32 n = c->n, blocks = (n + kBlock - 1) / kBlock;
     const Ps2dParams &P = c->params;
+    const double x0 = P.x_bounds[0], x1 = P.x_bounds[1], y0 = P.y_bounds[0], y1 = P.y_bounds[1];
     u32 launches = 0;
-    k2d_predict<<<blocks, kBlock, 0, s>>>(c->v, c->ep, c->p, c->imass, n, dt, P.gravity[0], P.gravity[1]);
-    k2d_boundary_flags<<<blocks, kBlock, 0, s>>>(c->ep, n, P.x_bounds[0], P.x_bounds[1], P.y_bounds[0], P.y_bounds[1], c->flags, c->counts);
-    k2d_scan_counts<<<1, 1024, 0, s>>>(c->counts, c->rank, n, c->num_dev);
-    launches += 3;
-    // the number of wall constraints decides how many draws of the rand() stream this tick consumes: one per constraint
-    // per solver iteration, in list order (the only host round trip of a tick)
-    CU2(cudaMemcpyAsync(c->num_host, c->num_dev, 4, cudaMemcpyDeviceToHost, s));
+    k2d_predict<<<blocks, kBlock, 0, s>>>(c->v, c->ep, c->f, c->tmass, c->p, c->imass, c->phase, n, dt, P.gravity[0], P.gravity[1]);
+    k2d_find_contacts<<<blocks, kBlock, 0, s>>>(c->ep, c->imass, c->phase, c->bod, c->static_counts, n, x0, x1, y0, y1, c->nb, c->cnt, c->flags, c->counts,
+                                                c->draws, c->scalars + 3, c->any_solid);
+    k2d_scan_counts<<<1, 1024, 0, s>>>(c->draws, c->rank, n, c->scalars);
+    k2d_contact_levels<<<1, kSerialBlock, 0, s>>>(c->nb, c->cnt, c->flags, n, c->nbq, c->lvl, c->scalars + 1);
+    launches += 4;
+    // the number of jittered wall constraints decides how many draws of the rand() stream this tick consumes: one per
+    // constraint per solver iteration, in list order (the only host round trip of a tick)
+    CU2(cudaMemcpyAsync(c->scalars_host, c->scalars, 16, cudaMemcpyDeviceToHost, s));
     CU2(cudaStreamSynchronize(s));
-    const u32 num = *c->num_host;
+    const u32 num = c->scalars_host[0];
     c->last_num_boundary = num;
-    const size_t draws = (size_t)num * P.solver_iterations;
-    if (draws) {
-        c->h_raw.resize(draws);
-        for (size_t k = 0; k < draws; k++) c->h_raw[k] = c->rng.next();
-        if (draws > c->raw_cap) {
-            if (c->raw) CU2(cudaFree(c->raw));
-            CU2(cudaMalloc(&c->raw, draws * 2 * sizeof(int)));
-            c->raw_cap = draws * 2;
-        }
-        CU2(cudaMemcpyAsync(c->raw, c->h_raw.data(), draws * sizeof(int), cudaMemcpyHostToDevice, s));
+    c->last_levels = c->scalars_host[1];
+    c->last_contacts = c->scalars_host[2];
+    if (c->scalars_host[3]) {
+        ps_set_error("ps2d_tick: a particle has %u contacts, more than PS2D_MAX_CONTACTS = %d", c->scalars_host[3], kMaxC);
+        cudaMemsetAsync(c->scalars + 3, 0, 4, s);
+        return PS_ERR_CAPACITY;
     }
+    const size_t ndraws = (size_t)num * P.solver_iterations;
+    if (ndraws) {
+        c->h_raw.resize(ndraws);
+        for (size_t k = 0; k < ndraws; k++) c->h_raw[k] = c->rng.next();
+        if (ndraws > c->raw_cap) {
+            if (c->raw) CU2(cudaFree(c->raw));
+            c->raw = nullptr;
+            CU2(cudaMalloc(&c->raw, ndraws * 2 * sizeof(int)));
+            c->raw_cap = ndraws * 2;
+        }
+        CU2(cudaMemcpyAsync(c->raw, c->h_raw.data(), ndraws * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    Particles2D V{c->ep, c->p, c->tmass, c->sfric, c->kfric, c->phase, c->bod, c->counts, c->sdf_grad, c->sdf_dist, c->b_angle};
     for (u32 it = 0; it < P.solver_iterations; it++) {
-        if (num) {
-            k2d_boundary_project<<<blocks, kBlock, 0, s>>>(c->ep, c->flags, c->rank, n, c->raw, it * num, P.x_bounds[0], P.x_bounds[1], P.y_bounds[0], P.y_bounds[1]);
+        if (c->last_contacts) {  // CONTACT group
+            k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, it * num, x0, x1, y0, y1);
             launches++;
         }
-        for (size_t f = 0; f < c->rho0.size(); f++) {
-            k2d_fluid_lambda<<<blocks, kBlock, 0, s>>>(c->ep, c->imass, c->fluid, n, (int)f, c->rho0[f], c->lambda, c->nbcount);
-            k2d_fluid_delta<<<blocks, kBlock, 0, s>>>(c->ep, c->imass, c->fluid, n, (int)f, c->rho0[f], c->lambda, c->nbcount, c->counts, c->delta);
-            k2d_fluid_apply<<<blocks, kBlock, 0, s>>>(c->ep, c->delta, c->fluid, n, (int)f);
+        size_t run = 0;  // STANDARD group, in list order
+        for (size_t k = 0; k < c->standard.size();) {
+            const StdOp &op = c->standard[k];
+            if (op.kind == STD_DISTANCE) {
+                const DistanceRun &R = c->runs[run++];
+                k2d_distance_run<<<1, kSerialBlock, 0, s>>>(c->ep, c->imass, c->counts, c->dc_i1, c->dc_i2, c->dc_rest, c->dc_level_off + R.dev_level_first, R.levels);
+                launches++;
+                k = R.end;
+                continue;
+            }
+            const FluidConsts K = op.kind == STD_GAS ? FluidConsts{.2, .25, .5, 1, op.open} : FluidConsts{.1, .2, 0., 0, 0};
+            k2d_fluid_lambda<<<blocks, kBlock, 0, s>>>(c->ep, c->imass, c->phase, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->v, c->f);
+            k2d_fluid_delta<<<blocks, kBlock, 0, s>>>(c->ep, c->imass, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->counts, c->delta, c->v, c->f);
+            k2d_fluid_apply<<<blocks, kBlock, 0, s>>>(c->ep, c->delta, c->group, n, (int)k);
             launches += 3;
+            k++;
+        }
+        if (c->nbodies) {  // SHAPE group
+            k2d_shape<<<(c->nbodies + kBlock - 1) / kBlock, kBlock, 0, s>>>(c->ep, c->imass, c->rs, c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_center,
+                                                                             c->b_angle, c->nbodies);
+            launches++;
         }
     }
     k2d_finish<<<blocks, kBlock, 0, s>>>(c->p, c->v, c->ep, n, dt);
@@ -409,10 +1106,25 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ps_set_error("ps2d_tick: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
     CU2(cudaStreamSynchronize(s));  // h_raw is reused by the next tick
+    // OpenSmokeEmitter::tick (opensmokeemitter.cpp:17-29): particle injection into the gas constraint
+    for (Emitter &em : c->emitters) {
+        em.timer += dt;
+        while (em.timer >= 1. / em.rate) {
+            em.timer -= 1. / em.rate;
+            if (em.standard_index == UINT32_MAX) continue;
+            const double pos[2] = {em.x, em.y}, im = 1. / 1.;
+            const int32_t ph = PS2D_PHASE_GAS;
+            uint64_t at = 0;
+            int r = ps2d_add_particles(c, pos, nullptr, &im, &ph, nullptr, nullptr, nullptr, 1, &at);
+            if (r != PS_OK) return r;
+            const int id = (int)em.standard_index;
+            CU2(upload(c, c->group + at, &id, 1));
+        }
+    }
     return PS_OK;
 }
 
-extern "C" int ps2d_download(Ps2dCtx *c, int which, double *host) {
+extern "C" int ps2d_download(Ps2dCtx *c, int which, void *host) {
     if (!c || !host) { ps_set_error("ps2d_download: null argument"); return PS_ERR_INVALID; }
     CU2(cudaSetDevice(c->device));
     const void *src = nullptr;
@@ -421,7 +1133,10 @@ extern "C" int ps2d_download(Ps2dCtx *c, int which, double *host) {
         case PS2D_ARR_P: src = c->p; break;
         case PS2D_ARR_V: src = c->v; break;
         case PS2D_ARR_EP: src = c->ep; break;
+        case PS2D_ARR_F: src = c->f; break;
         case PS2D_ARR_LAMBDA: src = c->lambda; bytes = (size_t)c->n * 8; break;
+        case PS2D_ARR_TMASS: src = c->tmass; bytes = (size_t)c->n * 8; break;
+        case PS2D_ARR_COUNTS: src = c->counts; bytes = (size_t)c->n * 4; break;
         default: ps_set_error("ps2d_download: unknown array %d", which); return PS_ERR_INVALID;
     }
     CU2(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -431,13 +1146,12 @@ extern "C" int ps2d_download(Ps2dCtx *c, int which, double *host) {
 
 extern "C" int ps2d_kinetic_energy(Ps2dCtx *c, double *out) {
     if (!c || !out) return PS_ERR_INVALID;
-    std::vector<double> v((size_t)c->n * 2), im(c->n);
+    std::vector<double> v((size_t)c->n * 2);
     int r = ps2d_download(c, PS2D_ARR_V, v.data());
     if (r != PS_OK) return r;
-    CU2(cudaMemcpy(im.data(), c->imass, (size_t)c->n * 8, cudaMemcpyDeviceToHost));
     double e = 0;  // same order as Simulation::getKineticEnergy
     for (u32 i = 0; i < c->n; i++)
-        if (im[i] != 0.) e += .5 * (v[2 * i] * v[2 * i] + v[2 * i + 1] * v[2 * i + 1]) / im[i];
+        if (c->h_imass[i] != 0.) e += .5 * (v[2 * i] * v[2 * i] + v[2 * i + 1] * v[2 * i + 1]) / c->h_imass[i];
     *out = e;
     return PS_OK;
 }
