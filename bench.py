@@ -297,8 +297,22 @@ def run_ours(args, rank, world, local_rank):
             traffic = json.load(open(tp)).get(dom)
         except Exception:
             traffic = None
+    # The dominant kernels are bound by instruction issue, not HBM: report that ceiling beside the (required) HBM one.
+    # warp-instructions per launch come from the committed ncu capture (smsp__inst_executed.sum, profiles/ncu_inst.json);
+    # peak issue rate = 148 SMs x 4 schedulers x 1 warp-instruction per cycle at the SM clock sampled during the run.
+    issue = None
+    ip = os.path.join(ROOT, "profiles", "ncu_inst.json")
+    if os.path.exists(ip):
+        try:
+            inst = float(json.load(open(ip))[dom])
+            sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+            per_launch_s = kernels[dom]["ms_per_step"] * 1e-3 / ITERS
+            issue = {"warp_inst_per_launch": inst, "achieved_ginst_s": round(inst / per_launch_s / 1e9, 1),
+                     "peak_ginst_s": round(148 * 4 * sm_hz / 1e9, 1), "frac": round(inst / per_launch_s / (148 * 4 * sm_hz), 4)}
+        except Exception:
+            issue = None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac_hbm"], "traffic": traffic, "peak_kind": peak_kind,
+                "frac": kernels[dom]["frac_hbm"], "traffic": traffic, "peak_kind": peak_kind, "issue": issue,
                 "note": "the PBF kernels are FP32-issue bound, not HBM bound: ~200 candidate tests + ~140 interactions per particle against "
                         "36-64 compulsory bytes (SURVEY 8d, DESIGN.md 4).  'traffic' exceeds the algorithmic bytes on purpose: K6 leaves "
                         "~0.7 KB/particle of neighbour lists in HBM so that K7 does not search again (idle bandwidth traded for issue slots); "

@@ -176,6 +176,22 @@ int ps_slab_pack_migrants(PsCtx *ctx, float x_lo, float x_hi, void *left_buf, vo
 int ps_slab_append_migrants(PsCtx *ctx, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right);
 /* lambda is computed for owned particles and for ghosts with x in [x_min, x_max] only (default: everywhere) */
 int ps_slab_set_lambda_range(PsCtx *ctx, float x_min, float x_max);
+
+/* ---- parts of the unified solver that the reference's GPU code does not contain (its rigid_body_functor is an empty
+ * stub, solver_kernel.cuh:289-312; XSPH / vorticity exist nowhere in it — SURVEY §0).  Off unless asked for; every
+ * parity run of the reference's scenes is unaffected.  Parity unpinned (no reference implementation). ---- */
+/* 3-D shape matching (Macklin et al. 2014 §5.1): a rigid body over existing particles whose rest shape is their current
+ * configuration; projected once per solver iteration after the distance constraints (one warp per body: shuffle-reduced
+ * moment matrix, polar decomposition by the quaternion iteration of Mueller et al. 2016).  stiffness in (0, 1]. */
+int ps_add_rigid_body(PsCtx *ctx, const uint32_t *indices, uint64_t n, float stiffness, uint32_t *body);
+uint64_t ps_num_rigid_bodies(PsCtx *ctx);
+int ps_solve_shapes(PsCtx *ctx);                                         /* the stage alone */
+int ps_rigid_body_rotation(PsCtx *ctx, uint32_t body, float *quat_xyzw); /* rotation found by the last projection */
+/* XSPH viscosity (v_i += c sum_j (v_j - v_i) W_ij) and vorticity confinement (Macklin & Mueller 2013, eqs. 15-17) as a
+ * velocity post-pass of ps_step on the PBF neighbour lists; both coefficients 0 (the default) = off. */
+int ps_set_viscosity(PsCtx *ctx, float xsph_c, float vorticity_eps);
+int ps_find_neighbors(PsCtx *ctx);            /* K6 alone on the current grid: lambda, neighbour counts, neighbour lists */
+int ps_apply_viscosity(PsCtx *ctx, float dt); /* the post-pass alone (after ps_build_grid + ps_find_neighbors) */
 int ps_set_ghost_count(PsCtx *ctx, uint64_t ghosts);
 uint64_t ps_num_owned(PsCtx *ctx);
 #ifdef __cplusplus

@@ -144,6 +144,14 @@ def lib():
                   "pshost_set_particle_to_add", "pshost_set_fluid_to_add", "pshost_make_point_constraint",
                   "pshost_make_distance_constraint", "pshost_get_positions", "pshost_get_velocities"):
             getattr(L, f).restype = None
+        L.ps_add_rigid_body.argtypes = [vp, vp, u64, f32, C.POINTER(u32)]
+        L.ps_num_rigid_bodies.argtypes = [vp]
+        L.ps_num_rigid_bodies.restype = u64
+        L.ps_solve_shapes.argtypes = [vp]
+        L.ps_rigid_body_rotation.argtypes = [vp, u32, vp]
+        L.ps_set_viscosity.argtypes = [vp, f32, f32]
+        L.ps_find_neighbors.argtypes = [vp]
+        L.ps_apply_viscosity.argtypes = [vp, f32]
         # 2-D double-precision path (include/psolver2d.h)
         L.ps2d_default_params.argtypes = [C.POINTER(Params2D)]
         L.ps2d_default_params.restype = None
@@ -315,6 +323,28 @@ class Solver:
     def solve_distance(self): _check(lib().ps_solve_distance(self._h))
     def solve_point(self): _check(lib().ps_solve_point(self._h))
     def update_velocity(self, dt): _check(lib().ps_update_velocity(self._h, dt))
+
+    # --- not in the reference's GPU solver: 3-D shape matching, XSPH viscosity, vorticity confinement (psolver.h) ---
+    def add_rigid_body(self, indices, stiffness=1.0):
+        idx = _arr(indices, np.uint32).reshape(-1)
+        b = C.c_uint32()
+        _check(lib().ps_add_rigid_body(self._h, _ptr(idx), idx.size, stiffness, C.byref(b)))
+        return int(b.value)
+
+    @property
+    def num_rigid_bodies(self):
+        return int(lib().ps_num_rigid_bodies(self._h))
+
+    def solve_shapes(self): _check(lib().ps_solve_shapes(self._h))
+
+    def rigid_body_rotation(self, body):
+        q = np.zeros(4, np.float32)
+        _check(lib().ps_rigid_body_rotation(self._h, int(body), _ptr(q)))
+        return q
+
+    def set_viscosity(self, xsph_c=0.0, vorticity_eps=0.0): _check(lib().ps_set_viscosity(self._h, xsph_c, vorticity_eps))
+    def find_neighbors(self): _check(lib().ps_find_neighbors(self._h))
+    def apply_viscosity(self, dt): _check(lib().ps_apply_viscosity(self._h, dt))
 
     # --- data ---
     def _count(self, which):

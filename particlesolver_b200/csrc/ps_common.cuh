@@ -122,6 +122,13 @@ void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spo
 u32 ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
                            const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s);  // returns the number of launches
+// K13 (optional, not in the reference): XSPH viscosity + vorticity confinement on the PBF neighbour structure; returns #launches
+u32 ps_launch_viscosity(float4 *vel, float4 *scratch, const float4 *spos, const int *sphase, const u32 *index, const u32 *cell_begin, u32 n, GridDesc g,
+                        const StencilDesc &st, float c_xsph, float vorticity_eps, float dt, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows,
+                        cudaStream_t s);
+// ps_shape_kernels.cu — K12 (not in the reference's GPU solver): shape matching, one warp per rigid body
+void ps_launch_shape_match(float4 *pos, const u32 *body_off, const u32 *body_idx, const float4 *rest, float4 *quat, const float *stiff, u32 num_bodies,
+                           int max_iters, cudaStream_t s);
 // ps_slab_kernels.cu — slab decomposition: ordered selection / packing / compaction
 size_t ps_slab_scratch_elems(u32 n);
 void ps_launch_slab_select(const float4 *pos, u32 n, float left_below, float right_from, u32 *scratch, cudaStream_t s);

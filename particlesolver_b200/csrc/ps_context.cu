@@ -256,6 +256,7 @@ extern "C" int ps_destroy(PsCtx *c) {
                     c->sort_status, c->rands, c->slab_scratch, c->nbr_list, c->nbr_rows, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
                     c->d_point_xyz, c->dist_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
+    ps_ext_free(c);
     if (c->slab_counts_host) cudaFreeHost(c->slab_counts_host);
     if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -440,7 +441,10 @@ u32 ps_issue_build_grid(PsCtx *c, const float4 *pos) {
 static int ready(PsCtx *c) {
     NEED(c);
     if (c->n == 0) return PS_OK;
-    return ps_ctx_sync_constraints(c);
+    int r = ps_ctx_sync_constraints(c);
+    if (r == PS_OK) r = ps_ext_sync_bodies(c);
+    if (r == PS_OK) r = ps_ext_prepare_step(c);
+    return r;
 }
 static int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -547,10 +551,12 @@ static u32 issue_step(PsCtx *c, float dt) {
         ps_launch_collide_world(c->pos, c->prev, c->phase, n_owned, c->rands + 6 * it, c->world, s);
         launches++;
         if (c->num_constrained) { ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained, p.omega, s); launches += 2; }
+        launches += ps_ext_issue_shapes(c);
         if (c->num_points) { ps_launch_point(c->pos, c->d_point_idx, c->d_point_xyz, c->num_points, s); launches++; }
     }
     ps_launch_velocity(c->pos, c->prev, c->vel, n_owned, dt, s);
     launches++;
+    launches += ps_ext_issue_viscosity(c, dt);
     return launches;
 }
 
@@ -567,7 +573,8 @@ extern "C" int ps_step(PsCtx *c, float dt) {
     if (no_graph) {
         c->launches_per_step = issue_step(c, dt);
     } else {
-        PsCtx::GraphKey key{c->n, c->n_ghost, (u32)c->h_dist_rest.size(), c->num_points, c->params.solver_iterations, c->params.flags, dt, c->params.omega};
+        PsCtx::GraphKey key{c->n, c->n_ghost, (u32)c->h_dist_rest.size(), c->num_points, c->params.solver_iterations, c->params.flags, dt, c->params.omega,
+                            c->num_bodies, c->xsph_c, c->vorticity_eps};
         if (!c->graph_exec || !(key == c->graph_key)) {
             if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
             cudaGraph_t graph = nullptr;
@@ -606,7 +613,7 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
     const u32 n = c->n;
     const u32 iters = p.solver_iterations;
     const bool has_contact = !c->census_known || c->n_contact > 0, has_fluid = !c->census_known || c->n_fluid > 0;
-    const int max_marks = 2 + (int)iters * 16;
+    const int max_marks = 4 + (int)iters * 17;
     std::vector<cudaEvent_t> ev(max_marks);
     std::vector<int> tag(max_marks, -1);
     for (auto &e : ev) CU(cudaEventCreate(&e));
@@ -634,9 +641,11 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
         }
         ps_launch_collide_world(c->pos, c->prev, c->phase, n, c->rands + 6 * it, c->world, s); mark(8, 1);
         if (c->num_constrained) { ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained, p.omega, s); mark(9, 2); }
+        if (c->num_bodies) { const u32 l = ps_ext_issue_shapes(c); mark(9, l); }
         if (c->num_points) { ps_launch_point(c->pos, c->d_point_idx, c->d_point_xyz, c->num_points, s); mark(10, 1); }
     }
     ps_launch_velocity(c->pos, c->prev, c->vel, n, dt, s); mark(11, 1);
+    if (c->xsph_c != 0.f || c->vorticity_eps != 0.f) { const u32 l = ps_ext_issue_viscosity(c, dt); mark(11, l); }
     CU(cudaStreamSynchronize(s));
     for (int k = 1; k < m; k++) {
         float ms = 0.f;

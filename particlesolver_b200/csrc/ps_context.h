@@ -61,10 +61,23 @@ struct PsCtx {
     float4 *dist_scratch = nullptr;
     bool dist_prefix_ok = true;  // constrained particles are the index prefix [0,K) (see K9 note)
 
+    // rigid bodies (shape matching, K12): CSR over particle indices, rest offsets (xyz, mass), rotation quaternion per body
+    std::vector<u32> h_body_off{0u}, h_body_idx;
+    std::vector<float> h_body_rest, h_body_stiff;  // 4 per member; 1 per body
+    u32 num_bodies = 0, bodies_uploaded = 0;
+    u32 *body_off = nullptr, *body_idx = nullptr;
+    float4 *body_rest = nullptr, *body_quat = nullptr;
+    float *body_stiff = nullptr;
+    // XSPH viscosity / vorticity confinement (K13): coefficients (0 = off) and scratch (omega | dv, float4[2 * capacity])
+    float xsph_c = 0.f, vorticity_eps = 0.f;
+    float4 *visc_scratch = nullptr;
+    uint64_t visc_scratch_cap = 0;
+
     // CUDA graph of one whole step
     cudaGraphExec_t graph_exec = nullptr;
-    struct GraphKey { u32 n, n_ghost, m, p, iters, flags; float dt, omega; bool operator==(const GraphKey &o) const {
-        return n == o.n && n_ghost == o.n_ghost && m == o.m && p == o.p && iters == o.iters && flags == o.flags && dt == o.dt && omega == o.omega; } } graph_key{};
+    struct GraphKey { u32 n, n_ghost, m, p, iters, flags; float dt, omega; u32 bodies; float xsph, vort; bool operator==(const GraphKey &o) const {
+        return n == o.n && n_ghost == o.n_ghost && m == o.m && p == o.p && iters == o.iters && flags == o.flags && dt == o.dt && omega == o.omega &&
+               bodies == o.bodies && xsph == o.xsph && vort == o.vort; } } graph_key{};
     u32 launches_per_step = 0;
     u32 launch_counter = 0;  // counts launches while a step is being issued
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
@@ -85,6 +98,13 @@ int ps_ctx_sync_constraints(PsCtx *c);
 void ps_ctx_refresh_descs(PsCtx *c);
 void ps_set_error(const char *fmt, ...);
 SortScratch ps_ctx_sort_scratch(PsCtx *c, u32 n);
+
+// ps_extensions.cu: rigid bodies and viscosity (issued from the step when present / enabled); each returns #launches
+int ps_ext_sync_bodies(PsCtx *c);
+int ps_ext_prepare_step(PsCtx *c);
+u32 ps_ext_issue_shapes(PsCtx *c);
+u32 ps_ext_issue_viscosity(PsCtx *c, float dt);
+void ps_ext_free(PsCtx *c);
 
 // stage issue functions on explicit arrays (used by both ABIs); each returns the number of launches issued
 u32 ps_issue_build_grid(PsCtx *c, const float4 *pos);

@@ -1,0 +1,181 @@
+// particlesolver_b200/csrc/ps_extensions.cu — the parts of the unified solver step that north_star names but the
+// reference does not contain, behind the same context API:
+//   rigid bodies with 3-D shape matching (K12, ps_shape_kernels.cu)       ps_add_rigid_body, ps_solve_shapes
+//   XSPH viscosity + vorticity confinement (K13, ps_neighbor_kernels.cu)   ps_set_viscosity, ps_find_neighbors, ps_apply_viscosity
+// Both are off unless asked for (no body added, coefficients 0), so every parity run of the reference's scenes is unaffected.
+// Parity unpinned: the reference has no implementation to compare with; tests check them against float64 restatements.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "ps_context.h"
+
+#define XCU(x)                                                                                       \
+    do {                                                                                             \
+        cudaError_t e_ = (x);                                                                        \
+        if (e_ != cudaSuccess) {                                                                     \
+            ps_set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+            return PS_ERR_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+namespace {
+struct DevGuard {
+    int prev = 0;
+    explicit DevGuard(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+constexpr int kShapeIters = 64;  // rotation-extraction iterations per call at most: convergence is linear (~0.7 per iteration for an
+                                 // anisotropic body), a cold start after a large rotation needs ~45; warm-started calls stop after 1-3
+}  // namespace
+
+void ps_ext_free(PsCtx *c) {
+    void *ptrs[] = {c->body_off, c->body_idx, c->body_rest, c->body_quat, c->body_stiff, c->visc_scratch};
+    for (void *p : ptrs) if (p) cudaFree(p);
+}
+
+// A rigid body over existing particles; its rest shape is their CURRENT configuration (rest offsets from the centre of
+// mass, masses 1 / inverse mass).  Members should share one phase >= PS_PHASE_RIGID so that they do not collide with each
+// other (the contact pass skips equal phases above SOLID, integration_kernel.cuh:336-337).
+extern "C" int ps_add_rigid_body(PsCtx *c, const uint32_t *indices, uint64_t n, float stiffness, uint32_t *body) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    if (!indices || n < 2) { ps_set_error("ps_add_rigid_body: a rigid body needs at least 2 particles"); return PS_ERR_INVALID; }
+    if (!(stiffness > 0.f && stiffness <= 1.f)) { ps_set_error("ps_add_rigid_body: stiffness must be in (0, 1]"); return PS_ERR_INVALID; }
+    if (c->n_ghost) { ps_set_error("ps_add_rigid_body: index-based constraints are not supported on slab contexts"); return PS_ERR_STATE; }
+    for (uint64_t k = 0; k < n; k++)
+        if (indices[k] >= c->n) { ps_set_error("ps_add_rigid_body: particle index %u >= %u particles", indices[k], c->n); return PS_ERR_INVALID; }
+    DevGuard dg(c->device);
+    XCU(cudaStreamSynchronize(c->stream));
+    std::vector<float> pos(4 * n), w(n);
+    for (uint64_t k = 0; k < n; k++) {  // bodies are small; setup path
+        XCU(cudaMemcpy(&pos[4 * k], c->pos + indices[k], sizeof(float4), cudaMemcpyDeviceToHost));
+        XCU(cudaMemcpy(&w[k], c->w + indices[k], sizeof(float), cudaMemcpyDeviceToHost));
+        if (!(w[k] > 0.f)) { ps_set_error("ps_add_rigid_body: particle %u has infinite mass", indices[k]); return PS_ERR_INVALID; }
+    }
+    double cx = 0, cy = 0, cz = 0, mt = 0;
+    for (uint64_t k = 0; k < n; k++) { const double m = 1.0 / w[k]; cx += m * pos[4 * k]; cy += m * pos[4 * k + 1]; cz += m * pos[4 * k + 2]; mt += m; }
+    cx /= mt; cy /= mt; cz /= mt;
+    for (uint64_t k = 0; k < n; k++) {
+        c->h_body_idx.push_back(indices[k]);
+        c->h_body_rest.push_back((float)(pos[4 * k] - cx)); c->h_body_rest.push_back((float)(pos[4 * k + 1] - cy));
+        c->h_body_rest.push_back((float)(pos[4 * k + 2] - cz)); c->h_body_rest.push_back(1.0f / w[k]);
+    }
+    c->h_body_off.push_back((u32)c->h_body_idx.size());
+    c->h_body_stiff.push_back(stiffness);
+    if (body) *body = c->num_bodies;
+    c->num_bodies++;
+    return PS_OK;
+}
+extern "C" uint64_t ps_num_rigid_bodies(PsCtx *c) { return c ? c->num_bodies : 0; }
+
+int ps_ext_sync_bodies(PsCtx *c) {
+    if (c->bodies_uploaded == c->num_bodies) return PS_OK;
+    cudaStream_t s = c->stream;
+    XCU(cudaStreamSynchronize(s));
+    // keep the rotations of the bodies that already existed (warm start), identity for the new ones
+    std::vector<float> quat(4 * (size_t)c->num_bodies, 0.f);
+    for (u32 b = 0; b < c->num_bodies; b++) quat[4 * b + 3] = 1.f;
+    if (c->bodies_uploaded) XCU(cudaMemcpy(quat.data(), c->body_quat, 16 * (size_t)c->bodies_uploaded, cudaMemcpyDeviceToHost));
+    void *old[] = {c->body_off, c->body_idx, c->body_rest, c->body_quat, c->body_stiff};
+    for (void *p : old) if (p) cudaFree(p);
+    c->body_off = c->body_idx = nullptr; c->body_rest = c->body_quat = nullptr; c->body_stiff = nullptr;
+    const size_t m = c->h_body_idx.size();
+    XCU(cudaMalloc((void **)&c->body_off, (c->num_bodies + 1) * sizeof(u32)));
+    XCU(cudaMalloc((void **)&c->body_idx, m * sizeof(u32)));
+    XCU(cudaMalloc((void **)&c->body_rest, m * sizeof(float4)));
+    XCU(cudaMalloc((void **)&c->body_quat, c->num_bodies * sizeof(float4)));
+    XCU(cudaMalloc((void **)&c->body_stiff, c->num_bodies * sizeof(float)));
+    XCU(cudaMemcpy(c->body_off, c->h_body_off.data(), (c->num_bodies + 1) * sizeof(u32), cudaMemcpyHostToDevice));
+    XCU(cudaMemcpy(c->body_idx, c->h_body_idx.data(), m * sizeof(u32), cudaMemcpyHostToDevice));
+    XCU(cudaMemcpy(c->body_rest, c->h_body_rest.data(), m * sizeof(float4), cudaMemcpyHostToDevice));
+    XCU(cudaMemcpy(c->body_quat, quat.data(), c->num_bodies * sizeof(float4), cudaMemcpyHostToDevice));
+    XCU(cudaMemcpy(c->body_stiff, c->h_body_stiff.data(), c->num_bodies * sizeof(float), cudaMemcpyHostToDevice));
+    c->bodies_uploaded = c->num_bodies;
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    return PS_OK;
+}
+
+u32 ps_ext_issue_shapes(PsCtx *c) {
+    if (!c->num_bodies) return 0;
+    ps_launch_shape_match(c->pos, c->body_off, c->body_idx, c->body_rest, c->body_quat, c->body_stiff, c->num_bodies, kShapeIters, c->stream);
+    return 1;
+}
+
+extern "C" int ps_solve_shapes(PsCtx *c) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    DevGuard dg(c->device);
+    int r = ps_ext_sync_bodies(c);
+    if (r != PS_OK) return r;
+    ps_ext_issue_shapes(c);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ps_set_error("ps_solve_shapes: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
+    return PS_OK;
+}
+extern "C" int ps_rigid_body_rotation(PsCtx *c, uint32_t body, float *quat_xyzw) {
+    if (!c || !quat_xyzw || body >= c->num_bodies) { ps_set_error("ps_rigid_body_rotation: bad argument"); return PS_ERR_INVALID; }
+    DevGuard dg(c->device);
+    int r = ps_ext_sync_bodies(c);
+    if (r != PS_OK) return r;
+    XCU(cudaStreamSynchronize(c->stream));
+    XCU(cudaMemcpy(quat_xyzw, c->body_quat + body, sizeof(float4), cudaMemcpyDeviceToHost));
+    return PS_OK;
+}
+
+extern "C" int ps_set_viscosity(PsCtx *c, float xsph_c, float vorticity_eps) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    if (!(xsph_c >= 0.f && xsph_c <= 1.f) || !(vorticity_eps >= 0.f)) { ps_set_error("ps_set_viscosity: xsph_c in [0,1], vorticity_eps >= 0"); return PS_ERR_INVALID; }
+    c->xsph_c = xsph_c;
+    c->vorticity_eps = vorticity_eps;
+    return PS_OK;
+}
+
+static int ensure_visc_scratch(PsCtx *c) {
+    if (c->visc_scratch_cap >= c->capacity && c->visc_scratch) return PS_OK;
+    if (c->visc_scratch) cudaFree(c->visc_scratch);
+    c->visc_scratch = nullptr;
+    XCU(cudaMalloc((void **)&c->visc_scratch, 2 * (size_t)c->capacity * sizeof(float4)));
+    c->visc_scratch_cap = c->capacity;
+    return PS_OK;
+}
+
+u32 ps_ext_issue_viscosity(PsCtx *c, float dt) {
+    if (c->xsph_c == 0.f && c->vorticity_eps == 0.f) return 0;
+    if (!c->n || !c->visc_scratch || !c->grid_valid) return 0;
+    return ps_launch_viscosity(c->vel, c->visc_scratch, c->spos, c->sphase, c->index, c->cell_begin, c->n, c->grid, c->stencil, c->xsph_c, c->vorticity_eps,
+                               dt, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
+}
+
+// K6 alone on the current grid: fills lambda, the neighbour counts and the neighbour lists without moving anything
+extern "C" int ps_find_neighbors(PsCtx *c) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    if (!c->n) return PS_OK;
+    if (!c->grid_valid) { ps_set_error("ps_find_neighbors before ps_build_grid"); return PS_ERR_STATE; }
+    DevGuard dg(c->device);
+    ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost, c->lambda_xmin,
+                           c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list, c->nbr_rows,
+                           c->nbr_max_rows, c->stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ps_set_error("ps_find_neighbors: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
+    return PS_OK;
+}
+
+// velocity post-pass on the neighbour structure of the last grid build + K6 (ps_step runs it after the velocity update when
+// a coefficient is non-zero; standalone: ps_build_grid, ps_find_neighbors, ps_apply_viscosity)
+extern "C" int ps_apply_viscosity(PsCtx *c, float dt) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    if (!c->n) return PS_OK;
+    if (c->n_ghost) { ps_set_error("ps_apply_viscosity: ghost particles carry no velocity (slab contexts)"); return PS_ERR_STATE; }
+    if (!c->grid_valid) { ps_set_error("ps_apply_viscosity before ps_build_grid / ps_find_neighbors"); return PS_ERR_STATE; }
+    DevGuard dg(c->device);
+    int r = ensure_visc_scratch(c);
+    if (r != PS_OK) return r;
+    ps_ext_issue_viscosity(c, dt);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ps_set_error("ps_apply_viscosity: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
+    return PS_OK;
+}
+
+// called by ps_step's ready(): scratch must exist before the step is captured into a graph
+int ps_ext_prepare_step(PsCtx *c) {
+    if (c->xsph_c == 0.f && c->vorticity_eps == 0.f) return PS_OK;
+    return ensure_visc_scratch(c);
+}

@@ -24,7 +24,13 @@ namespace {
 #define PS_FBLOCK 128
 #endif
 #ifndef PS_KQ
-#define PS_KQ 8
+#define PS_KQ 12  // a multiple of 4 (K7 reads the lists four rows at a time)
+#endif
+#ifndef PS_FLUSH_PREFETCH
+#define PS_FLUSH_PREFETCH 0
+#endif
+#ifndef PS_VOTE_PAIR
+#define PS_VOTE_PAIR 1
 #endif
 typedef unsigned long long u64;
 constexpr int kBlock = PS_FBLOCK;  // tuning knobs of the neighbour kernels (build variants: scripts/bench_variants.sh)
@@ -139,6 +145,23 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
                 nl.overflow = true;
             }
         }
+#if PS_FLUSH_PREFETCH
+        // positions are re-read (L1 hits: the lines were gathered a few instructions ago) PS_FLUSH_PREFETCH at a time
+        // before the interactions that use them, so that each lane has that many loads in flight
+#pragma unroll
+        for (int k0 = 0; k0 < kQ; k0 += PS_FLUSH_PREFETCH) {
+            u32 jj[PS_FLUSH_PREFETCH];
+            float4 pp[PS_FLUSH_PREFETCH];
+#pragma unroll
+            for (int k = 0; k < PS_FLUSH_PREFETCH; k++) {
+                jj[k] = (k0 + k < cnt) ? q[k0 + k][tid] : i;
+                pp[k] = __ldg(spos + jj[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < PS_FLUSH_PREFETCH; k++)
+                if (k0 + k < cnt) body(pi.x - pp[k].x, pi.y - pp[k].y, pi.z - pp[k].z, jj[k]);
+        }
+#else
 #pragma unroll
         for (int k = 0; k < kQ; k++)
             if (k < cnt) {
@@ -146,6 +169,7 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
                 const float4 pj = __ldg(spos + j);  // an L1 hit: the line was gathered a few instructions ago
                 body(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z, j);
             }
+#endif
         nn += cnt;  // accepted neighbours are counted when they leave the queue
         cnt = 0;
     };
@@ -238,14 +262,20 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
                     if (t + 2 < total) { j0 = next_j(); p0 = __ldg(spos + j0); } else { j0 = i; }
                     test(j, pj);
                 }
+#if !PS_VOTE_PAIR
                 if (__any_sync(kFull, cnt == kQ)) flush();
+#endif
                 {
                     const u32 j = j1;
                     const float4 pj = p1;
                     if (t + 3 < total) { j1 = next_j(); p1 = __ldg(spos + j1); } else { j1 = i; }
                     test(j, pj);
                 }
+#if PS_VOTE_PAIR
+                if (__any_sync(kFull, cnt >= kQ - 1)) flush();  // one vote per two candidates: room for both of the next pair
+#else
                 if (__any_sync(kFull, cnt == kQ)) flush();
+#endif
             }
         };
         if (capped) walk(cuda::std::true_type{});
@@ -416,6 +446,122 @@ __global__ void __launch_bounds__(kBlock) k_solve_fluids(float4 *__restrict__ po
     pos[orig] = P;
 }
 
+// ------------------------------------------------------------------ K13: XSPH viscosity + vorticity confinement ------------------------------------------------------------------
+// Optional, default off, NOT in the reference (neither exists there): the two velocity post-passes of
+// Macklin & Mueller 2013 ("Position Based Fluids", eqs. 15-17) on the neighbour structure the PBF passes already built.
+//   pass 1  omega_i = sum_j (v_j - v_i) x grad_pj W(p_i - p_j)                       -> omega[i] = (omega, |omega|) by sorted slot
+//   pass 2  dv_i = c sum_j (v_j - v_i) W_poly6(p_i - p_j)  +  dt eps (N x omega_i),   N = eta / |eta|, eta = sum_j |omega_j| grad_pi W
+//   pass 3  v_i += dv_i   (separate, so that pass 2 reads only old velocities)
+// Positions are the sorted copies of the last grid build; W_poly6 / grad W_spiky are the solver's own kernels.  A pass
+// walks K6's neighbour lists; warps whose list overflowed (or everything, when no lists are kept) re-walk the grid.
+struct OmegaOp {
+    const float4 *__restrict__ vel;
+    const u32 *__restrict__ index;
+    float4 *__restrict__ out;  // omega by sorted slot
+    float4 vi;
+    float ox, oy, oz;
+    __device__ __forceinline__ void begin(u32, u32 orig) { vi = vel[orig]; ox = oy = oz = 0.f; }
+    __device__ __forceinline__ void operator()(float rx, float ry, float rz, u32 j) {
+        const float r2 = rx * rx + ry * ry + rz * rz;
+        const float inv_r = rsqrtf(r2), rlen = r2 * inv_r;
+        if (!(rlen >= 0.0001f)) return;
+        const float4 vj = __ldg(vel + __ldg(index + j));
+        const float hm = PS_H - rlen;
+        const float c = (PS_SPIKY * hm * hm) * inv_r;  // grad_pj W(p_i - p_j) = +SPIKY (H - r)^2 r / |r|
+        const float gx = rx * c, gy = ry * c, gz = rz * c;
+        const float dx = vj.x - vi.x, dy = vj.y - vi.y, dz = vj.z - vi.z;
+        ox += dy * gz - dz * gy; oy += dz * gx - dx * gz; oz += dx * gy - dy * gx;
+    }
+    __device__ __forceinline__ void end(u32 i, u32) { out[i] = make_float4(ox, oy, oz, sqrtf(ox * ox + oy * oy + oz * oz)); }
+};
+struct ViscosityOp {
+    const float4 *__restrict__ vel;
+    const u32 *__restrict__ index;
+    const float4 *__restrict__ omega;
+    float4 *__restrict__ out;  // dv by sorted slot
+    float c_xsph, eps_dt;
+    float4 vi;
+    float sx, sy, sz, ex, ey, ez;
+    __device__ __forceinline__ void begin(u32, u32 orig) { vi = vel[orig]; sx = sy = sz = ex = ey = ez = 0.f; }
+    __device__ __forceinline__ void operator()(float rx, float ry, float rz, u32 j) {
+        const float r2 = rx * rx + ry * ry + rz * rz;
+        const float4 vj = __ldg(vel + __ldg(index + j));
+        const float hm2 = PS_H2 - r2;
+        const float W = PS_POLY6 * (hm2 * hm2 * hm2);
+        sx += (vj.x - vi.x) * W; sy += (vj.y - vi.y) * W; sz += (vj.z - vi.z) * W;
+        const float inv_r = rsqrtf(r2), rlen = r2 * inv_r;
+        if (!(rlen >= 0.0001f)) return;
+        const float hm = PS_H - rlen;
+        const float c = __ldg(omega + j).w * ((-PS_SPIKY * hm * hm) * inv_r);  // |omega_j| grad_pi W
+        ex += rx * c; ey += ry * c; ez += rz * c;
+    }
+    __device__ __forceinline__ void end(u32 i, u32) {
+        float dx = c_xsph * sx, dy = c_xsph * sy, dz = c_xsph * sz;
+        const float en = sqrtf(ex * ex + ey * ey + ez * ez);
+        if (en > 1e-6f && eps_dt != 0.f) {
+            const float s = eps_dt / en;
+            const float4 w = omega[i];
+            dx += s * (ey * w.z - ez * w.y); dy += s * (ez * w.x - ex * w.z); dz += s * (ex * w.y - ey * w.x);
+        }
+        out[i] = make_float4(dx, dy, dz, 0.f);
+    }
+};
+
+template <class Op>
+__global__ void __launch_bounds__(kListBlock) k_fluid_pass_list(Op op, const float4 *__restrict__ spos, const int *__restrict__ sphase,
+                                                                const u32 *__restrict__ index, const u32 *__restrict__ nbr_list,
+                                                                const u32 *__restrict__ nbr_rows, u32 max_rows, u32 n) {
+    const u32 i = blockIdx.x * kListBlock + threadIdx.x;
+    if (i >= n) return;
+    const u32 warp = i >> 5;
+    const u32 rows = nbr_rows[warp];
+    if (rows == kListOverflow) return;  // redone by k_fluid_pass_walk
+    if (sphase[i] != PH_FLUID) return;
+    const u32 orig = index[i];
+    const float4 pi = spos[i];
+    op.begin(i, orig);
+    const u32 *L = nbr_list + ((size_t)warp * max_rows) * 32 + (threadIdx.x & 31);
+    for (u32 r = 0; r < rows; r += 4) {
+        u32 j[4];
+        float4 pj[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) j[k] = __ldg(L + (r + k) * 32);
+#pragma unroll
+        for (int k = 0; k < 4; k++) pj[k] = __ldg(spos + (j[k] != kNoNeighbor ? j[k] : i));
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (j[k] != kNoNeighbor) op(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z, j[k]);
+    }
+    op.end(i, orig);
+}
+template <int RAD, class Op>
+__global__ void __launch_bounds__(kBlock) k_fluid_pass_walk(Op op, const float4 *__restrict__ spos, const int *__restrict__ sphase,
+                                                            const u32 *__restrict__ index, const u32 *__restrict__ cell_begin, u32 n, GridDesc g,
+                                                            StencilDesc st, const u32 *__restrict__ nbr_rows) {
+    extern __shared__ u32 fluid_smem[];
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    if (nbr_rows && ((u64)(i >> 5) * 32 >= n || nbr_rows[i >> 5] != kListOverflow)) return;  // warp-uniform
+    const bool act = i < n && sphase[i] == PH_FLUID;
+    if (!__any_sync(kFull, act)) return;
+    const u32 orig = act ? index[i] : 0u;
+    const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
+    if (act) op.begin(i, orig);
+    NeighborListWriter nl;
+    nl.list = nullptr; nl.max_rows = 0; nl.rows = 0; nl.overflow = false;
+    walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, nl, op);
+    if (act) op.end(i, orig);
+}
+__global__ void __launch_bounds__(256) k_apply_dv(float4 *__restrict__ vel, const float4 *__restrict__ dv, const int *__restrict__ sphase,
+                                                  const u32 *__restrict__ index, u32 n) {
+    const u32 i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n || sphase[i] != PH_FLUID) return;
+    const u32 orig = index[i];
+    const float4 d = dv[i];
+    float4 v = vel[orig];
+    v.x += d.x; v.y += d.y; v.z += d.z;
+    vel[orig] = v;
+}
+
 // ------------------------------------------------------------------ K5: contacts + friction ------------------------------------------------------------------
 // 27 cells = 9 rows of 3.  Two sweeps over the same rows: the first only counts (every per-neighbour term is
 // divided by the final neighbour count, and friction is non-linear in it), the second accumulates.
@@ -554,4 +700,41 @@ u32 ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos,
     else
         k_solve_fluids<0><<<cdiv(n, kBlock), kBlock, sm, s>>>(pos, lambda, spos, sphase, index, cell_begin, ros, n, n_owned, g, st, omega, nbr_rows);
     return launches;
+}
+
+template <class Op>
+static u32 launch_fluid_pass(Op op, const float4 *spos, const int *sphase, const u32 *index, const u32 *cell_begin, u32 n, GridDesc g,
+                             const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s) {
+    const size_t sm = fluid_smem_bytes(st.rad);
+    static const cudaError_t optin = cudaFuncSetAttribute(k_fluid_pass_walk<0, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
+    (void)optin;
+    u32 launches = 1;
+    if (nbr_list) {
+        k_fluid_pass_list<Op><<<cdiv(n, kListBlock), kListBlock, 0, s>>>(op, spos, sphase, index, nbr_list, nbr_rows, max_rows, n);
+        launches++;
+    } else {
+        nbr_rows = nullptr;
+    }
+    if (st.rad == 4) k_fluid_pass_walk<4, Op><<<cdiv(n, kBlock), kBlock, sm, s>>>(op, spos, sphase, index, cell_begin, n, g, st, nbr_rows);
+    else k_fluid_pass_walk<0, Op><<<cdiv(n, kBlock), kBlock, sm, s>>>(op, spos, sphase, index, cell_begin, n, g, st, nbr_rows);
+    return launches;
+}
+
+// XSPH viscosity + vorticity confinement (K13): vel += dv, see the kernels.  scratch: float4[2n] (omega | dv by sorted slot).
+u32 ps_launch_viscosity(float4 *vel, float4 *scratch, const float4 *spos, const int *sphase, const u32 *index, const u32 *cell_begin, u32 n, GridDesc g,
+                        const StencilDesc &st, float c_xsph, float vorticity_eps, float dt, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows,
+                        cudaStream_t s) {
+    if (!n) return 0;
+    float4 *omega = scratch, *dv = scratch + n;
+    u32 launches = 0;
+    if (vorticity_eps != 0.f) {
+        OmegaOp o1{vel, index, omega};
+        launches += launch_fluid_pass(o1, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, max_rows, s);
+    } else {
+        cudaMemsetAsync(omega, 0, (size_t)n * sizeof(float4), s);
+    }
+    ViscosityOp o2{vel, index, omega, dv, c_xsph, vorticity_eps * dt};
+    launches += launch_fluid_pass(o2, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, max_rows, s);
+    k_apply_dv<<<cdiv(n, 256), 256, 0, s>>>(vel, dv, sphase, index, n);
+    return launches + 1;
 }
