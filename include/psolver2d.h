@@ -49,8 +49,19 @@ typedef struct Ps2dParams {
 
 typedef struct Ps2dCtx Ps2dCtx;
 
-/* double[2n] x5, double[n] x2, int32[n] x1, uint32[n] x1 */
-enum { PS2D_ARR_P = 0, PS2D_ARR_V = 1, PS2D_ARR_EP = 2, PS2D_ARR_LAMBDA = 3, PS2D_ARR_F = 4, PS2D_ARR_COUNTS = 5, PS2D_ARR_TMASS = 6 };
+/* array selectors of ps2d_download */
+enum {
+    PS2D_ARR_P = 0, PS2D_ARR_V = 1, PS2D_ARR_EP = 2,   /* double[2n]: position, velocity, predicted position */
+    PS2D_ARR_LAMBDA = 3,                               /* double[n]  of the last fluid / gas constraint projected */
+    PS2D_ARR_F = 4,                                    /* double[2n] Particle::f */
+    PS2D_ARR_COUNTS = 5,                               /* uint32[n]  constraints per particle of the last tick */
+    PS2D_ARR_TMASS = 6, PS2D_ARR_IMASS = 7,            /* double[n]  height-scaled / plain inverse mass */
+    PS2D_ARR_SFRICTION = 8, PS2D_ARR_KFRICTION = 9,    /* double[n] */
+    PS2D_ARR_SDF_DIST = 10,                            /* double[n]  SDFData::distance (-1: none) */
+    PS2D_ARR_RS = 11, PS2D_ARR_SDF_GRAD = 12,          /* double[2n] Body::rs, SDFData::gradient */
+    PS2D_ARR_PHASE = 13, PS2D_ARR_BOD = 14,            /* int32[n] */
+    PS2D_ARR_GROUP = 15                                /* int32[n]   STANDARD index of the particle's fluid / gas constraint, -1 none */
+};
 
 void ps2d_default_params(Ps2dParams *p);
 int ps2d_create(int device, const Ps2dParams *params, uint64_t max_particles, Ps2dCtx **out);
@@ -98,6 +109,7 @@ uint32_t ps2d_num_bodies(Ps2dCtx *ctx);
  * (the reference never seeds — seed 1 — and its scene builders consume draws before the first tick) */
 int ps2d_seed_rand(Ps2dCtx *ctx, uint32_t seed, uint64_t skip);
 uint64_t ps2d_rand_calls(Ps2dCtx *ctx);              /* draws consumed so far, including `skip` */
+int ps2d_rand(Ps2dCtx *ctx, int *out);               /* one rand() of that stream (the scene builders' frand() jitter) */
 int ps2d_tick(Ps2dCtx *ctx, double seconds);         /* Simulation::tick(seconds); the reference's app uses .01 (view.cpp:197) */
 uint64_t ps2d_num_particles(Ps2dCtx *ctx);
 uint32_t ps2d_last_num_boundary_constraints(Ps2dCtx *ctx);  /* wall constraints of the last tick that draw jitter (fluid / gas particles) */

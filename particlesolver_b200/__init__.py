@@ -158,6 +158,10 @@ def lib():
         L.ps2d_create.argtypes = [i32, C.POINTER(Params2D), u64, C.POINTER(vp)]
         L.ps2d_destroy.argtypes = [vp]
         L.ps2d_create_fluid.argtypes = [vp, vp, vp, vp, u64, C.c_double]
+        L.ps2d_build_scene.argtypes = [C.c_char_p, i32, u64, C.POINTER(vp)]
+        L.ps2d_scene_name.argtypes = [C.c_char_p]
+        L.ps2d_scene_name.restype = C.c_char_p
+        L.ps2d_rand.argtypes = [vp, C.POINTER(i32)]
         L.ps2d_add_particles.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u64, C.POINTER(u64)]
         L.ps2d_add_distance_constraint.argtypes = [vp, u32, u32, C.c_double]
         L.ps2d_add_fluid_constraint.argtypes = [vp, vp, u64, C.c_double, C.POINTER(u32)]
@@ -605,6 +609,30 @@ class Simulation2D:
     @property
     def num_levels(self):
         return int(lib().ps2d_last_num_levels(self._h))
+
+    def _geti(self, which):
+        a = np.empty(self.getNumParticles(), np.int32)
+        _check(lib().ps2d_download(self._h, which, _ptr(a)))
+        return a
+
+    def inv_mass(self): return self._get(7, 1)
+    def s_friction(self): return self._get(8, 1)
+    def k_friction(self): return self._get(9, 1)
+    def sdf_dist(self): return self._get(10, 1)
+    def rs(self): return self._get(11, 2)
+    def sdf_grad(self): return self._get(12, 2)
+    def phases(self): return self._geti(13)
+    def bods(self): return self._geti(14)
+    def groups(self): return self._geti(15)
+
+    @classmethod
+    def scene(cls, key, max_particles=0, device=0):
+        """Simulation::init(type) for the CPU app's key-bound scenes (include/ps_scenes2d.h), jitter included"""
+        h = C.c_void_p()
+        _check(lib().ps2d_build_scene(str(key).encode(), device, max_particles, C.byref(h)))
+        self = cls.__new__(cls)
+        self._h = h
+        return self
 
     def forces(self): return self._get(4, 2)
     def tmass(self): return self._get(6, 1)

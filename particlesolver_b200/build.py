@@ -14,7 +14,7 @@ OUT = os.path.join(HERE, "libpsolver.so")
 OBJ = os.path.join(HERE, "build")
 CU_SOURCES = ["ps_stream_kernels.cu", "ps_grid_kernels.cu", "ps_sort_kernels.cu", "ps_neighbor_kernels.cu", "ps_slab_kernels.cu", "ps_shape_kernels.cu", "ps_context.cu", "ps_extensions.cu",
               "ps_reference_abi.cu", "ps2d.cu"]
-CPP_SOURCES = ["particle_system.cpp"]
+CPP_SOURCES = ["particle_system.cpp", "scenes2d.cpp"]
 # -use_fast_math mirrors the reference's own build flags (gpu/particles_cuda.pro:153-158): div.approx / sqrt.approx /
 # ftz are parity-relevant, see SURVEY Appendix A.1
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-use_fast_math", "-lineinfo", "-std=c++17", "-Xcompiler",

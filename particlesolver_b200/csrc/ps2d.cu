@@ -968,6 +968,12 @@ extern "C" int ps2d_seed_rand(Ps2dCtx *c, uint32_t seed, uint64_t skip) {
     return PS_OK;
 }
 extern "C" uint64_t ps2d_rand_calls(Ps2dCtx *c) { return c ? c->rng.calls : 0; }
+// one draw of the context's rand() stream (scene builders jitter particles with it, like the reference's frand())
+extern "C" int ps2d_rand(Ps2dCtx *c, int *out) {
+    if (!c || !out) { ps_set_error("ps2d_rand: null argument"); return PS_ERR_INVALID; }
+    *out = c->rng.next();
+    return PS_OK;
+}
 extern "C" uint64_t ps2d_num_particles(Ps2dCtx *c) { return c ? c->n : 0; }
 extern "C" uint32_t ps2d_last_num_boundary_constraints(Ps2dCtx *c) { return c ? c->last_num_boundary : 0; }
 extern "C" uint32_t ps2d_last_num_contact_constraints(Ps2dCtx *c) { return c ? c->last_contacts : 0; }
@@ -1137,6 +1143,15 @@ extern "C" int ps2d_download(Ps2dCtx *c, int which, void *host) {
         case PS2D_ARR_LAMBDA: src = c->lambda; bytes = (size_t)c->n * 8; break;
         case PS2D_ARR_TMASS: src = c->tmass; bytes = (size_t)c->n * 8; break;
         case PS2D_ARR_COUNTS: src = c->counts; bytes = (size_t)c->n * 4; break;
+        case PS2D_ARR_IMASS: src = c->imass; bytes = (size_t)c->n * 8; break;
+        case PS2D_ARR_SFRICTION: src = c->sfric; bytes = (size_t)c->n * 8; break;
+        case PS2D_ARR_KFRICTION: src = c->kfric; bytes = (size_t)c->n * 8; break;
+        case PS2D_ARR_SDF_DIST: src = c->sdf_dist; bytes = (size_t)c->n * 8; break;
+        case PS2D_ARR_RS: src = c->rs; break;
+        case PS2D_ARR_SDF_GRAD: src = c->sdf_grad; break;
+        case PS2D_ARR_PHASE: src = c->phase; bytes = (size_t)c->n * 4; break;
+        case PS2D_ARR_BOD: src = c->bod; bytes = (size_t)c->n * 4; break;
+        case PS2D_ARR_GROUP: src = c->group; bytes = (size_t)c->n * 4; break;
         default: ps_set_error("ps2d_download: unknown array %d", which); return PS_ERR_INVALID;
     }
     CU2(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, c->stream));

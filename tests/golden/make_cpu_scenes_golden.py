@@ -5,7 +5,8 @@ Runs anywhere (no GPU):   python tests/golden/make_cpu_scenes_golden.py
 Per scene NAME: NAME_scene = the full restart state as JSON (particles incl. friction and force accumulators, rigid
 bodies with r vectors / SDF / centre / angle, the STANDARD constraint list in order, smoke emitters, position of the glibc
 rand() stream) taken after tick T0 (0 = the freshly built scene; later for scenes whose rigid contacts start late), and
-NAME_p{t}, NAME_v{t}, NAME_rand{t} for a few ticks t > T0 (particle counts may grow: smoke emitters)."""
+NAME_p{t}, NAME_v{t}, NAME_rand{t} for a few ticks t > T0 (particle counts may grow: smoke emitters); NAME_scene0 = the
+freshly built scene where T0 > 0; NAME_key = the app's key for the scene."""
 import json
 import os
 import subprocess
@@ -54,6 +55,9 @@ def main():
         text = open(os.path.join(raw_dir, f"scene_t{t0:05d}.json" if t0 else "scene.json")).read()
         json.loads(text)
         keep[f"{name}_scene"] = np.array(text)
+        if t0:  # the freshly built scene as well (what the scene builders are compared with)
+            keep[f"{name}_scene0"] = np.array(open(os.path.join(raw_dir, "scene.json")).read())
+        keep[f"{name}_key"] = np.array(key)
         keep[f"{name}_t0"] = np.array(t0)
         keep[f"{name}_ticks"] = np.array(ticks)
         for t in ticks:

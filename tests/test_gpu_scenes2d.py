@@ -1,0 +1,77 @@
+"""The CPU application's scene builders (include/ps_scenes2d.h, csrc/scenes2d.cpp) against the scenes the reference's own
+unmodified Simulation::init* built (tests/golden/ref_cpu_scenes.npz): particle for particle and bit for bit — positions
+(jitter drawn from the same rand() stream in the same order), velocities, masses, friction, phases, rigid bodies (r
+vectors, SDF, centre, inverse mass) — and, ticked from there, the reference's states at the kept ticks."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import particlesolver_b200 as psb
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = np.load(os.path.join(ROOT, "tests", "golden", "ref_cpu_scenes.npz"))
+SCENES = sorted(k[:-6] for k in G.files if k.endswith("_scene"))
+
+
+def scene0(name):
+    return json.loads(str(G[f"{name}_scene0"] if f"{name}_scene0" in G.files else G[f"{name}_scene"]))
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_built_scene_is_the_reference_scene(name):
+    ref = scene0(name)
+    sim = psb.Simulation2D.scene(str(G[f"{name}_key"]))
+    P = np.array(ref["particles"])
+    assert sim.getNumParticles() == P.shape[0]
+    assert np.array_equal(sim.positions(), P[:, 0:2]), np.abs(sim.positions() - P[:, 0:2]).max()
+    assert np.array_equal(sim.velocities(), P[:, 2:4])
+    assert np.array_equal(sim.inv_mass(), P[:, 4])
+    assert np.array_equal(sim.phases(), P[:, 5].astype(np.int32))
+    assert np.array_equal(sim.s_friction(), P[:, 7]) and np.array_equal(sim.k_friction(), P[:, 8])
+    solid = P[:, 5] == 0
+    assert np.array_equal(sim.bods()[solid], P[solid, 6].astype(np.int32))   # fluids carry a random tag nobody reads
+    assert sim.rand_calls == ref["rand_calls"]
+    assert sim.getNumBodies() == len(ref["bodies"])
+    rs, sg, sd = sim.rs(), sim.sdf_grad(), sim.sdf_dist()
+    for b, body in enumerate(ref["bodies"]):
+        idx = np.array(body["particles"])
+        assert np.abs(rs[idx] - np.array(body["rs"])).max() <= 1e-15
+        sdf = np.array(body["sdf"])
+        assert np.array_equal(sg[idx], sdf[:, 0:2]) and np.array_equal(sd[idx], sdf[:, 2])
+        cen, ang = sim.bodyState(b)
+        assert np.abs(cen - np.array(body["center"])).max() <= 1e-15 and ang == body["angle"]
+    groups = sim.groups()
+    for k, c in enumerate(ref["standard"]):
+        if c["type"] in ("fluid", "gas"):
+            assert np.array_equal(np.nonzero(groups == k)[0], np.array(c["ps"]))
+    sim.close()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_built_scene_ticks_like_the_reference(name):
+    sim = psb.Simulation2D.scene(str(G[f"{name}_key"]))
+    t0 = int(G[f"{name}_t0"])
+    ticks = [int(x) for x in G[f"{name}_ticks"]]
+    t = 0
+    for k, target in enumerate(ticks if t0 == 0 else ticks[:3]):
+        while t < target:
+            sim.tick(.01)
+            t += 1
+        p = G[f"{name}_p{t}"]
+        assert sim.getNumParticles() == p.shape[0]
+        dp = np.abs(sim.positions() - p).max()
+        tol = (1e-12 if k < 3 else 1e-9) if t0 == 0 else 1e-8   # t0 > 0: ~100 ticks from the built scene to the first kept state
+        assert dp <= tol, f"{name} tick {t}: |dp| {dp:.3e}"
+        assert sim.rand_calls == int(G[f"{name}_rand{t}"])
+    sim.close()
+
+
+def test_unknown_and_unsupported_scenes():
+    with pytest.raises(psb.PsError, match="unknown scene"):
+        psb.Simulation2D.scene("x")
+    with pytest.raises(psb.PsError, match="FluidEmitter"):
+        psb.Simulation2D.scene("v")
+    assert psb.lib().ps2d_scene_name(b"6") == b"FLUID_TEST"
