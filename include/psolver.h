@@ -177,6 +177,12 @@ int ps_slab_append_migrants(PsCtx *ctx, const void *from_left, uint64_t n_left, 
 /* lambda is computed for owned particles and for ghosts with x in [x_min, x_max] only (default: everywhere) */
 int ps_slab_set_lambda_range(PsCtx *ctx, float x_min, float x_max);
 
+/* ---- checkpoints (the reference has no persistence: scenes exist only as code, particleapp.cpp:141-215) ----
+ * Everything a run needs to continue bit-identically: parameters, particle arrays, constraint lists in insertion order,
+ * rigid bodies, viscosity coefficients, position of the wall-jitter stream. */
+int ps_save(PsCtx *ctx, const char *path);
+int ps_load(const char *path, int device, PsCtx **out);
+
 /* ---- parts of the unified solver that the reference's GPU code does not contain (its rigid_body_functor is an empty
  * stub, solver_kernel.cuh:289-312; XSPH / vorticity exist nowhere in it — SURVEY §0).  Off unless asked for; every
  * parity run of the reference's scenes is unaffected.  Parity unpinned (no reference implementation). ---- */

@@ -116,6 +116,10 @@ uint32_t ps2d_last_num_boundary_constraints(Ps2dCtx *ctx);  /* wall constraints 
 uint32_t ps2d_last_num_contact_constraints(Ps2dCtx *ctx);   /* size of the last tick's CONTACT list: pairs + walls */
 uint32_t ps2d_last_num_levels(Ps2dCtx *ctx);                /* depth of the last tick's CONTACT level schedule */
 int ps2d_download(Ps2dCtx *ctx, int which, void *host);
+/* checkpoints: everything a run needs to continue bit-identically (particles, bodies, the STANDARD list, emitters, the
+ * rand() stream).  The reference has no persistence. */
+int ps2d_save(Ps2dCtx *ctx, const char *path);
+int ps2d_load(const char *path, int device, Ps2dCtx **out);
 int ps2d_kinetic_energy(Ps2dCtx *ctx, double *out);  /* Simulation::getKineticEnergy, simulation.cpp:1293-1303 */
 uint32_t ps2d_launches_per_tick(Ps2dCtx *ctx);
 #ifdef __cplusplus

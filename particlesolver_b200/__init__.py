@@ -158,6 +158,10 @@ def lib():
         L.ps2d_create.argtypes = [i32, C.POINTER(Params2D), u64, C.POINTER(vp)]
         L.ps2d_destroy.argtypes = [vp]
         L.ps2d_create_fluid.argtypes = [vp, vp, vp, vp, u64, C.c_double]
+        L.ps_save.argtypes = [vp, C.c_char_p]
+        L.ps_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
+        L.ps2d_save.argtypes = [vp, C.c_char_p]
+        L.ps2d_load.argtypes = [C.c_char_p, i32, C.POINTER(vp)]
         L.ps2d_build_scene.argtypes = [C.c_char_p, i32, u64, C.POINTER(vp)]
         L.ps2d_scene_name.argtypes = [C.c_char_p]
         L.ps2d_scene_name.restype = C.c_char_p
@@ -327,6 +331,17 @@ class Solver:
     def solve_distance(self): _check(lib().ps_solve_distance(self._h))
     def solve_point(self): _check(lib().ps_solve_point(self._h))
     def update_velocity(self, dt): _check(lib().ps_update_velocity(self._h, dt))
+
+    # --- checkpoints ---
+    def save(self, path): _check(lib().ps_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path, device=0):
+        h = C.c_void_p()
+        _check(lib().ps_load(os.fsencode(path), device, C.byref(h)))
+        self = cls.__new__(cls)
+        self._owned, self._h = True, h
+        return self
 
     # --- not in the reference's GPU solver: 3-D shape matching, XSPH viscosity, vorticity confinement (psolver.h) ---
     def add_rigid_body(self, indices, stiffness=1.0):
@@ -624,6 +639,16 @@ class Simulation2D:
     def phases(self): return self._geti(13)
     def bods(self): return self._geti(14)
     def groups(self): return self._geti(15)
+
+    def save(self, path): _check(lib().ps2d_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path, device=0):
+        h = C.c_void_p()
+        _check(lib().ps2d_load(os.fsencode(path), device, C.byref(h)))
+        self = cls.__new__(cls)
+        self._h = h
+        return self
 
     @classmethod
     def scene(cls, key, max_particles=0, device=0):

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpsolver.so")
 OBJ = os.path.join(HERE, "build")
-CU_SOURCES = ["ps_stream_kernels.cu", "ps_grid_kernels.cu", "ps_sort_kernels.cu", "ps_neighbor_kernels.cu", "ps_slab_kernels.cu", "ps_shape_kernels.cu", "ps_context.cu", "ps_extensions.cu",
+CU_SOURCES = ["ps_stream_kernels.cu", "ps_grid_kernels.cu", "ps_sort_kernels.cu", "ps_neighbor_kernels.cu", "ps_slab_kernels.cu", "ps_shape_kernels.cu", "ps_context.cu", "ps_extensions.cu", "ps_checkpoint.cu",
               "ps_reference_abi.cu", "ps2d.cu"]
 CPP_SOURCES = ["particle_system.cpp", "scenes2d.cpp"]
 # -use_fast_math mirrors the reference's own build flags (gpu/particles_cuda.pro:153-158): div.approx / sqrt.approx /
@@ -78,7 +78,24 @@ def build_all(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+    build_cli(env)
     return OUT
+
+
+def build_cli(env=None):
+    """psolver_cli: the headless runner (csrc/psolver_cli.cpp), linked against the in-tree libpsolver.so"""
+    cli, src = os.path.join(HERE, "psolver_cli"), os.path.join(CSRC, "psolver_cli.cpp")
+    if not _newer(src, cli, [OUT]):
+        return cli
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc))), "include")
+    cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"), "-I", cuda_inc, src, "-o", cli,
+           "-L", HERE, "-l:" + os.path.basename(OUT), "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("psolver_cli link failed")
+    return cli
 
 
 if __name__ == "__main__":

@@ -1170,3 +1170,112 @@ extern "C" int ps2d_kinetic_energy(Ps2dCtx *c, double *out) {
     *out = e;
     return PS_OK;
 }
+
+// ------------------------------------------------------------------ checkpoints ------------------------------------------------------------------
+// The restartable state of a Ps2dCtx: parameters, per-particle arrays, rigid bodies, the STANDARD list in
+// order, emitters and the rand() stream (its 31 state words).  A run continued from a checkpoint is bit-identical to the
+// uninterrupted one (tests/test_gpu_checkpoint.py).  Little-endian, fixed-width fields.
+namespace {
+const char kMagic2d[8] = {'P', 'S', 'B', '2', 'D', 'C', 'K', '1'};
+struct Header2d {
+    char magic[8];
+    uint32_t version, params_bytes;
+    uint64_t n, cap, num_bodies, num_standard, num_emitters, rand_calls;
+};
+struct StdRecord { uint32_t kind, open, i1, i2; double p0, d; };
+struct EmitRecord { double x, y, rate, timer; uint32_t standard_index, pad; };
+template <class T> bool put2(FILE *f, const T *p, size_t n) { return n == 0 || fwrite(p, sizeof(T), n, f) == n; }
+template <class T> bool get2(FILE *f, T *p, size_t n) { return n == 0 || fread(p, sizeof(T), n, f) == n; }
+template <class T> cudaError_t fetch(std::vector<T> &h, const void *d, size_t count) {
+    h.resize(count);
+    return count ? cudaMemcpy(h.data(), d, count * sizeof(T), cudaMemcpyDeviceToHost) : cudaSuccess;
+}
+}  // namespace
+
+extern "C" int ps2d_save(Ps2dCtx *c, const char *path) {
+    if (!c || !path) { ps_set_error("ps2d_save: null argument"); return PS_ERR_INVALID; }
+    CU2(cudaSetDevice(c->device));
+    CU2(cudaStreamSynchronize(c->stream));
+    const size_t n = c->n, nb = c->nbodies;
+    std::vector<double> p, v, f, rs, sg, im, sf, kf, sd, bim, bst, ban, bce;
+    std::vector<int> ph, bod, grp;
+    std::vector<u32> bf, bc;
+    CU2(fetch(p, c->p, 2 * n)); CU2(fetch(v, c->v, 2 * n)); CU2(fetch(f, c->f, 2 * n)); CU2(fetch(rs, c->rs, 2 * n)); CU2(fetch(sg, c->sdf_grad, 2 * n));
+    CU2(fetch(im, c->imass, n)); CU2(fetch(sf, c->sfric, n)); CU2(fetch(kf, c->kfric, n)); CU2(fetch(sd, c->sdf_dist, n));
+    CU2(fetch(ph, c->phase, n)); CU2(fetch(bod, c->bod, n)); CU2(fetch(grp, c->group, n));
+    CU2(fetch(bf, c->b_first, nb)); CU2(fetch(bc, c->b_count, nb)); CU2(fetch(bim, c->b_imass, nb)); CU2(fetch(bst, c->b_stiff, nb));
+    CU2(fetch(ban, c->b_angle, nb)); CU2(fetch(bce, c->b_center, 2 * nb));
+    Header2d h{};
+    memcpy(h.magic, kMagic2d, 8);
+    h.version = 1; h.params_bytes = (uint32_t)sizeof(Ps2dParams);
+    h.n = n; h.cap = c->cap; h.num_bodies = nb; h.num_standard = c->standard.size(); h.num_emitters = c->emitters.size(); h.rand_calls = c->rng.calls;
+    std::vector<StdRecord> st;
+    for (const StdOp &o : c->standard) st.push_back(StdRecord{(uint32_t)o.kind, (uint32_t)o.open, o.i1, o.i2, o.p0, o.d});
+    std::vector<EmitRecord> em;
+    for (const Emitter &e : c->emitters) em.push_back(EmitRecord{e.x, e.y, e.rate, e.timer, e.standard_index, 0});
+    FILE *fp = fopen(path, "wb");
+    if (!fp) { ps_set_error("ps2d_save: cannot open %s for writing", path); return PS_ERR_INVALID; }
+    bool ok = put2(fp, &h, 1) && put2(fp, &c->params, 1) && put2(fp, c->rng.r.data(), 31) && put2(fp, p.data(), p.size()) && put2(fp, v.data(), v.size()) &&
+              put2(fp, f.data(), f.size()) && put2(fp, rs.data(), rs.size()) && put2(fp, sg.data(), sg.size()) && put2(fp, im.data(), n) && put2(fp, sf.data(), n) &&
+              put2(fp, kf.data(), n) && put2(fp, sd.data(), n) && put2(fp, ph.data(), n) && put2(fp, bod.data(), n) && put2(fp, grp.data(), n) &&
+              put2(fp, c->h_static_counts.data(), n) && put2(fp, bf.data(), nb) && put2(fp, bc.data(), nb) && put2(fp, bim.data(), nb) && put2(fp, bst.data(), nb) &&
+              put2(fp, ban.data(), nb) && put2(fp, bce.data(), 2 * nb) && put2(fp, st.data(), st.size()) && put2(fp, em.data(), em.size());
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok) { ps_set_error("ps2d_save: short write to %s", path); return PS_ERR_INVALID; }
+    return PS_OK;
+}
+
+extern "C" int ps2d_load(const char *path, int device, Ps2dCtx **out) {
+    if (!path || !out) { ps_set_error("ps2d_load: null argument"); return PS_ERR_INVALID; }
+    *out = nullptr;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) { ps_set_error("ps2d_load: cannot open %s", path); return PS_ERR_INVALID; }
+    struct Closer { FILE *f; ~Closer() { fclose(f); } } closer{fp};
+    Header2d h{};
+    if (!get2(fp, &h, 1) || memcmp(h.magic, kMagic2d, 8) != 0) { ps_set_error("ps2d_load: %s is not a 2-D libpsolver checkpoint", path); return PS_ERR_INVALID; }
+    if (h.version != 1 || h.params_bytes != sizeof(Ps2dParams)) { ps_set_error("ps2d_load: checkpoint version %u not understood", h.version); return PS_ERR_INVALID; }
+    if (h.n > h.cap || h.cap > (1u << 28) || h.num_bodies > h.n || h.num_standard > (1u << 28) || h.num_emitters > 4096) { ps_set_error("ps2d_load: implausible sizes in %s", path); return PS_ERR_INVALID; }
+    Ps2dParams P;
+    uint32_t rng[31];
+    const size_t n = h.n, nb = h.num_bodies;
+    std::vector<double> p(2 * n), v(2 * n), f(2 * n), rs(2 * n), sg(2 * n), im(n), sf(n), kf(n), sd(n), bim(nb), bst(nb), ban(nb), bce(2 * nb);
+    std::vector<int> ph(n), bod(n), grp(n);
+    std::vector<u32> sc(n), bf(nb), bc(nb);
+    std::vector<StdRecord> st(h.num_standard);
+    std::vector<EmitRecord> em(h.num_emitters);
+    bool ok = get2(fp, &P, 1) && get2(fp, rng, 31) && get2(fp, p.data(), p.size()) && get2(fp, v.data(), v.size()) && get2(fp, f.data(), f.size()) &&
+              get2(fp, rs.data(), rs.size()) && get2(fp, sg.data(), sg.size()) && get2(fp, im.data(), n) && get2(fp, sf.data(), n) && get2(fp, kf.data(), n) &&
+              get2(fp, sd.data(), n) && get2(fp, ph.data(), n) && get2(fp, bod.data(), n) && get2(fp, grp.data(), n) && get2(fp, sc.data(), n) &&
+              get2(fp, bf.data(), nb) && get2(fp, bc.data(), nb) && get2(fp, bim.data(), nb) && get2(fp, bst.data(), nb) && get2(fp, ban.data(), nb) &&
+              get2(fp, bce.data(), 2 * nb) && get2(fp, st.data(), st.size()) && get2(fp, em.data(), em.size());
+    if (!ok) { ps_set_error("ps2d_load: truncated file %s", path); return PS_ERR_INVALID; }
+    for (size_t b = 0; b < nb; b++) if ((uint64_t)bf[b] + bc[b] > n) { ps_set_error("ps2d_load: body out of range"); return PS_ERR_INVALID; }
+    for (const StdRecord &o : st) if (o.kind > STD_DISTANCE || (o.kind == STD_DISTANCE && (o.i1 >= n || o.i2 >= n))) { ps_set_error("ps2d_load: bad STANDARD record"); return PS_ERR_INVALID; }
+    Ps2dCtx *c = nullptr;
+    int r = ps2d_create(device, &P, h.cap, &c);
+    if (r != PS_OK) return r;
+    auto fail = [&](int code) { ps2d_destroy(c); return code; };
+    if (n && (r = ps2d_add_particles(c, p.data(), v.data(), im.data(), ph.data(), bod.data(), sf.data(), kf.data(), n, nullptr)) != PS_OK) return fail(r);
+    bool up = upload(c, (double *)c->f, f.data(), 2 * n) == cudaSuccess && upload(c, (double *)c->rs, rs.data(), 2 * n) == cudaSuccess &&
+              upload(c, (double *)c->sdf_grad, sg.data(), 2 * n) == cudaSuccess && upload(c, c->sdf_dist, sd.data(), n) == cudaSuccess &&
+              upload(c, c->group, grp.data(), n) == cudaSuccess && upload(c, c->static_counts, sc.data(), n) == cudaSuccess;
+    c->h_static_counts = sc;
+    for (size_t b = 0; b < nb && up; b++) {
+        if (grow_bodies(c) != PS_OK) return fail(PS_ERR_CUDA);
+        up = upload(c, c->b_first + b, &bf[b], 1) == cudaSuccess && upload(c, c->b_count + b, &bc[b], 1) == cudaSuccess && upload(c, c->b_imass + b, &bim[b], 1) == cudaSuccess &&
+             upload(c, c->b_stiff + b, &bst[b], 1) == cudaSuccess && upload(c, c->b_angle + b, &ban[b], 1) == cudaSuccess && upload(c, (double *)(c->b_center + b), &bce[2 * b], 2) == cudaSuccess;
+        c->nbodies++;
+    }
+    if (!up) { ps_set_error("ps2d_load: upload failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(PS_ERR_CUDA); }
+    for (const StdRecord &o : st) {
+        StdOp op;
+        op.kind = (StdKind)o.kind; op.open = (int)o.open; op.i1 = o.i1; op.i2 = o.i2; op.p0 = o.p0; op.d = o.d;
+        c->standard.push_back(op);
+    }
+    c->standard_dirty = true;
+    for (const EmitRecord &e : em) c->emitters.push_back(Emitter{e.x, e.y, e.rate, e.timer, e.standard_index});
+    c->rng.r.assign(rng, rng + 31);
+    c->rng.calls = h.rand_calls;
+    *out = c;
+    return PS_OK;
+}

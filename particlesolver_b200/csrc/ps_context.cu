@@ -458,6 +458,7 @@ extern "C" int ps_begin_step(PsCtx *c) {
     const u32 iters = c->params.solver_iterations;
     // one curandGenerateUniform(gen, rands, 6) per solver iteration, exactly like collideWorld (integration.cu:326)
     for (u32 it = 0; it < iters; it++) CR(curandGenerateUniform(c->gen, c->rands + 6 * it, 6));
+    c->rand_calls += iters;
     return PS_OK;
 }
 

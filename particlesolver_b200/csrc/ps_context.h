@@ -47,6 +47,7 @@ struct PsCtx {
     float *rands = nullptr;
     u32 rands_iters = 0;
     curandGenerator_t gen = nullptr;
+    uint64_t rand_calls = 0;  // curandGenerateUniform(gen, ., 6) calls so far (a checkpoint replays them to reposition the stream)
 
     // constraints: host mirror + device arrays
     std::vector<u32> h_dist_idx;    // 2 per constraint

@@ -149,6 +149,7 @@ void collideWorld(float *pos, float *sortedPos, uint n, PsRefInt3 minB, PsRefInt
     (void)sortedPos;
     PsCtx *c = ctx();
     if (curandGenerateUniform(c->gen, c->rands, 6) != CURAND_STATUS_SUCCESS) { ps_set_error("curandGenerateUniform failed"); die("collideWorld"); }
+    c->rand_calls++;
     WorldDesc w;
     w.radius = c->params.particle_radius;
     w.min_x = minB.x; w.min_y = minB.y; w.min_z = minB.z;

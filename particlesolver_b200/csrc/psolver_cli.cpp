@@ -1,0 +1,162 @@
+// particlesolver_b200/csrc/psolver_cli.cpp — headless runner for both of the reference's applications.
+// The reference's only front ends are two Qt viewers whose scenes are bound to keys (gpu/src/particleapp.cpp:141-215,
+// cpu/src/view.cpp:129-177); this runs the same scenes without a display, over libpsolver.so's public C / C++ API only:
+//   psolver_cli --app gpu --scene 7 --steps 600 [--dt 0.016667] [--grid 64] [--max-particles 15000] [--side 100]
+//               [--iterations 5] [--xsph 0.01 --vorticity 0.3]
+//   psolver_cli --app cpu --scene 6 --steps 1000 [--dt 0.01]
+// common: [--load FILE] [--save FILE] [--dump-every K --out DIR] [--json] [--device D]
+// --load continues a checkpoint written by --save (ps_save / ps2d_save) instead of building a scene; --dump-every
+// writes raw little-endian positions (header: "PSDUMP1\0", uint32 dims per particle, uint32 bytes per scalar, uint64 n).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+#include "../../include/particle_system.h"
+#include "../../include/ps_scenes.h"
+#include "../../include/ps_scenes2d.h"
+#include "../../include/psolver.h"
+
+namespace {
+struct Args {
+    std::string app = "gpu", scene = "7", load, save, out = "psolver_out";
+    int steps = 100, grid = 64, side = 100, iterations = 5, dump_every = 0, device = 0;
+    unsigned max_particles = 15000;
+    double dt = -1;
+    float xsph = 0.f, vorticity = 0.f;
+    bool json = false;
+};
+[[noreturn]] void die(const std::string &m) { fprintf(stderr, "psolver_cli: %s\n", m.c_str()); exit(1); }
+void check(int r, const char *what) { if (r != PS_OK) die(std::string(what) + ": " + ps_last_error()); }
+
+void dump(const std::string &dir, int step, const void *data, uint32_t dims, uint32_t scalar_bytes, uint64_t n) {
+    mkdir(dir.c_str(), 0755);
+    char name[512];
+    snprintf(name, sizeof name, "%s/step%06d.bin", dir.c_str(), step);
+    FILE *f = fopen(name, "wb");
+    if (!f) die(std::string("cannot write ") + name);
+    const char magic[8] = {'P', 'S', 'D', 'U', 'M', 'P', '1', 0};
+    fwrite(magic, 1, 8, f); fwrite(&dims, 4, 1, f); fwrite(&scalar_bytes, 4, 1, f); fwrite(&n, 8, 1, f);
+    fwrite(data, (size_t)dims * scalar_bytes, n, f);
+    fclose(f);
+}
+
+int run_gpu(const Args &a) {
+    psb200::ParticleSystem *ps = nullptr;
+    PsCtx *ctx = nullptr;
+    if (!a.load.empty()) {
+        check(ps_load(a.load.c_str(), a.device, &ctx), "ps_load");
+    } else {
+        ps_scenes::SceneSpec s;
+        s.scene = a.scene; s.grid = a.grid; s.max_particles = a.max_particles; s.iterations = a.iterations; s.side = a.side;
+        ps = ps_scenes::build<psb200::ParticleSystem>(s, psb200::colors, psb200::numColors);
+        if (!ps) die("unknown GPU scene '" + a.scene + "' (1-9, c2, c3)");
+        if (!ps->lastError().empty()) die(ps->lastError());
+        ctx = ps->context();
+    }
+    if (a.xsph != 0.f || a.vorticity != 0.f) check(ps_set_viscosity(ctx, a.xsph, a.vorticity), "ps_set_viscosity");
+    const float dt = a.dt > 0 ? (float)a.dt : 1.f / 60.f;
+    const uint64_t n = ps_num_particles(ctx);
+    std::vector<float> pos(4 * n), vel(4 * n), w(n);
+    double dev_ms = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int s = 1; s <= a.steps; s++) {
+        if (ps) ps->update(dt); else check(ps_step(ctx, dt), "ps_step");
+        float ms = 0;
+        check(ps_last_step_ms(ctx, &ms), "ps_last_step_ms");
+        dev_ms += ms;
+        if (a.dump_every > 0 && s % a.dump_every == 0) {
+            check(ps_download(ctx, PS_ARR_POS, pos.data(), 0, 4 * n), "ps_download");
+            dump(a.out, s, pos.data(), 4, 4, n);
+        }
+    }
+    check(ps_sync(ctx), "ps_sync");
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    check(ps_download(ctx, PS_ARR_POS, pos.data(), 0, 4 * n), "ps_download");
+    check(ps_download(ctx, PS_ARR_VEL, vel.data(), 0, 4 * n), "ps_download");
+    check(ps_download(ctx, PS_ARR_INV_MASS, w.data(), 0, n), "ps_download");
+    double ke = 0, sum = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (w[i] > 0) ke += .5 * (vel[4 * i] * (double)vel[4 * i] + vel[4 * i + 1] * (double)vel[4 * i + 1] + vel[4 * i + 2] * (double)vel[4 * i + 2]) / w[i];
+        sum += pos[4 * i] + 2.0 * pos[4 * i + 1] + 3.0 * pos[4 * i + 2];
+    }
+    if (!a.save.empty()) check(ps_save(ctx, a.save.c_str()), "ps_save");
+    if (a.json)
+        printf("{\"app\": \"gpu\", \"scene\": \"%s\", \"particles\": %llu, \"steps\": %d, \"dt\": %.9g, \"device_ms_per_step\": %.4f, \"wall_ms_per_step\": %.4f, "
+               "\"particle_steps_per_s\": %.1f, \"kinetic_energy\": %.9g, \"position_checksum\": %.9g, \"launches_per_step\": %u}\n",
+               a.scene.c_str(), (unsigned long long)n, a.steps, dt, a.steps ? dev_ms / a.steps : 0., a.steps ? 1e3 * wall / a.steps : 0.,
+               dev_ms > 0 ? n * (double)a.steps / (dev_ms * 1e-3) : 0., ke, sum, ps_launches_per_step(ctx));
+    else
+        printf("gpu scene %s: %llu particles, %d steps, %.3f ms/step on the device (%.3f wall), KE %.6g\n", a.scene.c_str(), (unsigned long long)n, a.steps,
+               a.steps ? dev_ms / a.steps : 0., a.steps ? 1e3 * wall / a.steps : 0., ke);
+    if (ps) delete ps; else ps_destroy(ctx);
+    return 0;
+}
+
+int run_cpu_app(const Args &a) {
+    Ps2dCtx *ctx = nullptr;
+    if (!a.load.empty()) check(ps2d_load(a.load.c_str(), a.device, &ctx), "ps2d_load");
+    else check(ps2d_build_scene(a.scene.c_str(), a.device, 0, &ctx), "ps2d_build_scene");
+    const double dt = a.dt > 0 ? a.dt : .01;  // cpu/src/view.cpp:197
+    std::vector<double> p;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int s = 1; s <= a.steps; s++) {
+        check(ps2d_tick(ctx, dt), "ps2d_tick");
+        if (a.dump_every > 0 && s % a.dump_every == 0) {
+            const uint64_t n = ps2d_num_particles(ctx);
+            p.resize(2 * n);
+            check(ps2d_download(ctx, PS2D_ARR_P, p.data()), "ps2d_download");
+            dump(a.out, s, p.data(), 2, 8, n);
+        }
+    }
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const uint64_t n = ps2d_num_particles(ctx);
+    double ke = 0;
+    check(ps2d_kinetic_energy(ctx, &ke), "ps2d_kinetic_energy");
+    if (!a.save.empty()) check(ps2d_save(ctx, a.save.c_str()), "ps2d_save");
+    const char *name = ps2d_scene_name(a.scene.c_str());
+    if (a.json)
+        printf("{\"app\": \"cpu\", \"scene\": \"%s\", \"scene_name\": \"%s\", \"particles\": %llu, \"ticks\": %d, \"dt\": %.9g, \"wall_ms_per_tick\": %.4f, "
+               "\"particle_steps_per_s\": %.1f, \"kinetic_energy\": %.17g, \"rand_calls\": %llu, \"launches_per_tick\": %u}\n",
+               a.scene.c_str(), name ? name : "", (unsigned long long)n, a.steps, dt, a.steps ? 1e3 * wall / a.steps : 0., wall > 0 ? n * (double)a.steps / wall : 0., ke,
+               (unsigned long long)ps2d_rand_calls(ctx), ps2d_launches_per_tick(ctx));
+    else
+        printf("cpu-app scene %s (%s): %llu particles, %d ticks, %.3f ms/tick, KE %.17g\n", a.scene.c_str(), name ? name : "checkpoint", (unsigned long long)n, a.steps,
+               a.steps ? 1e3 * wall / a.steps : 0., ke);
+    ps2d_destroy(ctx);
+    return 0;
+}
+}  // namespace
+
+int main(int argc, char **argv) {
+    Args a;
+    for (int i = 1; i < argc; i++) {
+        const std::string k = argv[i];
+        auto val = [&]() -> const char * { if (i + 1 >= argc) die("missing value after " + k); return argv[++i]; };
+        if (k == "--app") a.app = val();
+        else if (k == "--scene") a.scene = val();
+        else if (k == "--steps" || k == "--ticks") a.steps = atoi(val());
+        else if (k == "--dt") a.dt = atof(val());
+        else if (k == "--grid") a.grid = atoi(val());
+        else if (k == "--side") a.side = atoi(val());
+        else if (k == "--iterations") a.iterations = atoi(val());
+        else if (k == "--max-particles") a.max_particles = (unsigned)strtoul(val(), nullptr, 10);
+        else if (k == "--load") a.load = val();
+        else if (k == "--save") a.save = val();
+        else if (k == "--dump-every") a.dump_every = atoi(val());
+        else if (k == "--out") a.out = val();
+        else if (k == "--xsph") a.xsph = (float)atof(val());
+        else if (k == "--vorticity") a.vorticity = (float)atof(val());
+        else if (k == "--device") a.device = atoi(val());
+        else if (k == "--json") a.json = true;
+        else if (k == "--help" || k == "-h") { printf("see the header of particlesolver_b200/csrc/psolver_cli.cpp\n"); return 0; }
+        else die("unknown option " + k);
+    }
+    if (a.steps < 0 || a.grid <= 0 || (a.grid & (a.grid - 1))) die("--steps >= 0, --grid a power of two");
+    if (a.app == "gpu") return run_gpu(a);
+    if (a.app == "cpu") return run_cpu_app(a);
+    die("--app gpu | cpu");
+}

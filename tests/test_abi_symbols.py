@@ -6,6 +6,8 @@ import re
 
 import pytest
 
+from conftest import HAS_GPU
+
 import particlesolver_b200 as psb
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -98,3 +100,31 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_py" not in src and "libpsoracle" not in src and "gpu_step_oracle" not in src and "cpu2d_oracle" not in src, f
+
+
+def test_ps_scenes2d_h_symbols_exported():
+    names = _declared("ps_scenes2d.h", r"\b(ps2d_[a-z_0-9]+)\s*\(")
+    assert {"ps2d_build_scene", "ps2d_scene_name"} <= set(names)
+    missing = [n for n in names if not hasattr(psb.lib(), n)]
+    assert not missing, f"declared in include/ps_scenes2d.h but not exported: {missing}"
+
+
+def test_checkpoint_loaders_reject_foreign_files_before_touching_the_gpu(tmp_path):
+    import ctypes as C
+    bad = tmp_path / "not_a_checkpoint.bin"
+    bad.write_bytes(b"hello world, definitely not a checkpoint" * 4)
+    h = C.c_void_p()
+    assert psb.lib().ps_load(str(bad).encode(), 0, C.byref(h)) == psb.PS_ERR_INVALID and not h.value
+    assert b"not a libpsolver checkpoint" in psb.lib().ps_last_error()
+    assert psb.lib().ps2d_load(str(bad).encode(), 0, C.byref(h)) == psb.PS_ERR_INVALID and not h.value
+    assert psb.lib().ps_load(str(tmp_path / "missing").encode(), 0, C.byref(h)) == psb.PS_ERR_INVALID
+
+
+def test_headless_cli_is_built_and_fails_loudly_without_a_gpu():
+    import subprocess
+    cli = os.path.join(ROOT, "particlesolver_b200", "psolver_cli")
+    assert os.path.exists(cli), "python -m particlesolver_b200.build builds it next to libpsolver.so"
+    assert subprocess.run([cli, "--help"], capture_output=True).returncode == 0
+    if not HAS_GPU:
+        r = subprocess.run([cli, "--app", "cpu", "--scene", "6", "--ticks", "1"], capture_output=True, text=True)
+        assert r.returncode == 1 and "ps2d_build_scene" in r.stderr   # no CPU fallback
