@@ -147,6 +147,26 @@ def time_reference_cpu_solver():
     return None
 
 
+def time_c1_gpu(ticks=200):
+    """Config C1 beside the headline: the CPU app's scene 6 (two-fluid Rayleigh-Taylor, 432 particles, double precision)
+    on the 2-D GPU path, ticks timed end to end by the host clock (a tick has one host round trip: the jitter count)."""
+    try:
+        import particlesolver_b200 as psb
+        sim = psb.Simulation2D.scene("6")
+        for _ in range(20):
+            sim.tick(.01)
+        t0 = time.perf_counter()
+        for _ in range(ticks):
+            sim.tick(.01)
+        sec = time.perf_counter() - t0
+        n, launches = sim.getNumParticles(), sim.launches_per_tick
+        sim.close()
+        return {"scene": "6 (FLUID_TEST)", "n": n, "ticks": ticks, "ms_per_tick": round(1e3 * sec / ticks, 4), "particle_steps_per_s": round(n * ticks / sec, 1),
+                "launches_per_tick": launches, "dtype": "f64"}
+    except Exception as e:  # the headline must not die on the side measurement
+        return {"error": str(e)}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -335,8 +355,12 @@ def run_ours(args, rank, world, local_rank):
                 "cpu_baseline": {"value": cpu_v, "unit": "particle-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
                                  "sample": f"oracle port (OpenMP) on a 46^3 = {cpu_n} particle block of the same lattice, 1 step"},
                 "clocks": clocks}
+        ps.close()
+        ps = None
+        line["c1_2d_path"] = time_c1_gpu()
         print(json.dumps(line), flush=True)
-    ps.close()
+    if ps is not None:
+        ps.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -12,8 +12,7 @@
 // contact partners in ascending index followed by its walls, so the levels are the least fixpoint of a local rule and are
 // found by parallel relaxation (k2d_contact_levels).  Distance constraints are static: their schedule is built once on
 // the host when the list changes.  Fluid / gas constraints are Jacobi inside and run as whole kernels at their place in
-// the STANDARD list; sums over neighbours run sequentially in ascending particle index, like the reference's O(N^2)
-// loops (totalfluidconstraint.cpp:52-76), with the other particles staged through shared memory in tiles.
+// the STANDARD list; their all-pairs neighbour loops (totalfluidconstraint.cpp:52-76) run one warp per particle.
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cmath>
@@ -446,49 +445,52 @@ __global__ void __launch_bounds__(kBlock) k2d_shape(double2 *__restrict__ ep, co
 // TotalFluidConstraint / GasConstraint::project, first loop (totalfluidconstraint.cpp:45-93, gasconstraint.cpp:33-85): lambda
 // of every particle of STANDARD constraint `op`, 0 for everybody else (the constraint's lambdas is a QHash cleared per
 // call: any other particle reads 0, :106).  SOLID neighbours count S_SOLID-fold, immovable ones not at all.
+// One WARP per particle: lane l takes the candidates j = l, l + 32, ... of the reference's all-pairs loop and the partial
+// sums meet in a butterfly of xor-shuffles (deterministic; the summation order differs from the reference's sequential
+// one, i.e. the result agrees to rounding, ~1e-16 relative, instead of bit for bit — measured in tests/test_gpu_2d_full.py).
+// The serial form of this loop (one thread per particle) cost 115 + 177 us per constraint at N = 432: 96 % of a tick.
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ phase,
                                                            const int *__restrict__ group, u32 n, int op, double p0, FluidConsts K, double *__restrict__ lambda,
                                                            u32 *__restrict__ nbcount, const double2 *__restrict__ v, double2 *__restrict__ f) {
-    __shared__ double2 s_ep[kTile];
-    __shared__ double s_im[kTile];
-    __shared__ int s_ph[kTile];
-    const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    const bool mine = i < n && group[i] == op;
-    const double2 pi = i < n ? ep[i] : make_double2(0., 0.);
+    const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    if (i >= n) return;  // warp-uniform
+    if (group[i] != op) { if (lane == 0) lambda[i] = 0.; return; }
+    const double2 pi = ep[i];
     double rho = 0., denom = 0., ox = 0., oy = 0.;
     u32 nbc = 0;
-    for (u32 base = 0; base < n; base += kTile) {
-        __syncthreads();
-        if (base + threadIdx.x < n) { s_ep[threadIdx.x] = ep[base + threadIdx.x]; s_im[threadIdx.x] = imass[base + threadIdx.x]; s_ph[threadIdx.x] = phase[base + threadIdx.x]; }
-        __syncthreads();
-        if (!mine) continue;
-        const u32 m = min((u32)kTile, n - base);
-        for (u32 t = 0; t < m; t++) {
-            const u32 j = base + t;
-            if (j == i) {  // the particle itself, at its place in the index order (:78-81)
-                nbc++;
-                rho += poly6(0.) / s_im[t];
-                continue;
-            }
-            if (s_im[t] == 0.) continue;  // fixed particles are ignored
-            const double rx = pi.x - s_ep[t].x, ry = pi.y - s_ep[t].y;
-            const double r2 = rx * rx + ry * ry;
-            if (r2 < kH2) {
-                nbc++;
-                double incr = poly6(r2) / s_im[t];
-                const bool solid = s_ph[t] == PS2D_PHASE_SOLID;
-                if (solid) incr *= K.s_solid;
-                rho += incr;
-                const double2 sg = spiky_grad(rx, ry, sqrt(r2));
-                const double gx = -sg.x / p0, gy = -sg.y / p0;  // grad(k, j) = -spikyGrad / p0 (:137-144)
-                denom += gx * gx + gy * gy;
-                const double w = solid ? K.s_solid : 1.;       // grad(k, i) = sum_j w_j spikyGrad / p0 (:146-157)
-                ox += w * sg.x; oy += w * sg.y;
-            }
+    for (u32 j = lane; j < n; j += 32) {
+        const double im = imass[j];
+        if (j == i) {  // the particle itself (:78-81)
+            nbc++;
+            rho += poly6(0.) / im;
+            continue;
+        }
+        if (im == 0.) continue;  // fixed particles are ignored
+        const double2 pj = ep[j];
+        const double rx = pi.x - pj.x, ry = pi.y - pj.y;
+        const double r2 = rx * rx + ry * ry;
+        if (r2 < kH2) {
+            nbc++;
+            double incr = poly6(r2) / im;
+            const bool solid = phase[j] == PS2D_PHASE_SOLID;
+            if (solid) incr *= K.s_solid;
+            rho += incr;
+            const double2 sg = spiky_grad(rx, ry, sqrt(r2));
+            const double gx = -sg.x / p0, gy = -sg.y / p0;  // grad(k, j) = -spikyGrad / p0 (:137-144)
+            denom += gx * gx + gy * gy;
+            const double w = solid ? K.s_solid : 1.;       // grad(k, i) = sum_j w_j spikyGrad / p0 (:146-157)
+            ox += w * sg.x; oy += w * sg.y;
         }
     }
-    if (i >= n) return;
-    if (!mine) { lambda[i] = 0.; return; }
+    rho = warp_sum_d(rho); denom = warp_sum_d(denom); ox = warp_sum_d(ox); oy = warp_sum_d(oy);
+    nbc = __reduce_add_sync(0xffffffffu, nbc);
+    if (lane != 0) return;
     ox = ox / p0; oy = oy / p0;
     denom += ox * ox + oy * oy;
     const double p_rat = rho / p0;
@@ -505,51 +507,44 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__rest
 
 // second loop (:95-111): delta_i = sum_j (lambda_i + lambda_j + s_corr) spikyGrad / p0, divided by (#neighbours incl. self +
 // constraint count) (:113-115).  Written to `delta`, applied by k2d_fluid_apply: all deltas of a constraint come from the
-// same ep.  Gas: the pseudo-vorticity force of gasconstraint.cpp:99-107 goes to the force accumulator.
+// same ep.  Gas: the pseudo-vorticity force of gasconstraint.cpp:99-107 goes to the force accumulator.  One warp per particle.
 __global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ group, u32 n,
                                                           int op, double p0, FluidConsts K, const double *__restrict__ lambda, const u32 *__restrict__ nbcount,
                                                           const u32 *__restrict__ counts, double2 *__restrict__ delta, const double2 *__restrict__ v,
                                                           double2 *__restrict__ f) {
-    __shared__ double2 s_ep[kTile], s_v[kTile];
-    __shared__ double s_im[kTile], s_lam[kTile];
-    const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    const bool mine = i < n && group[i] == op;
-    const double2 pi = i < n ? ep[i] : make_double2(0., 0.);
-    const double li = mine ? lambda[i] : 0.;
+    const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    if (i >= n || group[i] != op) return;  // warp-uniform
+    const double2 pi = ep[i];
+    const double li = lambda[i];
     const double base6 = poly6(K.dq_p * K.dq_p * kH * kH);
     double dx = 0., dy = 0., fvx = 0., fvy = 0.;
-    for (u32 base = 0; base < n; base += kTile) {
-        __syncthreads();
-        if (base + threadIdx.x < n) {
-            s_ep[threadIdx.x] = ep[base + threadIdx.x]; s_im[threadIdx.x] = imass[base + threadIdx.x]; s_lam[threadIdx.x] = lambda[base + threadIdx.x];
-            if (K.gas) s_v[threadIdx.x] = v[base + threadIdx.x];
-        }
-        __syncthreads();
-        if (!mine) continue;
-        const u32 m = min((u32)kTile, n - base);
-        for (u32 t = 0; t < m; t++) {
-            const u32 j = base + t;
-            if (j == i || s_im[t] == 0.) continue;
-            const double rx = pi.x - s_ep[t].x, ry = pi.y - s_ep[t].y;
-            const double r2 = rx * rx + ry * ry;
-            if (r2 < kH2) {
-                const double rlen = sqrt(r2);
-                const double2 sg = spiky_grad(rx, ry, rlen);
-                const double corr = -K.k_p * pow(poly6(rlen * rlen) / base6, 4.);  // E_P 4
-                const double s = (li + s_lam[t]) + corr;
-                dx += s * sg.x; dy += s * sg.y;
-                if (K.gas) {
-                    const double2 g = spiky_grad(rx, ry, r2);  // [sic] the squared length as the length
-                    const double wx = g.x * s_v[t].x, wy = g.y * s_v[t].y;
-                    const double L = sqrt(wx * wx + wy * wy);
-                    const double cx = 0. * 0. - ry * L, cy = L * rx - 0. * 0.;  // cross((0,0,L), (rx,ry,0))
-                    const double p6 = poly6(r2);
-                    fvx += cx * p6; fvy += cy * p6;
-                }
+    for (u32 j = lane; j < n; j += 32) {
+        if (j == i || imass[j] == 0.) continue;
+        const double2 pj = ep[j];
+        const double rx = pi.x - pj.x, ry = pi.y - pj.y;
+        const double r2 = rx * rx + ry * ry;
+        if (r2 < kH2) {
+            const double rlen = sqrt(r2);
+            const double2 sg = spiky_grad(rx, ry, rlen);
+            const double q = poly6(rlen * rlen) / base6, q2 = q * q;
+            const double corr = -K.k_p * (q2 * q2);  // pow(q, E_P), E_P = 4, as two squarings (within 1 ulp of libm's pow)
+            const double s = (li + lambda[j]) + corr;
+            dx += s * sg.x; dy += s * sg.y;
+            if (K.gas) {
+                const double2 g = spiky_grad(rx, ry, r2);  // [sic] the squared length as the length
+                const double2 vj = v[j];
+                const double wx = g.x * vj.x, wy = g.y * vj.y;
+                const double L = sqrt(wx * wx + wy * wy);
+                const double cx = 0. * 0. - ry * L, cy = L * rx - 0. * 0.;  // cross((0,0,L), (rx,ry,0))
+                const double p6 = poly6(r2);
+                fvx += cx * p6; fvy += cy * p6;
             }
         }
     }
-    if (!mine) return;
+    dx = warp_sum_d(dx); dy = warp_sum_d(dy);
+    if (K.gas) { fvx = warp_sum_d(fvx); fvy = warp_sum_d(fvy); }
+    if (lane != 0) return;
     const double div = (double)nbcount[i] + (double)counts[i];
     delta[i] = make_double2((dx / p0) / div, (dy / p0) / div);
     if (K.gas) {
@@ -1094,8 +1089,9 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
                 continue;
             }
             const FluidConsts K = op.kind == STD_GAS ? FluidConsts{.2, .25, .5, 1, op.open} : FluidConsts{.1, .2, 0., 0, 0};
-            k2d_fluid_lambda<<<blocks, kBlock, 0, s>>>(c->ep, c->imass, c->phase, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->v, c->f);
-            k2d_fluid_delta<<<blocks, kBlock, 0, s>>>(c->ep, c->imass, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->counts, c->delta, c->v, c->f);
+            const u32 wblocks = (n + kBlock / 32 - 1) / (kBlock / 32);  // one warp per particle
+            k2d_fluid_lambda<<<wblocks, kBlock, 0, s>>>(c->ep, c->imass, c->phase, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->v, c->f);
+            k2d_fluid_delta<<<wblocks, kBlock, 0, s>>>(c->ep, c->imass, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->counts, c->delta, c->v, c->f);
             k2d_fluid_apply<<<blocks, kBlock, 0, s>>>(c->ep, c->delta, c->group, n, (int)k);
             launches += 3;
             k++;
