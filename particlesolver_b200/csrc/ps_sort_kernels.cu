@@ -18,7 +18,7 @@
 namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kItems = 16;                       // keys per thread
+constexpr int kItems = 16;                       // keys per thread (8, i.e. 2048-pair tiles, was measured slower even at 1M pairs: 94 vs 86 us per sort)
 constexpr int kTile = kThreads * kItems;         // 4096 pairs per CTA
 constexpr int kWarpTile = 32 * kItems;           // 512 contiguous pairs per warp (keeps the rank order stable)
 constexpr u32 kFlagAgg = 1u << 30, kFlagPrefix = 2u << 30, kValMask = (1u << 30) - 1;

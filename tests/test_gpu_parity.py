@@ -114,10 +114,10 @@ def test_graph_and_eager_agree():
     a.close(); b.close()
 
 
-def test_sort_large_random_keys():
+@pytest.mark.parametrize("n", [3_000_001, 3_300_001])  # tile count not / a multiple of the tile size
+def test_sort_large_random_keys(n):
     """K3 alone at a size that needs many tiles and look-back: stable sort of 3M random 24-bit keys."""
     rng = np.random.default_rng(7)
-    n = 3_000_001
     p = psb.default_params()
     p.grid_size[:] = (256, 256, 256)
     sol = psb.Solver(p, max_particles=n)
