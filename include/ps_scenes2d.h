@@ -2,8 +2,7 @@
  * include/ps_scenes2d.h — the scene builders of the reference's 2-D CPU application (Simulation::init*,
  * cpu/src/simulation.cpp:659-1286) over the ps2d_* C ABI, selected by the app's key bindings (cpu/src/view.cpp:129-177):
  *   "1" GRANULAR  "2" STACKS  "3" WALL  "4" PENDULUM  "5" ROPE  "6" FLUID  "7" FLUID_SOLID  "8" GAS_ROPE  "9" FRICTION
- *   "0" WATER_BALLOON  "n" CRADLE  "s" SMOKE_OPEN  "d" SMOKE_CLOSED  "." SDF  "w" WRECKING_BALL
- * ("v" VOLCANO needs the FluidEmitter, which is not on this path: PS_ERR_INVALID.)
+ *   "0" WATER_BALLOON  "n" CRADLE  "s" SMOKE_OPEN  "d" SMOKE_CLOSED  "." SDF  "v" VOLCANO  "w" WRECKING_BALL
  * A scene is reproduced bit for bit, jitter included: the builders draw from the context's glibc rand() stream in the
  * reference's order, starting where the app's stream stands when a key is pressed — `Simulation::Simulation()` has
  * built WRECKING_BALL once already (simulation.cpp:11-16), which consumes 541 draws.

@@ -14,6 +14,7 @@
  *                                      cpu/src/constraint/totalshapeconstraint.cpp:14-24,80-87, cpu/src/solver/particle.cpp:15-57
  *   velocity update + sleeping         Particle::confirmGuess             cpu/src/particle.h:60-65
  *   smoke emitter (particle injection) OpenSmokeEmitter::tick             cpu/src/opensmokeemitter.cpp:17-29
+ *   fluid emitter (emission, freezing) FluidEmitter::tick                 cpu/src/fluidemitter.cpp:13-79
  * in the reference's order: 3 solver iterations of [CONTACT list, STANDARD list, SHAPE list].  The reference projects
  * each list sequentially (Gauss-Seidel); here a list is LEVEL-SCHEDULED on the device: a constraint's level is one more
  * than the highest level of the earlier constraints that share a particle with it, constraints of one level touch
@@ -23,8 +24,8 @@
  *
  * The reference keeps this state in `Simulation` (QList<Particle*>, Body, Constraint objects); there is no extern "C"
  * boundary on its CPU side, so this header defines one whose entry points mirror the reference's constructors and
- * Simulation::create* helpers.  Not on this path: FluidEmitter (VOLCANO scene), the stabilization pass (#undef in the
- * reference), the UMFPACK matrix solver (dead under #define ITERATIVE).  No CPU fallback.
+ * Simulation::create* helpers.  Not on this path: the stabilization pass (#undef in the reference), the UMFPACK matrix
+ * solver (dead under #define ITERATIVE), the emitters' display-only tracer particles.  No CPU fallback.
  */
 #ifndef PSOLVER2D_H
 #define PSOLVER2D_H
@@ -100,7 +101,16 @@ int ps2d_create_gas(Ps2dCtx *ctx, const double *p2, const double *v2, const doub
  * The emitter's display-only tracer particles are not simulated.  timer: time already accumulated (0 for a new one). */
 int ps2d_create_smoke_emitter(Ps2dCtx *ctx, const double *posn2, double rate, uint32_t standard_index, double timer);
 
+/* createFluidEmitter(posn, particlesPerSec, fs) (simulation.cpp:459-461; FluidEmitter::tick, fluidemitter.cpp:13-79 — the
+ * VOLCANO scene): for the first 5 seconds one FLUID particle of mass 1 and velocity (frand(), 1) is emitted at posn every
+ * 1/rate seconds into the fluid constraint at `standard_index`; fluid particles that are slow (|v| < .06) and low (y <= 5)
+ * count down Particle::t and then freeze into immovable SOLID particles that leave the fluid.  timer / total_timer: time
+ * already accumulated (0, 0 for a new emitter). */
+int ps2d_create_fluid_emitter(Ps2dCtx *ctx, const double *posn2, double rate, uint32_t standard_index, double timer, double total_timer);
+
 /* ---- state access (checkpoint / restore) ---- */
+int ps2d_set_particle_timers(Ps2dCtx *ctx, const double *t);   /* Particle::t of every particle (4 when created) */
+int ps2d_get_particle_timers(Ps2dCtx *ctx, double *t);
 int ps2d_set_forces(Ps2dCtx *ctx, const double *f2);     /* Particle::f of every particle (read by the next tick's prediction) */
 int ps2d_body_state(Ps2dCtx *ctx, uint32_t body, double *center2, double *angle);
 uint32_t ps2d_num_bodies(Ps2dCtx *ctx);

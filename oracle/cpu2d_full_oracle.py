@@ -25,8 +25,8 @@ reference's, expression by expression (double precision, glm's component-wise ve
   GasConstraint::project & co.         cpu/src/constraint/gasconstraint.cpp:30-116,...
   OpenSmokeEmitter::tick               cpu/src/opensmokeemitter.cpp:17-29  (particle injection only; the emitter's own
                                        tracer particles are display-only and never read by the solver)
-Not restated: FluidEmitter (VOLCANO scene), the stabilization pass (#undef in the reference), the matrix solver (dead
-under ITERATIVE).
+  FluidEmitter::tick                   cpu/src/fluidemitter.cpp:13-79  (VOLCANO scene: emission, freezing into solids)
+Not restated: the stabilization pass (#undef in the reference), the matrix solver (dead under ITERATIVE).
 """
 import math
 
@@ -78,6 +78,7 @@ class Cpu2dFullOracle:
         self.bod = [int(q[6]) for q in P]
         self.sfric = [q[7] for q in P]
         self.kfric = [q[8] for q in P]
+        self.t = [q[11] if len(q) > 11 else 4. for q in P]   # Particle::t (particle.h:38), only read by the FluidEmitter
         self.xb, self.yb, self.gravity = list(scene["xbounds"]), list(scene["ybounds"]), list(scene["gravity"])
         self.bodies = []
         for b in scene["bodies"]:
@@ -92,6 +93,9 @@ class Cpu2dFullOracle:
             self.standard.append(c)
         self.emitters = [dict(posn=list(e["posn"]), rate=e["rate"], timer=e.get("timer", 0.), gas=(self.standard[e["standard_index"]] if e["standard_index"] >= 0 else None))
                          for e in scene.get("smoke_emitters", [])]
+        fe = scene.get("fluid_emitters", [])
+        self.fluid_emitters = [dict(posn=list(e["posn"]), rate=e["rate"], timer=e.get("timer", 0.), total_timer=e.get("total_timer", 0.),
+                                    fluid=self.standard[e["standard_index"]]) for e in (fe if isinstance(fe, list) else [])]
         self.rng = GlibcRand(rand_seed, int(scene["rand_calls"]))
         self.num_contacts = 0
 
@@ -340,6 +344,7 @@ class Cpu2dFullOracle:
                 self.f[i][1] += (self.v[i][1] * s) * -50.
             lambdas[i] = -(p_rat - 1.) / (denom + RELAXATION)
             neighbors.append(nb)
+        c["lambdas"] = lambdas   # TotalFluidConstraint::lambdas survives the call (the FluidEmitter reads it)
         base6 = poly6(K["DQ_P"] * K["DQ_P"] * H * H)
         deltas = []
         for k, i in enumerate(ps):
@@ -462,6 +467,35 @@ class Cpu2dFullOracle:
                     e["gas"]["ps"].append(len(self.p))
                     self.add_particle(e["posn"], 1., GAS)
 
+        for e in self.fluid_emitters:  # FluidEmitter::tick, cpu/src/fluidemitter.cpp:13-79
+            fs = e["fluid"]
+            ps, lambdas = fs["ps"], fs.get("lambdas", {})
+            for i in range(len(ps) - 1, -1, -1):
+                k = ps[i]
+                if math.sqrt(v[k][0] * v[k][0] + v[k][1] * v[k][1]) < .06 and p[k][1] <= 5:
+                    # [sic] the hash is keyed by particle index but read with the loop index i; a missing key reads 0
+                    if lambdas.get(i, 0.) <= 0:
+                        self.t[k] -= 1
+                        if self.t[k] <= 0:  # the particle freezes into an immovable solid and leaves the fluid
+                            self.t[k] = 0
+                            self.imass[k] = 0
+                            self.ph[k] = SOLID
+                            ep[k][0], ep[k][1] = p[k][0], p[k][1]
+                            v[k][0] = v[k][1] = 0.
+                            f[k][0] = f[k][1] = 0.
+                            del ps[i]
+                    else:
+                        self.t[k] += dt
+                        if self.t[k] > 3:
+                            self.t[k] = 3
+            e["timer"] += dt
+            e["total_timer"] += dt
+            while e["total_timer"] < 5 and e["timer"] >= 1. / e["rate"]:
+                e["timer"] -= 1. / e["rate"]
+                fs["ps"].append(len(self.p))
+                self.add_particle(e["posn"], 1., FLUID)
+                self.v[-1] = [self.frand(), 1.]
+
     def add_particle(self, pos, mass, phase):
         """Particle(pos, mass, phase) (particle.h:31-52) appended to the particle list"""
         self.p.append([pos[0], pos[1]])
@@ -475,6 +509,7 @@ class Cpu2dFullOracle:
         self.bod.append(-1)
         self.sfric.append(0.)
         self.kfric.append(0.)
+        self.t.append(4.)
 
     def positions(self):
         return np.array(self.p)

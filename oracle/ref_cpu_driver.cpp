@@ -28,6 +28,7 @@
 #include "distanceconstraint.h"
 #include "totalshapeconstraint.h"
 #include "opensmokeemitter.h"
+#include "fluidemitter.h"
 #undef protected
 #undef private
 
@@ -72,11 +73,11 @@ static void dump_scene(Simulation &sim, const std::string &dir, int tick) {
     int n = sim.m_particles.size();
     fprintf(f, "{\"n\": %d, \"rand_calls\": %ld,\n \"xbounds\": [%.17g, %.17g], \"ybounds\": [%.17g, %.17g], \"gravity\": [%.17g, %.17g],\n", n, g_rand_calls,
             sim.m_xBoundaries.x, sim.m_xBoundaries.y, sim.m_yBoundaries.x, sim.m_yBoundaries.y, sim.m_gravity.x, sim.m_gravity.y);
-    fprintf(f, " \"particles\": [");  // [px, py, vx, vy, imass, phase, bod, sFriction, kFriction, fx, fy]
+    fprintf(f, " \"particles\": [");  // [px, py, vx, vy, imass, phase, bod, sFriction, kFriction, fx, fy, t]
     for (int i = 0; i < n; i++) {
         Particle *p = sim.m_particles[i];
-        fprintf(f, "%s[%.17g, %.17g, %.17g, %.17g, %.17g, %d, %d, %.17g, %.17g, %.17g, %.17g]", i ? ",\n  " : "", p->p.x, p->p.y, p->v.x, p->v.y, p->imass,
-                (int)p->ph, p->bod, p->sFriction, p->kFriction, p->f.x, p->f.y);
+        fprintf(f, "%s[%.17g, %.17g, %.17g, %.17g, %.17g, %d, %d, %.17g, %.17g, %.17g, %.17g, %.17g]", i ? ",\n  " : "", p->p.x, p->p.y, p->v.x, p->v.y, p->imass,
+                (int)p->ph, p->bod, p->sFriction, p->kFriction, p->f.x, p->f.y, p->t);
     }
     fprintf(f, "],\n \"bodies\": [");
     for (int b = 0; b < sim.m_bodies.size(); b++) {
@@ -116,7 +117,15 @@ static void dump_scene(Simulation &sim, const std::string &dir, int tick) {
         fprintf(f, "%s{\"posn\": [%.17g, %.17g], \"rate\": %.17g, \"timer\": %.17g, \"standard_index\": %d}", e ? ", " : "", E->m_posn.x, E->m_posn.y,
                 E->m_particlesPerSec, E->timer, gi);
     }
-    fprintf(f, "], \"fluid_emitters\": %d}\n", (int)sim.m_fluidEmitters.size());
+    fprintf(f, "], \"fluid_emitters\": [");
+    for (int e = 0; e < sim.m_fluidEmitters.size(); e++) {
+        FluidEmitter *E = sim.m_fluidEmitters[e];
+        int gi = -1;
+        for (int c = 0; c < glob.size(); c++) if ((Constraint *)E->m_fs == glob[c]) gi = c;
+        fprintf(f, "%s{\"posn\": [%.17g, %.17g], \"rate\": %.17g, \"timer\": %.17g, \"total_timer\": %.17g, \"standard_index\": %d}", e ? ", " : "", E->m_posn.x,
+                E->m_posn.y, E->m_particlesPerSec, E->timer, E->totalTimer, gi);
+    }
+    fprintf(f, "]}\n");
     fclose(f);
 }
 

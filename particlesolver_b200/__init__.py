@@ -175,6 +175,9 @@ def lib():
         L.ps2d_create_gas.argtypes = [vp, vp, vp, vp, u64, C.c_double, i32, C.POINTER(u32)]
         L.ps2d_create_smoke_emitter.argtypes = [vp, vp, C.c_double, u32, C.c_double]
         L.ps2d_set_forces.argtypes = [vp, vp]
+        L.ps2d_create_fluid_emitter.argtypes = [vp, vp, C.c_double, u32, C.c_double, C.c_double]
+        L.ps2d_set_particle_timers.argtypes = [vp, vp]
+        L.ps2d_get_particle_timers.argtypes = [vp, vp]
         L.ps2d_body_state.argtypes = [vp, u32, vp, C.POINTER(C.c_double)]
         L.ps2d_num_bodies.argtypes = [vp]
         L.ps2d_num_bodies.restype = u32
@@ -603,6 +606,20 @@ class Simulation2D:
         q = _arr(posn, np.float64).reshape(2)
         _check(lib().ps2d_create_smoke_emitter(self._h, _ptr(q), particles_per_sec, 0xFFFFFFFF if gas_index is None else int(gas_index), timer))
 
+    def createFluidEmitter(self, posn, particles_per_sec, fluid_index, timer=0.0, total_timer=0.0):
+        q = _arr(posn, np.float64).reshape(2)
+        _check(lib().ps2d_create_fluid_emitter(self._h, _ptr(q), particles_per_sec, int(fluid_index), timer, total_timer))
+
+    def setParticleTimers(self, t):
+        t = _arr(t, np.float64).reshape(-1)
+        assert t.shape[0] == self.getNumParticles()
+        _check(lib().ps2d_set_particle_timers(self._h, _ptr(t)))
+
+    def particleTimers(self):
+        t = np.empty(self.getNumParticles(), np.float64)
+        _check(lib().ps2d_get_particle_timers(self._h, _ptr(t)))
+        return t
+
     def setForces(self, f):
         f = _arr(f, np.float64).reshape(-1, 2)
         assert f.shape[0] == self.getNumParticles()
@@ -671,8 +688,8 @@ class Simulation2D:
     def from_state(cls, scene, max_particles=None, device=0):
         """Builds a simulation from a full restart state: the dict layout written by the reference driver
         (oracle/ref_cpu_driver.cpp dump_scene; tests/golden/ref_cpu_scenes.npz) — particles [px, py, vx, vy, imass, phase,
-        bod, sFriction, kFriction(, fx, fy)], bodies, the STANDARD constraint list in order, smoke emitters, rand() position."""
-        P = np.array(scene["particles"], np.float64).reshape(-1, 11 if scene["particles"] and len(scene["particles"][0]) > 9 else 9)
+        bod, sFriction, kFriction(, fx, fy(, t))], bodies, the STANDARD constraint list in order, smoke / fluid emitters, rand() position."""
+        P = np.array(scene["particles"], np.float64).reshape(-1, len(scene["particles"][0]) if scene["particles"] else 9)
         n = P.shape[0]
         sim = cls(scene["xbounds"], scene["ybounds"], scene["gravity"], max_particles=max_particles or max(1024, 2 * n), device=device)
         sim.addParticles(P[:, 0:2], P[:, 2:4], P[:, 4], P[:, 5].astype(np.int32), P[:, 6].astype(np.int32), P[:, 7], P[:, 8])
@@ -691,8 +708,13 @@ class Simulation2D:
                 raise ValueError(c["type"])
         for e in scene.get("smoke_emitters", []):
             sim.createSmokeEmitter(e["posn"], e["rate"], e["standard_index"] if e["standard_index"] >= 0 else None, e.get("timer", 0.0))
+        fe = scene.get("fluid_emitters", [])
+        for e in (fe if isinstance(fe, list) else []):
+            sim.createFluidEmitter(e["posn"], e["rate"], e["standard_index"], e.get("timer", 0.0), e.get("total_timer", 0.0))
         if P.shape[1] > 9:
             sim.setForces(P[:, 9:11])
+        if P.shape[1] > 11:
+            sim.setParticleTimers(P[:, 11])
         sim.seedRand(1, int(scene["rand_calls"]))
         return sim
 

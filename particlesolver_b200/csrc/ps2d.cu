@@ -613,6 +613,7 @@ struct DistanceRun {  // consecutive distance constraints [begin, end) of the ST
     u32 dev_first, dev_level_first, levels;
 };
 struct Emitter { double x, y, rate, timer; u32 standard_index; };
+struct FluidEmitterRec { double x, y, rate, timer, total_timer; u32 standard_index; };
 }  // namespace
 
 struct Ps2dCtx {
@@ -643,6 +644,10 @@ struct Ps2dCtx {
     std::vector<double> h_imass;  // host mirror: constraint constructors validate against it
     std::vector<int> h_phase;
     std::vector<Emitter> emitters;
+    std::vector<FluidEmitterRec> fluid_emitters;
+    std::vector<int> h_group;   // host mirror of `group` (the FluidEmitter walks its fluid's member list)
+    std::vector<double> h_t;    // Particle::t (particle.h:38): freeze countdown, only the FluidEmitter reads it
+    double *lambda_keep = nullptr;  // lambda of the fluid emitters' constraints after the last solver iteration
     size_t raw_cap = 0;
     std::vector<int> h_raw;
     GlibcRand rng;
@@ -712,7 +717,7 @@ extern "C" int ps2d_destroy(Ps2dCtx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->p, c->v, c->ep, c->f, c->delta, c->rs, c->sdf_grad, c->imass, c->tmass, c->sfric, c->kfric, c->lambda, c->sdf_dist, c->phase, c->bod,
                     c->group, c->raw, c->static_counts, c->flags, c->counts, c->draws, c->rank, c->nbcount, c->nb, c->cnt, c->lvl, c->cur, c->nbq, c->scalars,
-                    c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center, c->dc_i1, c->dc_i2, c->dc_level_off, c->dc_rest};
+                    c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center, c->dc_i1, c->dc_i2, c->dc_level_off, c->dc_rest, c->lambda_keep};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (c->scalars_host) cudaFreeHost(c->scalars_host);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -761,6 +766,8 @@ extern "C" int ps2d_add_particles(Ps2dCtx *c, const double *p2, const double *v2
         c->h_imass.push_back(inv_mass[k]);
         c->h_phase.push_back(phase[k]);
         c->h_static_counts.push_back(0);
+        c->h_group.push_back(-1);
+        c->h_t.push_back(4.);
         if (phase[k] == PS2D_PHASE_SOLID) c->any_solid = 1; else c->any_jitter = 1;
     }
     c->n += (u32)n;
@@ -804,7 +811,7 @@ static int add_group(Ps2dCtx *c, const uint32_t *indices, uint64_t n, double den
     }
     CU2(cudaSetDevice(c->device));
     const int id = (int)c->standard.size();
-    for (uint64_t k = 0; k < n; k++) CU2(upload(c, c->group + indices[k], &id, 1));
+    for (uint64_t k = 0; k < n; k++) { CU2(upload(c, c->group + indices[k], &id, 1)); c->h_group[indices[k]] = id; }
     StdOp op;
     op.kind = want_phase == PS2D_PHASE_GAS ? STD_GAS : STD_FLUID; op.p0 = density; op.open = open;
     c->standard.push_back(op);
@@ -1028,6 +1035,94 @@ static int rebuild_standard(Ps2dCtx *c) {
     return PS_OK;
 }
 
+// FluidEmitter::tick (cpu/src/fluidemitter.cpp:13-79) after a solver tick: slow fluid particles low in the scene count down
+// and freeze into immovable solids that leave the fluid; new fluid particles are emitted for the first 5 seconds.  Host
+// logic over the emitter's fluid (a few hundred particles), like the reference's; it reads p, v and the constraint's
+// lambdas of the last iteration.  [sic] The reference reads that hash — keyed by particle index — with the position i
+// in the member list: `m_fs->lambdas[i]`; a key that is not a member reads 0.  Kept, or the scene would evolve differently.
+static int fluid_emitters_tick(Ps2dCtx *c, double dt) {
+    if (c->fluid_emitters.empty()) return PS_OK;
+    std::vector<double> p, v, lam;
+    for (FluidEmitterRec &e : c->fluid_emitters) {
+        const u32 n = c->n;
+        p.resize(2 * (size_t)n); v.resize(2 * (size_t)n); lam.resize(n);
+        CU2(cudaMemcpyAsync(p.data(), c->p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+        CU2(cudaMemcpyAsync(v.data(), c->v, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+        CU2(cudaMemcpyAsync(lam.data(), c->lambda_keep, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU2(cudaStreamSynchronize(c->stream));
+        const int id = (int)e.standard_index;
+        std::vector<u32> ps;  // the constraint's member list: ascending particle index (append-only, removeAt keeps the order)
+        for (u32 k = 0; k < n; k++) if (c->h_group[k] == id) ps.push_back(k);
+        for (int i = (int)ps.size() - 1; i >= 0; i--) {
+            const u32 k = ps[i];
+            const double vx = v[2 * k], vy = v[2 * k + 1];
+            if (std::sqrt(vx * vx + vy * vy) < .06 && p[2 * k + 1] <= 5) {
+                const double l = ((u32)i < n && c->h_group[i] == id) ? lam[i] : 0.;
+                if (l <= 0) {
+                    c->h_t[k] -= 1;
+                    if (c->h_t[k] <= 0) {
+                        c->h_t[k] = 0;
+                        const double zero2[2] = {0., 0.}, zero = 0.;
+                        const int solid = PS2D_PHASE_SOLID, none = -1;
+                        CU2(upload(c, c->imass + k, &zero, 1));
+                        CU2(upload(c, c->tmass + k, &zero, 1));
+                        CU2(upload(c, c->phase + k, &solid, 1));
+                        CU2(upload(c, c->group + k, &none, 1));
+                        CU2(upload(c, (double *)(c->ep + k), &p[2 * k], 2));
+                        CU2(upload(c, (double *)(c->v + k), zero2, 2));
+                        CU2(upload(c, (double *)(c->f + k), zero2, 2));
+                        c->h_imass[k] = 0.; c->h_phase[k] = solid; c->h_group[k] = -1;
+                        c->any_solid = 1;
+                    }
+                } else {
+                    c->h_t[k] += dt;
+                    if (c->h_t[k] > 3) c->h_t[k] = 3;
+                }
+            }
+        }
+        e.timer += dt;
+        e.total_timer += dt;
+        while (e.total_timer < 5 && e.timer >= 1. / e.rate) {
+            e.timer -= 1. / e.rate;
+            const double pos[2] = {e.x, e.y}, im = 1. / 1.;
+            const double vel[2] = {(double)(float)((double)c->rng.next() / (double)2147483647), 1.};  // glm::dvec2(frand(), 1)
+            const int32_t ph = PS2D_PHASE_FLUID;
+            uint64_t at = 0;
+            int r = ps2d_add_particles(c, pos, vel, &im, &ph, nullptr, nullptr, nullptr, 1, &at);
+            if (r != PS_OK) return r;
+            CU2(upload(c, c->group + at, &id, 1));
+            c->h_group[at] = id;
+        }
+    }
+    return PS_OK;
+}
+
+// createFluidEmitter(posn, particlesPerSec, fs) (simulation.cpp:459-461)
+extern "C" int ps2d_create_fluid_emitter(Ps2dCtx *c, const double *posn2, double rate, uint32_t standard_index, double timer, double total_timer) {
+    if (!c || !posn2) { ps_set_error("ps2d_create_fluid_emitter: null argument"); return PS_ERR_INVALID; }
+    if (!(rate > 0.)) { ps_set_error("ps2d_create_fluid_emitter: rate must be positive"); return PS_ERR_INVALID; }
+    if (standard_index >= c->standard.size() || c->standard[standard_index].kind != STD_FLUID) {
+        ps_set_error("ps2d_create_fluid_emitter: STANDARD constraint %u is not a fluid", standard_index); return PS_ERR_INVALID;
+    }
+    CU2(cudaSetDevice(c->device));
+    if (!c->lambda_keep) {
+        if (!dev_alloc(&c->lambda_keep, c->cap)) { ps_set_error("ps2d_create_fluid_emitter: allocation failed"); return PS_ERR_CUDA; }
+        CU2(cudaMemset(c->lambda_keep, 0, c->cap * 8));
+    }
+    c->fluid_emitters.push_back(FluidEmitterRec{posn2[0], posn2[1], rate, timer, total_timer, standard_index});
+    return PS_OK;
+}
+extern "C" int ps2d_set_particle_timers(Ps2dCtx *c, const double *t) {
+    if (!c || !t) { ps_set_error("ps2d_set_particle_timers: null argument"); return PS_ERR_INVALID; }
+    c->h_t.assign(t, t + c->n);
+    return PS_OK;
+}
+extern "C" int ps2d_get_particle_timers(Ps2dCtx *c, double *t) {
+    if (!c || !t) { ps_set_error("ps2d_get_particle_timers: null argument"); return PS_ERR_INVALID; }
+    std::copy(c->h_t.begin(), c->h_t.end(), t);
+    return PS_OK;
+}
+
 extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
     if (!c->n) return PS_OK;
@@ -1091,6 +1186,9 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
             const FluidConsts K = op.kind == STD_GAS ? FluidConsts{.2, .25, .5, 1, op.open} : FluidConsts{.1, .2, 0., 0, 0};
             const u32 wblocks = (n + kBlock / 32 - 1) / (kBlock / 32);  // one warp per particle
             k2d_fluid_lambda<<<wblocks, kBlock, 0, s>>>(c->ep, c->imass, c->phase, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->v, c->f);
+            if (it + 1 == P.solver_iterations)
+                for (const FluidEmitterRec &fe : c->fluid_emitters)
+                    if (fe.standard_index == k) CU2(cudaMemcpyAsync(c->lambda_keep, c->lambda, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
             k2d_fluid_delta<<<wblocks, kBlock, 0, s>>>(c->ep, c->imass, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->counts, c->delta, c->v, c->f);
             k2d_fluid_apply<<<blocks, kBlock, 0, s>>>(c->ep, c->delta, c->group, n, (int)k);
             launches += 3;
@@ -1121,9 +1219,10 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
             if (r != PS_OK) return r;
             const int id = (int)em.standard_index;
             CU2(upload(c, c->group + at, &id, 1));
+            c->h_group[at] = id;
         }
     }
-    return PS_OK;
+    return fluid_emitters_tick(c, dt);
 }
 
 extern "C" int ps2d_download(Ps2dCtx *c, int which, void *host) {
@@ -1176,8 +1275,9 @@ const char kMagic2d[8] = {'P', 'S', 'B', '2', 'D', 'C', 'K', '1'};
 struct Header2d {
     char magic[8];
     uint32_t version, params_bytes;
-    uint64_t n, cap, num_bodies, num_standard, num_emitters, rand_calls;
+    uint64_t n, cap, num_bodies, num_standard, num_emitters, num_fluid_emitters, rand_calls;
 };
+struct FluidEmitRecord { double x, y, rate, timer, total_timer; uint32_t standard_index, pad; };
 struct StdRecord { uint32_t kind, open, i1, i2; double p0, d; };
 struct EmitRecord { double x, y, rate, timer; uint32_t standard_index, pad; };
 template <class T> bool put2(FILE *f, const T *p, size_t n) { return n == 0 || fwrite(p, sizeof(T), n, f) == n; }
@@ -1203,8 +1303,13 @@ extern "C" int ps2d_save(Ps2dCtx *c, const char *path) {
     CU2(fetch(ban, c->b_angle, nb)); CU2(fetch(bce, c->b_center, 2 * nb));
     Header2d h{};
     memcpy(h.magic, kMagic2d, 8);
-    h.version = 1; h.params_bytes = (uint32_t)sizeof(Ps2dParams);
-    h.n = n; h.cap = c->cap; h.num_bodies = nb; h.num_standard = c->standard.size(); h.num_emitters = c->emitters.size(); h.rand_calls = c->rng.calls;
+    h.version = 2; h.params_bytes = (uint32_t)sizeof(Ps2dParams);
+    h.n = n; h.cap = c->cap; h.num_bodies = nb; h.num_standard = c->standard.size(); h.num_emitters = c->emitters.size();
+    h.num_fluid_emitters = c->fluid_emitters.size(); h.rand_calls = c->rng.calls;
+    std::vector<FluidEmitRecord> fem;
+    for (const FluidEmitterRec &e : c->fluid_emitters) fem.push_back(FluidEmitRecord{e.x, e.y, e.rate, e.timer, e.total_timer, e.standard_index, 0});
+    std::vector<double> lk;
+    if (c->lambda_keep) CU2(fetch(lk, c->lambda_keep, n));
     std::vector<StdRecord> st;
     for (const StdOp &o : c->standard) st.push_back(StdRecord{(uint32_t)o.kind, (uint32_t)o.open, o.i1, o.i2, o.p0, o.d});
     std::vector<EmitRecord> em;
@@ -1215,7 +1320,8 @@ extern "C" int ps2d_save(Ps2dCtx *c, const char *path) {
               put2(fp, f.data(), f.size()) && put2(fp, rs.data(), rs.size()) && put2(fp, sg.data(), sg.size()) && put2(fp, im.data(), n) && put2(fp, sf.data(), n) &&
               put2(fp, kf.data(), n) && put2(fp, sd.data(), n) && put2(fp, ph.data(), n) && put2(fp, bod.data(), n) && put2(fp, grp.data(), n) &&
               put2(fp, c->h_static_counts.data(), n) && put2(fp, bf.data(), nb) && put2(fp, bc.data(), nb) && put2(fp, bim.data(), nb) && put2(fp, bst.data(), nb) &&
-              put2(fp, ban.data(), nb) && put2(fp, bce.data(), 2 * nb) && put2(fp, st.data(), st.size()) && put2(fp, em.data(), em.size());
+              put2(fp, ban.data(), nb) && put2(fp, bce.data(), 2 * nb) && put2(fp, st.data(), st.size()) && put2(fp, em.data(), em.size()) &&
+              put2(fp, c->h_t.data(), n) && put2(fp, fem.data(), fem.size()) && put2(fp, lk.data(), lk.size());
     ok = (fclose(fp) == 0) && ok;
     if (!ok) { ps_set_error("ps2d_save: short write to %s", path); return PS_ERR_INVALID; }
     return PS_OK;
@@ -1229,8 +1335,8 @@ extern "C" int ps2d_load(const char *path, int device, Ps2dCtx **out) {
     struct Closer { FILE *f; ~Closer() { fclose(f); } } closer{fp};
     Header2d h{};
     if (!get2(fp, &h, 1) || memcmp(h.magic, kMagic2d, 8) != 0) { ps_set_error("ps2d_load: %s is not a 2-D libpsolver checkpoint", path); return PS_ERR_INVALID; }
-    if (h.version != 1 || h.params_bytes != sizeof(Ps2dParams)) { ps_set_error("ps2d_load: checkpoint version %u not understood", h.version); return PS_ERR_INVALID; }
-    if (h.n > h.cap || h.cap > (1u << 28) || h.num_bodies > h.n || h.num_standard > (1u << 28) || h.num_emitters > 4096) { ps_set_error("ps2d_load: implausible sizes in %s", path); return PS_ERR_INVALID; }
+    if (h.version != 2 || h.params_bytes != sizeof(Ps2dParams)) { ps_set_error("ps2d_load: checkpoint version %u not understood", h.version); return PS_ERR_INVALID; }
+    if (h.n > h.cap || h.cap > (1u << 28) || h.num_bodies > h.n || h.num_standard > (1u << 28) || h.num_emitters > 4096 || h.num_fluid_emitters > 4096) { ps_set_error("ps2d_load: implausible sizes in %s", path); return PS_ERR_INVALID; }
     Ps2dParams P;
     uint32_t rng[31];
     const size_t n = h.n, nb = h.num_bodies;
@@ -1239,11 +1345,14 @@ extern "C" int ps2d_load(const char *path, int device, Ps2dCtx **out) {
     std::vector<u32> sc(n), bf(nb), bc(nb);
     std::vector<StdRecord> st(h.num_standard);
     std::vector<EmitRecord> em(h.num_emitters);
+    std::vector<FluidEmitRecord> fem(h.num_fluid_emitters);
+    std::vector<double> ht(n), lk(h.num_fluid_emitters ? n : 0);
     bool ok = get2(fp, &P, 1) && get2(fp, rng, 31) && get2(fp, p.data(), p.size()) && get2(fp, v.data(), v.size()) && get2(fp, f.data(), f.size()) &&
               get2(fp, rs.data(), rs.size()) && get2(fp, sg.data(), sg.size()) && get2(fp, im.data(), n) && get2(fp, sf.data(), n) && get2(fp, kf.data(), n) &&
               get2(fp, sd.data(), n) && get2(fp, ph.data(), n) && get2(fp, bod.data(), n) && get2(fp, grp.data(), n) && get2(fp, sc.data(), n) &&
               get2(fp, bf.data(), nb) && get2(fp, bc.data(), nb) && get2(fp, bim.data(), nb) && get2(fp, bst.data(), nb) && get2(fp, ban.data(), nb) &&
-              get2(fp, bce.data(), 2 * nb) && get2(fp, st.data(), st.size()) && get2(fp, em.data(), em.size());
+              get2(fp, bce.data(), 2 * nb) && get2(fp, st.data(), st.size()) && get2(fp, em.data(), em.size()) && get2(fp, ht.data(), n) &&
+              get2(fp, fem.data(), fem.size()) && get2(fp, lk.data(), lk.size());
     if (!ok) { ps_set_error("ps2d_load: truncated file %s", path); return PS_ERR_INVALID; }
     for (size_t b = 0; b < nb; b++) if ((uint64_t)bf[b] + bc[b] > n) { ps_set_error("ps2d_load: body out of range"); return PS_ERR_INVALID; }
     for (const StdRecord &o : st) if (o.kind > STD_DISTANCE || (o.kind == STD_DISTANCE && (o.i1 >= n || o.i2 >= n))) { ps_set_error("ps2d_load: bad STANDARD record"); return PS_ERR_INVALID; }
@@ -1256,6 +1365,8 @@ extern "C" int ps2d_load(const char *path, int device, Ps2dCtx **out) {
               upload(c, (double *)c->sdf_grad, sg.data(), 2 * n) == cudaSuccess && upload(c, c->sdf_dist, sd.data(), n) == cudaSuccess &&
               upload(c, c->group, grp.data(), n) == cudaSuccess && upload(c, c->static_counts, sc.data(), n) == cudaSuccess;
     c->h_static_counts = sc;
+    c->h_group = grp;
+    c->h_t = ht;
     for (size_t b = 0; b < nb && up; b++) {
         if (grow_bodies(c) != PS_OK) return fail(PS_ERR_CUDA);
         up = upload(c, c->b_first + b, &bf[b], 1) == cudaSuccess && upload(c, c->b_count + b, &bc[b], 1) == cudaSuccess && upload(c, c->b_imass + b, &bim[b], 1) == cudaSuccess &&
@@ -1270,6 +1381,11 @@ extern "C" int ps2d_load(const char *path, int device, Ps2dCtx **out) {
     }
     c->standard_dirty = true;
     for (const EmitRecord &e : em) c->emitters.push_back(Emitter{e.x, e.y, e.rate, e.timer, e.standard_index});
+    for (const FluidEmitRecord &e : fem) {
+        const double posn[2] = {e.x, e.y};
+        if ((r = ps2d_create_fluid_emitter(c, posn, e.rate, e.standard_index, e.timer, e.total_timer)) != PS_OK) return fail(r);
+    }
+    if (!fem.empty() && upload(c, c->lambda_keep, lk.data(), n) != cudaSuccess) { ps_set_error("ps2d_load: upload failed"); return fail(PS_ERR_CUDA); }
     c->rng.r.assign(rng, rng + 31);
     c->rng.calls = h.rand_calls;
     *out = c;

@@ -90,7 +90,7 @@ const SceneInfo kScenes[] = {
     {"9", "FRICTION_TEST", {-20, 20}, {0, 1000000}, 64},       {"0", "WATER_BALLOON_TEST", {-10, 10}, {-10, 1000000}, 1024},
     {"n", "CRADLE_TEST", {-10, 10}, {-5, 1000000}, 64},        {"s", "SMOKE_OPEN_TEST", {-6, 6}, {-4, 200}, 8192},
     {"d", "SMOKE_CLOSED_TEST", {-4, 4}, {-4, 4}, 1024},        {".", "SDF_TEST", {-20, 20}, {0, 1000000}, 64},
-    {"w", "WRECKING_BALL", {-15, 100}, {0, 1000000}, 1024},
+    {"w", "WRECKING_BALL", {-15, 100}, {0, 1000000}, 1024},  {"v", "VOLCANO_TEST", {-20, 20}, {0, 100}, 1024},
 };
 const SceneInfo *find_scene(const char *key) {
     if (!key) return nullptr;
@@ -317,6 +317,25 @@ void build(Builder &B, const std::string &k, const SceneInfo &S) {
         B.group(g, 1.5, true, true, &gs);
         const double posn[2] = {0, 0};
         if (B.err == PS_OK) B.err = ps2d_create_smoke_emitter(B.c, posn, 15, gs, 0.);
+    } else if (k == "v") {  // initVolcano, :1206-1216 + :1177-1203
+        const double scale = 10.;
+        double delta = .2;
+        std::vector<Part> slope;
+        for (double x = 1.; x <= scale; x += delta) {
+            slope.push_back(Part(-x, scale - x, 0));
+            slope.push_back(Part(x, scale - x, 0));
+        }
+        B.add(slope);
+        delta = .8;
+        std::vector<Part> f;
+        for (double y = 0.; y < scale - 1.; y += delta)
+            for (double x = 0.; x < scale - y - 1; x += delta) {
+                f.push_back(B.jittered(x, y, 1.1, PS2D_PHASE_FLUID));
+                f.push_back(B.jittered(-x, y, 1.1, PS2D_PHASE_FLUID));
+            }
+        B.group(f, 1, false, false);
+        const double posn[2] = {0, 0};
+        if (B.err == PS_OK) B.err = ps2d_create_fluid_emitter(B.c, posn, scale * 4, 0, 0., 0.);
     } else if (k == "w") {  // initWreckingBall, :1218-1286
         brick_wall(B, 8, 2, 30., 1, 1);
         const double scale = 6., delta = .4, num = 1.;
@@ -353,7 +372,7 @@ extern "C" int ps2d_build_scene(const char *key, int device, uint64_t max_partic
     *out = nullptr;
     const SceneInfo *S = find_scene(key);
     if (!S) {
-        ps_set_error(key && !std::strcmp(key, "v") ? "ps2d_build_scene: VOLCANO_TEST needs the FluidEmitter, which is not on this path" : "ps2d_build_scene: unknown scene key");
+        ps_set_error("ps2d_build_scene: unknown scene key");
         return PS_ERR_INVALID;
     }
     Ps2dParams P;

@@ -1,6 +1,6 @@
 """tests/golden/ref_cpu_scenes.npz — scene descriptions and states of the reference's UNMODIFIED 2-D CPU solver
 (oracle/_ref/ref_cpu, built from /root/reference/cpu/src by `make -C oracle ref`) for every key-bound scene of its app
-(cpu/src/view.cpp:129-177) except VOLCANO (FluidEmitter): SURVEY §8 row a19.
+(cpu/src/view.cpp:129-177): SURVEY §8 row a19.
 Runs anywhere (no GPU):   python tests/golden/make_cpu_scenes_golden.py
 Per scene NAME: NAME_scene = the full restart state as JSON (particles incl. friction and force accumulators, rigid
 bodies with r vectors / SDF / centre / angle, the STANDARD constraint list in order, smoke emitters, position of the glibc
@@ -30,6 +30,8 @@ SCENES = {
     "smoke_closed": ("d", 0, [1, 2, 3, 10, 20]),
     "sdf": (".", 46, [47, 48, 49, 52, 56]),
     "wrecking_ball": ("w", 0, [1, 2, 3, 5, 10]),
+    "volcano": ("v", 0, [1, 2, 3, 10, 20]),
+    "volcano_freezing": ("v", 240, [241, 242, 243, 250, 260]),   # fluid particles freeze into solids from tick ~150 on
 }
 
 

@@ -1,5 +1,5 @@
 """Pins oracle/cpu2d_full_oracle.py (every constraint group of the reference's 2-D CPU solver) to
-tests/golden/ref_cpu_scenes.npz: states written by the reference's own unmodified CPU solver for 14 of its scenes.
+tests/golden/ref_cpu_scenes.npz: states written by the reference's own unmodified CPU solver for all 15 key-bound scenes.
 The restatement follows the reference expression by expression and uses the same libm, so the bar is 1e-12 (observed: 0)."""
 import json
 import os
@@ -19,7 +19,7 @@ BUDGET = {"wrecking_ball": 2, "wall": 3, "fluid_solid": 4, "balloon": 4}
 
 
 def test_all_scenes_present():
-    assert len(SCENES) == 14
+    assert len(SCENES) == 16
 
 
 @pytest.mark.parametrize("name", SCENES)

@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(ROOT, "tests", "golden", "ref_cpu_scenes.npz"))
 SCENES = sorted(k[:-6] for k in G.files if k.endswith("_scene"))
-CONTACT_SCENES = ("granular", "stacks", "wall", "friction", "sdf", "wrecking_ball", "fluid_solid", "balloon", "rope")
+CONTACT_SCENES = ("granular", "stacks", "wall", "friction", "sdf", "wrecking_ball", "fluid_solid", "balloon", "rope", "volcano", "volcano_freezing")
 REPORT = os.environ.get("PS2D_REPORT")
 
 
@@ -55,6 +55,8 @@ def test_scene_matches_reference_cpu_solver(name):
     if REPORT:
         with open(REPORT, "a") as f:
             f.write(f"{name}: contacts {contacts} levels {levels} launches/tick {sim.launches_per_tick} " + " ".join(f"t{t}:{dp:.1e}/{dv:.1e}" for t, dp, dv in rows) + "\n")
+    if name == "volcano_freezing":   # the FluidEmitter froze fluid particles into solids during the replayed ticks, like the reference
+        assert (sim.phases() == 0).sum() > (np.array(scene["particles"])[:, 5] == 0).sum()
     if name in CONTACT_SCENES:
         assert contacts > 0 and levels > 0, f"{name}: no contact constraint exercised"
     sim.close()

@@ -45,7 +45,7 @@ def test_3d_checkpoint_continues_bit_identically(scene, tmp_path):
     ps.close()
 
 
-@pytest.mark.parametrize("key", ["w", "8", "0", "2"])
+@pytest.mark.parametrize("key", ["w", "8", "0", "2", "v"])
 def test_2d_checkpoint_continues_bit_identically(key, tmp_path):
     sim = psb.Simulation2D.scene(key)
     for _ in range(12):
@@ -81,5 +81,5 @@ def test_cli_runs_both_apps_and_round_trips_checkpoints(tmp_path):
     assert a["position_checksum"] == b["position_checksum"] and a["kinetic_energy"] == b["kinetic_energy"]
     raw = open(tmp_path / "d" / "step000003.bin", "rb").read()
     assert raw[:7] == b"PSDUMP1" and len(raw) == 24 + 16 * 5324
-    bad = subprocess.run([CLI, "--app", "cpu", "--scene", "v"], capture_output=True, text=True)
-    assert bad.returncode == 1 and "FluidEmitter" in bad.stderr
+    bad = subprocess.run([CLI, "--app", "cpu", "--scene", "x"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "unknown scene" in bad.stderr

@@ -50,7 +50,10 @@ def test_built_scene_is_the_reference_scene(name):
     sim.close()
 
 
-@pytest.mark.parametrize("name", SCENES)
+# volcano_freezing is the same built scene as volcano, restarted after 240 ticks of splashing fluid with emission and freezing
+# events: from the built scene that far is a chaotic trajectory (rounding differences flip a freeze by a tick); its restart
+# state is compared tick by tick in tests/test_gpu_2d_full.py instead
+@pytest.mark.parametrize("name", [s for s in SCENES if s != "volcano_freezing"])
 def test_built_scene_ticks_like_the_reference(name):
     sim = psb.Simulation2D.scene(str(G[f"{name}_key"]))
     t0 = int(G[f"{name}_t0"])
@@ -69,9 +72,7 @@ def test_built_scene_ticks_like_the_reference(name):
     sim.close()
 
 
-def test_unknown_and_unsupported_scenes():
+def test_unknown_scene_key():
     with pytest.raises(psb.PsError, match="unknown scene"):
         psb.Simulation2D.scene("x")
-    with pytest.raises(psb.PsError, match="FluidEmitter"):
-        psb.Simulation2D.scene("v")
     assert psb.lib().ps2d_scene_name(b"6") == b"FLUID_TEST"
