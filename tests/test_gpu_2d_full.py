@@ -1,6 +1,6 @@
 """SURVEY §8 row a19 on the GPU: the general 2-D double-precision path (include/psolver2d.h — contacts, rigid SDF contacts
 with friction, walls, distance constraints, shape matching, fluid / gas constraints with solid coupling, smoke emitter)
-against the states the reference's own unmodified CPU solver wrote for 14 of its scenes (tests/golden/ref_cpu_scenes.npz),
+against the states the reference's own unmodified CPU solver wrote for all of its key-bound scenes (tests/golden/ref_cpu_scenes.npz),
 each started from a full restart state of the reference.
 
 Tolerances (double precision; the level-scheduled lists execute the reference's update sequence per particle, so the GPU
