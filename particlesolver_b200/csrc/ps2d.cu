@@ -1226,7 +1226,9 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
 }
 
 extern "C" int ps2d_download(Ps2dCtx *c, int which, void *host) {
-    if (!c || !host) { ps_set_error("ps2d_download: null argument"); return PS_ERR_INVALID; }
+    if (!c) { ps_set_error("ps2d_download: null context"); return PS_ERR_INVALID; }
+    if (c->n == 0) return PS_OK;  // nothing to copy (host may be NULL)
+    if (!host) { ps_set_error("ps2d_download: null argument"); return PS_ERR_INVALID; }
     CU2(cudaSetDevice(c->device));
     const void *src = nullptr;
     size_t bytes = (size_t)c->n * 16;
@@ -1256,6 +1258,8 @@ extern "C" int ps2d_download(Ps2dCtx *c, int which, void *host) {
 
 extern "C" int ps2d_kinetic_energy(Ps2dCtx *c, double *out) {
     if (!c || !out) return PS_ERR_INVALID;
+    *out = 0.;
+    if (c->n == 0) return PS_OK;
     std::vector<double> v((size_t)c->n * 2);
     int r = ps2d_download(c, PS2D_ARR_V, v.data());
     if (r != PS_OK) return r;

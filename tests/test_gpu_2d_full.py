@@ -111,3 +111,40 @@ def test_errors_like_the_reference():
     with pytest.raises(psb.PsError, match="phase"):
         sim.addFluidConstraint([first], 1.0)
     sim.close()
+
+
+def test_edge_cases_empty_single_and_capacity():
+    sim = psb.Simulation2D(max_particles=4)
+    sim.tick(.01)                                            # empty: no-op, like the reference's loops over an empty list
+    assert sim.getNumParticles() == 0 and sim.getKineticEnergy() == 0.0
+    first = sim.addParticles([[0.0, 5.0]], phase=[0])
+    assert first == 0
+    sim.tick(.01)                                            # one free SOLID particle: v += g dt, p += v dt
+    assert np.allclose(sim.velocities(), [[0.0, -0.098]]) and np.allclose(sim.positions(), [[0.0, 5.0 - 0.00098]])
+    sim.addParticles([[1.0, 5.0], [2.0, 5.0], [3.0, 5.0]], phase=[0, 0, 0])
+    with pytest.raises(psb.PsError, match="exceeds max_particles"):
+        sim.addParticles([[4.0, 5.0]], phase=[0])
+    sim.close()
+
+
+def test_more_contacts_than_slots_is_reported_not_truncated():
+    """PS2D_MAX_CONTACTS (14) partners per particle: discs of one size cannot exceed 6 touching neighbours unless they
+    overlap heavily; 20 coincident-ish particles do, and the tick must fail loudly instead of dropping constraints"""
+    rng = np.random.default_rng(0)
+    sim = psb.Simulation2D(x_bounds=(-50, 50), y_bounds=(-50, 50))
+    sim.addParticles(rng.uniform(-0.05, 0.05, (20, 2)) + [0.0, 10.0], phase=np.zeros(20, np.int32))
+    with pytest.raises(psb.PsError, match="PS2D_MAX_CONTACTS"):
+        sim.tick(.01)
+    sim.close()
+
+
+def test_resting_particle_sleeps_and_wall_clamps_like_the_reference():
+    """confirmGuess: a move shorter than EPSILON zeroes the velocity and keeps p (particle.h:60-65); walls clamp to
+    boundary + radius (boundaryconstraint.cpp:29-66)"""
+    sim = psb.Simulation2D(x_bounds=(-5, 5), y_bounds=(0, 100), gravity=(0.0, 0.0))
+    sim.addParticles([[0.0, 10.0], [4.9, 10.0]], velocities=[[0.005, 0.0], [3.0, 0.0]], phase=[0, 0])
+    sim.tick(.01)
+    p, v = sim.positions(), sim.velocities()
+    assert np.array_equal(p[0], [0.0, 10.0]) and np.array_equal(v[0], [0.0, 0.0])     # moved 5e-5 < 1e-4: asleep
+    assert p[1, 0] == 5 - 0.25 and abs(v[1, 0] - (4.75 - 4.9) / .01) < 1e-12             # pushed back inside the right wall
+    sim.close()
