@@ -50,9 +50,10 @@ typedef struct PsParams {
     uint32_t solver_iterations;  /* 5           particleapp.cpp:38 */
     float omega;                 /* SOR factor on the Jacobi-averaged deltas; 1.0 == reference */
     uint32_t flags;              /* PS_FLAG_* */
-    uint32_t neighbor_list_rows; /* rows (of 32 interleaved lists) per warp kept between the two PBF passes: 128 B x rows per 32
-                                    particles; 256 holds ~210 neighbours per particle, a warp that needs more falls back to a second
-                                    grid walk (results identical); 0 = keep no lists.  Multiple of 8. */
+    uint32_t neighbor_list_rows; /* neighbour lists kept between the two PBF passes: rows (128 B: one entry for each of a warp's 32
+                                    particles) of a pool shared by all warps, per warp ON AVERAGE — 256 = 1 KB per particle.  A warp
+                                    takes 48-row chunks as it goes, up to 1488 rows; one that needs more, or finds the pool empty, falls
+                                    back to a second grid walk (results identical).  0 = keep no lists.  Multiple of 8. */
 } PsParams;
 
 #define PS_FLAG_NONE 0u
@@ -79,7 +80,9 @@ enum {
     PS_ARR_NUM_NEIGHBORS = 14, /* uint[n] by sorted slot integration.cu:30 */
     PS_ARR_RANDS = 15,       /* float[iterations*6] wall-jitter uniforms of the last step */
     PS_ARR_OCCURRENCES = 16, /* uint[n]    solver.cu:41 */
-    PS_ARR_CELL_BEGIN = 17   /* uint[cells+1] dense lower-bound table (internal; exposed for tests) */
+    PS_ARR_CELL_BEGIN = 17,  /* uint[cells+1] dense lower-bound table (internal; exposed for tests) */
+    PS_ARR_NEIGHBOR_ROWS = 18 /* uint[32 * ceil(n/32)] per-warp list records of the last lambda pass (diagnostics): word 0 = rows used,
+                                 0xffffffff = the warp overflowed and its delta-p pass walks the grid again; words 1..31 = pool chunks */
 };
 
 void ps_default_params(PsParams *p);

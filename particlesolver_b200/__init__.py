@@ -26,12 +26,12 @@ NUM_STAGES = 12
 
 (ARR_POS, ARR_VEL, ARR_PREV, ARR_INV_MASS, ARR_PHASE, ARR_REST_DENSITY, ARR_HASH, ARR_INDEX, ARR_CELL_START, ARR_CELL_END,
  ARR_SORTED_POS, ARR_SORTED_INV_MASS, ARR_SORTED_PHASE, ARR_LAMBDA, ARR_NUM_NEIGHBORS, ARR_RANDS, ARR_OCCURRENCES,
- ARR_CELL_BEGIN) = range(18)
+ ARR_CELL_BEGIN, ARR_NEIGHBOR_ROWS) = range(19)
 _ARR_DTYPE = {ARR_POS: np.float32, ARR_VEL: np.float32, ARR_PREV: np.float32, ARR_INV_MASS: np.float32, ARR_PHASE: np.int32,
               ARR_REST_DENSITY: np.float32, ARR_HASH: np.uint32, ARR_INDEX: np.uint32, ARR_CELL_START: np.uint32,
               ARR_CELL_END: np.uint32, ARR_SORTED_POS: np.float32, ARR_SORTED_INV_MASS: np.float32, ARR_SORTED_PHASE: np.int32,
               ARR_LAMBDA: np.float32, ARR_NUM_NEIGHBORS: np.uint32, ARR_RANDS: np.float32, ARR_OCCURRENCES: np.uint32,
-              ARR_CELL_BEGIN: np.uint32}
+              ARR_CELL_BEGIN: np.uint32, ARR_NEIGHBOR_ROWS: np.uint32}
 _ARR_WIDTH = {ARR_POS: 4, ARR_VEL: 4, ARR_PREV: 4, ARR_SORTED_POS: 4}
 
 
@@ -376,6 +376,8 @@ class Solver:
             return self.num_cells + 1
         if which == ARR_RANDS:
             return int(self.params.solver_iterations) * 6
+        if which == ARR_NEIGHBOR_ROWS:
+            return 32 * ((self.n + 31) // 32) if self.params.neighbor_list_rows else 0
         return self.n * _ARR_WIDTH.get(which, 1)
 
     def download(self, which, out=None):

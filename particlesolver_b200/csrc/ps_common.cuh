@@ -29,6 +29,8 @@ typedef uint32_t u32;
 #define PS_K_FRICTION .0002f
 
 #define PS_MAX_RAD 8
+#define PS_LIST_CHUNK_ROWS 48   // neighbour-list pool: rows per chunk
+#define PS_LIST_RECORD_WORDS 32 // per-warp list record: rows used + 31 chunk ids (1488 rows: lanes capped at 500 neighbours fill unevenly)
 
 // uniform grid descriptor, passed by value (kernel parameter space == constant bank, one per launch, so
 // several contexts can coexist; the reference uses a single __constant__ SimParams, integration_kernel.cuh:55)
@@ -115,7 +117,11 @@ void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool 
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                        const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, cudaStream_t s);
 // nbr_list / nbr_rows: interleaved per-warp neighbour lists written by K6 and consumed by K7 (nullptr: K7 re-walks the grid)
-size_t ps_neighbor_list_elems(unsigned long long capacity, u32 max_rows);
+// (in the launchers below `max_rows` is the number of chunks in the pool, ps_neighbor_pool_chunks, and `nbr_rows` the first
+// per-warp record of the buffer sized by ps_neighbor_record_elems)
+u32 ps_neighbor_pool_chunks(unsigned long long capacity, u32 rows_per_warp);
+size_t ps_neighbor_list_elems(unsigned long long capacity, u32 rows_per_warp);
+size_t ps_neighbor_record_elems(unsigned long long capacity);
 void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                             const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
                             const StencilDesc &st, bool zero_nonfluid, u32 *nbr_list, u32 *nbr_rows, u32 max_rows, cudaStream_t s);

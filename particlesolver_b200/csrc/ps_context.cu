@@ -64,7 +64,7 @@ extern "C" void ps_default_params(PsParams *p) {
     p->solver_iterations = 5;
     p->omega = 1.0f;
     p->flags = PS_FLAG_NONE;
-    p->neighbor_list_rows = 256;
+    p->neighbor_list_rows = 256;  // rows of the shared pool per warp ON AVERAGE (1 KB per particle); a warp may take up to 1488
 }
 
 static bool is_pow2(u32 v) { return v && !(v & (v - 1)); }
@@ -134,6 +134,23 @@ static int grow(T **p, uint64_t old_n, uint64_t new_n, cudaStream_t s, bool zero
     return PS_OK;
 }
 
+// neighbour-list row pool + per-warp records for `cap` particles (ps_neighbor_kernels.cu); params.neighbor_list_rows rows per
+// warp on average, 0 = no lists
+int ps_ctx_alloc_lists(PsCtx *c, uint64_t cap) {
+    if (c->nbr_list) { CU(cudaFree(c->nbr_list)); c->nbr_list = nullptr; }
+    if (c->nbr_rows) { CU(cudaFree(c->nbr_rows - 4)); c->nbr_rows = nullptr; }
+    c->nbr_max_rows = 0;
+    if (!c->params.neighbor_list_rows || !cap) return PS_OK;
+    c->nbr_max_rows = ps_neighbor_pool_chunks(cap, c->params.neighbor_list_rows);
+    if (!c->nbr_max_rows) return PS_OK;
+    u32 *rec = nullptr;
+    CU(cudaMalloc((void **)&c->nbr_list, ps_neighbor_list_elems(cap, c->params.neighbor_list_rows) * sizeof(u32)));
+    CU(cudaMalloc((void **)&rec, ps_neighbor_record_elems(cap) * sizeof(u32)));
+    CU(cudaMemsetAsync(rec, 0, ps_neighbor_record_elems(cap) * sizeof(u32), c->stream));
+    c->nbr_rows = rec + 4;
+    return PS_OK;
+}
+
 int ps_ctx_ensure_capacity(PsCtx *c, uint64_t want) {
     if (want <= c->capacity) return PS_OK;
     uint64_t cap = std::max<uint64_t>(want, c->capacity ? c->capacity * 2 : 1024);
@@ -149,12 +166,7 @@ int ps_ctx_ensure_capacity(PsCtx *c, uint64_t want) {
     G(hash, true) G(index, true) G(hash_tmp, true) G(index_tmp, true) G(num_neighbors, true) G(occ, true)
 #undef G
     c->capacity = cap;
-    if (c->nbr_list) { CU(cudaFree(c->nbr_list)); CU(cudaFree(c->nbr_rows)); c->nbr_list = c->nbr_rows = nullptr; }
-    c->nbr_max_rows = c->params.neighbor_list_rows;
-    if (c->nbr_max_rows) {
-        CU(cudaMalloc((void **)&c->nbr_list, ps_neighbor_list_elems(cap, c->nbr_max_rows) * sizeof(u32)));
-        CU(cudaMalloc((void **)&c->nbr_rows, ((cap + 31) / 32) * sizeof(u32)));
-    }
+    if ((r = ps_ctx_alloc_lists(c, cap)) != PS_OK) return r;
     // sort look-back status words for the largest n this capacity allows
     size_t need = ps_sort_status_elems((u32)cap, 4);
     if (need > c->sort_status_elems) {
@@ -253,7 +265,7 @@ extern "C" int ps_destroy(PsCtx *c) {
     if (c->gen) curandDestroyGenerator(c->gen);
     void *ptrs[] = {c->pos, c->vel, c->prev, c->spos, c->w, c->ros, c->sw, c->lambda, c->phase, c->sphase, c->hash, c->index, c->hash_tmp,
                     c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->chunk_lb,
-                    c->sort_status, c->rands, c->slab_scratch, c->nbr_list, c->nbr_rows, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
+                    c->sort_status, c->rands, c->slab_scratch, c->nbr_list, c->nbr_rows ? c->nbr_rows - 4 : nullptr, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
                     c->d_point_xyz, c->dist_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     ps_ext_free(c);
@@ -278,12 +290,9 @@ extern "C" int ps_set_params(PsCtx *c, const PsParams *p) {
     if ((r = ps_ctx_ensure_cells(c)) != PS_OK) return r;
     if (rows_changed) {
         CU(cudaStreamSynchronize(c->stream));
-        if (c->nbr_list) { CU(cudaFree(c->nbr_list)); CU(cudaFree(c->nbr_rows)); c->nbr_list = c->nbr_rows = nullptr; }
-        c->nbr_max_rows = p->neighbor_list_rows;
-        if (c->nbr_max_rows) {
-            CU(cudaMalloc((void **)&c->nbr_list, ps_neighbor_list_elems(c->capacity, c->nbr_max_rows) * sizeof(u32)));
-            CU(cudaMalloc((void **)&c->nbr_rows, ((c->capacity + 31) / 32) * sizeof(u32)));
-        }
+        c->params.neighbor_list_rows = p->neighbor_list_rows;
+        int lr = ps_ctx_alloc_lists(c, c->capacity);
+        if (lr != PS_OK) return lr;
     }
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     c->grid_valid = false;
@@ -712,6 +721,7 @@ static ArrInfo arr_info(PsCtx *c, int which) {
         case PS_ARR_RANDS: return {c->rands, 4, (uint64_t)c->params.solver_iterations * 6};
         case PS_ARR_OCCURRENCES: return {c->occ, 4, n};
         case PS_ARR_CELL_BEGIN: return {c->cell_begin, 4, cells + 1};
+        case PS_ARR_NEIGHBOR_ROWS: return {c->nbr_rows, 4, c->nbr_rows ? ((n + 31) / 32) * PS_LIST_RECORD_WORDS : 0};
         default: return {nullptr, 0, 0};
     }
 }

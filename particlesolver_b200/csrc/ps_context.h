@@ -32,7 +32,8 @@ struct PsCtx {
     float *w = nullptr, *ros = nullptr, *sw = nullptr, *lambda = nullptr;
     int *phase = nullptr, *sphase = nullptr;
     u32 *hash = nullptr, *index = nullptr, *hash_tmp = nullptr, *index_tmp = nullptr, *num_neighbors = nullptr, *occ = nullptr;
-    // neighbour lists between K6 and K7 (ps_neighbor_kernels.cu); nbr_rows[warp] = rows used or overflow mark
+    // neighbour lists between K6 and K7 (ps_neighbor_kernels.cu): row pool, per-warp records (rows used or overflow mark, chunk
+    // ids; the pool's bump allocator sits 4 words before the first record), number of chunks in the pool
     u32 *nbr_list = nullptr, *nbr_rows = nullptr;
     u32 nbr_max_rows = 0;
     // per-cell state
@@ -93,6 +94,7 @@ struct PsCtx {
 // internal helpers shared with the reference-ABI shim
 int ps_create_internal(int device, const PsParams *params, uint64_t max_particles, bool legacy_default_stream, PsCtx **out);
 int ps_ctx_ensure_capacity(PsCtx *c, uint64_t want);
+int ps_ctx_alloc_lists(PsCtx *c, uint64_t cap);
 int ps_ctx_ensure_cells(PsCtx *c);
 int ps_ctx_emit_reference_tables(PsCtx *c);
 int ps_ctx_sync_constraints(PsCtx *c);

@@ -84,22 +84,33 @@ __device__ __forceinline__ void for_each_candidate(const GridDesc &g, const Sten
 //
 // Neighbour lists.  NOT the reference's (500 slots = 2 KB per particle, 4x over-allocated, strided by thread,
 // integration.cu:70): a warp's 32 lists are interleaved, row r of warp w is the 128-byte line
-// list[(w * max_rows + r) * 32 + lane], and the warp appends in lock-step — every queue flush writes kQ full rows, lanes
+// row[r * 32 + lane], and the warp appends in lock-step — every queue flush writes kQ full rows, lanes
 // with fewer accepted neighbours pad with kNoNeighbor.  Writes and K7's reads are therefore fully coalesced, ~170 rows
-// (21 KB per warp, 0.7 KB per particle) for ~140 neighbours.  A warp that would need more than max_rows rows marks itself
-// overflowed and K7 re-walks the grid for it (k_solve_fluids below), so the result never depends on max_rows.
+// (21 KB per warp, 0.7 KB per particle) for ~140 neighbours.  Rows live in a POOL shared by all warps: a warp takes chunks
+// of kChunkRows rows from a bump allocator as it goes (its chunk ids sit beside its row count, kListRecord words per warp),
+// so memory follows the actual list lengths — a warp in a compressed layer on the floor may hold 4x the rows of one in the
+// bulk (lanes pad to the warp's longest list) without any per-warp reservation.  A warp that needs more than
+// kMaxChunks chunks, or finds the pool empty, marks itself overflowed and K7 re-walks the grid for it (k_solve_fluids
+// below), so the result never depends on the pool size.
 constexpr int kQ = PS_KQ;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr u32 kNoNeighbor = 0xffffffffu, kListOverflow = 0xffffffffu;
+constexpr u32 kChunkRows = PS_LIST_CHUNK_ROWS;         // 48: a multiple of kQ (a flush never straddles chunks) and of 4 (K7 reads 4 rows at a time)
+constexpr u32 kListRecord = PS_LIST_RECORD_WORDS;      // per warp: [rows used | overflow mark, chunk id 0, chunk id 1, ...]
+constexpr u32 kMaxChunks = kListRecord - 1;            // 31 chunks = 1488 rows
+static_assert(kChunkRows % PS_KQ == 0 && kChunkRows % 4 == 0, "chunk size");
 typedef unsigned short u16;
 
 static inline size_t fluid_smem_bytes(int rad) {
     return (size_t)kQ * kBlock * sizeof(u32) + (size_t)2 * (2 * rad + 1) * kBlock * (sizeof(u32) + sizeof(u16));
 }
 
-struct NeighborListWriter {  // per-warp view of the list being written by K6 (list == nullptr: no list)
-    u32 *list;               // this lane's column of the warp's block: row r at list[r * 32]
-    u32 max_rows, rows;
+struct NeighborListWriter {  // per-warp view of the list being written by K6 (pool == nullptr: no list)
+    u32 *pool;               // row pool; the bump allocator's counter sits at rec_base[-4] (see ps_launch_find_lambdas)
+    u32 *rec;                // this warp's record: rows, chunk ids
+    u32 *next;               // bump allocator
+    u32 *cur;                // this lane's column of the warp's current chunk: row r of the chunk at cur[r * 32]
+    u32 pool_chunks, rows;
     bool overflow;
 };
 
@@ -136,13 +147,26 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
     int cnt = 0;
 
     auto flush = [&]() {
-        if (nl.list) {  // kQ full rows of the warp's interleaved list (uniform branch)
-            if (nl.rows + kQ <= nl.max_rows) {
+        if (nl.pool && !nl.overflow) {  // kQ full rows of the warp's interleaved list (uniform branches)
+            const u32 in_chunk = nl.rows % kChunkRows;
+            if (in_chunk == 0) {  // the warp needs its next chunk
+                const u32 ci = nl.rows / kChunkRows;
+                u32 chunk = 0xffffffffu;
+                if (ci < kMaxChunks) {
+                    if ((tid & 31) == 0) chunk = atomicAdd(nl.next, 1u);
+                    chunk = __shfl_sync(kFull, chunk, 0);
+                }
+                if (chunk >= nl.pool_chunks) {
+                    nl.overflow = true;
+                } else {
+                    if ((tid & 31) == 0) nl.rec[1 + ci] = chunk;
+                    nl.cur = nl.pool + (size_t)chunk * (kChunkRows * 32) + (tid & 31);
+                }
+            }
+            if (!nl.overflow) {
 #pragma unroll
-                for (int k = 0; k < kQ; k++) nl.list[(nl.rows + k) * 32] = k < cnt ? q[k][tid] : kNoNeighbor;
+                for (int k = 0; k < kQ; k++) nl.cur[(in_chunk + k) * 32] = k < cnt ? q[k][tid] : kNoNeighbor;
                 nl.rows += kQ;
-            } else {
-                nl.overflow = true;
             }
         }
 #if PS_FLUSH_PREFETCH
@@ -316,7 +340,7 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
     const bool ghost = act && orig >= n_owned;
     if (ghost && !(pi.x >= ghost_xmin && pi.x <= ghost_xmax)) act = false;
     if (!__any_sync(kFull, act)) {
-        if (nbr_rows && lane == 0 && (u64)warp * 32 < n) nbr_rows[warp] = 0;
+        if (nbr_rows && lane == 0 && (u64)warp * 32 < n) nbr_rows[(size_t)warp * kListRecord] = 0;
         return;
     }
     if (!act) pi = make_float4(g.ox, g.oy, g.oz, 0.f);
@@ -324,8 +348,8 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
     const float inv_ro0 = __fdividef(1.f, ro0);
     const float cs = -PS_SPIKY * inv_ro0;
     NeighborListWriter nl;
-    nl.list = nbr_list ? nbr_list + ((size_t)warp * max_rows) * 32 + lane : nullptr;
-    nl.max_rows = max_rows; nl.rows = 0; nl.overflow = false;
+    nl.pool = nbr_list; nl.rec = nbr_rows ? nbr_rows + (size_t)warp * kListRecord : nullptr; nl.next = nbr_rows ? nbr_rows - 4 : nullptr; nl.cur = nullptr;
+    nl.pool_chunks = max_rows; nl.rows = 0; nl.overflow = false;
 
     float ro = 0.f, denom = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
     const u32 nn = walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, nl, [&](float rx, float ry, float rz, u32) {
@@ -340,7 +364,7 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
         gx += rx * c; gy += ry * c; gz += rz * c;
         denom += (c * c) * r2;
     });
-    if (nbr_rows && lane == 0) nbr_rows[warp] = nl.overflow ? kListOverflow : nl.rows;
+    if (nbr_rows && lane == 0) nl.rec[0] = nl.overflow ? kListOverflow : nl.rows;
     if (!act) return;
     const float inv_w = __fdividef(1.f, sw[i]);
     ro = (ro + PS_H6) * (PS_POLY6 * inv_w);  // + self term poly6(0) = POLY6 * H^6 (integration_kernel.cuh:589)
@@ -390,20 +414,23 @@ __global__ void __launch_bounds__(kListBlock) k_solve_fluids_list(float4 *__rest
     const u32 i = blockIdx.x * kListBlock + threadIdx.x;
     if (i >= n) return;
     const u32 warp = i >> 5;
-    const u32 rows = nbr_rows[warp];
+    const u32 *rec = nbr_rows + (size_t)warp * kListRecord;
+    const u32 rows = rec[0];
     if (rows == kListOverflow || rows == 0) return;  // overflowed warps are redone by k_solve_fluids
     if (sphase[i] != PH_FLUID) return;
     const u32 orig = index[i];
     if (orig >= n_owned) return;
     const float4 pi = spos[i];
     DeltaP f{lambda[i], delta_p_inv_den(), 0.f, 0.f, 0.f, lambda};
-    const u32 *L = nbr_list + ((size_t)warp * max_rows) * 32 + (threadIdx.x & 31);
+    const u32 *L = nbr_list;
     u32 nn = 0;
-    for (u32 r = 0; r < rows; r += 4) {  // rows is a multiple of kQ (4 or 8 ...)
+    for (u32 r = 0, rc = 0; r < rows; r += 4, rc += 4) {  // rows is a multiple of kQ, chunks of 4
+        if (rc == kChunkRows) rc = 0;
+        if (rc == 0) L = nbr_list + (size_t)__ldg(rec + 1 + r / kChunkRows) * (kChunkRows * 32) + (threadIdx.x & 31);
         u32 j[4];
         float4 pj[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) j[k] = __ldg(L + (r + k) * 32);
+        for (int k = 0; k < 4; k++) j[k] = __ldg(L + (rc + k) * 32);
 #pragma unroll
         for (int k = 0; k < 4; k++) pj[k] = __ldg(spos + (j[k] != kNoNeighbor ? j[k] : i));
 #pragma unroll
@@ -428,7 +455,7 @@ __global__ void __launch_bounds__(kBlock) k_solve_fluids(float4 *__restrict__ po
                                                          float omega, const u32 *__restrict__ nbr_rows) {
     extern __shared__ u32 fluid_smem[];
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (nbr_rows && ((u64)(i >> 5) * 32 >= n || nbr_rows[i >> 5] != kListOverflow)) return;  // warp-uniform
+    if (nbr_rows && ((u64)(i >> 5) * 32 >= n || nbr_rows[(size_t)(i >> 5) * kListRecord] != kListOverflow)) return;  // warp-uniform
     bool act = i < n && sphase[i] == PH_FLUID;
     u32 orig = 0;
     if (act) {
@@ -439,7 +466,7 @@ __global__ void __launch_bounds__(kBlock) k_solve_fluids(float4 *__restrict__ po
     const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
     DeltaP f{act ? lambda[i] : 0.f, delta_p_inv_den(), 0.f, 0.f, 0.f, lambda};
     NeighborListWriter nl;
-    nl.list = nullptr; nl.max_rows = 0; nl.rows = 0; nl.overflow = false;
+    nl.pool = nullptr; nl.rec = nullptr; nl.next = nullptr; nl.cur = nullptr; nl.pool_chunks = 0; nl.rows = 0; nl.overflow = false;
     const u32 nn = walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, nl, f);
     if (!act) return;
     const float inv_div = __fdividef(omega, ros[orig] + (float)nn);
@@ -516,18 +543,21 @@ __global__ void __launch_bounds__(kListBlock) k_fluid_pass_list(Op op, const flo
     const u32 i = blockIdx.x * kListBlock + threadIdx.x;
     if (i >= n) return;
     const u32 warp = i >> 5;
-    const u32 rows = nbr_rows[warp];
+    const u32 *rec = nbr_rows + (size_t)warp * kListRecord;
+    const u32 rows = rec[0];
     if (rows == kListOverflow) return;  // redone by k_fluid_pass_walk
     if (sphase[i] != PH_FLUID) return;
     const u32 orig = index[i];
     const float4 pi = spos[i];
     op.begin(i, orig);
-    const u32 *L = nbr_list + ((size_t)warp * max_rows) * 32 + (threadIdx.x & 31);
-    for (u32 r = 0; r < rows; r += 4) {
+    const u32 *L = nbr_list;
+    for (u32 r = 0, rc = 0; r < rows; r += 4, rc += 4) {
+        if (rc == kChunkRows) rc = 0;
+        if (rc == 0) L = nbr_list + (size_t)__ldg(rec + 1 + r / kChunkRows) * (kChunkRows * 32) + (threadIdx.x & 31);
         u32 j[4];
         float4 pj[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) j[k] = __ldg(L + (r + k) * 32);
+        for (int k = 0; k < 4; k++) j[k] = __ldg(L + (rc + k) * 32);
 #pragma unroll
         for (int k = 0; k < 4; k++) pj[k] = __ldg(spos + (j[k] != kNoNeighbor ? j[k] : i));
 #pragma unroll
@@ -542,14 +572,14 @@ __global__ void __launch_bounds__(kBlock) k_fluid_pass_walk(Op op, const float4 
                                                             StencilDesc st, const u32 *__restrict__ nbr_rows) {
     extern __shared__ u32 fluid_smem[];
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (nbr_rows && ((u64)(i >> 5) * 32 >= n || nbr_rows[i >> 5] != kListOverflow)) return;  // warp-uniform
+    if (nbr_rows && ((u64)(i >> 5) * 32 >= n || nbr_rows[(size_t)(i >> 5) * kListRecord] != kListOverflow)) return;  // warp-uniform
     const bool act = i < n && sphase[i] == PH_FLUID;
     if (!__any_sync(kFull, act)) return;
     const u32 orig = act ? index[i] : 0u;
     const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
     if (act) op.begin(i, orig);
     NeighborListWriter nl;
-    nl.list = nullptr; nl.max_rows = 0; nl.rows = 0; nl.overflow = false;
+    nl.pool = nullptr; nl.rec = nullptr; nl.next = nullptr; nl.cur = nullptr; nl.pool_chunks = 0; nl.rows = 0; nl.overflow = false;
     walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, nl, op);
     if (act) op.end(i, orig);
 }
@@ -664,7 +694,12 @@ void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, cons
     k_collide<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, prev, spos, sw, sphase, index, cell_begin, num_neighbors, n, n_owned, g, st, radius);
 }
 
-size_t ps_neighbor_list_elems(u64 capacity, u32 max_rows) { return (size_t)((capacity + 31) / 32) * max_rows * 32; }
+// pool of list rows for `capacity` particles at `rows_per_warp` rows reserved per warp on average
+u32 ps_neighbor_pool_chunks(u64 capacity, u32 rows_per_warp) { return (u32)(((capacity + 31) / 32) * rows_per_warp / kChunkRows); }
+size_t ps_neighbor_list_elems(u64 capacity, u32 rows_per_warp) { return (size_t)ps_neighbor_pool_chunks(capacity, rows_per_warp) * kChunkRows * 32; }
+// per-warp records (kListRecord words each) behind a 4-word header whose first word is the pool's bump allocator;
+// the kernels are handed the address of the first record
+size_t ps_neighbor_record_elems(u64 capacity) { return 4 + (size_t)((capacity + 31) / 32) * kListRecord; }
 
 void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                             const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
@@ -674,6 +709,7 @@ void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spo
     static const cudaError_t optin = cudaFuncSetAttribute(k_find_lambdas<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
     (void)optin;
     if (!nbr_list) nbr_rows = nullptr;
+    if (nbr_rows) cudaMemsetAsync(nbr_rows - 4, 0, sizeof(u32), s);  // empty the row pool
     if (st.rad == 4)  // the reference's configuration (H = 2, cell = 2r = 0.5): stencil loops fully unrolled
         k_find_lambdas<4><<<cdiv(n, kBlock), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin,
                                                              ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, max_rows);
