@@ -18,6 +18,7 @@ SCENES = [
     ("8", dict()),                 # combo: cloths, ropes, solids, pinned sphere (BASELINE config "GPU scene 8")
     ("1", dict()),                 # rope
     ("6", dict()),                 # solids falling on a held cloth
+    ("c2", dict(max_particles=66000, side=256)),  # BASELINE config C2 at full size: 256 x 256 cloth, 130,560 distance constraints
 ]
 
 
