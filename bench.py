@@ -114,14 +114,14 @@ def c3_sample(side, seed=1234):
     return pos
 
 
-def time_oracle_port(side, steps):
-    """particle-steps/s of the CPU port on a side^3 sample of the workload, all host threads."""
+def time_oracle_port(side, steps, rho0=1.5):
+    """particle-steps/s of the CPU port on a side^3 sample of the workload (c3: rho0 1.5; c5: rho0 4.1, same lattice), all host threads."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_py as orc
     pos = c3_sample(side)
     n = pos.shape[0]
     p = orc.make_params(grid=(GRID, GRID, GRID))
-    o = orc.OracleSystem(p, pos, np.zeros((n, 4), np.float32), np.ones(n, np.float32), np.zeros(n, np.int32), np.full(n, 1.5, np.float32),
+    o = orc.OracleSystem(p, pos, np.zeros((n, 4), np.float32), np.ones(n, np.float32), np.zeros(n, np.int32), np.full(n, rho0, np.float32),
                          iterations=ITERS)
     rands = np.full((ITERS, 6), 0.5, np.float32)
     o.step(DT, rands)  # warm-up (page faults, thread pool)
@@ -175,12 +175,14 @@ def run_reference(args, rank, world):
     steps = max(1, min(args.steps, 3))
     for _ in range(max(0, min(args.warmup, 1))):
         pass  # time_oracle_port warms up once itself
-    v, n, sec = time_oracle_port(side, steps)
+    c5 = args.gpus > 1 or args.workload == "c5"   # our arm runs the slab-decomposed dam break on several GPUs
+    v, n, sec = time_oracle_port(side, steps, rho0=C5_RHO0 if c5 else 1.5)
     line = {"metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": "c3: reference GPU scene 7 scaled, PBF fluid, 5 solver iterations, dt=1/60, 256^3 grid",
-                       "sample": f"{side}^3 = {n} particles of the 1,000,000 (same lattice, density, parameters)", "steps_timed": steps},
+            "config": {"workload": ("c5: synthetic PBF dam break (lattice spacing 2.5 r, rho0 4.1), 5 solver iterations, dt=1/60" if c5 else
+                                    "c3: reference GPU scene 7 scaled, PBF fluid, 5 solver iterations, dt=1/60, 256^3 grid"),
+                       "sample": f"{side}^3 = {n} particles of the workload's lattice (same spacing, density, parameters)", "steps_timed": steps},
             "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port",
                              "sample": f"oracle/gpu_step_oracle.c (C restatement of the reference GPU step, OpenMP) on {n} particles x {steps} steps"},
             "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
