@@ -117,6 +117,9 @@ def c3_sample(side, seed=1234):
 def time_oracle_port(side, steps, rho0=1.5):
     """particle-steps/s of the CPU port on a side^3 sample of the workload (c3: rho0 1.5; c5: rho0 4.1, same lattice), all host threads."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host thread (libgomp reads the
+    # variable when the oracle library is loaded, i.e. below)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import oracle_py as orc
     pos = c3_sample(side)
     n = pos.shape[0]
