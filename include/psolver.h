@@ -58,6 +58,9 @@ typedef struct PsParams {
 
 #define PS_FLAG_NONE 0u
 #define PS_FLAG_ZERO_NONFLUID_LAMBDA 1u /* deviation: lambda of non-fluid slots reads 0 instead of a stale value */
+#define PS_FLAG_GAS 2u /* not in the reference's GPU solver (its kernels ignore phase GAS): GAS particles take part in the
+                          fluid density constraint with their own rest density and rise — they are predicted with gravity x -0.2, the
+                          CPU app's ALPHA (cpu/src/simulation.h:21, simulation.cpp:144).  Parity unpinned in 3-D. */
 
 typedef struct PsCtx PsCtx;
 

@@ -27,6 +27,7 @@ typedef uint32_t u32;
 #define PS_DQ_P .2f
 #define PS_S_FRICTION .005f
 #define PS_K_FRICTION .0002f
+#define PS_GAS_ALPHA -.2f  // buoyancy of GAS particles (reference CPU app: ALPHA, cpu/src/simulation.h:21); only with PS_FLAG_GAS
 
 #define PS_MAX_RAD 8
 #define PS_LIST_CHUNK_ROWS 48   // neighbour-list pool: rows per chunk
@@ -83,7 +84,8 @@ __device__ __forceinline__ void st_stream4(float4 *p, float4 v) {
 
 // ---------------- launchers (host side, all asynchronous on `s`) ----------------
 // ps_stream_kernels.cu
-void ps_launch_predict(float4 *pos, const float4 *vel, float4 *prev, u32 n, float dt, float3 g, cudaStream_t s);
+// gas_phase != nullptr (PS_FLAG_GAS): phase array; GAS particles are predicted with gravity x PS_GAS_ALPHA
+void ps_launch_predict(float4 *pos, const float4 *vel, float4 *prev, u32 n, float dt, float3 g, cudaStream_t s, const int *gas_phase = nullptr);
 void ps_launch_velocity(const float4 *pos, const float4 *prev, float4 *vel, u32 n, float dt, cudaStream_t s);
 void ps_launch_collide_world(float4 *pos, const float4 *prev, const int *phase, u32 n, const float *rands6, WorldDesc w, cudaStream_t s);
 void ps_launch_point(float4 *pos, const u32 *pidx, const float *pxyz, u32 np, cudaStream_t s);
@@ -93,7 +95,7 @@ void ps_launch_distance(float4 *pos, float4 *scratch, const u32 *csr_particle, c
 void ps_launch_calc_hash(u32 *hash, u32 *index, const float4 *pos, u32 n, GridDesc g, cudaStream_t s);
 // K4: gather into sorted order + per-chunk lower bounds (chunk_lb[ps_chunk_table_elems(num_cells)])
 void ps_launch_reorder(float4 *spos, float *sw, int *sphase, u32 *chunk_lb, const u32 *hash, const u32 *index, const float4 *pos,
-                       const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s);
+                       const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s, bool gas_as_fluid = false);
 size_t ps_chunk_table_elems(u32 num_cells);
 // dense lower-bound table cell_begin[c] = #particles with key < c, c in [0,num_cells]; from the sorted keys + chunk_lb
 void ps_launch_cell_begin(u32 *cell_begin, const u32 *hash, const u32 *chunk_lb, u32 n, u32 num_cells, cudaStream_t s);

@@ -326,7 +326,7 @@ extern "C" int ps_append_particles(PsCtx *c, const float *pos4, const float *vel
     CU(cudaMemcpyAsync(c->ros + c->n, rest_density, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(c->phase + c->n, phase, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));  // host buffers may be stack arrays of the caller (the reference's builders are)
-    for (uint64_t k = 0; k < n; k++) { c->n_fluid += phase[k] == PH_FLUID; c->n_contact += phase[k] >= PH_CLOTH; }
+    for (uint64_t k = 0; k < n; k++) { c->n_fluid += phase[k] == PH_FLUID; c->n_gas += phase[k] == 1; c->n_contact += phase[k] >= PH_CLOTH; }
     c->n += (u32)n;
     c->h_occ.resize(c->n, 0u);
     c->constraints_dirty = true;
@@ -439,12 +439,17 @@ u32 ps_issue_build_grid(PsCtx *c, const float4 *pos) {
     u32 *kB = odd ? c->hash : c->hash_tmp, *vB = odd ? c->index : c->index_tmp;
     ps_launch_calc_hash(kA, nullptr, pos, n, c->grid, s);
     ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s);
-    ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, pos, c->w, c->phase, n, c->num_cells, s);
+    ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, pos, c->w, c->phase, n, c->num_cells, s, (c->params.flags & PS_FLAG_GAS) != 0);
     ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s);
     c->grid_valid = true;
     c->ref_tables_valid = false;
     // kernels only (the memset node of the sort is not counted): calc_hash 1 + hist 1 + passes + reorder 1 + cell_begin 1
     return 1 + 1 + (u32)c->sort_passes + 1 + 1;
+}
+
+// PS_FLAG_GAS and the scene holds (or may hold) GAS particles: the prediction reads the phases for their buoyancy
+const int *ps_ctx_gas_phase(PsCtx *c) {
+    return ((c->params.flags & PS_FLAG_GAS) && (!c->census_known || c->n_gas > 0)) ? c->phase : nullptr;
 }
 
 static int ready(PsCtx *c) {
@@ -476,7 +481,7 @@ extern "C" int ps_predict(PsCtx *c, float dt) {
     DeviceGuard dg(c->device);
     dt = std::min(dt, .05f);
     const PsParams &p = c->params;
-    ps_launch_predict(c->pos, c->vel, c->prev, c->n - c->n_ghost, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), c->stream);
+    ps_launch_predict(c->pos, c->vel, c->prev, c->n - c->n_ghost, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), c->stream, ps_ctx_gas_phase(c));
     return check_launch("ps_predict");
 }
 extern "C" int ps_build_grid(PsCtx *c) {
@@ -541,8 +546,8 @@ static u32 issue_step(PsCtx *c, float dt) {
     u32 launches = 0;
     // the phase census lets an all-fluid scene skip the contact pass and a fluid-free scene the two PBF passes
     // (both kernels would only read every phase and return)
-    const bool has_contact = !c->census_known || c->n_contact > 0, has_fluid = !c->census_known || c->n_fluid > 0;
-    ps_launch_predict(c->pos, c->vel, c->prev, n_owned, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), s);
+    const bool has_contact = !c->census_known || c->n_contact > 0, has_fluid = !c->census_known || c->n_fluid > 0 || ((c->params.flags & PS_FLAG_GAS) && c->n_gas > 0);
+    ps_launch_predict(c->pos, c->vel, c->prev, n_owned, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), s, ps_ctx_gas_phase(c));
     launches++;
     for (u32 it = 0; it < p.solver_iterations; it++) {
         launches += ps_issue_build_grid(c, c->pos);
@@ -622,7 +627,7 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
     cudaStream_t s = c->stream;
     const u32 n = c->n;
     const u32 iters = p.solver_iterations;
-    const bool has_contact = !c->census_known || c->n_contact > 0, has_fluid = !c->census_known || c->n_fluid > 0;
+    const bool has_contact = !c->census_known || c->n_contact > 0, has_fluid = !c->census_known || c->n_fluid > 0 || ((c->params.flags & PS_FLAG_GAS) && c->n_gas > 0);
     const int max_marks = 4 + (int)iters * 17;
     std::vector<cudaEvent_t> ev(max_marks);
     std::vector<int> tag(max_marks, -1);
@@ -630,14 +635,14 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
     int m = 0;
     auto mark = [&](int stage, u32 launches) { cudaEventRecord(ev[m], s); tag[m] = stage; if (stage >= 0 && stage_launches) stage_launches[stage] += launches; m++; };
     mark(-1, 0);
-    ps_launch_predict(c->pos, c->vel, c->prev, n, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), s); mark(0, 1);
+    ps_launch_predict(c->pos, c->vel, c->prev, n, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), s, ps_ctx_gas_phase(c)); mark(0, 1);
     const bool odd = (c->sort_passes & 1) != 0;
     u32 *kA = odd ? c->hash_tmp : c->hash, *vA = odd ? c->index_tmp : c->index;
     u32 *kB = odd ? c->hash : c->hash_tmp, *vB = odd ? c->index : c->index_tmp;
     for (u32 it = 0; it < iters; it++) {
         ps_launch_calc_hash(kA, nullptr, c->pos, n, c->grid, s); mark(1, 1);
         ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s); mark(2, 1 + c->sort_passes);
-        ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, c->pos, c->w, c->phase, n, c->num_cells, s); mark(3, 1);
+        ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, c->pos, c->w, c->phase, n, c->num_cells, s, (p.flags & PS_FLAG_GAS) != 0); mark(3, 1);
         ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s); mark(4, 1);
         c->grid_valid = true;
         c->ref_tables_valid = false;

@@ -25,7 +25,7 @@ struct PsCtx {
     // phase census of the appended particles, so that a step skips the contact pass of an all-fluid scene and the
     // fluid passes of a scene without fluid; unknown after a raw phase upload (then nothing is skipped)
     bool census_known = true;
-    u32 n_fluid = 0, n_contact = 0;  // phase == FLUID, phase >= CLOTH
+    u32 n_fluid = 0, n_contact = 0, n_gas = 0;  // phase == FLUID, phase >= CLOTH, phase == GAS
 
     // per-particle state (SoA).  pos may be caller-owned in the reference-ABI shim, hence the indirection.
     float4 *pos = nullptr, *vel = nullptr, *prev = nullptr, *spos = nullptr;
@@ -95,6 +95,7 @@ struct PsCtx {
 int ps_create_internal(int device, const PsParams *params, uint64_t max_particles, bool legacy_default_stream, PsCtx **out);
 int ps_ctx_ensure_capacity(PsCtx *c, uint64_t want);
 int ps_ctx_alloc_lists(PsCtx *c, uint64_t cap);
+const int *ps_ctx_gas_phase(PsCtx *c);
 int ps_ctx_ensure_cells(PsCtx *c);
 int ps_ctx_emit_reference_tables(PsCtx *c);
 int ps_ctx_sync_constraints(PsCtx *c);

@@ -35,7 +35,8 @@ static_assert((1 << kChunkShift) == kCellsPerBlock, "chunk size");
 __global__ void __launch_bounds__(kBlock) k_reorder(float4 *__restrict__ spos, float *__restrict__ sw, int *__restrict__ sphase,
                                                     u32 *__restrict__ chunk_lb, const u32 *__restrict__ hash,
                                                     const u32 *__restrict__ index, const float4 *__restrict__ pos,
-                                                    const float *__restrict__ w, const int *__restrict__ phase, u32 n, u32 num_chunks) {
+                                                    const float *__restrict__ w, const int *__restrict__ phase, u32 n, u32 num_chunks,
+                                                    int gas_as_fluid) {
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
     const bool ok = i < n;
     const int lane = threadIdx.x & 31;
@@ -51,7 +52,9 @@ __global__ void __launch_bounds__(kBlock) k_reorder(float4 *__restrict__ spos, f
         k0 = i > 0 ? (hash[i - 1] >> kChunkShift) + 1 : 0;
         st_stream4(spos + i, p);
         sw[i] = wi;
-        sphase[i] = ph;
+        // PS_FLAG_GAS: GAS particles take part in the density constraint — the neighbour kernels see them as fluid (the
+        // reference's GPU kernels ignore phase 1 altogether; its CPU app solves gas as a PBF fluid, gasconstraint.cpp)
+        sphase[i] = (gas_as_fluid && ph == 1) ? PH_FLUID : ph;
     }
     unsigned todo = __ballot_sync(0xffffffffu, k1 > k0);
     while (todo) {
@@ -149,9 +152,10 @@ void ps_launch_calc_hash(u32 *hash, u32 *index, const float4 *pos, u32 n, GridDe
 size_t ps_chunk_table_elems(u32 num_cells) { return (size_t)cdiv(num_cells, kCellsPerBlock) + 1; }
 
 void ps_launch_reorder(float4 *spos, float *sw, int *sphase, u32 *chunk_lb, const u32 *hash, const u32 *index, const float4 *pos,
-                       const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s) {
+                       const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s, bool gas_as_fluid) {
     if (!n) return;
-    k_reorder<<<cdiv(n, kBlock), kBlock, 0, s>>>(spos, sw, sphase, chunk_lb, hash, index, pos, w, phase, n, cdiv(num_cells, kCellsPerBlock));
+    k_reorder<<<cdiv(n, kBlock), kBlock, 0, s>>>(spos, sw, sphase, chunk_lb, hash, index, pos, w, phase, n, cdiv(num_cells, kCellsPerBlock),
+                                                 gas_as_fluid ? 1 : 0);
 }
 
 void ps_launch_cell_begin(u32 *cell_begin, const u32 *hash, const u32 *chunk_lb, u32 n, u32 num_cells, cudaStream_t s) {

@@ -33,6 +33,21 @@ __global__ void __launch_bounds__(kBlock) k_predict(float4 *__restrict__ pos, co
     }
 }
 
+// K1 with buoyant gas (PS_FLAG_GAS; not in the reference's GPU solver): GAS particles feel gravity x PS_GAS_ALPHA, like the CPU
+// app's prediction (cpu/src/simulation.cpp:144, ALPHA -.2 simulation.h:21).  One more 4-byte read per particle.
+__global__ void __launch_bounds__(kBlock) k_predict_gas(float4 *__restrict__ pos, const float4 *__restrict__ vel, float4 *__restrict__ prev,
+                                                        const int *__restrict__ phase, u32 n, float dt, float3 g, float alpha) {
+    const u32 j = blockIdx.x * kBlock + threadIdx.x;
+    if (j >= n) return;
+    float4 p = ld_stream4(pos + j);
+    const float4 v = ld_stream4(vel + j);
+    const float s = phase[j] == 1 ? alpha : 1.f;
+    st_stream4(prev + j, p);
+    const float vx = v.x + (g.x * s) * dt, vy = v.y + (g.y * s) * dt, vz = v.z + (g.z * s) * dt;
+    p.x += vx * dt; p.y += vy * dt; p.z += vz * dt;
+    st_stream4(pos + j, p);
+}
+
 // ---- K11: V = (Xstar - pos) / -dt on all four components.  48 B/particle. ----
 __global__ void __launch_bounds__(kBlock) k_velocity(const float4 *__restrict__ pos, const float4 *__restrict__ prev,
                                                      float4 *__restrict__ vel, u32 n, float neg_dt) {
@@ -162,9 +177,10 @@ __global__ void __launch_bounds__(kBlock) k_distance_apply(float4 *__restrict__ 
 
 static inline u32 cdiv(u32 a, u32 b) { return (a + b - 1) / b; }
 
-void ps_launch_predict(float4 *pos, const float4 *vel, float4 *prev, u32 n, float dt, float3 g, cudaStream_t s) {
+void ps_launch_predict(float4 *pos, const float4 *vel, float4 *prev, u32 n, float dt, float3 g, cudaStream_t s, const int *gas_phase) {
     if (!n) return;
-    k_predict<<<cdiv(n, kBlock * 2), kBlock, 0, s>>>(pos, vel, prev, n, dt, g);
+    if (gas_phase) k_predict_gas<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, vel, prev, gas_phase, n, dt, g, PS_GAS_ALPHA);
+    else k_predict<<<cdiv(n, kBlock * 2), kBlock, 0, s>>>(pos, vel, prev, n, dt, g);
 }
 void ps_launch_velocity(const float4 *pos, const float4 *prev, float4 *vel, u32 n, float dt, cudaStream_t s) {
     if (!n) return;

@@ -205,3 +205,46 @@ def test_viscosity_paths_agree_and_default_is_off():
     assert not np.array_equal(sol.download(psb.ARR_VEL), outs[0][1])  # and switched on it does change the velocities
     sol.close()
     base.close()
+
+
+def gas_scene(flags):
+    x = cube(8, 8, 8, spacing=0.625, origin=(-2.5, 20, -2.5))
+    n = x.shape[0]
+    p = psb.default_params()
+    p.flags = flags
+    sol = psb.Solver(p, max_particles=1024)
+    pos4 = np.concatenate([x, np.ones((n, 1))], 1).astype(np.float32)
+    sol.append(pos4, np.zeros((n, 4), np.float32), np.ones(n), np.full(n, 4.1), np.full(n, psb.GAS))
+    return sol, x
+
+
+def test_gas_is_ignored_without_the_flag_like_the_reference():
+    """the reference's GPU kernels skip phase GAS: such particles only fall ballistically"""
+    sol, x = gas_scene(0)
+    for _ in range(10):
+        sol.step(1 / 60)
+    got = sol.download(psb.ARR_POS)[:, :3].astype(np.float64)
+    dt, g = 1 / 60, -9.8
+    fall = sum(g * dt * dt * k for k in range(1, 11))
+    assert np.abs(got[:, [0, 2]] - x[:, [0, 2]]).max() < 1e-5 and np.abs((got[:, 1] - x[:, 1]) - fall).max() < 1e-3
+    sol.close()
+
+
+def test_gas_with_the_flag_is_a_buoyant_pbf_fluid():
+    sol, x = gas_scene(psb.FLAG_GAS)
+    sol.predict(1 / 60)
+    y1 = sol.download(psb.ARR_POS)[:, 1].astype(np.float64)
+    assert np.allclose(y1 - x[:, 1], -9.8 * -0.2 / 3600, atol=1e-5)          # gravity x ALPHA (-0.2): the gas rises
+    sol.build_grid()
+    assert np.all(sol.download(psb.ARR_SORTED_PHASE) == psb.FLUID)           # the neighbour kernels see it as fluid ...
+    assert np.all(sol.download(psb.ARR_PHASE) == psb.GAS)                     # ... the particle keeps its phase
+    sol.find_neighbors()
+    nn = sol.download(psb.ARR_NUM_NEIGHBORS)
+    assert nn.min() > 20 and nn.max() <= 146 and np.abs(sol.download(psb.ARR_LAMBDA)).max() > 0
+    for _ in range(60):
+        sol.step(1 / 60)
+    got = sol.download(psb.ARR_POS)[:, :3].astype(np.float64)
+    assert np.isfinite(got).all() and got[:, 1].mean() > x[:, 1].mean() + 0.5  # a second later the cloud has risen
+    spread = np.linalg.norm(got - got.mean(0), axis=1).mean() / np.linalg.norm(x - x.mean(0), axis=1).mean()
+    assert 0.5 < spread < 3.0                                                 # and is held together / apart by the density constraint
+    sol.close()
