@@ -139,14 +139,27 @@ __global__ void __launch_bounds__(kThreads) k_radix_pass(const u32 *__restrict__
         atomicExch(my_status, kFlagPrefix | cnt);
     } else {
         atomicExch(my_status, kFlagAgg | cnt);
-        // decoupled look-back: walk predecessors until one has published an inclusive prefix
+        // decoupled look-back: walk predecessors until one has published an inclusive prefix.  All tiles of a small array
+        // are resident at once and publish their aggregates at about the same time, so the walk is a chain of dependent L2
+        // round trips (one per predecessor, ~245 at 1M pairs): kLook status words are requested per round trip instead.
+        constexpr int kLook = 8;
         int p = (int)tile - 1;
-        while (true) {
-            u32 sv = *((volatile u32 *)(status + (size_t)p * 256 + tid));
-            if ((sv >> 30) == 0) continue;  // not published yet (tiles are ticketed in order, so it is running)
-            excl += sv & kValMask;
-            if (sv & kFlagPrefix) break;
-            p--;
+        bool done = false;
+        while (!done) {
+            u32 sv[kLook];
+#pragma unroll
+            for (int q = 0; q < kLook; q++)
+                sv[q] = (p - q >= 0) ? *((volatile u32 *)(status + (size_t)(p - q) * 256 + tid)) : (2u << 30);  // before tile 0: an inclusive prefix of 0 (kFlagPrefix)
+            int used = 0;
+#pragma unroll
+            for (int q = 0; q < kLook; q++) {
+                if (done || used != q) continue;       // stopped at an unpublished word: re-read from there
+                if ((sv[q] >> 30) == 0) continue;      // not published yet (tiles are ticketed in order, so it is running)
+                excl += sv[q] & kValMask;
+                used = q + 1;
+                if (sv[q] & kFlagPrefix) done = true;
+            }
+            p -= used;
         }
         atomicExch(my_status, kFlagPrefix | (excl + cnt));
     }
