@@ -339,8 +339,9 @@ __device__ void project_boundary(const Particles2D &P, u32 i, double value, bool
 __global__ void __launch_bounds__(kSerialBlock) k2d_contact_project(Particles2D P, const u32 *__restrict__ nb, const u32 *__restrict__ cnt,
                                                                     const u32 *__restrict__ flags, const u32 *__restrict__ lvl, const u32 *__restrict__ rank,
                                                                     const u32 *__restrict__ info, u32 *__restrict__ cur, u32 n, const int *__restrict__ raw,
-                                                                    u32 draw_base, double x0, double x1, double y0, double y1) {
-    const u32 levels = info[0];
+                                                                    u32 window_base, u32 iteration, double x0, double x1, double y0, double y1) {
+    // info[-1] = jittered wall constraints of this tick (k2d_scan_counts): iteration t draws window[base + t * num + position]
+    const u32 levels = info[0], draw_base = window_base + iteration * info[-1];
     for (u32 i = threadIdx.x; i < n; i += kSerialBlock) cur[i] = 0;
     for (u32 l = 1; l <= levels; l++) {
         __syncthreads();
@@ -643,7 +644,11 @@ struct Ps2dCtx {
     std::vector<int> h_group;   // host mirror of `group` (the FluidEmitter walks its fluid's member list)
     std::vector<double> h_t;    // Particle::t (particle.h:38): freeze countdown, only the FluidEmitter reads it
     double *lambda_keep = nullptr;  // lambda of the fluid emitters' constraints after the last solver iteration
+    // look-ahead window of the rand() stream on the device: raw[k] = draw number win_pos + k of the stream (counted like
+    // rng.calls).  A tick indexes it with its own (device-side) constraint count, so the host learns how many draws were
+    // consumed only at the end of the tick and no round trip is needed in the middle of it.
     size_t raw_cap = 0;
+    uint64_t win_pos = 0, win_len = 0;
     std::vector<int> h_raw;
     GlibcRand rng;
     int any_solid = 0, any_jitter = 0;
@@ -962,6 +967,7 @@ extern "C" int ps2d_seed_rand(Ps2dCtx *c, uint32_t seed, uint64_t skip) {
     if (!c) return PS_ERR_INVALID;
     c->rng.seed(seed);
     for (uint64_t k = 0; k < skip; k++) c->rng.next();
+    c->win_len = 0;  // another stream: the look-ahead window on the device is stale
     return PS_OK;
 }
 extern "C" uint64_t ps2d_rand_calls(Ps2dCtx *c) { return c ? c->rng.calls : 0; }
@@ -1137,37 +1143,33 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     k2d_scan_counts<<<1, 1024, 0, s>>>(c->draws, c->rank, n, c->scalars);
     k2d_contact_levels<<<1, kSerialBlock, 0, s>>>(c->nb, c->cnt, c->flags, n, c->nbq, c->lvl, c->scalars + 1);
     launches += 4;
-    // the number of jittered wall constraints decides how many draws of the rand() stream this tick consumes: one per
-    // constraint per solver iteration, in list order (the only host round trip of a tick)
-    CU2(cudaMemcpyAsync(c->scalars_host, c->scalars, 16, cudaMemcpyDeviceToHost, s));
-    CU2(cudaStreamSynchronize(s));
-    const u32 num = c->scalars_host[0];
-    c->last_num_boundary = num;
-    c->last_levels = c->scalars_host[1];
-    c->last_contacts = c->scalars_host[2];
-    if (c->scalars_host[3]) {
-        ps_set_error("ps2d_tick: a particle has %u contacts, more than PS2D_MAX_CONTACTS = %d", c->scalars_host[3], kMaxC);
-        cudaMemsetAsync(c->scalars + 3, 0, 4, s);
-        return PS_ERR_CAPACITY;
-    }
-    const size_t ndraws = (size_t)num * P.solver_iterations;
-    if (ndraws) {
-        c->h_raw.resize(ndraws);
-        for (size_t k = 0; k < ndraws; k++) c->h_raw[k] = c->rng.next();
-        if (ndraws > c->raw_cap) {
+    // the number of jittered wall constraints decides how many draws of the rand() stream this tick consumes — one per
+    // constraint per solver iteration, in list order; at most 2 n per iteration.  The kernels take them from the look-ahead
+    // window, which is refilled (from a copy of the generator) when it no longer covers a worst-case tick.
+    const uint64_t worst = (uint64_t)2 * n * P.solver_iterations;
+    if (c->any_jitter && (c->rng.calls < c->win_pos || c->rng.calls + worst > c->win_pos + c->win_len)) {
+        const size_t want = std::max<size_t>(worst * 16, 1u << 16);
+        GlibcRand ahead = c->rng;
+        c->h_raw.resize(want);
+        for (size_t k = 0; k < want; k++) c->h_raw[k] = ahead.next();
+        if (want > c->raw_cap) {
+            CU2(cudaStreamSynchronize(s));
             if (c->raw) CU2(cudaFree(c->raw));
             c->raw = nullptr;
-            CU2(cudaMalloc(&c->raw, ndraws * 2 * sizeof(int)));
-            c->raw_cap = ndraws * 2;
+            CU2(cudaMalloc(&c->raw, want * sizeof(int)));
+            c->raw_cap = want;
         }
-        CU2(cudaMemcpyAsync(c->raw, c->h_raw.data(), ndraws * sizeof(int), cudaMemcpyHostToDevice, s));
+        CU2(cudaMemcpyAsync(c->raw, c->h_raw.data(), want * sizeof(int), cudaMemcpyHostToDevice, s));
+        CU2(cudaStreamSynchronize(s));  // h_raw is pageable
+        c->win_pos = c->rng.calls;
+        c->win_len = want;
     }
+    const u32 window_base = (u32)(c->rng.calls - c->win_pos);
     Particles2D V{c->ep, c->p, c->tmass, c->sfric, c->kfric, c->phase, c->bod, c->counts, c->sdf_grad, c->sdf_dist, c->b_angle};
     for (u32 it = 0; it < P.solver_iterations; it++) {
-        if (c->last_contacts) {  // CONTACT group
-            k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, it * num, x0, x1, y0, y1);
-            launches++;
-        }
+        // CONTACT group (the kernel returns at once when the list is empty)
+        k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, window_base, it, x0, x1, y0, y1);
+        launches++;
         size_t run = 0;  // STANDARD group, in list order
         for (size_t k = 0; k < c->standard.size();) {
             const StdOp &op = c->standard[k];
@@ -1200,7 +1202,19 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     c->launches = launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ps_set_error("ps2d_tick: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
-    CU2(cudaStreamSynchronize(s));  // h_raw is reused by the next tick
+    // the one host round trip of a tick, at its end: what the CONTACT list looked like and how many draws it consumed
+    CU2(cudaMemcpyAsync(c->scalars_host, c->scalars, 16, cudaMemcpyDeviceToHost, s));
+    CU2(cudaStreamSynchronize(s));
+    const u32 num = c->scalars_host[0];
+    c->last_num_boundary = num;
+    c->last_levels = c->scalars_host[1];
+    c->last_contacts = c->scalars_host[2];
+    if (c->scalars_host[3]) {
+        ps_set_error("ps2d_tick: a particle has %u contacts, more than PS2D_MAX_CONTACTS = %d", c->scalars_host[3], kMaxC);
+        cudaMemsetAsync(c->scalars + 3, 0, 4, s);
+        return PS_ERR_CAPACITY;
+    }
+    for (size_t k = 0, nd = (size_t)num * P.solver_iterations; k < nd; k++) c->rng.next();  // the stream moves on by what was drawn
     // OpenSmokeEmitter::tick (opensmokeemitter.cpp:17-29): particle injection into the gas constraint
     for (Emitter &em : c->emitters) {
         em.timer += dt;
