@@ -312,7 +312,7 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
 // ------------------------------------------------------------------ K6: lambda (+ neighbour lists) ------------------------------------------------------------------
 template <int RAD>
 // (forcing more resident CTAs through a register cap — 56, 48, 40 registers — makes K6 slower: 0.92 / 0.96 / 1.05 ms against
-// 0.78 ms at the compiler's 64; more warps only thrash L1, profiles/r1k)
+// 0.78 ms at the compiler's 64; more warps only thrash L1, profiles/r1l)
 __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lambda, u32 *__restrict__ num_neighbors,
                                                          const float4 *__restrict__ spos, const float *__restrict__ sw,
                                                          const int *__restrict__ sphase, const u32 *__restrict__ index,
