@@ -18,6 +18,9 @@ extern "C" {
 /* Simulation::init(type): creates a context with the scene's bounds / gravity and builds the scene into it.
  * max_particles 0 = scene size + room for emitted particles. */
 int ps2d_build_scene(const char *key, int device, uint64_t max_particles, Ps2dCtx **out);
+/* the same with the position of the rand() stream given explicitly: srand(seed), `draws_consumed` draws already taken
+ * (Simulation::init continues the stream wherever earlier scenes and ticks left it) */
+int ps2d_build_scene_from(const char *key, int device, uint64_t max_particles, uint32_t seed, uint64_t draws_consumed, Ps2dCtx **out);
 const char *ps2d_scene_name(const char *key); /* "GRANULAR_TEST", ...; NULL for an unknown key */
 #ifdef __cplusplus
 }

@@ -120,6 +120,7 @@ uint32_t ps2d_num_bodies(Ps2dCtx *ctx);
 int ps2d_seed_rand(Ps2dCtx *ctx, uint32_t seed, uint64_t skip);
 uint64_t ps2d_rand_calls(Ps2dCtx *ctx);              /* draws consumed so far, including `skip` */
 int ps2d_rand(Ps2dCtx *ctx, int *out);               /* one rand() of that stream (the scene builders' frand() jitter) */
+int ps2d_mouse_pressed(Ps2dCtx *ctx, double x, double y);  /* Simulation::mousePressed: v += 7 normalize(point - p), every particle */
 int ps2d_tick(Ps2dCtx *ctx, double seconds);         /* Simulation::tick(seconds); the reference's app uses .01 (view.cpp:197) */
 uint64_t ps2d_num_particles(Ps2dCtx *ctx);
 uint32_t ps2d_last_num_boundary_constraints(Ps2dCtx *ctx);  /* wall constraints of the last tick that draw jitter (fluid / gas particles) */

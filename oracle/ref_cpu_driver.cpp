@@ -1,6 +1,7 @@
 // Headless driver around the reference's UNMODIFIED 2-D CPU solver (cpu/src/simulation.cpp + constraint/*.cpp,
 // compiled from /root/reference by oracle/Makefile into oracle/_ref/ref_cpu).  TEST INFRASTRUCTURE ONLY.
 //   ref_cpu --scene KEY --ticks N [--dump dir [--dump-every K] [--scene-at T]] [--json]
+//   ref_cpu --script "6:100,1:50,w:20"      one Simulation object, scenes switched like key presses
 // Builds a scene exactly as the Qt app does (Simulation() runs init(WRECKING_BALL) first, then the key handler
 // calls init(type): cpu/src/simulation.cpp:11-16, cpu/src/view.cpp:121-179), runs tick(.01) N times
 // (cpu/src/view.cpp:185-202) and reports kinetic energy / timing; --dump writes particle state after chosen ticks.
@@ -163,7 +164,7 @@ static void dump_state(Simulation &sim, const std::string &dir, int tick) {
 }
 
 int main(int argc, char **argv) {
-    std::string scene = "6", dump;
+    std::string scene = "6", dump, script;
     int ticks = 100, dump_every = 0, scene_at = -1;
     bool json = false;
     for (int i = 1; i < argc; i++) {
@@ -173,9 +174,30 @@ int main(int argc, char **argv) {
         else if (k == "--dump" && i + 1 < argc) dump = argv[++i];
         else if (k == "--dump-every" && i + 1 < argc) dump_every = atoi(argv[++i]);
         else if (k == "--scene-at" && i + 1 < argc) scene_at = atoi(argv[++i]);  // full restart state after that tick
+        else if (k == "--script" && i + 1 < argc) script = argv[++i];  // a session: "KEY:TICKS,KEY:TICKS,..." on ONE Simulation object
         else if (k == "--json") json = true;
     }
     Simulation sim;  // constructor builds WRECKING_BALL first, consuming rand() like the app does
+    if (!script.empty()) {  // key presses and ticks like a user's session: the rand() stream runs on across scenes
+        printf("[");
+        size_t at = 0;
+        bool first = true;
+        while (at < script.size()) {
+            size_t comma = script.find(',', at);
+            if (comma == std::string::npos) comma = script.size();
+            const std::string item = script.substr(at, comma - at);
+            at = comma + 1;
+            const size_t colon = item.find(':');
+            const int ticks = colon == std::string::npos ? 0 : atoi(item.c_str() + colon + 1);
+            sim.init(scene_of(item.substr(0, colon)));
+            for (int k = 0; k < ticks; k++) sim.tick(.01);
+            printf("%s{\"scene\": \"%s\", \"particles\": %d, \"ticks\": %d, \"kinetic_energy\": %.17g, \"rand_calls\": %ld}", first ? "" : ", ",
+                   item.substr(0, colon).c_str(), sim.getNumParticles(), ticks, sim.getKineticEnergy(), g_rand_calls);
+            first = false;
+        }
+        printf("]\n");
+        return 0;
+    }
     sim.init(scene_of(scene));
     int n = sim.getNumParticles();
     if (!dump.empty()) { std::string c = "mkdir -p '" + dump + "'"; if (system(c.c_str())) return 1; dump_scene(sim, dump, 0); dump_state(sim, dump, 0); }

@@ -569,6 +569,18 @@ __global__ void k2d_finish(double2 *__restrict__ p, double2 *__restrict__ v, con
     p[i] = e;
 }
 
+// Simulation::mousePressed (simulation.cpp:1305-1314): every particle gets a velocity impulse of 7 towards the point
+__global__ void k2d_impulse(double2 *__restrict__ v, const double2 *__restrict__ p, u32 n, double px, double py) {
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const double2 q = p[i];
+    const double dx = px - q.x, dy = py - q.y;
+    const double inv = 1. / sqrt(dx * dx + dy * dy);  // glm::normalize
+    double2 vi = v[i];
+    vi.x += 7. * (dx * inv); vi.y += 7. * (dy * inv);
+    v[i] = vi;
+}
+
 // glibc rand() = random(), TYPE_3: r[i] = r[i-31] + r[i-3], output r[i] >> 1 (after 310 discarded words)
 struct GlibcRand {
     std::vector<uint32_t> r;
@@ -944,6 +956,15 @@ extern "C" int ps2d_create_smoke_emitter(Ps2dCtx *c, const double *posn2, double
         ps_set_error("ps2d_create_smoke_emitter: STANDARD constraint %u is not a gas", standard_index); return PS_ERR_INVALID;
     }
     c->emitters.push_back(Emitter{posn2[0], posn2[1], rate, timer, standard_index});
+    return PS_OK;
+}
+
+extern "C" int ps2d_mouse_pressed(Ps2dCtx *c, double x, double y) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    if (!c->n) return PS_OK;
+    CU2(cudaSetDevice(c->device));
+    k2d_impulse<<<(c->n + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->v, c->p, c->n, x, y);
+    CU2(cudaStreamSynchronize(c->stream));
     return PS_OK;
 }
 

@@ -4,6 +4,8 @@
 //   psolver_cli --app gpu --scene 7 --steps 600 [--dt 0.016667] [--grid 64] [--max-particles 15000] [--side 100]
 //               [--iterations 5] [--xsph 0.01 --vorticity 0.3]
 //   psolver_cli --app cpu --scene 6 --steps 1000 [--dt 0.01]
+//   psolver_cli --app session --script "6:100,1:50,w:20"     the CPU app as a user drives it: psb200::Simulation (constructor
+//               builds WRECKING_BALL), then key presses and ticks; the rand() stream runs on across scenes like the reference's
 // common: [--load FILE] [--save FILE] [--dump-every K --out DIR] [--json] [--device D]
 // --load continues a checkpoint written by --save (ps_save / ps2d_save) instead of building a scene; --dump-every
 // writes raw little-endian positions (header: "PSDUMP1\0", uint32 dims per particle, uint32 bytes per scalar, uint64 n).
@@ -18,11 +20,12 @@
 #include "../../include/particle_system.h"
 #include "../../include/ps_scenes.h"
 #include "../../include/ps_scenes2d.h"
+#include "../../include/simulation2d.h"
 #include "../../include/psolver.h"
 
 namespace {
 struct Args {
-    std::string app = "gpu", scene = "7", load, save, out = "psolver_out";
+    std::string app = "gpu", scene = "7", load, save, out = "psolver_out", script;
     int steps = 100, grid = 64, side = 100, iterations = 5, dump_every = 0, device = 0;
     unsigned max_particles = 15000;
     double dt = -1;
@@ -129,6 +132,40 @@ int run_cpu_app(const Args &a) {
     ps2d_destroy(ctx);
     return 0;
 }
+
+// a scripted session of the CPU app through the host class (include/simulation2d.h): "KEY:TICKS,KEY:TICKS,..."
+int run_session(const Args &a, const std::string &script) {
+    using namespace psb200;
+    const SimulationType types[] = {FRICTION_TEST, SDF_TEST, GRANULAR_TEST, STACKS_TEST, WALL_TEST, PENDULUM_TEST, ROPE_TEST, FLUID_TEST, FLUID_SOLID_TEST,
+                                    GAS_ROPE_TEST, WATER_BALLOON_TEST, CRADLE_TEST, SMOKE_OPEN_TEST, SMOKE_CLOSED_TEST, VOLCANO_TEST, WRECKING_BALL};
+    try {
+        Simulation sim(a.device);
+        printf("[");
+        size_t at = 0;
+        bool first = true;
+        while (at < script.size()) {
+            size_t comma = script.find(',', at);
+            if (comma == std::string::npos) comma = script.size();
+            const std::string item = script.substr(at, comma - at);
+            at = comma + 1;
+            const size_t colon = item.find(':');
+            const std::string key = item.substr(0, colon);
+            const int ticks = colon == std::string::npos ? 0 : atoi(item.c_str() + colon + 1);
+            bool found = false;
+            for (SimulationType t : types)
+                if (key == Simulation::key_of(t)) { sim.init(t); found = true; break; }
+            if (!found) die("unknown scene key '" + key + "' in --script");
+            for (int k = 0; k < ticks; k++) sim.tick(a.dt > 0 ? a.dt : .01);
+            printf("%s{\"scene\": \"%s\", \"particles\": %d, \"ticks\": %d, \"kinetic_energy\": %.17g, \"rand_calls\": %llu}", first ? "" : ", ", key.c_str(),
+                   sim.getNumParticles(), ticks, sim.getKineticEnergy(), (unsigned long long)ps2d_rand_calls(sim.context()));
+            first = false;
+        }
+        printf("]\n");
+    } catch (const std::exception &e) {
+        die(e.what());
+    }
+    return 0;
+}
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -144,6 +181,7 @@ int main(int argc, char **argv) {
         else if (k == "--side") a.side = atoi(val());
         else if (k == "--iterations") a.iterations = atoi(val());
         else if (k == "--max-particles") a.max_particles = (unsigned)strtoul(val(), nullptr, 10);
+        else if (k == "--script") a.script = val();
         else if (k == "--load") a.load = val();
         else if (k == "--save") a.save = val();
         else if (k == "--dump-every") a.dump_every = atoi(val());
@@ -158,5 +196,6 @@ int main(int argc, char **argv) {
     if (a.steps < 0 || a.grid <= 0 || (a.grid & (a.grid - 1))) die("--steps >= 0, --grid a power of two");
     if (a.app == "gpu") return run_gpu(a);
     if (a.app == "cpu") return run_cpu_app(a);
-    die("--app gpu | cpu");
+    if (a.app == "session") return run_session(a, a.script);
+    die("--app gpu | cpu | session");
 }

@@ -368,6 +368,11 @@ extern "C" const char *ps2d_scene_name(const char *key) {
 }
 
 extern "C" int ps2d_build_scene(const char *key, int device, uint64_t max_particles, Ps2dCtx **out) {
+    // the app's stream: seed 1 (never seeded), the constructor's WRECKING_BALL already built
+    return ps2d_build_scene_from(key, device, max_particles, 1, PS2D_APP_START_DRAWS, out);
+}
+
+extern "C" int ps2d_build_scene_from(const char *key, int device, uint64_t max_particles, uint32_t seed, uint64_t draws_consumed, Ps2dCtx **out) {
     if (!out) { ps_set_error("ps2d_build_scene: null output"); return PS_ERR_INVALID; }
     *out = nullptr;
     const SceneInfo *S = find_scene(key);
@@ -381,8 +386,7 @@ extern "C" int ps2d_build_scene(const char *key, int device, uint64_t max_partic
     Builder B;
     int r = ps2d_create(device, &P, max_particles ? max_particles : S->room + 2048, &B.c);
     if (r != PS_OK) return r;
-    // the app's stream: seed 1 (never seeded), the constructor's WRECKING_BALL already built
-    ps2d_seed_rand(B.c, 1, PS2D_APP_START_DRAWS);
+    ps2d_seed_rand(B.c, seed, draws_consumed);
     build(B, key, *S);
     if (B.err != PS_OK) { ps2d_destroy(B.c); return B.err; }
     *out = B.c;

@@ -76,3 +76,19 @@ def test_unknown_scene_key():
     with pytest.raises(psb.PsError, match="unknown scene"):
         psb.Simulation2D.scene("x")
     assert psb.lib().ps2d_scene_name(b"6") == b"FLUID_TEST"
+
+
+def test_host_class_session_replays_the_reference_app():
+    """psb200::Simulation (include/simulation2d.h) driven like the CPU app — the constructor builds WRECKING_BALL, keys switch
+    scenes, the rand() stream runs on across scenes and ticks — against the same session on the reference's own Simulation
+    (tests/golden/ref_cpu_session.json, written by oracle/_ref/ref_cpu --script)."""
+    import subprocess
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_cpu_session.json")))
+    cli = os.path.join(ROOT, "particlesolver_b200", "psolver_cli")
+    out = subprocess.run([cli, "--app", "session", "--script", ref["script"]], capture_output=True, text=True, check=True).stdout
+    got = json.loads(out)
+    assert len(got) == len(ref["segments"])
+    for g, r in zip(got, ref["segments"]):
+        assert g["scene"] == r["scene"] and g["particles"] == r["particles"] and g["ticks"] == r["ticks"]
+        assert g["rand_calls"] == r["rand_calls"], (g, r)                       # the stream position after every segment: exact
+        assert abs(g["kinetic_energy"] - r["kinetic_energy"]) <= 1e-9 * max(1.0, abs(r["kinetic_energy"])), (g, r)
