@@ -496,6 +496,14 @@ class Cpu2dFullOracle:
                 self.add_particle(e["posn"], 1., FLUID)
                 self.v[-1] = [self.frand(), 1.]
 
+    def mouse_pressed(self, x, y):
+        """Simulation::mousePressed (simulation.cpp:1305-1314): v += 7 * normalize(point - p) for every particle"""
+        for i in range(self.n):
+            dx, dy = x - self.p[i][0], y - self.p[i][1]
+            inv = 1. / math.sqrt(dx * dx + dy * dy)
+            self.v[i][0] += 7. * (dx * inv)
+            self.v[i][1] += 7. * (dy * inv)
+
     def add_particle(self, pos, mass, phase):
         """Particle(pos, mass, phase) (particle.h:31-52) appended to the particle list"""
         self.p.append([pos[0], pos[1]])

@@ -176,6 +176,8 @@ def lib():
         L.ps2d_create_gas.argtypes = [vp, vp, vp, vp, u64, C.c_double, i32, C.POINTER(u32)]
         L.ps2d_create_smoke_emitter.argtypes = [vp, vp, C.c_double, u32, C.c_double]
         L.ps2d_set_forces.argtypes = [vp, vp]
+        L.ps2d_mouse_pressed.argtypes = [vp, C.c_double, C.c_double]
+        L.ps2d_build_scene_from.argtypes = [C.c_char_p, i32, u64, u32, u64, C.POINTER(vp)]
         L.ps2d_create_fluid_emitter.argtypes = [vp, vp, C.c_double, u32, C.c_double, C.c_double]
         L.ps2d_set_particle_timers.argtypes = [vp, vp]
         L.ps2d_get_particle_timers.argtypes = [vp, vp]
@@ -622,6 +624,10 @@ class Simulation2D:
         t = np.empty(self.getNumParticles(), np.float64)
         _check(lib().ps2d_get_particle_timers(self._h, _ptr(t)))
         return t
+
+    def mousePressed(self, x, y):
+        """Simulation::mousePressed: every particle's velocity gets an impulse of 7 towards the point"""
+        _check(lib().ps2d_mouse_pressed(self._h, float(x), float(y)))
 
     def setForces(self, f):
         f = _arr(f, np.float64).reshape(-1, 2)

@@ -148,3 +148,18 @@ def test_resting_particle_sleeps_and_wall_clamps_like_the_reference():
     assert np.array_equal(p[0], [0.0, 10.0]) and np.array_equal(v[0], [0.0, 0.0])     # moved 5e-5 < 1e-4: asleep
     assert p[1, 0] == 5 - 0.25 and abs(v[1, 0] - (4.75 - 4.9) / .01) < 1e-12             # pushed back inside the right wall
     sim.close()
+
+
+def test_mouse_pressed_impulse_matches_the_oracle():
+    import cpu2d_full_oracle as full
+    scene = json.loads(str(G["friction_scene"]))
+    sim = psb.Simulation2D.from_state(scene)
+    o = full.Cpu2dFullOracle(scene)
+    sim.mousePressed(3.0, 7.5)
+    o.mouse_pressed(3.0, 7.5)
+    assert np.abs(sim.velocities() - o.velocities()).max() <= 1e-14
+    for _ in range(3):
+        sim.tick(.01)
+        o.tick(.01)
+    assert np.abs(sim.positions() - o.positions()).max() <= 1e-12
+    sim.close()
