@@ -182,6 +182,9 @@ int ps_slab_pack_migrants(PsCtx *ctx, float x_lo, float x_hi, void *left_buf, vo
 int ps_slab_append_migrants(PsCtx *ctx, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right);
 /* lambda is computed for owned particles and for ghosts with x in [x_min, x_max] only (default: everywhere) */
 int ps_slab_set_lambda_range(PsCtx *ctx, float x_min, float x_max);
+/* load balancing: counts of the owned particles' x in `bins` (<= 65536) equal bins of [x_min, x_max) (values outside fall
+ * into the end bins), copied to host_counts[bins].  The ranks' histograms summed are what the slabs are re-cut from. */
+int ps_slab_x_histogram(PsCtx *ctx, float x_min, float x_max, uint32_t bins, uint64_t *host_counts);
 
 /* ---- checkpoints (the reference has no persistence: scenes exist only as code, particleapp.cpp:141-215) ----
  * Everything a run needs to continue bit-identically: parameters, particle arrays, constraint lists in insertion order,

@@ -115,6 +115,7 @@ def lib():
         L.ps_slab_pack_migrants.argtypes = [vp, f32, f32, vp, vp, u64, C.POINTER(u32 * 2)]
         L.ps_slab_append_migrants.argtypes = [vp, vp, u64, vp, u64]
         L.ps_slab_set_lambda_range.argtypes = [vp, f32, f32]
+        L.ps_slab_x_histogram.argtypes = [vp, f32, f32, u32, vp]
         # C++ host class (csrc/particle_system.cpp)
         L.pshost_create.argtypes = [f32, u32, u32, u32, u32, vp, vp, i32]
         L.pshost_create.restype = vp
@@ -424,6 +425,11 @@ class Solver:
 
     def slab_append_migrants(self, left_ptr, n_left, right_ptr, n_right):
         _check(lib().ps_slab_append_migrants(self._h, left_ptr, n_left, right_ptr, n_right))
+
+    def slab_x_histogram(self, x_min, x_max, bins):
+        h = np.zeros(int(bins), np.uint64)
+        _check(lib().ps_slab_x_histogram(self._h, x_min, x_max, int(bins), _ptr(h)))
+        return h.astype(np.int64)
 
     def slab_set_lambda_range(self, x_min, x_max):
         _check(lib().ps_slab_set_lambda_range(self._h, max(x_min, -3.0e38), min(x_max, 3.0e38)))

@@ -871,6 +871,28 @@ extern "C" int ps_slab_append_migrants(PsCtx *c, const void *from_left, uint64_t
     return check_launch("ps_slab_append_migrants");
 }
 
+// histogram of the OWNED particles' x (current positions) over `bins` equal bins of [x_min, x_max), out-of-range values in
+// the end bins: every rank's histogram summed gives the global distribution the slabs are re-cut from (slab.balanced_cuts)
+extern "C" int ps_slab_x_histogram(PsCtx *c, float x_min, float x_max, uint32_t bins, uint64_t *host_counts) {
+    NEED(c);
+    if (!host_counts || !bins || bins > 65536 || !(x_min < x_max)) { ps_set_error("ps_slab_x_histogram: bad argument"); return PS_ERR_INVALID; }
+    DeviceGuard dg(c->device);
+    const u32 n_owned = c->n - c->n_ghost;
+    const size_t need = bins;
+    if (c->slab_scratch_elems < need) {
+        if (c->slab_scratch) CU(cudaFree(c->slab_scratch));
+        c->slab_scratch = nullptr;
+        CU(cudaMalloc((void **)&c->slab_scratch, need * sizeof(u32)));
+        c->slab_scratch_elems = need;
+    }
+    ps_launch_slab_x_histogram(c->pos, n_owned, x_min, x_max, bins, c->slab_scratch, c->stream);
+    std::vector<u32> h(bins);
+    CU(cudaMemcpyAsync(h.data(), c->slab_scratch, bins * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (u32 b = 0; b < bins; b++) host_counts[b] = h[b];
+    return check_launch("ps_slab_x_histogram");
+}
+
 extern "C" int ps_slab_set_lambda_range(PsCtx *c, float x_min, float x_max) {
     NEED(c);
     c->lambda_xmin = x_min;

@@ -245,3 +245,20 @@ void ps_launch_slab_append_migrants(float4 *pos, float4 *prev, float4 *vel, floa
     k_slab_append_migrants<<<cdiv(n_left + n_right, kBlock), kBlock, 0, s>>>(pos, prev, vel, w, ros, phase, first, (const MigrantRec *)from_left,
                                                                             n_left, (const MigrantRec *)from_right, n_right);
 }
+
+// ---- load balancing: histogram of the owned particles' x over [x_min, x_max) (bins <= 65536), for re-cutting the slabs ----
+namespace {
+__global__ void __launch_bounds__(256) k_slab_x_histogram(const float4 *__restrict__ pos, u32 n, float x_min, float inv_width, u32 bins, u32 *__restrict__ hist) {
+    const u32 i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float t = (__ldg(&pos[i].x) - x_min) * inv_width;
+    int b = (int)floorf(t);
+    b = b < 0 ? 0 : (b >= (int)bins ? (int)bins - 1 : b);
+    atomicAdd(hist + b, 1u);  // x-sorted-ish input: neighbouring threads hit neighbouring bins, few conflicts
+}
+}  // namespace
+void ps_launch_slab_x_histogram(const float4 *pos, u32 n, float x_min, float x_max, u32 bins, u32 *hist, cudaStream_t s) {
+    cudaMemsetAsync(hist, 0, (size_t)bins * sizeof(u32), s);
+    if (!n) return;
+    k_slab_x_histogram<<<(n + 255) / 256, 256, 0, s>>>(pos, n, x_min, (float)bins / (x_max - x_min), bins, hist);
+}

@@ -9,6 +9,8 @@ arrays, ghost copies of its neighbours' particles within `halo` of the two faces
     5 x        : refresh the ghost halo (positions change every solver iteration, and the reference rebuilds its grid
                  every iteration too), then K2-K8 on owned + ghosts, writing owned particles only
     finish     : velocity update (K11)
+    re-cut     : optionally, every k steps right after the predict, the cut planes move to the equal-count quantiles of the
+                 particles' x (per-rank histograms, all-reduced); the migration that follows hands the particles over
 
 Only the exchange itself happens here (torch.distributed send/recv between neighbouring ranks: NCCL over NVLink on
 the GPU box, gloo in the CPU tests); selection, packing, compaction and unpacking are CUDA kernels behind the C ABI
@@ -40,6 +42,43 @@ def quantile_cuts(x, nranks):
     """Equal-count cut planes from the x coordinates of the initial particle set."""
     q = np.quantile(np.asarray(x, np.float64), [r / nranks for r in range(1, nranks)]) if nranks > 1 else []
     return [-math.inf, *[float(v) for v in q], math.inf]
+
+
+def balanced_cuts(hist, x_min, x_max, old_cuts, min_width, max_shift):
+    """New cut planes from the global histogram of the particles' x (`hist[b]` = count in bin b of [x_min, x_max)): the
+    equal-count quantiles, linearly interpolated inside a bin, then limited — a cut moves by at most `max_shift` per
+    re-cut (particles change owner by hopping to the NEIGHBOURING rank, one hop per step, so a cut must not jump over a
+    slab) and slabs stay at least `min_width` wide (a rank's ghosts all come from its two neighbours: the halo must fit
+    inside a slab).  Pure function of its arguments: every rank computes the same planes from the all-reduced histogram."""
+    nranks = len(old_cuts) - 1
+    if nranks == 1:
+        return [-math.inf, math.inf]
+    hist = np.asarray(hist, np.float64)
+    bins = hist.shape[0]
+    cum = np.concatenate([[0.0], np.cumsum(hist)])
+    total = cum[-1]
+    edges = x_min + (x_max - x_min) * np.arange(bins + 1) / bins
+    new = []
+    for r in range(1, nranks):
+        target = total * r / nranks
+        b = int(np.searchsorted(cum, target, side="right")) - 1
+        b = min(max(b, 0), bins - 1)
+        frac = (target - cum[b]) / hist[b] if hist[b] > 0 else 0.5
+        new.append(float(edges[b] + frac * (edges[b + 1] - edges[b])))
+    out = [-math.inf]
+    for r in range(1, nranks):
+        c = new[r - 1]
+        old = old_cuts[r]
+        if math.isfinite(old):
+            c = min(max(c, old - max_shift), old + max_shift)
+        if math.isfinite(out[-1]):
+            c = max(c, out[-1] + min_width)
+        out.append(c)
+    out.append(math.inf)
+    for r in range(nranks - 1, 1, -1):  # keep the minimum width from the right as well
+        if out[r] - out[r - 1] < min_width:
+            out[r - 1] = out[r] - min_width
+    return out
 
 
 class CtxEngine:
@@ -81,6 +120,9 @@ class CtxEngine:
 
     def set_lambda_range(self, x_min, x_max):
         self.sol.slab_set_lambda_range(x_min, x_max)
+
+    def x_histogram(self, x_min, x_max, bins):
+        return self.sol.slab_x_histogram(x_min, x_max, bins)
 
     # stages
     def begin_step(self): self.sol.begin_step()
@@ -138,19 +180,48 @@ class DistComm:
         self.bytes_sent += (to_left.shape[0] * (r > 0) + to_right.shape[0] * (r < w - 1)) * record_bytes
         return from_left, from_right
 
+    def allreduce_sum(self, counts):
+        """element-wise sum of an int64 numpy array over the ranks (the x-histograms of a re-cut)"""
+        t = self.torch.as_tensor(np.ascontiguousarray(counts, np.int64), device=self.count_device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
 
 class SlabDomain:
     """Host logic of one rank's slab.  Backend-agnostic: `engine` is a CtxEngine (GPU) or, in the CPU tests, an engine
     over the oracle with the same methods."""
 
-    def __init__(self, engine, rank, nranks, cuts, drift=0.25, comm=None):
+    def __init__(self, engine, rank, nranks, cuts, drift=0.25, comm=None, recut_every=0, recut_range=None, recut_bins=4096):
+        """recut_every > 0: every that many steps the cut planes are moved to the equal-count quantiles of the particles' x
+        (a histogram over `recut_range` = (x_min, x_max) with `recut_bins` bins, summed over the ranks), so that slabs keep
+        equal particle counts while the fluid flows — SURVEY §8e."""
         assert len(cuts) == nranks + 1 and all(cuts[k] < cuts[k + 1] for k in range(nranks))
         self.eng, self.rank, self.nranks, self.comm = engine, rank, nranks, comm
-        self.x_lo, self.x_hi = float(cuts[rank]), float(cuts[rank + 1])
         self.halo = 2.0 * H + 2.0 * drift
         self.lambda_ext = H + drift
-        engine.set_lambda_range(self.x_lo - self.lambda_ext, self.x_hi + self.lambda_ext)
-        self.stats = {"migrated_out": 0, "ghosts": 0}
+        self.stats = {"migrated_out": 0, "ghosts": 0, "recuts": 0}
+        self.recut_every, self.recut_range, self.recut_bins = int(recut_every), recut_range, int(recut_bins)
+        assert not self.recut_every or (recut_range is not None and recut_range[0] < recut_range[1])
+        self.steps_done = 0
+        self.set_cuts(cuts)
+
+    def set_cuts(self, cuts):
+        self.cuts = [float(c) for c in cuts]
+        self.x_lo, self.x_hi = self.cuts[self.rank], self.cuts[self.rank + 1]
+        self.eng.set_lambda_range(self.x_lo - self.lambda_ext, self.x_hi + self.lambda_ext)
+
+    def x_histogram(self):
+        return np.asarray(self.eng.x_histogram(self.recut_range[0], self.recut_range[1], self.recut_bins), np.int64)
+
+    def recut_due(self):
+        return self.recut_every > 0 and self.nranks > 1 and self.steps_done > 0 and self.steps_done % self.recut_every == 0
+
+    def apply_recut(self, global_hist):
+        """new cut planes from the summed histogram; takes effect with the migration that follows"""
+        width = min((b - a for a, b in zip(self.cuts[1:-2], self.cuts[2:-1])), default=math.inf)
+        max_shift = 0.5 * min(width, 4.0 * self.halo) if math.isfinite(width) else 2.0 * self.halo
+        self.set_cuts(balanced_cuts(global_hist, self.recut_range[0], self.recut_range[1], self.cuts, min_width=self.halo + 0.5, max_shift=max_shift))
+        self.stats["recuts"] += 1
 
     # ---- phases (a LocalCluster drives them in lock-step; step() strings them together over a communicator) ----
     def begin(self, dt):
@@ -204,20 +275,23 @@ class SlabDomain:
 
     def step(self, dt):
         self.begin(dt)
+        if self.recut_due():
+            self.apply_recut(self.comm.allreduce_sum(self.x_histogram()))
         self.migrate()
         for it in range(self.eng.iterations):
             self.refresh_halo()
             self.solve(it)
         self.finish(dt)
+        self.steps_done += 1
 
 
 class LocalCluster:
     """All slabs in one process, stepped in lock-step with in-process hand-over of the record buffers (tests; also a way
     to run several slabs on one GPU)."""
 
-    def __init__(self, engines, cuts, drift=0.25):
+    def __init__(self, engines, cuts, drift=0.25, **recut):
         n = len(engines)
-        self.doms = [SlabDomain(e, r, n, cuts, drift) for r, e in enumerate(engines)]
+        self.doms = [SlabDomain(e, r, n, cuts, drift, **recut) for r, e in enumerate(engines)]
 
     def _hand_over(self, sends, apply, record_bytes):
         n = len(self.doms)
@@ -231,6 +305,10 @@ class LocalCluster:
     def step(self, dt):
         for d in self.doms:
             d.begin(dt)
+        if self.doms[0].recut_due():
+            total = sum(d.x_histogram() for d in self.doms)
+            for d in self.doms:
+                d.apply_recut(total)
         self._hand_over([d.pack_migrants() for d in self.doms], lambda d, a, b: d.apply_migrants(a, b), MIGRANT_RECORD_BYTES)
         for it in range(self.doms[0].eng.iterations):
             self._hand_over([d.pack_halo() for d in self.doms], lambda d, a, b: d.apply_halo(a, b), HALO_RECORD_BYTES)
@@ -238,6 +316,7 @@ class LocalCluster:
                 d.solve(it)
         for d in self.doms:
             d.finish(dt)
+            d.steps_done += 1
 
 
 # ---------------------------------------------------------------- synthetic dam break ----------------------------------------------------------------

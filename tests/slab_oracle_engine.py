@@ -91,6 +91,11 @@ class OracleEngine:
     def set_lambda_range(self, x_min, x_max):
         self.lambda_range = (x_min, x_max)
 
+    def x_histogram(self, x_min, x_max, bins):
+        x = self.pos[:self.n_owned, 0].astype(np.float64)
+        b = np.clip(np.floor((x - x_min) * (bins / (x_max - x_min))).astype(np.int64), 0, bins - 1)
+        return np.bincount(b, minlength=bins).astype(np.int64)
+
     # ---- stages: the oracle runs on owned + ghosts, ghosts are put back afterwards (they are never moved) ----
     def begin_step(self):
         pass

@@ -112,3 +112,43 @@ def test_record_buffer_overflow_is_reported():
         eng.sol.slab_pack_halo(8.0, 15.0, 4.5, buf.data_ptr(), buf.data_ptr(), 8)
     assert e.value.code == psb.PS_ERR_CAPACITY
     eng.sol.close()
+
+
+def test_x_histogram_kernel_matches_numpy():
+    p_or, pos, vel, w, phase, ros = _scene()
+    eng = _ctx_engine(_params(p_or), (pos, vel, w, phase, ros))
+    ref = OracleEngine(p_or, pos, vel, w, phase, ros)
+    for lo, hi, bins in ((0.0, 40.0, 512), (5.0, 12.0, 64), (0.0, 40.0, 65536)):
+        got, want = eng.x_histogram(lo, hi, bins), ref.x_histogram(lo, hi, bins)
+        assert got.sum() == pos.shape[0] == want.sum()
+        assert np.abs(np.cumsum(got) - np.cumsum(want)).max() <= 2   # float32 vs float64 binning: a particle on a bin edge may move by one bin
+    with pytest.raises(psb.PsError):
+        eng.x_histogram(1.0, 1.0, 16)
+    eng.sol.close()
+
+
+def test_recut_on_the_gpu_keeps_the_result_and_balances():
+    p_or, pos, vel, w, phase, ros = _scene(nx=36)
+    p = _params(p_or)
+    steps = 6
+    whole = psb.Solver(p, max_particles=pos.shape[0] + 16)
+    whole.append(pos, vel, w, ros, phase)
+    for _ in range(steps):
+        whole.step(DT)
+    x = pos[:, 0]
+    cuts = [-np.inf, float(np.quantile(x, 0.66)), float(np.quantile(x, 0.83)), np.inf]   # deliberately unbalanced
+    engines = [_ctx_engine(p, part) for part in _split(cuts, pos, vel, w, phase, ros)]
+    n0 = [e.n_owned for e in engines]
+    cl = slab.LocalCluster(engines, cuts, recut_every=1, recut_range=(0.0, 40.0), recut_bins=512)
+    for _ in range(steps):
+        cl.step(DT)
+    n1 = [e.n_owned for e in engines]
+    got_pos = np.concatenate([e.sol.download_owned(psb.ARR_POS) for e in engines])
+    got_vel = np.concatenate([e.sol.download_owned(psb.ARR_VEL) for e in engines])
+    # 6 steps (the other slab tests run 4 at 5e-5): ghosts enter the neighbour sums in another order, the differences compound
+    _match(whole.download(psb.ARR_POS), whole.download(psb.ARR_VEL), got_pos, got_vel, tol=1e-4)
+    assert cl.doms[0].stats["recuts"] == steps - 1
+    assert max(n1) / (sum(n1) / 3) < max(n0) / (sum(n0) / 3) - 0.3, (n0, n1)
+    for e in engines:
+        e.sol.close()
+    whole.close()

@@ -119,3 +119,73 @@ def test_two_processes_over_gloo_match_single_domain(tmp_path):
     got_vel = np.concatenate([z["vel"] for z in parts])
     assert sum(int(z["migrated"]) for z in parts) > 0 and all(int(z["sent"]) > 0 for z in parts)
     _match(ref_pos, ref_vel, got_pos, got_vel, tol=2e-5)
+
+
+def test_balanced_cuts_properties():
+    hist = np.zeros(100, np.int64)
+    hist[10:30] = 50      # all particles in [10, 30)
+    old = [-np.inf, 40.0, 70.0, np.inf]
+    new = slab.balanced_cuts(hist, 0.0, 100.0, old, min_width=5.0, max_shift=8.0)
+    assert new[0] == -np.inf and new[-1] == np.inf
+    assert new[1] == 32.0 and new[2] == 62.0                      # wanted 16.67 and 23.33, limited to a shift of 8 per re-cut
+    for _ in range(10):                                           # repeated re-cuts converge to the quantiles, minimum width kept
+        new = slab.balanced_cuts(hist, 0.0, 100.0, new, min_width=5.0, max_shift=8.0)
+    assert abs(new[1] - (10 + 20 / 3)) < 1e-9 and abs(new[2] - (10 + 40 / 3)) < 1e-9 and new[2] - new[1] >= 5.0
+    tight = slab.balanced_cuts(hist, 0.0, 100.0, new, min_width=9.0, max_shift=8.0)
+    assert tight[2] - tight[1] >= 9.0 - 1e-12
+    assert slab.balanced_cuts(hist, 0.0, 100.0, [-np.inf, np.inf], 5.0, 8.0) == [-np.inf, np.inf]
+
+
+def test_recut_keeps_the_result_and_balances_the_slabs():
+    """cut planes follow the moving block (re-cut every step from the summed x-histograms): same particles as the single
+    domain, better balanced than with fixed planes"""
+    p, pos, vel, w, phase, ros = _scene(nx=36)
+    steps, nranks = 6, 3
+    ref_pos, ref_vel = _single(p, pos, vel, w, phase, ros, steps)
+    # deliberately unbalanced start: 2/3 of the block in the first slab
+    x = pos[:, 0]
+    cuts = [-np.inf, float(np.quantile(x, 0.66)), float(np.quantile(x, 0.83)), np.inf]
+    counts = {}
+    for recut in (0, 1):
+        engines = [OracleEngine(p, a, b, c, d, e) for a, b, c, d, e in _split(cuts, pos, vel, w, phase, ros)]
+        cl = slab.LocalCluster(engines, cuts, recut_every=recut, recut_range=(0.0, 40.0), recut_bins=512)
+        for _ in range(steps):
+            cl.step(DT)
+        got_pos = np.concatenate([e.pos[:e.n_owned] for e in engines])
+        got_vel = np.concatenate([e.vel for e in engines])
+        _match(ref_pos, ref_vel, got_pos, got_vel, tol=2e-5)
+        counts[recut] = [e.n_owned for e in engines]
+        if recut:
+            assert cl.doms[0].stats["recuts"] == steps - 1 and cl.doms[0].cuts != [float(c) for c in cuts]
+            assert all(d.cuts == cl.doms[0].cuts for d in cl.doms)
+    imbalance = {k: max(v) / (sum(v) / len(v)) for k, v in counts.items()}
+    assert imbalance[1] < imbalance[0] - 0.3, (counts, imbalance)
+
+
+def _gloo_recut_worker(rank, world, port, steps, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p, pos, vel, w, phase, ros = _scene(nx=36)
+    cuts = [-np.inf, float(np.quantile(pos[:, 0], 0.7)), np.inf]
+    mine = _split(cuts, pos, vel, w, phase, ros)[rank]
+    eng = OracleEngine(p, *mine)
+    dom = slab.SlabDomain(eng, rank, world, cuts, comm=slab.DistComm(eng), recut_every=1, recut_range=(0.0, 40.0), recut_bins=512)
+    for _ in range(steps):
+        dom.step(DT)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), pos=eng.pos[:eng.n_owned], vel=eng.vel, cuts=np.array(dom.cuts[1:-1]), recuts=dom.stats["recuts"])
+    dist.destroy_process_group()
+
+
+def test_recut_over_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    steps, world = 5, 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_recut_worker, args=(world, port, steps, str(tmp_path)), nprocs=world, join=True)
+    p, pos, vel, w, phase, ros = _scene(nx=36)
+    ref_pos, ref_vel = _single(p, pos, vel, w, phase, ros, steps)
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    _match(ref_pos, ref_vel, np.concatenate([z["pos"] for z in parts]), np.concatenate([z["vel"] for z in parts]), tol=2e-5)
+    assert np.array_equal(parts[0]["cuts"], parts[1]["cuts"]) and int(parts[0]["recuts"]) == steps - 1
+    n = [z["pos"].shape[0] for z in parts]
+    assert max(n) / (sum(n) / 2) < 1.25, n                           # started at 70 / 30
