@@ -7,7 +7,7 @@ RAW=${1:-/tmp/ref_gpu_raw}
 OUT=${2:-gpurun_out/golden}
 REF=oracle/_ref/ref_gpu
 rm -rf "$RAW"; mkdir -p "$RAW" "$OUT"
-for s in 1 2 3 5 6 7 8; do
+for s in ${SCENES:-1 2 3 4 5 6 7 8 9}; do
   $REF --scene $s --mode staged --steps 1 --out "$RAW/scene$s"
 done
 python tests/golden/pack_golden.py "$RAW" "$OUT"

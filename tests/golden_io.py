@@ -7,7 +7,7 @@ import numpy as np
 import oracle_py as orc
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SCENES = ["1", "2", "3", "5", "6", "7", "8"]
+SCENES = ["1", "2", "3", "4", "5", "6", "7", "8", "9"]  # every key-bound scene of the GPU app (particleapp.cpp:141-215)
 DT = np.float32(1.0 / 60.0)
 
 

@@ -18,6 +18,8 @@ SCENES = [
     ("8", dict()),                 # combo: cloths, ropes, solids, pinned sphere (BASELINE config "GPU scene 8")
     ("1", dict()),                 # rope
     ("6", dict()),                 # solids falling on a held cloth
+    ("4", dict()),                 # one solid stack, 6,929 particles
+    ("9", dict()),                 # fifty ropes draped over an immovable sphere
     ("c2", dict(max_particles=66000, side=256)),  # BASELINE config C2 at full size: 256 x 256 cloth, 130,560 distance constraints
 ]
 
@@ -167,7 +169,7 @@ def _run_ref_binary(name, scene, out, mode="staged", steps=1, extra=()):
     return r.stdout
 
 
-@pytest.mark.parametrize("scene", ["7", "8", "5", "3"])
+@pytest.mark.parametrize("scene", ["7", "8", "5", "3", "4", "9"])
 def test_reference_host_on_libpsolver_matches_reference_gpu_golden(scene, tmp_path):
     import sys
     import os
