@@ -186,6 +186,12 @@ int ps_slab_set_lambda_range(PsCtx *ctx, float x_min, float x_max);
  * into the end bins), copied to host_counts[bins].  The ranks' histograms summed are what the slabs are re-cut from. */
 int ps_slab_x_histogram(PsCtx *ctx, float x_min, float x_max, uint32_t bins, uint64_t *host_counts);
 
+/* Diagnostics of the current state, the quantities north_star's 1000-step parity bar is stated in: mean and largest density
+ * error |rho_i / rho0_i - 1| over the fluid particles (rho_i: the lambda pass's estimate, integration_kernel.cuh:565-589, on a
+ * freshly built grid) and the kinetic energy sum 1/2 m v^2 (the CPU app shows it on screen, cpu/src/view.cpp:66-68).  Any
+ * output pointer may be NULL.  Rebuilds the grid and the neighbour lists; positions and velocities are not touched. */
+int ps_fluid_stats(PsCtx *ctx, double *mean_density_error, double *max_density_error, double *kinetic_energy);
+
 /* ---- checkpoints (the reference has no persistence: scenes exist only as code, particleapp.cpp:141-215) ----
  * Everything a run needs to continue bit-identically: parameters, particle arrays, constraint lists in insertion order,
  * rigid bodies, viscosity coefficients, position of the wall-jitter stream. */

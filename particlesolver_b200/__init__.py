@@ -146,6 +146,7 @@ def lib():
                   "pshost_set_particle_to_add", "pshost_set_fluid_to_add", "pshost_make_point_constraint",
                   "pshost_make_distance_constraint", "pshost_get_positions", "pshost_get_velocities"):
             getattr(L, f).restype = None
+        L.ps_fluid_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.ps_add_rigid_body.argtypes = [vp, vp, u64, f32, C.POINTER(u32)]
         L.ps_num_rigid_bodies.argtypes = [vp]
         L.ps_num_rigid_bodies.restype = u64
@@ -338,6 +339,12 @@ class Solver:
     def solve_distance(self): _check(lib().ps_solve_distance(self._h))
     def solve_point(self): _check(lib().ps_solve_point(self._h))
     def update_velocity(self, dt): _check(lib().ps_update_velocity(self._h, dt))
+
+    def fluid_stats(self):
+        """(mean |rho/rho0 - 1|, max |rho/rho0 - 1|, kinetic energy) of the current state"""
+        a, b, k = C.c_double(), C.c_double(), C.c_double()
+        _check(lib().ps_fluid_stats(self._h, C.byref(a), C.byref(b), C.byref(k)))
+        return a.value, b.value, k.value
 
     # --- checkpoints ---
     def save(self, path): _check(lib().ps_save(self._h, os.fsencode(path)))

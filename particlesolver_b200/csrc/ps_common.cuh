@@ -134,6 +134,8 @@ u32 ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos,
 u32 ps_launch_viscosity(float4 *vel, float4 *scratch, const float4 *spos, const int *sphase, const u32 *index, const u32 *cell_begin, u32 n, GridDesc g,
                         const StencilDesc &st, float c_xsph, float vorticity_eps, float dt, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows,
                         cudaStream_t s);
+u32 ps_launch_density_error(float4 *scratch, const float4 *spos, const float *sw, const int *sphase, const u32 *index, const float *ros, const u32 *cell_begin,
+                            u32 n, GridDesc g, const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s);
 // ps_shape_kernels.cu — K12 (not in the reference's GPU solver): shape matching, one warp per rigid body
 void ps_launch_shape_match(float4 *pos, const u32 *body_off, const u32 *body_idx, const float4 *rest, float4 *quat, const float *stiff, u32 num_bodies,
                            int max_iters, cudaStream_t s);

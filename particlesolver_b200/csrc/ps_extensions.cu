@@ -174,6 +174,46 @@ extern "C" int ps_apply_viscosity(PsCtx *c, float dt) {
     return PS_OK;
 }
 
+// Diagnostics of the current state (north_star's long-run parity bar is stated in these): the mean and the largest density
+// error |rho_i / rho0_i - 1| over the fluid particles, rho_i being the K6 estimate on a freshly built grid
+// (integration_kernel.cuh:565-589), and the kinetic energy sum 1/2 m v^2.  Rebuilds the grid and the neighbour lists from the
+// current positions; positions and velocities are not touched.
+extern "C" int ps_fluid_stats(PsCtx *c, double *mean_density_error, double *max_density_error, double *kinetic_energy) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    if (mean_density_error) *mean_density_error = 0.;
+    if (max_density_error) *max_density_error = 0.;
+    if (kinetic_energy) *kinetic_energy = 0.;
+    if (!c->n) return PS_OK;
+    if (c->n_ghost) { ps_set_error("ps_fluid_stats: not for slab contexts holding ghosts"); return PS_ERR_STATE; }
+    DevGuard dg(c->device);
+    int r = ensure_visc_scratch(c);
+    if (r != PS_OK) return r;
+    ps_issue_build_grid(c, c->pos);
+    if ((r = ps_find_neighbors(c)) != PS_OK) return r;
+    const u32 n = c->n;
+    XCU(cudaMemsetAsync(c->visc_scratch, 0, (size_t)n * sizeof(float4), c->stream));
+    ps_launch_density_error(c->visc_scratch, c->spos, c->sw, c->sphase, c->index, c->ros, c->cell_begin, n, c->grid, c->stencil, c->nbr_list, c->nbr_rows,
+                            c->nbr_max_rows, c->stream);
+    std::vector<float> err(4 * (size_t)n), vel(4 * (size_t)n), w(n);
+    std::vector<int> sph(n);
+    XCU(cudaMemcpyAsync(err.data(), c->visc_scratch, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    XCU(cudaMemcpyAsync(sph.data(), c->sphase, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    XCU(cudaMemcpyAsync(vel.data(), c->vel, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    XCU(cudaMemcpyAsync(w.data(), c->w, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    XCU(cudaStreamSynchronize(c->stream));
+    double sum = 0., mx = 0., ke = 0.;
+    uint64_t cnt = 0;
+    for (u32 i = 0; i < n; i++) {
+        if (sph[i] == PH_FLUID) { const double e = err[4 * (size_t)i]; sum += e; mx = std::max(mx, e); cnt++; }
+        if (w[i] != 0.f) ke += 0.5 * ((double)vel[4 * (size_t)i] * vel[4 * (size_t)i] + (double)vel[4 * (size_t)i + 1] * vel[4 * (size_t)i + 1] +
+                                       (double)vel[4 * (size_t)i + 2] * vel[4 * (size_t)i + 2]) / w[i];
+    }
+    if (mean_density_error) *mean_density_error = cnt ? sum / (double)cnt : 0.;
+    if (max_density_error) *max_density_error = mx;
+    if (kinetic_energy) *kinetic_energy = ke;
+    return PS_OK;
+}
+
 // called by ps_step's ready(): scratch must exist before the step is captured into a graph
 int ps_ext_prepare_step(PsCtx *c) {
     if (c->xsph_c == 0.f && c->vorticity_eps == 0.f) return PS_OK;

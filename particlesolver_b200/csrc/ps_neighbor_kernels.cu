@@ -536,6 +536,23 @@ struct ViscosityOp {
     }
 };
 
+// diagnostics: the K6 density estimate of every fluid particle as |rho / rho0 - 1| (the quantity the constraint drives to 0)
+struct DensityErrorOp {
+    const float *__restrict__ sw;
+    const float *__restrict__ ros;
+    float4 *__restrict__ out;  // .x by sorted slot
+    float ro;
+    __device__ __forceinline__ void begin(u32, u32) { ro = 0.f; }
+    __device__ __forceinline__ void operator()(float rx, float ry, float rz, u32) {
+        const float hm2 = PS_H2 - (rx * rx + ry * ry + rz * rz);
+        ro += hm2 * hm2 * hm2;
+    }
+    __device__ __forceinline__ void end(u32 i, u32 orig) {
+        const float rho = (ro + PS_H6) * __fdividef(PS_POLY6, sw[i]);
+        out[i] = make_float4(fabsf(__fdividef(rho, ros[orig]) - 1.f), 0.f, 0.f, 0.f);
+    }
+};
+
 template <class Op>
 __global__ void __launch_bounds__(kListBlock) k_fluid_pass_list(Op op, const float4 *__restrict__ spos, const int *__restrict__ sphase,
                                                                 const u32 *__restrict__ index, const u32 *__restrict__ nbr_list,
@@ -775,4 +792,12 @@ u32 ps_launch_viscosity(float4 *vel, float4 *scratch, const float4 *spos, const 
     launches += launch_fluid_pass(o2, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, max_rows, s);
     k_apply_dv<<<cdiv(n, 256), 256, 0, s>>>(vel, dv, sphase, index, n);
     return launches + 1;
+}
+
+// |rho / rho0 - 1| per fluid particle into scratch[i].x (sorted slot), on the neighbour structure K6 just built
+u32 ps_launch_density_error(float4 *scratch, const float4 *spos, const float *sw, const int *sphase, const u32 *index, const float *ros, const u32 *cell_begin,
+                            u32 n, GridDesc g, const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s) {
+    if (!n) return 0;
+    DensityErrorOp op{sw, ros, scratch};
+    return launch_fluid_pass(op, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, max_rows, s);
 }

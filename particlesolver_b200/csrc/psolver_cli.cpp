@@ -87,11 +87,14 @@ int run_gpu(const Args &a) {
         sum += pos[4 * i] + 2.0 * pos[4 * i + 1] + 3.0 * pos[4 * i + 2];
     }
     if (!a.save.empty()) check(ps_save(ctx, a.save.c_str()), "ps_save");
+    double derr_mean = 0, derr_max = 0;
+    check(ps_fluid_stats(ctx, &derr_mean, &derr_max, nullptr), "ps_fluid_stats");
     if (a.json)
         printf("{\"app\": \"gpu\", \"scene\": \"%s\", \"particles\": %llu, \"steps\": %d, \"dt\": %.9g, \"device_ms_per_step\": %.4f, \"wall_ms_per_step\": %.4f, "
-               "\"particle_steps_per_s\": %.1f, \"kinetic_energy\": %.9g, \"position_checksum\": %.9g, \"launches_per_step\": %u}\n",
+               "\"particle_steps_per_s\": %.1f, \"kinetic_energy\": %.9g, \"position_checksum\": %.9g, \"launches_per_step\": %u, "
+               "\"density_error_mean\": %.6g, \"density_error_max\": %.6g}\n",
                a.scene.c_str(), (unsigned long long)n, a.steps, dt, a.steps ? dev_ms / a.steps : 0., a.steps ? 1e3 * wall / a.steps : 0.,
-               dev_ms > 0 ? n * (double)a.steps / (dev_ms * 1e-3) : 0., ke, sum, ps_launches_per_step(ctx));
+               dev_ms > 0 ? n * (double)a.steps / (dev_ms * 1e-3) : 0., ke, sum, ps_launches_per_step(ctx), derr_mean, derr_max);
     else
         printf("gpu scene %s: %llu particles, %d steps, %.3f ms/step on the device (%.3f wall), KE %.6g\n", a.scene.c_str(), (unsigned long long)n, a.steps,
                a.steps ? dev_ms / a.steps : 0., a.steps ? 1e3 * wall / a.steps : 0., ke);

@@ -248,3 +248,23 @@ def test_gas_with_the_flag_is_a_buoyant_pbf_fluid():
     spread = np.linalg.norm(got - got.mean(0), axis=1).mean() / np.linalg.norm(x - x.mean(0), axis=1).mean()
     assert 0.5 < spread < 3.0                                                 # and is held together / apart by the density constraint
     sol.close()
+
+
+@pytest.mark.parametrize("scene", ["7", "3", "8"])
+def test_fluid_stats_match_the_oracle_estimator(scene):
+    """ps_fluid_stats (mean / max density error, kinetic energy — the quantities of the 1000-step parity bar) against the
+    oracle's estimator on the same state; positions and velocities must come out untouched"""
+    import helpers as H
+    ps = psb.ParticleSystem.scene(scene)
+    sol = ps.solver
+    for _ in range(5):
+        ps.update(1 / 60)
+    pos, vel = sol.download(psb.ARR_POS), sol.download(psb.ARR_VEL)
+    mean, mx, ke = sol.fluid_stats()
+    o = H.oracle_from_solver(sol)
+    omean, omx, oke = o.fluid_stats()
+    assert abs(mean - omean) <= 1e-4 * max(omean, 1e-3) and abs(mx - omx) <= 1e-4 * max(omx, 1e-3), (mean, omean, mx, omx)
+    assert abs(ke - oke) <= 1e-6 * max(oke, 1.0)
+    assert np.array_equal(sol.download(psb.ARR_POS), pos) and np.array_equal(sol.download(psb.ARR_VEL), vel)
+    ps.update(1 / 60)   # and the run goes on (graph replay after the diagnostics pass)
+    ps.close()
