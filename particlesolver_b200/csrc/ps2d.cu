@@ -14,6 +14,7 @@
 // the host when the list changes.  Fluid / gas constraints are Jacobi inside and run as whole kernels at their place in
 // the STANDARD list; their all-pairs neighbour loops (totalfluidconstraint.cpp:52-76) run one warp per particle.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -1146,6 +1147,7 @@ extern "C" int ps2d_get_particle_timers(Ps2dCtx *c, double *t) {
 }
 
 extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
+    struct Range { Range() { nvtxRangePushA("ps2d_tick"); } ~Range() { nvtxRangePop(); } } nvtx;  // ncu / nsys timelines
     if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
     if (!c->n) return PS_OK;
     CU2(cudaSetDevice(c->device));

@@ -477,6 +477,7 @@ extern "C" int ps_begin_step(PsCtx *c) {
 }
 
 extern "C" int ps_predict(PsCtx *c, float dt) {
+    PsNvtxRange nvtx("ps_predict");
     int r = ready(c); if (r != PS_OK) return r;
     DeviceGuard dg(c->device);
     dt = std::min(dt, .05f);
@@ -485,12 +486,14 @@ extern "C" int ps_predict(PsCtx *c, float dt) {
     return check_launch("ps_predict");
 }
 extern "C" int ps_build_grid(PsCtx *c) {
+    PsNvtxRange nvtx("ps_build_grid");
     int r = ready(c); if (r != PS_OK) return r;
     DeviceGuard dg(c->device);
     if (c->n) ps_issue_build_grid(c, c->pos);
     return check_launch("ps_build_grid");
 }
 extern "C" int ps_solve_contacts(PsCtx *c) {
+    PsNvtxRange nvtx("ps_solve_contacts");
     int r = ready(c); if (r != PS_OK) return r;
     if (c->n && !c->grid_valid) { ps_set_error("ps_solve_contacts: no grid (call ps_build_grid)"); return PS_ERR_STATE; }
     DeviceGuard dg(c->device);
@@ -499,6 +502,7 @@ extern "C" int ps_solve_contacts(PsCtx *c) {
     return check_launch("ps_solve_contacts");
 }
 extern "C" int ps_solve_fluid(PsCtx *c) {
+    PsNvtxRange nvtx("ps_solve_fluid");
     int r = ready(c); if (r != PS_OK) return r;
     if (c->n && !c->grid_valid) { ps_set_error("ps_solve_fluid: no grid (call ps_build_grid)"); return PS_ERR_STATE; }
     DeviceGuard dg(c->device);
@@ -511,6 +515,7 @@ extern "C" int ps_solve_fluid(PsCtx *c) {
     return check_launch("ps_solve_fluid");
 }
 extern "C" int ps_collide_world(PsCtx *c, uint32_t iteration) {
+    PsNvtxRange nvtx("ps_collide_world");
     int r = ready(c); if (r != PS_OK) return r;
     if (iteration >= c->rands_iters) { ps_set_error("ps_collide_world: iteration %u out of range", iteration); return PS_ERR_INVALID; }
     DeviceGuard dg(c->device);
@@ -518,6 +523,7 @@ extern "C" int ps_collide_world(PsCtx *c, uint32_t iteration) {
     return check_launch("ps_collide_world");
 }
 extern "C" int ps_solve_distance(PsCtx *c) {
+    PsNvtxRange nvtx("ps_solve_distance");
     int r = ready(c); if (r != PS_OK) return r;
     DeviceGuard dg(c->device);
     ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained,
@@ -525,12 +531,14 @@ extern "C" int ps_solve_distance(PsCtx *c) {
     return check_launch("ps_solve_distance");
 }
 extern "C" int ps_solve_point(PsCtx *c) {
+    PsNvtxRange nvtx("ps_solve_point");
     int r = ready(c); if (r != PS_OK) return r;
     DeviceGuard dg(c->device);
     ps_launch_point(c->pos, c->d_point_idx, c->d_point_xyz, c->num_points, c->stream);
     return check_launch("ps_solve_point");
 }
 extern "C" int ps_update_velocity(PsCtx *c, float dt) {
+    PsNvtxRange nvtx("ps_update_velocity");
     int r = ready(c); if (r != PS_OK) return r;
     DeviceGuard dg(c->device);
     dt = std::min(dt, .05f);
@@ -576,6 +584,7 @@ static u32 issue_step(PsCtx *c, float dt) {
 }
 
 extern "C" int ps_step(PsCtx *c, float dt) {
+    PsNvtxRange nvtx("ps_step");
     int r = ready(c); if (r != PS_OK) return r;
     if (c->n == 0) return PS_OK;  // the reference returns early too (particlesystem.cpp:151-155)
     if (c->n_ghost) { ps_set_error("ps_step: slab contexts with ghosts are stepped stage by stage (halo refresh between stages)"); return PS_ERR_STATE; }
@@ -633,7 +642,12 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
     std::vector<int> tag(max_marks, -1);
     for (auto &e : ev) CU(cudaEventCreate(&e));
     int m = 0;
-    auto mark = [&](int stage, u32 launches) { cudaEventRecord(ev[m], s); tag[m] = stage; if (stage >= 0 && stage_launches) stage_launches[stage] += launches; m++; };
+    // one NVTX range per stage: opened after the previous stage's mark, closed at this stage's mark
+    nvtxRangePushA("predict");
+    auto mark = [&](int stage, u32 launches) {
+        cudaEventRecord(ev[m], s); tag[m] = stage; if (stage >= 0 && stage_launches) stage_launches[stage] += launches; m++;
+        if (stage >= 0) { nvtxRangePop(); nvtxRangePushA("solver stage"); }
+    };
     mark(-1, 0);
     ps_launch_predict(c->pos, c->vel, c->prev, n, dt, make_float3(p.gravity[0], p.gravity[1], p.gravity[2]), s, ps_ctx_gas_phase(c)); mark(0, 1);
     const bool odd = (c->sort_passes & 1) != 0;
@@ -661,6 +675,7 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
     }
     ps_launch_velocity(c->pos, c->prev, c->vel, n, dt, s); mark(11, 1);
     if (c->xsph_c != 0.f || c->vorticity_eps != 0.f) { const u32 l = ps_ext_issue_viscosity(c, dt); mark(11, l); }
+    nvtxRangePop();
     CU(cudaStreamSynchronize(s));
     for (int k = 1; k < m; k++) {
         float ms = 0.f;

@@ -6,6 +6,13 @@
 #include <vector>
 #include "../../include/psolver.h"
 #include "ps_common.cuh"
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX range for the scope (shows up in ncu / nsys timelines; a no-op without a tool attached)
+struct PsNvtxRange {
+    explicit PsNvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~PsNvtxRange() { nvtxRangePop(); }
+};
 
 struct PsCtx {
     int device = 0;
