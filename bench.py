@@ -409,7 +409,9 @@ def run_slabs(args, rank, world, local_rank):
     n_mine = (ix1 - ix0) * plane
     cuts = slab.uniform_cuts(0.0, nx * C5_SPACING, world)
     drift = 0.25
-    halo_cells = int(math.ceil((2 * slab.H + 2 * drift) / 0.5)) + 1
+    exchange_lambda = not args.local_ghost_lambda
+    halo_width = (slab.H + drift) if exchange_lambda else (2 * slab.H + 2 * drift)
+    halo_cells = int(math.ceil(halo_width / 0.5)) + 1
     slab_cells = int(math.ceil((ix1 - ix0) * C5_SPACING / 0.5))
     gx = 1 << int(math.ceil(math.log2(slab_cells + 2 * halo_cells + 8)))  # no aliasing inside a slab + its halo
     p = psb.default_params()
@@ -417,7 +419,7 @@ def run_slabs(args, rank, world, local_rank):
     p.min_bounds[:] = (0, 0, 0)
     p.max_bounds[:] = (int(2 * nx * C5_SPACING), 256, int(C5_NZ * C5_SPACING))
     p.solver_iterations = ITERS
-    halo_cap = int(plane * (2 * slab.H + 2 * drift + 2.0) / C5_SPACING)      # particles within the halo width of a face, with slack
+    halo_cap = int(plane * (halo_width + 2.0) / C5_SPACING)      # particles within the halo width of a face, with slack
     cap = n_mine + 2 * halo_cap + n_mine // 8
     sol = psb.Solver(p, max_particles=cap, device=local_rank)
     step_planes = max(1, (4_000_000 // plane))
@@ -428,7 +430,8 @@ def run_slabs(args, rank, world, local_rank):
     assert sol.n == n_mine
     eng = slab.CtxEngine(sol, halo_capacity=halo_cap, migrant_capacity=max(plane * 2, 1 << 16))
     comm = slab.DistComm(eng) if world > 1 else None
-    dom = slab.SlabDomain(eng, rank, world, cuts, drift=drift, comm=comm)
+    dom = slab.SlabDomain(eng, rank, world, cuts, drift=drift, comm=comm, exchange_lambda=exchange_lambda)
+    assert dom.halo == halo_width
 
     def step():
         if world > 1:
@@ -461,7 +464,8 @@ def run_slabs(args, rank, world, local_rank):
     # kernels launched per step and rank: predict 1 + iterations x (grid build 4 + passes, lambda, delta_p, world, halo select/pack/unpack 4)
     # + migration (select 2 [+ pack 1 + compaction 6 + append 1 when particles leave / arrive]) + velocity 1
     passes = 4 if gx * 512 * 512 > (1 << 24) else 3
-    launches_per_step = 1 + ITERS * (4 + passes + 3 + (4 if world > 1 else 0)) + (2 if world > 1 else 0) + 1
+    # (+ lambda pack / unpack 2 per iteration when the ghost lambdas are exchanged)
+    launches_per_step = 1 + ITERS * (4 + passes + 3 + ((4 + 2 * exchange_lambda) if world > 1 else 0)) + (2 if world > 1 else 0) + 1
 
     # ---- end to end: the step's inputs come from pinned host memory, its result goes back to it ----
     n_cap = cap
@@ -500,8 +504,8 @@ def run_slabs(args, rank, world, local_rank):
         def __init__(self, e): self.e = e
         def __getattr__(self, name):
             f = getattr(self.e, name)
-            if name not in ("predict", "build_grid", "solve_contacts", "solve_fluid", "collide_world", "update_velocity", "pack_halo",
-                            "set_ghosts", "pack_migrants", "append_migrants"):
+            if name not in ("predict", "build_grid", "solve_contacts", "solve_fluid", "solve_fluid_lambda", "solve_fluid_delta", "collide_world",
+                            "update_velocity", "pack_halo", "set_ghosts", "pack_lambda", "set_ghost_lambda", "pack_migrants", "append_migrants"):
                 return f
             def g(*a, **k):
                 sol.timer_start(); r = f(*a, **k); acc[name] = acc.get(name, 0.0) + sol.timer_stop(); return r
@@ -513,7 +517,7 @@ def run_slabs(args, rank, world, local_rank):
     dom.eng = eng
     peak, peak_kind = measured_peaks()
     n_local = sol.n  # owned + ghosts: what the kernels process
-    fluid_ms = acc.get("solve_fluid", 0.0) / prof_steps / ITERS
+    fluid_ms = (acc.get("solve_fluid", 0.0) + acc.get("solve_fluid_lambda", 0.0) + acc.get("solve_fluid_delta", 0.0)) / prof_steps / ITERS
     fluid_bytes = (36 + 64) * n_local  # K6 + K7, SURVEY 8(d)
     stage_ms = {k: round(v / prof_steps, 4) for k, v in acc.items()}
     roofline = {"kernel": "lambda+delta_p (solve_fluid stage: k_find_lambdas + k_solve_fluids)", "bound": "hbm",
@@ -525,7 +529,8 @@ def run_slabs(args, rank, world, local_rank):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if weak else "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"c5: synthetic PBF dam break, {total} particles ({nx} x {C5_NY} x {C5_NZ} lattice, spacing 2.5 r, rho0 4.1), "
-                                       f"{world} x-slab(s), ghost halo {2 * slab.H + 2 * drift} wide refreshed every solver iteration, migration every step, "
+                                       f"{world} x-slab(s), ghost halo {halo_width} wide refreshed every solver iteration, "
+                                       f"ghost lambdas {'received from their owners between K6 and K7' if exchange_lambda else 'computed locally'}, migration every step, "
                                        f"per-rank grid {gx} x 512 x 512, 5 solver iterations, dt=1/60",
                            "particles_total": total, "particles_per_gpu": [int(owned_min), int(owned_max)], "ghosts_total": int(ghosts),
                            "exchange": "torch.distributed send/recv over NCCL between neighbouring ranks" if world > 1 else "none",
@@ -556,6 +561,8 @@ def main():
         real_stdout.flush()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--local-ghost-lambda", action="store_true",
+                    help="c5: compute ghost lambdas locally (halo 2H + 2 drift) instead of exchanging them between K6 and K7 (halo H + drift)")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

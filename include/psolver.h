@@ -139,6 +139,8 @@ int ps_predict(PsCtx *ctx, float dt);        /* K1  integrateSystem             
 int ps_build_grid(PsCtx *ctx);               /* K2-K4 calcHash, sortParticles, reorderDataAndFindCellStart */
 int ps_solve_contacts(PsCtx *ctx);           /* K5  collide                       integration.cu:338-386 */
 int ps_solve_fluid(PsCtx *ctx);              /* K6+K7 solveFluids                 integration.cu:453-508 */
+int ps_solve_fluid_lambda(PsCtx *ctx);       /* K6 alone  findLambdasD            integration_kernel.cuh:521-593 */
+int ps_solve_fluid_delta(PsCtx *ctx);        /* K7 alone  solveFluidsD            integration_kernel.cuh:596-642 */
 int ps_collide_world(PsCtx *ctx, uint32_t iteration); /* K8 collideWorld          integration.cu:319-336 */
 int ps_solve_distance(PsCtx *ctx);           /* K9  solveDistanceConstraints      solver.cu:196-231 */
 int ps_solve_point(PsCtx *ctx);              /* K10 solvePointConstraints         solver.cu:180-194 */
@@ -180,6 +182,12 @@ int ps_slab_set_ghosts(PsCtx *ctx, const void *from_left, uint64_t n_left, const
 int ps_slab_pack_migrants(PsCtx *ctx, float x_lo, float x_hi, void *left_buf, void *right_buf, uint64_t capacity_records, uint32_t counts[2]);
 /* appends received migrants as owned particles (left neighbour's first) */
 int ps_slab_append_migrants(PsCtx *ctx, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right);
+/* Lambda exchange (the K6 -> K7 dependency across a face): between ps_solve_fluid_lambda and ps_solve_fluid_delta a rank
+ * sends the lambdas of the particles of its last ps_slab_pack_halo — one float per record, in record order, counts[] = the
+ * halo pack's — and hands the values received for its own ghosts (left neighbour's first) to ps_slab_set_ghost_lambda.
+ * With the exchange the halo need only be H (+ drift) wide and K6 skips the ghosts (ps_slab_set_lambda_range(ctx, 1, -1)). */
+int ps_slab_pack_lambda(PsCtx *ctx, void *left_buf, void *right_buf, uint64_t capacity_values, uint32_t counts[2]);
+int ps_slab_set_ghost_lambda(PsCtx *ctx, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right);
 /* lambda is computed for owned particles and for ghosts with x in [x_min, x_max] only (default: everywhere) */
 int ps_slab_set_lambda_range(PsCtx *ctx, float x_min, float x_max);
 /* load balancing: counts of the owned particles' x in `bins` (<= 65536) equal bins of [x_min, x_max) (values outside fall

@@ -254,9 +254,12 @@ static u32 fluid_neighbors(const OrParams *p, const float *spos, const u32 *cell
 /* ---- K6 + K7: solveFluids = findLambdasD then solveFluidsD (integration.cu:453-508,
  *      integration_kernel.cuh:521-642).  lambda[] and num_neighbors[] are persistent, indexed by SORTED slot
  *      and only written at fluid slots (non-fluid neighbours contribute whatever the slot last held). ---- */
-void or_solve_fluids(const float *spos, const float *sw, const int *sphase, const u32 *index, const u32 *cell_start,
-                     const u32 *cell_end, float *pos, u32 n, const OrParams *p, const float *ros, float *lambda,
-                     u32 *num_neighbors) {
+/* stages: 1 = lambda (findLambdasD), 2 = delta p (solveFluidsD), 3 = both.  The two halves can be called separately — a
+ * slab-decomposed run exchanges ghost lambdas in between (tests/slab_oracle_engine.py); the second half then gathers the
+ * neighbour lists again, which yields the lists the first half saw (positions in spos do not change in between). */
+void or_solve_fluids_stages(const float *spos, const float *sw, const int *sphase, const u32 *index, const u32 *cell_start,
+                            const u32 *cell_end, float *pos, u32 n, const OrParams *p, const float *ros, float *lambda,
+                            u32 *num_neighbors, int stages) {
     u32 **lists = (u32 **)calloc(n, sizeof(u32 *));
     #pragma omp parallel
     {
@@ -268,6 +271,7 @@ void or_solve_fluids(const float *spos, const float *sw, const int *sphase, cons
             num_neighbors[i] = nn;
             lists[i] = (u32 *)malloc((nn ? nn : 1) * sizeof(u32));
             memcpy(lists[i], nb, nn * sizeof(u32));
+            if (!(stages & 1)) continue;
             const float *x = spos + 4 * (size_t)i;
             float w = sw[i];
             float ro0 = ros[index[i]];
@@ -298,7 +302,7 @@ void or_solve_fluids(const float *spos, const float *sw, const int *sphase, cons
         /* implicit barrier: all lambdas written before any Δp reads them (two kernel launches) */
         #pragma omp for schedule(dynamic, 64)
         for (u32 i = 0; i < n; i++) {
-            if (sphase[i] != PH_FLUID) continue;
+            if (sphase[i] != PH_FLUID || !(stages & 2)) continue;
             u32 nn = num_neighbors[i];
             const u32 *l = lists[i];
             const float *x = spos + 4 * (size_t)i;
@@ -331,6 +335,11 @@ void or_solve_fluids(const float *spos, const float *sw, const int *sphase, cons
     }
     for (u32 i = 0; i < n; i++) free(lists[i]);
     free(lists);
+}
+void or_solve_fluids(const float *spos, const float *sw, const int *sphase, const u32 *index, const u32 *cell_start,
+                     const u32 *cell_end, float *pos, u32 n, const OrParams *p, const float *ros, float *lambda,
+                     u32 *num_neighbors) {
+    or_solve_fluids_stages(spos, sw, sphase, index, cell_start, cell_end, pos, n, p, ros, lambda, num_neighbors, 3);
 }
 
 /* ---- K8: collideWorld / collide_world_functor (integration.cu:319-336, integration_kernel.cuh:57-157).

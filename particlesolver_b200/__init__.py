@@ -98,7 +98,8 @@ def lib():
         L.ps_step.argtypes = [vp, f32]
         L.ps_sync.argtypes = [vp]
         L.ps_last_step_ms.argtypes = [vp, C.POINTER(f32)]
-        for f in ("ps_begin_step", "ps_build_grid", "ps_solve_contacts", "ps_solve_fluid", "ps_solve_distance", "ps_solve_point"):
+        for f in ("ps_begin_step", "ps_build_grid", "ps_solve_contacts", "ps_solve_fluid", "ps_solve_fluid_lambda", "ps_solve_fluid_delta", "ps_solve_distance",
+                  "ps_solve_point"):
             getattr(L, f).argtypes = [vp]
         L.ps_predict.argtypes = [vp, f32]
         L.ps_update_velocity.argtypes = [vp, f32]
@@ -115,6 +116,8 @@ def lib():
         L.ps_slab_pack_migrants.argtypes = [vp, f32, f32, vp, vp, u64, C.POINTER(u32 * 2)]
         L.ps_slab_append_migrants.argtypes = [vp, vp, u64, vp, u64]
         L.ps_slab_set_lambda_range.argtypes = [vp, f32, f32]
+        L.ps_slab_pack_lambda.argtypes = [vp, vp, vp, u64, C.POINTER(u32 * 2)]
+        L.ps_slab_set_ghost_lambda.argtypes = [vp, vp, u64, vp, u64]
         L.ps_slab_x_histogram.argtypes = [vp, f32, f32, u32, vp]
         # C++ host class (csrc/particle_system.cpp)
         L.pshost_create.argtypes = [f32, u32, u32, u32, u32, vp, vp, i32]
@@ -335,6 +338,8 @@ class Solver:
     def build_grid(self): _check(lib().ps_build_grid(self._h))
     def solve_contacts(self): _check(lib().ps_solve_contacts(self._h))
     def solve_fluid(self): _check(lib().ps_solve_fluid(self._h))
+    def solve_fluid_lambda(self): _check(lib().ps_solve_fluid_lambda(self._h))
+    def solve_fluid_delta(self): _check(lib().ps_solve_fluid_delta(self._h))
     def collide_world(self, iteration): _check(lib().ps_collide_world(self._h, iteration))
     def solve_distance(self): _check(lib().ps_solve_distance(self._h))
     def solve_point(self): _check(lib().ps_solve_point(self._h))
@@ -440,6 +445,14 @@ class Solver:
 
     def slab_set_lambda_range(self, x_min, x_max):
         _check(lib().ps_slab_set_lambda_range(self._h, max(x_min, -3.0e38), min(x_max, 3.0e38)))
+
+    def slab_pack_lambda(self, left_ptr, right_ptr, capacity):
+        c = (C.c_uint32 * 2)()
+        _check(lib().ps_slab_pack_lambda(self._h, left_ptr, right_ptr, capacity, C.byref(c)))
+        return int(c[0]), int(c[1])
+
+    def slab_set_ghost_lambda(self, left_ptr, n_left, right_ptr, n_right):
+        _check(lib().ps_slab_set_ghost_lambda(self._h, left_ptr, n_left, right_ptr, n_right))
 
     def download_owned(self, which):
         """The owned particles' part of a per-particle array (ghosts follow them)."""

@@ -143,7 +143,12 @@ void ps_launch_shape_match(float4 *pos, const u32 *body_off, const u32 *body_idx
 size_t ps_slab_scratch_elems(u32 n);
 void ps_launch_slab_select(const float4 *pos, u32 n, float left_below, float right_from, u32 *scratch, cudaStream_t s);
 void ps_launch_slab_pack_halo(const float4 *pos, const float *w, const float *ros, const int *phase, u32 n, float left_below, float right_from,
-                              const u32 *scratch, void *left, void *right, u32 cap, cudaStream_t s);
+                              const u32 *scratch, void *left, void *right, u32 cap, cudaStream_t s, u32 *ranks = nullptr);
+// lambda exchange: ranks = uint2[n_owned] written by the halo pack (position of each owned particle in the two halo buffers)
+void ps_launch_slab_pack_lambda(const float *lambda, const u32 *index, const u32 *ranks, u32 n, u32 n_owned, float *left, float *right, u32 cap,
+                                cudaStream_t s);
+void ps_launch_slab_unpack_lambda(float *lambda, const u32 *index, u32 n, u32 n_owned, const float *from_left, u32 n_left, const float *from_right,
+                                  cudaStream_t s);
 void ps_launch_slab_unpack_halo(float4 *pos, float *w, float *ros, int *phase, u32 first, const void *from_left, u32 n_left, const void *from_right,
                                 u32 n_right, cudaStream_t s);
 void ps_launch_slab_pack_migrants(const float4 *pos, const float4 *prev, const float4 *vel, const float *w, const float *ros, const int *phase, u32 n,

@@ -265,7 +265,7 @@ extern "C" int ps_destroy(PsCtx *c) {
     if (c->gen) curandDestroyGenerator(c->gen);
     void *ptrs[] = {c->pos, c->vel, c->prev, c->spos, c->w, c->ros, c->sw, c->lambda, c->phase, c->sphase, c->hash, c->index, c->hash_tmp,
                     c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->chunk_lb,
-                    c->sort_status, c->rands, c->slab_scratch, c->nbr_list, c->nbr_rows ? c->nbr_rows - 4 : nullptr, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
+                    c->sort_status, c->rands, c->slab_scratch, c->slab_ranks, c->nbr_list, c->nbr_rows ? c->nbr_rows - 4 : nullptr, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
                     c->d_point_xyz, c->dist_scratch};
     for (void *p : ptrs) if (p) cudaFree(p);
     ps_ext_free(c);
@@ -501,19 +501,25 @@ extern "C" int ps_solve_contacts(PsCtx *c) {
                       c->params.particle_radius, c->stream);
     return check_launch("ps_solve_contacts");
 }
-extern "C" int ps_solve_fluid(PsCtx *c) {
-    PsNvtxRange nvtx("ps_solve_fluid");
+static int issue_fluid(PsCtx *c, const char *what, bool do_lambda, bool do_delta) {
+    PsNvtxRange nvtx(what);
     int r = ready(c); if (r != PS_OK) return r;
-    if (c->n && !c->grid_valid) { ps_set_error("ps_solve_fluid: no grid (call ps_build_grid)"); return PS_ERR_STATE; }
+    if (c->n && !c->grid_valid) { ps_set_error("%s: no grid (call ps_build_grid)", what); return PS_ERR_STATE; }
     DeviceGuard dg(c->device);
-    // lambda is needed for the ghosts next to a face too (their owners are on another GPU): see ps_slab_set_lambda_range
-    ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost,
-                           c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list,
-                           c->nbr_rows, c->nbr_max_rows, c->stream);
-    ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost, c->grid, c->stencil,
-                           c->params.omega, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
-    return check_launch("ps_solve_fluid");
+    // lambda is needed for the ghosts next to a face too (their owners are on another GPU): computed here for the ghosts inside
+    // ps_slab_set_lambda_range, or received from the owners between the two halves (ps_slab_pack_lambda / ps_slab_set_ghost_lambda)
+    if (do_lambda)
+        ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost,
+                               c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list,
+                               c->nbr_rows, c->nbr_max_rows, c->stream);
+    if (do_delta)
+        ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost, c->grid, c->stencil,
+                               c->params.omega, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
+    return check_launch(what);
 }
+extern "C" int ps_solve_fluid(PsCtx *c) { return issue_fluid(c, "ps_solve_fluid", true, true); }
+extern "C" int ps_solve_fluid_lambda(PsCtx *c) { return issue_fluid(c, "ps_solve_fluid_lambda", true, false); }
+extern "C" int ps_solve_fluid_delta(PsCtx *c) { return issue_fluid(c, "ps_solve_fluid_delta", false, true); }
 extern "C" int ps_collide_world(PsCtx *c, uint32_t iteration) {
     PsNvtxRange nvtx("ps_collide_world");
     int r = ready(c); if (r != PS_OK) return r;
@@ -806,6 +812,17 @@ static int slab_ready(PsCtx *c, const char *what) {
         c->slab_scratch_elems = need;
     }
     if (!c->slab_counts_host) CU(cudaMallocHost((void **)&c->slab_counts_host, 2 * sizeof(u32)));
+    if (c->slab_ranks_cap < c->capacity) {  // the arrays grew (ghosts arriving): keep the ranks of the last halo pack
+        u32 *grown = nullptr;
+        CU(cudaMalloc((void **)&grown, 2 * c->capacity * sizeof(u32)));
+        if (c->slab_ranks) {
+            CU(cudaMemcpyAsync(grown, c->slab_ranks, 2 * c->slab_ranks_cap * sizeof(u32), cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            CU(cudaFree(c->slab_ranks));
+        }
+        c->slab_ranks = grown;
+        c->slab_ranks_cap = c->capacity;
+    }
     return PS_OK;
 }
 static int slab_fetch_counts(PsCtx *c, u32 n, uint32_t counts[2]) {
@@ -824,9 +841,13 @@ extern "C" int ps_slab_pack_halo(PsCtx *c, float x_lo, float x_hi, float width, 
     const u32 owned = c->n - c->n_ghost;
     const float left_below = x_lo + width, right_from = x_hi - width;
     ps_launch_slab_select(c->pos, owned, left_below, right_from, c->slab_scratch, c->stream);
-    ps_launch_slab_pack_halo(c->pos, c->w, c->ros, c->phase, owned, left_below, right_from, c->slab_scratch, left_buf, right_buf, (u32)std::min<uint64_t>(cap, 0xffffffffu), c->stream);
+    ps_launch_slab_pack_halo(c->pos, c->w, c->ros, c->phase, owned, left_below, right_from, c->slab_scratch, left_buf, right_buf, (u32)std::min<uint64_t>(cap, 0xffffffffu), c->stream,
+                             c->slab_ranks);
     if ((r = check_launch("ps_slab_pack_halo")) != PS_OK) return r;
     if ((r = slab_fetch_counts(c, owned, counts)) != PS_OK) return r;
+    c->slab_halo_counts[0] = counts[0];
+    c->slab_halo_counts[1] = counts[1];
+    c->slab_ranks_valid = true;
     if (counts[0] > cap || counts[1] > cap) { ps_set_error("ps_slab_pack_halo: %u / %u records exceed the buffer capacity %llu", counts[0], counts[1], (unsigned long long)cap); return PS_ERR_CAPACITY; }
     return PS_OK;
 }
@@ -841,8 +862,33 @@ extern "C" int ps_slab_set_ghosts(PsCtx *c, const void *from_left, uint64_t n_le
     return check_launch("ps_slab_set_ghosts");
 }
 
+// lambda exchange between K6 and K7 (ps_solve_fluid_lambda / ps_solve_fluid_delta): one float per record of the last halo pack,
+// in the order of those records
+extern "C" int ps_slab_pack_lambda(PsCtx *c, void *left_buf, void *right_buf, uint64_t cap, uint32_t counts[2]) {
+    int r = slab_ready(c, "ps_slab_pack_lambda"); if (r != PS_OK) return r;
+    if (!counts || ((!left_buf || !right_buf) && cap)) { ps_set_error("ps_slab_pack_lambda: null argument"); return PS_ERR_INVALID; }
+    if (!c->slab_ranks_valid) { ps_set_error("ps_slab_pack_lambda: no halo pack to answer (call ps_slab_pack_halo first)"); return PS_ERR_STATE; }
+    if (c->n && !c->grid_valid) { ps_set_error("ps_slab_pack_lambda: no grid (lambda lives by sorted slot)"); return PS_ERR_STATE; }
+    counts[0] = c->slab_halo_counts[0];
+    counts[1] = c->slab_halo_counts[1];
+    if (counts[0] > cap || counts[1] > cap) { ps_set_error("ps_slab_pack_lambda: %u / %u values exceed the buffer capacity %llu", counts[0], counts[1], (unsigned long long)cap); return PS_ERR_CAPACITY; }
+    DeviceGuard dg(c->device);
+    ps_launch_slab_pack_lambda(c->lambda, c->index, c->slab_ranks, c->n, c->n - c->n_ghost, (float *)left_buf, (float *)right_buf, (u32)std::min<uint64_t>(cap, 0xffffffffu), c->stream);
+    return check_launch("ps_slab_pack_lambda");
+}
+extern "C" int ps_slab_set_ghost_lambda(PsCtx *c, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right) {
+    int r = slab_ready(c, "ps_slab_set_ghost_lambda"); if (r != PS_OK) return r;
+    if ((n_left && !from_left) || (n_right && !from_right)) { ps_set_error("ps_slab_set_ghost_lambda: null buffer"); return PS_ERR_INVALID; }
+    if (n_left + n_right != c->n_ghost) { ps_set_error("ps_slab_set_ghost_lambda: %llu + %llu values for %u ghosts", (unsigned long long)n_left, (unsigned long long)n_right, c->n_ghost); return PS_ERR_INVALID; }
+    if (c->n && !c->grid_valid) { ps_set_error("ps_slab_set_ghost_lambda: no grid (lambda lives by sorted slot)"); return PS_ERR_STATE; }
+    DeviceGuard dg(c->device);
+    ps_launch_slab_unpack_lambda(c->lambda, c->index, c->n, c->n - c->n_ghost, (const float *)from_left, (u32)n_left, (const float *)from_right, c->stream);
+    return check_launch("ps_slab_set_ghost_lambda");
+}
+
 extern "C" int ps_slab_pack_migrants(PsCtx *c, float x_lo, float x_hi, void *left_buf, void *right_buf, uint64_t cap, uint32_t counts[2]) {
     int r = slab_ready(c, "ps_slab_pack_migrants"); if (r != PS_OK) return r;
+    c->slab_ranks_valid = false;  // particle indices change
     if (!counts || ((!left_buf || !right_buf) && cap)) { ps_set_error("ps_slab_pack_migrants: null argument"); return PS_ERR_INVALID; }
     if (!(x_lo < x_hi)) { ps_set_error("ps_slab_pack_migrants: empty slab [%g, %g)", x_lo, x_hi); return PS_ERR_INVALID; }
     if ((r = ps_set_ghost_count(c, 0)) != PS_OK) return r;

@@ -95,6 +95,10 @@ struct PsCtx {
     u32 *slab_scratch = nullptr;
     size_t slab_scratch_elems = 0;
     u32 *slab_counts_host = nullptr;  // pinned, 2 words
+    u32 *slab_ranks = nullptr;        // uint2 per owned particle: its record's position in the last halo pack's two buffers (lambda exchange)
+    uint64_t slab_ranks_cap = 0;
+    u32 slab_halo_counts[2] = {0, 0}; // records of the last halo pack
+    bool slab_ranks_valid = false;
     float lambda_xmin = -3.0e38f, lambda_xmax = 3.0e38f;
 };
 

@@ -18,6 +18,7 @@ constexpr int kTile = kBlock * kItems;  // 2048 particles per CTA
 struct HaloRec { float4 pos; float w, ros; int phase; u32 pad; };
 struct MigrantRec { float4 pos, prev, vel; float w, ros; int phase; u32 pad; };
 static_assert(sizeof(HaloRec) == 32 && sizeof(MigrantRec) == 64, "record sizes are part of the wire format");
+constexpr u32 kNoRank = 0xffffffffu;
 
 // class of a particle: 0 = stays / not selected, 1 = left buffer, 2 = right buffer (3 = both, halo of a thin slab)
 __device__ __forceinline__ u32 classify(float x, float left_below, float right_from) { return (x < left_below ? 1u : 0u) | (x >= right_from ? 2u : 0u); }
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(1024) k_slab_scan_tiles(u32 *__restrict__ tile
 __global__ void __launch_bounds__(kBlock) k_slab_pack_halo(const float4 *__restrict__ pos, const float *__restrict__ w, const float *__restrict__ ros,
                                                            const int *__restrict__ phase, u32 n, float left_below, float right_from,
                                                            const u32 *__restrict__ tile_offsets, HaloRec *__restrict__ left, HaloRec *__restrict__ right,
-                                                           u32 cap) {
+                                                           u32 cap, uint2 *__restrict__ ranks) {
     __shared__ u32 sm[kBlock / 32];
     const u32 base = blockIdx.x * kTile + threadIdx.x * kItems;
     u32 cls[kItems], cl = 0, cr = 0;
@@ -116,13 +117,42 @@ __global__ void __launch_bounds__(kBlock) k_slab_pack_halo(const float4 *__restr
     u32 orr = tile_offsets[2 * blockIdx.x + 1] + block_excl_scan(cr, sm, dummy);
 #pragma unroll
     for (int k = 0; k < kItems; k++) {
-        if (!cls[k]) continue;
         const u32 i = base + k;
+        // where particle i went in the two buffers (kNoRank: not selected), for the lambda exchange that follows K6
+        if (ranks && i < n) ranks[i] = make_uint2((cls[k] & 1u) ? ol : kNoRank, (cls[k] & 2u) ? orr : kNoRank);
+        if (!cls[k]) continue;
         HaloRec r;
         r.pos = pos[i]; r.w = w[i]; r.ros = ros[i]; r.phase = phase[i]; r.pad = 0;
         if (cls[k] & 1u) { if (ol < cap) left[ol] = r; ol++; }
         if (cls[k] & 2u) { if (orr < cap) right[orr] = r; orr++; }
     }
+}
+
+// ---- lambda exchange (the K6 -> K7 dependency across a face) ----
+// K7 reads lambda_j of every neighbour j of an owned particle; for a ghost j that value belongs to the rank that owns j.
+// After K6 each rank sends the lambdas of the particles it put into the halo buffers — in the order of those records, so
+// lambda k of a message belongs to ghost k of the receiver — and the receiver drops them into the ghosts' sorted slots.
+// lambda lives by SORTED slot (index[slot] = particle), the halo ranks by particle.
+__global__ void __launch_bounds__(kBlock) k_slab_pack_lambda(const float *__restrict__ lambda, const u32 *__restrict__ index, const uint2 *__restrict__ ranks,
+                                                             u32 n, u32 n_owned, float *__restrict__ left, float *__restrict__ right, u32 cap) {
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const u32 orig = __ldg(index + i);
+    if (orig >= n_owned) return;
+    const uint2 r = __ldg(ranks + orig);
+    if (r.x == kNoRank && r.y == kNoRank) return;
+    const float l = lambda[i];
+    if (r.x < cap) left[r.x] = l;
+    if (r.y < cap) right[r.y] = l;
+}
+__global__ void __launch_bounds__(kBlock) k_slab_unpack_lambda(float *__restrict__ lambda, const u32 *__restrict__ index, u32 n, u32 n_owned,
+                                                               const float *__restrict__ from_left, u32 n_left, const float *__restrict__ from_right) {
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const u32 orig = __ldg(index + i);
+    if (orig < n_owned) return;
+    const u32 k = orig - n_owned;  // ghosts sit behind the owned particles, the left neighbour's first (k_slab_unpack_halo)
+    lambda[i] = k < n_left ? __ldg(from_left + k) : __ldg(from_right + (k - n_left));
 }
 
 // ghosts received from the two neighbours -> the tails of the SoA arrays, left neighbour's first
@@ -213,9 +243,20 @@ void ps_launch_slab_select(const float4 *pos, u32 n, float left_below, float rig
     k_slab_scan_tiles<<<1, 1024, 0, s>>>(scratch, tiles, scratch + 2 * tiles);
 }
 void ps_launch_slab_pack_halo(const float4 *pos, const float *w, const float *ros, const int *phase, u32 n, float left_below, float right_from,
-                              const u32 *scratch, void *left, void *right, u32 cap, cudaStream_t s) {
+                              const u32 *scratch, void *left, void *right, u32 cap, cudaStream_t s, u32 *ranks) {
     if (!n) return;
-    k_slab_pack_halo<<<cdiv(n, kTile), kBlock, 0, s>>>(pos, w, ros, phase, n, left_below, right_from, scratch, (HaloRec *)left, (HaloRec *)right, cap);
+    k_slab_pack_halo<<<cdiv(n, kTile), kBlock, 0, s>>>(pos, w, ros, phase, n, left_below, right_from, scratch, (HaloRec *)left, (HaloRec *)right, cap,
+                                                      (uint2 *)ranks);
+}
+void ps_launch_slab_pack_lambda(const float *lambda, const u32 *index, const u32 *ranks, u32 n, u32 n_owned, float *left, float *right, u32 cap,
+                                cudaStream_t s) {
+    if (!n) return;
+    k_slab_pack_lambda<<<cdiv(n, kBlock), kBlock, 0, s>>>(lambda, index, (const uint2 *)ranks, n, n_owned, left, right, cap);
+}
+void ps_launch_slab_unpack_lambda(float *lambda, const u32 *index, u32 n, u32 n_owned, const float *from_left, u32 n_left, const float *from_right,
+                                  cudaStream_t s) {
+    if (!n || n == n_owned) return;
+    k_slab_unpack_lambda<<<cdiv(n, kBlock), kBlock, 0, s>>>(lambda, index, n, n_owned, from_left, n_left, from_right);
 }
 void ps_launch_slab_unpack_halo(float4 *pos, float *w, float *ros, int *phase, u32 first, const void *from_left, u32 n_left, const void *from_right,
                                 u32 n_right, cudaStream_t s) {

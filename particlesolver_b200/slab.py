@@ -16,9 +16,13 @@ Only the exchange itself happens here (torch.distributed send/recv between neigh
 the GPU box, gloo in the CPU tests); selection, packing, compaction and unpacking are CUDA kernels behind the C ABI
 (ps_slab_* in include/psolver.h).  There is no data-path collective besides that neighbour exchange.
 
-Halo width.  K7 reads lambda_j of every neighbour j of an owned particle i.  Ghost lambdas are computed locally instead
-of being exchanged: a ghost within H (+ drift) of the face has its whole neighbourhood inside a 2H-wide halo, so its
-local lambda equals its owner's up to summation order.  halo = 2H + 2*drift, lambda range = face +- (H + drift), where
+Halo width.  K7 reads lambda_j of every neighbour j of an owned particle i, ghosts included.  Two ways to have them:
+  * exchange_lambda=True (default): between K6 and K7 every rank sends the lambdas of the particles it
+    put into its halo buffers (4 bytes per record, same order, so no counts travel) and K6 skips the ghosts altogether.
+    halo = H + drift: just the neighbours of the owned particles.
+  * exchange_lambda=False: ghost lambdas are computed locally.  A ghost within H (+ drift) of the face has its whole
+    neighbourhood inside a 2H-wide halo, so its local lambda equals its owner's up to summation order:
+    halo = 2H + 2*drift, lambda range = face +- (H + drift).  Twice the ghosts and K6 work for them, one message less.
 `drift` bounds how far a particle moves inside the solver iterations of one step (migration runs once per step, right
 after the predict, which is where velocities move particles).
 """
@@ -28,6 +32,7 @@ import numpy as np
 
 H = 2.0  # PBF support radius, reference gpu/src/cuda/integration_kernel.cuh:25
 HALO_RECORD_BYTES = 32
+LAMBDA_RECORD_BYTES = 4
 MIGRANT_RECORD_BYTES = 64
 
 
@@ -95,6 +100,7 @@ class CtxEngine:
         self.halo_cap, self.migr_cap = int(halo_capacity), int(migrant_capacity)
         self.halo_send = (mk(halo_capacity, HALO_RECORD_BYTES), mk(halo_capacity, HALO_RECORD_BYTES))
         self.migr_send = (mk(migrant_capacity, MIGRANT_RECORD_BYTES), mk(migrant_capacity, MIGRANT_RECORD_BYTES))
+        self.lam_send = (mk(halo_capacity, LAMBDA_RECORD_BYTES), mk(halo_capacity, LAMBDA_RECORD_BYTES))
 
     # records in, records out (torch uint8 tensors [count, record_bytes] on the engine's device)
     def empty_records(self, count, record_bytes):
@@ -121,6 +127,15 @@ class CtxEngine:
     def set_lambda_range(self, x_min, x_max):
         self.sol.slab_set_lambda_range(x_min, x_max)
 
+    def pack_lambda(self):
+        nl, nr = self.sol.slab_pack_lambda(self.lam_send[0].data_ptr(), self.lam_send[1].data_ptr(), self.halo_cap)
+        return self.lam_send[0][:nl], self.lam_send[1][:nr]
+
+    def set_ghost_lambda(self, from_left, from_right):
+        self._keep_l = (from_left, from_right)
+        self.sol.slab_set_ghost_lambda(from_left.data_ptr() if from_left.shape[0] else None, from_left.shape[0],
+                                       from_right.data_ptr() if from_right.shape[0] else None, from_right.shape[0])
+
     def x_histogram(self, x_min, x_max, bins):
         return self.sol.slab_x_histogram(x_min, x_max, bins)
 
@@ -130,6 +145,8 @@ class CtxEngine:
     def build_grid(self): self.sol.build_grid()
     def solve_contacts(self): self.sol.solve_contacts()
     def solve_fluid(self): self.sol.solve_fluid()
+    def solve_fluid_lambda(self): self.sol.solve_fluid_lambda()
+    def solve_fluid_delta(self): self.sol.solve_fluid_delta()
     def collide_world(self, it): self.sol.collide_world(it)
     def update_velocity(self, dt): self.sol.update_velocity(dt)
     def sync(self): self.sol.sync()
@@ -152,17 +169,22 @@ class DistComm:
         self.count_device = getattr(engine, "device", torch.device("cpu"))
         self.bytes_sent = 0
 
-    def exchange(self, to_left, to_right, record_bytes):
-        """Send `to_left` to rank-1 and `to_right` to rank+1; returns (from_left, from_right)."""
+    def exchange(self, to_left, to_right, record_bytes, recv_counts=None):
+        """Send `to_left` to rank-1 and `to_right` to rank+1; returns (from_left, from_right).  recv_counts = (from the
+        left, from the right) when the receiver already knows them (the lambda exchange answers the halo exchange record
+        by record): then nothing but the payload travels and the host never waits."""
         torch, dist = self.torch, self.dist
-        mine = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=self.count_device)
-        allc = torch.empty((self.world, 2), dtype=torch.int64, device=self.count_device)
-        dist.all_gather_into_tensor(allc, mine, group=self.group) if self.count_device.type == "cuda" else \
-            dist.all_gather(list(allc.unbind(0)), mine, group=self.group)
-        counts = allc.cpu().tolist()
         r, w = self.rank, self.world
-        n_from_left = counts[r - 1][1] if r > 0 else 0
-        n_from_right = counts[r + 1][0] if r < w - 1 else 0
+        if recv_counts is None:
+            mine = torch.tensor([to_left.shape[0], to_right.shape[0]], dtype=torch.int64, device=self.count_device)
+            allc = torch.empty((self.world, 2), dtype=torch.int64, device=self.count_device)
+            dist.all_gather_into_tensor(allc, mine, group=self.group) if self.count_device.type == "cuda" else \
+                dist.all_gather(list(allc.unbind(0)), mine, group=self.group)
+            counts = allc.cpu().tolist()
+            n_from_left = counts[r - 1][1] if r > 0 else 0
+            n_from_right = counts[r + 1][0] if r < w - 1 else 0
+        else:
+            n_from_left, n_from_right = (int(recv_counts[0]) if r > 0 else 0), (int(recv_counts[1]) if r < w - 1 else 0)
         from_left = self.eng.empty_records(n_from_left, record_bytes)
         from_right = self.eng.empty_records(n_from_right, record_bytes)
         ops = []
@@ -191,14 +213,17 @@ class SlabDomain:
     """Host logic of one rank's slab.  Backend-agnostic: `engine` is a CtxEngine (GPU) or, in the CPU tests, an engine
     over the oracle with the same methods."""
 
-    def __init__(self, engine, rank, nranks, cuts, drift=0.25, comm=None, recut_every=0, recut_range=None, recut_bins=4096):
-        """recut_every > 0: every that many steps the cut planes are moved to the equal-count quantiles of the particles' x
+    def __init__(self, engine, rank, nranks, cuts, drift=0.25, comm=None, recut_every=0, recut_range=None, recut_bins=4096, exchange_lambda=True):
+        """exchange_lambda: ghost lambdas come from their owners between K6 and K7 (narrow halo) instead of being computed
+        locally (wide halo), see the module docstring.  recut_every > 0: every that many steps the cut planes are moved to the equal-count quantiles of the particles' x
         (a histogram over `recut_range` = (x_min, x_max) with `recut_bins` bins, summed over the ranks), so that slabs keep
         equal particle counts while the fluid flows — SURVEY §8e."""
         assert len(cuts) == nranks + 1 and all(cuts[k] < cuts[k + 1] for k in range(nranks))
         self.eng, self.rank, self.nranks, self.comm = engine, rank, nranks, comm
-        self.halo = 2.0 * H + 2.0 * drift
+        self.exchange_lambda = bool(exchange_lambda)
+        self.halo = (H + drift) if self.exchange_lambda else (2.0 * H + 2.0 * drift)
         self.lambda_ext = H + drift
+        self.ghost_counts = (0, 0)
         self.stats = {"migrated_out": 0, "ghosts": 0, "recuts": 0}
         self.recut_every, self.recut_range, self.recut_bins = int(recut_every), recut_range, int(recut_bins)
         assert not self.recut_every or (recut_range is not None and recut_range[0] < recut_range[1])
@@ -208,7 +233,10 @@ class SlabDomain:
     def set_cuts(self, cuts):
         self.cuts = [float(c) for c in cuts]
         self.x_lo, self.x_hi = self.cuts[self.rank], self.cuts[self.rank + 1]
-        self.eng.set_lambda_range(self.x_lo - self.lambda_ext, self.x_hi + self.lambda_ext)
+        if self.exchange_lambda:
+            self.eng.set_lambda_range(1.0, -1.0)  # empty: no ghost computes a lambda, they all receive one
+        else:
+            self.eng.set_lambda_range(self.x_lo - self.lambda_ext, self.x_hi + self.lambda_ext)
 
     def x_histogram(self):
         return np.asarray(self.eng.x_histogram(self.recut_range[0], self.recut_range[1], self.recut_bins), np.int64)
@@ -240,14 +268,34 @@ class SlabDomain:
         return self.eng.pack_halo(self.x_lo, self.x_hi, self.halo)
 
     def apply_halo(self, from_left, from_right):
-        self.stats["ghosts"] = int(from_left.shape[0]) + int(from_right.shape[0])
+        self.ghost_counts = (int(from_left.shape[0]), int(from_right.shape[0]))
+        self.stats["ghosts"] = sum(self.ghost_counts)
         self.eng.set_ghosts(from_left, from_right)
 
     def solve(self, it):
+        """one solver iteration without a lambda exchange (ghost lambdas computed locally)"""
+        self.solve_first_half()
+        self.solve_second_half(it)
+
+    def solve_first_half(self):
         e = self.eng
         e.build_grid()
         e.solve_contacts()
-        e.solve_fluid()
+        if self.exchange_lambda:
+            e.solve_fluid_lambda()  # K6; K7 follows the exchange
+
+    def pack_lambda(self):
+        return self.eng.pack_lambda()
+
+    def apply_lambda(self, from_left, from_right):
+        self.eng.set_ghost_lambda(from_left, from_right)
+
+    def solve_second_half(self, it):
+        e = self.eng
+        if self.exchange_lambda:
+            e.solve_fluid_delta()
+        else:
+            e.solve_fluid()
         e.collide_world(it)
 
     def finish(self, dt):
@@ -273,6 +321,12 @@ class SlabDomain:
             fl, fr = self.comm.exchange(l, r, HALO_RECORD_BYTES)
         self.apply_halo(fl, fr)
 
+    def exchange_ghost_lambda(self):
+        l, r = self.pack_lambda()
+        with self._on_stream():
+            fl, fr = self.comm.exchange(l, r, LAMBDA_RECORD_BYTES, recv_counts=self.ghost_counts)
+        self.apply_lambda(fl, fr)
+
     def step(self, dt):
         self.begin(dt)
         if self.recut_due():
@@ -280,7 +334,10 @@ class SlabDomain:
         self.migrate()
         for it in range(self.eng.iterations):
             self.refresh_halo()
-            self.solve(it)
+            self.solve_first_half()
+            if self.exchange_lambda:
+                self.exchange_ghost_lambda()
+            self.solve_second_half(it)
         self.finish(dt)
         self.steps_done += 1
 
@@ -289,9 +346,9 @@ class LocalCluster:
     """All slabs in one process, stepped in lock-step with in-process hand-over of the record buffers (tests; also a way
     to run several slabs on one GPU)."""
 
-    def __init__(self, engines, cuts, drift=0.25, **recut):
+    def __init__(self, engines, cuts, drift=0.25, **options):
         n = len(engines)
-        self.doms = [SlabDomain(e, r, n, cuts, drift, **recut) for r, e in enumerate(engines)]
+        self.doms = [SlabDomain(e, r, n, cuts, drift, **options) for r, e in enumerate(engines)]
 
     def _hand_over(self, sends, apply, record_bytes):
         n = len(self.doms)
@@ -313,7 +370,14 @@ class LocalCluster:
         for it in range(self.doms[0].eng.iterations):
             self._hand_over([d.pack_halo() for d in self.doms], lambda d, a, b: d.apply_halo(a, b), HALO_RECORD_BYTES)
             for d in self.doms:
-                d.solve(it)
+                d.solve_first_half()
+            if self.doms[0].exchange_lambda:
+                sends = [d.pack_lambda() for d in self.doms]
+                for d in self.doms:
+                    d.eng.sync()  # every context has its own stream; the lambda pack is asynchronous (no counts to wait for)
+                self._hand_over(sends, lambda d, a, b: d.apply_lambda(a, b), LAMBDA_RECORD_BYTES)
+            for d in self.doms:
+                d.solve_second_half(it)
         for d in self.doms:
             d.finish(dt)
             d.steps_done += 1

@@ -44,6 +44,8 @@ def lib():
         L.or_reorder.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp]
         L.or_collide.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32, P, vp]
         L.or_solve_fluids.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, P, vp, vp, vp]
+        L.or_solve_fluids_stages.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, P, vp, vp, vp, C.c_int]
+        L.or_solve_fluids_stages.restype = None
         L.or_collide_world.argtypes = [vp, vp, vp, u32, vp, P]
         L.or_solve_distance.argtypes = [vp, vp, vp, u32, vp, u32]
         L.or_solve_distance.restype = C.c_int
@@ -140,6 +142,11 @@ class OracleSystem:
     def solve_fluids(self):
         lib().or_solve_fluids(_p(self.spos), _p(self.sw), _p(self.sphase), _p(self.index), _p(self.cell_start), _p(self.cell_end),
                               _p(self.pos), self.n, C.byref(self.p), _p(self.ros), _p(self.lam), _p(self.nn))
+
+    def solve_fluids_stage(self, stages):
+        """1: lambdas only, 2: delta p only (from the lambdas in self.lam), 3: both"""
+        lib().or_solve_fluids_stages(_p(self.spos), _p(self.sw), _p(self.sphase), _p(self.index), _p(self.cell_start), _p(self.cell_end),
+                                     _p(self.pos), self.n, C.byref(self.p), _p(self.ros), _p(self.lam), _p(self.nn), int(stages))
 
     def collide_world(self, rands6):
         r = np.ascontiguousarray(rands6, np.float32)

@@ -23,6 +23,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
     recut = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # re-cut the slabs every that many steps (0: fixed planes)
+    exchange = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True   # ghost lambdas from their owners (1) or computed locally (0)
     p_or, pos, vel, w, phase, ros = _scene(nx=40)
     p = psb.default_params()
     p.grid_size[:] = tuple(p_or.grid); p.min_bounds[:] = tuple(p_or.min_b); p.max_bounds[:] = tuple(p_or.max_b)
@@ -34,7 +35,8 @@ def main():
     sol = psb.Solver(p, max_particles=pos.shape[0], device=local)
     sol.append(mine[0], mine[1], mine[2], mine[4], mine[3])
     eng = slab.CtxEngine(sol, halo_capacity=pos.shape[0], migrant_capacity=pos.shape[0])
-    dom = slab.SlabDomain(eng, rank, world, cuts, comm=slab.DistComm(eng), recut_every=recut, recut_range=(0.0, 40.0), recut_bins=1024)
+    dom = slab.SlabDomain(eng, rank, world, cuts, comm=slab.DistComm(eng), recut_every=recut, recut_range=(0.0, 40.0), recut_bins=1024,
+                          exchange_lambda=exchange)
     n_start = sol.n_owned
     for _ in range(steps):
         dom.step(DT)
@@ -63,7 +65,7 @@ def main():
         if recut:
             assert dom.stats["recuts"] == (steps - 1) // recut and max(ns) / (sum(ns) / world) < 1.3, (ns, dom.cuts)
         assert int(stats[0]) > 0 and int(stats[1]) > 0 and int(stats[2]) > 0
-        print(f"SLAB_NCCL_OK recut={recut} cuts={[round(c, 3) for c in dom.cuts[1:-1]]} world={world} particles={pos.shape[0]} owned={ns} migrated={int(stats[0])} bytes_sent={int(stats[2])}", flush=True)
+        print(f"SLAB_NCCL_OK recut={recut} exchange_lambda={exchange} ghosts={int(stats[1])} cuts={[round(c, 3) for c in dom.cuts[1:-1]]} world={world} particles={pos.shape[0]} owned={ns} migrated={int(stats[0])} bytes_sent={int(stats[2])}", flush=True)
     dist.barrier()
     sol.close()
     dist.destroy_process_group()

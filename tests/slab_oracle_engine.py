@@ -46,7 +46,8 @@ class OracleEngine:
         n = self.n_owned
         x = self.pos[:n, 0]
         out = []
-        for sel in (x < np.float32(x_lo + width), x >= np.float32(x_hi - width)):
+        self._halo_sel = (x < np.float32(x_lo + width), x >= np.float32(x_hi - width))
+        for sel in self._halo_sel:
             r = np.zeros(int(sel.sum()), HALO_DT)
             r["pos"], r["w"], r["ros"], r["phase"] = self.pos[:n][sel], self.w[:n][sel], self.ros[:n][sel], self.phase[:n][sel]
             out.append(_to_t(r))
@@ -124,6 +125,28 @@ class OracleEngine:
 
     def solve_fluid(self):
         before = self.pos.copy(); self.o.solve_fluids(); self._keep_ghosts(before)
+
+    # lambda exchange: K6, then the lambdas of the last halo pack's particles (record order) go out and the ghosts' come in, then K7
+    def solve_fluid_lambda(self):
+        self.o.solve_fluids_stage(1)
+        lo, hi = self.lambda_range
+        assert lo > hi, "exchange mode: no ghost computes its own lambda"
+        slot_of = np.empty(self.o.n, np.int64); slot_of[self.o.index] = np.arange(self.o.n)
+        self.o.lam[slot_of[self.n_owned:]] = np.nan  # a ghost lambda that is never received must show up in the result
+        self._slot_of = slot_of
+
+    def pack_lambda(self):
+        lam_by_particle = self.o.lam[self._slot_of[:self.n_owned]]
+        return tuple(torch.from_numpy(np.ascontiguousarray(lam_by_particle[sel]).view(np.uint8).reshape(-1, 4).copy()) for sel in self._halo_sel)
+
+    def set_ghost_lambda(self, from_left, from_right):
+        vals = np.concatenate([np.ascontiguousarray(t.numpy()).reshape(-1).view(np.float32) if t.shape[0] else np.zeros(0, np.float32)
+                               for t in (from_left, from_right)])
+        assert vals.size == self.o.n - self.n_owned
+        self.o.lam[self._slot_of[self.n_owned:]] = vals
+
+    def solve_fluid_delta(self):
+        before = self.pos.copy(); self.o.solve_fluids_stage(2); self._keep_ghosts(before)
 
     def collide_world(self, it):
         before = self.pos.copy(); self.o.collide_world(self.rands[it]); self._keep_ghosts(before)

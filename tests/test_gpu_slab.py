@@ -68,8 +68,52 @@ def test_pack_kernels_match_the_cpu_engine():
     eng.sol.close()
 
 
+def test_lambda_exchange_kernels():
+    """ps_slab_pack_lambda answers the halo pack record by record (lambda lives by sorted slot, the records by particle);
+    ps_slab_set_ghost_lambda drops the received values into the ghosts' sorted slots, left neighbour's first"""
+    p_or, pos, vel, w, phase, ros = _scene()
+    rng = np.random.default_rng(1)
+    pos[:, 0] += rng.uniform(-0.3, 0.3, pos.shape[0]).astype(np.float32)
+    eng = _ctx_engine(_params(p_or), (pos, vel, w, phase, ros))
+    sol = eng.sol
+    n = pos.shape[0]
+    with pytest.raises(psb.PsError) as e:   # nothing to answer yet
+        eng.pack_lambda()
+    assert e.value.code == psb.PS_ERR_STATE
+    x_lo, x_hi, width = 8.0, 15.0, 2.25
+    gl, gr = eng.pack_halo(x_lo, x_hi, width)
+    nl, nr = gl.shape[0], gr.shape[0]
+    assert nl > 0 and nr > 0
+    # pretend the particle's own halo records come back as ghosts (right buffer as the left neighbour's, and vice versa)
+    eng.set_ghosts(gr, gl)
+    assert sol.n == n + nl + nr
+    sol.build_grid()
+    sol.solve_fluid_lambda()
+    index = sol.download(psb.ARR_INDEX)
+    lam_sorted = sol.download(psb.ARR_LAMBDA)
+    lam = np.empty(n + nl + nr, np.float32); lam[index] = lam_sorted       # by particle
+    ll, lr = eng.pack_lambda()
+    assert (ll.shape[0], lr.shape[0]) == (nl, nr)
+    x = pos[:, 0]
+    sel_l, sel_r = x < np.float32(x_lo + width), x >= np.float32(x_hi - width)
+    assert np.array_equal(ll.cpu().numpy().view(np.float32).ravel(), lam[:n][sel_l])
+    assert np.array_equal(lr.cpu().numpy().view(np.float32).ravel(), lam[:n][sel_r])
+    # hand recognisable values to the ghosts
+    fl = torch.arange(nr, dtype=torch.float32, device="cuda").add_(1000.0).view(torch.uint8).reshape(-1, 4)
+    fr = torch.arange(nl, dtype=torch.float32, device="cuda").add_(5000.0).view(torch.uint8).reshape(-1, 4)
+    eng.set_ghost_lambda(fl, fr)
+    got = np.empty_like(lam); got[index] = sol.download(psb.ARR_LAMBDA)
+    assert np.array_equal(got[:n], lam[:n])                                # owned lambdas untouched
+    assert np.array_equal(got[n:n + nr], 1000.0 + np.arange(nr, dtype=np.float32))
+    assert np.array_equal(got[n + nr:], 5000.0 + np.arange(nl, dtype=np.float32))
+    with pytest.raises(psb.PsError):                                       # one value per ghost, no more, no fewer
+        sol.slab_set_ghost_lambda(fl.data_ptr(), nr - 1, fr.data_ptr(), nl)
+    sol.close()
+
+
+@pytest.mark.parametrize("exchange_lambda", [True, False], ids=["lambda-exchanged", "lambda-local"])
 @pytest.mark.parametrize("nranks", [2, 3])
-def test_slabs_on_one_gpu_match_one_context(nranks):
+def test_slabs_on_one_gpu_match_one_context(nranks, exchange_lambda):
     p_or, pos, vel, w, phase, ros = _scene()
     p = _params(p_or)
     steps = 4
@@ -79,7 +123,7 @@ def test_slabs_on_one_gpu_match_one_context(nranks):
         whole.step(DT)
     cuts = slab.quantile_cuts(pos[:, 0], nranks)
     engines = [_ctx_engine(p, part) for part in _split(cuts, pos, vel, w, phase, ros)]
-    cl = slab.LocalCluster(engines, cuts)
+    cl = slab.LocalCluster(engines, cuts, exchange_lambda=exchange_lambda)
     for _ in range(steps):
         cl.step(DT)
     got_pos = np.concatenate([e.sol.download_owned(psb.ARR_POS) for e in engines])

@@ -49,20 +49,23 @@ def _split(cuts, pos, *arrays):
     return out
 
 
+@pytest.mark.parametrize("exchange_lambda", [True, False], ids=["lambda-exchanged", "lambda-local"])
 @pytest.mark.parametrize("nranks", [2, 3])
-def test_local_cluster_matches_single_domain(nranks):
+def test_local_cluster_matches_single_domain(nranks, exchange_lambda):
     p, pos, vel, w, phase, ros = _scene()
     steps = 4
     ref_pos, ref_vel = _single(p, pos, vel, w, phase, ros, steps)
     cuts = slab.quantile_cuts(pos[:, 0], nranks)
     engines = [OracleEngine(p, a, b, c, d, e) for a, b, c, d, e in _split(cuts, pos, vel, w, phase, ros)]
     n0 = [e.n_owned for e in engines]
-    cl = slab.LocalCluster(engines, cuts)
+    cl = slab.LocalCluster(engines, cuts, exchange_lambda=exchange_lambda)
+    assert cl.doms[0].halo == (2.25 if exchange_lambda else 4.5)
     for _ in range(steps):
         cl.step(DT)
     got_pos = np.concatenate([e.pos[:e.n_owned] for e in engines])
     got_vel = np.concatenate([e.vel for e in engines])
     assert got_pos.shape[0] == pos.shape[0]                       # nothing lost, nothing duplicated
+    assert np.isfinite(got_pos).all()                             # every ghost received its lambda (the engine poisons them)
     assert sum(d.stats["migrated_out"] for d in cl.doms) > 0      # the block moves: particles did change owner
     assert [e.n_owned for e in engines] != n0
     assert all(d.stats["ghosts"] > 0 for d in cl.doms)
@@ -91,7 +94,7 @@ def test_dam_break_block_is_rank_count_independent():
     assert np.abs(whole[:, :3] - np.round((whole[:, :3] - 0.3125) / 0.625) * 0.625 - 0.3125).max() <= 0.0025 + 1e-6
 
 
-def _gloo_worker(rank, world, port, steps, out_dir):
+def _gloo_worker(rank, world, port, steps, out_dir, exchange_lambda=True):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
@@ -99,19 +102,20 @@ def _gloo_worker(rank, world, port, steps, out_dir):
     cuts = slab.quantile_cuts(pos[:, 0], world)
     mine = _split(cuts, pos, vel, w, phase, ros)[rank]
     eng = OracleEngine(p, *mine)
-    dom = slab.SlabDomain(eng, rank, world, cuts, comm=slab.DistComm(eng))
+    dom = slab.SlabDomain(eng, rank, world, cuts, comm=slab.DistComm(eng), exchange_lambda=exchange_lambda)
     for _ in range(steps):
         dom.step(DT)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), pos=eng.pos[:eng.n_owned], vel=eng.vel, migrated=dom.stats["migrated_out"],
-             sent=dom.comm.bytes_sent)
+             sent=dom.comm.bytes_sent, ghosts=dom.stats["ghosts"])
     dist.destroy_process_group()
 
 
-def test_two_processes_over_gloo_match_single_domain(tmp_path):
+@pytest.mark.parametrize("exchange_lambda", [True, False], ids=["lambda-exchanged", "lambda-local"])
+def test_two_processes_over_gloo_match_single_domain(tmp_path, exchange_lambda):
     import torch.multiprocessing as mp
     steps, world = 5, 2
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_gloo_worker, args=(world, port, steps, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + (2000 if exchange_lambda else 0)
+    mp.spawn(_gloo_worker, args=(world, port, steps, str(tmp_path), exchange_lambda), nprocs=world, join=True)
     p, pos, vel, w, phase, ros = _scene()
     ref_pos, ref_vel = _single(p, pos, vel, w, phase, ros, steps)
     parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
