@@ -32,6 +32,13 @@ namespace {
 #ifndef PS_VOTE_PAIR
 #define PS_VOTE_PAIR 1
 #endif
+#ifndef PS_LIST_CS
+#define PS_LIST_CS 3  // bit 0: list rows are written with st.global.cs, bit 1: read with ld.global.cs (streaming: evict first)
+#endif
+#ifndef PS_K7_ROWS
+#define PS_K7_ROWS 6  // list rows K7 reads per trip = gathers in flight per lane; must divide PS_KQ (measured 2 / 4 / 6 / 12: 0.323 / 0.308 / 0.289 / 0.324 ms)
+#endif
+
 typedef unsigned long long u64;
 constexpr int kBlock = PS_FBLOCK;  // tuning knobs of the neighbour kernels (build variants: scripts/bench_variants.sh)
 
@@ -98,7 +105,8 @@ constexpr u32 kNoNeighbor = 0xffffffffu, kListOverflow = 0xffffffffu;
 constexpr u32 kChunkRows = PS_LIST_CHUNK_ROWS;         // 48: a multiple of kQ (a flush never straddles chunks) and of 4 (K7 reads 4 rows at a time)
 constexpr u32 kListRecord = PS_LIST_RECORD_WORDS;      // per warp: [rows used | overflow mark, chunk id 0, chunk id 1, ...]
 constexpr u32 kMaxChunks = kListRecord - 1;            // 31 chunks = 1488 rows
-static_assert(kChunkRows % PS_KQ == 0 && kChunkRows % 4 == 0, "chunk size");
+static_assert(kChunkRows % PS_KQ == 0 && kChunkRows % 4 == 0 && PS_KQ % PS_K7_ROWS == 0, "chunk size");
+constexpr int kK7Rows = PS_K7_ROWS;
 typedef unsigned short u16;
 
 static inline size_t fluid_smem_bytes(int rad) {
@@ -165,7 +173,11 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
             }
             if (!nl.overflow) {
 #pragma unroll
-                for (int k = 0; k < kQ; k++) nl.cur[(in_chunk + k) * 32] = k < cnt ? q[k][tid] : kNoNeighbor;
+                for (int k = 0; k < kQ; k++) {
+                    const u32 v = k < cnt ? q[k][tid] : kNoNeighbor;
+                    if (PS_LIST_CS & 1) __stcs(nl.cur + (in_chunk + k) * 32, v);
+                    else nl.cur[(in_chunk + k) * 32] = v;
+                }
                 nl.rows += kQ;
             }
         }
@@ -403,9 +415,12 @@ __device__ __forceinline__ float delta_p_inv_den() {
     return __fdividef(1.f, term2 * term2 * term2);
 }
 
-// K7 from the neighbour lists K6 left behind: no search, no shared memory; rows are read 4 at a time so that four
+// K7 from the neighbour lists K6 left behind: no search, no shared memory; rows are read kK7Rows at a time so that as many
 // position / lambda gathers are in flight per lane.
-constexpr int kListBlock = 256;
+#ifndef PS_K7_BLOCK
+#define PS_K7_BLOCK 256
+#endif
+constexpr int kListBlock = PS_K7_BLOCK;
 __global__ void __launch_bounds__(kListBlock) k_solve_fluids_list(float4 *__restrict__ pos, const float *__restrict__ lambda,
                                                                   const float4 *__restrict__ spos, const int *__restrict__ sphase,
                                                                   const u32 *__restrict__ index, const float *__restrict__ ros,
@@ -424,17 +439,17 @@ __global__ void __launch_bounds__(kListBlock) k_solve_fluids_list(float4 *__rest
     DeltaP f{lambda[i], delta_p_inv_den(), 0.f, 0.f, 0.f, lambda};
     const u32 *L = nbr_list;
     u32 nn = 0;
-    for (u32 r = 0, rc = 0; r < rows; r += 4, rc += 4) {  // rows is a multiple of kQ, chunks of 4
+    for (u32 r = 0, rc = 0; r < rows; r += kK7Rows, rc += kK7Rows) {  // rows is a multiple of kQ, which kK7Rows divides
         if (rc == kChunkRows) rc = 0;
         if (rc == 0) L = nbr_list + (size_t)__ldg(rec + 1 + r / kChunkRows) * (kChunkRows * 32) + (threadIdx.x & 31);
-        u32 j[4];
-        float4 pj[4];
+        u32 j[kK7Rows];
+        float4 pj[kK7Rows];
 #pragma unroll
-        for (int k = 0; k < 4; k++) j[k] = __ldg(L + (rc + k) * 32);
+        for (int k = 0; k < kK7Rows; k++) j[k] = (PS_LIST_CS & 2) ? __ldcs(L + (rc + k) * 32) : __ldg(L + (rc + k) * 32);
 #pragma unroll
-        for (int k = 0; k < 4; k++) pj[k] = __ldg(spos + (j[k] != kNoNeighbor ? j[k] : i));
+        for (int k = 0; k < kK7Rows; k++) pj[k] = __ldg(spos + (j[k] != kNoNeighbor ? j[k] : i));
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < kK7Rows; k++)
             if (j[k] != kNoNeighbor) {
                 f(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z, j[k]);
                 nn++;
