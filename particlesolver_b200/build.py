@@ -78,7 +78,8 @@ def build_all(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    build_cli(env)
+    if os.path.basename(OUT) == "libpsolver.so":  # tuning variants (build_variant) leave the CLI on the default library
+        build_cli(env)
     return OUT
 
 

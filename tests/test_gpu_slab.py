@@ -93,6 +93,7 @@ def test_lambda_exchange_kernels():
     lam_sorted = sol.download(psb.ARR_LAMBDA)
     lam = np.empty(n + nl + nr, np.float32); lam[index] = lam_sorted       # by particle
     ll, lr = eng.pack_lambda()
+    sol.sync()   # the pack runs on the solver's stream and reports no counts, so nothing has waited for it yet
     assert (ll.shape[0], lr.shape[0]) == (nl, nr)
     x = pos[:, 0]
     sel_l, sel_r = x < np.float32(x_lo + width), x >= np.float32(x_hi - width)
