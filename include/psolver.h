@@ -62,6 +62,12 @@ typedef struct PsParams {
                           fluid density constraint with their own rest density and rise — they are predicted with gravity x -0.2, the
                           CPU app's ALPHA (cpu/src/simulation.h:21, simulation.cpp:144).  Parity unpinned in 3-D. */
 
+#define PS_FLAG_SELF_COLLISION 4u /* not in the reference: there all particles of one phase > SOLID skip each other in the contact
+                          pass (integration_kernel.cuh:336-337), so its cloth never self-collides.  With this flag two
+                          such particles collide (contact + friction, like particles of different bodies) when both carry
+                          distance constraints and no distance constraint joins them: a cloth or rope touches itself, its
+                          constrained neighbours and the members of shape-matched bodies still skip each other.  Unpinned. */
+
 typedef struct PsCtx PsCtx;
 
 /* array selectors for ps_download / ps_upload / ps_device_ptr */

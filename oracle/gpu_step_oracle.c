@@ -138,8 +138,21 @@ static inline float dot3(const float *a, const float *b) { return a[0] * b[0] + 
 
 /* ---- K5: collide / collideD / collideCell (integration.cu:338-386, integration_kernel.cuh:303-462).
  *          Runs for sorted-phase >= CLOTH only; others leave pos[] and num_neighbors[] untouched. ---- */
-void or_collide(float *pos, const float *prev, const float *spos, const float *sw, const int *sphase, const u32 *index,
-                const u32 *cell_start, const u32 *cell_end, u32 n, const OrParams *p, u32 *num_neighbors) {
+/* adj_off / adj: NULL = the reference (particles of one phase > SOLID never collide with each other).  Otherwise the opt-in
+ * self-collision of PS_FLAG_SELF_COLLISION (NOT in the reference): CSR adjacency of the distance constraints by
+ * original index; a same-phase pair is skipped only when either particle has no distance constraint (a shape-matched body)
+ * or the two are joined by one. */
+static int same_body_skip(const u32 *adj_off, const u32 *adj, u32 oi, u32 oj) {
+    if (!adj_off) return 1;
+    if (adj_off[oi] == adj_off[oi + 1] || adj_off[oj] == adj_off[oj + 1]) return 1;
+    for (u32 k = adj_off[oi]; k < adj_off[oi + 1]; k++)
+        if (adj[k] == oj) return 1;
+    return 0;
+}
+
+void or_collide_adj(float *pos, const float *prev, const float *spos, const float *sw, const int *sphase, const u32 *index,
+                    const u32 *cell_start, const u32 *cell_end, u32 n, const OrParams *p, u32 *num_neighbors, const u32 *adj_off,
+                    const u32 *adj) {
     const float collideDist = p->radius * 2.001f;
     const float collideDist2 = collideDist * collideDist;
     #pragma omp parallel
@@ -163,7 +176,7 @@ void or_collide(float *pos, const float *prev, const float *spos, const float *s
                         for (u32 j = s; j < e; j++) {
                             if (j == i) continue;
                             int phase2 = sphase[j];
-                            if (phase > PH_SOLID && phase == phase2) continue;
+                            if (phase > PH_SOLID && phase == phase2 && same_body_skip(adj_off, adj, index[i], index[j])) continue;
                             float d[3] = {x[0] - spos[4 * (size_t)j], x[1] - spos[4 * (size_t)j + 1], x[2] - spos[4 * (size_t)j + 2]};
                             float mag2 = dot3(d, d);
                             if (mag2 < collideDist2 && nn < MAX_FLUID_NEIGHBORS) nb[nn++] = j;
@@ -224,6 +237,11 @@ void or_collide(float *pos, const float *prev, const float *spos, const float *s
         }
         free(nb);
     }
+}
+
+void or_collide(float *pos, const float *prev, const float *spos, const float *sw, const int *sphase, const u32 *index,
+                const u32 *cell_start, const u32 *cell_end, u32 n, const OrParams *p, u32 *num_neighbors) {
+    or_collide_adj(pos, prev, spos, sw, sphase, index, cell_start, cell_end, n, p, num_neighbors, NULL, NULL);
 }
 
 /* neighbour gather of findLambdasD / collideCellRadius (integration_kernel.cuh:482-559) */

@@ -23,6 +23,7 @@ NO_COLLIDE, FLUID, GAS, CLOTH, SOLID, RIGID = -1, 0, 1, 2, 3, 4
 PS_OK, PS_ERR_INVALID, PS_ERR_CUDA, PS_ERR_CAPACITY, PS_ERR_STATE = 0, 1, 2, 3, 4
 FLAG_ZERO_NONFLUID_LAMBDA = 1
 FLAG_GAS = 2
+FLAG_SELF_COLLISION = 4
 NUM_STAGES = 12
 
 (ARR_POS, ARR_VEL, ARR_PREV, ARR_INV_MASS, ARR_PHASE, ARR_REST_DENSITY, ARR_HASH, ARR_INDEX, ARR_CELL_START, ARR_CELL_END,

@@ -266,7 +266,7 @@ extern "C" int ps_destroy(PsCtx *c) {
     void *ptrs[] = {c->pos, c->vel, c->prev, c->spos, c->w, c->ros, c->sw, c->lambda, c->phase, c->sphase, c->hash, c->index, c->hash_tmp,
                     c->index_tmp, c->num_neighbors, c->occ, c->cell_start, c->cell_end, c->cell_begin, c->chunk_lb,
                     c->sort_status, c->rands, c->slab_scratch, c->slab_ranks, c->nbr_list, c->nbr_rows ? c->nbr_rows - 4 : nullptr, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
-                    c->d_point_xyz, c->dist_scratch};
+                    c->d_point_xyz, c->dist_scratch, c->adj_off, c->adj};
     for (void *p : ptrs) if (p) cudaFree(p);
     ps_ext_free(c);
     if (c->slab_counts_host) cudaFreeHost(c->slab_counts_host);
@@ -415,6 +415,18 @@ int ps_ctx_sync_constraints(PsCtx *c) {
     if ((r = upload_vec(&c->csr_off, off, s)) != PS_OK) return r;
     if ((r = upload_vec(&c->csr_other, other, s)) != PS_OK) return r;
     if ((r = upload_vec(&c->csr_rest, rest, s)) != PS_OK) return r;
+    // adjacency of the distance constraints by particle index, for the opt-in self-collision of K5 (PS_FLAG_SELF_COLLISION);
+    // fluid-only scenes (m == 0) carry none
+    std::vector<u32> adj_off, adj;
+    if (m) {
+        adj_off.assign((size_t)c->n + 1, 0u);
+        for (u32 i = 0; i < c->n; i++) adj_off[i + 1] = adj_off[i] + deg[i];
+        adj.resize(2 * m);
+        for (u32 k = 0; k < K; k++)
+            for (u32 t = off[k]; t < off[k + 1]; t++) adj[adj_off[particle[k]] + (t - off[k])] = other[t] & 0x7fffffffu;
+    }
+    if ((r = upload_vec(&c->adj_off, adj_off, s)) != PS_OK) return r;
+    if ((r = upload_vec(&c->adj, adj, s)) != PS_OK) return r;
     if ((r = upload_vec(&c->d_point_idx, c->h_point_idx, s)) != PS_OK) return r;
     if ((r = upload_vec(&c->d_point_xyz, c->h_point_xyz, s)) != PS_OK) return r;
     if (c->dist_scratch) { CU(cudaFree(c->dist_scratch)); c->dist_scratch = nullptr; }
@@ -492,13 +504,16 @@ extern "C" int ps_build_grid(PsCtx *c) {
     if (c->n) ps_issue_build_grid(c, c->pos);
     return check_launch("ps_build_grid");
 }
+// K5's same-phase rule: nullptr = the reference's (no self-collision); the constraint adjacency under PS_FLAG_SELF_COLLISION
+static inline const u32 *self_collision_adj(const PsCtx *c) { return (c->params.flags & PS_FLAG_SELF_COLLISION) ? c->adj_off : nullptr; }
+
 extern "C" int ps_solve_contacts(PsCtx *c) {
     PsNvtxRange nvtx("ps_solve_contacts");
     int r = ready(c); if (r != PS_OK) return r;
     if (c->n && !c->grid_valid) { ps_set_error("ps_solve_contacts: no grid (call ps_build_grid)"); return PS_ERR_STATE; }
     DeviceGuard dg(c->device);
     ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, c->n, c->n - c->n_ghost, c->grid,
-                      c->params.particle_radius, c->stream);
+                      c->params.particle_radius, self_collision_adj(c), c->adj, c->stream);
     return check_launch("ps_solve_contacts");
 }
 static int issue_fluid(PsCtx *c, const char *what, bool do_lambda, bool do_delta) {
@@ -567,7 +582,7 @@ static u32 issue_step(PsCtx *c, float dt) {
         launches += ps_issue_build_grid(c, c->pos);
         if (has_contact) {
             ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n_owned, c->grid,
-                              p.particle_radius, s);
+                              p.particle_radius, self_collision_adj(c), c->adj, s);
             launches++;
         }
         if (has_fluid) {
@@ -666,7 +681,7 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
         ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s); mark(4, 1);
         c->grid_valid = true;
         c->ref_tables_valid = false;
-        if (has_contact) { ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, s); mark(5, 1); }
+        if (has_contact) { ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, self_collision_adj(c), c->adj, s); mark(5, 1); }
         if (has_fluid) {
             ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->lambda_xmin,
                                    c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list, c->nbr_rows,

@@ -67,6 +67,7 @@ struct PsCtx {
     u32 num_constrained = 0, num_points = 0;
     u32 *csr_particle = nullptr, *csr_off = nullptr, *csr_other = nullptr, *d_point_idx = nullptr;
     float *csr_rest = nullptr, *d_point_xyz = nullptr;
+    u32 *adj_off = nullptr, *adj = nullptr;  // distance-constraint adjacency by particle index (n + 1 offsets, 2m partners); null when m == 0
     float4 *dist_scratch = nullptr;
     bool dist_prefix_ok = true;  // constrained particles are the index prefix [0,K) (see K9 note)
 

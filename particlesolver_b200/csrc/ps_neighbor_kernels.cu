@@ -638,7 +638,8 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
                                                     const float4 *__restrict__ spos, const float *__restrict__ sw,
                                                     const int *__restrict__ sphase, const u32 *__restrict__ index,
                                                     const u32 *__restrict__ cell_begin, u32 *__restrict__ num_neighbors, u32 n, u32 n_owned,
-                                                    GridDesc g, StencilDesc st, float radius) {
+                                                    GridDesc g, StencilDesc st, float radius, const u32 *__restrict__ adj_off,
+                                                    const u32 *__restrict__ adj) {
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
     const int phase = sphase[i];
@@ -650,14 +651,31 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
     const float collide_dist = radius * 2.001f;
     const float collide_dist2 = collide_dist * collide_dist;
 
+    // Particles of one phase > SOLID never collide with each other in the reference (integration_kernel.cuh:336-337: a cloth
+    // does not self-collide).  adj_off != nullptr (PS_FLAG_SELF_COLLISION, not in the reference): such a pair inside
+    // the contact distance is skipped only when either particle has no distance constraint (a shape-matched body) or the two
+    // are joined by one (CSR adjacency by original index); the lookup runs after the distance test, i.e. for contacts only.
+    u32 ab = 0, ae = 0;
+    if (adj_off && phase > PH_SOLID) { ab = __ldg(adj_off + orig); ae = __ldg(adj_off + orig + 1); }
+    auto same_body = [&](u32 j) {
+        if (ab == ae) return true;
+        const u32 oj = __ldg(index + j);
+        if (__ldg(adj_off + oj) == __ldg(adj_off + oj + 1)) return true;
+        for (u32 k = ab; k < ae; k++)
+            if (__ldg(adj + k) == oj) return true;
+        return false;
+    };
     u32 nn = 0;
     for_each_candidate(g, st, cell_begin, gp, [&](u32 j) {
         if (j == i) return;
         const int phase2 = __ldg(sphase + j);
-        if (phase > PH_SOLID && phase == phase2) return;
+        const bool same = phase > PH_SOLID && phase == phase2;
+        if (same && !adj_off) return;
         const float4 pj = __ldg(spos + j);
         const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
-        if (rx * rx + ry * ry + rz * rz < collide_dist2 && nn < PS_MAX_NEIGHBORS) nn++;
+        if (!(rx * rx + ry * ry + rz * rz < collide_dist2)) return;
+        if (same && same_body(j)) return;
+        if (nn < PS_MAX_NEIGHBORS) nn++;
     });
     num_neighbors[i] = nn;
     float dxs = 0.f, dys = 0.f, dzs = 0.f;
@@ -670,11 +688,13 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
         for_each_candidate(g, st, cell_begin, gp, [&](u32 j) {
             if (j == i || seen >= nn) return;
             const int phase2 = __ldg(sphase + j);
-            if (phase > PH_SOLID && phase == phase2) return;
+            const bool same = phase > PH_SOLID && phase == phase2;
+            if (same && !adj_off) return;
             const float4 pj = __ldg(spos + j);
             const float rx = pi.x - pj.x, ry = pi.y - pj.y, rz = pi.z - pj.z;
             const float d2 = rx * rx + ry * ry + rz * rz;
             if (!(d2 < collide_dist2)) return;
+            if (same && same_body(j)) return;
             seen++;
             const float w2 = __ldg(sw + j);
             const float dist = sqrtf(d2);
@@ -718,12 +738,13 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
 static inline u32 cdiv(u32 a, u32 b) { return (a + b - 1) / b; }
 
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
-                       const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, cudaStream_t s) {
+                       const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, const u32 *adj_off,
+                       const u32 *adj, cudaStream_t s) {
     if (!n) return;
     StencilDesc st;  // 3x3x3: every row keeps its full extent (contact radius 2.001r slightly exceeds one cell)
     st.rad = 1;
     for (int k = 0; k < 9; k++) st.xr[k] = 1;
-    k_collide<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, prev, spos, sw, sphase, index, cell_begin, num_neighbors, n, n_owned, g, st, radius);
+    k_collide<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, prev, spos, sw, sphase, index, cell_begin, num_neighbors, n, n_owned, g, st, radius, adj_off, adj);
 }
 
 // pool of list rows for `capacity` particles at `rows_per_warp` rows reserved per warp on average

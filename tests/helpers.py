@@ -23,9 +23,11 @@ def oracle_from_solver(sol: "psb.Solver"):
                          gravity=tuple(p.gravity), origin=tuple(p.world_origin), cell=tuple(p.cell_size))
     didx, drest = sol.distance_constraints()
     pidx, pxyz = sol.point_constraints()
-    return orc.OracleSystem(op, sol.download(psb.ARR_POS), sol.download(psb.ARR_VEL), sol.download(psb.ARR_INV_MASS),
-                            sol.download(psb.ARR_PHASE), sol.download(psb.ARR_REST_DENSITY), didx, drest, pidx, pxyz,
-                            iterations=int(p.solver_iterations))
+    o = orc.OracleSystem(op, sol.download(psb.ARR_POS), sol.download(psb.ARR_VEL), sol.download(psb.ARR_INV_MASS),
+                         sol.download(psb.ARR_PHASE), sol.download(psb.ARR_REST_DENSITY), didx, drest, pidx, pxyz,
+                         iterations=int(p.solver_iterations))
+    o.self_collision = bool(p.flags & psb.FLAG_SELF_COLLISION)
+    return o
 
 
 def max_abs(a, b):

@@ -43,6 +43,8 @@ def lib():
         L.or_sort.argtypes = [vp, vp, u32]
         L.or_reorder.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp]
         L.or_collide.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32, P, vp]
+        L.or_collide_adj.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32, P, vp, vp, vp]
+        L.or_collide_adj.restype = None
         L.or_solve_fluids.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, P, vp, vp, vp]
         L.or_solve_fluids_stages.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, P, vp, vp, vp, C.c_int]
         L.or_solve_fluids_stages.restype = None
@@ -117,6 +119,8 @@ class OracleSystem:
         self.occ = np.zeros(n, np.uint32)
         lib().or_occurrences(_p(self.occ), n, _p(self.dist_idx), self.dist_rest.size, _p(self.point_idx), self.point_idx.size)
         self.dist_nonprefix = 0
+        self.self_collision = False  # True: the opt-in rule of PS_FLAG_SELF_COLLISION (not the reference's)
+        self._adj = None
 
     def predict(self, dt):
         g = np.array(list(self.p.gravity), np.float32)
@@ -135,7 +139,23 @@ class OracleSystem:
     def build_grid(self):
         self.calc_hash(); self.sort(); self.reorder()
 
+    def _adjacency(self):
+        """CSR of the distance constraints by particle index (offsets n + 1, partners 2m)"""
+        if self._adj is None:
+            pairs = self.dist_idx.reshape(-1, 2).astype(np.int64)
+            a = np.concatenate([pairs[:, 0], pairs[:, 1]]); b = np.concatenate([pairs[:, 1], pairs[:, 0]])
+            order = np.argsort(a, kind="stable")
+            off = np.zeros(self.n + 1, np.uint32)
+            off[1:] = np.cumsum(np.bincount(a, minlength=self.n))
+            self._adj = (off, np.ascontiguousarray(b[order], np.uint32))
+        return self._adj
+
     def collide(self):
+        if self.self_collision and self.dist_rest.size:
+            off, adj = self._adjacency()
+            lib().or_collide_adj(_p(self.pos), _p(self.prev), _p(self.spos), _p(self.sw), _p(self.sphase), _p(self.index), _p(self.cell_start),
+                                 _p(self.cell_end), self.n, C.byref(self.p), _p(self.nn), _p(off), _p(adj))
+            return
         lib().or_collide(_p(self.pos), _p(self.prev), _p(self.spos), _p(self.sw), _p(self.sphase), _p(self.index), _p(self.cell_start),
                          _p(self.cell_end), self.n, C.byref(self.p), _p(self.nn))
 
