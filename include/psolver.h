@@ -222,6 +222,16 @@ int ps_add_rigid_body(PsCtx *ctx, const uint32_t *indices, uint64_t n, float sti
 uint64_t ps_num_rigid_bodies(PsCtx *ctx);
 int ps_solve_shapes(PsCtx *ctx);                                         /* the stage alone */
 int ps_rigid_body_rotation(PsCtx *ctx, uint32_t body, float *quat_xyzw); /* rotation found by the last projection */
+/* SDF contacts between rigid bodies — the reference CPU app's RigidContactConstraint (cpu/src/constraint/rigidcontactconstraint.cpp:
+ * 13-96, 2-D) lifted to 3-D inside the contact pass; the reference's GPU solver has nothing like it.  sdf4: per member of the body,
+ * in ps_add_rigid_body's order, (gx, gy, gz, depth): the outward surface normal nearest to the particle, in the frame the body was
+ * added in (it is turned by the body's current rotation before every contact pass), and the particle's depth below the surface
+ * (SDFData, cpu/src/solver/particle.h:82-93; the CPU app's boxes: depth = radius on faces, radius * sqrt(2) at corners).  depth < 0:
+ * no data for that member.  A contact of two particles that BOTH carry SDF data takes normal and depth from the shallower one
+ * (ties: the lower particle index); for particles of the outermost layers (depth < diameter + EPS) the depth is the particles'
+ * overlap and the normal is x_ij mirrored at the SDF normal (Macklin et al. 2014 eq. 13-14); friction uses that normal and depth.
+ * All other contacts are unchanged.  Parity unpinned in 3-D. */
+int ps_set_rigid_body_sdf(PsCtx *ctx, uint32_t body, const float *sdf4);
 /* XSPH viscosity (v_i += c sum_j (v_j - v_i) W_ij) and vorticity confinement (Macklin & Mueller 2013, eqs. 15-17) as a
  * velocity post-pass of ps_step on the PBF neighbour lists; both coefficients 0 (the default) = off. */
 int ps_set_viscosity(PsCtx *ctx, float xsph_c, float vorticity_eps);

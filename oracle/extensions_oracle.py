@@ -1,5 +1,5 @@
 """oracle/extensions_oracle.py — float64 numpy restatements of the solver parts that north_star names but the reference
-does not contain: 3-D shape matching (K12), XSPH viscosity and vorticity confinement (K13).
+does not contain: 3-D shape matching (K12), XSPH viscosity and vorticity confinement (K13), SDF contacts between rigid bodies in K5.
 
 TEST INFRASTRUCTURE ONLY (tests/test_gpu_extensions.py).  PARITY UNPINNED: there is no reference implementation of
 these — the reference GPU solver's rigid_body_functor is an empty stub (gpu/src/cuda/solver_kernel.cuh:289-312) and
@@ -62,3 +62,81 @@ def viscosity(pos, vel, fluid, c_xsph, vorticity_eps, dt):
     out = vel.copy()
     out[fluid] += dv[fluid]
     return out, omega
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# K5 with SDF contacts between rigid bodies (ps_set_rigid_body_sdf): float64 all-pairs restatement of the whole contact pass —
+# gpu/src/cuda/integration_kernel.cuh:303-462 (collideD / collideCell: neighbour count, Jacobi average, exp(-y) mass scaling,
+# friction with its [sic]s) with the pair rule of the reference CPU app's RigidContactConstraint (cpu/src/constraint/
+# rigidcontactconstraint.cpp:13-66) for pairs that both carry SDF data, lifted to 3-D.  Independent of the C oracle's traversal.
+CLOTH, SOLID = 2, 3
+EPS, S_FRICTION, K_FRICTION = 0.001, 0.005, 0.0002
+
+
+def sdf_pair(si, sj, i_first, r, dist, diam):
+    """(depth, normal i -> j) of one SDF contact, or None; si / sj = (gx, gy, gz, depth) world frame, r = x_i - x_j"""
+    if si[3] < sj[3] or (si[3] == sj[3] and i_first):
+        d, e = si[3], np.array(si[:3], np.float64)
+    else:
+        d, e = sj[3], -np.array(sj[:3], np.float64)
+    if d < diam + EPS:                                   # initBoundary (:13-27)
+        d = diam - dist
+        if d < EPS:
+            return None
+        x = r / dist if dist > EPS else np.array([0.0, 1.0, 0.0])
+        dp = float(x @ e)
+        e = x - 2.0 * dp * e if dp < 0 else x
+    return d, e
+
+
+def contact_pass(pos, prev, w, phase, radius, sdf_world=None, same_body_skip=None):
+    """one K5 launch over all particles; returns (new positions, contact counts).  same_body_skip(i, j) -> bool for equal phases > SOLID
+    (default: always skip, the reference)"""
+    pos, prev, w = np.asarray(pos, np.float64)[:, :3], np.asarray(prev, np.float64)[:, :3], np.asarray(w, np.float64)
+    n = pos.shape[0]
+    cd = radius * 2.001
+    out, counts = pos.copy(), np.zeros(n, np.int64)
+    scaled = lambda wi, y: 1.0 / ((1.0 / wi) * np.exp(-y)) if wi != 0 else wi
+    for i in range(n):
+        if phase[i] < CLOTH:
+            continue
+        nb = []
+        for j in range(n):
+            if j == i:
+                continue
+            if phase[i] > SOLID and phase[i] == phase[j] and (same_body_skip is None or same_body_skip(i, j)):
+                continue
+            if np.linalg.norm(pos[i] - pos[j]) < cd:
+                nb.append(j)
+        counts[i] = len(nb)
+        delta = np.zeros(3)
+        for j in nb:
+            r = pos[i] - pos[j]
+            dist = np.linalg.norm(r)
+            both = phase[i] >= SOLID and phase[j] >= SOLID
+            cw, cw2 = (scaled(w[i], pos[i, 1]), scaled(w[j], pos[i, 1])) if both else (w[i], w[j])   # [sic] both use y of particle i
+            wsum = cw + cw2
+            dp = r / dist * ((dist - cd) / wsum)
+            fn, fd = r, dist
+            if both and sdf_world is not None and sdf_world[i][3] >= 0 and sdf_world[j][3] >= 0:
+                c = sdf_pair(sdf_world[i], sdf_world[j], i < j, r, dist, 2 * radius)
+                if c is None:
+                    continue
+                fd, fn = c
+                dp = fn * (fd / wsum)
+            dp1, dp2 = -cw * dp / len(nb), cw2 * dp / len(nb)
+            delta += dp1
+            if not both:
+                continue
+            nf = fn / np.linalg.norm(fn)
+            rel = (pos[i] + dp1 - prev[i]) - (prev[i] + dp2 - prev[j])   # [sic] integration_kernel.cuh:447
+            t = rel - (rel @ nf) * nf
+            lt = np.linalg.norm(t)
+            if lt < EPS:
+                continue
+            if lt < S_FRICTION * fd:
+                delta -= t * cw / wsum
+            else:
+                delta -= t * min(K_FRICTION * fd / lt, 1.0)
+        out[i] = pos[i] + delta
+    return out, counts

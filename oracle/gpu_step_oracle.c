@@ -150,9 +150,29 @@ static int same_body_skip(const u32 *adj_off, const u32 *adj, u32 oi, u32 oj) {
     return 0;
 }
 
-void or_collide_adj(float *pos, const float *prev, const float *spos, const float *sw, const int *sphase, const u32 *index,
+/* SDF contact of two rigid-body particles: RigidContactConstraint of the reference CPU app (cpu/src/constraint/
+ * rigidcontactconstraint.cpp:13-66, 2-D) lifted to 3-D, as the gather form of K5 sees it (particle 1 = the particle being updated).
+ * si / sj = (outward unit gradient in world frame, depth); r = x_i - x_j.  NOT in the reference's GPU solver; unpinned. */
+static int sdf_contact(const float *si, const float *sj, int i_first, const float *r, float dist, float diam, float *d, float *e) {
+    int mine = si[3] < sj[3] || (si[3] == sj[3] && i_first);
+    if (mine) { *d = si[3]; e[0] = si[0]; e[1] = si[1]; e[2] = si[2]; }
+    else { *d = sj[3]; e[0] = -sj[0]; e[1] = -sj[1]; e[2] = -sj[2]; }
+    if (*d < diam + EPS) {               /* initBoundary (:13-27) */
+        *d = diam - dist;
+        if (*d < EPS) return 0;
+        float x[3] = {0.f, 1.f, 0.f};
+        if (dist > EPS) { x[0] = r[0] / dist; x[1] = r[1] / dist; x[2] = r[2] / dist; }
+        float dp = x[0] * e[0] + x[1] * e[1] + x[2] * e[2];
+        if (dp < 0.f) { for (int c = 0; c < 3; c++) e[c] = x[c] - 2.f * dp * e[c]; }
+        else { for (int c = 0; c < 3; c++) e[c] = x[c]; }
+    }
+    return 1;
+}
+
+/* sdf_world: NULL, or per ORIGINAL particle index (gx, gy, gz, depth), depth < 0 or NaN = none (ps_set_rigid_body_sdf) */
+void or_collide_ext(float *pos, const float *prev, const float *spos, const float *sw, const int *sphase, const u32 *index,
                     const u32 *cell_start, const u32 *cell_end, u32 n, const OrParams *p, u32 *num_neighbors, const u32 *adj_off,
-                    const u32 *adj) {
+                    const u32 *adj, const float *sdf_world) {
     const float collideDist = p->radius * 2.001f;
     const float collideDist2 = collideDist * collideDist;
     #pragma omp parallel
@@ -205,6 +225,17 @@ void or_collide_adj(float *pos, const float *prev, const float *spos, const floa
                 float scale = mag / (colW + colW2);
                 float sd = scale / dist;
                 float dp[3] = {d[0] * sd, d[1] * sd, d[2] * sd};
+                float fnv[3] = {d[0], d[1], d[2]}, fd = dist; /* friction: normal before normalisation, length scale of the cone */
+                if (sdf_world && phase >= PH_SOLID && phase2 >= PH_SOLID) {
+                    const float *si = sdf_world + 4 * (size_t)orig, *sj = sdf_world + 4 * (size_t)index[j];
+                    if (si[3] >= 0.f && sj[3] >= 0.f) {
+                        float depth, e[3];
+                        if (!sdf_contact(si, sj, orig < index[j], d, dist, 2.f * p->radius, &depth, e)) continue;
+                        float s_ = depth / (colW + colW2);
+                        for (int c = 0; c < 3; c++) { dp[c] = e[c] * s_; fnv[c] = e[c]; }
+                        fd = depth;
+                    }
+                }
                 float dp1[3], dp2[3];
                 for (int c = 0; c < 3; c++) {
                     dp1[c] = (-colW * dp[c]) / fn;
@@ -213,8 +244,8 @@ void or_collide_adj(float *pos, const float *prev, const float *spos, const floa
                 }
                 if (phase < PH_SOLID || phase2 < PH_SOLID) continue;
                 const float *pp2 = prev + 4 * (size_t)index[j];
-                float inv = 1.0f / sqrtf(dot3(d, d)); /* normalize(): v * rsqrtf(dot(v,v)) */
-                float nf[3] = {d[0] * inv, d[1] * inv, d[2] * inv};
+                float inv = 1.0f / sqrtf(dot3(fnv, fnv)); /* normalize(): v * rsqrtf(dot(v,v)) */
+                float nf[3] = {fnv[0] * inv, fnv[1] * inv, fnv[2] * inv};
                 float rel[3];
                 /* [sic] second term starts from prevPos of i, not pos2 (integration_kernel.cuh:447) */
                 for (int c = 0; c < 3; c++) rel[c] = (x[c] + dp1[c] - pp[c]) - (pp[c] + dp2[c] - pp2[c]);
@@ -222,10 +253,10 @@ void or_collide_adj(float *pos, const float *prev, const float *spos, const floa
                 float dpt[3] = {rel[0] - dn * nf[0], rel[1] - dn * nf[1], rel[2] - dn * nf[2]};
                 float ldpt = sqrtf(dot3(dpt, dpt));
                 if (ldpt < EPS) continue;
-                if (ldpt < S_FRICTION * dist) {
+                if (ldpt < S_FRICTION * fd) {
                     for (int c = 0; c < 3; c++) delta[c] -= (dpt[c] * colW) / (colW + colW2);
                 } else {
-                    float m = fminf(K_FRICTION * dist / ldpt, 1.f);
+                    float m = fminf(K_FRICTION * fd / ldpt, 1.f);
                     for (int c = 0; c < 3; c++) delta[c] -= dpt[c] * m;
                 }
             }
@@ -241,7 +272,7 @@ void or_collide_adj(float *pos, const float *prev, const float *spos, const floa
 
 void or_collide(float *pos, const float *prev, const float *spos, const float *sw, const int *sphase, const u32 *index,
                 const u32 *cell_start, const u32 *cell_end, u32 n, const OrParams *p, u32 *num_neighbors) {
-    or_collide_adj(pos, prev, spos, sw, sphase, index, cell_start, cell_end, n, p, num_neighbors, NULL, NULL);
+    or_collide_ext(pos, prev, spos, sw, sphase, index, cell_start, cell_end, n, p, num_neighbors, NULL, NULL, NULL);
 }
 
 /* neighbour gather of findLambdasD / collideCellRadius (integration_kernel.cuh:482-559) */

@@ -156,6 +156,7 @@ def lib():
         L.ps_num_rigid_bodies.restype = u64
         L.ps_solve_shapes.argtypes = [vp]
         L.ps_rigid_body_rotation.argtypes = [vp, u32, vp]
+        L.ps_set_rigid_body_sdf.argtypes = [vp, u32, vp]
         L.ps_set_viscosity.argtypes = [vp, f32, f32]
         L.ps_find_neighbors.argtypes = [vp]
         L.ps_apply_viscosity.argtypes = [vp, f32]
@@ -227,6 +228,27 @@ def _ptr(a):
 
 def _arr(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def box_sdf(nx, ny, nz, radius=0.25):
+    """SDF data of an nx x ny x nz lattice box of touching particles (x slowest, z fastest — np.meshgrid(..., indexing="ij") order), the way
+    the reference CPU app's builders write it down (cpu/src/simulation.cpp:666-672): outward normal of the nearest face — the
+    normalised sum of the nearest faces' normals on edges and corners — and depth = (layer + 1/2) * diameter * sqrt(number of such faces)"""
+    out = np.zeros((nx * ny * nz, 4), np.float32)
+    k = 0
+    for a in range(nx):
+        for b in range(ny):
+            for c in range(nz):
+                depth = [(a, (-1, 0, 0)), (nx - 1 - a, (1, 0, 0)), (b, (0, -1, 0)), (ny - 1 - b, (0, 1, 0)), (c, (0, 0, -1)), (nz - 1 - c, (0, 0, 1))]
+                lo = min(d for d, _ in depth)
+                g = np.sum([nrm for d, nrm in depth if d == lo], axis=0).astype(np.float64)
+                faces = sum(1 for d, _ in depth if d == lo)
+                if np.linalg.norm(g) < 1e-9:      # opposite faces equally near (a one- or two-particle-thick direction): no preferred side
+                    g = np.array([0.0, 1.0, 0.0]); faces = 1
+                out[k, :3] = g / np.linalg.norm(g)
+                out[k, 3] = (lo + 0.5) * 2 * radius * np.sqrt(faces)
+                k += 1
+    return out
 
 
 class Solver:
@@ -380,6 +402,11 @@ class Solver:
         q = np.zeros(4, np.float32)
         _check(lib().ps_rigid_body_rotation(self._h, int(body), _ptr(q)))
         return q
+
+    def set_rigid_body_sdf(self, body, sdf4):
+        """per member (gx, gy, gz, depth): outward normal in the body's rest frame and depth below the surface; depth < 0 = none"""
+        a = _arr(sdf4, np.float32).reshape(-1, 4)
+        _check(lib().ps_set_rigid_body_sdf(self._h, int(body), _ptr(a)))
 
     def set_viscosity(self, xsph_c=0.0, vorticity_eps=0.0): _check(lib().ps_set_viscosity(self._h, xsph_c, vorticity_eps))
     def find_neighbors(self): _check(lib().ps_find_neighbors(self._h))

@@ -57,7 +57,7 @@ extern "C" int ps_save(PsCtx *c, const char *path) {
     if (c->num_bodies) KCU(cudaMemcpy(quat.data(), c->body_quat, 16 * (size_t)c->num_bodies, cudaMemcpyDeviceToHost));
     Header h{};
     memcpy(h.magic, kMagic, 8);
-    h.version = 1; h.params_bytes = (uint32_t)sizeof(PsParams);
+    h.version = 2; h.params_bytes = (uint32_t)sizeof(PsParams);
     h.n = n; h.limit = c->limit; h.num_distance = c->h_dist_rest.size(); h.num_point = c->h_point_idx.size();
     h.num_bodies = c->num_bodies; h.body_members = c->h_body_idx.size(); h.rand_calls = c->rand_calls;
     h.xsph_c = c->xsph_c; h.vorticity_eps = c->vorticity_eps;
@@ -71,6 +71,8 @@ extern "C" int ps_save(PsCtx *c, const char *path) {
               put(F.f, c->h_body_off.data(), c->h_body_off.size()) && put(F.f, c->h_body_idx.data(), c->h_body_idx.size()) &&
               put(F.f, c->h_body_rest.data(), c->h_body_rest.size()) && put(F.f, c->h_body_stiff.data(), c->h_body_stiff.size()) &&
               put(F.f, quat.data(), quat.size());
+    const uint64_t sdf_members = c->has_sdf ? c->h_body_idx.size() : 0;  // version 2: SDF data of the rigid bodies (4 floats per member) or none
+    ok = ok && put(F.f, &sdf_members, 1) && put(F.f, c->h_body_sdf.data(), (size_t)(4 * sdf_members));
     if (!ok || fflush(F.f) != 0) { ps_set_error("ps_save: short write to %s", path); return PS_ERR_INVALID; }
     return PS_OK;
 }
@@ -83,7 +85,7 @@ extern "C" int ps_load(const char *path, int device, PsCtx **out) {
     if (!F.f) { ps_set_error("ps_load: cannot open %s", path); return PS_ERR_INVALID; }
     Header h{};
     if (!get(F.f, &h, 1) || memcmp(h.magic, kMagic, 8) != 0) { ps_set_error("ps_load: %s is not a libpsolver checkpoint", path); return PS_ERR_INVALID; }
-    if (h.version != 1 || h.params_bytes != sizeof(PsParams)) { ps_set_error("ps_load: checkpoint version %u / parameter block of %u bytes not understood", h.version, h.params_bytes); return PS_ERR_INVALID; }
+    if ((h.version != 1 && h.version != 2) || h.params_bytes != sizeof(PsParams)) { ps_set_error("ps_load: checkpoint version %u / parameter block of %u bytes not understood", h.version, h.params_bytes); return PS_ERR_INVALID; }
     if (h.n > h.limit || h.limit > (1ull << 31) || h.num_distance > (1ull << 32) || h.num_point > (1ull << 32) || h.body_members > h.n * 64 + 64 || h.num_bodies > h.body_members) {
         ps_set_error("ps_load: implausible sizes in %s", path); return PS_ERR_INVALID;
     }
@@ -99,6 +101,14 @@ extern "C" int ps_load(const char *path, int device, PsCtx **out) {
               get(F.f, pidx.data(), pidx.size()) && get(F.f, pxyz.data(), pxyz.size()) && get(F.f, boff.data(), boff.size()) &&
               get(F.f, bidx.data(), bidx.size()) && get(F.f, brest.data(), brest.size()) && get(F.f, bstiff.data(), bstiff.size()) &&
               get(F.f, quat.data(), quat.size());
+    std::vector<float> bsdf(4 * h.body_members, 0.f);
+    for (size_t k = 3; k < bsdf.size(); k += 4) bsdf[k] = -1.f;
+    bool has_sdf = false;
+    if (ok && h.version >= 2) {
+        uint64_t sdf_members = 0;
+        ok = get(F.f, &sdf_members, 1) && (sdf_members == 0 || sdf_members == h.body_members) && get(F.f, bsdf.data(), (size_t)(4 * sdf_members));
+        has_sdf = ok && sdf_members != 0;
+    }
     if (!ok) { ps_set_error("ps_load: truncated file %s", path); return PS_ERR_INVALID; }
     for (u32 v : bidx) if (v >= n) { ps_set_error("ps_load: body member index out of range"); return PS_ERR_INVALID; }
     if (boff[0] != 0 || boff[h.num_bodies] != h.body_members) { ps_set_error("ps_load: inconsistent body table"); return PS_ERR_INVALID; }
@@ -112,6 +122,7 @@ extern "C" int ps_load(const char *path, int device, PsCtx **out) {
     if ((r = ps_add_point_constraints(c, pidx.data(), pxyz.data(), h.num_point)) != PS_OK) return fail(r);
     // bodies: the stored rest shape, not the current configuration
     c->h_body_off = boff; c->h_body_idx = bidx; c->h_body_rest = brest; c->h_body_stiff = bstiff;
+    c->h_body_sdf = bsdf; c->has_sdf = has_sdf; c->sdf_dirty = has_sdf;
     c->num_bodies = (u32)h.num_bodies;
     c->bodies_uploaded = 0;
     if ((r = ps_ext_sync_bodies(c)) != PS_OK) return fail(r);

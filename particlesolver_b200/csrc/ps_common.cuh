@@ -118,7 +118,7 @@ void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool 
 // ps_neighbor_kernels.cu
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                        const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, const u32 *adj_off,
-                       const u32 *adj, cudaStream_t s);
+                       const u32 *adj, const float4 *sdf_world, cudaStream_t s);
 // nbr_list / nbr_rows: interleaved per-warp neighbour lists written by K6 and consumed by K7 (nullptr: K7 re-walks the grid)
 // (in the launchers below `max_rows` is the number of chunks in the pool, ps_neighbor_pool_chunks, and `nbr_rows` the first
 // per-warp record of the buffer sized by ps_neighbor_record_elems)
@@ -138,6 +138,8 @@ u32 ps_launch_viscosity(float4 *vel, float4 *scratch, const float4 *spos, const 
 u32 ps_launch_density_error(float4 *scratch, const float4 *spos, const float *sw, const int *sphase, const u32 *index, const float *ros, const u32 *cell_begin,
                             u32 n, GridDesc g, const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s);
 // ps_shape_kernels.cu — K12 (not in the reference's GPU solver): shape matching, one warp per rigid body
+void ps_launch_sdf_world(float4 *sdf_world, const float4 *sdf_rest, const u32 *body_idx, const u32 *member_body, const float4 *quat, u32 members,
+                         cudaStream_t s);
 void ps_launch_shape_match(float4 *pos, const u32 *body_off, const u32 *body_idx, const float4 *rest, float4 *quat, const float *stiff, u32 num_bodies,
                            int max_iters, cudaStream_t s);
 // ps_slab_kernels.cu — slab decomposition: ordered selection / packing / compaction

@@ -512,8 +512,9 @@ extern "C" int ps_solve_contacts(PsCtx *c) {
     int r = ready(c); if (r != PS_OK) return r;
     if (c->n && !c->grid_valid) { ps_set_error("ps_solve_contacts: no grid (call ps_build_grid)"); return PS_ERR_STATE; }
     DeviceGuard dg(c->device);
+    ps_ext_issue_sdf(c);
     ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, c->n, c->n - c->n_ghost, c->grid,
-                      c->params.particle_radius, self_collision_adj(c), c->adj, c->stream);
+                      c->params.particle_radius, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, c->stream);
     return check_launch("ps_solve_contacts");
 }
 static int issue_fluid(PsCtx *c, const char *what, bool do_lambda, bool do_delta) {
@@ -581,8 +582,9 @@ static u32 issue_step(PsCtx *c, float dt) {
     for (u32 it = 0; it < p.solver_iterations; it++) {
         launches += ps_issue_build_grid(c, c->pos);
         if (has_contact) {
+            launches += ps_ext_issue_sdf(c);
             ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n_owned, c->grid,
-                              p.particle_radius, self_collision_adj(c), c->adj, s);
+                              p.particle_radius, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, s);
             launches++;
         }
         if (has_fluid) {
@@ -681,7 +683,7 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
         ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s); mark(4, 1);
         c->grid_valid = true;
         c->ref_tables_valid = false;
-        if (has_contact) { ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, self_collision_adj(c), c->adj, s); mark(5, 1); }
+        if (has_contact) { const u32 lsdf = ps_ext_issue_sdf(c); ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, s); mark(5, 1 + lsdf); }
         if (has_fluid) {
             ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->lambda_xmin,
                                    c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list, c->nbr_rows,

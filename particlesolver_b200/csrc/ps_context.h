@@ -78,6 +78,13 @@ struct PsCtx {
     u32 *body_off = nullptr, *body_idx = nullptr;
     float4 *body_rest = nullptr, *body_quat = nullptr;
     float *body_stiff = nullptr;
+    // SDF contacts between rigid bodies (ps_set_rigid_body_sdf): per member (unit outward gradient in the rest frame, depth), w < 0 = none;
+    // sdf_world = the same by particle index in the world frame, refreshed before every contact pass
+    std::vector<float> h_body_sdf;  // 4 per member
+    bool has_sdf = false, sdf_dirty = false;
+    float4 *body_sdf = nullptr, *sdf_world = nullptr;
+    u32 *member_body = nullptr;
+    uint64_t sdf_capacity = 0;
     // XSPH viscosity / vorticity confinement (K13): coefficients (0 = off) and scratch (omega | dv, float4[2 * capacity])
     float xsph_c = 0.f, vorticity_eps = 0.f;
     float4 *visc_scratch = nullptr;
@@ -119,6 +126,7 @@ SortScratch ps_ctx_sort_scratch(PsCtx *c, u32 n);
 int ps_ext_sync_bodies(PsCtx *c);
 int ps_ext_prepare_step(PsCtx *c);
 u32 ps_ext_issue_shapes(PsCtx *c);
+u32 ps_ext_issue_sdf(PsCtx *c);  // world-frame SDF for the next contact pass (0 launches when no body carries one)
 u32 ps_ext_issue_viscosity(PsCtx *c, float dt);
 void ps_ext_free(PsCtx *c);
 

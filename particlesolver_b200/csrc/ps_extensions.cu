@@ -29,7 +29,7 @@ constexpr int kShapeIters = 64;  // rotation-extraction iterations per call at m
 }  // namespace
 
 void ps_ext_free(PsCtx *c) {
-    void *ptrs[] = {c->body_off, c->body_idx, c->body_rest, c->body_quat, c->body_stiff, c->visc_scratch};
+    void *ptrs[] = {c->body_off, c->body_idx, c->body_rest, c->body_quat, c->body_stiff, c->visc_scratch, c->body_sdf, c->sdf_world, c->member_body};
     for (void *p : ptrs) if (p) cudaFree(p);
 }
 
@@ -58,6 +58,8 @@ extern "C" int ps_add_rigid_body(PsCtx *c, const uint32_t *indices, uint64_t n, 
         c->h_body_idx.push_back(indices[k]);
         c->h_body_rest.push_back((float)(pos[4 * k] - cx)); c->h_body_rest.push_back((float)(pos[4 * k + 1] - cy));
         c->h_body_rest.push_back((float)(pos[4 * k + 2] - cz)); c->h_body_rest.push_back(1.0f / w[k]);
+        const float none[4] = {0.f, 0.f, 0.f, -1.f};
+        c->h_body_sdf.insert(c->h_body_sdf.end(), none, none + 4);
     }
     c->h_body_off.push_back((u32)c->h_body_idx.size());
     c->h_body_stiff.push_back(stiffness);
@@ -67,17 +69,46 @@ extern "C" int ps_add_rigid_body(PsCtx *c, const uint32_t *indices, uint64_t n, 
 }
 extern "C" uint64_t ps_num_rigid_bodies(PsCtx *c) { return c ? c->num_bodies : 0; }
 
+// Signed-distance data of a body's particles, in the frame the body was added in: per member (gx, gy, gz, depth) — the outward
+// surface normal nearest to the particle and how deep the particle sits below the surface (the reference CPU app's SDFData,
+// cpu/src/solver/particle.h:82-93: its box builders use depth = radius for face particles, radius * sqrt(2) at corners,
+// simulation.cpp:666-672).  depth < 0 = this member has none.  Contacts between two particles that both carry SDF data then
+// follow RigidContactConstraint (rigidcontactconstraint.cpp:13-96) instead of the centre-to-centre rule.
+extern "C" int ps_set_rigid_body_sdf(PsCtx *c, uint32_t body, const float *sdf4) {
+    if (!c || !sdf4) { ps_set_error("ps_set_rigid_body_sdf: null argument"); return PS_ERR_INVALID; }
+    if (body >= c->num_bodies) { ps_set_error("ps_set_rigid_body_sdf: body %u of %u", body, c->num_bodies); return PS_ERR_INVALID; }
+    const u32 b0 = c->h_body_off[body], b1 = c->h_body_off[body + 1];
+    for (u32 k = b0; k < b1; k++) {
+        const float *g = sdf4 + 4 * (size_t)(k - b0);
+        if (!(g[3] >= 0.f)) continue;
+        const float len = std::sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+        if (!(len > 1e-6f) || !std::isfinite(len) || !std::isfinite(g[3])) { ps_set_error("ps_set_rigid_body_sdf: member %u has depth %g but no gradient", k - b0, (double)g[3]); return PS_ERR_INVALID; }
+    }
+    for (u32 k = b0; k < b1; k++) {
+        const float *g = sdf4 + 4 * (size_t)(k - b0);
+        float *o = &c->h_body_sdf[4 * (size_t)k];
+        if (!(g[3] >= 0.f)) { o[0] = o[1] = o[2] = 0.f; o[3] = -1.f; continue; }
+        const float inv = 1.f / std::sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+        o[0] = g[0] * inv; o[1] = g[1] * inv; o[2] = g[2] * inv; o[3] = g[3];
+    }
+    c->has_sdf = false;
+    for (size_t k = 3; k < c->h_body_sdf.size(); k += 4) if (c->h_body_sdf[k] >= 0.f) { c->has_sdf = true; break; }
+    c->sdf_dirty = true;
+    return PS_OK;
+}
+
 int ps_ext_sync_bodies(PsCtx *c) {
-    if (c->bodies_uploaded == c->num_bodies) return PS_OK;
+    if (c->bodies_uploaded == c->num_bodies && !c->sdf_dirty && (!c->has_sdf || c->sdf_capacity >= c->capacity)) return PS_OK;
     cudaStream_t s = c->stream;
     XCU(cudaStreamSynchronize(s));
     // keep the rotations of the bodies that already existed (warm start), identity for the new ones
     std::vector<float> quat(4 * (size_t)c->num_bodies, 0.f);
     for (u32 b = 0; b < c->num_bodies; b++) quat[4 * b + 3] = 1.f;
     if (c->bodies_uploaded) XCU(cudaMemcpy(quat.data(), c->body_quat, 16 * (size_t)c->bodies_uploaded, cudaMemcpyDeviceToHost));
-    void *old[] = {c->body_off, c->body_idx, c->body_rest, c->body_quat, c->body_stiff};
+    void *old[] = {c->body_off, c->body_idx, c->body_rest, c->body_quat, c->body_stiff, c->body_sdf, c->sdf_world, c->member_body};
     for (void *p : old) if (p) cudaFree(p);
-    c->body_off = c->body_idx = nullptr; c->body_rest = c->body_quat = nullptr; c->body_stiff = nullptr;
+    c->body_off = c->body_idx = c->member_body = nullptr; c->body_rest = c->body_quat = c->body_sdf = c->sdf_world = nullptr; c->body_stiff = nullptr;
+    c->sdf_capacity = 0;
     const size_t m = c->h_body_idx.size();
     XCU(cudaMalloc((void **)&c->body_off, (c->num_bodies + 1) * sizeof(u32)));
     XCU(cudaMalloc((void **)&c->body_idx, m * sizeof(u32)));
@@ -89,9 +120,28 @@ int ps_ext_sync_bodies(PsCtx *c) {
     XCU(cudaMemcpy(c->body_rest, c->h_body_rest.data(), m * sizeof(float4), cudaMemcpyHostToDevice));
     XCU(cudaMemcpy(c->body_quat, quat.data(), c->num_bodies * sizeof(float4), cudaMemcpyHostToDevice));
     XCU(cudaMemcpy(c->body_stiff, c->h_body_stiff.data(), c->num_bodies * sizeof(float), cudaMemcpyHostToDevice));
+    if (c->has_sdf) {
+        std::vector<u32> member_body(m);
+        for (u32 b = 0; b < c->num_bodies; b++)
+            for (u32 k = c->h_body_off[b]; k < c->h_body_off[b + 1]; k++) member_body[k] = b;
+        XCU(cudaMalloc((void **)&c->body_sdf, m * sizeof(float4)));
+        XCU(cudaMalloc((void **)&c->member_body, m * sizeof(u32)));
+        XCU(cudaMalloc((void **)&c->sdf_world, (size_t)c->capacity * sizeof(float4)));
+        XCU(cudaMemcpy(c->body_sdf, c->h_body_sdf.data(), m * sizeof(float4), cudaMemcpyHostToDevice));
+        XCU(cudaMemcpy(c->member_body, member_body.data(), m * sizeof(u32), cudaMemcpyHostToDevice));
+        XCU(cudaMemset(c->sdf_world, 0xff, (size_t)c->capacity * sizeof(float4)));  // NaN depth = no SDF
+        c->sdf_capacity = c->capacity;
+    }
+    c->sdf_dirty = false;
     c->bodies_uploaded = c->num_bodies;
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     return PS_OK;
+}
+
+u32 ps_ext_issue_sdf(PsCtx *c) {
+    if (!c->has_sdf) return 0;
+    ps_launch_sdf_world(c->sdf_world, c->body_sdf, c->body_idx, c->member_body, c->body_quat, (u32)c->h_body_idx.size(), c->stream);
+    return 1;
 }
 
 u32 ps_ext_issue_shapes(PsCtx *c) {

@@ -634,12 +634,36 @@ __device__ __forceinline__ float ps_scaled_w(float w, float y) {
     return (w != 0.f) ? __fdividef(1.f, __fdividef(1.f, w) * __expf(-y)) : w;
 }
 
+// SDF contact of two rigid-body particles: the reference CPU app's RigidContactConstraint (cpu/src/constraint/
+// rigidcontactconstraint.cpp:13-66, 2-D) lifted to 3-D.  si / sj = (outward unit gradient in world frame, depth below the body's
+// surface) of this particle and its partner, r = x_i - x_j.  The particle that sits shallower in its own body supplies normal and
+// depth (ties: the lower particle index, so that both particles of a pair see the same contact); for a particle of the outermost
+// layers (depth < diameter + EPS) the depth is the particles' overlap and the normal x_ij mirrored at the SDF normal when it points
+// against it (Macklin et al. 2014, eq. 13-14).  Returns false when the pair needs no correction; e = normal as the reference
+// leaves it (not normalised in the boundary case), pointing from i to j.
+__device__ __forceinline__ bool sdf_contact(float4 si, float4 sj, bool i_first, float rx, float ry, float rz, float dist, float diam, float &d,
+                                            float &ex, float &ey, float &ez) {
+    const bool mine = si.w < sj.w || (si.w == sj.w && i_first);
+    if (mine) { d = si.w; ex = si.x; ey = si.y; ez = si.z; }
+    else { d = sj.w; ex = -sj.x; ey = -sj.y; ez = -sj.z; }
+    if (d < diam + PS_EPS) {
+        d = diam - dist;
+        if (d < PS_EPS) return false;
+        float x = 0.f, y = 1.f, z = 0.f;
+        if (dist > PS_EPS) { const float inv = __fdividef(1.f, dist); x = rx * inv; y = ry * inv; z = rz * inv; }
+        const float dp = x * ex + y * ey + z * ez;
+        if (dp < 0.f) { ex = x - 2.f * dp * ex; ey = y - 2.f * dp * ey; ez = z - 2.f * dp * ez; }
+        else { ex = x; ey = y; ez = z; }
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, const float4 *__restrict__ prev,
                                                     const float4 *__restrict__ spos, const float *__restrict__ sw,
                                                     const int *__restrict__ sphase, const u32 *__restrict__ index,
                                                     const u32 *__restrict__ cell_begin, u32 *__restrict__ num_neighbors, u32 n, u32 n_owned,
                                                     GridDesc g, StencilDesc st, float radius, const u32 *__restrict__ adj_off,
-                                                    const u32 *__restrict__ adj) {
+                                                    const u32 *__restrict__ adj, const float4 *__restrict__ sdf_world) {
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
     const int phase = sphase[i];
@@ -684,6 +708,8 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
         const float sW = ps_scaled_w(w, pi.y);
         const float4 pp = __ldg(prev + orig);
         const float fn = (float)nn;
+        // SDF contacts between rigid bodies (ps_set_rigid_body_sdf; not in the reference's GPU solver): w < 0 (or NaN) = no SDF
+        const float4 si = sdf_world ? __ldg(sdf_world + orig) : make_float4(0.f, 0.f, 0.f, -1.f);
         u32 seen = 0;
         for_each_candidate(g, st, cell_begin, gp, [&](u32 j) {
             if (j == i || seen >= nn) return;
@@ -707,14 +733,26 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
             }
             const float wsum = colW + colW2;
             const float sd = __fdividef(__fdividef(mag, wsum), dist);
-            const float px = rx * sd, py = ry * sd, pz = rz * sd;  // dp
+            float px = rx * sd, py = ry * sd, pz = rz * sd;  // dp
+            float fnx = rx, fny = ry, fnz = rz, fd = dist;    // friction: normal before normalisation, length scale of the cone
+            if (both_solid && si.w >= 0.f) {
+                const u32 oj = __ldg(index + j);
+                const float4 sj = __ldg(sdf_world + oj);
+                if (sj.w >= 0.f) {
+                    float d, ex, ey, ez;
+                    if (!sdf_contact(si, sj, orig < oj, rx, ry, rz, dist, 2.f * radius, d, ex, ey, ez)) return;
+                    const float s_ = __fdividef(d, wsum);
+                    px = ex * s_; py = ey * s_; pz = ez * s_;
+                    fnx = ex; fny = ey; fnz = ez; fd = d;  // the CPU constraint's cone uses the depth (rigidcontactconstraint.cpp:84-90)
+                }
+            }
             const float d1x = __fdividef(-colW * px, fn), d1y = __fdividef(-colW * py, fn), d1z = __fdividef(-colW * pz, fn);
             dxs += d1x; dys += d1y; dzs += d1z;
             if (!both_solid) return;
             const float d2x = __fdividef(colW2 * px, fn), d2y = __fdividef(colW2 * py, fn), d2z = __fdividef(colW2 * pz, fn);
             const float4 pp2 = __ldg(prev + __ldg(index + j));
-            const float inv = rsqrtf(d2);
-            const float nx = rx * inv, ny = ry * inv, nz = rz * inv;
+            const float inv = rsqrtf(fnx * fnx + fny * fny + fnz * fnz);  // == rsqrtf(d2) for plain contacts
+            const float nx = fnx * inv, ny = fny * inv, nz = fnz * inv;
             // [sic] the reference's second term starts from prevPos of i, not pos2 (integration_kernel.cuh:447)
             const float ex = (pi.x + d1x - pp.x) - (pp.x + d2x - pp2.x);
             const float ey = (pi.y + d1y - pp.y) - (pp.y + d2y - pp2.y);
@@ -723,10 +761,10 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
             const float tx = ex - dn * nx, ty = ey - dn * ny, tz = ez - dn * nz;
             const float lt = sqrtf(tx * tx + ty * ty + tz * tz);
             if (lt < PS_EPS) return;
-            if (lt < PS_S_FRICTION * dist) {
+            if (lt < PS_S_FRICTION * fd) {
                 dxs -= __fdividef(tx * colW, wsum); dys -= __fdividef(ty * colW, wsum); dzs -= __fdividef(tz * colW, wsum);
             } else {
-                const float m = fminf(__fdividef(PS_K_FRICTION * dist, lt), 1.f);
+                const float m = fminf(__fdividef(PS_K_FRICTION * fd, lt), 1.f);
                 dxs -= tx * m; dys -= ty * m; dzs -= tz * m;
             }
         });
@@ -739,12 +777,12 @@ static inline u32 cdiv(u32 a, u32 b) { return (a + b - 1) / b; }
 
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                        const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, const u32 *adj_off,
-                       const u32 *adj, cudaStream_t s) {
+                       const u32 *adj, const float4 *sdf_world, cudaStream_t s) {
     if (!n) return;
     StencilDesc st;  // 3x3x3: every row keeps its full extent (contact radius 2.001r slightly exceeds one cell)
     st.rad = 1;
     for (int k = 0; k < 9; k++) st.xr[k] = 1;
-    k_collide<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, prev, spos, sw, sphase, index, cell_begin, num_neighbors, n, n_owned, g, st, radius, adj_off, adj);
+    k_collide<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, prev, spos, sw, sphase, index, cell_begin, num_neighbors, n, n_owned, g, st, radius, adj_off, adj, sdf_world);
 }
 
 // pool of list rows for `capacity` particles at `rows_per_warp` rows reserved per warp on average

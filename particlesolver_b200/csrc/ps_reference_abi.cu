@@ -129,7 +129,7 @@ void collide(float *particles, float *sortedPos, float *sortedW, int *sortedPhas
     PsCtx *c = ctx();
     need_dense(cellStart, numCells, "collide");
     ps_launch_collide((float4 *)particles, c->prev, (const float4 *)sortedPos, sortedW, sortedPhase, index, c->cell_begin, c->num_neighbors, n,
-                      n, c->grid, c->params.particle_radius, nullptr, nullptr, c->stream);  // the reference ABI: the reference same-phase rule
+                      n, c->grid, c->params.particle_radius, nullptr, nullptr, nullptr, c->stream);  // the reference ABI: the reference same-phase rule
     ck_launch("collide");
 }
 

@@ -110,7 +110,26 @@ __global__ void __launch_bounds__(kBlock) k_shape_match(float4 *__restrict__ pos
         pos[i] = p;
     }
 }
+
+// World-frame SDF of every rigid-body member for the contact pass: the stored gradient (rest frame) turned by the body's current
+// rotation; depth unchanged.  One thread per member; members without SDF data (w < 0) are left alone.
+__global__ void __launch_bounds__(256) k_sdf_world(float4 *__restrict__ sdf_world, const float4 *__restrict__ sdf_rest, const u32 *__restrict__ body_idx,
+                                                   const u32 *__restrict__ member_body, const float4 *__restrict__ quat, u32 members) {
+    const u32 k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= members) return;
+    const float4 g = sdf_rest[k];
+    if (!(g.w >= 0.f)) return;
+    const Mat3 R = quat_to_mat(quat[member_body[k]]);
+    sdf_world[body_idx[k]] = make_float4(R.m[0][0] * g.x + R.m[0][1] * g.y + R.m[0][2] * g.z, R.m[1][0] * g.x + R.m[1][1] * g.y + R.m[1][2] * g.z,
+                                         R.m[2][0] * g.x + R.m[2][1] * g.y + R.m[2][2] * g.z, g.w);
+}
 }  // namespace
+
+void ps_launch_sdf_world(float4 *sdf_world, const float4 *sdf_rest, const u32 *body_idx, const u32 *member_body, const float4 *quat, u32 members,
+                         cudaStream_t s) {
+    if (!members) return;
+    k_sdf_world<<<(members + 255) / 256, 256, 0, s>>>(sdf_world, sdf_rest, body_idx, member_body, quat, members);
+}
 
 void ps_launch_shape_match(float4 *pos, const u32 *body_off, const u32 *body_idx, const float4 *rest, float4 *quat, const float *stiff, u32 num_bodies,
                            int max_iters, cudaStream_t s) {

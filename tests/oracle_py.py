@@ -43,8 +43,8 @@ def lib():
         L.or_sort.argtypes = [vp, vp, u32]
         L.or_reorder.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp, vp, vp, vp, vp]
         L.or_collide.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32, P, vp]
-        L.or_collide_adj.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32, P, vp, vp, vp]
-        L.or_collide_adj.restype = None
+        L.or_collide_ext.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u32, P, vp, vp, vp, vp]
+        L.or_collide_ext.restype = None
         L.or_solve_fluids.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, P, vp, vp, vp]
         L.or_solve_fluids_stages.argtypes = [vp, vp, vp, vp, vp, vp, vp, u32, P, vp, vp, vp, C.c_int]
         L.or_solve_fluids_stages.restype = None
@@ -121,6 +121,7 @@ class OracleSystem:
         self.dist_nonprefix = 0
         self.self_collision = False  # True: the opt-in rule of PS_FLAG_SELF_COLLISION (not the reference's)
         self._adj = None
+        self.sdf_world = None        # (n, 4) float32 by particle index: world-frame SDF of rigid-body particles (ps_set_rigid_body_sdf), depth < 0 = none
 
     def predict(self, dt):
         g = np.array(list(self.p.gravity), np.float32)
@@ -151,10 +152,13 @@ class OracleSystem:
         return self._adj
 
     def collide(self):
-        if self.self_collision and self.dist_rest.size:
-            off, adj = self._adjacency()
-            lib().or_collide_adj(_p(self.pos), _p(self.prev), _p(self.spos), _p(self.sw), _p(self.sphase), _p(self.index), _p(self.cell_start),
-                                 _p(self.cell_end), self.n, C.byref(self.p), _p(self.nn), _p(off), _p(adj))
+        use_adj = self.self_collision and self.dist_rest.size
+        if use_adj or self.sdf_world is not None:
+            off, adj = self._adjacency() if use_adj else (None, None)
+            sdf = np.ascontiguousarray(self.sdf_world, np.float32) if self.sdf_world is not None else None
+            lib().or_collide_ext(_p(self.pos), _p(self.prev), _p(self.spos), _p(self.sw), _p(self.sphase), _p(self.index), _p(self.cell_start),
+                                 _p(self.cell_end), self.n, C.byref(self.p), _p(self.nn), _p(off) if use_adj else None, _p(adj) if use_adj else None,
+                                 _p(sdf) if sdf is not None else None)
             return
         lib().or_collide(_p(self.pos), _p(self.prev), _p(self.spos), _p(self.sw), _p(self.sphase), _p(self.index), _p(self.cell_start),
                          _p(self.cell_end), self.n, C.byref(self.p), _p(self.nn))
