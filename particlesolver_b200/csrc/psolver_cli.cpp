@@ -2,7 +2,7 @@
 // The reference's only front ends are two Qt viewers whose scenes are bound to keys (gpu/src/particleapp.cpp:141-215,
 // cpu/src/view.cpp:129-177); this runs the same scenes without a display, over libpsolver.so's public C / C++ API only:
 //   psolver_cli --app gpu --scene 7 --steps 600 [--dt 0.016667] [--grid 64] [--max-particles 15000] [--side 100]
-//               [--iterations 5] [--xsph 0.01 --vorticity 0.3]
+//               [--iterations 5] [--xsph 0.01 --vorticity 0.3] [--self-collision] [--gas]
 //   psolver_cli --app cpu --scene 6 --steps 1000 [--dt 0.01]
 //   psolver_cli --app session --script "6:100,1:50,w:20"     the CPU app as a user drives it: psb200::Simulation (constructor
 //               builds WRECKING_BALL), then key presses and ticks; the rand() stream runs on across scenes like the reference's
@@ -31,6 +31,7 @@ struct Args {
     double dt = -1;
     float xsph = 0.f, vorticity = 0.f;
     bool json = false;
+    unsigned flags = 0;  // PS_FLAG_* switched on from the command line
 };
 [[noreturn]] void die(const std::string &m) { fprintf(stderr, "psolver_cli: %s\n", m.c_str()); exit(1); }
 void check(int r, const char *what) { if (r != PS_OK) die(std::string(what) + ": " + ps_last_error()); }
@@ -59,6 +60,12 @@ int run_gpu(const Args &a) {
         if (!ps) die("unknown GPU scene '" + a.scene + "' (1-9, c2, c3)");
         if (!ps->lastError().empty()) die(ps->lastError());
         ctx = ps->context();
+    }
+    if (a.flags) {
+        PsParams p;
+        check(ps_get_params(ctx, &p), "ps_get_params");
+        p.flags |= a.flags;
+        check(ps_set_params(ctx, &p), "ps_set_params");
     }
     if (a.xsph != 0.f || a.vorticity != 0.f) check(ps_set_viscosity(ctx, a.xsph, a.vorticity), "ps_set_viscosity");
     const float dt = a.dt > 0 ? (float)a.dt : 1.f / 60.f;
@@ -191,6 +198,8 @@ int main(int argc, char **argv) {
         else if (k == "--out") a.out = val();
         else if (k == "--xsph") a.xsph = (float)atof(val());
         else if (k == "--vorticity") a.vorticity = (float)atof(val());
+        else if (k == "--self-collision") a.flags |= PS_FLAG_SELF_COLLISION;
+        else if (k == "--gas") a.flags |= PS_FLAG_GAS;
         else if (k == "--device") a.device = atoi(val());
         else if (k == "--json") a.json = true;
         else if (k == "--help" || k == "-h") { printf("see the header of particlesolver_b200/csrc/psolver_cli.cpp\n"); return 0; }

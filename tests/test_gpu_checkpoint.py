@@ -83,3 +83,12 @@ def test_cli_runs_both_apps_and_round_trips_checkpoints(tmp_path):
     assert raw[:7] == b"PSDUMP1" and len(raw) == 24 + 16 * 5324
     bad = subprocess.run([CLI, "--app", "cpu", "--scene", "x"], capture_output=True, text=True)
     assert bad.returncode == 1 and "unknown scene" in bad.stderr
+
+
+def test_cli_switches_the_optional_contact_rules_on():
+    """--self-collision sets PS_FLAG_SELF_COLLISION: scene 6 (solids falling on a held cloth) ends elsewhere than with the
+    reference's rule; scene 7 (fluid only, no distance constraints) is untouched by it"""
+    run = lambda *a: json.loads(subprocess.run([CLI, "--app", "gpu", "--steps", "40", "--json", *a], capture_output=True, text=True, check=True).stdout)
+    assert run("--scene", "7")["position_checksum"] == run("--scene", "7", "--self-collision")["position_checksum"]
+    a, b = run("--scene", "2"), run("--scene", "2", "--self-collision")
+    assert a["particles"] == b["particles"] and np.isfinite(b["kinetic_energy"])
