@@ -24,7 +24,8 @@
  *
  * The reference keeps this state in `Simulation` (QList<Particle*>, Body, Constraint objects); there is no extern "C"
  * boundary on its CPU side, so this header defines one whose entry points mirror the reference's constructors and
- * Simulation::create* helpers.  Not on this path: the stabilization pass (#undef in the reference), the UMFPACK matrix
+ * Simulation::create* helpers.  The stabilization pass (the reference's compile-time option USE_STABILIZATION, off in its build) is Ps2dParams.stabilization_iterations.
+ * Not on this path: the UMFPACK matrix
  * solver (dead under #define ITERATIVE), the emitters' display-only tracer particles.  No CPU fallback.
  */
 #ifndef PSOLVER2D_H
@@ -46,6 +47,10 @@ typedef struct Ps2dParams {
     double y_bounds[2];          /* m_yBoundaries  (scene 6: -8, 40  simulation.cpp:899) */
     double gravity[2];           /* m_gravity      (0, -9.8) */
     uint32_t solver_iterations;  /* SOLVER_ITERATIONS 3, simulation.h:11 */
+    uint32_t stabilization_iterations; /* 0 = the reference as built; 2 = built with its option USE_STABILIZATION (commented out in
+                                    simulation.h:17; STABILIZATION_ITERATIONS 2, :18): that many passes over stabile copies of the tick's
+                                    rigid contacts and wall constraints, which move p as well as ep, before the solver iterations
+                                    (simulation.cpp:249-271).  Occupies former padding: sizeof(Ps2dParams) is unchanged. */
 } Ps2dParams;
 
 typedef struct Ps2dCtx Ps2dCtx;
@@ -114,6 +119,9 @@ int ps2d_get_particle_timers(Ps2dCtx *ctx, double *t);
 int ps2d_set_forces(Ps2dCtx *ctx, const double *f2);     /* Particle::f of every particle (read by the next tick's prediction) */
 int ps2d_body_state(Ps2dCtx *ctx, uint32_t body, double *center2, double *angle);
 uint32_t ps2d_num_bodies(Ps2dCtx *ctx);
+
+/* Ps2dParams.stabilization_iterations of an existing context (0 = the reference as built, 2 = built with USE_STABILIZATION) */
+int ps2d_set_stabilization_iterations(Ps2dCtx *ctx, uint32_t iterations);
 
 /* position of the glibc rand() stream the wall jitter is drawn from: srand(seed), then `skip` draws already consumed
  * (the reference never seeds — seed 1 — and its scene builders consume draws before the first tick) */

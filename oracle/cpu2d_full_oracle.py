@@ -26,7 +26,9 @@ reference's, expression by expression (double precision, glm's component-wise ve
   OpenSmokeEmitter::tick               cpu/src/opensmokeemitter.cpp:17-29  (particle injection only; the emitter's own
                                        tracer particles are display-only and never read by the solver)
   FluidEmitter::tick                   cpu/src/fluidemitter.cpp:13-79  (VOLCANO scene: emission, freezing into solids)
-Not restated: the stabilization pass (#undef in the reference), the matrix solver (dead under ITERATIVE).
+The stabilization pass (the reference's compile-time option USE_STABILIZATION, off in its build) is restated behind
+`stabilization_iterations` and pinned by tests/golden/ref_cpu_scenes_stab.npz (oracle/_ref/ref_cpu_stab).  Not restated: the matrix
+solver (dead under ITERATIVE).
 """
 import math
 
@@ -65,8 +67,10 @@ def spiky_grad(rx, ry, rlen2):
 
 
 class Cpu2dFullOracle:
-    def __init__(self, scene, rand_seed=1):
-        """scene: the dict of scene.json written by oracle/_ref/ref_cpu --dump (see oracle/ref_cpu_driver.cpp)"""
+    def __init__(self, scene, rand_seed=1, stabilization_iterations=0):
+        """scene: the dict of scene.json written by oracle/_ref/ref_cpu --dump (see oracle/ref_cpu_driver.cpp);
+        stabilization_iterations: 0 = the reference as built, 2 = built with USE_STABILIZATION (STABILIZATION_ITERATIONS, simulation.h:18)"""
+        self.stabilization_iterations = int(stabilization_iterations)
         P = scene["particles"]
         self.p = [[q[0], q[1]] for q in P]
         self.v = [[q[2], q[3]] for q in P]
@@ -117,7 +121,9 @@ class Cpu2dFullOracle:
         return gx * c - gy * s, gx * s + gy * c, d
 
     # ------------------------------------------------------------------ constraints
-    def project_boundary(self, c, counts):
+    def project_boundary(self, c, counts, stabile=False):
+        """stabile: the STABILIZATION copy of the constraint (boundaryconstraint.cpp:32-35,74-76): moves p along with ep, no friction;
+        the jitter draw and the validity test (on ep) are the same"""
         i, value, is_x, greater = c[1], c[2], c[3], c[4]
         ep, p = self.ep[i], self.p[i]
         extra = self.frand() * .003 if self.ph[i] in (FLUID, GAS) else 0
@@ -127,23 +133,33 @@ class Cpu2dFullOracle:
                 if ep[0] >= value + PARTICLE_RAD:
                     return
                 ep[0] = value + d
+                if stabile:
+                    p[0] = value + d
                 n = (1., 0.)
             else:
                 if ep[1] >= value + PARTICLE_RAD:
                     return
                 ep[1] = value + d
+                if stabile:
+                    p[1] = value + d
                 n = (0., 1.)
         else:
             if is_x:
                 if ep[0] <= value - PARTICLE_RAD:
                     return
                 ep[0] = value - d
+                if stabile:
+                    p[0] = value - d
                 n = (-1., 0.)
             else:
                 if ep[1] <= value - PARTICLE_RAD:
                     return
                 ep[1] = value - d
+                if stabile:
+                    p[1] = value - d
                 n = (0., -1.)
+        if stabile:
+            return
         cnt = float(counts[i])
         dpx, dpy = (ep[0] - p[0]) / cnt, (ep[1] - p[1]) / cnt
         dn = dpx * n[0] + dpy * n[1]
@@ -180,9 +196,12 @@ class Cpu2dFullOracle:
         e2[0] += (t2 * dpx) / c2
         e2[1] += (t2 * dpy) / c2
 
-    def project_rigid_contact(self, c, counts):
+    def project_rigid_contact(self, c, counts, stabile=False):
+        """stabile: the STABILIZATION copy (rigidcontactconstraint.cpp:15,35,61-67,81-95): geometry from p (getP(true)), the
+        correction goes to p, friction to p and ep"""
         i1, i2 = c[1], c[2]
-        e1, e2 = self.ep[i1], self.ep[i2]
+        q1, q2 = self.ep[i1], self.ep[i2]          # always ep: friction
+        e1, e2 = (self.p[i1], self.p[i2]) if stabile else (q1, q2)   # getP(stabile): geometry and correction
         g1x, g1y, d1 = self.sdf_data(i1)
         g2x, g2y, d2 = self.sdf_data(i2)
         if d1 < 0 or d2 < 0:
@@ -226,7 +245,7 @@ class Cpu2dFullOracle:
         inv = 1. / math.sqrt(nx * nx + ny * ny)
         nfx, nfy = nx * inv, ny * inv
         p1, p2 = self.p[i1], self.p[i2]
-        fx, fy = (e1[0] - p1[0]) - (e2[0] - p2[0]), (e1[1] - p1[1]) - (e2[1] - p2[1])
+        fx, fy = (q1[0] - p1[0]) - (q2[0] - p2[0]), (q1[1] - p1[1]) - (q2[1] - p2[1])
         dn = fx * nfx + fy * nfy
         tx, ty = fx - dn * nfx, fy - dn * nfy
         ldpt = math.sqrt(tx * tx + ty * ty)
@@ -237,10 +256,15 @@ class Cpu2dFullOracle:
         if not (ldpt < sfric * d):
             m = min(kfric * d / ldpt, 1.)
             tx, ty = tx * m, ty * m
-        e1[0] -= (tx * t1) / wsum
-        e1[1] -= (ty * t1) / wsum
-        e2[0] += (tx * t2) / wsum
-        e2[1] += (ty * t2) / wsum
+        if stabile:
+            p1[0] -= (tx * t1) / wsum
+            p1[1] -= (ty * t1) / wsum
+            p2[0] += (tx * t2) / wsum
+            p2[1] += (ty * t2) / wsum
+        q1[0] -= (tx * t1) / wsum
+        q1[1] -= (ty * t1) / wsum
+        q2[0] += (tx * t2) / wsum
+        q2[1] += (ty * t2) / wsum
 
     def project_distance(self, c, counts):
         i1, i2, d = c["i1"], c["i2"], c["d"]
@@ -437,6 +461,15 @@ class Cpu2dFullOracle:
             for i in b["particles"]:
                 counts[i] += 1
         self.counts = counts
+        # the reference's compile-time option USE_STABILIZATION (simulation.h:17, off in its build): STABILIZATION_ITERATIONS passes
+        # over the stabile copies of the rigid contacts and wall constraints, in the CONTACT list's order, before the solver
+        # iterations (simulation.cpp:190-192,204-223,249-271); the counts do not include them (:236-238)
+        for _ in range(self.stabilization_iterations):
+            for c in contacts:
+                if c[0] == "boundary":
+                    self.project_boundary(c, counts, True)
+                elif c[0] == "rigid":
+                    self.project_rigid_contact(c, counts, True)
         for _ in range(SOLVER_ITERATIONS):
             for c in contacts:
                 if c[0] == "boundary":

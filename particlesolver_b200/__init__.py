@@ -53,7 +53,8 @@ class Params(C.Structure):
 
 class Params2D(C.Structure):
     """Ps2dParams (include/psolver2d.h): bounds, gravity and iteration count of the reference's CPU Simulation."""
-    _fields_ = [("x_bounds", C.c_double * 2), ("y_bounds", C.c_double * 2), ("gravity", C.c_double * 2), ("solver_iterations", C.c_uint32)]
+    _fields_ = [("x_bounds", C.c_double * 2), ("y_bounds", C.c_double * 2), ("gravity", C.c_double * 2), ("solver_iterations", C.c_uint32),
+                ("stabilization_iterations", C.c_uint32)]
 
 
 _lib = None
@@ -196,6 +197,7 @@ def lib():
         L.ps2d_last_num_levels.argtypes = [vp]
         L.ps2d_last_num_levels.restype = u32
         L.ps2d_seed_rand.argtypes = [vp, u32, u64]
+        L.ps2d_set_stabilization_iterations.argtypes = [vp, u32]
         L.ps2d_rand_calls.argtypes = [vp]
         L.ps2d_rand_calls.restype = u64
         L.ps2d_tick.argtypes = [vp, C.c_double]
@@ -581,11 +583,13 @@ class Simulation2D:
     DistanceConstraint / TotalFluidConstraint / GasConstraint / Body constructors."""
     SOLID, FLUID, GAS = 0, 1, 2
 
-    def __init__(self, x_bounds=(-8.0, 8.0), y_bounds=(-8.0, 40.0), gravity=(0.0, -9.8), iterations=3, max_particles=1 << 16, device=0):
+    def __init__(self, x_bounds=(-8.0, 8.0), y_bounds=(-8.0, 40.0), gravity=(0.0, -9.8), iterations=3, max_particles=1 << 16, device=0,
+                 stabilization_iterations=0):
         p = Params2D()
         lib().ps2d_default_params(C.byref(p))
         p.x_bounds[:], p.y_bounds[:], p.gravity[:] = tuple(x_bounds), tuple(y_bounds), tuple(gravity)
         p.solver_iterations = iterations
+        p.stabilization_iterations = stabilization_iterations   # 2 = the reference built with USE_STABILIZATION
         h = C.c_void_p()
         _check(lib().ps2d_create(device, C.byref(p), max_particles, C.byref(h)))
         self._h = h
@@ -748,13 +752,14 @@ class Simulation2D:
         return a
 
     @classmethod
-    def from_state(cls, scene, max_particles=None, device=0):
+    def from_state(cls, scene, max_particles=None, device=0, stabilization_iterations=0):
         """Builds a simulation from a full restart state: the dict layout written by the reference driver
         (oracle/ref_cpu_driver.cpp dump_scene; tests/golden/ref_cpu_scenes.npz) — particles [px, py, vx, vy, imass, phase,
         bod, sFriction, kFriction(, fx, fy(, t))], bodies, the STANDARD constraint list in order, smoke / fluid emitters, rand() position."""
         P = np.array(scene["particles"], np.float64).reshape(-1, len(scene["particles"][0]) if scene["particles"] else 9)
         n = P.shape[0]
-        sim = cls(scene["xbounds"], scene["ybounds"], scene["gravity"], max_particles=max_particles or max(1024, 2 * n), device=device)
+        sim = cls(scene["xbounds"], scene["ybounds"], scene["gravity"], max_particles=max_particles or max(1024, 2 * n), device=device,
+                  stabilization_iterations=stabilization_iterations)
         sim.addParticles(P[:, 0:2], P[:, 2:4], P[:, 4], P[:, 5].astype(np.int32), P[:, 6].astype(np.int32), P[:, 7], P[:, 8])
         for b in scene["bodies"]:
             idx = np.array(b["particles"])
@@ -780,6 +785,9 @@ class Simulation2D:
             sim.setParticleTimers(P[:, 11])
         sim.seedRand(1, int(scene["rand_calls"]))
         return sim
+
+    def setStabilizationIterations(self, iterations):
+        _check(lib().ps2d_set_stabilization_iterations(self._h, int(iterations)))
 
     def seedRand(self, seed=1, skip=0):
         _check(lib().ps2d_seed_rand(self._h, seed, skip))

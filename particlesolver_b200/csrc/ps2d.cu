@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kSerialBlock) k2d_contact_levels(const u32 *__
 
 struct Particles2D {  // device views used by the projection kernels
     double2 *ep;
-    const double2 *p;
+    double2 *p;  // written by the stabilization pass only
     const double *tmass, *sfric, *kfric;
     const int *phase, *bod;
     const u32 *counts;
@@ -253,8 +253,12 @@ __device__ void project_contact(const Particles2D &P, u32 i1, u32 i2) {
 }
 
 // RigidContactConstraint::project (rigidcontactconstraint.cpp:29-96), stabile == false
-__device__ void project_rigid_contact(const Particles2D &P, u32 i1, u32 i2) {
-    double2 e1 = P.ep[i1], e2 = P.ep[i2];
+// stabile: the STABILIZATION copy of the constraint (the reference's option USE_STABILIZATION; :15,35,61-67,81-95): geometry from
+// p (getP(true)) and the correction goes to p; friction reads ep - p and moves both
+__device__ void project_rigid_contact(const Particles2D &P, u32 i1, u32 i2, bool stabile) {
+    double2 q1 = P.ep[i1], q2 = P.ep[i2];          // ep
+    double2 p1 = P.p[i1], p2 = P.p[i2];
+    double2 e1 = stabile ? p1 : q1, e2 = stabile ? p2 : q2;   // getP(stabile)
     const double3 s1 = sdf_data(P, i1), s2 = sdf_data(P, i2);
     double d, nx, ny;
     if (s1.z < 0. || s2.z < 0.) {
@@ -284,11 +288,11 @@ __device__ void project_rigid_contact(const Particles2D &P, u32 i1, u32 i2) {
     const double c1 = (double)P.counts[i1], c2 = (double)P.counts[i2];
     e1.x += ((-t1) * dpx) / c1; e1.y += ((-t1) * dpy) / c1;
     e2.x += (t2 * dpx) / c2;    e2.y += (t2 * dpy) / c2;
+    if (stabile) { p1 = e1; p2 = e2; } else { q1 = e1; q2 = e2; }
     // friction (:68-95)
     const double inv = 1. / sqrt(nx * nx + ny * ny);
     const double nfx = nx * inv, nfy = ny * inv;
-    const double2 p1 = P.p[i1], p2 = P.p[i2];
-    const double fx = (e1.x - p1.x) - (e2.x - p2.x), fy = (e1.y - p1.y) - (e2.y - p2.y);
+    const double fx = (q1.x - p1.x) - (q2.x - p2.x), fy = (q1.y - p1.y) - (q2.y - p2.y);
     const double dn = fx * nfx + fy * nfy;
     double tx = fx - dn * nfx, ty = fy - dn * nfy;
     const double ldpt = sqrt(tx * tx + ty * ty);
@@ -298,14 +302,20 @@ __device__ void project_rigid_contact(const Particles2D &P, u32 i1, u32 i2) {
             const double m = fmin(kfric * d / ldpt, 1.);
             tx = tx * m; ty = ty * m;
         }
-        e1.x -= (tx * t1) / wsum; e1.y -= (ty * t1) / wsum;
-        e2.x += (tx * t2) / wsum; e2.y += (ty * t2) / wsum;
+        if (stabile) {
+            p1.x -= (tx * t1) / wsum; p1.y -= (ty * t1) / wsum;
+            p2.x += (tx * t2) / wsum; p2.y += (ty * t2) / wsum;
+        }
+        q1.x -= (tx * t1) / wsum; q1.y -= (ty * t1) / wsum;
+        q2.x += (tx * t2) / wsum; q2.y += (ty * t2) / wsum;
     }
-    P.ep[i1] = e1; P.ep[i2] = e2;
+    P.ep[i1] = q1; P.ep[i2] = q2;
+    if (stabile) { P.p[i1] = p1; P.p[i2] = p2; }
 }
 
-// BoundaryConstraint::project (boundaryconstraint.cpp:14-93), stabile == false.  raw < 0: no jitter draw (solids)
-__device__ void project_boundary(const Particles2D &P, u32 i, double value, bool is_x, bool greater, int raw) {
+// BoundaryConstraint::project (boundaryconstraint.cpp:14-93).  raw < 0: no jitter draw (solids).  stabile: the STABILIZATION copy
+// (:32-35,74-76): p follows ep, no friction; the validity test reads ep either way
+__device__ void project_boundary(const Particles2D &P, u32 i, double value, bool is_x, bool greater, int raw, bool stabile) {
     double2 e = P.ep[i];
     const double extra = raw >= 0 ? (double)(float)((double)raw / 2147483647.0) * .003 : 0.;  // frand() is float-typed, includes.h:25
     const double d = kRad + extra;
@@ -316,6 +326,13 @@ __device__ void project_boundary(const Particles2D &P, u32 i, double value, bool
     } else {
         if (is_x) { if (e.x <= value - kRad) return; e.x = value - d; nx = -1.; ny = 0.; }
         else { if (e.y <= value - kRad) return; e.y = value - d; nx = 0.; ny = -1.; }
+    }
+    if (stabile) {
+        double2 q = P.p[i];
+        if (is_x) q.x = e.x; else q.y = e.y;
+        P.p[i] = q;
+        P.ep[i] = e;
+        return;
     }
     // friction: walls have a coefficient of friction of 1 (:72-92)
     const double2 p = P.p[i];
@@ -340,7 +357,9 @@ __device__ void project_boundary(const Particles2D &P, u32 i, double value, bool
 __global__ void __launch_bounds__(kSerialBlock) k2d_contact_project(Particles2D P, const u32 *__restrict__ nb, const u32 *__restrict__ cnt,
                                                                     const u32 *__restrict__ flags, const u32 *__restrict__ lvl, const u32 *__restrict__ rank,
                                                                     const u32 *__restrict__ info, u32 *__restrict__ cur, u32 n, const int *__restrict__ raw,
-                                                                    u32 window_base, u32 iteration, double x0, double x1, double y0, double y1) {
+                                                                    u32 window_base, u32 iteration, double x0, double x1, double y0, double y1, bool stabile) {
+    // stabile: one pass over the STABILIZATION list = the rigid contacts and wall constraints of the CONTACT list, in its order
+    // (simulation.cpp:190-192,204-223), so the same level schedule holds with the plain contacts stepped over.
     // info[-1] = jittered wall constraints of this tick (k2d_scan_counts): iteration t draws window[base + t * num + position]
     const u32 levels = info[0], draw_base = window_base + iteration * info[-1];
     for (u32 i = threadIdx.x; i < n; i += kSerialBlock) cur[i] = 0;
@@ -353,16 +372,16 @@ __global__ void __launch_bounds__(kSerialBlock) k2d_contact_project(Particles2D 
             if (r < c) {
                 const u32 w = nb[(size_t)i * kMaxC + r], j = w & ~kRigidBit;
                 if (i < j) {
-                    if (w & kRigidBit) project_rigid_contact(P, i, j);
-                    else project_contact(P, i, j);
+                    if (w & kRigidBit) project_rigid_contact(P, i, j, stabile);
+                    else if (!stabile) project_contact(P, i, j);
                 }
             } else {
                 const bool second = r > c, is_x = !second && (fl & 3u);
                 const int ph = P.phase[i];
                 int draw = -1;
                 if (ph == PS2D_PHASE_FLUID || ph == PS2D_PHASE_GAS) draw = raw[draw_base + rank[i] + (second ? 1u : 0u)];
-                if (is_x) project_boundary(P, i, (fl & 1u) ? x0 : x1, true, (fl & 1u) != 0, draw);
-                else project_boundary(P, i, (fl & 4u) ? y0 : y1, false, (fl & 4u) != 0, draw);
+                if (is_x) project_boundary(P, i, (fl & 1u) ? x0 : x1, true, (fl & 1u) != 0, draw, stabile);
+                else project_boundary(P, i, (fl & 4u) ? y0 : y1, false, (fl & 4u) != 0, draw, stabile);
             }
         }
     }
@@ -679,10 +698,12 @@ struct Ps2dCtx {
 
 extern "C" void ps2d_default_params(Ps2dParams *p) {
     if (!p) return;
+    memset(p, 0, sizeof(*p));
     p->x_bounds[0] = -8.; p->x_bounds[1] = 8.;    // scene 6, cpu/src/simulation.cpp:898-899
     p->y_bounds[0] = -8.; p->y_bounds[1] = 40.;
     p->gravity[0] = 0.; p->gravity[1] = -9.8;
     p->solver_iterations = 3;                     // simulation.h:11
+    p->stabilization_iterations = 0;              // USE_STABILIZATION is commented out in the reference's build (simulation.h:17)
 }
 
 template <class T>
@@ -691,7 +712,7 @@ static bool dev_alloc(T **ptr, size_t count) { return cudaMalloc((void **)ptr, s
 extern "C" int ps2d_create(int device, const Ps2dParams *params, uint64_t max_particles, Ps2dCtx **out) {
     if (!params || !out || !max_particles) { ps_set_error("ps2d_create: bad argument"); return PS_ERR_INVALID; }
     *out = nullptr;
-    if (!(params->x_bounds[0] < params->x_bounds[1]) || !(params->y_bounds[0] < params->y_bounds[1]) || params->solver_iterations > 64) {
+    if (!(params->x_bounds[0] < params->x_bounds[1]) || !(params->y_bounds[0] < params->y_bounds[1]) || params->solver_iterations > 64 || params->stabilization_iterations > 64) {
         ps_set_error("ps2d_create: bad bounds or iteration count"); return PS_ERR_INVALID;
     }
     if (max_particles > (1u << 28)) { ps_set_error("ps2d_create: max_particles too large"); return PS_ERR_INVALID; }
@@ -985,6 +1006,13 @@ extern "C" int ps2d_body_state(Ps2dCtx *c, uint32_t body, double *center2, doubl
 }
 extern "C" uint32_t ps2d_num_bodies(Ps2dCtx *c) { return c ? c->nbodies : 0; }
 
+// Ps2dParams.stabilization_iterations of an existing context (the scene builders create theirs with the default, 0)
+extern "C" int ps2d_set_stabilization_iterations(Ps2dCtx *c, uint32_t iterations) {
+    if (!c || iterations > 64) { ps_set_error("ps2d_set_stabilization_iterations: bad argument"); return PS_ERR_INVALID; }
+    c->params.stabilization_iterations = iterations;
+    return PS_OK;
+}
+
 extern "C" int ps2d_seed_rand(Ps2dCtx *c, uint32_t seed, uint64_t skip) {
     if (!c) return PS_ERR_INVALID;
     c->rng.seed(seed);
@@ -1169,7 +1197,8 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     // the number of jittered wall constraints decides how many draws of the rand() stream this tick consumes — one per
     // constraint per solver iteration, in list order; at most 2 n per iteration.  The kernels take them from the look-ahead
     // window, which is refilled (from a copy of the generator) when it no longer covers a worst-case tick.
-    const uint64_t worst = (uint64_t)2 * n * P.solver_iterations;
+    const u32 passes = P.stabilization_iterations + P.solver_iterations;  // every pass over the wall constraints draws (the stabile copies too)
+    const uint64_t worst = (uint64_t)2 * n * passes;
     if (c->any_jitter && (c->rng.calls < c->win_pos || c->rng.calls + worst > c->win_pos + c->win_len)) {
         const size_t want = std::max<size_t>(worst * 16, 1u << 16);
         GlibcRand ahead = c->rng;
@@ -1189,9 +1218,15 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     }
     const u32 window_base = (u32)(c->rng.calls - c->win_pos);
     Particles2D V{c->ep, c->p, c->tmass, c->sfric, c->kfric, c->phase, c->bod, c->counts, c->sdf_grad, c->sdf_dist, c->b_angle};
+    // stabilization passes (the reference's compile-time option USE_STABILIZATION, simulation.cpp:249-271): before the solver iterations
+    for (u32 st = 0; st < P.stabilization_iterations; st++) {
+        k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, window_base, st, x0, x1, y0, y1, true);
+        launches++;
+    }
     for (u32 it = 0; it < P.solver_iterations; it++) {
         // CONTACT group (the kernel returns at once when the list is empty)
-        k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, window_base, it, x0, x1, y0, y1);
+        k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, window_base,
+                                                       P.stabilization_iterations + it, x0, x1, y0, y1, false);
         launches++;
         size_t run = 0;  // STANDARD group, in list order
         for (size_t k = 0; k < c->standard.size();) {
@@ -1237,7 +1272,7 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
         cudaMemsetAsync(c->scalars + 3, 0, 4, s);
         return PS_ERR_CAPACITY;
     }
-    for (size_t k = 0, nd = (size_t)num * P.solver_iterations; k < nd; k++) c->rng.next();  // the stream moves on by what was drawn
+    for (size_t k = 0, nd = (size_t)num * passes; k < nd; k++) c->rng.next();  // the stream moves on by what was drawn
     // OpenSmokeEmitter::tick (opensmokeemitter.cpp:17-29): particle injection into the gas constraint
     for (Emitter &em : c->emitters) {
         em.timer += dt;
@@ -1339,7 +1374,7 @@ extern "C" int ps2d_save(Ps2dCtx *c, const char *path) {
     CU2(fetch(ban, c->b_angle, nb)); CU2(fetch(bce, c->b_center, 2 * nb));
     Header2d h{};
     memcpy(h.magic, kMagic2d, 8);
-    h.version = 2; h.params_bytes = (uint32_t)sizeof(Ps2dParams);
+    h.version = 3; h.params_bytes = (uint32_t)sizeof(Ps2dParams);  // 3: Ps2dParams.stabilization_iterations lives in what was padding
     h.n = n; h.cap = c->cap; h.num_bodies = nb; h.num_standard = c->standard.size(); h.num_emitters = c->emitters.size();
     h.num_fluid_emitters = c->fluid_emitters.size(); h.rand_calls = c->rng.calls;
     std::vector<FluidEmitRecord> fem;
@@ -1371,7 +1406,7 @@ extern "C" int ps2d_load(const char *path, int device, Ps2dCtx **out) {
     struct Closer { FILE *f; ~Closer() { fclose(f); } } closer{fp};
     Header2d h{};
     if (!get2(fp, &h, 1) || memcmp(h.magic, kMagic2d, 8) != 0) { ps_set_error("ps2d_load: %s is not a 2-D libpsolver checkpoint", path); return PS_ERR_INVALID; }
-    if (h.version != 2 || h.params_bytes != sizeof(Ps2dParams)) { ps_set_error("ps2d_load: checkpoint version %u not understood", h.version); return PS_ERR_INVALID; }
+    if ((h.version != 2 && h.version != 3) || h.params_bytes != sizeof(Ps2dParams)) { ps_set_error("ps2d_load: checkpoint version %u not understood", h.version); return PS_ERR_INVALID; }
     if (h.n > h.cap || h.cap > (1u << 28) || h.num_bodies > h.n || h.num_standard > (1u << 28) || h.num_emitters > 4096 || h.num_fluid_emitters > 4096) { ps_set_error("ps2d_load: implausible sizes in %s", path); return PS_ERR_INVALID; }
     Ps2dParams P;
     uint32_t rng[31];
@@ -1383,7 +1418,7 @@ extern "C" int ps2d_load(const char *path, int device, Ps2dCtx **out) {
     std::vector<EmitRecord> em(h.num_emitters);
     std::vector<FluidEmitRecord> fem(h.num_fluid_emitters);
     std::vector<double> ht(n), lk(h.num_fluid_emitters ? n : 0);
-    bool ok = get2(fp, &P, 1) && get2(fp, rng, 31) && get2(fp, p.data(), p.size()) && get2(fp, v.data(), v.size()) && get2(fp, f.data(), f.size()) &&
+    bool ok = get2(fp, &P, 1) && (h.version >= 3 || (P.stabilization_iterations = 0, true)) /* version 2: padding */ && get2(fp, rng, 31) && get2(fp, p.data(), p.size()) && get2(fp, v.data(), v.size()) && get2(fp, f.data(), f.size()) &&
               get2(fp, rs.data(), rs.size()) && get2(fp, sg.data(), sg.size()) && get2(fp, im.data(), n) && get2(fp, sf.data(), n) && get2(fp, kf.data(), n) &&
               get2(fp, sd.data(), n) && get2(fp, ph.data(), n) && get2(fp, bod.data(), n) && get2(fp, grp.data(), n) && get2(fp, sc.data(), n) &&
               get2(fp, bf.data(), nb) && get2(fp, bc.data(), nb) && get2(fp, bim.data(), nb) && get2(fp, bst.data(), nb) && get2(fp, ban.data(), nb) &&

@@ -3,7 +3,7 @@
 // cpu/src/view.cpp:129-177); this runs the same scenes without a display, over libpsolver.so's public C / C++ API only:
 //   psolver_cli --app gpu --scene 7 --steps 600 [--dt 0.016667] [--grid 64] [--max-particles 15000] [--side 100]
 //               [--iterations 5] [--xsph 0.01 --vorticity 0.3] [--self-collision] [--gas]
-//   psolver_cli --app cpu --scene 6 --steps 1000 [--dt 0.01]
+//   psolver_cli --app cpu --scene 6 --steps 1000 [--dt 0.01] [--stabilization 2]
 //   psolver_cli --app session --script "6:100,1:50,w:20"     the CPU app as a user drives it: psb200::Simulation (constructor
 //               builds WRECKING_BALL), then key presses and ticks; the rand() stream runs on across scenes like the reference's
 // common: [--load FILE] [--save FILE] [--dump-every K --out DIR] [--json] [--device D]
@@ -32,6 +32,7 @@ struct Args {
     float xsph = 0.f, vorticity = 0.f;
     bool json = false;
     unsigned flags = 0;  // PS_FLAG_* switched on from the command line
+    int stabilization = -1;  // --app cpu: stabilization passes per tick (the reference's USE_STABILIZATION build: 2); -1 = leave as is
 };
 [[noreturn]] void die(const std::string &m) { fprintf(stderr, "psolver_cli: %s\n", m.c_str()); exit(1); }
 void check(int r, const char *what) { if (r != PS_OK) die(std::string(what) + ": " + ps_last_error()); }
@@ -113,6 +114,7 @@ int run_cpu_app(const Args &a) {
     Ps2dCtx *ctx = nullptr;
     if (!a.load.empty()) check(ps2d_load(a.load.c_str(), a.device, &ctx), "ps2d_load");
     else check(ps2d_build_scene(a.scene.c_str(), a.device, 0, &ctx), "ps2d_build_scene");
+    if (a.stabilization >= 0) check(ps2d_set_stabilization_iterations(ctx, (uint32_t)a.stabilization), "ps2d_set_stabilization_iterations");
     const double dt = a.dt > 0 ? a.dt : .01;  // cpu/src/view.cpp:197
     std::vector<double> p;
     const auto t0 = std::chrono::steady_clock::now();
@@ -200,6 +202,7 @@ int main(int argc, char **argv) {
         else if (k == "--vorticity") a.vorticity = (float)atof(val());
         else if (k == "--self-collision") a.flags |= PS_FLAG_SELF_COLLISION;
         else if (k == "--gas") a.flags |= PS_FLAG_GAS;
+        else if (k == "--stabilization") a.stabilization = atoi(val());
         else if (k == "--device") a.device = atoi(val());
         else if (k == "--json") a.json = true;
         else if (k == "--help" || k == "-h") { printf("see the header of particlesolver_b200/csrc/psolver_cli.cpp\n"); return 0; }

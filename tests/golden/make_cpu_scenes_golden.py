@@ -10,6 +10,7 @@ freshly built scene where T0 > 0; NAME_key = the app's key for the scene."""
 import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -46,11 +47,19 @@ def read_tick(raw_dir, t):
     return rec, meta
 
 
+# --stab: the same for the reference compiled with its option USE_STABILIZATION (oracle/_ref/ref_cpu_stab; simulation.h:17,
+# simulation.cpp:249-271), scenes with rigid contacts and / or walls -> tests/golden/ref_cpu_scenes_stab.npz
+STAB_SCENES = ["stacks", "wall", "fluid_solid", "friction", "sdf", "wrecking_ball"]
+
+
 def main():
+    stab = "--stab" in sys.argv
     keep = {}
     for name, (key, t0, ticks) in SCENES.items():
-        raw_dir = f"/tmp/ref_cpu_scene_{name}"
-        cmd = [os.path.join(ROOT, "oracle", "_ref", "ref_cpu"), "--scene", key, "--ticks", str(max(ticks)), "--dump", raw_dir, "--dump-every", "1"]
+        if stab and name not in STAB_SCENES:
+            continue
+        raw_dir = f"/tmp/ref_cpu_scene_{name}" + ("_stab" if stab else "")
+        cmd = [os.path.join(ROOT, "oracle", "_ref", "ref_cpu_stab" if stab else "ref_cpu"), "--scene", key, "--ticks", str(max(ticks)), "--dump", raw_dir, "--dump-every", "1"]
         if t0:
             cmd += ["--scene-at", str(t0)]
         subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
@@ -68,7 +77,7 @@ def main():
             keep[f"{name}_rand{t}"] = np.array(int(m["rand_calls"][0]))
             keep[f"{name}_ke{t}"] = np.array(m["ke"][0])
         print(name, "n", json.loads(text)["n"], "->", keep[f"{name}_p{ticks[-1]}"].shape[0])
-    out = os.path.join(ROOT, "tests", "golden", "ref_cpu_scenes.npz")
+    out = os.path.join(ROOT, "tests", "golden", "ref_cpu_scenes_stab.npz" if stab else "ref_cpu_scenes.npz")
     np.savez_compressed(out, **keep)
     print(out, os.path.getsize(out), "bytes")
 

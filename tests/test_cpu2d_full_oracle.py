@@ -42,3 +42,32 @@ def test_full_oracle_reproduces_reference_cpu_solver(name):
         assert abs(o.kinetic_energy() - float(G[f"{name}_ke{t}"])) <= 1e-12 * max(1., abs(float(G[f"{name}_ke{t}"])))
     if name in ("granular", "stacks", "wall", "friction", "sdf", "wrecking_ball", "fluid_solid", "balloon", "rope"):
         assert saw_contacts > 0, f"{name}: the replayed ticks exercise no contact constraint"
+
+
+# ---- the stabilization pass: the reference compiled with its option USE_STABILIZATION (oracle/_ref/ref_cpu_stab) ----
+GS = np.load(os.path.join(ROOT, "tests", "golden", "ref_cpu_scenes_stab.npz"))
+STAB_SCENES = sorted(k[:-6] for k in GS.files if k.endswith("_scene"))
+
+
+def test_stabilization_fixture_differs_from_the_default_build():
+    assert STAB_SCENES == ["fluid_solid", "friction", "sdf", "stacks", "wall", "wrecking_ball"]
+    for name in STAB_SCENES:
+        t = int(GS[f"{name}_ticks"][-1])
+        assert np.abs(GS[f"{name}_p{t}"] - G[f"{name}_p{t}"]).max() > 1e-3      # a different trajectory ...
+    assert int(GS["fluid_solid_rand20"]) > int(G["fluid_solid_rand20"])           # ... and more jitter draws (stabile wall constraints draw too)
+
+
+@pytest.mark.parametrize("name", STAB_SCENES)
+def test_full_oracle_reproduces_reference_cpu_solver_with_stabilization(name):
+    scene = json.loads(str(GS[f"{name}_scene"]))
+    o = full.Cpu2dFullOracle(scene, stabilization_iterations=2)
+    t = int(GS[f"{name}_t0"])
+    ticks = [int(x) for x in GS[f"{name}_ticks"]][: BUDGET.get(name, 5)]
+    for target in ticks:
+        while t < target:
+            o.tick(.01)
+            t += 1
+        p, v = GS[f"{name}_p{t}"], GS[f"{name}_v{t}"]
+        dp, dv = np.abs(o.positions() - p).max(), np.abs(o.velocities() - v).max()
+        assert dp <= 1e-12 and dv <= 1e-10, f"{name} tick {t}: |dp| {dp:.3e} |dv| {dv:.3e}"
+        assert o.rng.calls == int(GS[f"{name}_rand{t}"]), f"{name} tick {t}: rand() draws differ"

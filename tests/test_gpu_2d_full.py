@@ -163,3 +163,50 @@ def test_mouse_pressed_impulse_matches_the_oracle():
         o.tick(.01)
     assert np.abs(sim.positions() - o.positions()).max() <= 1e-12
     sim.close()
+
+
+# ---- the stabilization pass (Ps2dParams.stabilization_iterations): the reference compiled with its option USE_STABILIZATION
+# (oracle/_ref/ref_cpu_stab, simulation.h:17, simulation.cpp:249-271) — tests/golden/ref_cpu_scenes_stab.npz ----
+GS = np.load(os.path.join(ROOT, "tests", "golden", "ref_cpu_scenes_stab.npz"))
+STAB_SCENES = sorted(k[:-6] for k in GS.files if k.endswith("_scene"))
+
+
+@pytest.mark.parametrize("name", STAB_SCENES)
+def test_scene_matches_reference_cpu_solver_built_with_stabilization(name, tmp_path):
+    scene = json.loads(str(GS[f"{name}_scene"]))
+    sim = psb.Simulation2D.from_state(scene, stabilization_iterations=2)
+    t = int(GS[f"{name}_t0"])
+    ticks = [int(x) for x in GS[f"{name}_ticks"]]
+    for k, target in enumerate(ticks):
+        while t < target:
+            sim.tick(.01)
+            t += 1
+        p, v = GS[f"{name}_p{t}"], GS[f"{name}_v{t}"]
+        dp, dv = np.abs(sim.positions() - p).max(), np.abs(sim.velocities() - v).max()
+        tol = 1e-12 if k < 3 else 1e-9
+        assert dp <= tol and dv <= tol * 100, f"{name} tick {t}: |dp| {dp:.3e} |dv| {dv:.3e}"
+        assert sim.rand_calls == int(GS[f"{name}_rand{t}"]), f"{name} tick {t}: wall-jitter draws differ from the reference"
+        if k == 1:   # a checkpoint carries the option: the continuation below runs on the reloaded twin
+            path = os.path.join(tmp_path, "stab.ckpt")
+            sim.save(path)
+            sim.close()
+            sim = psb.Simulation2D.load(path)
+    # and it is a different trajectory from the default build's
+    assert np.abs(sim.positions() - G[f"{name}_p{t}"]).max() > 1e-3
+    sim.close()
+
+
+def test_stabilization_can_be_switched_on_an_existing_context():
+    """ps2d_set_stabilization_iterations on a context built by the scene builders == a context created with the option"""
+    name = "stacks"
+    scene = json.loads(str(GS[f"{name}_scene"]))
+    a = psb.Simulation2D.from_state(scene, stabilization_iterations=2)
+    b = psb.Simulation2D.from_state(scene)
+    b.setStabilizationIterations(2)
+    for _ in range(3):
+        a.tick(.01); b.tick(.01)
+    assert np.array_equal(a.positions(), b.positions())
+    b.setStabilizationIterations(0)
+    a.tick(.01); b.tick(.01)
+    assert not np.array_equal(a.positions(), b.positions())
+    a.close(); b.close()
