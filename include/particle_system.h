@@ -64,6 +64,9 @@ public:
     int3 getMaxBounds() { return m_maxBounds; }
 
     /* ---- headless additions ---- */
+    /* not in the reference (its GPU solver has no rigid bodies): a lattice box that is one shape-matched body with its own phase,
+     * with the box's SDF data when `sdf` (contacts between such boxes then follow their surfaces); returns the body index or -1 */
+    int addRigidBox(int3 ll, int3 ur, float mass, bool sdf = true, float stiffness = 1.f);
     PsCtx *context() const { return m_ctx; }
     bool ok() const { return m_ctx != nullptr && m_error.empty(); }
     const std::string &lastError() const { return m_error; }
@@ -95,6 +98,18 @@ private:
     int3 m_maxBounds;
     uint m_solverIterations;
 };
+
+/* Extension scene "r" (psolver_cli --app gpu --scene r; not one of the reference's): rigid boxes with SDF contacts — a tower of
+ * three 5x5x5 boxes dropped onto each other, a fourth box beside it, a loose pile of solid particles beside. */
+inline ParticleSystem *build_rigid_scene(int grid, uint maxParticles, int iterations) {
+    ParticleSystem *ps = new ParticleSystem(0.25f, make_uint3(grid, grid, grid), maxParticles, make_int3(-50, 0, -50), make_int3(50, 200, 50), iterations);
+    ps->addRigidBox(make_int3(0, 1, 0), make_int3(3, 4, 3), 1.f);   /* 5 x 5 x 5 particles each: two layers deep */
+    ps->addRigidBox(make_int3(0, 5, 0), make_int3(3, 8, 3), 1.f);
+    ps->addRigidBox(make_int3(0, 9, 0), make_int3(3, 12, 3), 1.f);
+    ps->addRigidBox(make_int3(-6, 3, 0), make_int3(-3, 6, 3), 1.f);  /* a fourth box beside the tower */
+    ps->addParticleGrid(make_int3(8, 0, 0), make_int3(10, 3, 2), 1.f, false);
+    return ps;
+}
 
 }  // namespace psb200
 #endif

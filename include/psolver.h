@@ -229,7 +229,9 @@ int ps_rigid_body_rotation(PsCtx *ctx, uint32_t body, float *quat_xyzw); /* rota
  * (SDFData, cpu/src/solver/particle.h:82-93; the CPU app's boxes: depth = radius on faces, radius * sqrt(2) at corners).  depth < 0:
  * no data for that member.  A contact of two particles that BOTH carry SDF data takes normal and depth from the shallower one
  * (ties: the lower particle index); for particles of the outermost layers (depth < diameter + EPS) the depth is the particles'
- * overlap and the normal is x_ij mirrored at the SDF normal (Macklin et al. 2014 eq. 13-14); friction uses that normal and depth.
+ * overlap and the normal is the direction to the partner, mirrored at the SDF normal when the partner lies behind the surface
+ * (Macklin et al. 2014 eq. 13-14; the reference's 2-D code measures that direction the other way round, which in 3-D makes resting
+ * edge contacts push sideways — see sdf_contact in csrc/ps_neighbor_kernels.cu); friction acts about that normal.
  * All other contacts are unchanged.  Parity unpinned in 3-D. */
 int ps_set_rigid_body_sdf(PsCtx *ctx, uint32_t body, const float *sdf4);
 /* XSPH viscosity (v_i += c sum_j (v_j - v_i) W_ij) and vorticity confinement (Macklin & Mueller 2013, eqs. 15-17) as a

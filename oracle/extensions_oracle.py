@@ -83,7 +83,8 @@ def sdf_pair(si, sj, i_first, r, dist, diam):
         d = diam - dist
         if d < EPS:
             return None
-        x = r / dist if dist > EPS else np.array([0.0, 1.0, 0.0])
+        # direction from i to j; the reference's 2-D code takes p1 - p2 (the opposite one), see sdf_contact in ps_neighbor_kernels.cu
+        x = -r / dist if dist > EPS else np.array([0.0, 1.0 if i_first else -1.0, 0.0])
         dp = float(x @ e)
         e = x - 2.0 * dp * e if dp < 0 else x
     return d, e
@@ -122,8 +123,8 @@ def contact_pass(pos, prev, w, phase, radius, sdf_world=None, same_body_skip=Non
                 c = sdf_pair(sdf_world[i], sdf_world[j], i < j, r, dist, 2 * radius)
                 if c is None:
                     continue
-                fd, fn = c
-                dp = fn * (fd / wsum)
+                depth, fn = c
+                dp = fn * (depth / wsum)
             dp1, dp2 = -cw * dp / len(nb), cw2 * dp / len(nb)
             delta += dp1
             if not both:

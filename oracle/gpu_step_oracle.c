@@ -160,8 +160,9 @@ static int sdf_contact(const float *si, const float *sj, int i_first, const floa
     if (*d < diam + EPS) {               /* initBoundary (:13-27) */
         *d = diam - dist;
         if (*d < EPS) return 0;
-        float x[3] = {0.f, 1.f, 0.f};
-        if (dist > EPS) { x[0] = r[0] / dist; x[1] = r[1] / dist; x[2] = r[2] / dist; }
+        /* direction from i to j (the reference's 2-D code takes p1 - p2, the opposite one: see sdf_contact in ps_neighbor_kernels.cu) */
+        float x[3] = {0.f, i_first ? 1.f : -1.f, 0.f};
+        if (dist > EPS) { x[0] = -r[0] / dist; x[1] = -r[1] / dist; x[2] = -r[2] / dist; }
         float dp = x[0] * e[0] + x[1] * e[1] + x[2] * e[2];
         if (dp < 0.f) { for (int c = 0; c < 3; c++) e[c] = x[c] - 2.f * dp * e[c]; }
         else { for (int c = 0; c < 3; c++) e[c] = x[c]; }
@@ -233,7 +234,6 @@ void or_collide_ext(float *pos, const float *prev, const float *spos, const floa
                         if (!sdf_contact(si, sj, orig < index[j], d, dist, 2.f * p->radius, &depth, e)) continue;
                         float s_ = depth / (colW + colW2);
                         for (int c = 0; c < 3; c++) { dp[c] = e[c] * s_; fnv[c] = e[c]; }
-                        fd = depth;
                     }
                 }
                 float dp1[3], dp2[3];

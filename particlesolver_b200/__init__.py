@@ -138,6 +138,8 @@ def lib():
         L.pshost_update.restype = None
         L.pshost_add_fluid.argtypes = [vp, vp, vp, f32, f32]
         L.pshost_add_particle_grid.argtypes = [vp, vp, vp, f32, i32]
+        L.pshost_add_rigid_box.argtypes = [vp, vp, vp, f32, i32, f32]
+        L.pshost_add_rigid_box.restype = i32
         L.pshost_add_horiz_cloth.argtypes = [vp, vp, vp, vp, vp, f32, i32]
         L.pshost_add_rope.argtypes = [vp, vp, vp, f32, i32, f32, i32]
         L.pshost_add_static_sphere.argtypes = [vp, vp, vp, f32]
@@ -548,6 +550,12 @@ class ParticleSystem:
 
     def addRope(self, start, spacing, dist, numLinks, mass, constrainStart):
         lib().pshost_add_rope(self._h, (C.c_float * 3)(*start), (C.c_float * 3)(*spacing), dist, numLinks, mass, int(constrainStart)); self._raise()
+
+    def addRigidBox(self, ll, ur, mass, sdf=True, stiffness=1.0):
+        """not in the reference: a lattice box as one shape-matched body with the box's SDF data; returns the body index"""
+        b = lib().pshost_add_rigid_box(self._h, (C.c_int * 3)(*ll), (C.c_int * 3)(*ur), mass, int(bool(sdf)), stiffness)
+        self._raise()
+        return int(b)
 
     def addStaticSphere(self, ll, ur, spacing):
         lib().pshost_add_static_sphere(self._h, (C.c_int * 3)(*ll), (C.c_int * 3)(*ur), spacing); self._raise()

@@ -158,6 +158,54 @@ void ParticleSystem::addParticleGrid(int3 ll, int3 ur, float mass, bool addJitte
     m_colors.push_back(make_float4(c.x, c.y, c.z, 1.f));
 }
 
+// Headless addition, not in the reference (its GPU solver has no rigid bodies: rigid_body_functor is an empty stub,
+// solver_kernel.cuh:289-312): a lattice box like addParticleGrid whose particles form ONE shape-matched body (ps_add_rigid_body)
+// with its own phase RIGID + k, and, when `sdf`, the box's signed-distance data the way the reference CPU app's builders write
+// it down (cpu/src/simulation.cpp:666-672): outward normal of the nearest face (normalised sum on edges and corners) and depth
+// (layer + 1/2) * diameter * sqrt(number of nearest faces), so that boxes meet each other through SDF contacts.
+int ParticleSystem::addRigidBox(int3 ll, int3 ur, float mass, bool sdf, float stiffness) {
+    const int start = m_numParticles;
+    const float distance = m_particleRadius * 2.002f;
+    const int3 count = make_int3(lattice_count(ll.x, ur.x, distance), lattice_count(ll.y, ur.y, distance), lattice_count(ll.z, ur.z, distance));
+    const size_t n = (size_t)std::max(count.x, 0) * std::max(count.y, 0) * std::max(count.z, 0);
+    if (n < 2) { m_error = "addRigidBox: a rigid body needs at least 2 particles"; return -1; }
+    std::vector<float> pos(n * 4), vel(n * 4, 0.f), w(n, 1.f / mass), ro(n, 1.f);
+    std::vector<int> phase(n, PS_PHASE_RIGID + m_rigidIndex);
+    fill_lattice(pos, ll, count, distance, 0.f);
+    addParticleMultiple(pos.data(), vel.data(), w.data(), ro.data(), phase.data(), (int)n);
+    if ((size_t)(m_numParticles - start) != n) { m_error = "addRigidBox: no room for the box"; return -1; }
+    m_rigidIndex++;
+    m_colorIndex.push_back(make_int2(start, m_numParticles));
+    const float3 c = colors[rand() % numColors];
+    m_colors.push_back(make_float4(c.x, c.y, c.z, 1.f));
+    std::vector<uint> idx(n);
+    for (size_t k = 0; k < n; k++) idx[k] = (uint)(start + k);
+    uint32_t body = 0;
+    if (ps_add_rigid_body(m_ctx, idx.data(), n, stiffness, &body) != PS_OK) { m_error = ps_last_error(); return -1; }
+    if (sdf) {
+        std::vector<float> data(n * 4);
+        size_t k = 0;
+        for (int z = 0; z < count.z; z++)
+            for (int y = 0; y < count.y; y++)
+                for (int x = 0; x < count.x; x++, k++) {  // fill_lattice's order
+                    const int depth[6] = {x, count.x - 1 - x, y, count.y - 1 - y, z, count.z - 1 - z};
+                    const float nrm[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+                    int lo = depth[0];
+                    for (int f = 1; f < 6; f++) lo = std::min(lo, depth[f]);
+                    float g[3] = {0, 0, 0};
+                    int faces = 0;
+                    for (int f = 0; f < 6; f++)
+                        if (depth[f] == lo) { g[0] += nrm[f][0]; g[1] += nrm[f][1]; g[2] += nrm[f][2]; faces++; }
+                    float len = std::sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+                    if (len < 1e-6f) { g[0] = 0.f; g[1] = 1.f; g[2] = 0.f; len = 1.f; faces = 1; }  // opposite faces equally near
+                    data[4 * k] = g[0] / len; data[4 * k + 1] = g[1] / len; data[4 * k + 2] = g[2] / len;
+                    data[4 * k + 3] = (lo + 0.5f) * 2.f * m_particleRadius * std::sqrt((float)faces);
+                }
+        if (ps_set_rigid_body_sdf(m_ctx, body, data.data()) != PS_OK) { m_error = ps_last_error(); return -1; }
+    }
+    return (int)body;
+}
+
 // horizontal cloth in the xz plane at height spacing.y: one distance constraint to the -x neighbour and one to
 // the -z neighbour per particle, pins on the x == 0 column (all four edges when holdEdges) (reference :461-568)
 void ParticleSystem::addHorizCloth(int2 ll, int2 ur, float3 spacing, float2 dist, float mass, bool holdEdges) {
@@ -281,6 +329,7 @@ void *pshost_create(float radius, unsigned gx, unsigned gy, unsigned gz, unsigne
 // reference never seeds: seed 1 reproduces a fresh process).
 void *pshost_build_scene(const char *scene, int grid, unsigned maxParticles, int iterations, int side, int seed) {
     if (seed >= 0) srand((unsigned)seed);
+    if (std::string(scene) == "r") return psb200::build_rigid_scene(grid, maxParticles, iterations);
     ps_scenes::SceneSpec s;
     s.scene = scene; s.grid = grid; s.max_particles = maxParticles; s.iterations = iterations; s.side = side;
     return ps_scenes::build<ParticleSystem>(s, psb200::colors, psb200::numColors);
@@ -303,6 +352,9 @@ void pshost_add_horiz_cloth(void *h, const int *ll, const int *ur, const float *
 void pshost_add_rope(void *h, const float *start, const float *spacing, float dist, int numLinks, float mass, int constrainStart) {
     ((ParticleSystem *)h)->addRope(make_float3(start[0], start[1], start[2]), make_float3(spacing[0], spacing[1], spacing[2]), dist, numLinks, mass,
                                    constrainStart != 0);
+}
+int pshost_add_rigid_box(void *h, const int *ll, const int *ur, float mass, int sdf, float stiffness) {
+    return ((ParticleSystem *)h)->addRigidBox(make_int3(ll[0], ll[1], ll[2]), make_int3(ur[0], ur[1], ur[2]), mass, sdf != 0, stiffness);
 }
 void pshost_add_static_sphere(void *h, const int *ll, const int *ur, float spacing) {
     ((ParticleSystem *)h)->addStaticSphere(make_int3(ll[0], ll[1], ll[2]), make_int3(ur[0], ur[1], ur[2]), spacing);

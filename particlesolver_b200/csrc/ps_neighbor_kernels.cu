@@ -637,10 +637,14 @@ __device__ __forceinline__ float ps_scaled_w(float w, float y) {
 // SDF contact of two rigid-body particles: the reference CPU app's RigidContactConstraint (cpu/src/constraint/
 // rigidcontactconstraint.cpp:13-66, 2-D) lifted to 3-D.  si / sj = (outward unit gradient in world frame, depth below the body's
 // surface) of this particle and its partner, r = x_i - x_j.  The particle that sits shallower in its own body supplies normal and
-// depth (ties: the lower particle index, so that both particles of a pair see the same contact); for a particle of the outermost
-// layers (depth < diameter + EPS) the depth is the particles' overlap and the normal x_ij mirrored at the SDF normal when it points
-// against it (Macklin et al. 2014, eq. 13-14).  Returns false when the pair needs no correction; e = normal as the reference
-// leaves it (not normalised in the boundary case), pointing from i to j.
+// depth (ties: the lower particle index, so that both particles of a pair see the same contact).  For a particle of the outermost
+// layers (depth < diameter + EPS) the depth is the particles' overlap and the normal is the direction to the partner, mirrored at
+// the SDF normal when the partner lies behind the surface (Macklin et al. 2014, eq. 13-14).
+// Deviation from the reference's 2-D code, on purpose: it takes x12 = p1 - p2 — pointing from the partner to the particle — so
+// its mirror branch is the common case and an oblique contact's sideways component comes out flipped.  Lifted as is, resting
+// contacts on a box's edges and corners push sideways and, with the GPU solver's friction constants (0.005 / 0.0002), a tower of
+// three boxes walks apart within 300 steps (scripts/diag_rigid_scene.py); with x_ij = (x_j - x_i) / |.| the tower rests.
+// Returns false when the pair needs no correction; e = unit normal pointing from i to j.
 __device__ __forceinline__ bool sdf_contact(float4 si, float4 sj, bool i_first, float rx, float ry, float rz, float dist, float diam, float &d,
                                             float &ex, float &ey, float &ez) {
     const bool mine = si.w < sj.w || (si.w == sj.w && i_first);
@@ -650,7 +654,8 @@ __device__ __forceinline__ bool sdf_contact(float4 si, float4 sj, bool i_first, 
         d = diam - dist;
         if (d < PS_EPS) return false;
         float x = 0.f, y = 1.f, z = 0.f;
-        if (dist > PS_EPS) { const float inv = __fdividef(1.f, dist); x = rx * inv; y = ry * inv; z = rz * inv; }
+        if (dist > PS_EPS) { const float inv = __fdividef(-1.f, dist); x = rx * inv; y = ry * inv; z = rz * inv; }
+        else if (!i_first) y = -1.f;  // coincident: the lower index is pushed down, the other up
         const float dp = x * ex + y * ey + z * ez;
         if (dp < 0.f) { ex = x - 2.f * dp * ex; ey = y - 2.f * dp * ey; ez = z - 2.f * dp * ez; }
         else { ex = x; ey = y; ez = z; }
@@ -743,7 +748,7 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
                     if (!sdf_contact(si, sj, orig < oj, rx, ry, rz, dist, 2.f * radius, d, ex, ey, ez)) return;
                     const float s_ = __fdividef(d, wsum);
                     px = ex * s_; py = ey * s_; pz = ez * s_;
-                    fnx = ex; fny = ey; fnz = ez; fd = d;  // the CPU constraint's cone uses the depth (rigidcontactconstraint.cpp:84-90)
+                    fnx = ex; fny = ey; fnz = ez;  // friction about the contact normal; its cone keeps this pass's own scale (dist)
                 }
             }
             const float d1x = __fdividef(-colW * px, fn), d1y = __fdividef(-colW * py, fn), d1z = __fdividef(-colW * pz, fn);

@@ -57,8 +57,9 @@ int run_gpu(const Args &a) {
     } else {
         ps_scenes::SceneSpec s;
         s.scene = a.scene; s.grid = a.grid; s.max_particles = a.max_particles; s.iterations = a.iterations; s.side = a.side;
-        ps = ps_scenes::build<psb200::ParticleSystem>(s, psb200::colors, psb200::numColors);
-        if (!ps) die("unknown GPU scene '" + a.scene + "' (1-9, c2, c3)");
+        ps = a.scene == "r" ? psb200::build_rigid_scene(a.grid, a.max_particles, a.iterations)
+                            : ps_scenes::build<psb200::ParticleSystem>(s, psb200::colors, psb200::numColors);
+        if (!ps) die("unknown GPU scene '" + a.scene + "' (1-9, c2, c3, r)");
         if (!ps->lastError().empty()) die(ps->lastError());
         ctx = ps->context();
     }

@@ -192,3 +192,30 @@ def test_sdf_argument_checks():
     sol.set_rigid_body_sdf(bodies[2], none)             # "no data" is fine
     sol.step(DT)
     sol.close()
+
+
+@pytest.mark.gpu
+def test_rigid_box_scene_of_the_host_class_stacks_and_stays_rigid():
+    """extension scene "r" (psb200::build_rigid_scene, addRigidBox): shape-matched boxes with SDF data through the C++ host class"""
+    ps = psb.ParticleSystem.scene("r")
+    sol = ps.solver
+    assert sol.num_rigid_bodies == 4 and ps.getNumParticles() == 4 * 125 + 3 * 5 * 3
+    x0 = ps.getPositions()[:, :3].astype(np.float64)
+    for _ in range(360):
+        ps.update(DT)
+    x = ps.getPositions()[:, :3].astype(np.float64)
+    assert np.isfinite(x).all()
+    boxes = [slice(125 * k, 125 * (k + 1)) for k in range(4)]
+    for s in boxes:                                   # every box is still a box
+        d0 = np.linalg.norm(x0[s][:, None] - x0[s][None], axis=2)
+        d1 = np.linalg.norm(x[s][:, None] - x[s][None], axis=2)
+        assert np.abs(d1 - d0).max() < 0.05
+    for a in range(4):                                # and no two boxes sit inside each other
+        for b in range(a + 1, 4):
+            gap = np.linalg.norm(x[boxes[a]][:, None] - x[boxes[b]][None], axis=2).min()
+            assert gap > 0.8 * 2 * R, (a, b, gap)
+    y = [x[s][:, 1].mean() for s in boxes[:3]]
+    assert abs(y[0] - 1.25) < 0.1 and abs(y[1] - 3.75) < 0.15 and abs(y[2] - 6.25) < 0.2   # the tower of 2.5-unit boxes stands, at rest
+    assert np.abs(ps.getVelocities()[:500, :3]).max() < 0.05
+    assert x[:, 1].min() > 0.2                        # nothing went through the floor
+    ps.close()
