@@ -357,7 +357,8 @@ __device__ void project_boundary(const Particles2D &P, u32 i, double value, bool
 __global__ void __launch_bounds__(kSerialBlock) k2d_contact_project(Particles2D P, const u32 *__restrict__ nb, const u32 *__restrict__ cnt,
                                                                     const u32 *__restrict__ flags, const u32 *__restrict__ lvl, const u32 *__restrict__ rank,
                                                                     const u32 *__restrict__ info, u32 *__restrict__ cur, u32 n, const int *__restrict__ raw,
-                                                                    u32 window_base, u32 iteration, double x0, double x1, double y0, double y1, bool stabile) {
+                                                                    const u32 *__restrict__ window_base_ptr, u32 iteration, double x0, double x1, double y0, double y1, bool stabile) {
+    const u32 window_base = *window_base_ptr;  // a device word, so that the tick's launch sequence can be replayed as a graph
     // stabile: one pass over the STABILIZATION list = the rigid contacts and wall constraints of the CONTACT list, in its order
     // (simulation.cpp:190-192,204-223), so the same level schedule holds with the plain contacts stepped over.
     // info[-1] = jittered wall constraints of this tick (k2d_scan_counts): iteration t draws window[base + t * num + position]
@@ -697,6 +698,12 @@ struct Ps2dCtx {
     int *phase = nullptr, *bod = nullptr, *group = nullptr, *raw = nullptr;
     u32 *static_counts = nullptr, *flags = nullptr, *counts = nullptr, *draws = nullptr, *rank = nullptr, *nbcount = nullptr, *nb = nullptr, *cnt = nullptr,
         *lvl = nullptr, *cur = nullptr, *scalars = nullptr, *scalars_host = nullptr;  // scalars: [0] draws, [1] levels, [2] constraints, [3] overflow
+    // the tick's launch sequence as a CUDA graph (a tick of the reference's scenes is 11-29 dependent launches of a few
+    // microseconds each: issued eagerly the host is the bottleneck).  Re-captured when anything its nodes bake in changes.
+    u32 *window_base_dev = nullptr;
+    cudaGraphExec_t tick_graph = nullptr;
+    struct TickKey { uint64_t n; double dt; uint64_t standard_version; Ps2dParams params; const void *bodies, *raw, *lambda_keep; uint64_t misc; } tick_key{};
+    uint64_t standard_version = 0;
     unsigned char *nbq = nullptr;
     // rigid bodies
     u32 nbodies = 0, bodies_cap = 0;
@@ -775,7 +782,8 @@ extern "C" int ps2d_create(int device, const Ps2dParams *params, uint64_t max_pa
          dev_alloc(&c->lambda, n) && dev_alloc(&c->sdf_dist, n) && dev_alloc(&c->phase, n) && dev_alloc(&c->bod, n) && dev_alloc(&c->group, n) &&
          dev_alloc(&c->static_counts, n) && dev_alloc(&c->flags, n) && dev_alloc(&c->counts, n) && dev_alloc(&c->draws, n) && dev_alloc(&c->rank, n) &&
          dev_alloc(&c->nbcount, n) && dev_alloc(&c->nb, n * kMaxC) && dev_alloc(&c->cnt, n) && dev_alloc(&c->lvl, n * kEntries) && dev_alloc(&c->cur, n) &&
-         dev_alloc(&c->nbq, n * kMaxC) && dev_alloc(&c->scalars, 4) && cudaMallocHost((void **)&c->scalars_host, 16) == cudaSuccess;
+         dev_alloc(&c->nbq, n * kMaxC) && dev_alloc(&c->scalars, 8) && cudaMallocHost((void **)&c->scalars_host, 32) == cudaSuccess;
+    if (ok) c->window_base_dev = c->scalars + 4;
     if (ok) ok = cudaMemsetAsync(c->f, 0, n * 16, c->stream) == cudaSuccess && cudaMemsetAsync(c->lambda, 0, n * 8, c->stream) == cudaSuccess &&
                  cudaMemsetAsync(c->scalars, 0, 16, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess;
     if (!ok) {
@@ -796,6 +804,7 @@ extern "C" int ps2d_destroy(Ps2dCtx *c) {
                     c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center, c->dc_i1, c->dc_i2, c->dc_level_off, c->dc_rest, c->lambda_keep};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (c->scalars_host) cudaFreeHost(c->scalars_host);
+    if (c->tick_graph) cudaGraphExecDestroy(c->tick_graph);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return PS_OK;
@@ -1126,6 +1135,7 @@ static int rebuild_standard(Ps2dCtx *c) {
     CU2(upload(c, c->dc_rest, rest.data(), rest.size()));
     CU2(upload(c, c->dc_level_off, level_off.data(), level_off.size()));
     c->standard_dirty = false;
+    c->standard_version++;
     return PS_OK;
 }
 
@@ -1217,15 +1227,8 @@ extern "C" int ps2d_get_particle_timers(Ps2dCtx *c, double *t) {
     return PS_OK;
 }
 
-extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
-    struct Range { Range() { nvtxRangePushA("ps2d_tick"); } ~Range() { nvtxRangePop(); } } nvtx;  // ncu / nsys timelines
-    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
-    if (!c->n) return PS_OK;
-    CU2(cudaSetDevice(c->device));
-    if (c->standard_dirty) {
-        int r = rebuild_standard(c);
-        if (r != PS_OK) return r;
-    }
+// The launch sequence of one tick, from the prediction to the final scalars' copy (what ps2d_tick replays as a graph).
+static u32 issue_tick(Ps2dCtx *c, double dt) {
     cudaStream_t s = c->stream;
     const u32 n = c->n, blocks = (n + kBlock - 1) / kBlock;
     const Ps2dParams &P = c->params;
@@ -1237,38 +1240,15 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     k2d_scan_counts<<<1, 1024, 0, s>>>(c->draws, c->rank, n, c->scalars);
     k2d_contact_levels<<<1, kSerialBlock, 0, s>>>(c->nb, c->cnt, c->flags, n, c->nbq, c->lvl, c->scalars + 1);
     launches += 4;
-    // the number of jittered wall constraints decides how many draws of the rand() stream this tick consumes — one per
-    // constraint per solver iteration, in list order; at most 2 n per iteration.  The kernels take them from the look-ahead
-    // window, which is refilled (from a copy of the generator) when it no longer covers a worst-case tick.
-    const u32 passes = P.stabilization_iterations + P.solver_iterations;  // every pass over the wall constraints draws (the stabile copies too)
-    const uint64_t worst = (uint64_t)2 * n * passes;
-    if (c->any_jitter && (c->rng.calls < c->win_pos || c->rng.calls + worst > c->win_pos + c->win_len)) {
-        const size_t want = std::max<size_t>(worst * 16, 1u << 16);
-        GlibcRand ahead = c->rng;
-        c->h_raw.resize(want);
-        for (size_t k = 0; k < want; k++) c->h_raw[k] = ahead.next();
-        if (want > c->raw_cap) {
-            CU2(cudaStreamSynchronize(s));
-            if (c->raw) CU2(cudaFree(c->raw));
-            c->raw = nullptr;
-            CU2(cudaMalloc(&c->raw, want * sizeof(int)));
-            c->raw_cap = want;
-        }
-        CU2(cudaMemcpyAsync(c->raw, c->h_raw.data(), want * sizeof(int), cudaMemcpyHostToDevice, s));
-        CU2(cudaStreamSynchronize(s));  // h_raw is pageable
-        c->win_pos = c->rng.calls;
-        c->win_len = want;
-    }
-    const u32 window_base = (u32)(c->rng.calls - c->win_pos);
     Particles2D V{c->ep, c->p, c->tmass, c->sfric, c->kfric, c->phase, c->bod, c->counts, c->sdf_grad, c->sdf_dist, c->b_angle};
     // stabilization passes (the reference's compile-time option USE_STABILIZATION, simulation.cpp:249-271): before the solver iterations
     for (u32 st = 0; st < P.stabilization_iterations; st++) {
-        k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, window_base, st, x0, x1, y0, y1, true);
+        k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, c->window_base_dev, st, x0, x1, y0, y1, true);
         launches++;
     }
     for (u32 it = 0; it < P.solver_iterations; it++) {
         // CONTACT group (the kernel returns at once when the list is empty)
-        k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, window_base,
+        k2d_contact_project<<<1, kSerialBlock, 0, s>>>(V, c->nb, c->cnt, c->flags, c->lvl, c->rank, c->scalars + 1, c->cur, n, c->raw, c->window_base_dev,
                                                        P.stabilization_iterations + it, x0, x1, y0, y1, false);
         launches++;
         size_t run = 0;  // STANDARD group, in list order
@@ -1279,8 +1259,6 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
                 const u32 count = (u32)(R.end - R.begin);
                 const size_t stage = distance_stage_bytes(n, count);
                 if (stage <= kDistanceStageMax) {  // the reference's scenes: a few hundred particles
-                    static const cudaError_t optin = cudaFuncSetAttribute(k2d_distance_run_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDistanceStageMax);
-                    (void)optin;
                     const u32 block = std::min<u32>(kSerialBlock, std::max<u32>(32u, (R.width + 31u) & ~31u));
                     k2d_distance_run_staged<<<1, block, stage, s>>>(c->ep, c->imass, c->counts, c->dc_i1, c->dc_i2, c->dc_rest, c->dc_level_off + R.dev_level_first,
                                                                     R.levels, n, R.dev_first, count);
@@ -1310,11 +1288,75 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     }
     k2d_finish<<<blocks, kBlock, 0, s>>>(c->p, c->v, c->ep, n, dt);
     launches++;
-    c->launches = launches;
+    cudaMemcpyAsync(c->scalars_host, c->scalars, 16, cudaMemcpyDeviceToHost, s);
+    return launches;
+}
+
+extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
+    struct Range { Range() { nvtxRangePushA("ps2d_tick"); } ~Range() { nvtxRangePop(); } } nvtx;  // ncu / nsys timelines
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    if (!c->n) return PS_OK;
+    CU2(cudaSetDevice(c->device));
+    if (c->standard_dirty) {
+        int r = rebuild_standard(c);
+        if (r != PS_OK) return r;
+    }
+    cudaStream_t s = c->stream;
+    const u32 n = c->n;
+    const Ps2dParams &P = c->params;
+    // the number of jittered wall constraints decides how many draws of the rand() stream this tick consumes — one per
+    // constraint per solver iteration, in list order; at most 2 n per iteration.  The kernels take them from the look-ahead
+    // window, which is refilled (from a copy of the generator) when it no longer covers a worst-case tick.
+    const u32 passes = P.stabilization_iterations + P.solver_iterations;  // every pass over the wall constraints draws (the stabile copies too)
+    const uint64_t worst = (uint64_t)2 * n * passes;
+    if (c->any_jitter && (c->rng.calls < c->win_pos || c->rng.calls + worst > c->win_pos + c->win_len)) {
+        const size_t want = std::max<size_t>(worst * 16, 1u << 16);
+        GlibcRand ahead = c->rng;
+        c->h_raw.resize(want);
+        for (size_t k = 0; k < want; k++) c->h_raw[k] = ahead.next();
+        if (want > c->raw_cap) {
+            CU2(cudaStreamSynchronize(s));
+            if (c->raw) CU2(cudaFree(c->raw));
+            c->raw = nullptr;
+            CU2(cudaMalloc(&c->raw, want * sizeof(int)));
+            c->raw_cap = want;
+        }
+        CU2(cudaMemcpyAsync(c->raw, c->h_raw.data(), want * sizeof(int), cudaMemcpyHostToDevice, s));
+        CU2(cudaStreamSynchronize(s));  // h_raw is pageable
+        c->win_pos = c->rng.calls;
+        c->win_len = want;
+    }
+    // draws of this tick start at window[window_base]; the kernels read it from a device word
+    c->scalars_host[4] = (u32)(c->rng.calls - c->win_pos);
+    CU2(cudaMemcpyAsync(c->window_base_dev, c->scalars_host + 4, 4, cudaMemcpyHostToDevice, s));
+    static const bool no_graph = getenv("PS_NO_GRAPH") != nullptr;
+    static const cudaError_t optin = cudaFuncSetAttribute(k2d_distance_run_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDistanceStageMax);
+    (void)optin;
+    if (no_graph) {
+        c->launches = issue_tick(c, dt);
+    } else {
+        Ps2dCtx::TickKey key;
+        memset(&key, 0, sizeof(key));
+        key.n = n; key.dt = dt; key.standard_version = c->standard_version; key.params = P;
+        key.bodies = c->b_first; key.raw = c->raw; key.lambda_keep = c->lambda_keep;
+        key.misc = (uint64_t)c->fluid_emitters.size() | ((uint64_t)c->nbodies << 20) | ((uint64_t)(c->any_solid ? 1 : 0) << 60);
+        if (!c->tick_graph || memcmp(&key, &c->tick_key, sizeof(key)) != 0) {
+            if (c->tick_graph) { cudaGraphExecDestroy(c->tick_graph); c->tick_graph = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CU2(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            c->launches = issue_tick(c, dt);
+            cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            if (ce != cudaSuccess) { ps_set_error("ps2d_tick: stream capture failed: %s", cudaGetErrorString(ce)); return PS_ERR_CUDA; }
+            ce = cudaGraphInstantiate(&c->tick_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { c->tick_graph = nullptr; ps_set_error("ps2d_tick: graph instantiation failed: %s", cudaGetErrorString(ce)); return PS_ERR_CUDA; }
+            memcpy(&c->tick_key, &key, sizeof(key));
+        }
+        CU2(cudaGraphLaunch(c->tick_graph, s));
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ps_set_error("ps2d_tick: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
     // the one host round trip of a tick, at its end: what the CONTACT list looked like and how many draws it consumed
-    CU2(cudaMemcpyAsync(c->scalars_host, c->scalars, 16, cudaMemcpyDeviceToHost, s));
     CU2(cudaStreamSynchronize(s));
     const u32 num = c->scalars_host[0];
     c->last_num_boundary = num;
