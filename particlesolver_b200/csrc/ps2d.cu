@@ -704,6 +704,7 @@ struct Ps2dCtx {
     cudaGraphExec_t tick_graph = nullptr;
     struct TickKey { uint64_t n; double dt; uint64_t standard_version; Ps2dParams params; const void *bodies, *raw, *lambda_keep; uint64_t misc; } tick_key{};
     uint64_t standard_version = 0;
+    u32 tick_key_age = 0;  // ticks the current key has been seen
     unsigned char *nbq = nullptr;
     // rigid bodies
     u32 nbodies = 0, bodies_cap = 0;
@@ -1340,8 +1341,19 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
         key.n = n; key.dt = dt; key.standard_version = c->standard_version; key.params = P;
         key.bodies = c->b_first; key.raw = c->raw; key.lambda_keep = c->lambda_keep;
         key.misc = (uint64_t)c->fluid_emitters.size() | ((uint64_t)c->nbodies << 20) | ((uint64_t)(c->any_solid ? 1 : 0) << 60);
-        if (!c->tick_graph || memcmp(&key, &c->tick_key, sizeof(key)) != 0) {
+        // a capture costs a few eager ticks: scenes whose emitters add particles every other tick keep changing the key and are
+        // issued eagerly; the graph is (re)built once the key has stood still for kStableTicks ticks
+        constexpr u32 kStableTicks = 4;
+        const bool same = memcmp(&key, &c->tick_key, sizeof(key)) == 0;
+        if (!same) {
             if (c->tick_graph) { cudaGraphExecDestroy(c->tick_graph); c->tick_graph = nullptr; }
+            memcpy(&c->tick_key, &key, sizeof(key));
+            c->tick_key_age = 0;
+        }
+        c->tick_key_age++;
+        if (!c->tick_graph && c->tick_key_age < kStableTicks) {
+            c->launches = issue_tick(c, dt);
+        } else if (!c->tick_graph) {
             cudaGraph_t graph = nullptr;
             CU2(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
             c->launches = issue_tick(c, dt);
@@ -1350,9 +1362,10 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
             ce = cudaGraphInstantiate(&c->tick_graph, graph, 0);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) { c->tick_graph = nullptr; ps_set_error("ps2d_tick: graph instantiation failed: %s", cudaGetErrorString(ce)); return PS_ERR_CUDA; }
-            memcpy(&c->tick_key, &key, sizeof(key));
+            CU2(cudaGraphLaunch(c->tick_graph, s));
+        } else {
+            CU2(cudaGraphLaunch(c->tick_graph, s));
         }
-        CU2(cudaGraphLaunch(c->tick_graph, s));
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ps_set_error("ps2d_tick: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
