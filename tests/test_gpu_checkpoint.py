@@ -92,3 +92,14 @@ def test_cli_switches_the_optional_contact_rules_on():
     assert run("--scene", "7")["position_checksum"] == run("--scene", "7", "--self-collision")["position_checksum"]
     a, b = run("--scene", "2"), run("--scene", "2", "--self-collision")
     assert a["particles"] == b["particles"] and np.isfinite(b["kinetic_energy"])
+
+
+def test_2d_tick_graph_replay_equals_eager_issue():
+    """the 2-D tick is replayed as a CUDA graph once its key has stood still for a few ticks; PS_NO_GRAPH=1 issues every launch
+    eagerly — the two must be the same computation (scenes with walls + jitter draws, rigid bodies, an emitter that changes n)"""
+    for key in ("6", "w", "s"):
+        a = subprocess.run([CLI, "--app", "cpu", "--scene", key, "--ticks", "120", "--json"], capture_output=True, text=True, check=True).stdout
+        b = subprocess.run([CLI, "--app", "cpu", "--scene", key, "--ticks", "120", "--json"], capture_output=True, text=True, check=True,
+                           env=dict(os.environ, PS_NO_GRAPH="1")).stdout
+        a, b = json.loads(a), json.loads(b)
+        assert a["kinetic_energy"] == b["kinetic_energy"] and a["rand_calls"] == b["rand_calls"] and a["particles"] == b["particles"], key
