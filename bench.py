@@ -252,9 +252,19 @@ def run_ours(args, rank, world, local_rank):
                     st, _ln = sol.step_profiled(DT)
                     for k, v in st.items():
                         stages[k] = round(stages.get(k, 0.0) + v / 3 / (1 if k in ("predict", "velocity") else ITERS), 4)
+            import ctypes
+            staged = None
+            try:
+                st = (ctypes.c_uint * 8)()
+                if psb.lib().ps_debug_staged_stats(st, 1) == 0:
+                    staged = list(st)[:5]
+            except AttributeError:
+                pass
+            rows = sol.download(psb.ARR_NEIGHBOR_ROWS)
             print(json.dumps({"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
                               "ms_per_step": ms / args.steps, "gpu_launches": launches, "quick": True, "lib": os.environ.get("PS_LIBRARY", "default"),
-                              "stage_ms_per_launch": stages, "clocks": clocks}), flush=True)
+                              "stage_ms_per_launch": stages, "staged_cta_outcomes[planes,rows,table,stage,ok]": staged,
+                              "clocks": clocks}), flush=True)
         ps.close()
         if dist is not None:
             dist.destroy_process_group()

@@ -51,9 +51,10 @@ typedef struct PsParams {
     float omega;                 /* SOR factor on the Jacobi-averaged deltas; 1.0 == reference */
     uint32_t flags;              /* PS_FLAG_* */
     uint32_t neighbor_list_rows; /* neighbour lists kept between the two PBF passes: rows (128 B: one entry for each of a warp's 32
-                                    particles) of a pool shared by all warps, per warp ON AVERAGE — 256 = 1 KB per particle.  A warp
-                                    takes 48-row chunks as it goes, up to 1488 rows; one that needs more, or finds the pool empty, falls
-                                    back to a second grid walk (results identical).  0 = keep no lists.  Multiple of 8. */
+                                    particles) of every warp's list region.  512 (default) >= the 500-neighbour cap: a list always fits;
+                                    2 KB of address space per particle, of which only the rows actually used are ever touched.  With
+                                    fewer rows a warp whose longest list does not fit falls back to a second grid walk (results
+                                    identical).  0 = keep no lists.  Multiple of 8. */
 } PsParams;
 
 #define PS_FLAG_NONE 0u
@@ -67,6 +68,10 @@ typedef struct PsParams {
                           such particles collide (contact + friction, like particles of different bodies) when both carry
                           distance constraints and no distance constraint joins them: a cloth or rope touches itself, its
                           constrained neighbours and the members of shape-matched bodies still skip each other.  Unpinned. */
+#define PS_FLAG_STAGED_LAMBDA 8u /* K6 (PBF lambda) by the TMA-staged kernel (csrc/ps_fluid_staged.cu: the neighbour rows of a CTA are
+                          copied into shared memory by cp.async.bulk) instead of the grid walk through L1.  Same results, bit for
+                          bit; measured slower than the walk on B200, kept as the measured alternative.  Needs neighbour
+                          lists (neighbor_list_rows != 0). */
 
 typedef struct PsCtx PsCtx;
 
@@ -82,7 +87,8 @@ enum {
     PS_ARR_INDEX = 7,        /* uint[n]    sorted order          m_dGridParticleIndex */
     PS_ARR_CELL_START = 8,   /* uint[cells] 0xffffffff = empty   m_dCellStart */
     PS_ARR_CELL_END = 9,     /* uint[cells] valid where start != 0xffffffff  m_dCellEnd */
-    PS_ARR_SORTED_POS = 10,  /* float4[n] */
+    PS_ARR_SORTED_POS = 10,  /* float4[n]  m_dSortedPos (download only; ps_device_ptr gives the resident array, whose .w holds the
+                                sorted slot's bit pattern instead of pos.w) */
     PS_ARR_SORTED_INV_MASS = 11,
     PS_ARR_SORTED_PHASE = 12,
     PS_ARR_LAMBDA = 13,      /* float[n] by sorted slot  integration.cu:24 */
@@ -90,8 +96,9 @@ enum {
     PS_ARR_RANDS = 15,       /* float[iterations*6] wall-jitter uniforms of the last step */
     PS_ARR_OCCURRENCES = 16, /* uint[n]    solver.cu:41 */
     PS_ARR_CELL_BEGIN = 17,  /* uint[cells+1] dense lower-bound table (internal; exposed for tests) */
-    PS_ARR_NEIGHBOR_ROWS = 18 /* uint[32 * ceil(n/32)] per-warp list records of the last lambda pass (diagnostics): word 0 = rows used,
-                                 0xffffffff = the warp overflowed and its delta-p pass walks the grid again; words 1..31 = pool chunks */
+    PS_ARR_NEIGHBOR_ROWS = 18 /* uint[ceil(n/32)] per-warp list status of the last lambda pass (diagnostics): 0 = no active fluid
+                                 particle, 1 = list valid, 0xffffffff = the warp has no list and its delta-p pass walks the grid again
+                                 (csrc/ps_fluid_lists.cuh) */
 };
 
 void ps_default_params(PsParams *p);

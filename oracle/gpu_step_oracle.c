@@ -135,6 +135,11 @@ void or_reorder(const u32 *hash, const u32 *index, const float *pos, const float
 }
 
 static inline float dot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+/* dot(r, r) as the reference's own build computes it where it DECIDES the neighbour sets (collideCell :330-336, collideCellRadius
+ * :505-508): nvcc -use_fast_math contracts helper_math's x*x + y*y + z*z into FMUL y*y, FFMA x*x + ., FFMA z*z + . (cuobjdump -sass
+ * of oracle/_ref/ref_gpu, findLambdasD / collideD).  A pair within one ulp of the radius is in or out by that rounding, so the
+ * neighbour COUNTS — an exact contract — need it; everything downstream of the decision keeps plain IEEE arithmetic. */
+static inline float dot3_self_nvcc(const float *r) { return fmaf(r[2], r[2], fmaf(r[0], r[0], r[1] * r[1])); }
 
 /* ---- K5: collide / collideD / collideCell (integration.cu:338-386, integration_kernel.cuh:303-462).
  *          Runs for sorted-phase >= CLOTH only; others leave pos[] and num_neighbors[] untouched. ---- */
@@ -199,7 +204,7 @@ void or_collide_ext(float *pos, const float *prev, const float *spos, const floa
                             int phase2 = sphase[j];
                             if (phase > PH_SOLID && phase == phase2 && same_body_skip(adj_off, adj, index[i], index[j])) continue;
                             float d[3] = {x[0] - spos[4 * (size_t)j], x[1] - spos[4 * (size_t)j + 1], x[2] - spos[4 * (size_t)j + 2]};
-                            float mag2 = dot3(d, d);
+                            float mag2 = dot3_self_nvcc(d);
                             if (mag2 < collideDist2 && nn < MAX_FLUID_NEIGHBORS) nb[nn++] = j;
                         }
                     }
@@ -293,7 +298,7 @@ static u32 fluid_neighbors(const OrParams *p, const float *spos, const u32 *cell
                     if (j == i) continue;
                     const float *x2 = spos + 4 * (size_t)j;
                     float r[3] = {x[0] - x2[0], x[1] - x2[1], x[2] - x2[2]};
-                    float d2 = dot3(r, r);
+                    float d2 = dot3_self_nvcc(r);
                     if (d2 < H2 && nn < MAX_FLUID_NEIGHBORS) nb[nn++] = j;
                 }
             }

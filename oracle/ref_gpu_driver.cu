@@ -90,6 +90,8 @@ static void dump_i(const std::string &n, const int *d, size_t c) { dump_dev(n, d
 struct Args {
     std::string scene = "7", mode = "staged", out = "gpurun_out/ref_gpu";
     int grid = 64, steps = 1, dump_every = 1, iters = 5, side = 100;
+    int dump_iters = 1 << 30;  // staged mode: dump the arrays of the first dump_iters solver iterations of a step only
+    int light = 0;             // staged mode: only what the full-size parity test reads (1M particles: 0.25 GB instead of 1.3 GB per step)
     unsigned max_particles = 15000;
     float dt = 1.0f / 60.0f;
 };
@@ -138,7 +140,8 @@ static void dump_scene(ParticleSystem *ps) {
 }
 
 // call-by-call replay of ParticleSystem::update (particlesystem.cpp:144-246) with dumps in between
-static void staged_step(ParticleSystem *ps, float dt, int step, bool dump) {
+static void staged_step(ParticleSystem *ps, float dt, int step, bool dump_step, int dump_iters, bool light) {
+    bool dump = dump_step;
     dt = std::min(dt, .05f);
     uint n = ps->m_numParticles, cells = ps->m_numGridCells;
     float *dPos = (float *)mapGLBufferObject(&ps->m_cuda_posvbo_resource);
@@ -147,12 +150,13 @@ static void staged_step(ParticleSystem *ps, float dt, int step, bool dump) {
     char tag[64];
     snprintf(tag, sizeof tag, "s%d_", step);
     std::string S(tag);
-    if (dump) { dump_f(S + "predict_pos", dPos, 4 * (size_t)n); dump_f(S + "prev", getXstarRawPtr(), 4 * (size_t)n); }
+    if (dump) { dump_f(S + "predict_pos", dPos, 4 * (size_t)n); if (!light) dump_f(S + "prev", getXstarRawPtr(), 4 * (size_t)n); }
     for (uint i = 0; i < ps->m_solverIterations; i++) {
+        dump = dump_step && (int)i < dump_iters;
         snprintf(tag, sizeof tag, "s%d_i%u_", step, i);
         std::string T(tag);
         calcHash(ps->m_dGridParticleHash, ps->m_dGridParticleIndex, dPos, n);
-        if (dump) dump_u(T + "hash_unsorted", ps->m_dGridParticleHash, n);
+        if (dump && !light) dump_u(T + "hash_unsorted", ps->m_dGridParticleHash, n);
         sortParticles(ps->m_dGridParticleHash, ps->m_dGridParticleIndex, n);
         if (dump) { dump_u(T + "hash", ps->m_dGridParticleHash, n); dump_u(T + "index", ps->m_dGridParticleIndex, n); }
         reorderDataAndFindCellStart(ps->m_dCellStart, ps->m_dCellEnd, ps->m_dSortedPos, ps->m_dSortedW, ps->m_dSortedPhase,
@@ -161,12 +165,11 @@ static void staged_step(ParticleSystem *ps, float dt, int step, bool dump) {
             dump_u(T + "cell_start", ps->m_dCellStart, cells);
             dump_u(T + "cell_end", ps->m_dCellEnd, cells);
             dump_f(T + "sorted_pos", ps->m_dSortedPos, 4 * (size_t)n);
-            dump_f(T + "sorted_w", ps->m_dSortedW, n);
-            dump_i(T + "sorted_phase", ps->m_dSortedPhase, n);
+            if (!light) { dump_f(T + "sorted_w", ps->m_dSortedW, n); dump_i(T + "sorted_phase", ps->m_dSortedPhase, n); }
         }
         collide(dPos, ps->m_dSortedPos, ps->m_dSortedW, ps->m_dSortedPhase, ps->m_dGridParticleIndex, ps->m_dCellStart,
                 ps->m_dCellEnd, n, cells);
-        if (dump) { dump_f(T + "collide_pos", dPos, 4 * (size_t)n); dump_u(T + "collide_nn", st_nn(), n); }
+        if (dump && !light) { dump_f(T + "collide_pos", dPos, 4 * (size_t)n); dump_u(T + "collide_nn", st_nn(), n); }
         solveFluids(ps->m_dSortedPos, ps->m_dSortedW, ps->m_dSortedPhase, ps->m_dGridParticleIndex, ps->m_dCellStart,
                     ps->m_dCellEnd, dPos, n, cells);
         if (dump) {
@@ -175,13 +178,14 @@ static void staged_step(ParticleSystem *ps, float dt, int step, bool dump) {
             dump_f(T + "fluid_pos", dPos, 4 * (size_t)n);
         }
         collideWorld(dPos, ps->m_dSortedPos, n, ps->m_minBounds, ps->m_maxBounds);
-        if (dump) { dump_f(T + "rands", st_rands(), 6); dump_f(T + "world_pos", dPos, 4 * (size_t)n); }
+        if (dump && !light) { dump_f(T + "rands", st_rands(), 6); dump_f(T + "world_pos", dPos, 4 * (size_t)n); }
         solveDistanceConstraints(dPos);
-        if (dump) dump_f(T + "dist_pos", dPos, 4 * (size_t)n);
+        if (dump && !light) dump_f(T + "dist_pos", dPos, 4 * (size_t)n);
         solvePointConstraints(dPos);
-        if (dump) dump_f(T + "point_pos", dPos, 4 * (size_t)n);
+        if (dump && !light) dump_f(T + "point_pos", dPos, 4 * (size_t)n);
     }
     calcVelocity(dPos, dt, n);
+    dump = dump_step;
     if (dump) { dump_f(S + "final_pos", dPos, 4 * (size_t)n); dump_f(S + "final_vel", st_vel(), 4 * (size_t)n); }
     unmapGLBufferObject(ps->m_cuda_posvbo_resource);
 }
@@ -210,6 +214,8 @@ int main(int argc, char **argv) {
         else if (k == "--side") a.side = atoi(val().c_str());
         else if (k == "--max") a.max_particles = (unsigned)atol(val().c_str());
         else if (k == "--dt") a.dt = (float)atof(val().c_str());
+        else if (k == "--dump-iters") a.dump_iters = atoi(val().c_str());
+        else if (k == "--light") a.light = atoi(val().c_str());
         else { fprintf(stderr, "unknown arg %s\n", k.c_str()); return 2; }
     }
     g_out = a.out;
@@ -224,7 +230,7 @@ int main(int argc, char **argv) {
     if (n == 0) { fprintf(stderr, "scene is empty (maxParticles too small?)\n"); return 3; }
     dump_scene(ps);
     if (a.mode == "staged") {
-        for (int s = 0; s < a.steps; s++) staged_step(ps, a.dt, s, true);
+        for (int s = 0; s < a.steps; s++) staged_step(ps, a.dt, s, true, a.dump_iters, a.light != 0);
     } else {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);

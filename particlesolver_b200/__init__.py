@@ -24,6 +24,7 @@ PS_OK, PS_ERR_INVALID, PS_ERR_CUDA, PS_ERR_CAPACITY, PS_ERR_STATE = 0, 1, 2, 3, 
 FLAG_ZERO_NONFLUID_LAMBDA = 1
 FLAG_GAS = 2
 FLAG_SELF_COLLISION = 4
+FLAG_STAGED_LAMBDA = 8
 NUM_STAGES = 12
 
 (ARR_POS, ARR_VEL, ARR_PREV, ARR_INV_MASS, ARR_PHASE, ARR_REST_DENSITY, ARR_HASH, ARR_INDEX, ARR_CELL_START, ARR_CELL_END,
@@ -425,7 +426,7 @@ class Solver:
         if which == ARR_RANDS:
             return int(self.params.solver_iterations) * 6
         if which == ARR_NEIGHBOR_ROWS:
-            return 32 * ((self.n + 31) // 32) if self.params.neighbor_list_rows else 0
+            return (self.n + 31) // 32 if self.params.neighbor_list_rows else 0
         return self.n * _ARR_WIDTH.get(which, 1)
 
     def download(self, which, out=None):

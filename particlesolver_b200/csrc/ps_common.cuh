@@ -30,8 +30,7 @@ typedef uint32_t u32;
 #define PS_GAS_ALPHA -.2f  // buoyancy of GAS particles (reference CPU app: ALPHA, cpu/src/simulation.h:21); only with PS_FLAG_GAS
 
 #define PS_MAX_RAD 8
-#define PS_LIST_CHUNK_ROWS 48   // neighbour-list pool: rows per chunk
-#define PS_LIST_RECORD_WORDS 32 // per-warp list record: rows used + 31 chunk ids (1488 rows: lanes capped at 500 neighbours fill unevenly)
+#define PS_LIST_RECORD_WORDS 1  // per-warp neighbour-list status word (ps_fluid_lists.cuh)
 
 // uniform grid descriptor, passed by value (kernel parameter space == constant bank, one per launch, so
 // several contexts can coexist; the reference uses a single __constant__ SimParams, integration_kernel.cuh:55)
@@ -82,6 +81,12 @@ __device__ __forceinline__ void st_stream4(float4 *p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// the same with the fourth component given as raw bits (a sorted slot travelling in .w must not pass through float arithmetic)
+__device__ __forceinline__ void st_stream4_wbits(float4 *p, float x, float y, float z, u32 wbits) {
+    asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__float_as_uint(x)), "r"(__float_as_uint(y)), "r"(__float_as_uint(z)),
+                 "r"(wbits) : "memory");
+}
+
 // ---------------- launchers (host side, all asynchronous on `s`) ----------------
 // ps_stream_kernels.cu
 // gas_phase != nullptr (PS_FLAG_GAS): phase array; GAS particles are predicted with gravity x PS_GAS_ALPHA
@@ -94,8 +99,13 @@ void ps_launch_distance(float4 *pos, float4 *scratch, const u32 *csr_particle, c
 // ps_grid_kernels.cu
 void ps_launch_calc_hash(u32 *hash, u32 *index, const float4 *pos, u32 n, GridDesc g, cudaStream_t s);
 // K4: gather into sorted order + per-chunk lower bounds (chunk_lb[ps_chunk_table_elems(num_cells)])
+// slot_in_w: spos[i].w = bit pattern of i instead of pos.w (the staged K6 reads a candidate's slot from there; nothing else reads
+// spos.w); exact_copy != nullptr: also the reference's sortedPos, exact float4 copies (the reference ABI hands that array out)
 void ps_launch_reorder(float4 *spos, float *sw, int *sphase, u32 *chunk_lb, const u32 *hash, const u32 *index, const float4 *pos,
-                       const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s, bool gas_as_fluid = false);
+                       const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s, bool gas_as_fluid = false, bool slot_in_w = false,
+                       float4 *exact_copy = nullptr);
+// out[i] = (spos[i].xyz, pos[index[i]].w): the reference's sortedPos from a slot_in_w array (downloads / diagnostics)
+void ps_launch_export_sorted_pos(float4 *out, const float4 *spos, const float4 *pos, const u32 *index, u32 n, cudaStream_t s);
 size_t ps_chunk_table_elems(u32 num_cells);
 // dense lower-bound table cell_begin[c] = #particles with key < c, c in [0,num_cells]; from the sorted keys + chunk_lb
 void ps_launch_cell_begin(u32 *cell_begin, const u32 *hash, const u32 *chunk_lb, u32 n, u32 num_cells, cudaStream_t s);
@@ -119,24 +129,27 @@ void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool 
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                        const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, const u32 *adj_off,
                        const u32 *adj, const float4 *sdf_world, cudaStream_t s);
-// nbr_list / nbr_rows: interleaved per-warp neighbour lists written by K6 and consumed by K7 (nullptr: K7 re-walks the grid)
-// (in the launchers below `max_rows` is the number of chunks in the pool, ps_neighbor_pool_chunks, and `nbr_rows` the first
-// per-warp record of the buffer sized by ps_neighbor_record_elems)
-u32 ps_neighbor_pool_chunks(unsigned long long capacity, u32 rows_per_warp);
+// nbr_list / nbr_rows: interleaved per-warp neighbour lists written by K6 and consumed by K7 and the other passes (nullptr: they
+// re-walk the grid); format in ps_fluid_lists.cuh.  `list_rows` = rows of a warp's region (PsParams.neighbor_list_rows), `capacity`
+// = the particle capacity the buffers were sized for, `nbr_rows` = the first per-warp status word of the buffer sized by
+// ps_neighbor_record_elems; `device` = the context's device (per-device shared-memory opt-in).
 size_t ps_neighbor_list_elems(unsigned long long capacity, u32 rows_per_warp);
 size_t ps_neighbor_record_elems(unsigned long long capacity);
-void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
-                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
-                            const StencilDesc &st, bool zero_nonfluid, u32 *nbr_list, u32 *nbr_rows, u32 max_rows, cudaStream_t s);
+u32 ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
+                           const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
+                           const StencilDesc &st, bool zero_nonfluid, u32 *nbr_list, u32 *nbr_rows, u32 list_rows, unsigned long long capacity,
+                           bool slot_in_w, bool staged, int device, cudaStream_t s);  // returns the number of launches
 u32 ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
-                           const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s);  // returns the number of launches
+                           const u32 *nbr_list, const u32 *nbr_rows, u32 list_rows, const u32 *num_neighbors, int device,
+                           cudaStream_t s);  // returns the number of launches
 // K13 (optional, not in the reference): XSPH viscosity + vorticity confinement on the PBF neighbour structure; returns #launches
 u32 ps_launch_viscosity(float4 *vel, float4 *scratch, const float4 *spos, const int *sphase, const u32 *index, const u32 *cell_begin, u32 n, GridDesc g,
-                        const StencilDesc &st, float c_xsph, float vorticity_eps, float dt, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows,
-                        cudaStream_t s);
+                        const StencilDesc &st, float c_xsph, float vorticity_eps, float dt, const u32 *nbr_list, const u32 *nbr_rows, u32 list_rows,
+                        const u32 *num_neighbors, int device, cudaStream_t s);
 u32 ps_launch_density_error(float4 *scratch, const float4 *spos, const float *sw, const int *sphase, const u32 *index, const float *ros, const u32 *cell_begin,
-                            u32 n, GridDesc g, const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s);
+                            u32 n, GridDesc g, const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 list_rows,
+                            const u32 *num_neighbors, int device, cudaStream_t s);
 // ps_shape_kernels.cu — K12 (not in the reference's GPU solver): shape matching, one warp per rigid body
 void ps_launch_sdf_world(float4 *sdf_world, const float4 *sdf_rest, const u32 *body_idx, const u32 *member_body, const float4 *quat, u32 members,
                          cudaStream_t s);

@@ -64,7 +64,9 @@ extern "C" void ps_default_params(PsParams *p) {
     p->solver_iterations = 5;
     p->omega = 1.0f;
     p->flags = PS_FLAG_NONE;
-    p->neighbor_list_rows = 256;  // rows of the shared pool per warp ON AVERAGE (1 KB per particle); a warp may take up to 1488
+    // tuning aid (A/B runs of bench.py and the CLI without a rebuild): PS_EXTRA_FLAGS=<bits> is ORed into the default flags
+    if (const char *e = getenv("PS_EXTRA_FLAGS")) p->flags |= (uint32_t)strtoul(e, nullptr, 0);
+    p->neighbor_list_rows = 512;  // rows of a warp's list region: >= the 500-neighbour cap, so a list always fits (2 KB of address space per particle)
 }
 
 static bool is_pow2(u32 v) { return v && !(v & (v - 1)); }
@@ -141,7 +143,7 @@ int ps_ctx_alloc_lists(PsCtx *c, uint64_t cap) {
     if (c->nbr_rows) { CU(cudaFree(c->nbr_rows - 4)); c->nbr_rows = nullptr; }
     c->nbr_max_rows = 0;
     if (!c->params.neighbor_list_rows || !cap) return PS_OK;
-    c->nbr_max_rows = ps_neighbor_pool_chunks(cap, c->params.neighbor_list_rows);
+    c->nbr_max_rows = c->params.neighbor_list_rows;  // rows of a warp's list region
     if (!c->nbr_max_rows) return PS_OK;
     u32 *rec = nullptr;
     CU(cudaMalloc((void **)&c->nbr_list, ps_neighbor_list_elems(cap, c->params.neighbor_list_rows) * sizeof(u32)));
@@ -451,7 +453,7 @@ u32 ps_issue_build_grid(PsCtx *c, const float4 *pos) {
     u32 *kB = odd ? c->hash : c->hash_tmp, *vB = odd ? c->index : c->index_tmp;
     ps_launch_calc_hash(kA, nullptr, pos, n, c->grid, s);
     ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s);
-    ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, pos, c->w, c->phase, n, c->num_cells, s, (c->params.flags & PS_FLAG_GAS) != 0);
+    ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, pos, c->w, c->phase, n, c->num_cells, s, (c->params.flags & PS_FLAG_GAS) != 0, true);
     ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s);
     c->grid_valid = true;
     c->ref_tables_valid = false;
@@ -527,10 +529,10 @@ static int issue_fluid(PsCtx *c, const char *what, bool do_lambda, bool do_delta
     if (do_lambda)
         ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost,
                                c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list,
-                               c->nbr_rows, c->nbr_max_rows, c->stream);
+                               c->nbr_rows, c->nbr_max_rows, c->capacity, true, (c->params.flags & PS_FLAG_STAGED_LAMBDA) != 0, c->device, c->stream);
     if (do_delta)
         ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost, c->grid, c->stencil,
-                               c->params.omega, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
+                               c->params.omega, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->num_neighbors, c->device, c->stream);
     return check_launch(what);
 }
 extern "C" int ps_solve_fluid(PsCtx *c) { return issue_fluid(c, "ps_solve_fluid", true, true); }
@@ -588,11 +590,11 @@ static u32 issue_step(PsCtx *c, float dt) {
             launches++;
         }
         if (has_fluid) {
-            ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned,
-                                   c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list,
-                                   c->nbr_rows, c->nbr_max_rows, s);
-            launches += 1 + ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned, c->grid,
-                                                   c->stencil, p.omega, c->nbr_list, c->nbr_rows, c->nbr_max_rows, s);
+            launches += ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned,
+                                               c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list,
+                                               c->nbr_rows, c->nbr_max_rows, c->capacity, true, (c->params.flags & PS_FLAG_STAGED_LAMBDA) != 0, c->device, s);
+            launches += ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n_owned, c->grid,
+                                               c->stencil, p.omega, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->num_neighbors, c->device, s);
         }
         ps_launch_collide_world(c->pos, c->prev, c->phase, n_owned, c->rands + 6 * it, c->world, s);
         launches++;
@@ -679,17 +681,17 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
     for (u32 it = 0; it < iters; it++) {
         ps_launch_calc_hash(kA, nullptr, c->pos, n, c->grid, s); mark(1, 1);
         ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s); mark(2, 1 + c->sort_passes);
-        ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, c->pos, c->w, c->phase, n, c->num_cells, s, (p.flags & PS_FLAG_GAS) != 0); mark(3, 1);
+        ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, c->pos, c->w, c->phase, n, c->num_cells, s, (p.flags & PS_FLAG_GAS) != 0, true); mark(3, 1);
         ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s); mark(4, 1);
         c->grid_valid = true;
         c->ref_tables_valid = false;
         if (has_contact) { const u32 lsdf = ps_ext_issue_sdf(c); ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, s); mark(5, 1 + lsdf); }
         if (has_fluid) {
-            ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->lambda_xmin,
-                                   c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list, c->nbr_rows,
-                                   c->nbr_max_rows, s); mark(6, 1);
+            const u32 k6 = ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->lambda_xmin,
+                                                  c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list, c->nbr_rows,
+                                                  c->nbr_max_rows, c->capacity, true, (c->params.flags & PS_FLAG_STAGED_LAMBDA) != 0, c->device, s); mark(6, k6);
             const u32 k7 = ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->grid, c->stencil, p.omega,
-                                                  c->nbr_list, c->nbr_rows, c->nbr_max_rows, s); mark(7, k7);
+                                                  c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->num_neighbors, c->device, s); mark(7, k7);
         }
         ps_launch_collide_world(c->pos, c->prev, c->phase, n, c->rands + 6 * it, c->world, s); mark(8, 1);
         if (c->num_constrained) { ps_launch_distance(c->pos, c->dist_scratch, c->csr_particle, c->csr_off, c->csr_other, c->csr_rest, c->occ, c->num_constrained, p.omega, s); mark(9, 2); }
@@ -782,6 +784,19 @@ static int copy_common(PsCtx *c, int which, void *host, uint64_t off, uint64_t c
         if (!to_host) { ps_set_error("cellStart/cellEnd are derived outputs"); return PS_ERR_INVALID; }
         int r = ps_ctx_emit_reference_tables(c); if (r != PS_OK) return r;
         a = arr_info(c, which);
+    }
+    if (which == PS_ARR_SORTED_POS) {
+        // derived outputs of the grid build; .w of the resident array carries the sorted slot (ps_fluid_staged.cu), the reference's
+        // sortedPos carries pos.w: hand out the reference's (a diagnostic path: temporary buffer, synchronous)
+        if (!to_host) { ps_set_error("the sorted arrays are derived outputs"); return PS_ERR_INVALID; }
+        float4 *tmp = nullptr;
+        CU(cudaMalloc((void **)&tmp, (size_t)c->n * sizeof(float4)));
+        ps_launch_export_sorted_pos(tmp, c->spos, c->pos, c->index, c->n, c->stream);
+        cudaError_t e = cudaMemcpyAsync(host, (char *)tmp + off * a.esz, cnt * a.esz, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) { ps_set_error("download of the sorted positions failed: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
+        return PS_OK;
     }
     char *d = (char *)a.ptr + off * a.esz;
     if (to_host) CU(cudaMemcpyAsync(host, d, cnt * a.esz, cudaMemcpyDeviceToHost, c->stream));

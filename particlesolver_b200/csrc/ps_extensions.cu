@@ -191,7 +191,7 @@ u32 ps_ext_issue_viscosity(PsCtx *c, float dt) {
     if (c->xsph_c == 0.f && c->vorticity_eps == 0.f) return 0;
     if (!c->n || !c->visc_scratch || !c->grid_valid) return 0;
     return ps_launch_viscosity(c->vel, c->visc_scratch, c->spos, c->sphase, c->index, c->cell_begin, c->n, c->grid, c->stencil, c->xsph_c, c->vorticity_eps,
-                               dt, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
+                               dt, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->num_neighbors, c->device, c->stream);
 }
 
 // K6 alone on the current grid: fills lambda, the neighbour counts and the neighbour lists without moving anything
@@ -202,7 +202,7 @@ extern "C" int ps_find_neighbors(PsCtx *c) {
     DevGuard dg(c->device);
     ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost, c->lambda_xmin,
                            c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list, c->nbr_rows,
-                           c->nbr_max_rows, c->stream);
+                           c->nbr_max_rows, c->capacity, true, (c->params.flags & PS_FLAG_STAGED_LAMBDA) != 0, c->device, c->stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { ps_set_error("ps_find_neighbors: %s", cudaGetErrorString(e)); return PS_ERR_CUDA; }
     return PS_OK;
@@ -243,7 +243,7 @@ extern "C" int ps_fluid_stats(PsCtx *c, double *mean_density_error, double *max_
     const u32 n = c->n;
     XCU(cudaMemsetAsync(c->visc_scratch, 0, (size_t)n * sizeof(float4), c->stream));
     ps_launch_density_error(c->visc_scratch, c->spos, c->sw, c->sphase, c->index, c->ros, c->cell_begin, n, c->grid, c->stencil, c->nbr_list, c->nbr_rows,
-                            c->nbr_max_rows, c->stream);
+                            c->nbr_max_rows, c->num_neighbors, c->device, c->stream);
     std::vector<float> err(4 * (size_t)n), vel(4 * (size_t)n), w(n);
     std::vector<int> sph(n);
     XCU(cudaMemcpyAsync(err.data(), c->visc_scratch, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kBlock) k_reorder(float4 *__restrict__ spos, f
                                                     u32 *__restrict__ chunk_lb, const u32 *__restrict__ hash,
                                                     const u32 *__restrict__ index, const float4 *__restrict__ pos,
                                                     const float *__restrict__ w, const int *__restrict__ phase, u32 n, u32 num_chunks,
-                                                    int gas_as_fluid) {
+                                                    int gas_as_fluid, int slot_in_w, float4 *__restrict__ exact_copy) {
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
     const bool ok = i < n;
     const int lane = threadIdx.x & 31;
@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(kBlock) k_reorder(float4 *__restrict__ spos, f
         const int ph = __ldg(phase + src);
         k1 = (h >> kChunkShift) + 1;
         k0 = i > 0 ? (hash[i - 1] >> kChunkShift) + 1 : 0;
-        st_stream4(spos + i, p);
+        if (exact_copy) st_stream4(exact_copy + i, p);
+        // the staged K6 stages candidates by TMA and takes a candidate's sorted slot from .w (nothing else reads spos.w)
+        st_stream4_wbits(spos + i, p.x, p.y, p.z, slot_in_w ? i : __float_as_uint(p.w));
         sw[i] = wi;
         // PS_FLAG_GAS: GAS particles take part in the density constraint — the neighbour kernels see them as fluid (the
         // reference's GPU kernels ignore phase 1 altogether; its CPU app solves gas as a PBF fluid, gasconstraint.cpp)
@@ -140,6 +142,13 @@ __global__ void __launch_bounds__(kBlock) k_emit_reference_tables(u32 *__restric
     cell_start[c] = e > b ? b : 0xffffffffu;
     cell_end[c] = e > b ? e : 0u;
 }
+__global__ void __launch_bounds__(kBlock) k_export_sorted_pos(float4 *__restrict__ out, const float4 *__restrict__ spos,
+                                                              const float4 *__restrict__ pos, const u32 *__restrict__ index, u32 n) {
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = spos[i];
+    out[i] = make_float4(p.x, p.y, p.z, pos[index[i]].w);
+}
 }  // namespace
 
 static inline u32 cdiv(u32 a, u32 b) { return (a + b - 1) / b; }
@@ -152,10 +161,15 @@ void ps_launch_calc_hash(u32 *hash, u32 *index, const float4 *pos, u32 n, GridDe
 size_t ps_chunk_table_elems(u32 num_cells) { return (size_t)cdiv(num_cells, kCellsPerBlock) + 1; }
 
 void ps_launch_reorder(float4 *spos, float *sw, int *sphase, u32 *chunk_lb, const u32 *hash, const u32 *index, const float4 *pos,
-                       const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s, bool gas_as_fluid) {
+                       const float *w, const int *phase, u32 n, u32 num_cells, cudaStream_t s, bool gas_as_fluid, bool slot_in_w, float4 *exact_copy) {
     if (!n) return;
     k_reorder<<<cdiv(n, kBlock), kBlock, 0, s>>>(spos, sw, sphase, chunk_lb, hash, index, pos, w, phase, n, cdiv(num_cells, kCellsPerBlock),
-                                                 gas_as_fluid ? 1 : 0);
+                                                 gas_as_fluid ? 1 : 0, slot_in_w ? 1 : 0, exact_copy);
+}
+
+void ps_launch_export_sorted_pos(float4 *out, const float4 *spos, const float4 *pos, const u32 *index, u32 n, cudaStream_t s) {
+    if (!n) return;
+    k_export_sorted_pos<<<cdiv(n, kBlock), kBlock, 0, s>>>(out, spos, pos, index, n);
 }
 
 void ps_launch_cell_begin(u32 *cell_begin, const u32 *hash, const u32 *chunk_lb, u32 n, u32 num_cells, cudaStream_t s) {

@@ -16,8 +16,10 @@
 //     so a warp's 32 loads fall in a handful of 128-byte lines).
 // These kernels are bound by FP32 issue and L1 bandwidth, not HBM: ~370 candidate tests and
 // ~140 interactions per particle against 36-64 compulsory bytes.
+#include <algorithm>
 #include <cuda/std/type_traits>
 #include "ps_common.cuh"
+#include "ps_fluid_lists.cuh"
 
 namespace {
 #ifndef PS_FBLOCK
@@ -31,12 +33,6 @@ namespace {
 #endif
 #ifndef PS_VOTE_PAIR
 #define PS_VOTE_PAIR 1
-#endif
-#ifndef PS_LIST_CS
-#define PS_LIST_CS 3  // bit 0: list rows are written with st.global.cs, bit 1: read with ld.global.cs (streaming: evict first)
-#endif
-#ifndef PS_K7_ROWS
-#define PS_K7_ROWS 6  // list rows K7 reads per trip = gathers in flight per lane; must divide PS_KQ (measured 2 / 4 / 6 / 12: 0.323 / 0.308 / 0.289 / 0.324 ms)
 #endif
 
 typedef unsigned long long u64;
@@ -84,49 +80,25 @@ __device__ __forceinline__ void for_each_candidate(const GridDesc &g, const Sten
 //   (3) accept/interact split: the distance test runs over all candidates, accepted neighbours (~65 % of them) are
 //       staged in a per-thread shared-memory queue of kQ slots and the expensive interaction body runs over full
 //       queues with (nearly) every lane active, instead of under a divergent branch;
-//   (4) K6 leaves the accepted neighbours behind as a compact list (below), so K7 does not search again.
 // All loops that contain a vote are warp-uniform.  Shared memory is carved out of the same 256 KB as L1, and the
 // candidate gather lives on L1 hits, so the per-thread footprint is kept small: kQ 4-byte queue slots (the neighbour's
 // sorted slot; its position is re-read, an L1 hit) + 2*(2*rad+1) list entries of (u32 begin, u16 length).
 //
-// Neighbour lists.  NOT the reference's (500 slots = 2 KB per particle, 4x over-allocated, strided by thread,
-// integration.cu:70): a warp's 32 lists are interleaved, row r of warp w is the 128-byte line
-// row[r * 32 + lane], and the warp appends in lock-step — every queue flush writes kQ full rows, lanes
-// with fewer accepted neighbours pad with kNoNeighbor.  Writes and K7's reads are therefore fully coalesced, ~170 rows
-// (21 KB per warp, 0.7 KB per particle) for ~140 neighbours.  Rows live in a POOL shared by all warps: a warp takes chunks
-// of kChunkRows rows from a bump allocator as it goes (its chunk ids sit beside its row count, kListRecord words per warp),
-// so memory follows the actual list lengths — a warp in a compressed layer on the floor may hold 4x the rows of one in the
-// bulk (lanes pad to the warp's longest list) without any per-warp reservation.  A warp that needs more than
-// kMaxChunks chunks, or finds the pool empty, marks itself overflowed and K7 re-walks the grid for it (k_solve_fluids
-// below), so the result never depends on the pool size.
+// The neighbour lists between K6 and K7 are written by the staged K6 (ps_fluid_staged.cu; format in ps_fluid_lists.cuh).  This walk
+// is the general path: every pass when no lists are kept (neighbor_list_rows = 0), and the later passes of the warps without a
+// list (kListOverflow: only when neighbor_list_rows is below the 500-neighbour cap).
 constexpr int kQ = PS_KQ;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr u32 kNoNeighbor = 0xffffffffu, kListOverflow = 0xffffffffu;
-constexpr u32 kChunkRows = PS_LIST_CHUNK_ROWS;         // 48: a multiple of kQ (a flush never straddles chunks) and of 4 (K7 reads 4 rows at a time)
-constexpr u32 kListRecord = PS_LIST_RECORD_WORDS;      // per warp: [rows used | overflow mark, chunk id 0, chunk id 1, ...]
-constexpr u32 kMaxChunks = kListRecord - 1;            // 31 chunks = 1488 rows
-static_assert(kChunkRows % PS_KQ == 0 && kChunkRows % 4 == 0 && PS_KQ % PS_K7_ROWS == 0, "chunk size");
-constexpr int kK7Rows = PS_K7_ROWS;
 typedef unsigned short u16;
 
 static inline size_t fluid_smem_bytes(int rad) {
     return (size_t)kQ * kBlock * sizeof(u32) + (size_t)2 * (2 * rad + 1) * kBlock * (sizeof(u32) + sizeof(u16));
 }
 
-struct NeighborListWriter {  // per-warp view of the list being written by K6 (pool == nullptr: no list)
-    u32 *pool;               // row pool; the bump allocator's counter sits at rec_base[-4] (see ps_launch_find_lambdas)
-    u32 *rec;                // this warp's record: rows, chunk ids
-    u32 *next;               // bump allocator
-    u32 *cur;                // this lane's column of the warp's current chunk: row r of the chunk at cur[r * 32]
-    u32 pool_chunks, rows;
-    bool overflow;
-};
-
 // body(rx, ry, rz, j) is called for every accepted neighbour, in the reference's traversal order.
 template <int RAD, class Body>
 __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const StencilDesc &st, const u32 *__restrict__ cell_begin,
-                                                     const float4 *__restrict__ spos, bool act, u32 i, float4 pi, u32 *smem,
-                                                     NeighborListWriter &nl, Body &&body) {
+                                                     const float4 *__restrict__ spos, bool act, u32 i, float4 pi, u32 *smem, Body &&body) {
     const int tid = threadIdx.x;
     const int rad = RAD ? RAD : st.rad;
     const int nseg = 2 * (2 * rad + 1);  // list capacity per slab: every row may wrap into two ranges
@@ -155,32 +127,6 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
     int cnt = 0;
 
     auto flush = [&]() {
-        if (nl.pool && !nl.overflow) {  // kQ full rows of the warp's interleaved list (uniform branches)
-            const u32 in_chunk = nl.rows % kChunkRows;
-            if (in_chunk == 0) {  // the warp needs its next chunk
-                const u32 ci = nl.rows / kChunkRows;
-                u32 chunk = 0xffffffffu;
-                if (ci < kMaxChunks) {
-                    if ((tid & 31) == 0) chunk = atomicAdd(nl.next, 1u);
-                    chunk = __shfl_sync(kFull, chunk, 0);
-                }
-                if (chunk >= nl.pool_chunks) {
-                    nl.overflow = true;
-                } else {
-                    if ((tid & 31) == 0) nl.rec[1 + ci] = chunk;
-                    nl.cur = nl.pool + (size_t)chunk * (kChunkRows * 32) + (tid & 31);
-                }
-            }
-            if (!nl.overflow) {
-#pragma unroll
-                for (int k = 0; k < kQ; k++) {
-                    const u32 v = k < cnt ? q[k][tid] : kNoNeighbor;
-                    if (PS_LIST_CS & 1) __stcs(nl.cur + (in_chunk + k) * 32, v);
-                    else nl.cur[(in_chunk + k) * 32] = v;
-                }
-                nl.rows += kQ;
-            }
-        }
 #if PS_FLUSH_PREFETCH
         // positions are re-read (L1 hits: the lines were gathered a few instructions ago) PS_FLUSH_PREFETCH at a time
         // before the interactions that use them, so that each lane has that many loads in flight
@@ -321,20 +267,23 @@ __device__ __forceinline__ u32 walk_fluid_neighbours(const GridDesc &g, const St
     return nn;
 }
 
-// ------------------------------------------------------------------ K6: lambda (+ neighbour lists) ------------------------------------------------------------------
+// ------------------------------------------------------------------ K6: lambda, grid-walking form ------------------------------------------------------------------
+// The lambda pass when no neighbour lists are kept; with lists the staged K6 (ps_fluid_staged.cu) is the whole pass.
 template <int RAD>
-// (forcing more resident CTAs through a register cap — 56, 48, 40 registers — makes K6 slower: 0.92 / 0.96 / 1.05 ms against
+// (forcing more resident CTAs through a register cap — 56, 48, 40 registers — makes the walk slower: 0.92 / 0.96 / 1.05 ms against
 // 0.78 ms at the compiler's 64; more warps only thrash L1, profiles/r1l)
 __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lambda, u32 *__restrict__ num_neighbors,
                                                          const float4 *__restrict__ spos, const float *__restrict__ sw,
                                                          const int *__restrict__ sphase, const u32 *__restrict__ index,
                                                          const u32 *__restrict__ cell_begin, const float *__restrict__ ros, u32 n,
                                                          u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g, StencilDesc st,
-                                                         int zero_nonfluid, u32 *__restrict__ nbr_list, u32 *__restrict__ nbr_rows, u32 max_rows) {
+                                                         int zero_nonfluid, u32 *__restrict__ pool, u32 *__restrict__ recs, u32 list_rows) {
     extern __shared__ u32 fluid_smem[];
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
     const u32 warp = i >> 5;
     const int lane = threadIdx.x & 31;
+    // per-warp list status (ps_fluid_lists.cuh); pool == nullptr: no lists are kept
+    u32 *rec = pool && (u64)warp * 32 < n ? recs + (size_t)warp * kListRecord : nullptr;
     bool act = i < n;
     u32 orig = 0;
     if (act) {
@@ -352,36 +301,34 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
     const bool ghost = act && orig >= n_owned;
     if (ghost && !(pi.x >= ghost_xmin && pi.x <= ghost_xmax)) act = false;
     if (!__any_sync(kFull, act)) {
-        if (nbr_rows && lane == 0 && (u64)warp * 32 < n) nbr_rows[(size_t)warp * kListRecord] = 0;
+        if (rec && lane == 0) *rec = 0;
         return;
     }
     if (!act) pi = make_float4(g.ox, g.oy, g.oz, 0.f);
     const float ro0 = act ? ros[orig] : 1.f;
     const float inv_ro0 = __fdividef(1.f, ro0);
     const float cs = -PS_SPIKY * inv_ro0;
-    NeighborListWriter nl;
-    nl.pool = nbr_list; nl.rec = nbr_rows ? nbr_rows + (size_t)warp * kListRecord : nullptr; nl.next = nbr_rows ? nbr_rows - 4 : nullptr; nl.cur = nullptr;
-    nl.pool_chunks = max_rows; nl.rows = 0; nl.overflow = false;
 
     float ro = 0.f, denom = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-    const u32 nn = walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, nl, [&](float rx, float ry, float rz, u32) {
-        const float r2 = rx * rx + ry * ry + rz * rz;
-        const float inv_r = rsqrtf(r2);
-        const float rlen = r2 * inv_r;  // sqrt(r2); r2 == 0 gives NaN here and is handled below
-        const float hm2 = PS_H2 - r2;
-        ro += hm2 * hm2 * hm2;
-        const float hm = PS_H - rlen;
-        // coincident particles contribute no gradient (the comparison is false for NaN as well)
-        const float c = rlen >= 0.0001f ? (cs * hm * hm) * inv_r : 0.f;  // spikyGrad / rho0 = r * c
-        gx += rx * c; gy += ry * c; gz += rz * c;
-        denom += (c * c) * r2;
+    // the lane's column of its warp's list region: entry k = the k-th accepted neighbour, appended as the queue is flushed
+    u32 *col = pool ? pool + (size_t)warp * list_rows * 32 + lane : nullptr;
+    u32 wr = 0;
+    bool lost = false;  // an accepted neighbour found no room in the column (only when neighbor_list_rows < 500)
+    const u32 nn = walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, [&](float rx, float ry, float rz, u32 j) {
+        ps_lambda_terms(rx, ry, rz, cs, ro, gx, gy, gz, denom);
+        if (col) {
+            if (wr < list_rows) __stcs(col + (size_t)wr * 32, j);
+            else lost = true;
+            wr++;
+        }
     });
-    if (nbr_rows && lane == 0) nl.rec[0] = nl.overflow ? kListOverflow : nl.rows;
+    if (rec) {
+        const bool ovf = __any_sync(kFull, lost);
+        if (lane == 0) *rec = ovf ? kListOverflow : 1u;
+    }
     if (!act) return;
     const float inv_w = __fdividef(1.f, sw[i]);
-    ro = (ro + PS_H6) * (PS_POLY6 * inv_w);  // + self term poly6(0) = POLY6 * H^6 (integration_kernel.cuh:589)
-    denom += gx * gx + gy * gy + gz * gz;
-    lambda[i] = -__fdividef(ro * inv_ro0 - 1.f, denom + PS_RELAX);
+    lambda[i] = ps_lambda_from_sums(ro, denom, gx, gy, gz, inv_w, inv_ro0);
     num_neighbors[i] = nn;
 }
 
@@ -390,23 +337,25 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
 struct DeltaP {
     float li, inv_den, dx, dy, dz;
     const float *__restrict__ lambda;
+    // explicit roundings (no compiler-chosen contraction): the list reader and the grid walk instantiate this in different kernels
+    // and must produce the same bits (tests/test_gpu_parity.py::test_neighbour_list_paths_agree_bit_for_bit)
     __device__ __forceinline__ void operator()(float rx, float ry, float rz, u32 j) {
         const float lj = __ldg(lambda + j);
-        const float r2 = rx * rx + ry * ry + rz * rz;
+        const float r2 = __fmaf_rn(rz, rz, __fmaf_rn(rx, rx, __fmul_rn(ry, ry)));
         const float inv_r = rsqrtf(r2);
-        const float rlen = r2 * inv_r;
-        const float hm2 = PS_H2 - r2;
-        const float qq = (hm2 * hm2 * hm2) * inv_den;
-        const float q2 = qq * qq;
-        const float s = li + lj + (-PS_K_P * q2 * q2);
+        const float rlen = __fmul_rn(r2, inv_r);
+        const float hm2 = __fsub_rn(PS_H2, r2);
+        const float qq = __fmul_rn(__fmul_rn(__fmul_rn(hm2, hm2), hm2), inv_den);
+        const float q2 = __fmul_rn(qq, qq);
+        const float s = __fmaf_rn(-PS_K_P, __fmul_rn(q2, q2), __fadd_rn(li, lj));
         if (rlen >= 0.0001f) {
-            const float hm = PS_H - rlen;
-            const float c = s * ((-PS_SPIKY * hm * hm) * inv_r);
-            dx += rx * c; dy += ry * c; dz += rz * c;
+            const float hm = __fsub_rn(PS_H, rlen);
+            const float c = __fmul_rn(s, __fmul_rn(__fmul_rn(__fmul_rn(-PS_SPIKY, hm), hm), inv_r));
+            dx = __fmaf_rn(rx, c, dx); dy = __fmaf_rn(ry, c, dy); dz = __fmaf_rn(rz, c, dz);
         } else {  // coincident: the reference nudges along +y, (0,EPS,0,0) * -SPIKY * (H-r)^2 (:625-626)
             const float rl = (r2 > 0.f) ? rlen : 0.f;
-            const float hm = PS_H - rl;
-            dy += s * (PS_EPS * -PS_SPIKY * hm * hm);
+            const float hm = __fsub_rn(PS_H, rl);
+            dy = __fmaf_rn(s, __fmul_rn(__fmul_rn(PS_EPS * -PS_SPIKY, hm), hm), dy);
         }
     }
 };
@@ -415,8 +364,7 @@ __device__ __forceinline__ float delta_p_inv_den() {
     return __fdividef(1.f, term2 * term2 * term2);
 }
 
-// K7 from the neighbour lists K6 left behind: no search, no shared memory; rows are read kK7Rows at a time so that as many
-// position / lambda gathers are in flight per lane.
+// K7 from the neighbour lists K6 left behind: no search, no shared memory (reader: ps_for_each_listed, ps_fluid_lists.cuh).
 #ifndef PS_K7_BLOCK
 #define PS_K7_BLOCK 256
 #endif
@@ -424,40 +372,23 @@ constexpr int kListBlock = PS_K7_BLOCK;
 __global__ void __launch_bounds__(kListBlock) k_solve_fluids_list(float4 *__restrict__ pos, const float *__restrict__ lambda,
                                                                   const float4 *__restrict__ spos, const int *__restrict__ sphase,
                                                                   const u32 *__restrict__ index, const float *__restrict__ ros,
-                                                                  const u32 *__restrict__ nbr_list, const u32 *__restrict__ nbr_rows, u32 max_rows,
-                                                                  u32 n, u32 n_owned, float omega) {
+                                                                  const u32 *__restrict__ nbr_list, const u32 *__restrict__ nbr_rows, u32 list_rows,
+                                                                  const u32 *__restrict__ num_neighbors, u32 n, u32 n_owned, float omega) {
     const u32 i = blockIdx.x * kListBlock + threadIdx.x;
     if (i >= n) return;
     const u32 warp = i >> 5;
-    const u32 *rec = nbr_rows + (size_t)warp * kListRecord;
-    const u32 rows = rec[0];
-    if (rows == kListOverflow || rows == 0) return;  // overflowed warps are redone by k_solve_fluids
+    const u32 status = nbr_rows[(size_t)warp * kListRecord];
+    if (status == kListOverflow || status == 0) return;  // warps without a list are redone by k_solve_fluids
     if (sphase[i] != PH_FLUID) return;
     const u32 orig = index[i];
     if (orig >= n_owned) return;
     const float4 pi = spos[i];
+    const u32 nn = num_neighbors[i];
     DeltaP f{lambda[i], delta_p_inv_den(), 0.f, 0.f, 0.f, lambda};
-    const u32 *L = nbr_list;
-    u32 nn = 0;
-    for (u32 r = 0, rc = 0; r < rows; r += kK7Rows, rc += kK7Rows) {  // rows is a multiple of kQ, which kK7Rows divides
-        if (rc == kChunkRows) rc = 0;
-        if (rc == 0) L = nbr_list + (size_t)__ldg(rec + 1 + r / kChunkRows) * (kChunkRows * 32) + (threadIdx.x & 31);
-        u32 j[kK7Rows];
-        float4 pj[kK7Rows];
-#pragma unroll
-        for (int k = 0; k < kK7Rows; k++) j[k] = (PS_LIST_CS & 2) ? __ldcs(L + (rc + k) * 32) : __ldg(L + (rc + k) * 32);
-#pragma unroll
-        for (int k = 0; k < kK7Rows; k++) pj[k] = __ldg(spos + (j[k] != kNoNeighbor ? j[k] : i));
-#pragma unroll
-        for (int k = 0; k < kK7Rows; k++)
-            if (j[k] != kNoNeighbor) {
-                f(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z, j[k]);
-                nn++;
-            }
-    }
-    const float inv_div = __fdividef(omega, ros[orig] + (float)nn);
+    ps_for_each_listed(ps_list_column(nbr_list, warp, list_rows, threadIdx.x & 31), nn, i, pi, spos, f);
+    const float inv_div = __fdividef(omega, __fadd_rn(ros[orig], (float)nn));
     float4 P = pos[orig];
-    P.x += f.dx * inv_div; P.y += f.dy * inv_div; P.z += f.dz * inv_div;
+    P.x = __fmaf_rn(f.dx, inv_div, P.x); P.y = __fmaf_rn(f.dy, inv_div, P.y); P.z = __fmaf_rn(f.dz, inv_div, P.z);
     pos[orig] = P;
 }
 
@@ -480,13 +411,11 @@ __global__ void __launch_bounds__(kBlock) k_solve_fluids(float4 *__restrict__ po
     if (!__any_sync(kFull, act)) return;
     const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
     DeltaP f{act ? lambda[i] : 0.f, delta_p_inv_den(), 0.f, 0.f, 0.f, lambda};
-    NeighborListWriter nl;
-    nl.pool = nullptr; nl.rec = nullptr; nl.next = nullptr; nl.cur = nullptr; nl.pool_chunks = 0; nl.rows = 0; nl.overflow = false;
-    const u32 nn = walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, nl, f);
+    const u32 nn = walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, f);
     if (!act) return;
-    const float inv_div = __fdividef(omega, ros[orig] + (float)nn);
+    const float inv_div = __fdividef(omega, __fadd_rn(ros[orig], (float)nn));
     float4 P = pos[orig];
-    P.x += f.dx * inv_div; P.y += f.dy * inv_div; P.z += f.dz * inv_div;
+    P.x = __fmaf_rn(f.dx, inv_div, P.x); P.y = __fmaf_rn(f.dy, inv_div, P.y); P.z = __fmaf_rn(f.dz, inv_div, P.z);
     pos[orig] = P;
 }
 
@@ -571,31 +500,19 @@ struct DensityErrorOp {
 template <class Op>
 __global__ void __launch_bounds__(kListBlock) k_fluid_pass_list(Op op, const float4 *__restrict__ spos, const int *__restrict__ sphase,
                                                                 const u32 *__restrict__ index, const u32 *__restrict__ nbr_list,
-                                                                const u32 *__restrict__ nbr_rows, u32 max_rows, u32 n) {
+                                                                const u32 *__restrict__ nbr_rows, u32 list_rows,
+                                                                const u32 *__restrict__ num_neighbors, u32 n) {
     const u32 i = blockIdx.x * kListBlock + threadIdx.x;
     if (i >= n) return;
     const u32 warp = i >> 5;
-    const u32 *rec = nbr_rows + (size_t)warp * kListRecord;
-    const u32 rows = rec[0];
-    if (rows == kListOverflow) return;  // redone by k_fluid_pass_walk
+    const u32 status = nbr_rows[(size_t)warp * kListRecord];
+    if (status == kListOverflow) return;  // redone by k_fluid_pass_walk
     if (sphase[i] != PH_FLUID) return;
     const u32 orig = index[i];
     const float4 pi = spos[i];
     op.begin(i, orig);
-    const u32 *L = nbr_list;
-    for (u32 r = 0, rc = 0; r < rows; r += 4, rc += 4) {
-        if (rc == kChunkRows) rc = 0;
-        if (rc == 0) L = nbr_list + (size_t)__ldg(rec + 1 + r / kChunkRows) * (kChunkRows * 32) + (threadIdx.x & 31);
-        u32 j[4];
-        float4 pj[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) j[k] = __ldg(L + (rc + k) * 32);
-#pragma unroll
-        for (int k = 0; k < 4; k++) pj[k] = __ldg(spos + (j[k] != kNoNeighbor ? j[k] : i));
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (j[k] != kNoNeighbor) op(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z, j[k]);
-    }
+    // status 0: K6 found no active fluid particle in the warp (ghosts outside the lambda range): nothing listed
+    if (status) ps_for_each_listed(ps_list_column(nbr_list, warp, list_rows, threadIdx.x & 31), num_neighbors[i], i, pi, spos, op);
     op.end(i, orig);
 }
 template <int RAD, class Op>
@@ -610,9 +527,7 @@ __global__ void __launch_bounds__(kBlock) k_fluid_pass_walk(Op op, const float4 
     const u32 orig = act ? index[i] : 0u;
     const float4 pi = act ? spos[i] : make_float4(g.ox, g.oy, g.oz, 0.f);
     if (act) op.begin(i, orig);
-    NeighborListWriter nl;
-    nl.pool = nullptr; nl.rec = nullptr; nl.next = nullptr; nl.cur = nullptr; nl.pool_chunks = 0; nl.rows = 0; nl.overflow = false;
-    walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, nl, op);
+    walk_fluid_neighbours<RAD>(g, st, cell_begin, spos, act, i, pi, fluid_smem, op);
     if (act) op.end(i, orig);
 }
 __global__ void __launch_bounds__(256) k_apply_dv(float4 *__restrict__ vel, const float4 *__restrict__ dv, const int *__restrict__ sphase,
@@ -780,6 +695,16 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
 
 static inline u32 cdiv(u32 a, u32 b) { return (a + b - 1) / b; }
 
+// The opt-in to > 48 KB of dynamic shared memory (generic stencil radius) is a per-device attribute: once for every device this
+// process drives (several contexts on several GPUs may live in one process).
+static void ps_optin_smem(int device) {
+    static bool opted[64] = {};
+    if (device < 0 || device >= 64 || opted[device]) return;
+    cudaFuncSetAttribute(k_find_lambdas<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
+    cudaFuncSetAttribute(k_solve_fluids<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
+    opted[device] = true;
+}
+
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                        const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, const u32 *adj_off,
                        const u32 *adj, const float4 *sdf_world, cudaStream_t s) {
@@ -790,41 +715,53 @@ void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, cons
     k_collide<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, prev, spos, sw, sphase, index, cell_begin, num_neighbors, n, n_owned, g, st, radius, adj_off, adj, sdf_world);
 }
 
-// pool of list rows for `capacity` particles at `rows_per_warp` rows reserved per warp on average
-u32 ps_neighbor_pool_chunks(u64 capacity, u32 rows_per_warp) { return (u32)(((capacity + 31) / 32) * rows_per_warp / kChunkRows); }
-size_t ps_neighbor_list_elems(u64 capacity, u32 rows_per_warp) { return (size_t)ps_neighbor_pool_chunks(capacity, rows_per_warp) * kChunkRows * 32; }
-// per-warp records (kListRecord words each) behind a 4-word header whose first word is the pool's bump allocator;
-// the kernels are handed the address of the first record
+// list regions for `capacity` particles (rows_per_warp rows of 32 entries per warp) + the staged K6's dump region + the read-ahead
+// of the list readers
+static size_t list_region_elems(u64 capacity, u32 rows_per_warp) { return (size_t)((capacity + 31) / 32) * rows_per_warp * 32; }
+size_t ps_neighbor_list_elems(u64 capacity, u32 rows_per_warp) {
+    return list_region_elems(capacity, rows_per_warp) + ((size_t)ps_staged_dump_rows() + PS_LIST_READ_ROWS) * 32;
+}
+// per-warp status words behind a 4-word header (kept for alignment); the kernels are handed the address of the first word
 size_t ps_neighbor_record_elems(u64 capacity) { return 4 + (size_t)((capacity + 31) / 32) * kListRecord; }
 
-void ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
-                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
-                            const StencilDesc &st, bool zero_nonfluid, u32 *nbr_list, u32 *nbr_rows, u32 max_rows, cudaStream_t s) {
-    if (!n) return;
+// K6.  With lists (nbr_list / nbr_rows / list_rows != 0) the pass also leaves the neighbour lists (ps_fluid_lists.cuh) for K7 and the
+// other list readers; else the caller passes nbr_list = nullptr to those as well.  staged: the TMA-staged kernel (ps_fluid_staged.cu;
+// needs lists and slot_in_w: spos[j].w = bit pattern of j, ps_launch_reorder(..., slot_in_w = true)) instead of the grid walk.
+u32 ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
+                           const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
+                           const StencilDesc &st, bool zero_nonfluid, u32 *nbr_list, u32 *nbr_rows, u32 list_rows, u64 capacity, bool slot_in_w,
+                           bool staged, int device, cudaStream_t s) {
+    if (!n) return 0;
+    const bool lists = nbr_list && nbr_rows && list_rows && n <= capacity;
+    if (lists && staged && slot_in_w) {
+        ps_launch_find_lambdas_staged(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin, ghost_xmax, g, st,
+                                      zero_nonfluid, nbr_list, nbr_rows, list_rows, list_region_elems(capacity, list_rows), device, s);
+        return 1;
+    }
     const size_t sm = fluid_smem_bytes(st.rad);
-    static const cudaError_t optin = cudaFuncSetAttribute(k_find_lambdas<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
-    (void)optin;
-    if (!nbr_list) nbr_rows = nullptr;
-    if (nbr_rows) cudaMemsetAsync(nbr_rows - 4, 0, sizeof(u32), s);  // empty the row pool
+    ps_optin_smem(device);
+    u32 *pool = lists ? nbr_list : nullptr;
     if (st.rad == 4)  // the reference's configuration (H = 2, cell = 2r = 0.5): stencil loops fully unrolled
         k_find_lambdas<4><<<cdiv(n, kBlock), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin,
-                                                             ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, max_rows);
+                                                             ghost_xmax, g, st, zero_nonfluid ? 1 : 0, pool, nbr_rows, list_rows);
     else
         k_find_lambdas<0><<<cdiv(n, kBlock), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin,
-                                                             ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, max_rows);
+                                                             ghost_xmax, g, st, zero_nonfluid ? 1 : 0, pool, nbr_rows, list_rows);
+    return 1;
 }
 
-// nbr_list != nullptr: K7 from the lists K6 wrote, then the grid walk for overflowed warps only; else the grid walk for all
+// nbr_list != nullptr: K7 from the lists K6 wrote, then the grid walk for the warps without a list; else the grid walk for all
 u32 ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
-                           const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s) {
+                           const u32 *nbr_list, const u32 *nbr_rows, u32 list_rows, const u32 *num_neighbors, int device, cudaStream_t s) {
     if (!n) return 0;
     const size_t sm = fluid_smem_bytes(st.rad);
-    static const cudaError_t optin = cudaFuncSetAttribute(k_solve_fluids<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
-    (void)optin;
+    ps_optin_smem(device);
     u32 launches = 1;
-    if (nbr_list) {
-        k_solve_fluids_list<<<cdiv(n, kListBlock), kListBlock, 0, s>>>(pos, lambda, spos, sphase, index, ros, nbr_list, nbr_rows, max_rows, n, n_owned, omega);
+    if (nbr_list && nbr_rows && list_rows) {
+        k_solve_fluids_list<<<cdiv(n, kListBlock), kListBlock, 0, s>>>(pos, lambda, spos, sphase, index, ros, nbr_list, nbr_rows, list_rows, num_neighbors, n,
+                                                                       n_owned, omega);
+        if (list_rows >= PS_MAX_NEIGHBORS) return 1;  // every list fits its region: no warp is left for the grid walk
         launches++;
     } else {
         nbr_rows = nullptr;
@@ -838,13 +775,18 @@ u32 ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos,
 
 template <class Op>
 static u32 launch_fluid_pass(Op op, const float4 *spos, const int *sphase, const u32 *index, const u32 *cell_begin, u32 n, GridDesc g,
-                             const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s) {
+                             const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 list_rows, const u32 *num_neighbors, int device,
+                             cudaStream_t s) {
     const size_t sm = fluid_smem_bytes(st.rad);
-    static const cudaError_t optin = cudaFuncSetAttribute(k_fluid_pass_walk<0, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
-    (void)optin;
+    static bool opted[64] = {};  // per device: the opt-in to > 48 KB of dynamic shared memory for the generic-radius walk
+    if (device >= 0 && device < 64 && !opted[device]) {
+        cudaFuncSetAttribute(k_fluid_pass_walk<0, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
+        opted[device] = true;
+    }
     u32 launches = 1;
-    if (nbr_list) {
-        k_fluid_pass_list<Op><<<cdiv(n, kListBlock), kListBlock, 0, s>>>(op, spos, sphase, index, nbr_list, nbr_rows, max_rows, n);
+    if (nbr_list && nbr_rows && list_rows) {
+        k_fluid_pass_list<Op><<<cdiv(n, kListBlock), kListBlock, 0, s>>>(op, spos, sphase, index, nbr_list, nbr_rows, list_rows, num_neighbors, n);
+        if (list_rows >= PS_MAX_NEIGHBORS) return 1;
         launches++;
     } else {
         nbr_rows = nullptr;
@@ -856,27 +798,28 @@ static u32 launch_fluid_pass(Op op, const float4 *spos, const int *sphase, const
 
 // XSPH viscosity + vorticity confinement (K13): vel += dv, see the kernels.  scratch: float4[2n] (omega | dv by sorted slot).
 u32 ps_launch_viscosity(float4 *vel, float4 *scratch, const float4 *spos, const int *sphase, const u32 *index, const u32 *cell_begin, u32 n, GridDesc g,
-                        const StencilDesc &st, float c_xsph, float vorticity_eps, float dt, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows,
-                        cudaStream_t s) {
+                        const StencilDesc &st, float c_xsph, float vorticity_eps, float dt, const u32 *nbr_list, const u32 *nbr_rows, u32 list_rows,
+                        const u32 *num_neighbors, int device, cudaStream_t s) {
     if (!n) return 0;
     float4 *omega = scratch, *dv = scratch + n;
     u32 launches = 0;
     if (vorticity_eps != 0.f) {
         OmegaOp o1{vel, index, omega};
-        launches += launch_fluid_pass(o1, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, max_rows, s);
+        launches += launch_fluid_pass(o1, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, list_rows, num_neighbors, device, s);
     } else {
         cudaMemsetAsync(omega, 0, (size_t)n * sizeof(float4), s);
     }
     ViscosityOp o2{vel, index, omega, dv, c_xsph, vorticity_eps * dt};
-    launches += launch_fluid_pass(o2, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, max_rows, s);
+    launches += launch_fluid_pass(o2, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, list_rows, num_neighbors, device, s);
     k_apply_dv<<<cdiv(n, 256), 256, 0, s>>>(vel, dv, sphase, index, n);
     return launches + 1;
 }
 
 // |rho / rho0 - 1| per fluid particle into scratch[i].x (sorted slot), on the neighbour structure K6 just built
 u32 ps_launch_density_error(float4 *scratch, const float4 *spos, const float *sw, const int *sphase, const u32 *index, const float *ros, const u32 *cell_begin,
-                            u32 n, GridDesc g, const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 max_rows, cudaStream_t s) {
+                            u32 n, GridDesc g, const StencilDesc &st, const u32 *nbr_list, const u32 *nbr_rows, u32 list_rows, const u32 *num_neighbors,
+                            int device, cudaStream_t s) {
     if (!n) return 0;
     DensityErrorOp op{sw, ros, scratch};
-    return launch_fluid_pass(op, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, max_rows, s);
+    return launch_fluid_pass(op, spos, sphase, index, cell_begin, n, g, st, nbr_list, nbr_rows, list_rows, num_neighbors, device, s);
 }

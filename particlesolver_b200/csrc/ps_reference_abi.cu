@@ -110,8 +110,11 @@ void reorderDataAndFindCellStart(uint *cellStart, uint *cellEnd, float *sortedPo
                                  uint *index, float *oldPos, uint n, uint numCells) {
     PsCtx *c = ctx();
     if (numCells != c->num_cells) { ps_set_error("numCells %u does not match setParameters' grid (%u)", numCells, c->num_cells); die("reorderDataAndFindCellStart"); }
-    ps_launch_reorder((float4 *)sortedPos, sortedW, sortedPhase, c->chunk_lb, hash, index, (const float4 *)oldPos, c->w, c->phase, n, numCells,
-                      c->stream);
+    // the caller's sortedPos receives the reference's exact float4 copies; the fluid kernels work from the context's own sorted
+    // positions, whose .w carries the sorted slot (what the staged K6 wants, ps_fluid_staged.cu)
+    ck(ps_ctx_ensure_capacity(c, n), "reorderDataAndFindCellStart");
+    ps_launch_reorder(c->spos, sortedW, sortedPhase, c->chunk_lb, hash, index, (const float4 *)oldPos, c->w, c->phase, n, numCells,
+                      c->stream, false, true, (float4 *)sortedPos);
     if (n) {
         ps_launch_cell_begin(c->cell_begin, hash, c->chunk_lb, n, numCells, c->stream);
         // the caller's tables in the reference's format (cellEnd of empty cells: 0; the reference leaves them stale)
@@ -138,10 +141,11 @@ void solveFluids(float *sortedPos, float *sortedW, int *sortedPhase, uint *index
     (void)cellEnd;
     PsCtx *c = ctx();
     need_dense(cellStart, numCells, "solveFluids");
-    ps_launch_find_lambdas(c->lambda, c->num_neighbors, (const float4 *)sortedPos, sortedW, sortedPhase, index, c->cell_begin, c->ros, n, n,
-                           -3.0e38f, 3.0e38f, c->grid, c->stencil, false, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
-    ps_launch_solve_fluids((float4 *)particles, c->lambda, (const float4 *)sortedPos, sortedPhase, index, c->cell_begin, c->ros, n, n, c->grid,
-                           c->stencil, 1.0f, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->stream);
+    (void)sortedPos;  // == the context's sorted positions up to .w (see reorderDataAndFindCellStart)
+    ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, sortedW, sortedPhase, index, c->cell_begin, c->ros, n, n,
+                           -3.0e38f, 3.0e38f, c->grid, c->stencil, false, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->capacity, true, false, c->device, c->stream);
+    ps_launch_solve_fluids((float4 *)particles, c->lambda, c->spos, sortedPhase, index, c->cell_begin, c->ros, n, n, c->grid,
+                           c->stencil, 1.0f, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->num_neighbors, c->device, c->stream);
     ck_launch("solveFluids");
 }
 

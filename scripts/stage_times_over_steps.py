@@ -14,6 +14,6 @@ for target in (3, 10, 20, 30, 40, 60, 90, 120):
     st, ln = sol.step_profiled(1 / 60); done += 1
     nn = sol.download(psb.ARR_NUM_NEIGHBORS)
     y = sol.download(psb.ARR_POS)[:, 1]
-    rows = sol.download(psb.ARR_NEIGHBOR_ROWS).reshape(-1, 32)[:, 0]
+    rows = sol.download(psb.ARR_NEIGHBOR_ROWS)
     ovf = int((rows == 0xFFFFFFFF).sum()); ok = rows[rows != 0xFFFFFFFF]
     print(f"step {done:4d}: lambda {st['lambda'] / 5:.3f} delta_p {st['delta_p'] / 5:.3f} sort {st['sort'] / 5:.3f} total {sum(st.values()):.2f} ms | neighbours mean {nn.mean():.1f} max {nn.max()} | y min {y.min():.2f} | rows mean {ok.mean():.0f} p99 {np.percentile(ok, 99):.0f} max {ok.max()} overflowed warps {ovf} | padding {(ok.sum() * 32.0) / max(nn.sum(), 1):.2f}x")

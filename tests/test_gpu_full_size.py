@@ -70,7 +70,7 @@ def test_interior_neighbour_counts_match_the_oracle_lattice():
     # the jittered lattice (+-0.0025) leaves every interior particle the same neighbour shell up to pairs at |r| = H +- jitter
     assert abs(nn[interior].mean() - n_small[interior_small].mean()) < 0.5
     assert set(np.unique(nn[interior])) <= set(range(int(n_small[interior_small].min()) - 4, int(n_small[interior_small].max()) + 5))
-    rows = sol.download(psb.ARR_NEIGHBOR_ROWS).reshape(-1, 32)[:, 0]
+    rows = sol.download(psb.ARR_NEIGHBOR_ROWS)
     assert not np.any(rows == 0xFFFFFFFF)                             # no warp overflowed its neighbour list
     ps.close()
 

@@ -214,7 +214,8 @@ def _random_fluid(n, box, seed, lo=(0.0, 0.0, 0.0)):
     (0.4, 64, (-5.0, 1.0, -5.0)),     # non-power-of-two cell: approximate divide in the cell assignment, radius 5
     (0.25, 128, (1.0, 1.0, 1.0)),     # radius 8 (largest supported)
 ])
-def test_fluid_walk_other_cell_sizes_and_wrap(cell, grid, lo):
+@pytest.mark.parametrize("flags", [0, psb.FLAG_STAGED_LAMBDA], ids=["walk", "staged"])
+def test_fluid_walk_other_cell_sizes_and_wrap(cell, grid, lo, flags):
     """K6/K7 against the oracle on a jittered random fluid for stencil radii other than the reference's 4, for a
     non-power-of-two cell size and for rows that wrap around the grid: identical neighbour counts (the per-particle
     pruning must never drop a neighbour), lambda and positions within tolerance."""
@@ -222,6 +223,7 @@ def test_fluid_walk_other_cell_sizes_and_wrap(cell, grid, lo):
     p = psb.default_params()
     p.grid_size[:] = (grid, grid, grid)
     p.cell_size[:] = (cell, cell, cell)
+    p.flags |= flags
     sol = psb.Solver(p, max_particles=n)
     pos = _random_fluid(n, (10.0, 6.0, 10.0), seed=int(cell * 100), lo=lo)  # ~10 particles per unit^3 -> ~330 neighbours
     sol.append(pos, np.zeros((n, 4), np.float32), np.ones(n, np.float32), np.full(n, 8.0, np.float32), np.zeros(n, np.int32))
@@ -236,10 +238,12 @@ def test_fluid_walk_other_cell_sizes_and_wrap(cell, grid, lo):
     sol.close()
 
 
-def test_fluid_neighbour_cap_500():
+@pytest.mark.parametrize("flags", [0, psb.FLAG_STAGED_LAMBDA], ids=["walk", "staged"])
+def test_fluid_neighbour_cap_500(flags):
     """More than 500 particles inside H: the first 500 in the reference's traversal order count (integration_kernel.cuh:508-513)."""
     n = 3000
     p = psb.default_params()
+    p.flags |= flags
     sol = psb.Solver(p, max_particles=n)
     pos = _random_fluid(n, (3.0, 3.0, 3.0), seed=5, lo=(2.0, 2.0, 2.0))  # ~110 per unit^3 -> thousands within H
     sol.append(pos, np.zeros((n, 4), np.float32), np.ones(n, np.float32), np.full(n, 100.0, np.float32), np.zeros(n, np.int32))
@@ -254,19 +258,26 @@ def test_fluid_neighbour_cap_500():
 
 
 def test_neighbour_list_paths_agree_bit_for_bit():
-    """K7 from K6's neighbour lists, K7 re-walking the grid (no lists kept), and the overflow fallback (lists too short for
-    every warp) take the same neighbours in the same order: identical bits."""
+    """K6 by the grid walk or by the TMA-staged kernel (PS_FLAG_STAGED_LAMBDA; its CTAs with sparse rows take its in-kernel
+    fallback), K7 from K6's neighbour lists, K7 re-walking the grid (no lists kept) and the overflow fallback (lists too short for
+    every warp) take the same neighbours in the same order with the same roundings: identical bits."""
     results = []
-    for rows in (256, 0, 8, 64):
+    for rows, flags in ((512, 0), (0, 0), (8, 0), (96, 0), (512, psb.FLAG_STAGED_LAMBDA), (96, psb.FLAG_STAGED_LAMBDA)):
         ps = psb.ParticleSystem.scene("3")  # two fluids, walls
         sol = ps.solver
         p = sol.params
         p.neighbor_list_rows = rows
+        p.flags |= flags
         sol.set_params(p)
         for _ in range(2):
             ps.update(DT)
         results.append((sol.download(psb.ARR_POS).copy(), sol.download(psb.ARR_LAMBDA).copy(), sol.download(psb.ARR_NUM_NEIGHBORS).copy()))
+        status = sol.download(psb.ARR_NEIGHBOR_ROWS)
+        if rows >= 500:
+            assert not np.any(status == 0xFFFFFFFF)       # every list fits its region
+        elif rows:
+            assert np.any(status == 0xFFFFFFFF)           # lists too short: those warps' delta-p pass walks the grid again
         ps.close()
     for pos, lam, nn in results[1:]:
         assert np.array_equal(nn, results[0][2]) and np.array_equal(lam, results[0][1]) and np.array_equal(pos, results[0][0])
-    assert results[0][2].max() > 64  # 64 rows cannot hold every warp's lists: that run mixed list warps and fallback warps
+    assert results[0][2].max() > 96 > results[0][2].min()  # 96 rows: some warps keep their lists, some do not
