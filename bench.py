@@ -16,14 +16,19 @@ BASELINE.json configs[4], SURVEY.md §8 C5.  --particles scales the block in x (
 Own arm (default):
   value     whole-job particle-steps/s, state resident in HBM, K steps timed with CUDA events on the solver's
             stream (CUDA-graph replay), max over ranks.
-  e2e       same metric through the public host API with HOST buffers: every step uploads positions+velocities
-            from pinned host memory, steps, and downloads positions+velocities.
+  e2e       same metric through the public C ABI call ps_step_streamed with HOST buffers: every step takes
+            positions+velocities from pinned host memory and delivers positions+velocities to pinned host memory
+            (32 B/particle each way); the library overlaps the transfers with the neighbouring steps' solver work.
+  long_run  200 further steps of the same scene (the blob reaches the floor and spreads), mean / max ms per step.
+  c5_8M_1gpu  the multi-GPU workload's per-rank share (8M-particle dam break) on this one GPU: the weak-scaling base,
+            and the streaming kernels' HBM fractions at a size far beyond the L2.
   roofline  dominant kernel (largest share of the step) against the measured HBM peak, from per-stage CUDA
             events of an instrumented (eager) pass over the same state.
   cpu_baseline  the oracle port (oracle/gpu_step_oracle.c, OpenMP) on a bounded sample of the workload.
-Reference arm (--impl reference): the reference algorithm on the host cores — the oracle port with all threads
-on a bounded sample (the reference's CPU app is 2-D only; its GPU sources need a GPU), plus, as extra fields, the
-reference's own unmodified CPU solver (oracle/_ref/ref_cpu, scene 6) when that binary is present.
+Reference arm (--impl reference): the reference algorithm on the host cores — the oracle port with all threads on the
+full 1M-particle workload for a bounded number of steps (the reference's CPU app is 2-D only) — plus, as extra fields,
+`reference_gpu_solver` = the reference's own unmodified CUDA sources built for sm_100a (oracle/_ref/ref_gpu) on the same
+scene and the same GPU, and `reference_cpu_solver` = its unmodified 2-D CPU solver on scene 6.
 """
 import argparse
 import json
@@ -44,7 +49,9 @@ ITERS = 5
 
 # algorithmic (compulsory) HBM bytes per particle per launch of each stage — SURVEY.md §8(d) / BASELINE.md §5.
 # sort: 4 + 16 P with P = radix passes (3 for 2^24 cells); cell_table: 4 B per CELL (one write of the dense table) + 4 B per key.
-STAGE_BYTES = {"predict": 64, "hash": 24, "sort": 52, "reorder": 56, "contacts": 60, "lambda": 36, "delta_p": 64, "world": 52,
+# world: 16 B for a particle away from the walls (one float4 load, early exit), 52 B for one that is moved; interior particles are
+# all but a boundary layer, so the line charges 16 B (the conservative figure).
+STAGE_BYTES = {"predict": 64, "hash": 24, "sort": 52, "reorder": 56, "contacts": 60, "lambda": 36, "delta_p": 64, "world": 16,
                "velocity": 48}
 
 
@@ -59,45 +66,72 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  nvidia-smi needs a few hundred
+    milliseconds to start, more than a 20-step timed region lasts, so the sampler is started BEFORE the warm-up (start), told
+    when the timed region begins and ends (mark_begin / mark_end), and reports the samples that fell inside it; when none did
+    (a region shorter than one sampling period), the samples taken under the same load just before it (warm-up) are reported
+    and `window` says so."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+        def parse(rows):
+            sm, mx, reasons = [], None, set()
+            for _t, r in rows:
+                f = [x.strip() for x in r.split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx = float(f[1])
+                except ValueError:
+                    continue
+                for nme, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            return sm, mx, reasons
+        tb = self.t_begin if self.t_begin is not None else 0.0
+        te = self.t_end if self.t_end is not None else float("inf")
+        inside = [r for r in self.rows if tb <= r[0] <= te + 0.02]
+        window = "timed region"
+        if not parse(inside)[0]:
+            inside = [r for r in self.rows if r[0] <= te + 0.02][-5:]
+            window = "warm-up under the same load, immediately before the timed region (the region is shorter than one sampling period)"
+        sm, mx, reasons = parse(inside)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 def c3_sample(side, seed=1234):
@@ -170,26 +204,64 @@ def time_c1_gpu(ticks=200):
         return {"error": str(e)}
 
 
+def time_reference_gpu_solver(steps, warmup):
+    """The reference's own UNMODIFIED CUDA sources (gpu/src/cuda/*.cu + particlesystem.cpp compiled for sm_100a with a
+    texture-reference shim, oracle/_ref/ref_gpu; the binary travels with the snapshot) on the c3 workload at the full
+    1,000,000 particles, `warmup` untimed + `steps` timed ParticleSystem::update calls, CUDA events around each."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_gpu is not in this snapshot"}
+    import shutil
+    import tempfile
+    out = tempfile.mkdtemp(prefix="ref_gpu_")
+    try:
+        r = subprocess.run([exe, "--scene", "c3", "--grid", str(GRID), "--side", str(SIDE), "--max", str(SIDE ** 3 + 4096), "--iters", str(ITERS),
+                            "--mode", "whole", "--steps", str(steps + warmup), "--warmup", str(warmup), "--dump-every", "0", "--out", out],
+                           capture_output=True, text=True, timeout=600)
+        for line in r.stdout.splitlines():
+            if line.startswith("{"):
+                j = json.loads(line)
+                med = j.get("ms_per_step_median", j["ms_per_step"])
+                return {"ms_per_step": med, "value": j["n"] / (med * 1e-3), "unit": "particle-steps/s", "n": j["n"],
+                        "steps_timed": j["steps_timed"], "warmup": warmup, "statistic": "median over the timed steps (the reference's step time has a "
+                        "heavy tail: per-call cudaMalloc / thrust temporaries; mean, min and max beside it)",
+                        "ms_per_step_mean": j["ms_per_step"], "ms_per_step_min": j.get("ms_per_step_min"), "ms_per_step_max": j.get("ms_per_step_max"),
+                        "what": "reference gpu/src CUDA sources, unmodified, built for sm_100a (oracle/Makefile), same scene script, same GPU"}
+        return {"unavailable": "ref_gpu printed no timing line (no GPU on this box?)", "rc": r.returncode, "stderr": r.stderr[-300:]}
+    except Exception as e:
+        return {"unavailable": str(e)}
+    finally:
+        shutil.rmtree(out, ignore_errors=True)
+
+
 def run_reference(args, rank, world):
+    """--impl reference.  The reference has no CPU implementation of its 3-D GPU step (its CPU app is a 2-D solver), so the line's
+    value is the C/OpenMP restatement of that step (oracle/gpu_step_oracle.c, pinned to the reference's golden dumps) on ALL host
+    threads at the workload's full size (c3: 1,000,000 particles) for a bounded number of steps; `steps` is what was timed.  Beside
+    it, when the box has a GPU: `reference_gpu_solver` = the reference's own unmodified CUDA code on the same scene and GPU (the
+    number this library is built to beat), and `reference_cpu_solver` = its unmodified 2-D CPU solver on scene 6."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    side = 58  # 195,112 particles: a few seconds per step on a multi-core host
-    steps = max(1, min(args.steps, 3))
-    for _ in range(max(0, min(args.warmup, 1))):
-        pass  # time_oracle_port warms up once itself
     c5 = args.gpus > 1 or args.workload == "c5"   # our arm runs the slab-decomposed dam break on several GPUs
-    v, n, sec = time_oracle_port(side, steps, rho0=C5_RHO0 if c5 else 1.5)
-    line = {"metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    # c3 at full size: ~2-4 s per step on the box's cores; c5: a 58^3 block of the dam-break lattice (64M does not fit a few minutes)
+    side = 58 if c5 else SIDE
+    steps = max(1, min(args.steps, 3))
+    v, n, sec = time_oracle_port(side, steps, rho0=C5_RHO0 if c5 else 1.5)   # (one untimed warm-up step inside)
+    line = {"metric": "particle-steps/sec", "value": v, "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
             "config": {"workload": ("c5: synthetic PBF dam break (lattice spacing 2.5 r, rho0 4.1), 5 solver iterations, dt=1/60" if c5 else
-                                    "c3: reference GPU scene 7 scaled, PBF fluid, 5 solver iterations, dt=1/60, 256^3 grid"),
-                       "sample": f"{side}^3 = {n} particles of the workload's lattice (same spacing, density, parameters)", "steps_timed": steps},
+                                    "c3: reference GPU scene 7 scaled to 100^3 = 1,000,000 PBF particles, 256^3 grid, 5 solver iterations, dt=1/60"),
+                       "sample": (f"{side}^3 = {n} particles of the workload's lattice (same spacing, density, parameters)" if c5 else
+                                  f"the full workload: {n} particles"), "steps_timed": steps},
             "cpu_baseline": {"value": v, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-                             "sample": f"oracle/gpu_step_oracle.c (C restatement of the reference GPU step, OpenMP) on {n} particles x {steps} steps"},
+                             "sample": f"oracle/gpu_step_oracle.c (C restatement of the reference GPU step, OpenMP, {cores} threads) on {n} particles x {steps} steps"},
             "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not c5:
+        line["reference_gpu_solver"] = time_reference_gpu_solver(max(1, min(args.steps, 20)), max(0, min(args.warmup, 5)))
     ref_cpu = time_reference_cpu_solver()
     if ref_cpu:
         line["reference_cpu_solver"] = ref_cpu
@@ -227,17 +299,20 @@ def run_ours(args, rank, world, local_rank):
     assert n == n_target, n
 
     # ---------------- resident: K graph-replayed steps, CUDA events on the solver stream ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first_sample()
     for _ in range(max(args.warmup, 3)):
         ps.update(DT)
     sol.sync()
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     sol.timer_start()
     for _ in range(args.steps):
         ps.update(DT)
     ms = sol.timer_stop()
+    sampler.mark_end()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
@@ -271,32 +346,52 @@ def run_ours(args, rank, world, local_rank):
         return
 
     # ---------------- end to end: host buffers in, host buffers out, every step ----------------
-    hpos = torch.empty((n, 4), dtype=torch.float32).pin_memory()
-    hvel = torch.empty((n, 4), dtype=torch.float32).pin_memory()
-    hpos.numpy()[:] = sol.download(psb.ARR_POS)
-    hvel.numpy()[:] = sol.download(psb.ARR_VEL)
+    # Through the public C ABI call ps_step_streamed (include/psolver.h): every step takes positions + velocities from pinned host
+    # memory and delivers positions + velocities to pinned host memory; the library double-buffers the transfers on its own copy
+    # streams, so the upload of step k+1 and the download of step k-1 run beside step k.  The host waits for every step's result
+    # (one call late: io_wait(1)) and for the last one before the clock stops.  "serial" = the same with plain
+    # upload / step / download / sync on one stream (what round 1 reported).
+    hin = [(torch.empty((n, 4), dtype=torch.float32).pin_memory(), torch.empty((n, 4), dtype=torch.float32).pin_memory()) for _ in range(2)]
+    hout = [(torch.empty((n, 4), dtype=torch.float32).pin_memory(), torch.empty((n, 4), dtype=torch.float32).pin_memory()) for _ in range(2)]
+    for hp, hv in hin:
+        hp.numpy()[:] = sol.download(psb.ARR_POS)
+        hv.numpy()[:] = sol.download(psb.ARR_VEL)
     e2e_steps = args.steps
 
-    def e2e_step():
-        sol.upload_async(psb.ARR_POS, hpos.data_ptr(), 4 * n)
-        sol.upload_async(psb.ARR_VEL, hvel.data_ptr(), 4 * n)
-        ps.update(DT)
-        sol.download_async(psb.ARR_POS, hpos.data_ptr(), 4 * n)
-        sol.download_async(psb.ARR_VEL, hvel.data_ptr(), 4 * n)
-        sol.sync()  # the host owns the result before it submits the next step
+    def e2e_run(steps):
+        for k in range(steps):
+            (ip, iv), (op, ov) = hin[k & 1], hout[k & 1]
+            sol.step_streamed(DT, ip.data_ptr(), iv.data_ptr(), op.data_ptr(), ov.data_ptr())
+            sol.io_wait(1)   # the host owns the result of the previous step before it submits the next one
+        sol.io_wait(0)
+        sol.sync()
 
-    for _ in range(3):
-        e2e_step()
+    e2e_run(4)
     barrier()
     t0 = time.perf_counter()
-    sol.timer_start()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e2e_ms_dev = sol.timer_stop()
+    e2e_run(e2e_steps)
     e2e_wall = (time.perf_counter() - t0) * 1e3
     barrier()
-    e2e_ms = max_over_ranks(max(e2e_ms_dev, e2e_wall))
+    e2e_ms = max_over_ranks(e2e_wall)   # host clock around submit .. last result in host memory (three streams: no single event pair spans it)
     e2e_value = n * world * e2e_steps / (e2e_ms * 1e-3)
+    # checksum of what came back: the last delivered frame equals the device state
+    last = hout[(e2e_steps - 1) & 1]
+    e2e_ok = bool(np.array_equal(last[0].numpy(), sol.download(psb.ARR_POS)) and np.array_equal(last[1].numpy(), sol.download(psb.ARR_VEL)))
+
+    def e2e_serial_step():
+        hp, hv = hin[0]
+        sol.upload_async(psb.ARR_POS, hp.data_ptr(), 4 * n)
+        sol.upload_async(psb.ARR_VEL, hv.data_ptr(), 4 * n)
+        ps.update(DT)
+        sol.download_async(psb.ARR_POS, hout[0][0].data_ptr(), 4 * n)
+        sol.download_async(psb.ARR_VEL, hout[0][1].data_ptr(), 4 * n)
+        sol.sync()
+
+    e2e_serial_step()
+    t0 = time.perf_counter()
+    for _ in range(min(e2e_steps, 10)):
+        e2e_serial_step()
+    e2e_serial_ms = (time.perf_counter() - t0) * 1e3 / min(e2e_steps, 10)
 
     # ---------------- per-stage device times (instrumented eager pass over the same state) ----------------
     prof_steps = min(args.steps, 10)
@@ -353,6 +448,23 @@ def run_ours(args, rank, world, local_rank):
                         "~0.7 KB/particle of neighbour lists in HBM so that K7 does not search again (idle bandwidth traded for issue slots); "
                         "the HBM-bound streaming kernels are in 'kernels'"}
 
+    # ---------------- the same scene further on: the blob has hit the floor and spreads (steps that the 20-step window never sees) ----------------
+    long_run = None
+    if rank == 0 and not args.no_long_run:
+        chunk, chunks = 10, 20
+        per = []
+        for _ in range(chunks):
+            sol.timer_start()
+            for _ in range(chunk):
+                ps.update(DT)
+            per.append(sol.timer_stop() / chunk)
+        mde, xde, ke = sol.fluid_stats()
+        long_run = {"steps": chunk * chunks, "after_steps": max(args.warmup, 3) + args.steps + 4 + 2 * e2e_steps + min(e2e_steps, 10) + 1 + prof_steps,
+                    "ms_per_step_mean": round(float(np.mean(per)), 4), "ms_per_step_max_of_10_step_means": round(float(np.max(per)), 4),
+                    "ms_per_step_first_last": [round(per[0], 4), round(per[-1], 4)],
+                    "particle_steps_per_s_mean": round(n / (float(np.mean(per)) * 1e-3), 1),
+                    "end_state": {"mean_density_error": mde, "max_density_error": xde, "kinetic_energy": ke}}
+
     if rank == 0:
         cpu_v, cpu_n, cpu_sec = time_oracle_port(46, 1)
         line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
@@ -361,18 +473,23 @@ def run_ours(args, rank, world, local_rank):
                 "config": {"workload": "c3: reference GPU scene 7 scaled to 100^3 = 1,000,000 PBF particles (addFluid((-31,6,-31),(32,69,32),1,1.5)), "
                                        "256^3 grid, 5 solver iterations, dt=1/60", "particles_per_gpu": n,
                            "multi_gpu": "independent replicas" if world > 1 else "single",
-                           "l2": "working set 1M x ~150 B + 2 x 64 MB cell tables > 126 MB L2; no flush"},
+                           "l2": "no flush: the step's working set (1M x ~150 B of state + 64 MB cell table + ~0.6 GB of neighbour lists per iteration) "
+                                 "exceeds the 126 MB L2, but the streaming kernels' own 24-64 MB do not - their HBM fractions are the ones in "
+                                 "c5_8M_1gpu.kernels_at_8M"},
                 "particle_iterations_per_s": value * ITERS,
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
-                        "ms_per_step": e2e_ms / e2e_steps},
+                        "ms_per_step": e2e_ms / e2e_steps, "api": "ps_step_streamed + ps_io_wait (double-buffered PCIe transfers beside the solver)",
+                        "delivered_frame_equals_device_state": e2e_ok, "serial_ms_per_step": round(e2e_serial_ms, 4)},
                 "gpu_launches": launches,
-                "roofline": roofline, "kernels": kernels,
+                "roofline": roofline, "kernels": kernels, "long_run": long_run,
                 "cpu_baseline": {"value": cpu_v, "unit": "particle-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
                                  "sample": f"oracle port (OpenMP) on a 46^3 = {cpu_n} particle block of the same lattice, 1 step"},
                 "clocks": clocks}
         ps.close()
         ps = None
         line["c1_2d_path"] = time_c1_gpu()
+        if not args.no_c5:
+            line["c5_8M_1gpu"] = c5_single_gpu(local_rank, peak)
         print(json.dumps(line), flush=True)
     if ps is not None:
         ps.close()
@@ -382,6 +499,60 @@ def run_ours(args, rank, world, local_rank):
 
 C5_NY, C5_NZ = 250, 400          # lattice sites in y and z: 100,000 particles per x-plane
 C5_SPACING, C5_RHO0 = 0.625, 4.1
+
+
+def c5_single_gpu(device, peak, particles=8_000_000, steps=5, warmup=3):
+    """The weak-scaling base of the N > 1 runs, carried in the N = 1 line: the c5 dam break at 8,000,000 particles (what every
+    rank of a multi-GPU run owns) on ONE GPU as one undecomposed context — whole-step graph replays timed with CUDA events — and
+    the per-stage times of an instrumented pass at that size, where every streaming kernel's working set is far beyond the L2."""
+    try:
+        import math
+        import particlesolver_b200 as psb
+        from particlesolver_b200 import slab
+        plane = C5_NY * C5_NZ
+        nx = max(1, int(round(particles / plane)))
+        n = nx * plane
+        gx = 1 << int(math.ceil(math.log2(math.ceil(nx * C5_SPACING / 0.5) + 16)))
+        p = psb.default_params()
+        p.grid_size[:] = (gx, 512, 512)
+        p.min_bounds[:] = (0, 0, 0)
+        p.max_bounds[:] = (int(2 * nx * C5_SPACING), 256, int(C5_NZ * C5_SPACING))
+        p.solver_iterations = ITERS
+        sol = psb.Solver(p, max_particles=n + 4096, device=device)
+        step_planes = max(1, 4_000_000 // plane)
+        for a in range(0, nx, step_planes):
+            sol.append(*slab.dam_break_block(nx, C5_NY, C5_NZ, ix0=a, ix1=min(a + step_planes, nx), spacing=C5_SPACING, rest_density=C5_RHO0))
+        for _ in range(warmup):
+            sol.step(DT)
+        sol.sync()
+        sol.timer_start()
+        for _ in range(steps):
+            sol.step(DT)
+        ms = sol.timer_stop() / steps
+        acc = {}
+        for _ in range(2):
+            st, _ln = sol.step_profiled(DT)
+            for k, v in st.items():
+                acc[k] = acc.get(k, 0.0) + v / 2
+        cells = gx * 512 * 512
+        bytes_of = dict(STAGE_BYTES)
+        bytes_of["sort"] = 4 + 16 * 4   # 2^25 cells: four 8-bit passes
+        kern = {}
+        for k, per_step in acc.items():
+            if per_step <= 0 or (k not in bytes_of and k != "cell_table"):
+                continue
+            calls = 1 if k in ("predict", "velocity") else ITERS
+            b = (4.0 * cells + 4.0 * n) if k == "cell_table" else bytes_of[k] * n
+            gbs = b * calls / (per_step * 1e-3) / 1e9
+            kern[k] = {"ms_per_launch": round(per_step / calls, 4), "achieved_gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}
+        mde, xde, ke = sol.fluid_stats()
+        out = {"particles": n, "grid": [gx, 512, 512], "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 4),
+               "value": round(n / (ms * 1e-3), 1), "unit": "particle-steps/s", "kernels_at_8M": kern,
+               "state": {"mean_density_error": mde, "max_density_error": xde, "kinetic_energy": ke}}
+        sol.close()
+        return out
+    except Exception as e:  # the headline must not die on the side measurement
+        return {"error": str(e)}
 
 
 def run_slabs(args, rank, world, local_rank):
@@ -452,18 +623,21 @@ def run_slabs(args, rank, world, local_rank):
                 dom.solve(it)
             dom.finish(DT)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first_sample()
     for _ in range(max(args.warmup, 3)):
         step()
     sol.sync()
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     sent0 = comm.bytes_sent if comm else 0
     sol.timer_start()
     for _ in range(args.steps):
         step()
     ms = sol.timer_stop()
+    sampler.mark_end()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = reduce(ms, dist.ReduceOp.MAX)
@@ -579,6 +753,8 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c5"], help="auto: c3 on one GPU, c5 (slabs) on several")
     ap.add_argument("--particles", type=int, default=0, help="c5: total particle count over all ranks (rounded to whole lattice planes); "
                     "default 8,000,000 per GPU, i.e. weak scaling up to the 64M-particle scene on 8 GPUs")
+    ap.add_argument("--no-long-run", action="store_true", help="c3: skip the 200 further steps of the long_run field")
+    ap.add_argument("--no-c5", action="store_true", help="c3: skip the c5_8M_1gpu field (the 8M-particle dam break on this GPU)")
     ap.add_argument("--quick", action="store_true", help="resident timing only (for runs under ncu): no e2e, no per-stage pass, no CPU baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -7,9 +7,10 @@
  * Declarations replaced, with the reference file:line of each:
  *   gpu/src/cuda/wrappers.cuh:12-97            integration + solver wrappers
  *   gpu/src/cuda/shared_variables.cuh:13-36    phase / inverse mass / Xstar state
- * Not re-exported: gpu/src/cuda/util.cuh:6-25 (cudaInit, allocateArray, GL-interop map/unmap ...): that file is
- * device/viewer plumbing with no solver arithmetic; a host keeps its own (the reference's util.cu for the Qt
- * viewer, or a headless one such as oracle/ref_gpu_glue.cu).
+ *   gpu/src/cuda/util.cuh:6-25                 device selection, raw device arrays, blocking copies, launch geometry
+ * Not re-exported: the four GL-interop entry points of util.cuh (registerGLBufferObject, unregisterGLBufferObject,
+ * mapGLBufferObject, unmapGLBufferObject, util.cuh:16-20): they belong to the viewer; the reference's util.cu keeps
+ * them for the Qt application, a headless host maps an ordinary device allocation (oracle/ref_gpu_glue.cu).
  *
  * Like the reference: one particle system per process (state lives in a library-global context), default
  * stream, blocking copies of host inputs, and any CUDA failure prints a message and exit(EXIT_FAILURE)s
@@ -65,6 +66,16 @@ void addDistanceConstraint(uint *index, float *distance, uint numConstraints);
 void freeSolverVectors(void);
 void solvePointConstraints(float *particles);
 void solveDistanceConstraints(float *particles);
+/* ---- util.cu without OpenGL ---- (util.cuh:9-14,22-25) */
+void cudaInit(void);
+void allocateArray(void **devPtr, int size);
+void freeArray(void *devPtr);
+void copyArrayToDevice(void *device, const void *host, int offset, int size);
+void copyArrayFromDevice(void *host, const void *device, int size);
+uint iDivUp(uint a, uint b);
+#ifdef __cplusplus
+void computeGridSize(uint n, uint blockSize, uint &numBlocks, uint &numThreads);
+#endif
 /* ---- shared_variables.cu ---- (shared_variables.cuh:13-36) */
 void freeSharedVectors(void);
 void appendPhaseAndMass(int *fase, float *w, uint numParticles);

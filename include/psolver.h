@@ -48,7 +48,8 @@ typedef struct PsParams {
     int32_t min_bounds[3];       /* scene box, integer like the reference's int3 */
     int32_t max_bounds[3];
     uint32_t solver_iterations;  /* 5           particleapp.cpp:38 */
-    float omega;                 /* SOR factor on the Jacobi-averaged deltas; 1.0 == reference */
+    float omega;                 /* SOR factor on every Jacobi-averaged delta: contacts / numNeighbors (K5), PBF delta-p /
+                                    (rho0 + numNeighbors) (K7), distance constraints / occurrences (K9); 1.0 == reference */
     uint32_t flags;              /* PS_FLAG_* */
     uint32_t neighbor_list_rows; /* neighbour lists kept between the two PBF passes: rows (128 B: one entry for each of a warp's 32
                                     particles) of every warp's list region.  512 (default) >= the 500-neighbour cap: a list always fits;
@@ -134,6 +135,16 @@ int ps_step(PsCtx *ctx, float dt);
 int ps_sync(PsCtx *ctx);
 /* milliseconds of device time of the last ps_step (CUDA events on the context's stream); syncs. */
 int ps_last_step_ms(PsCtx *ctx, float *ms);
+
+/* One whole step for a host that owns positions and velocities (the reference's host reads them back through
+ * copyArrayFromDevice / its GL buffer, particlesystem.cpp:122-142,248-262): the step's inputs come from host memory, its result
+ * goes to host memory, float4 per particle each; any of the four pointers may be NULL (that array stays on the device / is not
+ * delivered).  Asynchronous: the transfers run on two copy streams through double-buffered staging frames, so the upload of
+ * the next call and the download of the previous one overlap the solver (csrc/ps_stream_io.cu).  Host memory should be pinned,
+ * input buffers must stay untouched until the call after next has been made (or ps_io_wait(ctx, 0) returned), output buffers
+ * are valid after ps_io_wait.  ps_io_wait(ctx, k) blocks until the outputs of the call made k calls ago (0 = the last) landed. */
+int ps_step_streamed(PsCtx *ctx, float dt, const float *pos_in, const float *vel_in, float *pos_out, float *vel_out);
+int ps_io_wait(PsCtx *ctx, uint32_t calls_back);
 
 /* Device-time a region of work on the context's stream with CUDA events (stop synchronises). */
 int ps_timer_start(PsCtx *ctx);

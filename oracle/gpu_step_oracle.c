@@ -54,6 +54,14 @@ typedef struct {
     int max_b[3];
 } OrParams;
 
+/* SOR factor on the Jacobi-averaged deltas ("Jacobi averaging with SOR", BASELINE north_star).  The reference's live GPU path has
+ * none (its only omega is the dead dense solver's, gpu/src/cuda/solver_kernel.cuh:244,278, and the CPU app's relaxation constant,
+ * cpu/src/solver/solver.h:8): omega = 1 reproduces it exactly.  For omega != 1 every averaged delta — contacts (dp / numNeighbors,
+ * integration_kernel.cuh:436-437), PBF delta-p (/ (rho0 + numNeighbors), :640) and distance constraints (/ occurrences,
+ * solver_kernel.cuh:64-76) — is multiplied by omega, exactly where the CUDA path applies PsParams.omega. */
+static float g_omega = 1.0f;
+void or_set_omega(float omega) { g_omega = omega; }
+
 /* ---- K1: integrateSystem + copyToXstar (integration.cu:122-135, integration_kernel.cuh:159-184,
  *          shared_variables.cu:52-57).  vel is NOT written back; inverse mass is not consulted. ---- */
 void or_predict(float *pos, const float *vel, float *prev, u32 n, float dt, const float *g) {
@@ -214,7 +222,7 @@ void or_collide_ext(float *pos, const float *prev, const float *spos, const floa
             u32 orig = index[i];
             const float *pp = prev + 4 * (size_t)orig;
             float delta[3] = {0.f, 0.f, 0.f};
-            float fn = (float)nn;
+            float fn = (g_omega == 1.0f) ? (float)nn : (float)nn / g_omega;  /* omega scales the averaged contact delta */
             for (u32 k = 0; k < nn; k++) {
                 u32 j = nb[k];
                 const float *x2 = spos + 4 * (size_t)j;
@@ -383,6 +391,7 @@ void or_solve_fluids_stages(const float *spos, const float *sw, const int *sphas
             }
             u32 orig = index[i];
             float div = ros[orig] + (float)nn;
+            if (g_omega != 1.0f) div /= g_omega;
             for (int c = 0; c < 4; c++) pos[4 * (size_t)orig + c] += delta[c] / div;
         }
         free(nb);
@@ -474,7 +483,7 @@ int or_solve_distance(float *pos, const u32 *idx, const float *rest, u32 m, cons
     for (u32 i = 0; i < n; i++) {
         if (!touched[i]) continue;
         float o = (float)occ[i];
-        for (int k = 0; k < 3; k++) pos[4 * (size_t)i + k] += sum[4 * (size_t)i + k] / o;
+        for (int k = 0; k < 3; k++) pos[4 * (size_t)i + k] += g_omega * (sum[4 * (size_t)i + k] / o);
     }
     free(sum); free(dl); free(touched);
     return nonprefix;

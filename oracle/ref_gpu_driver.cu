@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -92,6 +93,7 @@ struct Args {
     int grid = 64, steps = 1, dump_every = 1, iters = 5, side = 100;
     int dump_iters = 1 << 30;  // staged mode: dump the arrays of the first dump_iters solver iterations of a step only
     int light = 0;             // staged mode: only what the full-size parity test reads (1M particles: 0.25 GB instead of 1.3 GB per step)
+    int warmup = -1;           // whole mode: untimed leading steps (default: the first step when more than one is run)
     unsigned max_particles = 15000;
     float dt = 1.0f / 60.0f;
 };
@@ -216,6 +218,7 @@ int main(int argc, char **argv) {
         else if (k == "--dt") a.dt = (float)atof(val().c_str());
         else if (k == "--dump-iters") a.dump_iters = atoi(val().c_str());
         else if (k == "--light") a.light = atoi(val().c_str());
+        else if (k == "--warmup") a.warmup = atoi(val().c_str());
         else { fprintf(stderr, "unknown arg %s\n", k.c_str()); return 2; }
     }
     g_out = a.out;
@@ -235,13 +238,16 @@ int main(int argc, char **argv) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         double total_ms = 0;
+        std::vector<float> per_step;
+        const int warm = a.warmup >= 0 ? (a.warmup < a.steps ? a.warmup : a.steps - 1) : (a.steps > 1 ? 1 : 0);
         for (int s = 0; s < a.steps; s++) {
             cudaEventRecord(e0);
             ps->update(a.dt);
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1);
-            if (s > 0 || a.steps == 1) total_ms += ms;
+            if (s >= warm) { total_ms += ms; per_step.push_back(ms); }
+            if (getenv("REF_GPU_VERBOSE")) fprintf(stderr, "step %d: %.3f ms\n", s, ms);
             if (a.dump_every > 0 && ((s + 1) % a.dump_every == 0 || s + 1 == a.steps)) {
                 char tag[64]; snprintf(tag, sizeof tag, "w%d_", s + 1);
                 float *dPos = (float *)mapGLBufferObject(&ps->m_cuda_posvbo_resource);
@@ -249,10 +255,16 @@ int main(int argc, char **argv) {
                 dump_f(std::string(tag) + "vel", st_vel(), 4 * (size_t)n);
             }
         }
-        int timed = a.steps > 1 ? a.steps - 1 : 1;
+        int timed = a.steps - warm;
         double ms = total_ms / timed;
+        // the reference's step time has a heavy tail on any box (per-call cudaMalloc / thrust temporaries, first touch of its 8 KB per
+        // particle of neighbour lists): the median is the figure that is fair to it
+        std::sort(per_step.begin(), per_step.end());
+        double med = per_step.empty() ? ms : (per_step.size() & 1 ? per_step[per_step.size() / 2]
+                                                                 : 0.5 * (per_step[per_step.size() / 2 - 1] + per_step[per_step.size() / 2]));
         printf("{\"impl\": \"" IMPL_NAME "\", \"scene\": \"%s\", \"n\": %u, \"grid\": %d, \"steps_timed\": %d, "
-               "\"ms_per_step\": %.4f, \"particle_steps_per_s\": %.1f}\n", a.scene.c_str(), n, a.grid, timed, ms, n / (ms * 1e-3));
+               "\"ms_per_step\": %.4f, \"particle_steps_per_s\": %.1f, \"ms_per_step_median\": %.4f, \"ms_per_step_min\": %.4f, \"ms_per_step_max\": %.4f}\n",
+               a.scene.c_str(), n, a.grid, timed, ms, n / (ms * 1e-3), med, per_step.empty() ? ms : per_step.front(), per_step.empty() ? ms : per_step.back());
         FILE *f = fopen((g_out + "/timing.json").c_str(), "w");
         fprintf(f, "{\"scene\": \"%s\", \"n\": %u, \"grid\": %d, \"steps_timed\": %d, \"ms_per_step\": %.4f, \"particle_steps_per_s\": %.1f}\n",
                 a.scene.c_str(), n, a.grid, timed, ms, n / (ms * 1e-3));

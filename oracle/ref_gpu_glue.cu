@@ -36,6 +36,7 @@ void glBufferSubData(GLenum, GLintptr off, GLsizeiptr size, const void *data) {
     CK(cudaMemcpy((char *)v.dptr + off, data, size, cudaMemcpyHostToDevice));
 }
 
+#ifndef PS_DROPIN  /* the drop-in build takes these seven from libpsolver.so (include/ps_reference_abi.h), like a real integration would */
 void cudaInit() { CK(cudaSetDevice(0)); }
 void allocateArray(void **devPtr, size_t size) { CK(cudaMalloc(devPtr, size)); }
 void freeArray(void *devPtr) { CK(cudaFree(devPtr)); }
@@ -43,14 +44,17 @@ void copyArrayToDevice(void *device, const void *host, int offset, int size) {
     CK(cudaMemcpy((char *)device + offset, host, size, cudaMemcpyHostToDevice));
 }
 void copyArrayFromDevice(void *host, const void *device, int size) { CK(cudaMemcpy(host, device, size, cudaMemcpyDeviceToHost)); }
+#endif
 // the "graphics resource" handle is just the vbo id smuggled through the pointer
 void registerGLBufferObject(unsigned int vbo, struct cudaGraphicsResource **res) { *res = (struct cudaGraphicsResource *)(size_t)vbo; }
 void unregisterGLBufferObject(struct cudaGraphicsResource *) {}
 void *mapGLBufferObject(struct cudaGraphicsResource **res) { return g_vbos[(GLuint)(size_t)*res].dptr; }
 void unmapGLBufferObject(struct cudaGraphicsResource *) {}
+#ifndef PS_DROPIN
 uint iDivUp(uint a, uint b) { return (a % b != 0) ? (a / b + 1) : (a / b); }
 void computeGridSize(uint n, uint blockSize, uint &numBlocks, uint &numThreads) {
     numThreads = std::min(blockSize, n);
     numBlocks = iDivUp(n, numThreads);
 }
+#endif
 }

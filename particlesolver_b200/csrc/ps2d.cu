@@ -1331,8 +1331,13 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     c->scalars_host[4] = (u32)(c->rng.calls - c->win_pos);
     CU2(cudaMemcpyAsync(c->window_base_dev, c->scalars_host + 4, 4, cudaMemcpyHostToDevice, s));
     static const bool no_graph = getenv("PS_NO_GRAPH") != nullptr;
-    static const cudaError_t optin = cudaFuncSetAttribute(k2d_distance_run_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDistanceStageMax);
-    (void)optin;
+    {   // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute: once for each device this process drives
+        static bool opted[64] = {};
+        if (c->device >= 0 && c->device < 64 && !opted[c->device]) {
+            CU2(cudaFuncSetAttribute(k2d_distance_run_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDistanceStageMax));
+            opted[c->device] = true;
+        }
+    }
     if (no_graph) {
         c->launches = issue_tick(c, dt);
     } else {
@@ -1534,6 +1539,12 @@ extern "C" int ps2d_load(const char *path, int device, Ps2dCtx **out) {
               get2(fp, fem.data(), fem.size()) && get2(fp, lk.data(), lk.size());
     if (!ok) { ps_set_error("ps2d_load: truncated file %s", path); return PS_ERR_INVALID; }
     for (size_t b = 0; b < nb; b++) if ((uint64_t)bf[b] + bc[b] > n) { ps_set_error("ps2d_load: body out of range"); return PS_ERR_INVALID; }
+    // index fields that address device arrays: body of a particle in [-1, bodies), constraint group in [-1, STANDARD records),
+    // emitters' STANDARD record (UINT32_MAX = none)
+    for (size_t k = 0; k < n; k++)
+        if (bod[k] < -1 || bod[k] >= (int)nb || grp[k] < -1 || (grp[k] >= 0 && (uint64_t)grp[k] >= h.num_standard)) { ps_set_error("ps2d_load: particle %zu refers to a body / constraint group that does not exist", k); return PS_ERR_INVALID; }
+    for (const EmitRecord &e : em) if (e.standard_index != 0xffffffffu && e.standard_index >= h.num_standard) { ps_set_error("ps2d_load: emitter refers to a missing STANDARD record"); return PS_ERR_INVALID; }
+    for (const FluidEmitRecord &e : fem) if (e.standard_index != 0xffffffffu && e.standard_index >= h.num_standard) { ps_set_error("ps2d_load: fluid emitter refers to a missing STANDARD record"); return PS_ERR_INVALID; }
     for (const StdRecord &o : st) if (o.kind > STD_DISTANCE || (o.kind == STD_DISTANCE && (o.i1 >= n || o.i2 >= n))) { ps_set_error("ps2d_load: bad STANDARD record"); return PS_ERR_INVALID; }
     Ps2dCtx *c = nullptr;
     int r = ps2d_create(device, &P, h.cap, &c);

@@ -2,8 +2,11 @@
 // I/O).  The reference has no persistence at all (scenes exist only as code, particleapp.cpp:141-215); this is the
 // restartable state of a PsCtx: parameters, the SoA particle arrays, the constraint lists in insertion order, rigid
 // bodies with their rotations, viscosity coefficients and the position of the wall-jitter stream (cuRAND XORWOW, seed
-// 1234: repositioned by replaying the same number of 6-value draws).  A run continued from a checkpoint is bit-identical
-// to the uninterrupted run (tests/test_gpu_checkpoint.py).  Little-endian, fixed-width fields, no pointers.
+// 1234: repositioned by replaying the same number of 6-value draws) and — version 3 — the lambda array by sorted slot: K6 leaves
+// the lambda of non-fluid slots untouched (the reference's behaviour; PS_FLAG_ZERO_NONFLUID_LAMBDA off) and K7 reads lambda_j of
+// every neighbour whatever its phase, so in a scene whose fluid touches solids those stale values are state that crosses steps.
+// A run continued from a checkpoint is bit-identical to the uninterrupted run (tests/test_gpu_checkpoint.py).  Little-endian,
+// fixed-width fields, no pointers.
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -46,8 +49,9 @@ extern "C" int ps_save(PsCtx *c, const char *path) {
     if (r != PS_OK) return r;
     KCU(cudaStreamSynchronize(c->stream));
     const size_t n = c->n;
-    std::vector<float> pos(4 * n), vel(4 * n), prev(4 * n), w(n), ros(n), quat(4 * (size_t)c->num_bodies);
+    std::vector<float> pos(4 * n), vel(4 * n), prev(4 * n), w(n), ros(n), quat(4 * (size_t)c->num_bodies), lam(n);
     std::vector<int> phase(n);
+    KCU(cudaMemcpy(lam.data(), c->lambda, 4 * n, cudaMemcpyDeviceToHost));
     KCU(cudaMemcpy(pos.data(), c->pos, 16 * n, cudaMemcpyDeviceToHost));
     KCU(cudaMemcpy(vel.data(), c->vel, 16 * n, cudaMemcpyDeviceToHost));
     KCU(cudaMemcpy(prev.data(), c->prev, 16 * n, cudaMemcpyDeviceToHost));
@@ -57,7 +61,7 @@ extern "C" int ps_save(PsCtx *c, const char *path) {
     if (c->num_bodies) KCU(cudaMemcpy(quat.data(), c->body_quat, 16 * (size_t)c->num_bodies, cudaMemcpyDeviceToHost));
     Header h{};
     memcpy(h.magic, kMagic, 8);
-    h.version = 2; h.params_bytes = (uint32_t)sizeof(PsParams);
+    h.version = 3; h.params_bytes = (uint32_t)sizeof(PsParams);
     h.n = n; h.limit = c->limit; h.num_distance = c->h_dist_rest.size(); h.num_point = c->h_point_idx.size();
     h.num_bodies = c->num_bodies; h.body_members = c->h_body_idx.size(); h.rand_calls = c->rand_calls;
     h.xsph_c = c->xsph_c; h.vorticity_eps = c->vorticity_eps;
@@ -73,6 +77,7 @@ extern "C" int ps_save(PsCtx *c, const char *path) {
               put(F.f, quat.data(), quat.size());
     const uint64_t sdf_members = c->has_sdf ? c->h_body_idx.size() : 0;  // version 2: SDF data of the rigid bodies (4 floats per member) or none
     ok = ok && put(F.f, &sdf_members, 1) && put(F.f, c->h_body_sdf.data(), (size_t)(4 * sdf_members));
+    ok = ok && put(F.f, lam.data(), n);  // version 3: lambda by sorted slot
     if (!ok || fflush(F.f) != 0) { ps_set_error("ps_save: short write to %s", path); return PS_ERR_INVALID; }
     return PS_OK;
 }
@@ -85,7 +90,7 @@ extern "C" int ps_load(const char *path, int device, PsCtx **out) {
     if (!F.f) { ps_set_error("ps_load: cannot open %s", path); return PS_ERR_INVALID; }
     Header h{};
     if (!get(F.f, &h, 1) || memcmp(h.magic, kMagic, 8) != 0) { ps_set_error("ps_load: %s is not a libpsolver checkpoint", path); return PS_ERR_INVALID; }
-    if ((h.version != 1 && h.version != 2) || h.params_bytes != sizeof(PsParams)) { ps_set_error("ps_load: checkpoint version %u / parameter block of %u bytes not understood", h.version, h.params_bytes); return PS_ERR_INVALID; }
+    if (h.version < 1 || h.version > 3 || h.params_bytes != sizeof(PsParams)) { ps_set_error("ps_load: checkpoint version %u / parameter block of %u bytes not understood", h.version, h.params_bytes); return PS_ERR_INVALID; }
     if (h.n > h.limit || h.limit > (1ull << 31) || h.num_distance > (1ull << 32) || h.num_point > (1ull << 32) || h.body_members > h.n * 64 + 64 || h.num_bodies > h.body_members) {
         ps_set_error("ps_load: implausible sizes in %s", path); return PS_ERR_INVALID;
     }
@@ -109,15 +114,22 @@ extern "C" int ps_load(const char *path, int device, PsCtx **out) {
         ok = get(F.f, &sdf_members, 1) && (sdf_members == 0 || sdf_members == h.body_members) && get(F.f, bsdf.data(), (size_t)(4 * sdf_members));
         has_sdf = ok && sdf_members != 0;
     }
+    std::vector<float> lam;
+    if (ok && h.version >= 3) { lam.resize(n); ok = get(F.f, lam.data(), n); }
     if (!ok) { ps_set_error("ps_load: truncated file %s", path); return PS_ERR_INVALID; }
     for (u32 v : bidx) if (v >= n) { ps_set_error("ps_load: body member index out of range"); return PS_ERR_INVALID; }
     if (boff[0] != 0 || boff[h.num_bodies] != h.body_members) { ps_set_error("ps_load: inconsistent body table"); return PS_ERR_INVALID; }
+    for (size_t b = 0; b < h.num_bodies; b++)
+        if (boff[b + 1] < boff[b]) { ps_set_error("ps_load: body offsets are not ascending"); return PS_ERR_INVALID; }
+    for (size_t k = 0; k < didx.size(); k++) if (didx[k] >= n) { ps_set_error("ps_load: distance constraint index out of range"); return PS_ERR_INVALID; }
+    for (u32 v : pidx) if (v >= n) { ps_set_error("ps_load: point constraint index out of range"); return PS_ERR_INVALID; }
     PsCtx *c = nullptr;
     int r = ps_create(device, &p, h.limit, &c);
     if (r != PS_OK) return r;
     auto fail = [&](int code) { ps_destroy(c); return code; };
     if (n && (r = ps_append_particles(c, pos.data(), vel.data(), w.data(), ros.data(), phase.data(), n)) != PS_OK) return fail(r);
     if (n && (r = ps_upload(c, PS_ARR_PREV, prev.data(), 0, 4 * n)) != PS_OK) return fail(r);
+    if (n && !lam.empty() && cudaMemcpy(c->lambda, lam.data(), 4 * n, cudaMemcpyHostToDevice) != cudaSuccess) { ps_set_error("ps_load: lambda upload failed"); return fail(PS_ERR_CUDA); }
     if ((r = ps_add_distance_constraints(c, didx.data(), drest.data(), h.num_distance)) != PS_OK) return fail(r);
     if ((r = ps_add_point_constraints(c, pidx.data(), pxyz.data(), h.num_point)) != PS_OK) return fail(r);
     // bodies: the stored rest shape, not the current configuration

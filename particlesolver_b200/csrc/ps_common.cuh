@@ -127,7 +127,7 @@ int ps_sort_passes(u32 num_cells);
 void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool identity_vals, SortScratch sc, cudaStream_t s);
 // ps_neighbor_kernels.cu
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
-                       const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, const u32 *adj_off,
+                       const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, float omega, const u32 *adj_off,
                        const u32 *adj, const float4 *sdf_world, cudaStream_t s);
 // nbr_list / nbr_rows: interleaved per-warp neighbour lists written by K6 and consumed by K7 and the other passes (nullptr: they
 // re-walk the grid); format in ps_fluid_lists.cuh.  `list_rows` = rows of a warp's region (PsParams.neighbor_list_rows), `capacity`

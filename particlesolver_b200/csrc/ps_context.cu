@@ -271,6 +271,7 @@ extern "C" int ps_destroy(PsCtx *c) {
                     c->d_point_xyz, c->dist_scratch, c->adj_off, c->adj};
     for (void *p : ptrs) if (p) cudaFree(p);
     ps_ext_free(c);
+    ps_io_free(c);
     if (c->slab_counts_host) cudaFreeHost(c->slab_counts_host);
     if (c->tm0) { cudaEventDestroy(c->tm0); cudaEventDestroy(c->tm1); }
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -340,6 +341,7 @@ extern "C" int ps_add_distance_constraints(PsCtx *c, const uint32_t *idx, const 
     NEED(c);
     if (m == 0) return PS_OK;
     if (!idx || !rest) { ps_set_error("ps_add_distance_constraints: null array"); return PS_ERR_INVALID; }
+    if (c->n_ghost || c->slab_used) { ps_set_error("ps_add_distance_constraints: index-based constraints are not supported on slab contexts"); return PS_ERR_STATE; }
     for (uint64_t k = 0; k < 2 * m; k++)
         if (idx[k] >= c->n) { ps_set_error("distance constraint endpoint %u >= %u particles", idx[k], c->n); return PS_ERR_INVALID; }
     c->h_dist_idx.insert(c->h_dist_idx.end(), idx, idx + 2 * m);
@@ -353,6 +355,7 @@ extern "C" int ps_add_point_constraints(PsCtx *c, const uint32_t *idx, const flo
     NEED(c);
     if (p == 0) return PS_OK;
     if (!idx || !xyz) { ps_set_error("ps_add_point_constraints: null array"); return PS_ERR_INVALID; }
+    if (c->n_ghost || c->slab_used) { ps_set_error("ps_add_point_constraints: index-based constraints are not supported on slab contexts"); return PS_ERR_STATE; }
     for (uint64_t k = 0; k < p; k++)
         if (idx[k] >= c->n) { ps_set_error("point constraint index %u >= %u particles", idx[k], c->n); return PS_ERR_INVALID; }
     c->h_point_idx.insert(c->h_point_idx.end(), idx, idx + p);
@@ -516,7 +519,7 @@ extern "C" int ps_solve_contacts(PsCtx *c) {
     DeviceGuard dg(c->device);
     ps_ext_issue_sdf(c);
     ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, c->n, c->n - c->n_ghost, c->grid,
-                      c->params.particle_radius, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, c->stream);
+                      c->params.particle_radius, c->params.omega, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, c->stream);
     return check_launch("ps_solve_contacts");
 }
 static int issue_fluid(PsCtx *c, const char *what, bool do_lambda, bool do_delta) {
@@ -586,7 +589,7 @@ static u32 issue_step(PsCtx *c, float dt) {
         if (has_contact) {
             launches += ps_ext_issue_sdf(c);
             ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n_owned, c->grid,
-                              p.particle_radius, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, s);
+                              p.particle_radius, p.omega, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, s);
             launches++;
         }
         if (has_fluid) {
@@ -623,7 +626,8 @@ extern "C" int ps_step(PsCtx *c, float dt) {
         c->launches_per_step = issue_step(c, dt);
     } else {
         PsCtx::GraphKey key{c->n, c->n_ghost, (u32)c->h_dist_rest.size(), c->num_points, c->params.solver_iterations, c->params.flags, dt, c->params.omega,
-                            c->num_bodies, c->xsph_c, c->vorticity_eps};
+                            c->num_bodies, c->xsph_c, c->vorticity_eps,
+                            (c->census_known ? 1u : 0u) | (c->n_contact ? 2u : 0u) | (c->n_fluid ? 4u : 0u) | (c->n_gas ? 8u : 0u), c->lambda_xmin, c->lambda_xmax};
         if (!c->graph_exec || !(key == c->graph_key)) {
             if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
             cudaGraph_t graph = nullptr;
@@ -685,7 +689,7 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
         ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s); mark(4, 1);
         c->grid_valid = true;
         c->ref_tables_valid = false;
-        if (has_contact) { const u32 lsdf = ps_ext_issue_sdf(c); ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, s); mark(5, 1 + lsdf); }
+        if (has_contact) { const u32 lsdf = ps_ext_issue_sdf(c); ps_launch_collide(c->pos, c->prev, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->num_neighbors, n, n, c->grid, p.particle_radius, p.omega, self_collision_adj(c), c->adj, c->has_sdf ? c->sdf_world : nullptr, s); mark(5, 1 + lsdf); }
         if (has_fluid) {
             const u32 k6 = ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, n, n, c->lambda_xmin,
                                                   c->lambda_xmax, c->grid, c->stencil, (p.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list, c->nbr_rows,
@@ -836,7 +840,11 @@ extern "C" int ps_set_ghost_count(PsCtx *c, uint64_t ghosts) {
 
 static int slab_ready(PsCtx *c, const char *what) {
     NEED(c);
-    if (!c->h_dist_rest.empty() || !c->h_point_idx.empty()) { ps_set_error("%s: slab contexts cannot hold distance / point constraints (particle indices change)", what); return PS_ERR_STATE; }
+    if (!c->h_dist_rest.empty() || !c->h_point_idx.empty() || c->num_bodies || !c->h_body_idx.empty()) {
+        ps_set_error("%s: slab contexts cannot hold distance / point constraints or rigid bodies (migration changes particle indices)", what);
+        return PS_ERR_STATE;
+    }
+    c->slab_used = true;
     const size_t need = ps_slab_scratch_elems((u32)c->capacity);
     if (need > c->slab_scratch_elems) {
         if (c->slab_scratch) CU(cudaFree(c->slab_scratch));

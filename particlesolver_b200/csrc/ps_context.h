@@ -14,6 +14,14 @@ struct PsNvtxRange {
     ~PsNvtxRange() { nvtxRangePop(); }
 };
 
+// ps_stream_io.cu: staging frames, copy streams and events of ps_step_streamed
+struct PsStreamIo {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    float4 *in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [frame][pos | vel]
+    cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr}, out_ready[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+    uint64_t cap = 0, calls = 0;
+};
+
 struct PsCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -92,9 +100,15 @@ struct PsCtx {
 
     // CUDA graph of one whole step
     cudaGraphExec_t graph_exec = nullptr;
-    struct GraphKey { u32 n, n_ghost, m, p, iters, flags; float dt, omega; u32 bodies; float xsph, vort; bool operator==(const GraphKey &o) const {
-        return n == o.n && n_ghost == o.n_ghost && m == o.m && p == o.p && iters == o.iters && flags == o.flags && dt == o.dt && omega == o.omega &&
-               bodies == o.bodies && xsph == o.xsph && vort == o.vort; } } graph_key{};
+    // everything issue_step bakes into the captured graph: sizes, parameters, which passes run (the phase census decides whether the
+    // contact pass and the fluid passes are issued at all) and the ghost-lambda range of a slab context
+    struct GraphKey {
+        u32 n, n_ghost, m, p, iters, flags; float dt, omega; u32 bodies; float xsph, vort; u32 passes; float lam_lo, lam_hi;
+        bool operator==(const GraphKey &o) const {
+            return n == o.n && n_ghost == o.n_ghost && m == o.m && p == o.p && iters == o.iters && flags == o.flags && dt == o.dt && omega == o.omega &&
+                   bodies == o.bodies && xsph == o.xsph && vort == o.vort && passes == o.passes && lam_lo == o.lam_lo && lam_hi == o.lam_hi;
+        }
+    } graph_key{};
     u32 launches_per_step = 0;
     u32 launch_counter = 0;  // counts launches while a step is being issued
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
@@ -107,7 +121,9 @@ struct PsCtx {
     uint64_t slab_ranks_cap = 0;
     u32 slab_halo_counts[2] = {0, 0}; // records of the last halo pack
     bool slab_ranks_valid = false;
+    bool slab_used = false;           // a slab call has compacted / appended particles: index-based constraints and bodies are refused from then on
     float lambda_xmin = -3.0e38f, lambda_xmax = 3.0e38f;
+    PsStreamIo io;
 };
 
 // internal helpers shared with the reference-ABI shim
@@ -129,6 +145,7 @@ u32 ps_ext_issue_shapes(PsCtx *c);
 u32 ps_ext_issue_sdf(PsCtx *c);  // world-frame SDF for the next contact pass (0 launches when no body carries one)
 u32 ps_ext_issue_viscosity(PsCtx *c, float dt);
 void ps_ext_free(PsCtx *c);
+void ps_io_free(PsCtx *c);  // ps_stream_io.cu
 
 // stage issue functions on explicit arrays (used by both ABIs); each returns the number of launches issued
 u32 ps_issue_build_grid(PsCtx *c, const float4 *pos);

@@ -40,7 +40,7 @@ extern "C" int ps_add_rigid_body(PsCtx *c, const uint32_t *indices, uint64_t n, 
     if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
     if (!indices || n < 2) { ps_set_error("ps_add_rigid_body: a rigid body needs at least 2 particles"); return PS_ERR_INVALID; }
     if (!(stiffness > 0.f && stiffness <= 1.f)) { ps_set_error("ps_add_rigid_body: stiffness must be in (0, 1]"); return PS_ERR_INVALID; }
-    if (c->n_ghost) { ps_set_error("ps_add_rigid_body: index-based constraints are not supported on slab contexts"); return PS_ERR_STATE; }
+    if (c->n_ghost || c->slab_used) { ps_set_error("ps_add_rigid_body: index-based constraints are not supported on slab contexts"); return PS_ERR_STATE; }
     for (uint64_t k = 0; k < n; k++)
         if (indices[k] >= c->n) { ps_set_error("ps_add_rigid_body: particle index %u >= %u particles", indices[k], c->n); return PS_ERR_INVALID; }
     DevGuard dg(c->device);

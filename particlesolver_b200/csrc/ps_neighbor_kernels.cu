@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
                                                     const float4 *__restrict__ spos, const float *__restrict__ sw,
                                                     const int *__restrict__ sphase, const u32 *__restrict__ index,
                                                     const u32 *__restrict__ cell_begin, u32 *__restrict__ num_neighbors, u32 n, u32 n_owned,
-                                                    GridDesc g, StencilDesc st, float radius, const u32 *__restrict__ adj_off,
+                                                    GridDesc g, StencilDesc st, float radius, float omega, const u32 *__restrict__ adj_off,
                                                     const u32 *__restrict__ adj, const float4 *__restrict__ sdf_world) {
     const u32 i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
@@ -627,7 +627,8 @@ __global__ void __launch_bounds__(kBlock) k_collide(float4 *__restrict__ pos, co
         const float w = sw[i];
         const float sW = ps_scaled_w(w, pi.y);
         const float4 pp = __ldg(prev + orig);
-        const float fn = (float)nn;
+        // Jacobi averaging over the contacts (integration_kernel.cuh:436-437) with the SOR factor: delta * omega / numNeighbors
+        const float fn = (omega == 1.f) ? (float)nn : __fdividef((float)nn, omega);
         // SDF contacts between rigid bodies (ps_set_rigid_body_sdf; not in the reference's GPU solver): w < 0 (or NaN) = no SDF
         const float4 si = sdf_world ? __ldg(sdf_world + orig) : make_float4(0.f, 0.f, 0.f, -1.f);
         u32 seen = 0;
@@ -706,13 +707,13 @@ static void ps_optin_smem(int device) {
 }
 
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
-                       const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, const u32 *adj_off,
+                       const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, float omega, const u32 *adj_off,
                        const u32 *adj, const float4 *sdf_world, cudaStream_t s) {
     if (!n) return;
     StencilDesc st;  // 3x3x3: every row keeps its full extent (contact radius 2.001r slightly exceeds one cell)
     st.rad = 1;
     for (int k = 0; k < 9; k++) st.xr[k] = 1;
-    k_collide<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, prev, spos, sw, sphase, index, cell_begin, num_neighbors, n, n_owned, g, st, radius, adj_off, adj, sdf_world);
+    k_collide<<<cdiv(n, kBlock), kBlock, 0, s>>>(pos, prev, spos, sw, sphase, index, cell_begin, num_neighbors, n, n_owned, g, st, radius, omega, adj_off, adj, sdf_world);
 }
 
 // list regions for `capacity` particles (rows_per_warp rows of 32 entries per warp) + the staged K6's dump region + the read-ahead

@@ -132,7 +132,7 @@ void collide(float *particles, float *sortedPos, float *sortedW, int *sortedPhas
     PsCtx *c = ctx();
     need_dense(cellStart, numCells, "collide");
     ps_launch_collide((float4 *)particles, c->prev, (const float4 *)sortedPos, sortedW, sortedPhase, index, c->cell_begin, c->num_neighbors, n,
-                      n, c->grid, c->params.particle_radius, nullptr, nullptr, nullptr, c->stream);  // the reference ABI: the reference same-phase rule
+                      n, c->grid, c->params.particle_radius, 1.0f, nullptr, nullptr, nullptr, c->stream);  // the reference ABI: the reference same-phase rule
     ck_launch("collide");
 }
 
@@ -226,6 +226,32 @@ void printXstar(void) {
     printf("Xstar: size: %u\n", (uint)h.size());
     for (u32 i = 0; i < g_n_shared; i++) printf("i: %u: %.2f, %.2f, %.2f\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2]);
     printf("\n");
+}
+
+// ---------------------------------------------------------------- util.cu (the part without OpenGL) ----------------------------------------------------------------
+// gpu/src/cuda/util.cuh:6-25 / util.cu: device selection, raw device arrays and blocking copies for the host class
+// (particlesystem.cpp:95-142), launch-geometry helpers.  The four GL-interop entry points (register / unregister / map / unmap of the
+// position VBO) stay with the viewer: a headless host maps an ordinary device allocation (oracle/ref_gpu_glue.cu shows one).
+void cudaInit(void) {
+    // the reference picks the device with the most GFLOP/s (findCudaDevice); here: PS_DEVICE, else the current device
+    int dev = 0, count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { printf("No CUDA Capable devices found, exiting...\n"); exit(EXIT_SUCCESS); }
+    if (const char *e = getenv("PS_DEVICE")) dev = atoi(e);
+    else cudaGetDevice(&dev);
+    ck_cuda(cudaSetDevice(dev), "cudaInit");
+}
+void allocateArray(void **devPtr, int size) { ck_cuda(cudaMalloc(devPtr, (size_t)(unsigned int)size), "allocateArray"); }
+void freeArray(void *devPtr) { ck_cuda(cudaFree(devPtr), "freeArray"); }
+void copyArrayToDevice(void *device, const void *host, int offset, int size) {
+    ck_cuda(cudaMemcpy((char *)device + offset, host, (size_t)(unsigned int)size, cudaMemcpyHostToDevice), "copyArrayToDevice");
+}
+void copyArrayFromDevice(void *host, const void *device, int size) {
+    ck_cuda(cudaMemcpy(host, device, (size_t)(unsigned int)size, cudaMemcpyDeviceToHost), "copyArrayFromDevice");
+}
+uint iDivUp(uint a, uint b) { return (a % b != 0) ? (a / b + 1) : (a / b); }
+void computeGridSize(uint n, uint blockSize, uint &numBlocks, uint &numThreads) {
+    numThreads = std::min(blockSize, n);
+    numBlocks = iDivUp(n, numThreads);
 }
 
 // ---------------------------------------------------------------- additions ----------------------------------------------------------------

@@ -2,7 +2,11 @@
 // The reference's only front ends are two Qt viewers whose scenes are bound to keys (gpu/src/particleapp.cpp:141-215,
 // cpu/src/view.cpp:129-177); this runs the same scenes without a display, over libpsolver.so's public C / C++ API only:
 //   psolver_cli --app gpu --scene 7 --steps 600 [--dt 0.016667] [--grid 64] [--max-particles 15000] [--side 100]
-//               [--iterations 5] [--xsph 0.01 --vorticity 0.3] [--self-collision] [--gas]
+//               [--iterations 5] [--xsph 0.01 --vorticity 0.3] [--self-collision] [--gas] [--staged-lambda]
+//               [--emit]      the GPU app's fluid emitter switched on (key handling of particleapp.cpp:74-79: every 0.1 s of
+//                             simulated time addFluid((-1,0,-1),(1,1,1), mass 1, density 1) until the system is full)
+//               [--shoot K]   a left mouse click every K steps (particleapp.cpp:91-96): setParticleToAdd(eye, dir * 30, mass 2) —
+//                             the viewer takes eye and ray from its camera; headless: eye (0,10,30) looking at (0,5,0)
 //   psolver_cli --app cpu --scene 6 --steps 1000 [--dt 0.01] [--stabilization 2]
 //   psolver_cli --app session --script "6:100,1:50,w:20"     the CPU app as a user drives it: psb200::Simulation (constructor
 //               builds WRECKING_BALL), then key presses and ticks; the rand() stream runs on across scenes like the reference's
@@ -32,6 +36,8 @@ struct Args {
     float xsph = 0.f, vorticity = 0.f;
     bool json = false;
     unsigned flags = 0;  // PS_FLAG_* switched on from the command line
+    bool emit = false;       // --app gpu: fluid emitter on
+    int shoot = 0;           // --app gpu: shoot a particle every `shoot` steps (0 = never)
     int stabilization = -1;  // --app cpu: stabilization passes per tick (the reference's USE_STABILIZATION build: 2); -1 = leave as is
 };
 [[noreturn]] void die(const std::string &m) { fprintf(stderr, "psolver_cli: %s\n", m.c_str()); exit(1); }
@@ -71,22 +77,46 @@ int run_gpu(const Args &a) {
     }
     if (a.xsph != 0.f || a.vorticity != 0.f) check(ps_set_viscosity(ctx, a.xsph, a.vorticity), "ps_set_viscosity");
     const float dt = a.dt > 0 ? (float)a.dt : 1.f / 60.f;
-    const uint64_t n = ps_num_particles(ctx);
+    if ((a.emit || a.shoot) && !ps) die("--emit / --shoot need a scene built through the host class (not --load)");
+    const uint64_t n0 = ps_num_particles(ctx);
+    uint64_t n = n0;
     std::vector<float> pos(4 * n), vel(4 * n), w(n);
-    double dev_ms = 0;
+    double dev_ms = 0, psteps = 0;
+    float emit_timer = 0.f;   // ParticleApp::m_timer
+    bool full = false;        // an emitter batch was dropped because maxParticles was reached
     const auto t0 = std::chrono::steady_clock::now();
     for (int s = 1; s <= a.steps; s++) {
+        // ParticleApp::tick (particleapp.cpp:72-83): the emitter queues a block of fluid, then update() steps and appends what is queued
+        if (a.emit && emit_timer <= 0.f) {
+            ps->addFluid(make_int3(-1, 0, -1), make_int3(1, 1, 1), 1.f, 1.f, make_float3(0, 0, 1));
+            emit_timer = 0.1f;
+        }
+        emit_timer -= dt;
+        if (a.shoot > 0 && s % a.shoot == 0) {  // ParticleApp::mousePressed, left button
+            const float3 eye = make_float3(0.f, 10.f, 30.f);
+            const float len = std::sqrt(5.f * 5.f + 30.f * 30.f);
+            ps->setParticleToAdd(eye, make_float3(0.f, -5.f / len * 30.f, -30.f / len * 30.f), 2.f);
+        }
         if (ps) ps->update(dt); else check(ps_step(ctx, dt), "ps_step");
+        // a full system drops the emitter's batch and carries on, like the reference (particlesystem.cpp:335); anything else is fatal
+        if (ps && !ps->lastError().empty()) {
+            if (ps->lastError().find("batch dropped") == std::string::npos) die(ps->lastError());
+            full = true;
+        }
         float ms = 0;
         check(ps_last_step_ms(ctx, &ms), "ps_last_step_ms");
         dev_ms += ms;
+        psteps += (double)n;   // the step ran over the particles present before this step's appends
+        n = ps_num_particles(ctx);
         if (a.dump_every > 0 && s % a.dump_every == 0) {
+            pos.resize(4 * n);
             check(ps_download(ctx, PS_ARR_POS, pos.data(), 0, 4 * n), "ps_download");
             dump(a.out, s, pos.data(), 4, 4, n);
         }
     }
     check(ps_sync(ctx), "ps_sync");
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    pos.resize(4 * n); vel.resize(4 * n); w.resize(n);
     check(ps_download(ctx, PS_ARR_POS, pos.data(), 0, 4 * n), "ps_download");
     check(ps_download(ctx, PS_ARR_VEL, vel.data(), 0, 4 * n), "ps_download");
     check(ps_download(ctx, PS_ARR_INV_MASS, w.data(), 0, n), "ps_download");
@@ -99,11 +129,11 @@ int run_gpu(const Args &a) {
     double derr_mean = 0, derr_max = 0;
     check(ps_fluid_stats(ctx, &derr_mean, &derr_max, nullptr), "ps_fluid_stats");
     if (a.json)
-        printf("{\"app\": \"gpu\", \"scene\": \"%s\", \"particles\": %llu, \"steps\": %d, \"dt\": %.9g, \"device_ms_per_step\": %.4f, \"wall_ms_per_step\": %.4f, "
+        printf("{\"app\": \"gpu\", \"scene\": \"%s\", \"particles\": %llu, \"particles_at_start\": %llu, \"steps\": %d, \"dt\": %.9g, \"device_ms_per_step\": %.4f, \"wall_ms_per_step\": %.4f, "
                "\"particle_steps_per_s\": %.1f, \"kinetic_energy\": %.9g, \"position_checksum\": %.9g, \"launches_per_step\": %u, "
-               "\"density_error_mean\": %.6g, \"density_error_max\": %.6g}\n",
-               a.scene.c_str(), (unsigned long long)n, a.steps, dt, a.steps ? dev_ms / a.steps : 0., a.steps ? 1e3 * wall / a.steps : 0.,
-               dev_ms > 0 ? n * (double)a.steps / (dev_ms * 1e-3) : 0., ke, sum, ps_launches_per_step(ctx), derr_mean, derr_max);
+               "\"density_error_mean\": %.6g, \"density_error_max\": %.6g, \"emitter_hit_capacity\": %s}\n",
+               a.scene.c_str(), (unsigned long long)n, (unsigned long long)n0, a.steps, dt, a.steps ? dev_ms / a.steps : 0., a.steps ? 1e3 * wall / a.steps : 0.,
+               dev_ms > 0 ? psteps / (dev_ms * 1e-3) : 0., ke, sum, ps_launches_per_step(ctx), derr_mean, derr_max, full ? "true" : "false");
     else
         printf("gpu scene %s: %llu particles, %d steps, %.3f ms/step on the device (%.3f wall), KE %.6g\n", a.scene.c_str(), (unsigned long long)n, a.steps,
                a.steps ? dev_ms / a.steps : 0., a.steps ? 1e3 * wall / a.steps : 0., ke);
@@ -203,6 +233,9 @@ int main(int argc, char **argv) {
         else if (k == "--vorticity") a.vorticity = (float)atof(val());
         else if (k == "--self-collision") a.flags |= PS_FLAG_SELF_COLLISION;
         else if (k == "--gas") a.flags |= PS_FLAG_GAS;
+        else if (k == "--staged-lambda") a.flags |= PS_FLAG_STAGED_LAMBDA;
+        else if (k == "--emit") a.emit = true;
+        else if (k == "--shoot") a.shoot = atoi(val());
         else if (k == "--stabilization") a.stabilization = atoi(val());
         else if (k == "--device") a.device = atoi(val());
         else if (k == "--json") a.json = true;

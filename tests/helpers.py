@@ -27,6 +27,7 @@ def oracle_from_solver(sol: "psb.Solver"):
                          sol.download(psb.ARR_PHASE), sol.download(psb.ARR_REST_DENSITY), didx, drest, pidx, pxyz,
                          iterations=int(p.solver_iterations))
     o.self_collision = bool(p.flags & psb.FLAG_SELF_COLLISION)
+    o.omega = float(p.omega)
     return o
 
 

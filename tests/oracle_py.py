@@ -58,6 +58,8 @@ def lib():
         L.or_state_new.restype = vp
         L.or_state_free.argtypes = [vp]
         L.or_fluid_stats.argtypes = [vp, vp, vp, vp, vp, vp, P, vp]
+        L.or_set_omega.argtypes = [f32]
+        L.or_set_omega.restype = None
         for f in ("or_state_hash", "or_state_index", "or_state_cell_start", "or_state_cell_end", "or_state_num_neighbors",
                   "or_state_lambda", "or_state_sorted_pos"):
             getattr(L, f).argtypes = [vp]
@@ -119,6 +121,7 @@ class OracleSystem:
         self.occ = np.zeros(n, np.uint32)
         lib().or_occurrences(_p(self.occ), n, _p(self.dist_idx), self.dist_rest.size, _p(self.point_idx), self.point_idx.size)
         self.dist_nonprefix = 0
+        self.omega = 1.0             # SOR factor on the averaged deltas (PsParams.omega); 1 == the reference
         self.self_collision = False  # True: the opt-in rule of PS_FLAG_SELF_COLLISION (not the reference's)
         self._adj = None
         self.sdf_world = None        # (n, 4) float32 by particle index: world-frame SDF of rigid-body particles (ps_set_rigid_body_sdf), depth < 0 = none
@@ -152,6 +155,7 @@ class OracleSystem:
         return self._adj
 
     def collide(self):
+        lib().or_set_omega(self.omega)
         use_adj = self.self_collision and self.dist_rest.size
         if use_adj or self.sdf_world is not None:
             off, adj = self._adjacency() if use_adj else (None, None)
@@ -164,11 +168,13 @@ class OracleSystem:
                          _p(self.cell_end), self.n, C.byref(self.p), _p(self.nn))
 
     def solve_fluids(self):
+        lib().or_set_omega(self.omega)
         lib().or_solve_fluids(_p(self.spos), _p(self.sw), _p(self.sphase), _p(self.index), _p(self.cell_start), _p(self.cell_end),
                               _p(self.pos), self.n, C.byref(self.p), _p(self.ros), _p(self.lam), _p(self.nn))
 
     def solve_fluids_stage(self, stages):
         """1: lambdas only, 2: delta p only (from the lambdas in self.lam), 3: both"""
+        lib().or_set_omega(self.omega)
         lib().or_solve_fluids_stages(_p(self.spos), _p(self.sw), _p(self.sphase), _p(self.index), _p(self.cell_start), _p(self.cell_end),
                                      _p(self.pos), self.n, C.byref(self.p), _p(self.ros), _p(self.lam), _p(self.nn), int(stages))
 
@@ -177,6 +183,7 @@ class OracleSystem:
         lib().or_collide_world(_p(self.pos), _p(self.prev), _p(self.phase), self.n, _p(r), C.byref(self.p))
 
     def solve_distance(self):
+        lib().or_set_omega(self.omega)
         self.dist_nonprefix |= lib().or_solve_distance(_p(self.pos), _p(self.dist_idx), _p(self.dist_rest), self.dist_rest.size, _p(self.occ), self.n)
 
     def solve_point(self):

@@ -40,7 +40,7 @@ def test_psolver2d_h_symbols_exported():
 
 
 def test_reference_abi_symbols_exported():
-    """Same names as the reference's wrappers.cuh:12-97 and shared_variables.cuh:13-36."""
+    """Same names as the reference's wrappers.cuh:12-97, shared_variables.cuh:13-36 and the non-GL part of util.cuh:6-25."""
     L = psb.lib()
     names = _declared("ps_reference_abi.h", r"^\s*(?:void|int|float|uint)\s*\*?\s*([A-Za-z_][A-Za-z_0-9]*)\s*\(")
     names = [n for n in names if n not in ("defined",)]
@@ -48,7 +48,8 @@ def test_reference_abi_symbols_exported():
                           "calcHash", "sortParticles", "reorderDataAndFindCellStart", "collideWorld", "collide", "sortByType",
                           "calcVelocity", "solveFluids", "appendSolverParticle", "addPointConstraint", "addDistanceConstraint",
                           "freeSolverVectors", "solvePointConstraints", "solveDistanceConstraints", "freeSharedVectors",
-                          "appendPhaseAndMass", "copyToXstar", "getPhaseRawPtr", "getXstarRawPtr", "getWRawPtr", "printXstar"]
+                          "appendPhaseAndMass", "copyToXstar", "getPhaseRawPtr", "getXstarRawPtr", "getWRawPtr", "printXstar",
+                          "cudaInit", "allocateArray", "freeArray", "copyArrayToDevice", "copyArrayFromDevice", "iDivUp", "computeGridSize"]
     for n in reference_wrappers:
         assert n in names, f"{n} not declared in ps_reference_abi.h"
     missing = [n for n in names if not hasattr(L, n)]

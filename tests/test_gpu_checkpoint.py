@@ -45,6 +45,40 @@ def test_3d_checkpoint_continues_bit_identically(scene, tmp_path):
     ps.close()
 
 
+def test_3d_checkpoint_carries_the_stale_lambdas_of_solids_next_to_fluid(tmp_path):
+    """K6 leaves lambda of non-fluid sorted slots untouched and K7 reads lambda_j of every neighbour (the reference's behaviour,
+    integration_kernel.cuh:596-642): with fluid resting against solids those values are state that crosses steps, so the
+    checkpoint (format v3) carries the lambda array.  Fluid block between two solid blocks, in contact from the first step."""
+    def block(x0, x1, phase, rho0):
+        g = np.mgrid[x0:x1:0.5, 0.25:4.0:0.5, -2.0:2.0:0.5].reshape(3, -1).T.astype(np.float32)
+        pos = np.ones((g.shape[0], 4), np.float32)
+        pos[:, :3] = g
+        k = g.shape[0]
+        return pos, np.zeros((k, 4), np.float32), np.ones(k, np.float32), np.full(k, rho0, np.float32), np.full(k, phase, np.int32)
+    parts = [block(-4.0, -2.0, psb.SOLID, 1.0), block(-2.0, 2.0, psb.FLUID, 1.5), block(2.0, 4.0, psb.SOLID, 1.0)]
+    n = sum(p[0].shape[0] for p in parts)
+    prm = psb.default_params()
+    sol = psb.Solver(prm, max_particles=n)
+    for p in parts:
+        sol.append(*p)
+    for _ in range(6):
+        sol.step(1 / 60)
+    # the premise: some solid slot holds a non-zero (stale) lambda, and it neighbours fluid
+    lam, sph = sol.download(psb.ARR_LAMBDA), sol.download(psb.ARR_SORTED_PHASE)
+    assert np.any(lam[sph != psb.FLUID] != 0.0)
+    path = str(tmp_path / "mixed.psb")
+    sol.save(path)
+    for _ in range(6):
+        sol.step(1 / 60)
+    re = psb.Solver.load(path)
+    for _ in range(6):
+        re.step(1 / 60)
+    assert np.array_equal(re.download(psb.ARR_POS), sol.download(psb.ARR_POS))
+    assert np.array_equal(re.download(psb.ARR_VEL), sol.download(psb.ARR_VEL))
+    re.close()
+    sol.close()
+
+
 @pytest.mark.parametrize("key", ["w", "8", "0", "2", "v"])
 def test_2d_checkpoint_continues_bit_identically(key, tmp_path):
     sim = psb.Simulation2D.scene(key)
@@ -103,3 +137,39 @@ def test_2d_tick_graph_replay_equals_eager_issue():
                            env=dict(os.environ, PS_NO_GRAPH="1")).stdout
         a, b = json.loads(a), json.loads(b)
         assert a["kinetic_energy"] == b["kinetic_energy"] and a["rand_calls"] == b["rand_calls"] and a["particles"] == b["particles"], key
+
+
+def test_cli_emitter_and_shooting_grow_the_system_until_it_is_full():
+    """The GPU app's run-time emission paths, headless: the fluid-emitter toggle (particleapp.cpp:74-79: addFluid of a
+    3 x 1 x 3 block every 0.1 s) and the mouse shot (:91-96: setParticleToAdd).  The particle count changes between steps, so the step's
+    CUDA graph is re-captured again and again; a batch that would reach maxParticles is dropped ('>=', particlesystem.cpp:335) and the
+    run carries on."""
+    def run(*extra):
+        r = subprocess.run([CLI, "--app", "gpu", "--scene", "1", "--json", *extra], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    base = run("--steps", "60")
+    assert base["particles"] == base["particles_at_start"] == 32
+    grown = run("--steps", "60", "--emit", "--shoot", "7")
+    # 60 steps of 1/60 s: a block at step 1 and then every 0.1 s (9 fluid particles each: ceil(2) / 0.625 = 3 per axis in x and z, ceil(1) / 0.625 = 1 in y), a shot every 7 steps
+    assert grown["particles"] > 32 + 9 * 9 and grown["emitter_hit_capacity"] is False
+    assert np.isfinite(grown["kinetic_energy"]) and np.isfinite(grown["position_checksum"])
+    full = run("--steps", "120", "--emit", "--max-particles", "80")
+    assert full["emitter_hit_capacity"] is True and 32 < full["particles"] < 80      # the batch that would reach 80 was dropped
+    assert np.isfinite(full["kinetic_energy"])
+
+
+def test_host_class_emission_matches_between_graph_and_eager_issue():
+    """growing n mid-run through the host class: the graph-replayed run (re-captured whenever n changes) equals the eagerly issued one"""
+    import os as _os
+    outs = []
+    for no_graph in (False, True):
+        env = dict(_os.environ)
+        if no_graph:
+            env["PS_NO_GRAPH"] = "1"
+        r = subprocess.run([CLI, "--app", "gpu", "--scene", "7", "--steps", "40", "--emit", "--shoot", "5", "--json"], capture_output=True, text=True,
+                           timeout=300, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0]["particles"] == outs[1]["particles"] > outs[0]["particles_at_start"]
+    assert outs[0]["position_checksum"] == outs[1]["position_checksum"] and outs[0]["kinetic_energy"] == outs[1]["kinetic_energy"]

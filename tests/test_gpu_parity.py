@@ -85,6 +85,36 @@ def test_stage_by_stage_vs_oracle(scene, kw):
     ps.close()
 
 
+@pytest.mark.parametrize("omega", [0.5, 1.5])
+@pytest.mark.parametrize("scene", ["7", "5", "2", "8"])
+def test_sor_omega_stage_by_stage_vs_oracle(scene, omega):
+    """PsParams.omega ("Jacobi averaging with SOR"): every averaged delta — contacts (K5), PBF delta-p (K7), distance constraints
+    (K9) — scaled by omega, stage by stage against the oracle carrying the same factor (oracle/gpu_step_oracle.c: or_set_omega);
+    scenes: fluid blob, solids on the floor (contacts + friction), cloth (distance constraints), the combo.  omega = 1 is the
+    reference and is what every other test runs."""
+    ps = psb.ParticleSystem.scene(scene)
+    sol = ps.solver
+    p = sol.params
+    p.omega = omega
+    sol.set_params(p)
+    worst = staged_compare(ps, steps=2)
+    print(scene, omega, {k: f"{v:.2e}" for k, v in worst.items()})
+    # and omega does something: the same two steps at omega = 1 end elsewhere
+    a = sol.download(psb.ARR_POS).copy()
+    ps.close()
+    ps = psb.ParticleSystem.scene(scene)
+    for _ in range(2):
+        for f in (ps.solver.begin_step,):
+            f()
+        ps.solver.predict(DT)
+        for it in range(int(ps.solver.params.solver_iterations)):
+            ps.solver.build_grid(); ps.solver.solve_contacts(); ps.solver.solve_fluid(); ps.solver.collide_world(it)
+            ps.solver.solve_distance(); ps.solver.solve_point()
+        ps.solver.update_velocity(DT)
+    assert H.max_abs(a, ps.solver.download(psb.ARR_POS)) > 1e-3
+    ps.close()
+
+
 @pytest.mark.parametrize("scene", ["7", "3", "5", "8"])
 def test_whole_step_vs_oracle(scene):
     """ParticleSystem::update (CUDA graph path) against the oracle's whole step, 3 steps, no re-synchronisation."""

@@ -111,3 +111,41 @@ def test_sort_is_stable_and_handles_edge_cases():
         orc.lib().or_sort(k2.ctypes.data, i2.ctypes.data, n)
         order = np.argsort(keys, kind="stable")
         assert np.array_equal(i2, order.astype(np.uint32)) and np.array_equal(k2, keys[order])
+
+
+def test_oracle_omega_scales_the_averaged_deltas():
+    """or_set_omega: the PBF delta-p and the distance-constraint correction are linear in omega (omega = 1 is the pinned reference
+    path, every golden test above runs it); contacts are not (friction sees the scaled delta), so they are only checked to move."""
+    import oracle_py as orc
+    rng = np.random.default_rng(3)
+    n = 4000
+    pos = np.ones((n, 4), np.float32)
+    pos[:, :3] = rng.uniform(2.0, 8.0, size=(n, 3)).astype(np.float32)
+    p = orc.make_params(grid=(64, 64, 64))
+    deltas = {}
+    for om in (1.0, 0.5, 1.5):
+        o = orc.OracleSystem(p, pos, np.zeros((n, 4), np.float32), np.ones(n, np.float32), np.zeros(n, np.int32), np.full(n, 8.0, np.float32))
+        o.omega = om
+        o.build_grid()
+        o.solve_fluids()
+        deltas[om] = (o.pos - pos)[:, :3].astype(np.float64)
+    scale = np.abs(deltas[1.0]).max()
+    assert scale > 1e-3
+    for om in (0.5, 1.5):
+        assert np.abs(deltas[om] - om * deltas[1.0]).max() <= 2e-6 * max(1.0, scale)
+    # distance constraints: a stretched chain
+    m = 50
+    cpos = np.ones((m, 4), np.float32)
+    cpos[:, 0] = np.arange(m) * 0.7
+    cpos[:, 1] = 5.0
+    idx = np.stack([np.arange(m - 1), np.arange(1, m)], 1).astype(np.uint32)
+    rest = np.full(m - 1, 0.5, np.float32)
+    d = {}
+    for om in (1.0, 0.5):
+        o = orc.OracleSystem(p, cpos, np.zeros((m, 4), np.float32), np.ones(m, np.float32), np.full(m, 2, np.int32), np.ones(m, np.float32),
+                             dist_idx=idx, dist_rest=rest)
+        o.omega = om
+        o.solve_distance()
+        d[om] = (o.pos - cpos)[:, :3].astype(np.float64)
+    assert np.abs(d[1.0]).max() > 1e-2 and np.abs(d[0.5] - 0.5 * d[1.0]).max() <= 4e-6  # float32 positions near x = 35: ulp 3.8e-6
+    orc.lib().or_set_omega(1.0)
