@@ -1539,10 +1539,11 @@ extern "C" int ps2d_load(const char *path, int device, Ps2dCtx **out) {
               get2(fp, fem.data(), fem.size()) && get2(fp, lk.data(), lk.size());
     if (!ok) { ps_set_error("ps2d_load: truncated file %s", path); return PS_ERR_INVALID; }
     for (size_t b = 0; b < nb; b++) if ((uint64_t)bf[b] + bc[b] > n) { ps_set_error("ps2d_load: body out of range"); return PS_ERR_INVALID; }
-    // index fields that address device arrays: body of a particle in [-1, bodies), constraint group in [-1, STANDARD records),
-    // emitters' STANDARD record (UINT32_MAX = none)
+    // index fields that address device arrays.  `bod` is the reference's free-form body tag (fluids carry 100 * frand(), ropes -2 / -3,
+    // simulation.cpp:411,865,1045); only a SOLID particle's non-negative tag indexes the body table (sdf_data).  Constraint group in
+    // [-1, STANDARD records); emitters' STANDARD record (UINT32_MAX = none).
     for (size_t k = 0; k < n; k++)
-        if (bod[k] < -1 || bod[k] >= (int)nb || grp[k] < -1 || (grp[k] >= 0 && (uint64_t)grp[k] >= h.num_standard)) { ps_set_error("ps2d_load: particle %zu refers to a body / constraint group that does not exist", k); return PS_ERR_INVALID; }
+        if ((ph[k] == PS2D_PHASE_SOLID && bod[k] >= (int)nb) || grp[k] < -1 || (grp[k] >= 0 && (uint64_t)grp[k] >= h.num_standard)) { ps_set_error("ps2d_load: particle %zu refers to a body / constraint group that does not exist", k); return PS_ERR_INVALID; }
     for (const EmitRecord &e : em) if (e.standard_index != 0xffffffffu && e.standard_index >= h.num_standard) { ps_set_error("ps2d_load: emitter refers to a missing STANDARD record"); return PS_ERR_INVALID; }
     for (const FluidEmitRecord &e : fem) if (e.standard_index != 0xffffffffu && e.standard_index >= h.num_standard) { ps_set_error("ps2d_load: fluid emitter refers to a missing STANDARD record"); return PS_ERR_INVALID; }
     for (const StdRecord &o : st) if (o.kind > STD_DISTANCE || (o.kind == STD_DISTANCE && (o.i1 >= n || o.i2 >= n))) { ps_set_error("ps2d_load: bad STANDARD record"); return PS_ERR_INVALID; }
