@@ -17,6 +17,7 @@
 // These kernels are bound by FP32 issue and L1 bandwidth, not HBM: ~370 candidate tests and
 // ~140 interactions per particle against 36-64 compulsory bytes.
 #include <algorithm>
+#include <cstdlib>
 #include <cuda/std/type_traits>
 #include "ps_common.cuh"
 #include "ps_fluid_lists.cuh"
@@ -330,6 +331,233 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
     const float inv_w = __fdividef(1.f, sw[i]);
     lambda[i] = ps_lambda_from_sums(ro, denom, gx, gy, gz, inv_w, inv_ro0);
     num_neighbors[i] = nn;
+}
+
+// ------------------------------------------------------------------ K6: lambda, fused walk (the default with lists) ------------------------------------------------------------------
+// The grid walk with the distance test, the interaction and the list append fused into ONE predicated body per candidate — no accept
+// queue, no flush, no votes inside the walk.  Measured on the queue form above (ncu source counters, profiles/r2e): 27 SASS instructions
+// per candidate for the test + queue, then 48 per queue slot for the flush (guard, slot and position re-read, interaction, list
+// store) = ~15.9 k warp-instructions per warp; the fused body is ~38 per candidate = ~10.8 k.  Running the interaction for rejected
+// candidates as well (30 % of them, predicated off) is cheaper than separating them.
+//   * phase 1 is the walk's: per z-slab every lane writes its non-empty row ranges [begin, end) to a list in shared memory;
+//   * phase 2: flat loop, trip count = the warp's largest candidate total of the slab; a candidate's float4 is requested two trips
+//     ahead (LDG.128 through L1, predicated on the lane still having candidates) and carries its own sorted slot in .w
+//     (ps_launch_reorder(..., slot_in_w)), so the walk tracks nothing but a slot counter and the end of the current range;
+//   * an accepted neighbour's slot goes straight to the lane's column of the warp's list region (ps_fluid_lists.cuh).
+// Arithmetic: PS_K6_BODY is, association for association, ps_lambda_terms (ps_fluid_lists.cuh) — every K6 variant gives the same bits.
+#ifndef PS_FUSED_MINB
+#define PS_FUSED_MINB 7  // resident CTAs the register allocation aims at: 7 (71 registers) measured 0-3 % faster than 8 (64 registers), profiles/r2i
+#endif
+static inline size_t fused_smem_bytes(int rad) { return (size_t)(2 * (2 * rad + 1) + 1) * kBlock * sizeof(uint2); }
+
+#define PS_K6_FUSED_VISIT(X, Y, Z, W, T, TNEXT, EXTRA_PRED)                                                                      \
+    asm volatile("{\n\t"                                                                                                          \
+                 ".reg .pred p, q, e, lv;\n\t"                                                                                    \
+                 ".reg .f32 rx, ry, rz, r2, ir, rl, h2, hh, hm, a, c, cc;\n\t"                                                     \
+                 ".reg .b32 jc;\n\t"                                                                                              \
+                 ".reg .b64 wa, la;\n\t"                                                                                          \
+                 "sub.ftz.f32 rx, %13, %8;\n\t"                                                                                   \
+                 "sub.ftz.f32 ry, %14, %9;\n\t"                                                                                   \
+                 "sub.ftz.f32 rz, %15, %10;\n\t"                                                                                  \
+                 "mov.b32 jc, %11;\n\t"                                                                                           \
+                 "setp.lt.u32 lv, %19, %20;\n\t"                                                                                  \
+                 "mul.wide.u32 la, %5, 16;\n\t"                                                                                   \
+                 "add.u64 la, la, %24;\n\t"                                                                                       \
+                 "@lv ld.global.nc.v4.b32 {%8, %9, %10, %11}, [la];\n\t"                                                          \
+                 "@lv add.u32 %5, %5, 1;\n\t"                                                                                     \
+                 "setp.eq.and.u32 e, %5, %6, lv;\n\t"                                                                             \
+                 "@e ld.shared.v2.u32 {%5, %6}, [%7];\n\t"                                                                        \
+                 "@e add.u32 %7, %7, %21;\n\t"                                                                                    \
+                 "mul.ftz.f32 r2, ry, ry;\n\t"                                                                                    \
+                 "fma.rn.ftz.f32 r2, rx, rx, r2;\n\t"                                                                             \
+                 "fma.rn.ftz.f32 r2, rz, rz, r2;\n\t"                                                                             \
+                 "setp.lt.ftz.f32 p, r2, 0f40800000;\n\t"                                                                         \
+                 "setp.lt.and.u32 p, %18, %20, p;\n\t"                                                                            \
+                 "setp.ne.and.u32 p, jc, %16, p;\n\t" EXTRA_PRED                                                                  \
+                 "rsqrt.approx.ftz.f32 ir, r2;\n\t"                                                                               \
+                 "mul.ftz.f32 rl, r2, ir;\n\t"                                                                                    \
+                 "sub.ftz.f32 h2, 0f40800000, r2;\n\t"                                                                            \
+                 "mul.ftz.f32 hh, h2, h2;\n\t"                                                                                    \
+                 "@p fma.rn.ftz.f32 %0, h2, hh, %0;\n\t"                                                                          \
+                 "sub.ftz.f32 hm, 0f40000000, rl;\n\t"                                                                            \
+                 "setp.ge.and.ftz.f32 q, rl, 0f38D1B717, p;\n\t"                                                                  \
+                 "mul.ftz.f32 a, hm, %17;\n\t"                                                                                    \
+                 "mul.ftz.f32 a, hm, a;\n\t"                                                                                      \
+                 "mul.ftz.f32 c, ir, a;\n\t"                                                                                      \
+                 "@q fma.rn.ftz.f32 %1, rx, c, %1;\n\t"                                                                           \
+                 "@q fma.rn.ftz.f32 %2, ry, c, %2;\n\t"                                                                           \
+                 "@q fma.rn.ftz.f32 %3, rz, c, %3;\n\t"                                                                           \
+                 "mul.ftz.f32 cc, c, c;\n\t"                                                                                      \
+                 "@q fma.rn.ftz.f32 %4, r2, cc, %4;\n\t"                                                                          \
+                 "cvt.u64.u32 wa, %12;\n\t"                                                                                       \
+                 "add.u64 wa, wa, %23;\n\t"                                                                                       \
+                 "@p st.global.cs.u32 [wa], jc;\n\t"                                                                              \
+                 "@p add.u32 %12, %12, 128;\n\t"                                                                                  \
+                 "}"                                                                                                              \
+                 : "+f"(ro), "+f"(gxs), "+f"(gys), "+f"(gzs), "+f"(denom), "+r"(jn), "+r"(jend), "+r"(sp), "+f"(X), "+f"(Y), "+f"(Z), "+r"(W), "+r"(woff) \
+                 : "f"(pi.x), "f"(pi.y), "f"(pi.z), "r"(i), "f"(cs), "r"(T), "r"(TNEXT), "r"(total), "r"((u32)(kBlock * sizeof(uint2))), "r"(room),  \
+                   "l"(wfirst_p), "l"(spos)                                                                            \
+                 : "memory")
+
+template <int RAD>
+__global__ void __launch_bounds__(kBlock, PS_FUSED_MINB) k_find_lambdas_fused(float *__restrict__ lambda, u32 *__restrict__ num_neighbors,
+                                                               const float4 *__restrict__ spos, const float *__restrict__ sw,
+                                                               const int *__restrict__ sphase, const u32 *__restrict__ index,
+                                                               const u32 *__restrict__ cell_begin, const float *__restrict__ ros, u32 n,
+                                                               u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g, StencilDesc st,
+                                                               int zero_nonfluid, u32 *__restrict__ pool, u32 *__restrict__ recs, u32 list_rows,
+                                                               size_t dump_offset) {
+    extern __shared__ __align__(16) uint2 fused_segs[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 i = blockIdx.x * kBlock + tid;
+    const u32 warp = i >> 5;
+    const bool warp_in = (u64)warp * 32 < n;
+    u32 *rec = recs + (size_t)warp * kListRecord;
+    bool act = i < n;
+    u32 orig = 0;
+    if (act) {
+        if (sphase[i] != PH_FLUID) {
+            if (zero_nonfluid) lambda[i] = 0.f;
+            act = false;
+        } else {
+            orig = index[i];
+        }
+    }
+    const float4 origin = make_float4(g.ox, g.oy, g.oz, 0.f);
+    float4 pi = act ? spos[i] : origin;
+    // ghost copies of a neighbour slab's particles: lambda only inside [ghost_xmin, ghost_xmax] (see k_find_lambdas)
+    if (act && orig >= n_owned && !(pi.x >= ghost_xmin && pi.x <= ghost_xmax)) act = false;
+    if (!__any_sync(kFull, act)) {
+        if (lane == 0 && warp_in) rec[0] = 0;
+        return;
+    }
+    if (!act) pi = origin;
+    const float ro0 = act ? ros[orig] : 1.f;
+    const float inv_ro0 = __fdividef(1.f, ro0);
+    const float cs = -PS_SPIKY * inv_ro0;
+
+    const int rad = RAD ? RAD : st.rad;
+    const int nseg = 2 * (2 * rad + 1);  // list capacity per slab: every row may wrap into two ranges (+ one spare entry the refill may read)
+    uint2 *segs = fused_segs + tid;      // entry s of this lane at segs[s * kBlock]
+    const u32 seg_addr = (u32)__cvta_generic_to_shared(segs);
+    const u32 seg_stride = (u32)(kBlock * sizeof(uint2));
+    const float relx = pi.x - g.ox, rely = pi.y - g.oy, relz = pi.z - g.oz;
+    const int3 gp = ps_grid_pos(g, pi.x, pi.y, pi.z);
+    // margin: covers the approximate divide of the cell assignment and coordinate rounding (ulp(1000) = 6e-5)
+    const float eps = 1e-3f + 2e-6f * fmaxf(fabsf(relx), fmaxf(fabsf(rely), fabsf(relz)));
+    const float inv_cx = __fdividef(1.f, g.cx);
+    const float fy0 = fmaxf(rely - (float)gp.y * g.cy, 0.f), fy1 = fmaxf((float)(gp.y + 1) * g.cy - rely, 0.f);
+    const float fz0 = fmaxf(relz - (float)gp.z * g.cz, 0.f), fz1 = fmaxf((float)(gp.z + 1) * g.cz - relz, 0.f);
+    auto dmin2 = [&](int d, float f0, float f1, float c) {  // squared distance to the slab of cells at offset d, minus margin
+        float m = d == 0 ? 0.f : (d > 0 ? f1 + (float)(d - 1) * c : f0 + (float)(-d - 1) * c);
+        m = fmaxf(m - eps, 0.f);
+        return m * m;
+    };
+    float ro = 0.f, denom = 0.f, gxs = 0.f, gys = 0.f, gzs = 0.f;
+    // the warp's list region: row k, entry lane = the k-th accepted neighbour of this lane (ps_fluid_lists.cuh)
+    u32 *wfirst_p = pool + (size_t)warp * list_rows * 32 + lane;
+    u32 woff = 0;  // bytes written to this lane's column: 128 per accepted neighbour
+    bool ovf = false;
+
+#pragma unroll 1
+    for (int dz = -rad; dz <= rad; dz++) {
+        // ---- phase 1: this lane's candidate ranges of the slab ----
+        const u32 rowmask = st.rowmask[dz + rad];  // uniform: rows no particle can reach
+        const u32 zrow = ((u32)(gp.z + dz) & g.mz) * g.gy;
+        const float remz = PS_H2 - dmin2(dz, fz0, fz1, g.cz);
+        u32 nlist = 0, total = 0;
+        auto push = [&](u32 b, u32 len) {
+            if (len) {
+                if (nlist >= (u32)nseg) __trap();
+                segs[nlist * kBlock] = make_uint2(b, b + len);
+                nlist++;
+                total += len;
+            }
+        };
+        auto do_row = [&](int dyi) {
+            if (!((rowmask >> dyi) & 1u)) return;
+            const int dy = dyi - rad;
+            const float rem = remz - dmin2(dy, fy0, fy1, g.cy);
+            u32 b0 = 0, len0 = 0, row = 0, hw = 0;
+            bool wrap = false;
+            if (act && rem >= 0.f) {
+                const float ext = sqrtf(rem) + eps;
+                int lo = (int)floorf((relx - ext) * inv_cx), hi = (int)floorf((relx + ext) * inv_cx);
+                lo = max(min(lo, gp.x), gp.x - rad);
+                hi = min(max(hi, gp.x), gp.x + rad);
+                row = (zrow + ((u32)(gp.y + dy) & g.my)) * g.gx;
+                const u32 lw = (u32)lo & g.mx;
+                hw = (u32)hi & g.mx;
+                wrap = lw > hw;  // the row wraps around the power-of-two grid: [lw, gx) then [0, hw]
+                b0 = __ldg(cell_begin + (row + lw));
+                len0 = __ldg(cell_begin + (row + (wrap ? g.mx : hw) + 1u)) - b0;
+            }
+            push(b0, len0);
+            if (__any_sync(kFull, wrap)) {
+                u32 b1 = 0, len1 = 0;
+                if (wrap) {
+                    b1 = __ldg(cell_begin + row);
+                    len1 = __ldg(cell_begin + (row + hw + 1u)) - b1;
+                }
+                push(b1, len1);
+            }
+        };
+        if (RAD) {
+#pragma unroll
+            for (int dyi = 0; dyi < 2 * RAD + 1; dyi++) do_row(dyi);
+        } else {
+#pragma unroll 1
+            for (int dyi = 0; dyi <= 2 * rad; dyi++) do_row(dyi);
+        }
+        // ---- phase 2: flat fused walk; the trip count is the warp's largest candidate total ----
+        const u32 maxtotal = __reduce_max_sync(kFull, total);
+        if (maxtotal == 0) continue;
+        // a lane's list would outgrow the warp's region (only when neighbor_list_rows < 500): the warp keeps no list from here on and
+        // K7 walks the grid for it; its writes land in the dump region behind the pool
+        if (!ovf && __any_sync(kFull, min((woff >> 7) + total, PS_MAX_NEIGHBORS) > list_rows)) {
+            ovf = true;
+            wfirst_p = pool + dump_offset + lane - (woff >> 2);
+        }
+        const bool capped = __any_sync(kFull, (woff >> 7) + total > PS_MAX_NEIGHBORS);  // the 500-neighbour cap can bite in this slab
+        __syncwarp();  // the lists are written and read by the same lane, but through different address expressions
+        // slot of the next candidate to request, end of its range, shared address of the next list entry
+        u32 jn = 0, jend = 0, sp = seg_addr;
+        if (total) { const uint2 s0 = segs[0]; jn = s0.x; jend = s0.y; sp += seg_stride; }
+        float X0 = pi.x, Y0 = pi.y, Z0 = pi.z, X1 = pi.x, Y1 = pi.y, Z1 = pi.z;
+        u32 W0 = i, W1 = i;
+        auto prime = [&](float &X, float &Y, float &Z, u32 &W, bool live) {
+            if (live) {
+                const float4 c4 = __ldg(spos + jn);
+                X = c4.x; Y = c4.y; Z = c4.z; W = __float_as_uint(c4.w);
+                if (++jn == jend) { const uint2 s1 = *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(fused_segs) + (sp - (u32)__cvta_generic_to_shared(fused_segs))); jn = s1.x; jend = s1.y; sp += seg_stride; }
+            }
+        };
+        prime(X0, Y0, Z0, W0, total > 0);
+        prime(X1, Y1, Z1, W1, total > 1);
+        if (!capped) {
+            const u32 room = 1u;
+#pragma unroll 2
+            for (u32 t = 0; t < maxtotal; t += 2) {
+                const u32 t1 = t + 1, t2 = t + 2, t3 = t + 3;
+                PS_K6_FUSED_VISIT(X0, Y0, Z0, W0, t, t2, "");
+                PS_K6_FUSED_VISIT(X1, Y1, Z1, W1, t1, t3, "");
+            }
+        } else {
+#pragma unroll 1
+            for (u32 t = 0; t < maxtotal; t += 2) {
+                const u32 t1 = t + 1, t2 = t + 2, t3 = t + 3;
+                u32 room = (woff >> 7) < PS_MAX_NEIGHBORS;
+                PS_K6_FUSED_VISIT(X0, Y0, Z0, W0, t, t2, "setp.ne.and.u32 p, %22, 0, p;\n\t");
+                room = (woff >> 7) < PS_MAX_NEIGHBORS;
+                PS_K6_FUSED_VISIT(X1, Y1, Z1, W1, t1, t3, "setp.ne.and.u32 p, %22, 0, p;\n\t");
+            }
+        }
+    }
+    if (lane == 0 && warp_in) rec[0] = ovf ? kListOverflow : 1u;
+    if (!act) return;
+    const float inv_w = __fdividef(1.f, sw[i]);
+    lambda[i] = ps_lambda_from_sums(ro, denom, gxs, gys, gzs, inv_w, inv_ro0);
+    num_neighbors[i] = woff >> 7;
 }
 
 // ------------------------------------------------------------------ K7: delta p ------------------------------------------------------------------
@@ -702,6 +930,7 @@ static void ps_optin_smem(int device) {
     static bool opted[64] = {};
     if (device < 0 || device >= 64 || opted[device]) return;
     cudaFuncSetAttribute(k_find_lambdas<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
+    cudaFuncSetAttribute(k_find_lambdas_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes(PS_MAX_RAD));
     cudaFuncSetAttribute(k_solve_fluids<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fluid_smem_bytes(PS_MAX_RAD));
     opted[device] = true;
 }
@@ -739,8 +968,20 @@ u32 ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos
                                       zero_nonfluid, nbr_list, nbr_rows, list_rows, list_region_elems(capacity, list_rows), device, s);
         return 1;
     }
-    const size_t sm = fluid_smem_bytes(st.rad);
     ps_optin_smem(device);
+    static const bool queue_walk = getenv("PS_K6_QUEUE_WALK") != nullptr;  // tuning aid: the queue form of the walk with lists
+    if (lists && slot_in_w && !queue_walk) {  // the default: fused walk
+        const size_t fsm = fused_smem_bytes(st.rad);
+        const size_t dump = list_region_elems(capacity, list_rows);
+        if (st.rad == 4)
+            k_find_lambdas_fused<4><<<cdiv(n, kBlock), kBlock, fsm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned,
+                                                                         ghost_xmin, ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, list_rows, dump);
+        else
+            k_find_lambdas_fused<0><<<cdiv(n, kBlock), kBlock, fsm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned,
+                                                                         ghost_xmin, ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, list_rows, dump);
+        return 1;
+    }
+    const size_t sm = fluid_smem_bytes(st.rad);
     u32 *pool = lists ? nbr_list : nullptr;
     if (st.rad == 4)  // the reference's configuration (H = 2, cell = 2r = 0.5): stencil loops fully unrolled
         k_find_lambdas<4><<<cdiv(n, kBlock), kBlock, sm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned, ghost_xmin,

@@ -1,0 +1,15 @@
+#!/bin/bash
+# r2i: fused-walk K6 (test + interaction + list append in one predicated body, L1 gathers two trips ahead): parity, A/B, ncu
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_extensions.py tests/test_gpu_full_size.py tests/test_gpu_headline_parity.py tests/test_gpu_slab.py -m gpu -q -x ) > gpurun_out/r2i_pytest.log 2>&1; echo "parity rc=$?"; tail -15 gpurun_out/r2i_pytest.log
+: > gpurun_out/r2i_variants.jsonl
+for w in 5 100; do
+  echo "--- warmup $w: fused / fused 7 CTAs / queue walk / staged"
+  timeout 300 python bench.py --quick --steps 20 --warmup $w | tee -a gpurun_out/r2i_variants.jsonl | cut -c1-560
+  PS_LIBRARY=$PWD/particlesolver_b200/libpsolver_f7.so timeout 300 python bench.py --quick --steps 20 --warmup $w | tee -a gpurun_out/r2i_variants.jsonl | cut -c1-560
+  PS_K6_QUEUE_WALK=1 timeout 300 python bench.py --quick --steps 20 --warmup $w | tee -a gpurun_out/r2i_variants.jsonl | cut -c1-560
+  PS_EXTRA_FLAGS=8 timeout 300 python bench.py --quick --steps 20 --warmup $w | tee -a gpurun_out/r2i_variants.jsonl | cut -c1-560
+done
+PS_NO_GRAPH=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_find_lambdas|k_solve_fluids' -s 8 -c 2 -o gpurun_out/prof_r2i python bench.py --quick --steps 2 --warmup 3 > gpurun_out/r2i_ncu_full.log 2>&1; echo "ncu full rc=$?"
+CS=/usr/local/cuda/bin/compute-sanitizer
+timeout 900 $CS --tool memcheck --print-limit 5 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "wrap or cap_500 or cell or paths_agree" > gpurun_out/r2i_sanitize_mem.log 2>&1; echo "sanitize mem rc=$? $(grep 'ERROR SUMMARY' gpurun_out/r2i_sanitize_mem.log | sort | uniq -c | tr '\n' ';')"; grep -E "passed|failed" gpurun_out/r2i_sanitize_mem.log | tail -1
