@@ -145,6 +145,10 @@ int ps_last_step_ms(PsCtx *ctx, float *ms);
  * are valid after ps_io_wait.  ps_io_wait(ctx, k) blocks until the outputs of the call made k calls ago (0 = the last) landed. */
 int ps_step_streamed(PsCtx *ctx, float dt, const float *pos_in, const float *vel_in, float *pos_out, float *vel_out);
 int ps_io_wait(PsCtx *ctx, uint32_t calls_back);
+/* the two halves of ps_step_streamed for callers that issue the step themselves (a slab context's step is a sequence of stage calls
+ * and exchanges): inputs before the step, outputs after it, over the OWNED particles; one begin and one end per step */
+int ps_io_begin(PsCtx *ctx, const float *pos_in, const float *vel_in);
+int ps_io_end(PsCtx *ctx, float *pos_out, float *vel_out);
 
 /* Device-time a region of work on the context's stream with CUDA events (stop synchronises). */
 int ps_timer_start(PsCtx *ctx);

@@ -101,6 +101,8 @@ def lib():
         L.ps_step.argtypes = [vp, f32]
         L.ps_step_streamed.argtypes = [vp, f32, vp, vp, vp, vp]
         L.ps_io_wait.argtypes = [vp, u32]
+        L.ps_io_begin.argtypes = [vp, vp, vp]
+        L.ps_io_end.argtypes = [vp, vp, vp]
         L.ps_sync.argtypes = [vp]
         L.ps_last_step_ms.argtypes = [vp, C.POINTER(f32)]
         for f in ("ps_begin_step", "ps_build_grid", "ps_solve_contacts", "ps_solve_fluid", "ps_solve_fluid_lambda", "ps_solve_fluid_delta", "ps_solve_distance",
@@ -333,6 +335,12 @@ class Solver:
         """ps_step_streamed: one step whose inputs / outputs are (pinned) host buffers given as raw addresses (or None); the transfers
         overlap the neighbouring calls' solver work.  io_wait(k) blocks until the outputs of the call made k calls ago have landed."""
         _check(lib().ps_step_streamed(self._h, dt, pos_in, vel_in, pos_out, vel_out))
+
+    def io_begin(self, pos_in=None, vel_in=None):
+        _check(lib().ps_io_begin(self._h, pos_in, vel_in))
+
+    def io_end(self, pos_out=None, vel_out=None):
+        _check(lib().ps_io_end(self._h, pos_out, vel_out))
 
     def io_wait(self, calls_back=0):
         _check(lib().ps_io_wait(self._h, calls_back))

@@ -124,7 +124,11 @@ int ps_sort_passes(u32 num_cells);
 // (kB,vB): input in A, result in A when `passes` is even and in B when it is odd (the caller picks where the
 // unsorted keys are written so that the result lands where it wants it).  1 + passes launches + 1 memset.
 // identity_vals: vals[i]==i on entry is assumed and vA is never read (saves one 4 B/particle read).
-void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool identity_vals, SortScratch sc, cudaStream_t s);
+void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool identity_vals, SortScratch sc, cudaStream_t s, bool hist_ready = false);
+// the fused form: ps_launch_sort_prepare (zeroes the sort's scratch), ps_launch_calc_hash_hist (K2 + the digit histograms of the keys it
+// writes), then ps_launch_sort(..., hist_ready = true)
+void ps_launch_sort_prepare(u32 n, int passes, SortScratch sc, cudaStream_t s);
+void ps_launch_calc_hash_hist(u32 *hash, const float4 *pos, u32 n, GridDesc g, int passes, u32 *hist, cudaStream_t s);
 // ps_neighbor_kernels.cu
 void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                        const u32 *cell_begin, u32 *num_neighbors, u32 n, u32 n_owned, GridDesc g, float radius, float omega, const u32 *adj_off,

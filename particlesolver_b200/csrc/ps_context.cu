@@ -454,14 +454,16 @@ u32 ps_issue_build_grid(PsCtx *c, const float4 *pos) {
     const bool odd = (c->sort_passes & 1) != 0;
     u32 *kA = odd ? c->hash_tmp : c->hash, *vA = odd ? c->index_tmp : c->index;
     u32 *kB = odd ? c->hash : c->hash_tmp, *vB = odd ? c->index : c->index_tmp;
-    ps_launch_calc_hash(kA, nullptr, pos, n, c->grid, s);
-    ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s);
+    const SortScratch sc = ps_ctx_sort_scratch(c, n);
+    ps_launch_sort_prepare(n, c->sort_passes, sc, s);
+    ps_launch_calc_hash_hist(kA, pos, n, c->grid, c->sort_passes, sc.hist, s);  // K2 + the sort's digit histograms
+    ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, sc, s, true);
     ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, pos, c->w, c->phase, n, c->num_cells, s, (c->params.flags & PS_FLAG_GAS) != 0, true);
     ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s);
     c->grid_valid = true;
     c->ref_tables_valid = false;
-    // kernels only (the memset node of the sort is not counted): calc_hash 1 + hist 1 + passes + reorder 1 + cell_begin 1
-    return 1 + 1 + (u32)c->sort_passes + 1 + 1;
+    // kernels only (the memset node of the sort is not counted): calc_hash + histograms 1, passes, reorder 1, cell_begin 1
+    return 1 + (u32)c->sort_passes + 1 + 1;
 }
 
 // PS_FLAG_GAS and the scene holds (or may hold) GAS particles: the prediction reads the phases for their buoyancy
@@ -683,8 +685,10 @@ extern "C" int ps_step_profiled(PsCtx *c, float dt, float *stage_ms, uint32_t *s
     u32 *kA = odd ? c->hash_tmp : c->hash, *vA = odd ? c->index_tmp : c->index;
     u32 *kB = odd ? c->hash : c->hash_tmp, *vB = odd ? c->index : c->index_tmp;
     for (u32 it = 0; it < iters; it++) {
-        ps_launch_calc_hash(kA, nullptr, c->pos, n, c->grid, s); mark(1, 1);
-        ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, ps_ctx_sort_scratch(c, n), s); mark(2, 1 + c->sort_passes);
+        const SortScratch sc = ps_ctx_sort_scratch(c, n);
+        ps_launch_sort_prepare(n, c->sort_passes, sc, s);
+        ps_launch_calc_hash_hist(kA, c->pos, n, c->grid, c->sort_passes, sc.hist, s); mark(1, 1);
+        ps_launch_sort(kA, vA, kB, vB, n, c->sort_passes, true, sc, s, true); mark(2, c->sort_passes);
         ps_launch_reorder(c->spos, c->sw, c->sphase, c->chunk_lb, c->hash, c->index, c->pos, c->w, c->phase, n, c->num_cells, s, (p.flags & PS_FLAG_GAS) != 0, true); mark(3, 1);
         ps_launch_cell_begin(c->cell_begin, c->hash, c->chunk_lb, n, c->num_cells, s); mark(4, 1);
         c->grid_valid = true;

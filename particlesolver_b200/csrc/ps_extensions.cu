@@ -234,7 +234,8 @@ extern "C" int ps_fluid_stats(PsCtx *c, double *mean_density_error, double *max_
     if (max_density_error) *max_density_error = 0.;
     if (kinetic_energy) *kinetic_energy = 0.;
     if (!c->n) return PS_OK;
-    if (c->n_ghost) { ps_set_error("ps_fluid_stats: not for slab contexts holding ghosts"); return PS_ERR_STATE; }
+    // a slab context: statistics over the OWNED particles, with the ghosts of the last halo refresh as their neighbours
+    const u32 n_owned = c->n - c->n_ghost;
     DevGuard dg(c->device);
     int r = ensure_visc_scratch(c);
     if (r != PS_OK) return r;
@@ -246,16 +247,18 @@ extern "C" int ps_fluid_stats(PsCtx *c, double *mean_density_error, double *max_
                             c->nbr_max_rows, c->num_neighbors, c->device, c->stream);
     std::vector<float> err(4 * (size_t)n), vel(4 * (size_t)n), w(n);
     std::vector<int> sph(n);
+    std::vector<u32> idx(n);
     XCU(cudaMemcpyAsync(err.data(), c->visc_scratch, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
     XCU(cudaMemcpyAsync(sph.data(), c->sphase, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    XCU(cudaMemcpyAsync(idx.data(), c->index, (size_t)n * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
     XCU(cudaMemcpyAsync(vel.data(), c->vel, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
     XCU(cudaMemcpyAsync(w.data(), c->w, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     XCU(cudaStreamSynchronize(c->stream));
     double sum = 0., mx = 0., ke = 0.;
     uint64_t cnt = 0;
     for (u32 i = 0; i < n; i++) {
-        if (sph[i] == PH_FLUID) { const double e = err[4 * (size_t)i]; sum += e; mx = std::max(mx, e); cnt++; }
-        if (w[i] != 0.f) ke += 0.5 * ((double)vel[4 * (size_t)i] * vel[4 * (size_t)i] + (double)vel[4 * (size_t)i + 1] * vel[4 * (size_t)i + 1] +
+        if (sph[i] == PH_FLUID && idx[i] < n_owned) { const double e = err[4 * (size_t)i]; sum += e; mx = std::max(mx, e); cnt++; }
+        if (i < n_owned && w[i] != 0.f) ke += 0.5 * ((double)vel[4 * (size_t)i] * vel[4 * (size_t)i] + (double)vel[4 * (size_t)i + 1] * vel[4 * (size_t)i + 1] +
                                        (double)vel[4 * (size_t)i + 2] * vel[4 * (size_t)i + 2]) / w[i];
     }
     if (mean_density_error) *mean_density_error = cnt ? sum / (double)cnt : 0.;

@@ -42,7 +42,14 @@ __device__ __forceinline__ float ps_lambda_from_sums(float ro, float denom, floa
     return -__fdividef(__fmaf_rn(rho, inv_ro0, -1.f), __fadd_rn(__fadd_rn(denom, g2), PS_RELAX));
 }
 
+// Keeps a loaded value "used" at this point of the program: without it the compiler sinks the gathers of a trip into the guarded
+// blocks that consume them (seen in the SASS of round 2's K7: LDG.128, wait, compute, next LDG.128 ...), which serialises the L1 / L2
+// round trips the trip was meant to overlap.
+__device__ __forceinline__ void ps_pin(float4 &v) { asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)); }
+__device__ __forceinline__ void ps_pin(float &v) { asm volatile("" : "+f"(v)); }
+
 // f(rx, ry, rz, j) for the cnt listed neighbours j of sorted slot i, in K6's traversal order.  L: this lane's column of its warp's region.
+// A trip requests U list rows, then the U positions they name (all in flight together), then runs the U bodies.
 template <class F>
 __device__ __forceinline__ void ps_for_each_listed(const u32 *__restrict__ L, u32 cnt, u32 i, float4 pi, const float4 *__restrict__ spos, F &&f) {
     constexpr int U = PS_LIST_READ_ROWS;
@@ -54,8 +61,30 @@ __device__ __forceinline__ void ps_for_each_listed(const u32 *__restrict__ L, u3
 #pragma unroll
         for (int k = 0; k < U; k++) pj[k] = __ldg(spos + j[k]);
 #pragma unroll
+        for (int k = 0; k < U; k++) ps_pin(pj[k]);
+#pragma unroll
         for (int k = 0; k < U; k++)
             if (r + k < cnt) f(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z, j[k]);
+    }
+}
+// the same for a body that also wants lambda_j (K7): f.apply(rx, ry, rz, lambda_j); the lambda gathers travel with the position gathers
+template <class F>
+__device__ __forceinline__ void ps_for_each_listed_lambda(const u32 *__restrict__ L, u32 cnt, u32 i, float4 pi, const float4 *__restrict__ spos,
+                                                          const float *__restrict__ lambda, F &&f) {
+    constexpr int U = PS_LIST_READ_ROWS;
+    for (u32 r = 0; r < cnt; r += U) {
+        u32 j[U];
+        float4 pj[U];
+        float lj[U];
+#pragma unroll
+        for (int k = 0; k < U; k++) j[k] = (r + k < cnt) ? __ldcs(L + (size_t)(r + k) * 32) : i;
+#pragma unroll
+        for (int k = 0; k < U; k++) { pj[k] = __ldg(spos + j[k]); lj[k] = __ldg(lambda + j[k]); }
+#pragma unroll
+        for (int k = 0; k < U; k++) { ps_pin(pj[k]); ps_pin(lj[k]); }
+#pragma unroll
+        for (int k = 0; k < U; k++)
+            if (r + k < cnt) f.apply(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z, lj[k]);
     }
 }
 __device__ __forceinline__ const u32 *ps_list_column(const u32 *pool, u32 warp, u32 list_rows, int lane) {

@@ -19,6 +19,53 @@ __global__ void __launch_bounds__(kBlock) k_calc_hash(u32 *__restrict__ hash, u3
     if (index) index[i] = i;  // the fused grid build sorts with implicit identity values and skips this write
 }
 
+// K2 fused with the radix sort's histogram kernel: the keys are in registers when they are written, so the 256-bin histograms of
+// all digit places (what k_radix_hist builds from a second read of the keys, ps_sort_kernels.cu) are accumulated here — one
+// launch and one 4 B/particle read less per grid build.  Shared-memory bins per CTA, a warp whose 32 keys share a digit adds 32
+// with one atomic (cell keys of consecutive particles share their high digits), non-empty bins flushed once per CTA.
+constexpr int kHashItems = 4;
+__global__ void __launch_bounds__(kBlock) k_calc_hash_hist(u32 *__restrict__ hash, const float4 *__restrict__ pos, u32 n, GridDesc g, int passes,
+                                                           u32 *__restrict__ hist) {
+    __shared__ u32 sh[4 * 256];
+    for (int i = threadIdx.x; i < passes * 256; i += kBlock) sh[i] = 0;
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31;
+    for (u32 base = blockIdx.x * (kBlock * kHashItems); base < n; base += gridDim.x * (kBlock * kHashItems)) {
+        u32 key[kHashItems];
+        bool ok[kHashItems];
+#pragma unroll
+        for (int k = 0; k < kHashItems; k++) {
+            const u32 i = base + k * kBlock + threadIdx.x;
+            ok[k] = i < n;
+            if (ok[k]) {
+                const float4 p = ld_stream4(pos + i);
+                key[k] = ps_grid_hash(g, ps_grid_pos(g, p.x, p.y, p.z));
+                hash[i] = key[k];
+            } else {
+                key[k] = 0xffffffffu;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kHashItems; k++) {
+            const bool full = __all_sync(0xffffffffu, ok[k]);  // (the loop bounds are CTA-uniform: every warp arrives here whole)
+            for (int p = 0; p < passes; p++) {
+                const u32 d = (key[k] >> (8 * p)) & 255u;
+                const u32 d0 = __shfl_sync(0xffffffffu, d, 0);
+                if (full && __all_sync(0xffffffffu, d == d0)) {
+                    if (lane == 0) atomicAdd(&sh[p * 256 + d0], 32u);
+                } else if (ok[k]) {
+                    atomicAdd(&sh[p * 256 + d], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * 256; i += kBlock) {
+        const u32 c = sh[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
 // ---------------- K4: gather into sorted order + chunk table ----------------
 // One thread per sorted slot: sortedPos/W/Phase[i] = pos/W/phase[index[i]] (exact copies, the contract).
 // The reference scatters cellStart/cellEnd from this kernel after a memset of the whole table
@@ -156,6 +203,14 @@ static inline u32 cdiv(u32 a, u32 b) { return (a + b - 1) / b; }
 void ps_launch_calc_hash(u32 *hash, u32 *index, const float4 *pos, u32 n, GridDesc g, cudaStream_t s) {
     if (!n) return;
     k_calc_hash<<<cdiv(n, kBlock), kBlock, 0, s>>>(hash, index, pos, n, g);
+}
+
+// K2 + the sort's histograms in one launch; hist = SortScratch::hist, zeroed by ps_launch_sort_prepare on the same stream before
+void ps_launch_calc_hash_hist(u32 *hash, const float4 *pos, u32 n, GridDesc g, int passes, u32 *hist, cudaStream_t s) {
+    if (!n) return;
+    u32 blocks = cdiv(n, kBlock * kHashItems);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_calc_hash_hist<<<blocks, kBlock, 0, s>>>(hash, pos, n, g, passes, hist);
 }
 
 size_t ps_chunk_table_elems(u32 num_cells) { return (size_t)cdiv(num_cells, kCellsPerBlock) + 1; }

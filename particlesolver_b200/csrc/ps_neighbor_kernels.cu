@@ -567,8 +567,8 @@ struct DeltaP {
     const float *__restrict__ lambda;
     // explicit roundings (no compiler-chosen contraction): the list reader and the grid walk instantiate this in different kernels
     // and must produce the same bits (tests/test_gpu_parity.py::test_neighbour_list_paths_agree_bit_for_bit)
-    __device__ __forceinline__ void operator()(float rx, float ry, float rz, u32 j) {
-        const float lj = __ldg(lambda + j);
+    __device__ __forceinline__ void operator()(float rx, float ry, float rz, u32 j) { apply(rx, ry, rz, __ldg(lambda + j)); }
+    __device__ __forceinline__ void apply(float rx, float ry, float rz, float lj) {
         const float r2 = __fmaf_rn(rz, rz, __fmaf_rn(rx, rx, __fmul_rn(ry, ry)));
         const float inv_r = rsqrtf(r2);
         const float rlen = __fmul_rn(r2, inv_r);
@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(kListBlock) k_solve_fluids_list(float4 *__rest
     const float4 pi = spos[i];
     const u32 nn = num_neighbors[i];
     DeltaP f{lambda[i], delta_p_inv_den(), 0.f, 0.f, 0.f, lambda};
-    ps_for_each_listed(ps_list_column(nbr_list, warp, list_rows, threadIdx.x & 31), nn, i, pi, spos, f);
+    ps_for_each_listed_lambda(ps_list_column(nbr_list, warp, list_rows, threadIdx.x & 31), nn, i, pi, spos, lambda, f);
     const float inv_div = __fdividef(omega, __fadd_rn(ros[orig], (float)nn));
     float4 P = pos[orig];
     P.x = __fmaf_rn(f.dx, inv_div, P.x); P.y = __fmaf_rn(f.dy, inv_div, P.y); P.z = __fmaf_rn(f.dz, inv_div, P.z);

@@ -15,6 +15,9 @@
 // HBM traffic: 4 B (histogram) + 16 B per pass per pair — the model in SURVEY §8(d).
 #include "ps_common.cuh"
 
+#ifndef PS_SORT_LOOK
+#define PS_SORT_LOOK 8
+#endif
 namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -139,10 +142,11 @@ __global__ void __launch_bounds__(kThreads) k_radix_pass(const u32 *__restrict__
         atomicExch(my_status, kFlagPrefix | cnt);
     } else {
         atomicExch(my_status, kFlagAgg | cnt);
-        // decoupled look-back: walk predecessors until one has published an inclusive prefix.  All tiles of a small array
-        // are resident at once and publish their aggregates at about the same time, so the walk is a chain of dependent L2
-        // round trips (one per predecessor, ~245 at 1M pairs): kLook status words are requested per round trip instead.
-        constexpr int kLook = 8;
+        // decoupled look-back: walk predecessors until one has published an inclusive prefix.  The tiles in flight publish their
+        // aggregates at about the same time, so the front of inclusive prefixes advances by at most kLook tiles per L2 round trip:
+        // a pass over 245 tiles (1M pairs) is that chain, not bandwidth.  kLook status words are requested per round trip
+        // (8; 16 and 32 measured slower — 66 / 71 / 76 us per 1M-pair sort, 0.35 / 0.39 / 0.44 ms at 8M: the registers they cost take a resident CTA away, profiles/r2k).
+        constexpr int kLook = PS_SORT_LOOK;
         int p = (int)tile - 1;
         bool done = false;
         while (!done) {
@@ -232,14 +236,23 @@ SortScratch ps_sort_scratch_layout(u32 *base) {
     return sc;
 }
 
-void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool identity_vals, SortScratch sc, cudaStream_t s) {
+// zeroes the histograms, the tickets and the look-back status words of one sort (one allocation, ps_sort_scratch_layout: one memset node)
+void ps_launch_sort_prepare(u32 n, int passes, SortScratch sc, cudaStream_t s) {
     if (!n) return;
     const u32 tiles = (n + kTile - 1) / kTile;
-    // hist | tickets | status words are one allocation (ps_sort_scratch_layout): one memset node per sort
     cudaMemsetAsync(sc.hist, 0, (kSortHeaderElems + (size_t)tiles * 256 * passes) * sizeof(u32), s);
-    u32 hist_blocks = (n + kThreads * 4 * 4 - 1) / (kThreads * 4 * 4);
-    if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-    k_radix_hist<<<hist_blocks, kThreads, 0, s>>>(kA, n, passes, sc.hist);
+}
+
+// hist_ready: ps_launch_sort_prepare has run and the digit histograms of kA are already in sc.hist (ps_launch_calc_hash_hist)
+void ps_launch_sort(u32 *kA, u32 *vA, u32 *kB, u32 *vB, u32 n, int passes, bool identity_vals, SortScratch sc, cudaStream_t s, bool hist_ready) {
+    if (!n) return;
+    const u32 tiles = (n + kTile - 1) / kTile;
+    if (!hist_ready) {
+        ps_launch_sort_prepare(n, passes, sc, s);
+        u32 hist_blocks = (n + kThreads * 4 * 4 - 1) / (kThreads * 4 * 4);
+        if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
+        k_radix_hist<<<hist_blocks, kThreads, 0, s>>>(kA, n, passes, sc.hist);
+    }
     u32 *kin = kA, *vin = vA, *kout = kB, *vout = vB;
     for (int p = 0; p < passes; p++) {
         u32 *st = sc.status + (size_t)p * tiles * 256;

@@ -69,11 +69,15 @@ void ps_io_free(PsCtx *c) {
     io = PsStreamIo{};
 }
 
-extern "C" int ps_step_streamed(PsCtx *c, float dt, const float *pos_in, const float *vel_in, float *pos_out, float *vel_out) {
+// The two halves of a streamed step, for callers that issue the step themselves (the slab-decomposed step is a sequence of stage
+// calls and exchanges, particlesolver_b200/slab.py): ps_io_begin stages this step's inputs (H2D on the copy stream, then D2D into
+// pos / vel on the solver stream), ps_io_end delivers the result (D2D to the staging frame on the solver stream, D2H on the copy
+// stream).  Both cover the OWNED particles (ghost copies of a slab context are rebuilt by the halo exchange).  One begin and one
+// end per step, in that order; either may be skipped by passing NULL pointers.
+extern "C" int ps_io_begin(PsCtx *c, const float *pos_in, const float *vel_in) {
     if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
-    if (c->n_ghost) { ps_set_error("ps_step_streamed: not on a slab context that holds ghosts"); return PS_ERR_STATE; }
-    const uint64_t n = c->n;
-    if (!n) return ps_step(c, dt);
+    const uint64_t n = c->n - c->n_ghost;
+    if (!n || (!pos_in && !vel_in)) return PS_OK;
     DevGuard dg(c->device);
     int r = io_ensure(c, c->capacity ? c->capacity : n);
     if (r != PS_OK) return r;
@@ -81,25 +85,33 @@ extern "C" int ps_step_streamed(PsCtx *c, float dt, const float *pos_in, const f
     const int k = (int)(io.calls & 1);
     const size_t bytes = n * sizeof(float4);
     const float *src[2] = {pos_in, vel_in};
+    float4 *state[2] = {c->pos, c->vel};
+    // host -> staging frame k on the h2d stream, once the frame's previous contents have been consumed
+    if (io.calls >= 2) IO_CU(cudaStreamWaitEvent(io.h2d, io.in_free[k], 0));
+    for (int a = 0; a < 2; a++)
+        if (src[a]) IO_CU(cudaMemcpyAsync(io.in[k][a], src[a], bytes, cudaMemcpyHostToDevice, io.h2d));
+    IO_CU(cudaEventRecord(io.in_ready[k], io.h2d));
+    IO_CU(cudaStreamWaitEvent(c->stream, io.in_ready[k], 0));
+    for (int a = 0; a < 2; a++)
+        if (src[a]) IO_CU(cudaMemcpyAsync(state[a], io.in[k][a], bytes, cudaMemcpyDeviceToDevice, c->stream));
+    IO_CU(cudaEventRecord(io.in_free[k], c->stream));
+    if (pos_in) c->grid_valid = false;
+    return PS_OK;
+}
+
+extern "C" int ps_io_end(PsCtx *c, float *pos_out, float *vel_out) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    const uint64_t n = c->n - c->n_ghost;
+    DevGuard dg(c->device);
+    int r = io_ensure(c, c->capacity ? c->capacity : (n ? n : 1));
+    if (r != PS_OK) return r;
+    PsStreamIo &io = c->io;
+    const int k = (int)(io.calls & 1);
+    const size_t bytes = n * sizeof(float4);
     float *dst[2] = {pos_out, vel_out};
     float4 *state[2] = {c->pos, c->vel};
-    // inputs: host -> staging frame k on the h2d stream, once the frame's previous contents have been consumed
-    const bool any_in = pos_in || vel_in;
-    if (any_in) {
-        if (io.calls >= 2) IO_CU(cudaStreamWaitEvent(io.h2d, io.in_free[k], 0));
-        for (int a = 0; a < 2; a++)
-            if (src[a]) IO_CU(cudaMemcpyAsync(io.in[k][a], src[a], bytes, cudaMemcpyHostToDevice, io.h2d));
-        IO_CU(cudaEventRecord(io.in_ready[k], io.h2d));
-        IO_CU(cudaStreamWaitEvent(c->stream, io.in_ready[k], 0));
-        for (int a = 0; a < 2; a++)
-            if (src[a]) IO_CU(cudaMemcpyAsync(state[a], io.in[k][a], bytes, cudaMemcpyDeviceToDevice, c->stream));
-        IO_CU(cudaEventRecord(io.in_free[k], c->stream));
-        if (pos_in) c->grid_valid = false;
-    }
-    r = ps_step(c, dt);
-    if (r != PS_OK) return r;
-    // outputs: state -> staging frame k on the solver stream (after the frame's previous download), then to the host on the d2h stream
-    if (pos_out || vel_out) {
+    // state -> staging frame k on the solver stream (after the frame's previous download), then to the host on the d2h stream
+    if (n && (pos_out || vel_out)) {
         if (io.calls >= 2) IO_CU(cudaStreamWaitEvent(c->stream, io.out_done[k], 0));
         for (int a = 0; a < 2; a++)
             if (dst[a]) IO_CU(cudaMemcpyAsync(io.out[k][a], state[a], bytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -111,6 +123,15 @@ extern "C" int ps_step_streamed(PsCtx *c, float dt, const float *pos_in, const f
     IO_CU(cudaEventRecord(io.out_done[k], io.d2h));
     io.calls++;
     return PS_OK;
+}
+
+extern "C" int ps_step_streamed(PsCtx *c, float dt, const float *pos_in, const float *vel_in, float *pos_out, float *vel_out) {
+    if (!c) { ps_set_error("null context"); return PS_ERR_INVALID; }
+    if (c->n_ghost) { ps_set_error("ps_step_streamed: a slab context steps through its stage calls; use ps_io_begin / ps_io_end around them"); return PS_ERR_STATE; }
+    int r = ps_io_begin(c, pos_in, vel_in);
+    if (r != PS_OK) return r;
+    if ((r = ps_step(c, dt)) != PS_OK) return r;
+    return ps_io_end(c, pos_out, vel_out);
 }
 
 // Blocks until the outputs of the ps_step_streamed call made `calls_back` calls ago (0 = the last one, 1 = the one before) are in
