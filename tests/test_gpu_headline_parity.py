@@ -118,6 +118,39 @@ def test_c3_one_million_particles_vs_the_reference_cuda_binary(tmp_path):
     ps.close()
 
 
+C3_STATS = os.path.join(H.ROOT, "tests", "golden", "ref_gpu_stats_c3.json")
+
+
+@pytest.mark.skipif(not os.path.exists(C3_STATS), reason="tests/golden/ref_gpu_stats_c3.json not generated (tests/golden/make_stats_golden.py c3 on a GPU box)")
+def test_c3_one_million_particles_100_steps_statistics_vs_the_reference():
+    """The headline workload over 100 steps (expansion, fall, floor contact) against the series of the reference's UNMODIFIED CUDA code on
+    the same scene (fixture from oracle/_ref/ref_gpu, generator tests/golden/make_stats_golden.py c3): every 20 steps the mean density
+    error |rho / rho0 - 1| within 35 % + 0.005 and the kinetic energy within [0.6, 1.6] of the reference's — the bands of
+    tests/test_long_run_stats.py; per-particle comparison is meaningless after ~10 steps."""
+    import json
+    ref = json.load(open(C3_STATS))
+    ps = psb.ParticleSystem.scene("c3", grid=ref["grid"], max_particles=ref["side"] ** 3 + 1024, side=ref["side"])
+    sol = ps.solver
+    assert sol.n == ref["n"]
+    o = H.oracle_from_solver(sol)   # statistics only: the same estimator the fixture was made with
+    got = []
+    for s in range(1, ref["steps"] + 1):
+        ps.update(DT)
+        if s % ref["every"] == 0:
+            o.pos[:] = sol.download(psb.ARR_POS)
+            o.vel[:] = sol.download(psb.ARR_VEL)
+            got.append(o.fluid_stats())
+    assert np.isfinite(sol.download(psb.ARR_POS)).all()
+    for k, ((err, mx, ke), (rerr, rmx, rke)) in enumerate(zip(got, ref["series"])):
+        step = (k + 1) * ref["every"]
+        assert abs(err - rerr) <= 0.35 * rerr + 0.005, f"step {step}: mean density error {err:.4f} vs the reference's {rerr:.4f}"
+        assert 0.6 * rke <= ke <= 1.6 * rke, f"step {step}: kinetic energy {ke:.4g} vs the reference's {rke:.4g}"
+    # the library's own estimator (ps_fluid_stats, K6 on a fresh grid) agrees with the oracle's on the final state
+    mde, xde, ke = sol.fluid_stats()
+    assert abs(mde - got[-1][0]) <= 0.02 * got[-1][0] + 1e-4 and abs(ke - got[-1][2]) <= 1e-3 * got[-1][2]
+    ps.close()
+
+
 # ---------------------------------------------------------------- C5 geometry ----------------------------------------------------------------
 C5_NX, C5_NY, C5_NZ = 16, 250, 400      # 1.6M particles: 16 of the scene's 640 x-planes at the full y/z extent
 C5_GRID = (128, 512, 512)               # a per-rank grid of bench.py's slab runs: 2^25 cells, four 8-bit radix passes
