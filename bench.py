@@ -614,8 +614,20 @@ def run_slabs(args, rank, world, local_rank):
     dom = slab.SlabDomain(eng, rank, world, cuts, drift=drift, comm=comm, exchange_lambda=exchange_lambda)
     assert dom.halo == halo_width
 
+    use_c = world > 1 and args.slab_host == "c"
+    if use_c:
+        # the whole slab step behind the C ABI (ps_comm_*: NCCL send / recv issued from C++ on the context's stream); rank 0's
+        # ncclGetUniqueId reaches the other ranks over the process group torchrun set up
+        ident = [psb.Solver.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        sol.comm_init(ident[0], rank, world)
+        sol.comm_set_slab(cuts[rank], cuts[rank + 1], drift=drift, exchange_lambda=exchange_lambda, halo_capacity=halo_cap,
+                          migrant_capacity=max(plane * 2, 1 << 16))
+
     def step():
-        if world > 1:
+        if use_c:
+            sol.comm_step(DT)
+        elif world > 1:
             dom.step(DT)
         else:  # one slab: no neighbours, no ghosts
             dom.begin(DT)
@@ -632,7 +644,8 @@ def run_slabs(args, rank, world, local_rank):
     sol.sync()
     barrier()
     sampler.mark_begin()
-    sent0 = comm.bytes_sent if comm else 0
+    bytes_now = (lambda: sol.comm_stats()["bytes_sent"]) if use_c else (lambda: comm.bytes_sent if comm else 0)
+    sent0 = bytes_now()
     sol.timer_start()
     for _ in range(args.steps):
         step()
@@ -642,8 +655,8 @@ def run_slabs(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     ms = reduce(ms, dist.ReduceOp.MAX)
     value = total * args.steps / (ms * 1e-3)
-    sent = reduce((comm.bytes_sent - sent0) if comm else 0, dist.ReduceOp.SUM) / max(args.steps, 1)
-    ghosts = reduce(dom.stats["ghosts"], dist.ReduceOp.SUM)
+    sent = reduce(bytes_now() - sent0, dist.ReduceOp.SUM) / max(args.steps, 1)
+    ghosts = reduce(sol.comm_stats()["ghosts"] if use_c else dom.stats["ghosts"], dist.ReduceOp.SUM)
     owned_min, owned_max = reduce(sol.n_owned, dist.ReduceOp.MIN), reduce(sol.n_owned, dist.ReduceOp.MAX)
     # kernels launched per step and rank: predict 1 + iterations x (grid build 4 + passes, lambda, delta_p, world, halo select/pack/unpack 4)
     # + migration (select 2 [+ pack 1 + compaction 6 + append 1 when particles leave / arrive]) + velocity 1
@@ -736,7 +749,8 @@ def run_slabs(args, rank, world, local_rank):
                                        f"ghost lambdas {'received from their owners between K6 and K7' if exchange_lambda else 'computed locally'}, migration every step, "
                                        f"per-rank grid {gx} x 512 x 512, 5 solver iterations, dt=1/60",
                            "particles_total": total, "particles_per_gpu": [int(owned_min), int(owned_max)], "ghosts_total": int(ghosts),
-                           "exchange": "torch.distributed send/recv over NCCL between neighbouring ranks" if world > 1 else "none",
+                           "exchange": ("ncclSend / ncclRecv between neighbouring ranks, issued by ps_comm_step (C ABI, csrc/ps_comm.cu) on the solver's stream" if use_c else
+                                        "torch.distributed send/recv over NCCL between neighbouring ranks (particlesolver_b200/slab.py)") if world > 1 else "none",
                            "exchange_bytes_per_step": int(sent), "l2": "per-rank working set >> 126 MB L2; no flush"},
                 "particle_iterations_per_s": value * ITERS,
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 32 * total, "d2h_bytes_per_step": 32 * total,
@@ -778,6 +792,8 @@ def main():
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c5"], help="auto: c3 on one GPU, c5 (slabs) on several")
     ap.add_argument("--particles", type=int, default=0, help="c5: total particle count over all ranks (rounded to whole lattice planes); "
                     "default 8,000,000 per GPU, i.e. weak scaling up to the 64M-particle scene on 8 GPUs")
+    ap.add_argument("--slab-host", default="c", choices=["c", "python"],
+                    help="N > 1: who drives the slab step — ps_comm_step behind the C ABI (default) or particlesolver_b200/slab.py over torch.distributed")
     ap.add_argument("--no-long-run", action="store_true", help="c3: skip the 200 further steps of the long_run field")
     ap.add_argument("--no-c5", action="store_true", help="c3: skip the c5_8M_1gpu field (the 8M-particle dam break on this GPU)")
     ap.add_argument("--quick", action="store_true", help="resident timing only (for runs under ncu): no e2e, no per-stage pass, no CPU baseline")

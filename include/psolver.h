@@ -262,6 +262,26 @@ int ps_set_viscosity(PsCtx *ctx, float xsph_c, float vorticity_eps);
 int ps_find_neighbors(PsCtx *ctx);            /* K6 alone on the current grid: lambda, neighbour counts, neighbour lists */
 int ps_apply_viscosity(PsCtx *ctx, float dt); /* the post-pass alone (after ps_build_grid + ps_find_neighbors) */
 int ps_set_ghost_count(PsCtx *ctx, uint64_t ghosts);
+
+/* ---- the slab-decomposed step over NCCL, behind the C ABI (csrc/ps_comm.cu) ----
+ * One context per GPU, one process per context.  Rank 0 obtains a 128-byte id (ncclGetUniqueId) and hands it to the other ranks
+ * by whatever channel the host has (a file, MPI, torch.distributed ...); every rank calls ps_comm_init, describes its slab and
+ * then steps with ps_comm_step instead of ps_step: predict, migration, and per solver iteration the halo refresh, the solver
+ * stages and the ghost-lambda exchange, with the neighbour exchange as NCCL send / recv on the context's stream.  NCCL is loaded
+ * at run time (dlopen of libnccl.so.2): a single-GPU host never needs it. */
+#define PS_COMM_ID_BYTES 128
+int ps_comm_get_unique_id(void *id128);
+int ps_comm_init(PsCtx *ctx, const void *id128, int rank, int nranks);
+int ps_comm_destroy(PsCtx *ctx);
+/* this rank owns x in [x_lo, x_hi) (first / last rank: -INFINITY / INFINITY); drift bounds the motion inside one step's solver
+ * iterations (0.25 for the reference's constants); exchange_lambda != 0: ghost lambdas come from their owners (halo H + drift),
+ * else they are computed locally (halo 2H + 2 drift); capacities in records of the halo / migrant buffers */
+int ps_comm_set_slab(PsCtx *ctx, float x_lo, float x_hi, float drift, int exchange_lambda, uint64_t halo_capacity, uint64_t migrant_capacity);
+int ps_comm_step(PsCtx *ctx, float dt);
+/* out[4]: particles handed to neighbours so far, ghosts held in the last iteration, payload bytes sent, steps */
+int ps_comm_stats(PsCtx *ctx, uint64_t out[4]);
+/* element-wise sum of up to 8 doubles over the ranks (global counts / energies of a decomposed run); blocking */
+int ps_comm_allreduce_sum(PsCtx *ctx, double *values, uint32_t count);
 uint64_t ps_num_owned(PsCtx *ctx);
 #ifdef __cplusplus
 }

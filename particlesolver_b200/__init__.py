@@ -126,6 +126,13 @@ def lib():
         L.ps_slab_pack_lambda.argtypes = [vp, vp, vp, u64, C.POINTER(u32 * 2)]
         L.ps_slab_set_ghost_lambda.argtypes = [vp, vp, u64, vp, u64]
         L.ps_slab_x_histogram.argtypes = [vp, f32, f32, u32, vp]
+        L.ps_comm_get_unique_id.argtypes = [vp]
+        L.ps_comm_init.argtypes = [vp, vp, i32, i32]
+        L.ps_comm_destroy.argtypes = [vp]
+        L.ps_comm_set_slab.argtypes = [vp, f32, f32, f32, i32, u64, u64]
+        L.ps_comm_step.argtypes = [vp, f32]
+        L.ps_comm_stats.argtypes = [vp, vp]
+        L.ps_comm_allreduce_sum.argtypes = [vp, vp, u32]
         # C++ host class (csrc/particle_system.cpp)
         L.pshost_create.argtypes = [f32, u32, u32, u32, u32, vp, vp, i32]
         L.pshost_create.restype = vp
@@ -335,6 +342,37 @@ class Solver:
         """ps_step_streamed: one step whose inputs / outputs are (pinned) host buffers given as raw addresses (or None); the transfers
         overlap the neighbouring calls' solver work.  io_wait(k) blocks until the outputs of the call made k calls ago have landed."""
         _check(lib().ps_step_streamed(self._h, dt, pos_in, vel_in, pos_out, vel_out))
+
+    # --- the slab-decomposed step over NCCL behind the C ABI (csrc/ps_comm.cu) ---
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes from ncclGetUniqueId: rank 0 calls this and hands the bytes to the other ranks"""
+        buf = C.create_string_buffer(128)
+        _check(lib().ps_comm_get_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, id_bytes, rank, nranks):
+        assert len(id_bytes) == 128
+        _check(lib().ps_comm_init(self._h, C.c_char_p(bytes(id_bytes)), rank, nranks))
+
+    def comm_set_slab(self, x_lo, x_hi, drift=0.25, exchange_lambda=True, halo_capacity=1 << 16, migrant_capacity=1 << 16):
+        _check(lib().ps_comm_set_slab(self._h, x_lo, x_hi, drift, int(bool(exchange_lambda)), int(halo_capacity), int(migrant_capacity)))
+
+    def comm_step(self, dt):
+        _check(lib().ps_comm_step(self._h, dt))
+
+    def comm_stats(self):
+        out = (C.c_uint64 * 4)()
+        _check(lib().ps_comm_stats(self._h, out))
+        return {"migrated_out": int(out[0]), "ghosts": int(out[1]), "bytes_sent": int(out[2]), "steps": int(out[3])}
+
+    def comm_allreduce_sum(self, values):
+        a = np.ascontiguousarray(values, np.float64).copy()
+        _check(lib().ps_comm_allreduce_sum(self._h, _ptr(a), a.size))
+        return a
+
+    def comm_destroy(self):
+        _check(lib().ps_comm_destroy(self._h))
 
     def io_begin(self, pos_in=None, vel_in=None):
         _check(lib().ps_io_begin(self._h, pos_in, vel_in))

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpsolver.so")
 OBJ = os.path.join(HERE, "build")
-CU_SOURCES = ["ps_stream_kernels.cu", "ps_grid_kernels.cu", "ps_sort_kernels.cu", "ps_neighbor_kernels.cu", "ps_fluid_staged.cu", "ps_slab_kernels.cu", "ps_shape_kernels.cu", "ps_context.cu", "ps_extensions.cu", "ps_checkpoint.cu", "ps_stream_io.cu",
+CU_SOURCES = ["ps_stream_kernels.cu", "ps_grid_kernels.cu", "ps_sort_kernels.cu", "ps_neighbor_kernels.cu", "ps_fluid_staged.cu", "ps_slab_kernels.cu", "ps_shape_kernels.cu", "ps_context.cu", "ps_extensions.cu", "ps_checkpoint.cu", "ps_stream_io.cu", "ps_comm.cu",
               "ps_reference_abi.cu", "ps2d.cu"]
 CPP_SOURCES = ["particle_system.cpp", "scenes2d.cpp"]
 # -use_fast_math mirrors the reference's own build flags (gpu/particles_cuda.pro:153-158): div.approx / sqrt.approx /
@@ -73,7 +73,7 @@ def build_all(force=False, verbose=False):
                 raise RuntimeError("nvcc failed on " + src)
             rebuilt = True
     if rebuilt or force or not os.path.exists(OUT):
-        cmd = [nvcc, "-shared", "-o", OUT, *objs, "-lcurand", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+        cmd = [nvcc, "-shared", "-o", OUT, *objs, "-lcurand", "-ldl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

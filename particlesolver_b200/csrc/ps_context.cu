@@ -270,6 +270,7 @@ extern "C" int ps_destroy(PsCtx *c) {
                     c->sort_status, c->rands, c->slab_scratch, c->slab_ranks, c->nbr_list, c->nbr_rows ? c->nbr_rows - 4 : nullptr, c->csr_particle, c->csr_off, c->csr_other, c->d_point_idx, c->csr_rest,
                     c->d_point_xyz, c->dist_scratch, c->adj_off, c->adj};
     for (void *p : ptrs) if (p) cudaFree(p);
+    ps_comm_free(c);
     ps_ext_free(c);
     ps_io_free(c);
     if (c->slab_counts_host) cudaFreeHost(c->slab_counts_host);

@@ -22,6 +22,8 @@ struct PsStreamIo {
     uint64_t cap = 0, calls = 0;
 };
 
+struct PsComm;  // ps_comm.cu: NCCL communicator, slab geometry and record buffers of a multi-GPU context
+
 struct PsCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -124,6 +126,7 @@ struct PsCtx {
     bool slab_used = false;           // a slab call has compacted / appended particles: index-based constraints and bodies are refused from then on
     float lambda_xmin = -3.0e38f, lambda_xmax = 3.0e38f;
     PsStreamIo io;
+    PsComm *comm = nullptr;
 };
 
 // internal helpers shared with the reference-ABI shim
@@ -146,6 +149,7 @@ u32 ps_ext_issue_sdf(PsCtx *c);  // world-frame SDF for the next contact pass (0
 u32 ps_ext_issue_viscosity(PsCtx *c, float dt);
 void ps_ext_free(PsCtx *c);
 void ps_io_free(PsCtx *c);  // ps_stream_io.cu
+void ps_comm_free(PsCtx *c);  // ps_comm.cu
 
 // stage issue functions on explicit arrays (used by both ABIs); each returns the number of launches issued
 u32 ps_issue_build_grid(PsCtx *c, const float4 *pos);

@@ -24,6 +24,7 @@ def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
     recut = int(sys.argv[2]) if len(sys.argv) > 2 else 0   # re-cut the slabs every that many steps (0: fixed planes)
     exchange = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True   # ghost lambdas from their owners (1) or computed locally (0)
+    c_abi = bool(int(sys.argv[4])) if len(sys.argv) > 4 else False      # the exchange behind the C ABI (ps_comm_*, NCCL C API) instead of slab.py
     p_or, pos, vel, w, phase, ros = _scene(nx=40)
     p = psb.default_params()
     p.grid_size[:] = tuple(p_or.grid); p.min_bounds[:] = tuple(p_or.min_b); p.max_bounds[:] = tuple(p_or.max_b)
@@ -38,8 +39,22 @@ def main():
     dom = slab.SlabDomain(eng, rank, world, cuts, comm=slab.DistComm(eng), recut_every=recut, recut_range=(0.0, 40.0), recut_bins=1024,
                           exchange_lambda=exchange)
     n_start = sol.n_owned
-    for _ in range(steps):
-        dom.step(DT)
+    if c_abi:
+        # rank 0's ncclGetUniqueId travels over the process group that launched us; from here on the step is ps_comm_step alone
+        ident = [psb.Solver.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        sol.comm_init(ident[0], rank, world)
+        sol.comm_set_slab(cuts[rank], cuts[rank + 1], drift=0.25, exchange_lambda=exchange, halo_capacity=pos.shape[0], migrant_capacity=pos.shape[0])
+        for _ in range(steps):
+            sol.comm_step(DT)
+        st = sol.comm_stats()
+        dom.stats["migrated_out"], dom.stats["ghosts"] = st["migrated_out"], st["ghosts"]
+        dom.comm.bytes_sent = st["bytes_sent"]
+        total = sol.comm_allreduce_sum([sol.n_owned])
+        assert int(total[0]) == pos.shape[0], (total, pos.shape)
+    else:
+        for _ in range(steps):
+            dom.step(DT)
     sol.sync()
     # gather the owned particles on rank 0
     n = torch.tensor([sol.n_owned], dtype=torch.int64, device="cuda")
@@ -65,7 +80,7 @@ def main():
         if recut:
             assert dom.stats["recuts"] == (steps - 1) // recut and max(ns) / (sum(ns) / world) < 1.3, (ns, dom.cuts)
         assert int(stats[0]) > 0 and int(stats[1]) > 0 and int(stats[2]) > 0
-        print(f"SLAB_NCCL_OK recut={recut} exchange_lambda={exchange} ghosts={int(stats[1])} cuts={[round(c, 3) for c in dom.cuts[1:-1]]} world={world} particles={pos.shape[0]} owned={ns} migrated={int(stats[0])} bytes_sent={int(stats[2])}", flush=True)
+        print(f"SLAB_NCCL_OK c_abi={int(c_abi)} recut={recut} exchange_lambda={exchange} ghosts={int(stats[1])} cuts={[round(c, 3) for c in dom.cuts[1:-1]]} world={world} particles={pos.shape[0]} owned={ns} migrated={int(stats[0])} bytes_sent={int(stats[2])}", flush=True)
     dist.barrier()
     sol.close()
     dist.destroy_process_group()
