@@ -689,6 +689,9 @@ def run_slabs(args, rank, world, local_rank):
             if sol.n_owned == k0:
                 sol.io_begin(ip.data_ptr(), iv.data_ptr())
                 staged[0] += 1
+            if k + 1 < steps and sol.n_owned == k0:   # the next step's upload starts now: issuing a slab step blocks the host
+                nip, niv = hin[(k + 1) & 1]
+                sol.io_prefetch(nip.data_ptr(), niv.data_ptr())
             step()
             sol.io_end(op.data_ptr(), ov.data_ptr())
             sol.io_wait(1)

@@ -148,6 +148,10 @@ int ps_io_wait(PsCtx *ctx, uint32_t calls_back);
 /* the two halves of ps_step_streamed for callers that issue the step themselves (a slab context's step is a sequence of stage calls
  * and exchanges): inputs before the step, outputs after it, over the OWNED particles; one begin and one end per step */
 int ps_io_begin(PsCtx *ctx, const float *pos_in, const float *vel_in);
+/* starts the transfer of the NEXT step's inputs now (call it before issuing the current step): needed where issuing a step blocks
+ * the host (ps_comm_step waits for its neighbours' counts), so that the upload still overlaps the step; the next ps_io_begin
+ * must name the same buffers */
+int ps_io_prefetch(PsCtx *ctx, const float *pos_in, const float *vel_in);
 int ps_io_end(PsCtx *ctx, float *pos_out, float *vel_out);
 
 /* Device-time a region of work on the context's stream with CUDA events (stop synchronises). */

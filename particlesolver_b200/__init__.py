@@ -102,6 +102,7 @@ def lib():
         L.ps_step_streamed.argtypes = [vp, f32, vp, vp, vp, vp]
         L.ps_io_wait.argtypes = [vp, u32]
         L.ps_io_begin.argtypes = [vp, vp, vp]
+        L.ps_io_prefetch.argtypes = [vp, vp, vp]
         L.ps_io_end.argtypes = [vp, vp, vp]
         L.ps_sync.argtypes = [vp]
         L.ps_last_step_ms.argtypes = [vp, C.POINTER(f32)]
@@ -376,6 +377,9 @@ class Solver:
 
     def io_begin(self, pos_in=None, vel_in=None):
         _check(lib().ps_io_begin(self._h, pos_in, vel_in))
+
+    def io_prefetch(self, pos_in=None, vel_in=None):
+        _check(lib().ps_io_prefetch(self._h, pos_in, vel_in))
 
     def io_end(self, pos_out=None, vel_out=None):
         _check(lib().ps_io_end(self._h, pos_out, vel_out))

@@ -20,6 +20,10 @@ struct PsStreamIo {
     float4 *in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [frame][pos | vel]
     cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr}, out_ready[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
     uint64_t cap = 0, calls = 0;
+    bool begun = false;  // between ps_io_begin and ps_io_end
+    bool prefetched[2] = {false, false}, frames_used[2] = {false, false};
+    uint64_t prefetch_n[2] = {0, 0};
+    const float *prefetch_src[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
 };
 
 struct PsComm;  // ps_comm.cu: NCCL communicator, slab geometry and record buffers of a multi-GPU context

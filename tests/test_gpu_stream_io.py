@@ -67,3 +67,36 @@ def test_streamed_pipeline_delivers_every_frame_in_order():
     for k in range(5):
         assert np.array_equal(got[k], frames[k]), f"frame {k}"
     ps.close()
+
+
+def test_begin_prefetch_end_around_explicit_steps():
+    """ps_io_begin / ps_io_prefetch / ps_io_end around a step the caller issues itself (what a slab-decomposed run does): step k's inputs
+    are the recorded state k of a resident run, the upload of step k+1's inputs is started before step k is issued, and every delivered
+    frame equals the resident run's next state"""
+    steps = 5
+    ref = psb.ParticleSystem.scene("7")
+    n = ref.solver.n
+    states = [(ref.solver.download(psb.ARR_POS).copy(), ref.solver.download(psb.ARR_VEL).copy())]
+    for _ in range(steps):
+        ref.update(DT)
+        states.append((ref.solver.download(psb.ARR_POS).copy(), ref.solver.download(psb.ARR_VEL).copy()))
+    ref.close()
+    ps = psb.ParticleSystem.scene("7")
+    sol = ps.solver
+    hin = [(_pinned(n), _pinned(n)) for _ in range(steps)]
+    for k in range(steps):
+        hin[k][0].numpy()[:] = states[k][0]
+        hin[k][1].numpy()[:] = states[k][1]
+    hout = [(_pinned(n), _pinned(n)) for _ in range(2)]
+    # perturb the resident state: every step must really start from the host's frame
+    sol.upload(psb.ARR_POS, states[0][0] + np.float32(0.01))
+    for k in range(steps):
+        sol.io_begin(hin[k][0].data_ptr(), hin[k][1].data_ptr())
+        if k + 1 < steps:
+            sol.io_prefetch(hin[k + 1][0].data_ptr(), hin[k + 1][1].data_ptr())
+        sol.step(DT)
+        op, ov = hout[k & 1]
+        sol.io_end(op.data_ptr(), ov.data_ptr())
+        sol.io_wait(0)
+        assert np.array_equal(op.numpy(), states[k + 1][0]) and np.array_equal(ov.numpy(), states[k + 1][1]), f"step {k}"
+    ps.close()
