@@ -166,6 +166,7 @@ static void dump_state(Simulation &sim, const std::string &dir, int tick) {
 int main(int argc, char **argv) {
     std::string scene = "6", dump, script;
     int ticks = 100, dump_every = 0, scene_at = -1;
+    double fluid_scale = 0;  // --fluid-scale S: scene 6 rebuilt at that scale (initFluid hard-codes 4) through the reference's own createFluid
     bool json = false;
     for (int i = 1; i < argc; i++) {
         std::string k = argv[i];
@@ -174,6 +175,7 @@ int main(int argc, char **argv) {
         else if (k == "--dump" && i + 1 < argc) dump = argv[++i];
         else if (k == "--dump-every" && i + 1 < argc) dump_every = atoi(argv[++i]);
         else if (k == "--scene-at" && i + 1 < argc) scene_at = atoi(argv[++i]);  // full restart state after that tick
+        else if (k == "--fluid-scale" && i + 1 < argc) fluid_scale = atof(argv[++i]);
         else if (k == "--script" && i + 1 < argc) script = argv[++i];  // a session: "KEY:TICKS,KEY:TICKS,..." on ONE Simulation object
         else if (k == "--json") json = true;
     }
@@ -199,6 +201,27 @@ int main(int argc, char **argv) {
         return 0;
     }
     sim.init(scene_of(scene));
+    if (fluid_scale > 0 && scene == "6") {
+        // BASELINE.md section 4's scaled replicas: initFluid's recipe (simulation.cpp:894-913: spacing 0.7, jitter +-0.1, two fluids of
+        // density 1 and 1.75) at another scale, built through the reference's own createFluid; init()'s epilogue repeated
+        sim.clear();
+        sim.m_counts = nullptr;
+        const double scale = fluid_scale, delta = .7, num = 2.;
+        sim.m_gravity = glm::dvec2(0, -9.8);
+        sim.m_xBoundaries = glm::dvec2(-2 * scale, 2 * scale);
+        sim.m_yBoundaries = glm::dvec2(-2 * scale, 10 * scale);
+        QList<Particle *> particles;
+        for (int d = 0; d < num; d++) {
+            double start = -2 * scale + 4 * scale * (d / num);
+            for (double x = start; x < start + (4 * scale / num); x += delta)
+                for (double y = -2 * scale; y < scale; y += delta)
+                    particles.append(new Particle(glm::dvec2(x, y) + .2 * glm::dvec2(frand() - .5, frand() - .5), 1));
+            sim.createFluid(&particles, 1 + .75 * d);
+            particles.clear();
+        }
+        sim.m_standardSolver.setupM(&sim.m_particles);
+        sim.m_counts = new int[sim.m_particles.size()];
+    }
     int n = sim.getNumParticles();
     if (!dump.empty()) { std::string c = "mkdir -p '" + dump + "'"; if (system(c.c_str())) return 1; dump_scene(sim, dump, 0); dump_state(sim, dump, 0); }
     std::vector<double> ke;

@@ -91,6 +91,9 @@ const SceneInfo kScenes[] = {
     {"n", "CRADLE_TEST", {-10, 10}, {-5, 1000000}, 64},        {"s", "SMOKE_OPEN_TEST", {-6, 6}, {-4, 200}, 8192},
     {"d", "SMOKE_CLOSED_TEST", {-4, 4}, {-4, 4}, 1024},        {".", "SDF_TEST", {-20, 20}, {0, 1000000}, 64},
     {"w", "WRECKING_BALL", {-15, 100}, {0, 1000000}, 1024},  {"v", "VOLCANO_TEST", {-20, 20}, {0, 100}, 1024},
+    // scaled replicas of FLUID_TEST (the scene built through createFluid with initFluid's spacing / jitter recipe at
+    // twice and four times the linear size: 1,728 and 6,912 particles); not key-bound in the reference
+    {"6x2", "FLUID_TEST x2", {-16, 16}, {-16, 80}, 4096},      {"6x4", "FLUID_TEST x4", {-32, 32}, {-32, 160}, 16384},
 };
 const SceneInfo *find_scene(const char *key) {
     if (!key) return nullptr;
@@ -236,8 +239,8 @@ void build(Builder &B, const std::string &k, const SceneInfo &S) {
         for (double x = -scale; x < scale; x += delta)
             for (double y = 10; y < 10 + scale; y += delta) f.push_back(B.jittered(x, y, 1, PS2D_PHASE_FLUID));
         B.group(f, 1.75, false, false);
-    } else if (k == "6") {  // initFluid, :923-943
-        const double scale = 4., delta = .7, num = 2.;
+    } else if (k == "6" || k == "6x2" || k == "6x4") {  // initFluid, :923-943 (scale 4; the replicas: 8 and 16)
+        const double scale = k == "6" ? 4. : k == "6x2" ? 8. : 16., delta = .7, num = 2.;
         std::vector<Part> f;
         for (int d = 0; d < num; d++) {
             const double start = -2 * scale + 4 * scale * (d / num);
