@@ -345,8 +345,11 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
 //     (ps_launch_reorder(..., slot_in_w)), so the walk tracks nothing but a slot counter and the end of the current range;
 //   * an accepted neighbour's slot goes straight to the lane's column of the warp's list region (ps_fluid_lists.cuh).
 // Arithmetic: PS_K6_BODY is, association for association, ps_lambda_terms (ps_fluid_lists.cuh) — every K6 variant gives the same bits.
+#ifndef PS_ROW_BATCH
+#define PS_ROW_BATCH 9  // stencil rows whose cell-table loads are issued together (fused K6)
+#endif
 #ifndef PS_FUSED_MINB
-#define PS_FUSED_MINB 7  // resident CTAs the register allocation aims at: 7 (71 registers) measured 0-3 % faster than 8 (64 registers), profiles/r2i
+#define PS_FUSED_MINB 6  // resident CTAs the register allocation aims at: with the batched row set-up 6 (80 registers) measured 0-1.5 % faster than 7 (72), profiles/r2r
 #endif
 static inline size_t fused_smem_bytes(int rad) { return (size_t)(2 * (2 * rad + 1) + 1) * kBlock * sizeof(uint2); }
 
@@ -474,40 +477,70 @@ __global__ void __launch_bounds__(kBlock, PS_FUSED_MINB) k_find_lambdas_fused(fl
                 total += len;
             }
         };
-        auto do_row = [&](int dyi) {
-            if (!((rowmask >> dyi) & 1u)) return;
+        // Row set-up in two stages per batch of rows: first the address arithmetic and BOTH cell-table loads of every row of the batch
+        // (all in flight together), then the list entries.  Done row by row the two dependent loads of a row were 19 % of the
+        // kernel's stall samples (profiles/r2i).  A lane's list is its own, so nothing here needs the warp: a row that wraps
+        // around the power-of-two grid ([lw, gx) then [0, hw]) gets its second range from the (few) lanes concerned.
+        auto row_geometry = [&](int dyi, u32 &row, u32 &lw, u32 &hw) -> bool {
             const int dy = dyi - rad;
             const float rem = remz - dmin2(dy, fy0, fy1, g.cy);
-            u32 b0 = 0, len0 = 0, row = 0, hw = 0;
-            bool wrap = false;
-            if (act && rem >= 0.f) {
-                const float ext = sqrtf(rem) + eps;
-                int lo = (int)floorf((relx - ext) * inv_cx), hi = (int)floorf((relx + ext) * inv_cx);
-                lo = max(min(lo, gp.x), gp.x - rad);
-                hi = min(max(hi, gp.x), gp.x + rad);
-                row = (zrow + ((u32)(gp.y + dy) & g.my)) * g.gx;
-                const u32 lw = (u32)lo & g.mx;
-                hw = (u32)hi & g.mx;
-                wrap = lw > hw;  // the row wraps around the power-of-two grid: [lw, gx) then [0, hw]
-                b0 = __ldg(cell_begin + (row + lw));
-                len0 = __ldg(cell_begin + (row + (wrap ? g.mx : hw) + 1u)) - b0;
-            }
-            push(b0, len0);
-            if (__any_sync(kFull, wrap)) {
-                u32 b1 = 0, len1 = 0;
-                if (wrap) {
-                    b1 = __ldg(cell_begin + row);
-                    len1 = __ldg(cell_begin + (row + hw + 1u)) - b1;
-                }
-                push(b1, len1);
+            if (!(act && rem >= 0.f)) return false;
+            const float ext = sqrtf(rem) + eps;
+            int lo = (int)floorf((relx - ext) * inv_cx), hi = (int)floorf((relx + ext) * inv_cx);
+            lo = max(min(lo, gp.x), gp.x - rad);
+            hi = min(max(hi, gp.x), gp.x + rad);
+            row = (zrow + ((u32)(gp.y + dy) & g.my)) * g.gx;
+            lw = (u32)lo & g.mx;
+            hw = (u32)hi & g.mx;
+            return true;
+        };
+        auto second_range = [&](int dyi) {  // rare: this lane's window of the row crosses the seam
+            u32 row, lw, hw;
+            if (row_geometry(dyi, row, lw, hw)) {
+                const u32 b1 = __ldg(cell_begin + row);
+                push(b1, __ldg(cell_begin + (row + hw + 1u)) - b1);
             }
         };
         if (RAD) {
+            constexpr int kRows = 2 * RAD + 1, kBatch = PS_ROW_BATCH;
 #pragma unroll
-            for (int dyi = 0; dyi < 2 * RAD + 1; dyi++) do_row(dyi);
+            for (int r0 = 0; r0 < kRows; r0 += kBatch) {
+                u32 b0[kBatch], e0[kBatch];
+                u32 wraps = 0;
+#pragma unroll
+                for (int k = 0; k < kBatch; k++) {
+                    const int dyi = r0 + k;
+                    b0[k] = e0[k] = 0;
+                    if (dyi < kRows && ((rowmask >> dyi) & 1u)) {
+                        u32 row, lw, hw;
+                        if (row_geometry(dyi, row, lw, hw)) {
+                            const bool wrap = lw > hw;
+                            wraps |= (wrap ? 1u : 0u) << k;
+                            b0[k] = __ldg(cell_begin + (row + lw));
+                            e0[k] = __ldg(cell_begin + (row + (wrap ? g.mx : hw) + 1u));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kBatch; k++) {
+                    const int dyi = r0 + k;
+                    if (dyi < kRows && ((rowmask >> dyi) & 1u)) {
+                        push(b0[k], e0[k] - b0[k]);
+                        if ((wraps >> k) & 1u) second_range(dyi);
+                    }
+                }
+            }
         } else {
 #pragma unroll 1
-            for (int dyi = 0; dyi <= 2 * rad; dyi++) do_row(dyi);
+            for (int dyi = 0; dyi <= 2 * rad; dyi++) {
+                if (!((rowmask >> dyi) & 1u)) continue;
+                u32 row, lw, hw;
+                if (!row_geometry(dyi, row, lw, hw)) continue;
+                const bool wrap = lw > hw;
+                const u32 b0 = __ldg(cell_begin + (row + lw));
+                push(b0, __ldg(cell_begin + (row + (wrap ? g.mx : hw) + 1u)) - b0);
+                if (wrap) second_range(dyi);
+            }
         }
         // ---- phase 2: flat fused walk; the trip count is the warp's largest candidate total ----
         const u32 maxtotal = __reduce_max_sync(kFull, total);
