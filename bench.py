@@ -445,7 +445,7 @@ def run_ours(args, rank, world, local_rank):
                 "frac": kernels[dom]["frac_hbm"], "traffic": traffic, "peak_kind": peak_kind, "issue": issue,
                 "note": "the PBF kernels are FP32-issue bound, not HBM bound: ~200 candidate tests + ~140 interactions per particle against "
                         "36-64 compulsory bytes (SURVEY 8d, DESIGN.md 4).  'traffic' exceeds the algorithmic bytes on purpose: K6 leaves "
-                        "~0.7 KB/particle of neighbour lists in HBM so that K7 does not search again (idle bandwidth traded for issue slots); "
+                        "~0.6 KB/particle of neighbour lists in HBM so that K7 does not search again (idle bandwidth traded for issue slots); "
                         "the HBM-bound streaming kernels are in 'kernels'"}
 
     # ---------------- the same scene further on: the blob has hit the floor and spreads (steps that the 20-step window never sees) ----------------

@@ -17,7 +17,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__throughput.avg.pct_of_peak_sustained_active",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
-STAGE_OF = {"k_find_lambdas": "lambda", "k_solve_fluids": "delta_p", "k_solve_fluids_list": "delta_p", "k_radix_pass": "sort", "k_radix_hist": "sort", "k_reorder": "reorder",
+STAGE_OF = {"k_find_lambdas": "lambda", "k_find_lambdas_fused": "lambda", "k_find_lambdas_staged": "lambda", "k_calc_hash_hist": "hash", "k_solve_fluids": "delta_p", "k_solve_fluids_list": "delta_p", "k_radix_pass": "sort", "k_radix_hist": "sort", "k_reorder": "reorder",
             "k_cell_begin": "cell_table", "k_cell_fill": "cell_table", "k_collide_world": "world", "k_collide": "contacts", "k_calc_hash": "hash",
             "k_predict": "predict", "k_velocity": "velocity", "k_lambda": "lambda", "k_delta": "delta_p"}
 
@@ -87,5 +87,20 @@ def traffic(rep):
     print(json.dumps(out, indent=1))
 
 
+def inst(rep):
+    """warp-instructions per stage call (smsp__inst_executed.sum), same aggregation as traffic(): profiles/ncu_inst.json"""
+    hdr, units, rows = raw_rows(rep)
+    ni, ii = hdr.index("Kernel Name"), hdr.index("smsp__inst_executed.sum")
+    acc = collections.defaultdict(lambda: collections.defaultdict(list))
+    for r in rows:
+        k = short(r[ni]).split("<")[0]
+        acc[STAGE_OF.get(k, k)][k].append(float(r[ii].replace(",", "")))
+    out = {}
+    for stage, ks in acc.items():
+        fewest = min(len(v) for v in ks.values())
+        out[stage] = sum(sum(v) / len(v) * round(len(v) / fewest, 2) for v in ks.values())
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic, "inst": inst}[sys.argv[1]](sys.argv[2])
