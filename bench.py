@@ -686,14 +686,18 @@ def run_slabs(args, rank, world, local_rank):
             # a host-driven loop would hand the delivered state back; the timing loop re-submits the same host frames, which hold a
             # valid state of exactly this rank's owned particles only while nothing migrates — so inputs are staged on the first
             # step of the run and the later steps deliver outputs only when the owned count has changed
-            if sol.n_owned == k0:
+            mode = os.environ.get("PS_E2E_MODE", "both")   # diagnostics: in | out | both | none
+            if sol.n_owned == k0 and mode in ("both", "in"):
                 sol.io_begin(ip.data_ptr(), iv.data_ptr())
                 staged[0] += 1
-            if k + 1 < steps and sol.n_owned == k0:   # the next step's upload starts now: issuing a slab step blocks the host
+            if k + 1 < steps and sol.n_owned == k0 and mode in ("both", "in"):   # the next step's upload starts now: issuing a slab step blocks the host
                 nip, niv = hin[(k + 1) & 1]
                 sol.io_prefetch(nip.data_ptr(), niv.data_ptr())
             step()
-            sol.io_end(op.data_ptr(), ov.data_ptr())
+            if mode in ("both", "out"):
+                sol.io_end(op.data_ptr(), ov.data_ptr())
+            else:
+                sol.io_end(None, None)
             sol.io_wait(1)
         sol.io_wait(0)
         sol.sync()

@@ -199,12 +199,13 @@ static int exchange(PsCtx *c, void *const to[2], const uint32_t counts[2], void 
     cudaStream_t s = c->stream;
     if (!recv_known) {
         m->counts_host[0] = counts[0]; m->counts_host[1] = counts[1]; m->counts_host[2] = 0; m->counts_host[3] = 0;
-        CC(cudaMemcpyAsync(m->counts_dev, m->counts_host, 4 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        // (kernel copies between pinned host memory and the device: a copy-engine transfer would queue behind a streamed step's bulk I/O)
+        ps_launch_copy_words(m->counts_dev, m->counts_host, 4, s);
         NC(g_nccl.GroupStart());
         if (has_l) { NC(g_nccl.Send(m->counts_dev + 0, 4, kNcclUint8, r - 1, m->comm, s)); NC(g_nccl.Recv(m->counts_dev + 2, 4, kNcclUint8, r - 1, m->comm, s)); }
         if (has_r) { NC(g_nccl.Send(m->counts_dev + 1, 4, kNcclUint8, r + 1, m->comm, s)); NC(g_nccl.Recv(m->counts_dev + 3, 4, kNcclUint8, r + 1, m->comm, s)); }
         NC(g_nccl.GroupEnd());
-        CC(cudaMemcpyAsync(m->counts_host + 2, m->counts_dev + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        ps_launch_copy_words(m->counts_host + 2, m->counts_dev + 2, 2, s);
         CC(cudaStreamSynchronize(s));
         recv[0] = has_l ? m->counts_host[2] : 0;
         recv[1] = has_r ? m->counts_host[3] : 0;

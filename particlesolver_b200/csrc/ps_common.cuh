@@ -179,4 +179,6 @@ void ps_launch_slab_compact1(const float4 *pos, const u32 *src, u32 *dst, u32 n,
                              cudaStream_t s);
 void ps_launch_slab_append_migrants(float4 *pos, float4 *prev, float4 *vel, float *w, float *ros, int *phase, u32 first, const void *from_left,
                                     u32 n_left, const void *from_right, u32 n_right, cudaStream_t s);
+// words between device memory and pinned (device-visible) host memory by a kernel, not by a copy engine
+void ps_launch_copy_words(u32 *dst, const u32 *src, u32 n, cudaStream_t s);
 void ps_launch_slab_x_histogram(const float4 *pos, u32 n, float x_min, float x_max, u32 bins, u32 *hist, cudaStream_t s);

@@ -872,7 +872,7 @@ static int slab_ready(PsCtx *c, const char *what) {
 }
 static int slab_fetch_counts(PsCtx *c, u32 n, uint32_t counts[2]) {
     const size_t tiles = (ps_slab_scratch_elems(n) - 2) / 2;
-    CU(cudaMemcpyAsync(c->slab_counts_host, c->slab_scratch + 2 * tiles, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c->stream));
+    ps_launch_copy_words(c->slab_counts_host, c->slab_scratch + 2 * tiles, 2, c->stream);  // (pinned host memory; not a copy-engine transfer)
     CU(cudaStreamSynchronize(c->stream));
     counts[0] = c->slab_counts_host[0];
     counts[1] = c->slab_counts_host[1];

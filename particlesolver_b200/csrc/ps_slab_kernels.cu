@@ -303,3 +303,18 @@ void ps_launch_slab_x_histogram(const float4 *pos, u32 n, float x_min, float x_m
     if (!n) return;
     k_slab_x_histogram<<<(n + 255) / 256, 256, 0, s>>>(pos, n, x_min, (float)bins / (x_max - x_min), bins, hist);
 }
+
+// A few 32-bit words between device memory and PINNED host memory (either direction) by a kernel instead of a copy-engine
+// transfer: the counts a slab step waits for must not queue behind a bulk host transfer of a streamed step's results on the same
+// engine (ps_step_streamed / ps_io_end: 2 x 128 MB at 8M particles held every count fetch for 2.7 ms, profiles/r2s).
+namespace {
+__global__ void k_copy_words(u32 *__restrict__ dst, const u32 *__restrict__ src, u32 n) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+    __threadfence_system();
+}
+}  // namespace
+void ps_launch_copy_words(u32 *dst, const u32 *src, u32 n, cudaStream_t s) {
+    if (!n) return;
+    k_copy_words<<<(n + 63) / 64, 64, 0, s>>>(dst, src, n);
+}
