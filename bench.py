@@ -204,7 +204,7 @@ def time_c1_gpu(ticks=200):
         return {"error": str(e)}
 
 
-def time_reference_gpu_solver(steps, warmup):
+def time_reference_gpu_solver(steps, warmup, scene="c3"):
     """The reference's own UNMODIFIED CUDA sources (gpu/src/cuda/*.cu + particlesystem.cpp compiled for sm_100a with a
     texture-reference shim, oracle/_ref/ref_gpu; the binary travels with the snapshot) on the c3 workload at the full
     1,000,000 particles, `warmup` untimed + `steps` timed ParticleSystem::update calls, CUDA events around each."""
@@ -215,9 +215,13 @@ def time_reference_gpu_solver(steps, warmup):
     import tempfile
     out = tempfile.mkdtemp(prefix="ref_gpu_")
     try:
-        r = subprocess.run([exe, "--scene", "c3", "--grid", str(GRID), "--side", str(SIDE), "--max", str(SIDE ** 3 + 4096), "--iters", str(ITERS),
+        if scene == "c5r":   # the per-GPU share of the multi-GPU workload (80 lattice planes = 7,968,000 particles; the reference's lists: 64 GB)
+            spec = ["--scene", "c5r", "--side", "80", "--max", str(80 * 250 * 400 + 4096)]
+        else:
+            spec = ["--scene", "c3", "--grid", str(GRID), "--side", str(SIDE), "--max", str(SIDE ** 3 + 4096)]
+        r = subprocess.run([exe, *spec, "--iters", str(ITERS),
                             "--mode", "whole", "--steps", str(steps + warmup), "--warmup", str(warmup), "--dump-every", "0", "--out", out],
-                           capture_output=True, text=True, timeout=600)
+                           capture_output=True, text=True, timeout=900)
         for line in r.stdout.splitlines():
             if line.startswith("{"):
                 j = json.loads(line)
@@ -262,6 +266,11 @@ def run_reference(args, rank, world):
             "gpu_launches": 0}
     if not c5:
         line["reference_gpu_solver"] = time_reference_gpu_solver(max(1, min(args.steps, 20)), max(0, min(args.warmup, 5)))
+    else:
+        # what ONE GPU of the multi-GPU run owns, through the reference's own CUDA code on one GPU (it cannot decompose a scene): the
+        # same lattice and rest density built by its addFluid; N x this rate is what the reference's kernels would deliver if they scaled perfectly
+        line["reference_gpu_solver"] = time_reference_gpu_solver(max(1, min(args.steps, 8)), max(0, min(args.warmup, 2)), scene="c5r")
+        line["reference_gpu_solver"]["note"] = "the per-GPU share (8M particles) of the c5 workload on ONE GPU; the reference has no multi-GPU path"
     ref_cpu = time_reference_cpu_solver()
     if ref_cpu:
         line["reference_cpu_solver"] = ref_cpu

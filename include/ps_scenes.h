@@ -16,7 +16,7 @@
 namespace ps_scenes {
 
 struct SceneSpec {
-    std::string scene = "7";  /* "1".."9" = reference keys, "c2" / "c3" = scaled configs */
+    std::string scene = "7";  /* "1".."9" = reference keys, "c2" / "c3" / "c5r" = scaled configs */
     int grid = 64;            /* grid is grid^3 cells (reference: 64, particleapp.cpp:25) */
     unsigned max_particles = 15000; /* reference MAX_PARTICLES, particleapp.cpp:23 */
     int iterations = 5;       /* particleapp.cpp:38 */
@@ -65,6 +65,12 @@ PS *build(const SceneSpec &a, const COLORS &colors, int numColors) {
         const int ext = (int)std::ceil(a.side * 0.625f); /* builder count = (int)ceil(ur-ll)/0.625 */
         const int l = -(ext / 2);
         ps->addFluid(make_int3(l, 6, l), make_int3(l + ext, 6 + ext, l + ext), 1.f, 1.5f, colors[rand() % numColors]);
+    } else if (s == "c5r") { /* the per-GPU share of the multi-GPU dam break (lattice spacing 2.5 r, rho0 4.1, 250 x 400 columns) built
+                                through addFluid: `side` lattice planes in x (80 -> 7,968,000 particles), grid 128 x 512 x 512 like a rank of bench.py */
+        const int xe = (int)std::ceil(a.side * 0.625f);
+        unsigned gx = 1; while ((int)gx < 2 * xe + 16) gx <<= 1;
+        ps = new PS(R, make_uint3(gx, 512, 512), a.max_particles, make_int3(0, 0, 0), make_int3(2 * xe, 256, 250), a.iterations);
+        ps->addFluid(make_int3(0, 0, 0), make_int3(xe, 156, 250), 1.f, 4.1f, colors[rand() % numColors]);
     } else if (s == "8") { /* combo scene */
         ps = new PS(R, g, a.max_particles, lo, hi, a.iterations);
         ps->addHorizCloth(make_int2(14, -4), make_int2(24, 6), make_float3(.3f, 2.5f, .3f), make_float2(.25f, .25f), 10.f, true);
