@@ -498,7 +498,7 @@ def run_ours(args, rank, world, local_rank):
         ps = None
         line["c1_2d_path"] = time_c1_gpu()
         if not args.no_c5:
-            line["c5_8M_1gpu"] = c5_single_gpu(local_rank, peak)
+            line["c5_8M_1gpu"] = c5_single_gpu(local_rank, peak, steps=args.steps, warmup=max(args.warmup, 3))  # the same steps of the scene as the N > 1 runs time
         print(json.dumps(line), flush=True)
     if ps is not None:
         ps.close()
