@@ -279,7 +279,9 @@ int ps_comm_init(PsCtx *ctx, const void *id128, int rank, int nranks);
 int ps_comm_destroy(PsCtx *ctx);
 /* this rank owns x in [x_lo, x_hi) (first / last rank: -INFINITY / INFINITY); drift bounds the motion inside one step's solver
  * iterations (0.25 for the reference's constants); exchange_lambda != 0: ghost lambdas come from their owners (halo H + drift),
- * else they are computed locally (halo 2H + 2 drift); capacities in records of the halo / migrant buffers */
+ * else they are computed locally (halo 2H + 2 drift); capacities in records of the halo / migrant buffers.  Collective: every rank
+ * calls it (it also takes the global phase census: a run in which no rank was ever handed a contact-phase particle skips the contact
+ * pass); call it again on every rank after appending particles to any of them. */
 int ps_comm_set_slab(PsCtx *ctx, float x_lo, float x_hi, float drift, int exchange_lambda, uint64_t halo_capacity, uint64_t migrant_capacity);
 int ps_comm_step(PsCtx *ctx, float dt);
 /* out[4]: particles handed to neighbours so far, ghosts held in the last iteration, payload bytes sent, steps */

@@ -98,6 +98,9 @@ struct PsComm {
     double *reduce_dev = nullptr;     // 8 doubles for ps_comm_allreduce_sum
     uint32_t ghost_counts[2] = {0, 0};
     uint64_t migrated_out = 0, ghosts = 0, bytes_sent = 0, steps = 0;
+    // the global phase census taken by ps_comm_set_slab: no rank was ever handed a contact-phase particle => the contact pass is skipped
+    bool any_contact = true;
+    uint64_t contact_sources_seen = 0;
 };
 
 static void comm_free_buffers(PsComm *m) {
@@ -184,6 +187,15 @@ extern "C" int ps_comm_set_slab(PsCtx *c, float x_lo, float x_hi, float drift, i
     // exchanged lambdas: no ghost computes one (empty range); local: ghosts within H + drift of a face do
     if (m->exchange_lambda) OK(ps_slab_set_lambda_range(c, 1.f, -1.f));
     else OK(ps_slab_set_lambda_range(c, x_lo - m->lambda_ext, x_hi + m->lambda_ext));
+    // one global agreement on the phases in play (particles only ever move between ranks, phases never change): a fluid-only run
+    // skips the contact pass, which would otherwise launch over all owned + ghost slots five times a step just to find nothing
+    double census = (double)c->contact_sources;
+    CC(cudaMemcpyAsync(m->reduce_dev, &census, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(m->reduce_dev, m->reduce_dev, 1, kNcclFloat64, kNcclSum, m->comm, c->stream));
+    CC(cudaMemcpyAsync(&census, m->reduce_dev, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CC(cudaStreamSynchronize(c->stream));
+    m->any_contact = census > 0.;
+    m->contact_sources_seen = c->contact_sources;
     m->slab_set = true;
     return PS_OK;
 }
@@ -230,6 +242,10 @@ static int exchange(PsCtx *c, void *const to[2], const uint32_t counts[2], void 
 extern "C" int ps_comm_step(PsCtx *c, float dt) {
     if (!c || !c->comm || !c->comm->slab_set) { ps_set_error("ps_comm_step: no communicator / slab (ps_comm_init, ps_comm_set_slab)"); return PS_ERR_STATE; }
     PsComm *m = c->comm;
+    if (c->contact_sources != m->contact_sources_seen) {
+        ps_set_error("ps_comm_step: particles or phases were added after ps_comm_set_slab; call it again on every rank (it takes the global phase census)");
+        return PS_ERR_STATE;
+    }
     DevGuard dg(c->device);
     uint32_t cnt[2], rcv[2];
     OK(ps_begin_step(c));
@@ -249,7 +265,7 @@ extern "C" int ps_comm_step(PsCtx *c, float dt) {
         m->ghosts = (uint64_t)rcv[0] + rcv[1];
         OK(ps_slab_set_ghosts(c, rcv[0] ? m->halo_recv[0] : nullptr, rcv[0], rcv[1] ? m->halo_recv[1] : nullptr, rcv[1]));
         OK(ps_build_grid(c));
-        OK(ps_solve_contacts(c));
+        if (m->any_contact) OK(ps_solve_contacts(c));
         if (m->exchange_lambda) {
             OK(ps_solve_fluid_lambda(c));
             // ---- ghost lambdas from their owners: one float per halo record, same order, counts known on both sides ----

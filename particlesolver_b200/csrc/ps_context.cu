@@ -330,7 +330,7 @@ extern "C" int ps_append_particles(PsCtx *c, const float *pos4, const float *vel
     CU(cudaMemcpyAsync(c->ros + c->n, rest_density, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(c->phase + c->n, phase, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));  // host buffers may be stack arrays of the caller (the reference's builders are)
-    for (uint64_t k = 0; k < n; k++) { c->n_fluid += phase[k] == PH_FLUID; c->n_gas += phase[k] == 1; c->n_contact += phase[k] >= PH_CLOTH; }
+    for (uint64_t k = 0; k < n; k++) { c->n_fluid += phase[k] == PH_FLUID; c->n_gas += phase[k] == 1; c->n_contact += phase[k] >= PH_CLOTH; c->contact_sources += phase[k] >= PH_CLOTH; }
     c->n += (u32)n;
     c->h_occ.resize(c->n, 0u);
     c->constraints_dirty = true;
@@ -812,7 +812,7 @@ static int copy_common(PsCtx *c, int which, void *host, uint64_t off, uint64_t c
     else CU(cudaMemcpyAsync(d, host, cnt * a.esz, cudaMemcpyHostToDevice, c->stream));
     if (sync) CU(cudaStreamSynchronize(c->stream));
     if (!to_host && (which == PS_ARR_POS || which == PS_ARR_INV_MASS || which == PS_ARR_PHASE)) c->grid_valid = false;
-    if (!to_host && which == PS_ARR_PHASE) { c->census_known = false; if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; } }
+    if (!to_host && which == PS_ARR_PHASE) { c->census_known = false; c->contact_sources++; if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; } }
     return PS_OK;
 }
 extern "C" int ps_download(PsCtx *c, int which, void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, host, off, cnt, true, true); }

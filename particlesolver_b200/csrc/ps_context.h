@@ -47,6 +47,9 @@ struct PsCtx {
     // fluid passes of a scene without fluid; unknown after a raw phase upload (then nothing is skipped)
     bool census_known = true;
     u32 n_fluid = 0, n_contact = 0, n_gas = 0;  // phase == FLUID, phase >= CLOTH, phase == GAS
+    // contact-phase (>= CLOTH) particles ever handed to this context by its host, +1 per raw phase upload (unknown contents): unlike the
+    // census above it survives the slab operations, so a decomposed run can agree once, globally, that no rank holds a contact particle
+    uint64_t contact_sources = 0;
 
     // per-particle state (SoA).  pos may be caller-owned in the reference-ABI shim, hence the indirection.
     float4 *pos = nullptr, *vel = nullptr, *prev = nullptr, *spos = nullptr;
