@@ -272,7 +272,10 @@ int ps_set_ghost_count(PsCtx *ctx, uint64_t ghosts);
  * by whatever channel the host has (a file, MPI, torch.distributed ...); every rank calls ps_comm_init, describes its slab and
  * then steps with ps_comm_step instead of ps_step: predict, migration, and per solver iteration the halo refresh, the solver
  * stages and the ghost-lambda exchange, with the neighbour exchange as NCCL send / recv on the context's stream.  NCCL is loaded
- * at run time (dlopen of libnccl.so.2): a single-GPU host never needs it. */
+ * at run time (dlopen of libnccl.so.2): a single-GPU host never needs it.  Scope: fluid scenes (BASELINE config C5).  Index-based
+ * constraints and rigid bodies are refused on slab contexts, and contact FRICTION across a face would need the neighbour's previous
+ * position, which the 32-byte halo record does not carry (positions, inverse mass, rest density and phase travel: enough for the
+ * density constraint and for frictionless contacts). */
 #define PS_COMM_ID_BYTES 128
 int ps_comm_get_unique_id(void *id128);
 int ps_comm_init(PsCtx *ctx, const void *id128, int rank, int nranks);
