@@ -45,15 +45,53 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *sm, u32 &total) {  //
     return base + incl - v;
 }
 
+// A tile's items are interleaved over the CTA — item (k, t) is particle tile_base + k * kBlock + t, so a warp's loads are contiguous
+// (a thread owning 8 CONSECUTIVE particles, the first layout, made every load instruction touch 32 different lines) — and are ranked
+// in PARTICLE order: rank(k, t) = number of flagged items (k', t') of the tile with (k', t') < (k, t), i.e. ballots inside a row of
+// 32, an exclusive scan over the kItems x kWarps row counts.  sm: 2 * kItems * kWarps + 1 words.
+constexpr int kWarps = kBlock / 32;
+constexpr int kRankSmem = 2 * kItems * kWarps + 1;
+__device__ __forceinline__ void tile_excl_ranks(const bool (&f)[kItems], u32 *sm, u32 (&rank)[kItems], u32 &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
+    u32 b[kItems];
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        b[k] = __ballot_sync(0xffffffffu, f[k]);
+        if (lane == 0) sm[k * kWarps + wid] = __popc(b[k]);
+    }
+    __syncthreads();
+    constexpr int kCounts = kItems * kWarps;  // 64: two per lane of warp 0
+    static_assert(kCounts == 64, "the scan below takes two counts per lane");
+    if (wid == 0) {
+        const u32 c0 = sm[2 * lane], c1 = sm[2 * lane + 1];
+        u32 incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const u32 excl = incl - (c0 + c1);
+        sm[kCounts + 2 * lane] = excl;
+        sm[kCounts + 2 * lane + 1] = excl + c0;
+        if (lane == 31) sm[2 * kCounts] = incl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kItems; k++) rank[k] = sm[kCounts + k * kWarps + wid] + __popc(b[k] & lt);
+    total = sm[2 * kCounts];
+    __syncthreads();  // sm may be reused by the next call
+}
+
 // pass 1: per-tile counts of class-1 (left) and class-2 (right) particles -> tile_counts[2*tile + {0,1}]
 __global__ void __launch_bounds__(kBlock) k_slab_count(const float4 *__restrict__ pos, u32 n, float left_below, float right_from,
                                                        u32 *__restrict__ tile_counts) {
     __shared__ u32 sm[kBlock / 32];
-    const u32 base = blockIdx.x * kTile + threadIdx.x * kItems;
+    const u32 base = blockIdx.x * kTile + threadIdx.x;
     u32 cl = 0, cr = 0;
 #pragma unroll
     for (int k = 0; k < kItems; k++) {
-        const u32 i = base + k;
+        const u32 i = base + k * kBlock;
         if (i < n) {
             const u32 c = classify(__ldg(&pos[i].x), left_below, right_from);
             cl += c & 1u;
@@ -102,29 +140,32 @@ __global__ void __launch_bounds__(kBlock) k_slab_pack_halo(const float4 *__restr
                                                            const int *__restrict__ phase, u32 n, float left_below, float right_from,
                                                            const u32 *__restrict__ tile_offsets, HaloRec *__restrict__ left, HaloRec *__restrict__ right,
                                                            u32 cap, uint2 *__restrict__ ranks) {
-    __shared__ u32 sm[kBlock / 32];
-    const u32 base = blockIdx.x * kTile + threadIdx.x * kItems;
-    u32 cls[kItems], cl = 0, cr = 0;
+    __shared__ u32 sm[kRankSmem];
+    const u32 base = blockIdx.x * kTile + threadIdx.x;
+    u32 cls[kItems];
+    bool fl[kItems], fr[kItems];
 #pragma unroll
     for (int k = 0; k < kItems; k++) {
-        const u32 i = base + k;
+        const u32 i = base + k * kBlock;
         cls[k] = i < n ? classify(__ldg(&pos[i].x), left_below, right_from) : 0u;
-        cl += cls[k] & 1u;
-        cr += cls[k] >> 1;
+        fl[k] = cls[k] & 1u;
+        fr[k] = cls[k] & 2u;
     }
-    u32 dummy;
-    u32 ol = tile_offsets[2 * blockIdx.x] + block_excl_scan(cl, sm, dummy);
-    u32 orr = tile_offsets[2 * blockIdx.x + 1] + block_excl_scan(cr, sm, dummy);
+    u32 rl[kItems], rr[kItems], dummy;
+    tile_excl_ranks(fl, sm, rl, dummy);
+    tile_excl_ranks(fr, sm, rr, dummy);
+    const u32 tl = tile_offsets[2 * blockIdx.x], tr = tile_offsets[2 * blockIdx.x + 1];
 #pragma unroll
     for (int k = 0; k < kItems; k++) {
-        const u32 i = base + k;
+        const u32 i = base + k * kBlock;
+        const u32 ol = tl + rl[k], orr = tr + rr[k];
         // where particle i went in the two buffers (kNoRank: not selected), for the lambda exchange that follows K6
         if (ranks && i < n) ranks[i] = make_uint2((cls[k] & 1u) ? ol : kNoRank, (cls[k] & 2u) ? orr : kNoRank);
         if (!cls[k]) continue;
         HaloRec r;
         r.pos = pos[i]; r.w = w[i]; r.ros = ros[i]; r.phase = phase[i]; r.pad = 0;
-        if (cls[k] & 1u) { if (ol < cap) left[ol] = r; ol++; }
-        if (cls[k] & 2u) { if (orr < cap) right[orr] = r; orr++; }
+        if ((cls[k] & 1u) && ol < cap) left[ol] = r;
+        if ((cls[k] & 2u) && orr < cap) right[orr] = r;
     }
 }
 
@@ -171,27 +212,29 @@ __global__ void __launch_bounds__(kBlock) k_slab_pack_migrants(const float4 *__r
                                                                const float *__restrict__ w, const float *__restrict__ ros, const int *__restrict__ phase,
                                                                u32 n, float left_below, float right_from, const u32 *__restrict__ tile_offsets,
                                                                MigrantRec *__restrict__ left, MigrantRec *__restrict__ right, u32 cap) {
-    __shared__ u32 sm[kBlock / 32];
-    const u32 base = blockIdx.x * kTile + threadIdx.x * kItems;
-    u32 cls[kItems], cl = 0, cr = 0;
+    __shared__ u32 sm[kRankSmem];
+    const u32 base = blockIdx.x * kTile + threadIdx.x;
+    u32 cls[kItems];
+    bool fl[kItems], fr[kItems];
 #pragma unroll
     for (int k = 0; k < kItems; k++) {
-        const u32 i = base + k;
+        const u32 i = base + k * kBlock;
         cls[k] = i < n ? classify(__ldg(&pos[i].x), left_below, right_from) : 0u;
-        cl += cls[k] & 1u;
-        cr += cls[k] >> 1;
+        fl[k] = cls[k] & 1u;
+        fr[k] = (cls[k] & 1u) == 0 && (cls[k] & 2u);
     }
-    u32 dummy;
-    u32 ol = tile_offsets[2 * blockIdx.x] + block_excl_scan(cl, sm, dummy);
-    u32 orr = tile_offsets[2 * blockIdx.x + 1] + block_excl_scan(cr, sm, dummy);
+    u32 rl[kItems], rr[kItems], dummy;
+    tile_excl_ranks(fl, sm, rl, dummy);
+    tile_excl_ranks(fr, sm, rr, dummy);
+    const u32 tl = tile_offsets[2 * blockIdx.x], tr = tile_offsets[2 * blockIdx.x + 1];
 #pragma unroll
     for (int k = 0; k < kItems; k++) {
         if (!cls[k]) continue;
-        const u32 i = base + k;
+        const u32 i = base + k * kBlock;
         MigrantRec r;
         r.pos = pos[i]; r.prev = prev[i]; r.vel = vel[i]; r.w = w[i]; r.ros = ros[i]; r.phase = phase[i]; r.pad = 0;
-        if (cls[k] & 1u) { if (ol < cap) left[ol] = r; ol++; }
-        else { if (orr < cap) right[orr] = r; orr++; }
+        if (cls[k] & 1u) { if (tl + rl[k] < cap) left[tl + rl[k]] = r; }
+        else { if (tr + rr[k] < cap) right[tr + rr[k]] = r; }
     }
 }
 
@@ -200,23 +243,21 @@ __global__ void __launch_bounds__(kBlock) k_slab_pack_migrants(const float4 *__r
 template <class T>
 __global__ void __launch_bounds__(kBlock) k_slab_compact(const float4 *__restrict__ pos, const T *__restrict__ src, T *__restrict__ dst, u32 n,
                                                          float left_below, float right_from, const u32 *__restrict__ tile_offsets) {
-    __shared__ u32 sm[kBlock / 32];
-    const u32 base = blockIdx.x * kTile + threadIdx.x * kItems;
-    u32 cls[kItems], gone = 0;
+    __shared__ u32 sm[kRankSmem];
+    const u32 base = blockIdx.x * kTile + threadIdx.x;
+    bool gone[kItems];
 #pragma unroll
     for (int k = 0; k < kItems; k++) {
-        const u32 i = base + k;
-        cls[k] = i < n ? classify(__ldg(&pos[i].x), left_below, right_from) : 0u;
-        gone += cls[k] ? 1u : 0u;
+        const u32 i = base + k * kBlock;
+        gone[k] = i < n && classify(__ldg(&pos[i].x), left_below, right_from) != 0u;
     }
-    u32 dummy;
-    u32 before = tile_offsets[2 * blockIdx.x] + tile_offsets[2 * blockIdx.x + 1] + block_excl_scan(gone, sm, dummy);
+    u32 rg[kItems], dummy;
+    tile_excl_ranks(gone, sm, rg, dummy);
+    const u32 before_tile = tile_offsets[2 * blockIdx.x] + tile_offsets[2 * blockIdx.x + 1];
 #pragma unroll
     for (int k = 0; k < kItems; k++) {
-        const u32 i = base + k;
-        if (i >= n) break;
-        if (cls[k]) { before++; continue; }
-        dst[i - before] = src[i];
+        const u32 i = base + k * kBlock;
+        if (i < n && !gone[k]) dst[i - (before_tile + rg[k])] = src[i];
     }
 }
 
