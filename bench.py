@@ -134,6 +134,35 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this process (and allocate its pinned host buffers) on the CPU cores that are local to its GPU's PCIe root: torchrun does
+    not bind its workers, and with eight ranks streaming 512 MB per step each through host memory, buffers that land on the other
+    socket cross the inter-socket link in both directions.  Returns a short description (for the JSON line) or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        dom, bus, dev = getattr(pr, "pci_domain_id", 0), getattr(pr, "pci_bus_id", None), getattr(pr, "pci_device_id", 0)
+        if bus is None:
+            return None
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        node = open(path.replace("local_cpulist", "numa_node")).read().strip()
+        return f"NUMA node {node} ({len(cpus)} cpus)"
+    except Exception:
+        return None
+
+
 def c3_sample(side, seed=1234):
     """CPU-side sample of the c3 workload: side^3 lattice, spacing 2.5 r, jitter +-0.01 r, rho0 1.5, mass 1."""
     rng = np.random.default_rng(seed)
@@ -573,6 +602,7 @@ def run_slabs(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the solver has no CPU path")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if not os.environ.get("PS_NO_NUMA_BIND") else None
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -774,7 +804,8 @@ def run_slabs(args, rank, world, local_rank):
                 "particle_iterations_per_s": value * ITERS,
                 "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 32 * total, "d2h_bytes_per_step": 32 * total,
                         "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "steps_with_inputs_staged_min_over_ranks": e2e_inputs_staged,
-                        "api": "ps_io_begin / ps_io_end / ps_io_wait around the slab step (double-buffered PCIe transfers beside the solver)"},
+                        "api": "ps_io_begin / ps_io_prefetch / ps_io_end / ps_io_wait around the slab step (double-buffered PCIe transfers beside the solver)",
+                        "host_binding_rank0": numa},
                 "gpu_launches": launches_per_step * args.steps * world,
                 "roofline": roofline, "stage_ms_per_step_rank0": stage_ms,
                 "state_check": {"particles_total_now": int(g_count), "particles_conserved": int(g_count) == total, "mean_density_error": g_mde,
