@@ -286,6 +286,11 @@ int ps_comm_destroy(PsCtx *ctx);
  * calls it (it also takes the global phase census: a run in which no rank was ever handed a contact-phase particle skips the contact
  * pass); call it again on every rank after appending particles to any of them. */
 int ps_comm_set_slab(PsCtx *ctx, float x_lo, float x_hi, float drift, int exchange_lambda, uint64_t halo_capacity, uint64_t migrant_capacity);
+/* load balancing: all the cut planes (nranks + 1 floats; the first / last are taken as -INFINITY / INFINITY) and a schedule — every
+ * `every` steps (0 = never) the planes move to the equal-count quantiles of the particles' x (per-rank histograms over `bins` <= 65536
+ * bins of [x_min, x_max), all-reduced); the migration of that step hands the particles over.  Same arguments on every rank. */
+int ps_comm_set_recut(PsCtx *ctx, const float *cuts, uint32_t every, float x_min, float x_max, uint32_t bins);
+int ps_comm_get_cuts(PsCtx *ctx, float *cuts, uint32_t *recuts);
 int ps_comm_step(PsCtx *ctx, float dt);
 /* out[4]: particles handed to neighbours so far, ghosts held in the last iteration, payload bytes sent, steps */
 int ps_comm_stats(PsCtx *ctx, uint64_t out[4]);

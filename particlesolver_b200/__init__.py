@@ -132,6 +132,8 @@ def lib():
         L.ps_comm_destroy.argtypes = [vp]
         L.ps_comm_set_slab.argtypes = [vp, f32, f32, f32, i32, u64, u64]
         L.ps_comm_step.argtypes = [vp, f32]
+        L.ps_comm_set_recut.argtypes = [vp, vp, u32, f32, f32, u32]
+        L.ps_comm_get_cuts.argtypes = [vp, vp, vp]
         L.ps_comm_stats.argtypes = [vp, vp]
         L.ps_comm_allreduce_sum.argtypes = [vp, vp, u32]
         # C++ host class (csrc/particle_system.cpp)
@@ -358,6 +360,17 @@ class Solver:
 
     def comm_set_slab(self, x_lo, x_hi, drift=0.25, exchange_lambda=True, halo_capacity=1 << 16, migrant_capacity=1 << 16):
         _check(lib().ps_comm_set_slab(self._h, x_lo, x_hi, drift, int(bool(exchange_lambda)), int(halo_capacity), int(migrant_capacity)))
+
+    def comm_set_recut(self, cuts, every, x_min, x_max, bins=4096):
+        """all nranks + 1 cut planes and the re-cut schedule (ps_comm_set_recut); same arguments on every rank"""
+        a = np.ascontiguousarray(cuts, np.float32)
+        _check(lib().ps_comm_set_recut(self._h, _ptr(a), int(every), x_min, x_max, int(bins)))
+
+    def comm_cuts(self, nranks):
+        a = np.zeros(nranks + 1, np.float32)
+        k = C.c_uint32()
+        _check(lib().ps_comm_get_cuts(self._h, _ptr(a), C.byref(k)))
+        return a, int(k.value)
 
     def comm_step(self, dt):
         _check(lib().ps_comm_step(self._h, dt))

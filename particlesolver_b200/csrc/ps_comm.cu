@@ -10,8 +10,10 @@
 // NCCL is resolved at run time (dlopen of libnccl.so.2 in ps_comm_init): libpsolver.so carries no link-time dependency on it, a
 // single-GPU host never loads it, and inside a process that already holds an NCCL (torch's) that one is used.
 #include <dlfcn.h>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 #include "ps_context.h"
 
 namespace {
@@ -101,6 +103,12 @@ struct PsComm {
     // the global phase census taken by ps_comm_set_slab: no rank was ever handed a contact-phase particle => the contact pass is skipped
     bool any_contact = true;
     uint64_t contact_sources_seen = 0;
+    // load balancing (ps_comm_set_recut): every `recut_every` steps the cut planes move to the equal-count quantiles of the particles' x
+    std::vector<double> cuts;         // nranks + 1 planes, outer ones +-inf; empty: fixed slab (ps_comm_set_slab alone)
+    uint32_t recut_every = 0, recut_bins = 0, recuts = 0;
+    float recut_xmin = 0.f, recut_xmax = 0.f;
+    double *hist_dev = nullptr;       // recut_bins doubles for the all-reduce of the x-histograms
+    uint32_t hist_cap = 0;
 };
 
 static void comm_free_buffers(PsComm *m) {
@@ -118,6 +126,7 @@ void ps_comm_free(PsCtx *c) {
     if (m->counts_dev) cudaFree(m->counts_dev);
     if (m->counts_host) cudaFreeHost(m->counts_host);
     if (m->reduce_dev) cudaFree(m->reduce_dev);
+    if (m->hist_dev) cudaFree(m->hist_dev);
     delete m;
     c->comm = nullptr;
 }
@@ -200,6 +209,90 @@ extern "C" int ps_comm_set_slab(PsCtx *c, float x_lo, float x_hi, float drift, i
     return PS_OK;
 }
 
+// ---- load balancing: re-cutting the slabs (slab.py: SlabDomain.apply_recut / balanced_cuts, restated) ----
+// New cut planes from the global histogram of the particles' x (hist[b] = count in bin b of [x_min, x_max)): the equal-count
+// quantiles, linearly interpolated inside a bin, then limited — a cut moves by at most max_shift per re-cut (particles change owner
+// by hopping to the NEIGHBOURING rank, one hop per step, so a cut must not jump over a slab) and slabs stay at least min_width wide
+// (a rank's ghosts all come from its two neighbours: the halo must fit inside a slab).  A pure function of its arguments: every rank
+// derives the same planes from the all-reduced histogram.
+static std::vector<double> balanced_cuts(const std::vector<double> &hist, double x_min, double x_max, const std::vector<double> &old_cuts, double min_width,
+                                         double max_shift) {
+    const int nranks = (int)old_cuts.size() - 1, bins = (int)hist.size();
+    std::vector<double> out(nranks + 1);
+    out[0] = -INFINITY; out[nranks] = INFINITY;
+    if (nranks == 1) return out;
+    std::vector<double> cum(bins + 1, 0.0);
+    for (int b = 0; b < bins; b++) cum[b + 1] = cum[b] + hist[b];
+    const double total = cum[bins];
+    for (int r = 1; r < nranks; r++) {
+        const double target = total * r / nranks;
+        int b = (int)(std::upper_bound(cum.begin(), cum.end(), target) - cum.begin()) - 1;   // np.searchsorted(cum, target, side="right") - 1
+        b = std::min(std::max(b, 0), bins - 1);
+        const double frac = hist[b] > 0 ? (target - cum[b]) / hist[b] : 0.5;
+        const double e0 = x_min + (x_max - x_min) * b / bins, e1 = x_min + (x_max - x_min) * (b + 1) / bins;
+        double cnew = e0 + frac * (e1 - e0);
+        const double old = old_cuts[r];
+        if (std::isfinite(old)) cnew = std::min(std::max(cnew, old - max_shift), old + max_shift);
+        if (std::isfinite(out[r - 1])) cnew = std::max(cnew, out[r - 1] + min_width);
+        out[r] = cnew;
+    }
+    for (int r = nranks - 1; r > 1; r--)  // keep the minimum width from the right as well
+        if (out[r] - out[r - 1] < min_width) out[r - 1] = out[r] - min_width;
+    return out;
+}
+
+static int apply_cuts(PsCtx *c, const std::vector<double> &cuts) {
+    PsComm *m = c->comm;
+    m->cuts = cuts;
+    m->x_lo = (float)cuts[m->rank]; m->x_hi = (float)cuts[m->rank + 1];
+    if (!m->exchange_lambda) OK(ps_slab_set_lambda_range(c, m->x_lo - m->lambda_ext, m->x_hi + m->lambda_ext));
+    return PS_OK;
+}
+
+// All the cut planes (nranks + 1 values, cuts[0] = -INFINITY, cuts[nranks] = INFINITY; this rank owns [cuts[rank], cuts[rank + 1])) and the
+// re-cut schedule: every `every` steps (0: never), right after the predict, the planes move to the equal-count quantiles of the owned
+// particles' x — per-rank histograms over `bins` bins of [x_min, x_max), all-reduced — and the migration that follows hands the
+// particles over.  Call after ps_comm_set_slab, with the same arguments on every rank.
+extern "C" int ps_comm_set_recut(PsCtx *c, const float *cuts, uint32_t every, float x_min, float x_max, uint32_t bins) {
+    if (!c || !c->comm || !c->comm->slab_set) { ps_set_error("ps_comm_set_recut: call ps_comm_init and ps_comm_set_slab first"); return PS_ERR_STATE; }
+    PsComm *m = c->comm;
+    if (!cuts) { ps_set_error("ps_comm_set_recut: null cut planes"); return PS_ERR_INVALID; }
+    if (every && (!(x_min < x_max) || bins < 2 || bins > 65536)) { ps_set_error("ps_comm_set_recut: need x_min < x_max and 2..65536 bins"); return PS_ERR_INVALID; }
+    std::vector<double> cv(m->nranks + 1);
+    for (int r = 0; r <= m->nranks; r++) cv[r] = cuts[r];
+    cv[0] = -INFINITY; cv[m->nranks] = INFINITY;
+    for (int r = 0; r < m->nranks; r++)
+        if (!(cv[r] < cv[r + 1])) { ps_set_error("ps_comm_set_recut: cut planes must ascend"); return PS_ERR_INVALID; }
+    DevGuard dg(c->device);
+    if (every && bins > m->hist_cap) {
+        if (m->hist_dev) CC(cudaFree(m->hist_dev));
+        CC(cudaMalloc((void **)&m->hist_dev, bins * sizeof(double)));
+        m->hist_cap = bins;
+    }
+    m->recut_every = every; m->recut_bins = bins; m->recut_xmin = x_min; m->recut_xmax = x_max;
+    return apply_cuts(c, cv);
+}
+
+static int recut(PsCtx *c) {
+    PsComm *m = c->comm;
+    const uint32_t bins = m->recut_bins;
+    std::vector<uint64_t> mine(bins);
+    OK(ps_slab_x_histogram(c, m->recut_xmin, m->recut_xmax, bins, mine.data()));
+    std::vector<double> h(bins);
+    for (uint32_t b = 0; b < bins; b++) h[b] = (double)mine[b];  // (exact: counts are far below 2^53)
+    CC(cudaMemcpyAsync(m->hist_dev, h.data(), bins * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(m->hist_dev, m->hist_dev, bins, kNcclFloat64, kNcclSum, m->comm, c->stream));
+    CC(cudaMemcpyAsync(h.data(), m->hist_dev, bins * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CC(cudaStreamSynchronize(c->stream));
+    double width = INFINITY;  // narrowest interior slab
+    for (int r = 1; r + 2 <= m->nranks - 1 + 1 && r + 1 < m->nranks; r++) width = std::min(width, m->cuts[r + 1] - m->cuts[r]);
+    const double halo = m->halo;
+    const double max_shift = std::isfinite(width) ? 0.5 * std::min(width, 4.0 * halo) : 2.0 * halo;
+    OK(apply_cuts(c, balanced_cuts(h, m->recut_xmin, m->recut_xmax, m->cuts, halo + 0.5, max_shift)));
+    m->recuts++;
+    return PS_OK;
+}
+
 // Sends `counts[0]` records of to[0] to rank - 1 and `counts[1]` of to[1] to rank + 1, receives the neighbours' into from[0] /
 // from[1].  recv_known: the receive counts are already known (the lambda exchange answers the halo exchange record by record), so
 // nothing but the payload travels and the host does not wait; otherwise the counts are exchanged first (one host synchronisation).
@@ -250,6 +343,7 @@ extern "C" int ps_comm_step(PsCtx *c, float dt) {
     uint32_t cnt[2], rcv[2];
     OK(ps_begin_step(c));
     OK(ps_predict(c, dt));
+    if (m->recut_every && m->nranks > 1 && m->steps > 0 && m->steps % m->recut_every == 0) OK(recut(c));
     // ---- migration: owned particles whose predicted x left the slab go to the neighbour with pos / prev / vel / w / rho0 / phase ----
     OK(ps_slab_pack_migrants(c, m->x_lo, m->x_hi, m->migr_send[0], m->migr_send[1], m->migr_cap, cnt));
     m->migrated_out += (uint64_t)cnt[0] + cnt[1];
@@ -281,6 +375,18 @@ extern "C" int ps_comm_step(PsCtx *c, float dt) {
     }
     OK(ps_update_velocity(c, dt));
     m->steps++;
+    return PS_OK;
+}
+
+// the cut planes in force (nranks + 1 floats) and the number of re-cuts so far
+extern "C" int ps_comm_get_cuts(PsCtx *c, float *cuts, uint32_t *recuts) {
+    if (!c || !c->comm) { ps_set_error("ps_comm_get_cuts: no communicator"); return PS_ERR_STATE; }
+    PsComm *m = c->comm;
+    if (cuts) {
+        if (m->cuts.empty()) { for (int r = 0; r <= m->nranks; r++) cuts[r] = r == m->rank ? m->x_lo : (r == m->rank + 1 ? m->x_hi : NAN); }
+        else for (int r = 0; r <= m->nranks; r++) cuts[r] = (float)m->cuts[r];
+    }
+    if (recuts) *recuts = m->recuts;
     return PS_OK;
 }
 

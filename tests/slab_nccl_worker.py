@@ -45,11 +45,16 @@ def main():
         dist.broadcast_object_list(ident, src=0)
         sol.comm_init(ident[0], rank, world)
         sol.comm_set_slab(cuts[rank], cuts[rank + 1], drift=0.25, exchange_lambda=exchange, halo_capacity=pos.shape[0], migrant_capacity=pos.shape[0])
+        if recut:
+            sol.comm_set_recut(cuts, recut, 0.0, 40.0, 1024)
         for _ in range(steps):
             sol.comm_step(DT)
         st = sol.comm_stats()
         dom.stats["migrated_out"], dom.stats["ghosts"] = st["migrated_out"], st["ghosts"]
         dom.comm.bytes_sent = st["bytes_sent"]
+        if recut:
+            new_cuts, dom.stats["recuts"] = sol.comm_cuts(world)
+            dom.cuts = [float(v) for v in new_cuts]
         total = sol.comm_allreduce_sum([sol.n_owned])
         assert int(total[0]) == pos.shape[0], (total, pos.shape)
     else:

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("world,recut,exchange,c_abi", [(2, 0, 1, 0), (4, 0, 1, 0), (2, 1, 1, 0), (2, 0, 0, 0), (2, 0, 1, 1), (2, 0, 0, 1), (4, 0, 1, 1)])
+@pytest.mark.parametrize("world,recut,exchange,c_abi", [(2, 0, 1, 0), (4, 0, 1, 0), (2, 1, 1, 0), (2, 0, 0, 0), (2, 0, 1, 1), (2, 0, 0, 1), (4, 0, 1, 1), (2, 1, 1, 1)])
 def test_slabs_over_nccl_match_one_gpu(world, recut, exchange, c_abi):
     """c_abi = 1: the whole slab step behind the C ABI (ps_comm_init / ps_comm_set_slab / ps_comm_step: NCCL send / recv issued from
     C++ on the context's stream), else particlesolver_b200/slab.py over torch.distributed"""
