@@ -345,6 +345,9 @@ __global__ void __launch_bounds__(kBlock) k_find_lambdas(float *__restrict__ lam
 //     (ps_launch_reorder(..., slot_in_w)), so the walk tracks nothing but a slot counter and the end of the current range;
 //   * an accepted neighbour's slot goes straight to the lane's column of the warp's list region (ps_fluid_lists.cuh).
 // Arithmetic: PS_K6_BODY is, association for association, ps_lambda_terms (ps_fluid_lists.cuh) — every K6 variant gives the same bits.
+#ifndef PS_K6_LD_HINT
+#define PS_K6_LD_HINT ""  // cache hint of the candidate gathers (".L1::evict_last" measured: see DESIGN section 9)
+#endif
 #ifndef PS_ROW_BATCH
 #define PS_ROW_BATCH 9  // stencil rows whose cell-table loads are issued together (fused K6)
 #endif
@@ -366,7 +369,7 @@ static inline size_t fused_smem_bytes(int rad) { return (size_t)(2 * (2 * rad + 
                  "setp.lt.u32 lv, %19, %20;\n\t"                                                                                  \
                  "mul.wide.u32 la, %5, 16;\n\t"                                                                                   \
                  "add.u64 la, la, %24;\n\t"                                                                                       \
-                 "@lv ld.global.nc.v4.b32 {%8, %9, %10, %11}, [la];\n\t"                                                          \
+                 "@lv ld.global.nc" PS_K6_LD_HINT ".v4.b32 {%8, %9, %10, %11}, [la];\n\t"                                                          \
                  "@lv add.u32 %5, %5, 1;\n\t"                                                                                     \
                  "setp.eq.and.u32 e, %5, %6, lv;\n\t"                                                                             \
                  "@e ld.shared.v2.u32 {%5, %6}, [%7];\n\t"                                                                        \
