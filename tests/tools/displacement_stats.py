@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """How far do particles move between the first grid build of a step and the later solver iterations?  (why a
 candidate superset kept from iteration 1 and re-tested in iterations 2-5 — a Verlet list with a skin — was not built.)
-CPU only (the oracle): python scripts/displacement_stats.py [side] [steps]   — a side^3 block of the c3 scene (spacing 2.5 r, rho0 1.5)."""
+CPU only (the oracle): python tests/tools/displacement_stats.py [side] [steps]   — a side^3 block of the c3 scene (spacing 2.5 r, rho0 1.5)."""
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # tests/: the oracle binding (test infrastructure)
 import oracle_py as orc  # noqa: E402
 
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 24
