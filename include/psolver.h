@@ -220,6 +220,9 @@ int ps_slab_append_migrants(PsCtx *ctx, const void *from_left, uint64_t n_left, 
  * With the exchange the halo need only be H (+ drift) wide and K6 skips the ghosts (ps_slab_set_lambda_range(ctx, 1, -1)). */
 int ps_slab_pack_lambda(PsCtx *ctx, void *left_buf, void *right_buf, uint64_t capacity_values, uint32_t counts[2]);
 int ps_slab_set_ghost_lambda(PsCtx *ctx, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right);
+/* the two lambda messages as sinks of the lambda pass: ps_solve_fluid_lambda then fills them as it computes (no separate pack pass) and
+ * ps_slab_pack_lambda on the same buffers only reports the counts.  All-FLUID contexts only; NULL, NULL, 0 switches it off. */
+int ps_slab_set_lambda_sinks(PsCtx *ctx, void *left_buf, void *right_buf, uint64_t capacity_values);
 /* lambda is computed for owned particles and for ghosts with x in [x_min, x_max] only (default: everywhere) */
 int ps_slab_set_lambda_range(PsCtx *ctx, float x_min, float x_max);
 /* load balancing: counts of the owned particles' x in `bins` (<= 65536) equal bins of [x_min, x_max) (values outside fall

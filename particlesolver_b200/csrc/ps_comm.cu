@@ -102,7 +102,7 @@ struct PsComm {
     uint64_t migrated_out = 0, ghosts = 0, bytes_sent = 0, steps = 0;
     // the global phase census taken by ps_comm_set_slab: no rank was ever handed a contact-phase particle => the contact pass is skipped
     bool any_contact = true;
-    uint64_t contact_sources_seen = 0;
+    uint64_t contact_sources_seen = 0, nonfluid_sources_seen = 0;
     // load balancing (ps_comm_set_recut): every `recut_every` steps the cut planes move to the equal-count quantiles of the particles' x
     std::vector<double> cuts;         // nranks + 1 planes, outer ones +-inf; empty: fixed slab (ps_comm_set_slab alone)
     uint32_t recut_every = 0, recut_bins = 0, recuts = 0;
@@ -198,13 +198,17 @@ extern "C" int ps_comm_set_slab(PsCtx *c, float x_lo, float x_hi, float drift, i
     else OK(ps_slab_set_lambda_range(c, x_lo - m->lambda_ext, x_hi + m->lambda_ext));
     // one global agreement on the phases in play (particles only ever move between ranks, phases never change): a fluid-only run
     // skips the contact pass, which would otherwise launch over all owned + ghost slots five times a step just to find nothing
-    double census = (double)c->contact_sources;
-    CC(cudaMemcpyAsync(m->reduce_dev, &census, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    NC(g_nccl.AllReduce(m->reduce_dev, m->reduce_dev, 1, kNcclFloat64, kNcclSum, m->comm, c->stream));
-    CC(cudaMemcpyAsync(&census, m->reduce_dev, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    double census[2] = {(double)c->contact_sources, (double)c->nonfluid_sources};
+    CC(cudaMemcpyAsync(m->reduce_dev, census, sizeof census, cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(m->reduce_dev, m->reduce_dev, 2, kNcclFloat64, kNcclSum, m->comm, c->stream));
+    CC(cudaMemcpyAsync(census, m->reduce_dev, sizeof census, cudaMemcpyDeviceToHost, c->stream));
     CC(cudaStreamSynchronize(c->stream));
-    m->any_contact = census > 0.;
+    m->any_contact = census[0] > 0.;
     m->contact_sources_seen = c->contact_sources;
+    m->nonfluid_sources_seen = c->nonfluid_sources;
+    // an all-fluid run: K6 fills the outgoing lambda messages itself (ps_slab_set_lambda_sinks), no pack pass over the sorted slots
+    if (m->exchange_lambda && census[1] == 0.) OK(ps_slab_set_lambda_sinks(c, m->lam_send[0], m->lam_send[1], m->halo_cap));
+    else OK(ps_slab_set_lambda_sinks(c, nullptr, nullptr, 0));
     m->slab_set = true;
     return PS_OK;
 }
@@ -335,7 +339,7 @@ static int exchange(PsCtx *c, void *const to[2], const uint32_t counts[2], void 
 extern "C" int ps_comm_step(PsCtx *c, float dt) {
     if (!c || !c->comm || !c->comm->slab_set) { ps_set_error("ps_comm_step: no communicator / slab (ps_comm_init, ps_comm_set_slab)"); return PS_ERR_STATE; }
     PsComm *m = c->comm;
-    if (c->contact_sources != m->contact_sources_seen) {
+    if (c->contact_sources != m->contact_sources_seen || c->nonfluid_sources != m->nonfluid_sources_seen) {
         ps_set_error("ps_comm_step: particles or phases were added after ps_comm_set_slab; call it again on every rank (it takes the global phase census)");
         return PS_ERR_STATE;
     }

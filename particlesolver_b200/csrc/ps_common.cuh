@@ -137,12 +137,20 @@ void ps_launch_collide(float4 *pos, const float4 *prev, const float4 *spos, cons
 // re-walk the grid); format in ps_fluid_lists.cuh.  `list_rows` = rows of a warp's region (PsParams.neighbor_list_rows), `capacity`
 // = the particle capacity the buffers were sized for, `nbr_rows` = the first per-warp status word of the buffer sized by
 // ps_neighbor_record_elems; `device` = the context's device (per-device shared-memory opt-in).
+// Where K6 drops the lambdas of the particles of the last halo pack (slab contexts, ps_slab_set_lambda_sinks): ranks[orig] = the record's
+// position in the left / right halo buffer (0xffffffff: none), left / right = the outgoing lambda messages.  ranks == nullptr: off.
+struct LambdaSinks {
+    const uint2 *ranks = nullptr;
+    float *left = nullptr, *right = nullptr;
+    u32 cap = 0;
+};
 size_t ps_neighbor_list_elems(unsigned long long capacity, u32 rows_per_warp);
 size_t ps_neighbor_record_elems(unsigned long long capacity);
 u32 ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
                            const StencilDesc &st, bool zero_nonfluid, u32 *nbr_list, u32 *nbr_rows, u32 list_rows, unsigned long long capacity,
-                           bool slot_in_w, bool staged, int device, cudaStream_t s);  // returns the number of launches
+                           bool slot_in_w, bool staged, int device, cudaStream_t s, LambdaSinks sinks = LambdaSinks(),
+                           bool *sinks_written = nullptr);  // returns the number of launches; *sinks_written: the pass filled the sinks itself
 u32 ps_launch_solve_fluids(float4 *pos, const float *lambda, const float4 *spos, const int *sphase, const u32 *index,
                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, GridDesc g, const StencilDesc &st, float omega,
                            const u32 *nbr_list, const u32 *nbr_rows, u32 list_rows, const u32 *num_neighbors, int device,

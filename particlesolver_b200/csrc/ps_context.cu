@@ -330,7 +330,7 @@ extern "C" int ps_append_particles(PsCtx *c, const float *pos4, const float *vel
     CU(cudaMemcpyAsync(c->ros + c->n, rest_density, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(c->phase + c->n, phase, n * 4, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));  // host buffers may be stack arrays of the caller (the reference's builders are)
-    for (uint64_t k = 0; k < n; k++) { c->n_fluid += phase[k] == PH_FLUID; c->n_gas += phase[k] == 1; c->n_contact += phase[k] >= PH_CLOTH; c->contact_sources += phase[k] >= PH_CLOTH; }
+    for (uint64_t k = 0; k < n; k++) { c->n_fluid += phase[k] == PH_FLUID; c->n_gas += phase[k] == 1; c->n_contact += phase[k] >= PH_CLOTH; c->contact_sources += phase[k] >= PH_CLOTH; c->nonfluid_sources += phase[k] != PH_FLUID; }
     c->n += (u32)n;
     c->h_occ.resize(c->n, 0u);
     c->constraints_dirty = true;
@@ -532,10 +532,17 @@ static int issue_fluid(PsCtx *c, const char *what, bool do_lambda, bool do_delta
     DeviceGuard dg(c->device);
     // lambda is needed for the ghosts next to a face too (their owners are on another GPU): computed here for the ghosts inside
     // ps_slab_set_lambda_range, or received from the owners between the two halves (ps_slab_pack_lambda / ps_slab_set_ghost_lambda)
-    if (do_lambda)
+    if (do_lambda) {
+        LambdaSinks sinks;
+        if (c->lam_sink[0] && c->slab_ranks_valid && c->slab_halo_counts[0] <= c->lam_sink_cap && c->slab_halo_counts[1] <= c->lam_sink_cap) {
+            sinks.ranks = reinterpret_cast<const uint2 *>(c->slab_ranks); sinks.left = c->lam_sink[0]; sinks.right = c->lam_sink[1];
+            sinks.cap = (u32)std::min<uint64_t>(c->lam_sink_cap, 0xfffffffeu);
+        }
         ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost,
                                c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list,
-                               c->nbr_rows, c->nbr_max_rows, c->capacity, true, (c->params.flags & PS_FLAG_STAGED_LAMBDA) != 0, c->device, c->stream);
+                               c->nbr_rows, c->nbr_max_rows, c->capacity, true, (c->params.flags & PS_FLAG_STAGED_LAMBDA) != 0, c->device, c->stream, sinks,
+                               &c->lam_sinks_written);
+    }
     if (do_delta)
         ps_launch_solve_fluids(c->pos, c->lambda, c->spos, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost, c->grid, c->stencil,
                                c->params.omega, c->nbr_list, c->nbr_rows, c->nbr_max_rows, c->num_neighbors, c->device, c->stream);
@@ -812,7 +819,7 @@ static int copy_common(PsCtx *c, int which, void *host, uint64_t off, uint64_t c
     else CU(cudaMemcpyAsync(d, host, cnt * a.esz, cudaMemcpyHostToDevice, c->stream));
     if (sync) CU(cudaStreamSynchronize(c->stream));
     if (!to_host && (which == PS_ARR_POS || which == PS_ARR_INV_MASS || which == PS_ARR_PHASE)) c->grid_valid = false;
-    if (!to_host && which == PS_ARR_PHASE) { c->census_known = false; c->contact_sources++; if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; } }
+    if (!to_host && which == PS_ARR_PHASE) { c->census_known = false; c->contact_sources++; c->nonfluid_sources++; if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; } }
     return PS_OK;
 }
 extern "C" int ps_download(PsCtx *c, int which, void *host, uint64_t off, uint64_t cnt) { return copy_common(c, which, host, off, cnt, true, true); }
@@ -917,9 +924,25 @@ extern "C" int ps_slab_pack_lambda(PsCtx *c, void *left_buf, void *right_buf, ui
     counts[0] = c->slab_halo_counts[0];
     counts[1] = c->slab_halo_counts[1];
     if (counts[0] > cap || counts[1] > cap) { ps_set_error("ps_slab_pack_lambda: %u / %u values exceed the buffer capacity %llu", counts[0], counts[1], (unsigned long long)cap); return PS_ERR_CAPACITY; }
+    if (c->lam_sinks_written && left_buf == c->lam_sink[0] && right_buf == c->lam_sink[1]) {  // K6 has filled these very buffers already
+        c->lam_sinks_written = false;
+        return PS_OK;
+    }
     DeviceGuard dg(c->device);
     ps_launch_slab_pack_lambda(c->lambda, c->index, c->slab_ranks, c->n, c->n - c->n_ghost, (float *)left_buf, (float *)right_buf, (u32)std::min<uint64_t>(cap, 0xffffffffu), c->stream);
     return check_launch("ps_slab_pack_lambda");
+}
+// The lambda messages of ps_slab_pack_lambda as sinks of the lambda pass itself: with them set, ps_solve_fluid_lambda (the default, fused
+// K6) writes the lambda of every particle of the last halo pack into left_buf / right_buf as it computes it, and a following
+// ps_slab_pack_lambda on the same buffers only reports the counts.  For contexts whose particles are all FLUID (K6 leaves the lambda
+// of other phases untouched, and a message must carry those too).  NULL buffers: off.
+extern "C" int ps_slab_set_lambda_sinks(PsCtx *c, void *left_buf, void *right_buf, uint64_t cap) {
+    NEED(c);
+    if ((left_buf == nullptr) != (right_buf == nullptr)) { ps_set_error("ps_slab_set_lambda_sinks: both buffers or none"); return PS_ERR_INVALID; }
+    c->lam_sink[0] = (float *)left_buf; c->lam_sink[1] = (float *)right_buf;
+    c->lam_sink_cap = left_buf ? cap : 0;
+    c->lam_sinks_written = false;
+    return PS_OK;
 }
 extern "C" int ps_slab_set_ghost_lambda(PsCtx *c, const void *from_left, uint64_t n_left, const void *from_right, uint64_t n_right) {
     int r = slab_ready(c, "ps_slab_set_ghost_lambda"); if (r != PS_OK) return r;

@@ -50,6 +50,7 @@ struct PsCtx {
     // contact-phase (>= CLOTH) particles ever handed to this context by its host, +1 per raw phase upload (unknown contents): unlike the
     // census above it survives the slab operations, so a decomposed run can agree once, globally, that no rank holds a contact particle
     uint64_t contact_sources = 0;
+    uint64_t nonfluid_sources = 0;   // the same for phase != FLUID
 
     // per-particle state (SoA).  pos may be caller-owned in the reference-ABI shim, hence the indirection.
     float4 *pos = nullptr, *vel = nullptr, *prev = nullptr, *spos = nullptr;
@@ -130,6 +131,10 @@ struct PsCtx {
     uint64_t slab_ranks_cap = 0;
     u32 slab_halo_counts[2] = {0, 0}; // records of the last halo pack
     bool slab_ranks_valid = false;
+    // ps_slab_set_lambda_sinks: the outgoing lambda messages K6 fills itself; lam_sinks_written: the last lambda pass did
+    float *lam_sink[2] = {nullptr, nullptr};
+    uint64_t lam_sink_cap = 0;
+    bool lam_sinks_written = false;
     bool slab_used = false;           // a slab call has compacted / appended particles: index-based constraints and bodies are refused from then on
     float lambda_xmin = -3.0e38f, lambda_xmax = 3.0e38f;
     PsStreamIo io;

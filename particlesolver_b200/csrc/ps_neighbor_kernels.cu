@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kBlock, PS_FUSED_MINB) k_find_lambdas_fused(fl
                                                                const u32 *__restrict__ cell_begin, const float *__restrict__ ros, u32 n,
                                                                u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g, StencilDesc st,
                                                                int zero_nonfluid, u32 *__restrict__ pool, u32 *__restrict__ recs, u32 list_rows,
-                                                               size_t dump_offset) {
+                                                               size_t dump_offset, LambdaSinks sinks) {
     extern __shared__ __align__(16) uint2 fused_segs[];
     const int tid = threadIdx.x, lane = tid & 31;
     const u32 i = blockIdx.x * kBlock + tid;
@@ -592,8 +592,16 @@ __global__ void __launch_bounds__(kBlock, PS_FUSED_MINB) k_find_lambdas_fused(fl
     if (lane == 0 && warp_in) rec[0] = ovf ? kListOverflow : 1u;
     if (!act) return;
     const float inv_w = __fdividef(1.f, sw[i]);
-    lambda[i] = ps_lambda_from_sums(ro, denom, gxs, gys, gzs, inv_w, inv_ro0);
+    const float lam = ps_lambda_from_sums(ro, denom, gxs, gys, gzs, inv_w, inv_ro0);
+    lambda[i] = lam;
     num_neighbors[i] = woff >> 7;
+    // slab contexts: a particle of the last halo pack hands its lambda straight to the outgoing messages (what k_slab_pack_lambda would
+    // collect in a pass of its own over all sorted slots)
+    if (sinks.ranks && orig < n_owned) {
+        const uint2 r = __ldg(sinks.ranks + orig);
+        if (r.x < sinks.cap) sinks.left[r.x] = lam;
+        if (r.y < sinks.cap) sinks.right[r.y] = lam;
+    }
 }
 
 // ------------------------------------------------------------------ K7: delta p ------------------------------------------------------------------
@@ -996,7 +1004,8 @@ size_t ps_neighbor_record_elems(u64 capacity) { return 4 + (size_t)((capacity + 
 u32 ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos, const float *sw, const int *sphase, const u32 *index,
                            const u32 *cell_begin, const float *ros, u32 n, u32 n_owned, float ghost_xmin, float ghost_xmax, GridDesc g,
                            const StencilDesc &st, bool zero_nonfluid, u32 *nbr_list, u32 *nbr_rows, u32 list_rows, u64 capacity, bool slot_in_w,
-                           bool staged, int device, cudaStream_t s) {
+                           bool staged, int device, cudaStream_t s, LambdaSinks sinks, bool *sinks_written) {
+    if (sinks_written) *sinks_written = false;
     if (!n) return 0;
     const bool lists = nbr_list && nbr_rows && list_rows && n <= capacity;
     if (lists && staged && slot_in_w) {
@@ -1011,10 +1020,11 @@ u32 ps_launch_find_lambdas(float *lambda, u32 *num_neighbors, const float4 *spos
         const size_t dump = list_region_elems(capacity, list_rows);
         if (st.rad == 4)
             k_find_lambdas_fused<4><<<cdiv(n, kBlock), kBlock, fsm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned,
-                                                                         ghost_xmin, ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, list_rows, dump);
+                                                                         ghost_xmin, ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, list_rows, dump, sinks);
         else
             k_find_lambdas_fused<0><<<cdiv(n, kBlock), kBlock, fsm, s>>>(lambda, num_neighbors, spos, sw, sphase, index, cell_begin, ros, n, n_owned,
-                                                                         ghost_xmin, ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, list_rows, dump);
+                                                                         ghost_xmin, ghost_xmax, g, st, zero_nonfluid ? 1 : 0, nbr_list, nbr_rows, list_rows, dump, sinks);
+        if (sinks_written) *sinks_written = sinks.ranks != nullptr;
         return 1;
     }
     const size_t sm = fluid_smem_bytes(st.rad);
