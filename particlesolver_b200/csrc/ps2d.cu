@@ -61,11 +61,8 @@ __device__ __forceinline__ double2 spiky_grad(double rx, double ry, double x) {
 
 // (1)-(4): v += dt g (gas: ALPHA g) + dt f; f = 0; ep = p + dt v (fixed particles stay); tmass = height-scaled inverse
 // mass; simulation.cpp:139-161, particle.h:56-58,67-73
-__global__ void k2d_predict(double2 *__restrict__ v, double2 *__restrict__ ep, double2 *__restrict__ f, double *__restrict__ tmass,
-                            const double2 *__restrict__ p, const double *__restrict__ imass, const int *__restrict__ phase, u32 n, double dt, double gx,
-                            double gy) {
-    const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void d_predict(u32 i, double2 *v, double2 *ep, double2 *f, double *tmass, const double2 *p, const double *imass, const int *phase,
+                                          double dt, double gx, double gy) {
     if (phase[i] == PS2D_PHASE_GAS) { gx = gx * kAlpha; gy = gy * kAlpha; }
     double2 vi = v[i];
     const double2 fi = f[i];
@@ -78,6 +75,12 @@ __global__ void k2d_predict(double2 *__restrict__ v, double2 *__restrict__ ep, d
     ep[i] = im == 0. ? pi : make_double2(pi.x + dt * vi.x, pi.y + dt * vi.y);
     tmass[i] = im != 0. ? 1. / ((1. / im) * exp(-pi.y)) : 0.;
 }
+__global__ void k2d_predict(double2 *__restrict__ v, double2 *__restrict__ ep, double2 *__restrict__ f, double *__restrict__ tmass,
+                            const double2 *__restrict__ p, const double *__restrict__ imass, const int *__restrict__ phase, u32 n, double dt, double gx,
+                            double gy) {
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) d_predict(i, v, ep, f, tmass, p, imass, phase, dt, gx, gy);
+}
 
 // (6)-(8): the CONTACT list of a tick, stored per particle.  nb[i*kMaxC + r], r < cnt[i]: i's contact partners in
 // ascending index (bit 31: both SOLID -> RigidContactConstraint, else ContactConstraint); flags: walls violated by the
@@ -85,15 +88,11 @@ __global__ void k2d_predict(double2 *__restrict__ v, double2 *__restrict__ ep, d
 // reference's list is [pairs (i, j > i) by j, wall x, wall y] for i = 0, 1, ...; particle i's own sequence in that list
 // is therefore [nb ascending, wall x, wall y].  counts[i] = constraints on i in all groups (Constraint::updateCounts);
 // draws[i] = wall constraints of i that draw jitter (fluid / gas particles only, boundaryconstraint.cpp:19).
-__global__ void __launch_bounds__(kBlock) k2d_find_contacts(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ phase,
-                                                            const int *__restrict__ bod, const u32 *__restrict__ static_counts, u32 n, double x0, double x1,
-                                                            double y0, double y1, u32 *__restrict__ nb, u32 *__restrict__ cnt, u32 *__restrict__ flags,
-                                                            u32 *__restrict__ counts, u32 *__restrict__ draws, u32 *__restrict__ overflow, int any_solid) {
+__device__ __forceinline__ void d_find_contacts(u32 i, u32 lane, const double2 *ep, const double *imass, const int *phase, const int *bod,
+                                                const u32 *static_counts, u32 n, double x0, double x1, double y0, double y1, u32 *nb, u32 *cnt, u32 *flags,
+                                                u32 *counts, u32 *draws, u32 *overflow, int any_solid) {
     // one WARP per particle: lane l tests partners l, l + 32, ...; a ballot per 32 candidates keeps the partner list in
     // ascending index (the serial form, one thread walking all n candidates, was 65 % of a tick at n = 1452)
-    const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
-    const u32 lane = threadIdx.x & 31;
-    if (i >= n) return;  // warp-uniform
     const double2 e = ep[i];
     const double im = imass[i];
     const int ph = phase[i], bd = bod[i];
@@ -130,15 +129,24 @@ __global__ void __launch_bounds__(kBlock) k2d_find_contacts(const double2 *__res
     draws[i] = (ph == PS2D_PHASE_FLUID || ph == PS2D_PHASE_GAS) ? __popc(fl) : 0u;
 }
 
+__global__ void __launch_bounds__(kBlock) k2d_find_contacts(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ phase,
+                                                            const int *__restrict__ bod, const u32 *__restrict__ static_counts, u32 n, double x0, double x1,
+                                                            double y0, double y1, u32 *__restrict__ nb, u32 *__restrict__ cnt, u32 *__restrict__ flags,
+                                                            u32 *__restrict__ counts, u32 *__restrict__ draws, u32 *__restrict__ overflow, int any_solid) {
+    const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    if (i >= n) return;  // warp-uniform
+    d_find_contacts(i, threadIdx.x & 31, ep, imass, phase, bod, static_counts, n, x0, x1, y0, y1, nb, cnt, flags, counts, draws, overflow, any_solid);
+}
+
 // rank[i] = sum of counts before i (the position of i's first jitter draw in the rand() stream of an iteration);
 // total -> *num.  One CTA, sequential over chunks.
-__global__ void __launch_bounds__(1024) k2d_scan_counts(const u32 *__restrict__ counts, u32 *__restrict__ rank, u32 n, u32 *__restrict__ num) {
+__device__ void d_scan_counts(const u32 *counts, u32 *rank, u32 n, u32 *num) {  // one CTA (a multiple of 32 threads, at most 1024)
     __shared__ u32 sm[32];
     __shared__ u32 carry;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (u32 base = 0; base < n; base += 1024) {
+    for (u32 base = 0; base < n; base += blockDim.x) {
         const u32 i = base + threadIdx.x;
         const u32 c = i < n ? counts[i] : 0u;
         u32 incl = c;
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(1024) k2d_scan_counts(const u32 *__restrict__ 
         if (lane == 31) sm[wid] = incl;
         __syncthreads();
         u32 before = carry, tot = 0;
-        for (int w = 0; w < 32; w++) {
+        for (int w = 0; w < nw; w++) {
             if (w < wid) before += sm[w];
             tot += sm[w];
         }
@@ -161,18 +169,21 @@ __global__ void __launch_bounds__(1024) k2d_scan_counts(const u32 *__restrict__ 
     }
     if (threadIdx.x == 0) *num = carry;
 }
+__global__ void __launch_bounds__(1024) k2d_scan_counts(const u32 *__restrict__ counts, u32 *__restrict__ rank, u32 n, u32 *__restrict__ num) {
+    d_scan_counts(counts, rank, n, num);
+}
 
 // Level schedule of the CONTACT list (see the file header).  Entry (i, r) is the r-th constraint of particle i's
 // sequence; a pair constraint appears in both particles' sequences, q = its position in the partner's.  The rule
 //     lvl(i, r) = 1 + max(lvl(i, r - 1), lvl(j, q - 1))      (pair with j; walls: the first term only)
 // is monotone, so relaxing it from 0 in any order converges to its least fixpoint — the levels of the sequential list.
 // info[0] = number of levels, info[1] = number of constraints in the list.
-__global__ void __launch_bounds__(kSerialBlock) k2d_contact_levels(const u32 *__restrict__ nb, const u32 *__restrict__ cnt, const u32 *__restrict__ flags,
-                                                                   u32 n, unsigned char *__restrict__ nbq, u32 *__restrict__ lvl, u32 *__restrict__ info) {
+__device__ void d_contact_levels(const u32 *nb, const u32 *cnt, const u32 *flags, u32 n, unsigned char *nbq, u32 *lvl, u32 *info) {  // one CTA
     __shared__ u32 s_max, s_pairs, s_walls;
     if (threadIdx.x == 0) { s_max = 0; s_pairs = 0; s_walls = 0; }
+    __syncthreads();
     u32 pairs = 0, walls = 0;
-    for (u32 i = threadIdx.x; i < n; i += kSerialBlock) {
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
         const u32 c = cnt[i], len = c + __popc(flags[i]);
         for (u32 r = 0; r < c; r++) {
             const u32 j = nb[(size_t)i * kMaxC + r] & ~kRigidBit, cj = cnt[j];
@@ -189,7 +200,7 @@ __global__ void __launch_bounds__(kSerialBlock) k2d_contact_levels(const u32 *__
     __syncthreads();
     for (;;) {
         int changed = 0;
-        for (u32 i = threadIdx.x; i < n; i += kSerialBlock) {
+        for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
             const u32 c = cnt[i], len = c + __popc(flags[i]);
             u32 prev = 0;
             for (u32 r = 0; r < len; r++) {
@@ -206,13 +217,18 @@ __global__ void __launch_bounds__(kSerialBlock) k2d_contact_levels(const u32 *__
         if (!__syncthreads_or(changed)) break;
     }
     u32 m = 0;
-    for (u32 i = threadIdx.x; i < n; i += kSerialBlock) {
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
         const u32 len = cnt[i] + __popc(flags[i]);
         if (len) m = max(m, lvl[(size_t)i * kEntries + len - 1]);
     }
     atomicMax(&s_max, m);
     __syncthreads();
     if (threadIdx.x == 0) { info[0] = s_max; info[1] = s_pairs / 2 + s_walls; }
+}
+
+__global__ void __launch_bounds__(kSerialBlock) k2d_contact_levels(const u32 *__restrict__ nb, const u32 *__restrict__ cnt, const u32 *__restrict__ flags,
+                                                                   u32 n, unsigned char *__restrict__ nbq, u32 *__restrict__ lvl, u32 *__restrict__ info) {
+    d_contact_levels(nb, cnt, flags, n, nbq, lvl, info);
 }
 
 struct Particles2D {  // device views used by the projection kernels
@@ -354,19 +370,16 @@ __device__ void project_boundary(const Particles2D &P, u32 i, double value, bool
 // One solver iteration over the CONTACT list, level by level.  Thread t owns particles t, t + 1024, ...; cur[i] walks
 // particle i's sequence (levels strictly increase along it).  A pair constraint is projected by its lower-index owner
 // (it is at the same level in both sequences); the partner just steps over it.
-__global__ void __launch_bounds__(kSerialBlock) k2d_contact_project(Particles2D P, const u32 *__restrict__ nb, const u32 *__restrict__ cnt,
-                                                                    const u32 *__restrict__ flags, const u32 *__restrict__ lvl, const u32 *__restrict__ rank,
-                                                                    const u32 *__restrict__ info, u32 *__restrict__ cur, u32 n, const int *__restrict__ raw,
-                                                                    const u32 *__restrict__ window_base_ptr, u32 iteration, double x0, double x1, double y0, double y1, bool stabile) {
-    const u32 window_base = *window_base_ptr;  // a device word, so that the tick's launch sequence can be replayed as a graph
+__device__ void d_contact_project(const Particles2D &P, const u32 *nb, const u32 *cnt, const u32 *flags, const u32 *lvl, const u32 *rank, const u32 *info, u32 *cur,
+                                  u32 n, const int *raw, u32 window_base, u32 iteration, double x0, double x1, double y0, double y1, bool stabile) {
     // stabile: one pass over the STABILIZATION list = the rigid contacts and wall constraints of the CONTACT list, in its order
     // (simulation.cpp:190-192,204-223), so the same level schedule holds with the plain contacts stepped over.
     // info[-1] = jittered wall constraints of this tick (k2d_scan_counts): iteration t draws window[base + t * num + position]
     const u32 levels = info[0], draw_base = window_base + iteration * info[-1];
-    for (u32 i = threadIdx.x; i < n; i += kSerialBlock) cur[i] = 0;
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) cur[i] = 0;
     for (u32 l = 1; l <= levels; l++) {
         __syncthreads();
-        for (u32 i = threadIdx.x; i < n; i += kSerialBlock) {
+        for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
             const u32 c = cnt[i], fl = flags[i], len = c + __popc(fl), r = cur[i];
             if (r >= len || lvl[(size_t)i * kEntries + r] != l) continue;
             cur[i] = r + 1;
@@ -388,82 +401,127 @@ __global__ void __launch_bounds__(kSerialBlock) k2d_contact_project(Particles2D 
     }
 }
 
+__global__ void __launch_bounds__(kSerialBlock) k2d_contact_project(Particles2D P, const u32 *__restrict__ nb, const u32 *__restrict__ cnt,
+                                                                    const u32 *__restrict__ flags, const u32 *__restrict__ lvl, const u32 *__restrict__ rank,
+                                                                    const u32 *__restrict__ info, u32 *__restrict__ cur, u32 n, const int *__restrict__ raw,
+                                                                    const u32 *__restrict__ window_base_ptr, u32 iteration, double x0, double x1, double y0, double y1, bool stabile) {
+    // the draws' base is a device word, so that the tick's launch sequence can be replayed as a graph
+    d_contact_project(P, nb, cnt, flags, lvl, rank, info, cur, n, raw, *window_base_ptr, iteration, x0, x1, y0, y1, stabile);
+}
+
 // DistanceConstraint::project (distanceconstraint.cpp:20-40) for one run of consecutive distance constraints of the
 // STANDARD list, stored level by level (level_off[l] .. level_off[l + 1]); the schedule is built on the host when the
 // list changes (constraints are static).
+// x / d for d = 2^k is x * 2^-k: both are the correctly rounded value of the same real number, bit for bit (a double-precision
+// divide is a ~25-instruction dependent sequence on the GPU; the rope's links divide by w1 + w2 = 2 and by constraint counts of 1 or 2)
+__device__ __forceinline__ bool pow2_reciprocal(double d, double *inv) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    const unsigned ex = (unsigned)(b >> 52);  // sign 0 and a zero mantissa, or the test below fails
+    if ((b & 0x800fffffffffffffull) != 0ull || ex < 2u || ex > 2044u) return false;
+    *inv = __longlong_as_double((long long)((unsigned long long)(2046u - ex) << 52));
+    return true;
+}
+// Everything a distance constraint needs that does not depend on the positions, prepared once per tick by all threads (inverse
+// masses are constant, the constraint counts are fixed once the tick's contacts are known): the level loop is a dependent chain
+// on ONE warp, whose every instruction — not only the double-precision ones — costs issue latency.  A divisor is stored as its
+// reciprocal when it is a power of two (flag bit set), else as itself.
+struct __align__(16) DistSlot {  // 64 bytes
+    u32 i1, i2, flags, pad;      // flags: 1 live, 2 / 4 / 8: wsum / count 1 / count 2 stored as reciprocals
+    double rest, nw1, w2, wsum, c1, c2;  // nw1 = -w1
+};
+__device__ __forceinline__ DistSlot dist_make_slot(u32 i1, u32 i2, double rest, const double *imass, const u32 *counts) {
+    DistSlot r;
+    r.i1 = i1; r.i2 = i2; r.flags = 0u; r.pad = 0u; r.rest = rest;
+    const double w1 = imass[i1], w2 = imass[i2];
+    r.nw1 = -w1; r.w2 = w2;
+    r.wsum = w1 + w2; r.c1 = (double)counts[i1]; r.c2 = (double)counts[i2];
+    if (!(w1 == 0. && w2 == 0.)) r.flags |= 1u;
+    double inv;
+    if (pow2_reciprocal(r.wsum, &inv)) { r.wsum = inv; r.flags |= 2u; }
+    if (pow2_reciprocal(r.c1, &inv)) { r.c1 = inv; r.flags |= 4u; }
+    if (pow2_reciprocal(r.c2, &inv)) { r.c2 = inv; r.flags |= 8u; }
+    return r;
+}
+// DistanceConstraint::project (distanceconstraint.cpp:20-40)
+__device__ __forceinline__ void dist_project(double2 *ep, const DistSlot &r) {
+    if (!(r.flags & 1u)) return;
+    double2 e1 = ep[r.i1], e2 = ep[r.i2];
+    const double dx = e1.x - e2.x, dy = e1.y - e2.y;
+    const double dist = sqrt(dx * dx + dy * dy), mag = dist - r.rest;
+    if ((r.flags & 14u) == 14u) {  // the straight line: one sqrt and one divide
+        const double sd = (mag * r.wsum) / dist;
+        const double dpx = sd * dx, dpy = sd * dy;
+        e1.x += (r.nw1 * dpx) * r.c1; e1.y += (r.nw1 * dpy) * r.c1;
+        e2.x += (r.w2 * dpx) * r.c2;  e2.y += (r.w2 * dpy) * r.c2;
+    } else {
+        const double sd = ((r.flags & 2u) ? mag * r.wsum : mag / r.wsum) / dist;
+        const double dpx = sd * dx, dpy = sd * dy;
+        if (r.flags & 4u) { e1.x += (r.nw1 * dpx) * r.c1; e1.y += (r.nw1 * dpy) * r.c1; }
+        else { e1.x += (r.nw1 * dpx) / r.c1; e1.y += (r.nw1 * dpy) / r.c1; }
+        if (r.flags & 8u) { e2.x += (r.w2 * dpx) * r.c2; e2.y += (r.w2 * dpy) * r.c2; }
+        else { e2.x += (r.w2 * dpx) / r.c2; e2.y += (r.w2 * dpy) / r.c2; }
+    }
+    ep[r.i1] = e1; ep[r.i2] = e2;
+}
+// slots[k - rec_base] for the records k of a run (or of all runs), by all threads of the caller
+__device__ __forceinline__ void d_distance_prepare(DistSlot *slots, u32 first, u32 count, const double *imass, const u32 *counts, const u32 *i1s, const u32 *i2s,
+                                                   const double *rest, u32 tid, u32 nthreads) {
+    for (u32 k = tid; k < count; k += nthreads) slots[k] = dist_make_slot(i1s[first + k], i2s[first + k], rest[first + k], imass, counts);
+}
+// The levels of one run, level_off[l] .. level_off[l + 1] (absolute record numbers; slots[0] is record rec_base).
+// kWarp: the caller is one warp and the levels are at most 32 wide — a warp barrier per level instead of a CTA barrier.
+template <bool kWarp>
+__device__ __forceinline__ void d_distance_levels(double2 *ep, const DistSlot *slots, u32 rec_base, const u32 *level_off, u32 levels, u32 tid, u32 nthreads) {
+    if (!levels) return;
+    u32 b = level_off[0], e = level_off[1];
+    u32 e_next = levels > 1 ? level_off[2] : e;
+    for (u32 l = 0; l < levels; l++) {
+        const u32 e_after = l + 3 <= levels ? level_off[l + 3] : e_next;  // offsets two levels ahead: never waited for
+        for (u32 k = b + tid; k < e; k += nthreads) dist_project(ep, slots[k - rec_base]);
+        if (kWarp) __syncwarp(); else __syncthreads();
+        b = e; e = e_next; e_next = e_after;
+    }
+}
+// runs too long for shared memory: straight from global memory, slots made on the fly
 __global__ void __launch_bounds__(kSerialBlock) k2d_distance_run(double2 *__restrict__ ep, const double *__restrict__ imass, const u32 *__restrict__ counts,
                                                                  const u32 *__restrict__ i1s, const u32 *__restrict__ i2s, const double *__restrict__ rest,
                                                                  const u32 *__restrict__ level_off, u32 levels) {
     for (u32 l = 0; l < levels; l++) {
         if (l) __syncthreads();
         const u32 b = level_off[l], e = level_off[l + 1];
-        for (u32 k = b + threadIdx.x; k < e; k += kSerialBlock) {
-            const u32 i1 = i1s[k], i2 = i2s[k];
-            const double w1 = imass[i1], w2 = imass[i2];
-            if (w1 == 0. && w2 == 0.) continue;
-            double2 e1 = ep[i1], e2 = ep[i2];
-            const double dx = e1.x - e2.x, dy = e1.y - e2.y;
-            const double wsum = w1 + w2, dist = sqrt(dx * dx + dy * dy), mag = dist - rest[k];
-            const double sd = (mag / wsum) / dist;
-            const double dpx = sd * dx, dpy = sd * dy;
-            const double c1 = (double)counts[i1], c2 = (double)counts[i2];
-            e1.x += ((-w1) * dpx) / c1; e1.y += ((-w1) * dpy) / c1;
-            e2.x += (w2 * dpx) / c2;    e2.y += (w2 * dpy) / c2;
-            ep[i1] = e1; ep[i2] = e2;
-        }
+        for (u32 k = b + threadIdx.x; k < e; k += kSerialBlock) dist_project(ep, dist_make_slot(i1s[k], i2s[k], rest[k], imass, counts));
     }
 }
 
-// The same, with everything the levels touch staged in shared memory: predicted positions, inverse masses and counts of all n
-// particles and the run's constraint records.  A rope of L links is L levels of one constraint each — a dependent chain whose every
-// step used to wait for two global round trips (record, then positions: 1.3 us per level on B200, 65 % of a tick of the gas-rope
-// scene); from shared memory a level costs the double-precision divide / sqrt chain and a barrier over `blockDim` threads, sized
-// to the widest level.  Same expressions in the same order per constraint: bit-identical to k2d_distance_run.
-__global__ void __launch_bounds__(kSerialBlock) k2d_distance_run_staged(double2 *__restrict__ ep, const double *__restrict__ imass, const u32 *__restrict__ counts,
+// The same out of shared memory: the predicted positions of all n particles and the run's prepared slots.  A rope of L links is L
+// levels of one constraint each — a dependent chain whose every step used to wait for two global round trips (record, then
+// positions: 1.3 us per level on B200, 65 % of a tick of the gas-rope scene); from shared memory, with the position-independent
+// part of every constraint prepared up front, a level costs two 16-byte loads, the sqrt / divide chain and a warp barrier.
+// Same expressions in the same order per constraint: bit-identical to k2d_distance_run.
+template <int kThreads>  // 32: the levels are at most a warp wide (ropes), one warp and warp barriers; else a CTA of up to kSerialBlock threads
+__global__ void __launch_bounds__(kThreads) k2d_distance_run_staged(double2 *__restrict__ ep, const double *__restrict__ imass, const u32 *__restrict__ counts,
                                                                         const u32 *__restrict__ i1s, const u32 *__restrict__ i2s, const double *__restrict__ rest,
                                                                         const u32 *__restrict__ level_off, u32 levels, u32 n, u32 first, u32 count) {
-    extern __shared__ double2 stage2d[];
-    double2 *s_ep = stage2d;                                        // n
-    double *s_im = reinterpret_cast<double *>(s_ep + n);            // n
-    double *s_rest = s_im + n;                                      // count
-    u32 *s_cnt = reinterpret_cast<u32 *>(s_rest + count);           // n
-    u32 *s_i1 = s_cnt + n, *s_i2 = s_i1 + count;                    // count each
-    for (u32 i = threadIdx.x; i < n; i += blockDim.x) { s_ep[i] = ep[i]; s_im[i] = imass[i]; s_cnt[i] = counts[i]; }
-    for (u32 k = threadIdx.x; k < count; k += blockDim.x) { s_i1[k] = i1s[first + k]; s_i2[k] = i2s[first + k]; s_rest[k] = rest[first + k]; }
+    extern __shared__ __align__(16) unsigned char stage2d[];
+    DistSlot *slots = reinterpret_cast<DistSlot *>(stage2d);                 // count
+    double2 *s_ep = reinterpret_cast<double2 *>(slots + count);              // n
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) s_ep[i] = ep[i];
+    d_distance_prepare(slots, first, count, imass, counts, i1s, i2s, rest, threadIdx.x, blockDim.x);
     __syncthreads();
-    for (u32 l = 0; l < levels; l++) {
-        if (l) __syncthreads();
-        const u32 b = level_off[l] - first, e = level_off[l + 1] - first;
-        for (u32 k = b + threadIdx.x; k < e; k += blockDim.x) {
-            const u32 i1 = s_i1[k], i2 = s_i2[k];
-            const double w1 = s_im[i1], w2 = s_im[i2];
-            if (w1 == 0. && w2 == 0.) continue;
-            double2 e1 = s_ep[i1], e2 = s_ep[i2];
-            const double dx = e1.x - e2.x, dy = e1.y - e2.y;
-            const double wsum = w1 + w2, dist = sqrt(dx * dx + dy * dy), mag = dist - s_rest[k];
-            const double sd = (mag / wsum) / dist;
-            const double dpx = sd * dx, dpy = sd * dy;
-            const double c1 = (double)s_cnt[i1], c2 = (double)s_cnt[i2];
-            e1.x += ((-w1) * dpx) / c1; e1.y += ((-w1) * dpy) / c1;
-            e2.x += (w2 * dpx) / c2;    e2.y += (w2 * dpy) / c2;
-            s_ep[i1] = e1; s_ep[i2] = e2;
-        }
-    }
+    if (kThreads == 32) d_distance_levels<true>(s_ep, slots, first, level_off, levels, threadIdx.x, 32u);
+    else d_distance_levels<false>(s_ep, slots, first, level_off, levels, threadIdx.x, blockDim.x);
     __syncthreads();
     for (u32 i = threadIdx.x; i < n; i += blockDim.x) ep[i] = s_ep[i];
 }
-static inline size_t distance_stage_bytes(u32 n, u32 count) { return (size_t)n * (16 + 8 + 4) + (size_t)count * (8 + 4 + 4) + 16; }
+static inline size_t distance_stage_bytes(u32 n, u32 count) { return (size_t)n * 16 + (size_t)count * sizeof(DistSlot) + 16; }
 constexpr size_t kDistanceStageMax = 200 * 1024;
 
 // TotalShapeConstraint::project for every body (totalshapeconstraint.cpp:14-24): Body::updateCOM (centre of mass and the
 // mass-weighted mean angle, with the reference's sequential unwrapping of consecutive angles, solver/particle.cpp:15-57),
 // then every member moves to its rotated rest position.  Bodies own disjoint particles, so they run in parallel; one
 // thread per body keeps the reference's summation order (bodies are a dozen particles).
-__global__ void __launch_bounds__(kBlock) k2d_shape(double2 *__restrict__ ep, const double *__restrict__ imass, const double2 *__restrict__ rs,
-                                                    const u32 *__restrict__ b_first, const u32 *__restrict__ b_count, const double *__restrict__ b_imass,
-                                                    const double *__restrict__ b_stiff, double2 *__restrict__ b_center, double *__restrict__ b_angle, u32 nb) {
-    const u32 b = blockIdx.x * kBlock + threadIdx.x;
-    if (b >= nb) return;
+__device__ void d_shape(u32 b, double2 *ep, const double *imass, const double2 *rs, const u32 *b_first, const u32 *b_count, const double *b_imass, const double *b_stiff,
+                        double2 *b_center, double *b_angle) {
     const u32 first = b_first[b], count = b_count[b];
     const double bim = b_imass[b];
     double tx = 0., ty = 0.;
@@ -500,6 +558,13 @@ __global__ void __launch_bounds__(kBlock) k2d_shape(double2 *__restrict__ ep, co
     }
 }
 
+__global__ void __launch_bounds__(kBlock) k2d_shape(double2 *__restrict__ ep, const double *__restrict__ imass, const double2 *__restrict__ rs,
+                                                    const u32 *__restrict__ b_first, const u32 *__restrict__ b_count, const double *__restrict__ b_imass,
+                                                    const double *__restrict__ b_stiff, double2 *__restrict__ b_center, double *__restrict__ b_angle, u32 nb) {
+    const u32 b = blockIdx.x * kBlock + threadIdx.x;
+    if (b < nb) d_shape(b, ep, imass, rs, b_first, b_count, b_imass, b_stiff, b_center, b_angle);
+}
+
 // TotalFluidConstraint / GasConstraint::project, first loop (totalfluidconstraint.cpp:45-93, gasconstraint.cpp:33-85): lambda
 // of every particle of STANDARD constraint `op`, 0 for everybody else (the constraint's lambdas is a QHash cleared per
 // call: any other particle reads 0, :106).  SOLID neighbours count S_SOLID-fold, immovable ones not at all.
@@ -512,12 +577,8 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ phase,
-                                                           const int *__restrict__ group, u32 n, int op, double p0, FluidConsts K, double *__restrict__ lambda,
-                                                           u32 *__restrict__ nbcount, const double2 *__restrict__ v, double2 *__restrict__ f) {
-    const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
-    const u32 lane = threadIdx.x & 31;
-    if (i >= n) return;  // warp-uniform
+__device__ void d_fluid_lambda(u32 i, u32 lane, const double2 *ep, const double *imass, const int *phase, const int *group, u32 n, int op, double p0,
+                               const FluidConsts &K, double *lambda, u32 *nbcount, const double2 *v, double2 *f) {
     if (group[i] != op) { if (lane == 0) lambda[i] = 0.; return; }
     const double2 pi = ep[i];
     double rho = 0., denom = 0., ox = 0., oy = 0.;
@@ -563,16 +624,19 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__rest
     nbcount[i] = nbc;
 }
 
+__global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ phase,
+                                                           const int *__restrict__ group, u32 n, int op, double p0, FluidConsts K, double *__restrict__ lambda,
+                                                           u32 *__restrict__ nbcount, const double2 *__restrict__ v, double2 *__restrict__ f) {
+    const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    if (i >= n) return;  // warp-uniform
+    d_fluid_lambda(i, threadIdx.x & 31, ep, imass, phase, group, n, op, p0, K, lambda, nbcount, v, f);
+}
+
 // second loop (:95-111): delta_i = sum_j (lambda_i + lambda_j + s_corr) spikyGrad / p0, divided by (#neighbours incl. self +
 // constraint count) (:113-115).  Written to `delta`, applied by k2d_fluid_apply: all deltas of a constraint come from the
 // same ep.  Gas: the pseudo-vorticity force of gasconstraint.cpp:99-107 goes to the force accumulator.  One warp per particle.
-__global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ group, u32 n,
-                                                          int op, double p0, FluidConsts K, const double *__restrict__ lambda, const u32 *__restrict__ nbcount,
-                                                          const u32 *__restrict__ counts, double2 *__restrict__ delta, const double2 *__restrict__ v,
-                                                          double2 *__restrict__ f) {
-    const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
-    const u32 lane = threadIdx.x & 31;
-    if (i >= n || group[i] != op) return;  // warp-uniform
+__device__ void d_fluid_delta(u32 i, u32 lane, const double2 *ep, const double *imass, u32 n, double p0, const FluidConsts &K, const double *lambda,
+                              const u32 *nbcount, const u32 *counts, double2 *delta, const double2 *v, double2 *f) {
     const double2 pi = ep[i];
     const double li = lambda[i];
     const double base6 = poly6(K.dq_p * K.dq_p * kH * kH);
@@ -611,24 +675,37 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restr
         f[i] = fi;
     }
 }
-__global__ void k2d_fluid_apply(double2 *__restrict__ ep, const double2 *__restrict__ delta, const int *__restrict__ group, u32 n, int op) {
-    const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n || group[i] != op) return;
+__global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ group, u32 n,
+                                                          int op, double p0, FluidConsts K, const double *__restrict__ lambda, const u32 *__restrict__ nbcount,
+                                                          const u32 *__restrict__ counts, double2 *__restrict__ delta, const double2 *__restrict__ v,
+                                                          double2 *__restrict__ f) {
+    const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+    if (i >= n || group[i] != op) return;  // warp-uniform
+    d_fluid_delta(i, threadIdx.x & 31, ep, imass, n, p0, K, lambda, nbcount, counts, delta, v, f);
+}
+__device__ __forceinline__ void d_fluid_apply(u32 i, double2 *ep, const double2 *delta) {
     double2 e = ep[i];
     const double2 d = delta[i];
     e.x += d.x; e.y += d.y;
     ep[i] = e;
 }
+__global__ void k2d_fluid_apply(double2 *__restrict__ ep, const double2 *__restrict__ delta, const int *__restrict__ group, u32 n, int op) {
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n || group[i] != op) return;
+    d_fluid_apply(i, ep, delta);
+}
 
 // (23)-(27): v = (ep - p) / dt; particles that moved less than EPSILON sleep (particle.h:60-65)
-__global__ void k2d_finish(double2 *__restrict__ p, double2 *__restrict__ v, const double2 *__restrict__ ep, u32 n, double dt) {
-    const u32 i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ void d_finish(u32 i, double2 *p, double2 *v, const double2 *ep, double dt) {
     const double2 pi = p[i], e = ep[i];
     const double dx = e.x - pi.x, dy = e.y - pi.y;
     if (sqrt(dx * dx + dy * dy) < kEps) { v[i] = make_double2(0., 0.); return; }
     v[i] = make_double2(dx / dt, dy / dt);
     p[i] = e;
+}
+__global__ void k2d_finish(double2 *__restrict__ p, double2 *__restrict__ v, const double2 *__restrict__ ep, u32 n, double dt) {
+    const u32 i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) d_finish(i, p, v, ep, dt);
 }
 
 // Simulation::mousePressed (simulation.cpp:1305-1314): every particle gets a velocity impulse of 7 towards the point
@@ -641,6 +718,131 @@ __global__ void k2d_impulse(double2 *__restrict__ v, const double2 *__restrict__
     double2 vi = v[i];
     vi.x += 7. * (dx * inv); vi.y += 7. * (dy * inv);
     v[i] = vi;
+}
+
+enum StdKind { STD_FLUID, STD_GAS, STD_DISTANCE };
+
+// ---- the whole tick as ONE kernel, for scenes of a few dozen particles ------------------------------------------------
+// A tick of such a scene is 11-29 dependent launches whose kernels run for a microsecond or two each: even replayed as a graph, the
+// gaps between dependent nodes (2-3 us each) are most of the tick.  k2d_tick_fused runs the same device functions in the same order
+// inside one CTA of 512 threads, with a CTA barrier where the launch boundaries were, the predicted positions and the contact
+// cursors in shared memory for the whole tick, and the STANDARD list as a device-side op table.  Same functions, same arithmetic:
+// bit-identical to the launch sequence (tests/test_gpu_2d_fused.py).  It stops paying where the all-pairs loops of the fluid / contact
+// search want more than one SM: above kFusedTickMaxN particles the launch sequence (148 SMs) is used.
+struct FusedOp {  // one entry of the STANDARD list, distance constraints as whole runs
+    u32 kind;      // STD_FLUID / STD_GAS / STD_DISTANCE
+    u32 open;      // gas: open boundary
+    u32 keep;      // fluid with an emitter: lambda of the last iteration is kept for the emitter's host logic
+    u32 index;     // position in the STANDARD list (= the value of group[] of its members)
+    double p0;
+    u32 level_first, levels, width, pad;  // distance run
+};
+struct FusedTick {
+    double2 *v, *ep, *f, *p, *delta;
+    double *tmass, *lambda, *lambda_keep;
+    const double *imass, *sfric, *kfric, *sdf_dist;
+    const double2 *sdf_grad, *rs;
+    const int *phase, *bod, *group, *raw;
+    const u32 *static_counts;
+    u32 *nb, *cnt, *flags, *counts, *draws, *rank, *lvl, *nbcount, *scalars, *scalars_out;
+    unsigned char *nbq;
+    const u32 *b_first, *b_count;
+    const double *b_imass, *b_stiff;
+    double2 *b_center;
+    double *b_angle;
+    const u32 *dc_i1, *dc_i2, *dc_level_off;
+    const double *dc_rest;
+    const FusedOp *ops;
+    u32 n, nops, nbodies, ndist, window_base, stabilization_iterations, solver_iterations;
+    int any_solid;
+    unsigned long long *prof;  // PS2D_FUSED_PROFILE: cycles per phase, accumulated over the ticks (thread 0's clock)
+    double dt, gx, gy, x0, x1, y0, y1;
+};
+// out of line: the chains' registers are then allocated for the chain alone, not for the whole tick
+__device__ __noinline__ void fused_distance_warp(double2 *ep, const DistSlot *slots, const u32 *level_off, u32 levels, u32 lane) {
+    d_distance_levels<true>(ep, slots, 0u, level_off, levels, lane, 32u);
+}
+__device__ __noinline__ void fused_distance_cta(double2 *ep, const DistSlot *slots, const u32 *level_off, u32 levels) {
+    d_distance_levels<false>(ep, slots, 0u, level_off, levels, threadIdx.x, blockDim.x);
+}
+constexpr u32 kFusedTickMaxN = 160;   // measured: profiles/r2zz_2d_fused_tick.txt
+constexpr u32 kFusedBlock = 512;      // registers: 128 per thread, the serial chains of a tick must not spill
+constexpr u32 kFusedTickCapN = 2048;
+constexpr size_t kFusedStageMax = 160 * 1024;  // shared memory of the fused tick: 64 B per distance constraint + 20 B per particle  // what the kernel's shared memory is sized for at most (PS2D_FUSED_MAX_N for measurements)
+
+__global__ void __launch_bounds__(kFusedBlock, 1) k2d_tick_fused(const FusedTick A) {
+    extern __shared__ __align__(16) unsigned char fused_stage[];
+    DistSlot *s_slots = reinterpret_cast<DistSlot *>(fused_stage);           // ndist: every distance constraint of the STANDARD list
+    double2 *s_ep = reinterpret_cast<double2 *>(s_slots + A.ndist);          // n
+    u32 *s_cur = reinterpret_cast<u32 *>(s_ep + A.n);                        // n
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = kFusedBlock / 32, n = A.n;
+    long long t_mark = A.prof ? clock64() : 0;
+#define PS2D_PHASE(k) do { if (A.prof && tid == 0) { const long long t_ = clock64(); A.prof[k] += (unsigned long long)(t_ - t_mark); t_mark = t_; } } while (0)
+    for (u32 i = tid; i < n; i += kFusedBlock) d_predict(i, A.v, s_ep, A.f, A.tmass, A.p, A.imass, A.phase, A.dt, A.gx, A.gy);
+    __syncthreads();
+    for (u32 i = warp; i < n; i += nwarps)
+        d_find_contacts(i, lane, s_ep, A.imass, A.phase, A.bod, A.static_counts, n, A.x0, A.x1, A.y0, A.y1, A.nb, A.cnt, A.flags, A.counts, A.draws, A.scalars + 3,
+                        A.any_solid);
+    __syncthreads();
+    d_scan_counts(A.draws, A.rank, n, A.scalars);
+    __syncthreads();
+    d_contact_levels(A.nb, A.cnt, A.flags, n, A.nbq, A.lvl, A.scalars + 1);
+    d_distance_prepare(s_slots, 0u, A.ndist, A.imass, A.counts, A.dc_i1, A.dc_i2, A.dc_rest, tid, kFusedBlock);  // counts are final since the contact search
+    __syncthreads();
+    PS2D_PHASE(0);
+    const Particles2D V{s_ep, A.p, A.tmass, A.sfric, A.kfric, A.phase, A.bod, A.counts, A.sdf_grad, A.sdf_dist, A.b_angle};
+    for (u32 st = 0; st < A.stabilization_iterations; st++) {
+        d_contact_project(V, A.nb, A.cnt, A.flags, A.lvl, A.rank, A.scalars + 1, s_cur, n, A.raw, A.window_base, st, A.x0, A.x1, A.y0, A.y1, true);
+        __syncthreads();
+    }
+    for (u32 it = 0; it < A.solver_iterations; it++) {
+        d_contact_project(V, A.nb, A.cnt, A.flags, A.lvl, A.rank, A.scalars + 1, s_cur, n, A.raw, A.window_base, A.stabilization_iterations + it, A.x0, A.x1, A.y0,
+                          A.y1, false);
+        __syncthreads();
+        PS2D_PHASE(1);
+        for (u32 o = 0; o < A.nops; o++) {
+            const FusedOp op = A.ops[o];
+            if (op.kind == STD_DISTANCE) {
+                const u32 *lo = A.dc_level_off + op.level_first;
+                if (op.width <= 32u) {
+                    if (warp == 0) fused_distance_warp(s_ep, s_slots, lo, op.levels, lane);
+                } else {
+                    fused_distance_cta(s_ep, s_slots, lo, op.levels);
+                }
+                __syncthreads();
+                PS2D_PHASE(2);
+                continue;
+            }
+            const FluidConsts K = op.kind == STD_GAS ? FluidConsts{.2, .25, .5, 1, (int)op.open} : FluidConsts{.1, .2, 0., 0, 0};
+            for (u32 i = warp; i < n; i += nwarps) d_fluid_lambda(i, lane, s_ep, A.imass, A.phase, A.group, n, (int)op.index, op.p0, K, A.lambda, A.nbcount, A.v, A.f);
+            __syncthreads();
+            PS2D_PHASE(3);
+            if (op.keep && it + 1 == A.solver_iterations)
+                for (u32 i = tid; i < n; i += kFusedBlock) A.lambda_keep[i] = A.lambda[i];
+            for (u32 i = warp; i < n; i += nwarps)
+                if (A.group[i] == (int)op.index) d_fluid_delta(i, lane, s_ep, A.imass, n, op.p0, K, A.lambda, A.nbcount, A.counts, A.delta, A.v, A.f);
+            __syncthreads();
+            for (u32 i = tid; i < n; i += kFusedBlock)
+                if (A.group[i] == (int)op.index) d_fluid_apply(i, s_ep, A.delta);
+            __syncthreads();
+            PS2D_PHASE(4);
+        }
+        if (A.nbodies) {
+            for (u32 b = tid; b < A.nbodies; b += kFusedBlock) d_shape(b, s_ep, A.imass, A.rs, A.b_first, A.b_count, A.b_imass, A.b_stiff, A.b_center, A.b_angle);
+            __syncthreads();
+            PS2D_PHASE(5);
+        }
+    }
+    for (u32 i = tid; i < n; i += kFusedBlock) {
+        A.ep[i] = s_ep[i];
+        d_finish(i, A.p, A.v, s_ep, A.dt);
+    }
+    if (tid == 0) {  // the tick's four scalars, straight into the host's (mapped, pinned) words
+        for (int k = 0; k < 4; k++) A.scalars_out[k] = A.scalars[k];
+        __threadfence_system();
+    }
+    PS2D_PHASE(6);
+#undef PS2D_PHASE
 }
 
 // glibc rand() = random(), TYPE_3: r[i] = r[i-31] + r[i-3], output r[i] >> 1 (after 310 discarded words)
@@ -670,7 +872,6 @@ struct GlibcRand {
     }
 };
 
-enum StdKind { STD_FLUID, STD_GAS, STD_DISTANCE };
 struct StdOp {  // one entry of m_globalConstraints[STANDARD]
     StdKind kind;
     double p0 = 0.;  // fluid / gas rest density
@@ -716,6 +917,14 @@ struct Ps2dCtx {
     double *dc_rest = nullptr;
     size_t dc_cap = 0, dc_level_cap = 0;
     std::vector<DistanceRun> runs;
+    FusedOp *fused_ops = nullptr;      // the STANDARD list for k2d_tick_fused (rebuild_standard)
+    size_t fused_ops_cap = 0;
+    u32 fused_nops = 0;
+    u32 dc_total = 0;                  // distance constraints in the STANDARD list
+    u32 *scalars_out = nullptr;        // scalars_host as the device sees it (mapped pinned memory), or null
+    bool last_tick_fused = false;
+    unsigned long long *fused_prof = nullptr;  // PS2D_FUSED_PROFILE=1: per-phase cycles of k2d_tick_fused, printed by ps2d_destroy
+    uint64_t fused_ticks = 0;
     bool standard_dirty = true;
     std::vector<StdOp> standard;
     std::vector<u32> h_static_counts;
@@ -785,6 +994,8 @@ extern "C" int ps2d_create(int device, const Ps2dParams *params, uint64_t max_pa
          dev_alloc(&c->nbcount, n) && dev_alloc(&c->nb, n * kMaxC) && dev_alloc(&c->cnt, n) && dev_alloc(&c->lvl, n * kEntries) && dev_alloc(&c->cur, n) &&
          dev_alloc(&c->nbq, n * kMaxC) && dev_alloc(&c->scalars, 8) && cudaMallocHost((void **)&c->scalars_host, 32) == cudaSuccess;
     if (ok) c->window_base_dev = c->scalars + 4;
+    if (ok && getenv("PS2D_FUSED_PROFILE")) ok = dev_alloc(&c->fused_prof, 8) && cudaMemset(c->fused_prof, 0, 64) == cudaSuccess;
+    if (ok && cudaHostGetDevicePointer((void **)&c->scalars_out, c->scalars_host, 0) != cudaSuccess) { c->scalars_out = nullptr; cudaGetLastError(); }
     if (ok) ok = cudaMemsetAsync(c->f, 0, n * 16, c->stream) == cudaSuccess && cudaMemsetAsync(c->lambda, 0, n * 8, c->stream) == cudaSuccess &&
                  cudaMemsetAsync(c->scalars, 0, 16, c->stream) == cudaSuccess && cudaStreamSynchronize(c->stream) == cudaSuccess;
     if (!ok) {
@@ -800,9 +1011,17 @@ extern "C" int ps2d_destroy(Ps2dCtx *c) {
     if (!c) return PS_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->fused_prof && c->fused_ticks) {
+        unsigned long long h[8] = {};
+        cudaMemcpy(h, c->fused_prof, sizeof h, cudaMemcpyDeviceToHost);
+        const double t = (double)c->fused_ticks;
+        fprintf(stderr, "ps2d fused tick, cycles per tick over %.0f ticks: set-up %.0f, contacts %.0f, distance runs %.0f, fluid lambda %.0f, fluid delta+apply %.0f, shape %.0f, finish %.0f\n",
+                t, h[0] / t, h[1] / t, h[2] / t, h[3] / t, h[4] / t, h[5] / t, h[6] / t);
+        cudaFree(c->fused_prof);
+    }
     void *ptrs[] = {c->p, c->v, c->ep, c->f, c->delta, c->rs, c->sdf_grad, c->imass, c->tmass, c->sfric, c->kfric, c->lambda, c->sdf_dist, c->phase, c->bod,
                     c->group, c->raw, c->static_counts, c->flags, c->counts, c->draws, c->rank, c->nbcount, c->nb, c->cnt, c->lvl, c->cur, c->nbq, c->scalars,
-                    c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center, c->dc_i1, c->dc_i2, c->dc_level_off, c->dc_rest, c->lambda_keep};
+                    c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center, c->dc_i1, c->dc_i2, c->dc_level_off, c->dc_rest, c->lambda_keep, c->fused_ops};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (c->scalars_host) cudaFreeHost(c->scalars_host);
     if (c->tick_graph) cudaGraphExecDestroy(c->tick_graph);
@@ -1135,6 +1354,34 @@ static int rebuild_standard(Ps2dCtx *c) {
     CU2(upload(c, c->dc_i2, i2.data(), i2.size()));
     CU2(upload(c, c->dc_rest, rest.data(), rest.size()));
     CU2(upload(c, c->dc_level_off, level_off.data(), level_off.size()));
+    c->dc_total = (u32)i1.size();
+    {   // the list as k2d_tick_fused walks it: fluid / gas constraints one by one, distance constraints run by run
+        std::vector<FusedOp> ops;
+        size_t run = 0;
+        for (size_t q = 0; q < m;) {
+            const StdOp &o = c->standard[q];
+            FusedOp f{};
+            f.kind = (u32)o.kind; f.index = (u32)q;
+            if (o.kind == STD_DISTANCE) {
+                const DistanceRun &R = c->runs[run++];
+                f.level_first = R.dev_level_first; f.levels = R.levels; f.width = R.width;
+                q = R.end;
+            } else {
+                f.open = (u32)o.open; f.p0 = o.p0;
+                for (const FluidEmitterRec &fe : c->fluid_emitters) if (fe.standard_index == q) f.keep = 1;
+                q++;
+            }
+            ops.push_back(f);
+        }
+        if (ops.size() > c->fused_ops_cap) {
+            if (c->fused_ops) cudaFree(c->fused_ops);
+            c->fused_ops = nullptr;
+            c->fused_ops_cap = ops.size() * 2;
+            if (!dev_alloc(&c->fused_ops, c->fused_ops_cap)) { ps_set_error("ps2d: op table allocation failed"); return PS_ERR_CUDA; }
+        }
+        CU2(upload(c, c->fused_ops, ops.data(), ops.size()));
+        c->fused_nops = (u32)ops.size();
+    }
     c->standard_dirty = false;
     c->standard_version++;
     return PS_OK;
@@ -1215,6 +1462,7 @@ extern "C" int ps2d_create_fluid_emitter(Ps2dCtx *c, const double *posn2, double
         CU2(cudaMemset(c->lambda_keep, 0, c->cap * 8));
     }
     c->fluid_emitters.push_back(FluidEmitterRec{posn2[0], posn2[1], rate, timer, total_timer, standard_index});
+    c->standard_dirty = true;  // the op table of the fused tick marks the constraints whose lambda an emitter reads
     return PS_OK;
 }
 extern "C" int ps2d_set_particle_timers(Ps2dCtx *c, const double *t) {
@@ -1261,8 +1509,12 @@ static u32 issue_tick(Ps2dCtx *c, double dt) {
                 const size_t stage = distance_stage_bytes(n, count);
                 if (stage <= kDistanceStageMax) {  // the reference's scenes: a few hundred particles
                     const u32 block = std::min<u32>(kSerialBlock, std::max<u32>(32u, (R.width + 31u) & ~31u));
-                    k2d_distance_run_staged<<<1, block, stage, s>>>(c->ep, c->imass, c->counts, c->dc_i1, c->dc_i2, c->dc_rest, c->dc_level_off + R.dev_level_first,
-                                                                    R.levels, n, R.dev_first, count);
+                    if (block == 32)
+                        k2d_distance_run_staged<32><<<1, 32, stage, s>>>(c->ep, c->imass, c->counts, c->dc_i1, c->dc_i2, c->dc_rest, c->dc_level_off + R.dev_level_first,
+                                                                         R.levels, n, R.dev_first, count);
+                    else
+                        k2d_distance_run_staged<kSerialBlock><<<1, block, stage, s>>>(c->ep, c->imass, c->counts, c->dc_i1, c->dc_i2, c->dc_rest,
+                                                                                      c->dc_level_off + R.dev_level_first, R.levels, n, R.dev_first, count);
                 } else {
                     k2d_distance_run<<<1, kSerialBlock, 0, s>>>(c->ep, c->imass, c->counts, c->dc_i1, c->dc_i2, c->dc_rest, c->dc_level_off + R.dev_level_first, R.levels);
                 }
@@ -1328,17 +1580,51 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
         c->win_len = want;
     }
     // draws of this tick start at window[window_base]; the kernels read it from a device word
+    // scenes of a few dozen particles: the whole tick as one kernel (k2d_tick_fused); PS2D_FUSED_MAX_N moves the threshold (0: never)
+    static const u32 fused_max_n = [] { const char *e = getenv("PS2D_FUSED_MAX_N"); return e ? std::min<u32>((u32)strtoul(e, nullptr, 10), kFusedTickCapN) : kFusedTickMaxN; }();
+    const size_t fused_stage = (size_t)c->dc_total * sizeof(DistSlot) + (size_t)n * (sizeof(double2) + sizeof(u32));
+    c->last_tick_fused = n <= fused_max_n && c->scalars_out != nullptr && fused_stage <= kFusedStageMax;
     c->scalars_host[4] = (u32)(c->rng.calls - c->win_pos);
-    CU2(cudaMemcpyAsync(c->window_base_dev, c->scalars_host + 4, 4, cudaMemcpyHostToDevice, s));
+    if (!c->last_tick_fused) CU2(cudaMemcpyAsync(c->window_base_dev, c->scalars_host + 4, 4, cudaMemcpyHostToDevice, s));  // the fused kernel takes it as an argument
     static const bool no_graph = getenv("PS_NO_GRAPH") != nullptr;
     {   // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute: once for each device this process drives
         static bool opted[64] = {};
         if (c->device >= 0 && c->device < 64 && !opted[c->device]) {
-            CU2(cudaFuncSetAttribute(k2d_distance_run_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDistanceStageMax));
+            CU2(cudaFuncSetAttribute(k2d_distance_run_staged<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDistanceStageMax));
+            CU2(cudaFuncSetAttribute(k2d_distance_run_staged<kSerialBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDistanceStageMax));
             opted[c->device] = true;
         }
     }
-    if (no_graph) {
+    if (c->last_tick_fused) {
+        static bool opted_fused[64] = {};
+        const size_t stage = fused_stage;
+        if (c->device >= 0 && c->device < 64 && !opted_fused[c->device]) {
+            CU2(cudaFuncSetAttribute(k2d_tick_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedStageMax));
+            opted_fused[c->device] = true;
+        }
+        FusedTick A{};
+        A.v = c->v; A.ep = c->ep; A.f = c->f; A.p = c->p; A.delta = c->delta;
+        A.tmass = c->tmass; A.lambda = c->lambda; A.lambda_keep = c->lambda_keep;
+        A.imass = c->imass; A.sfric = c->sfric; A.kfric = c->kfric; A.sdf_dist = c->sdf_dist;
+        A.sdf_grad = c->sdf_grad; A.rs = c->rs;
+        A.phase = c->phase; A.bod = c->bod; A.group = c->group; A.raw = c->raw;
+        A.static_counts = c->static_counts;
+        A.nb = c->nb; A.cnt = c->cnt; A.flags = c->flags; A.counts = c->counts; A.draws = c->draws; A.rank = c->rank; A.lvl = c->lvl; A.nbcount = c->nbcount;
+        A.scalars = c->scalars; A.scalars_out = c->scalars_out;
+        A.nbq = c->nbq;
+        A.b_first = c->b_first; A.b_count = c->b_count; A.b_imass = c->b_imass; A.b_stiff = c->b_stiff; A.b_center = c->b_center; A.b_angle = c->b_angle;
+        A.dc_i1 = c->dc_i1; A.dc_i2 = c->dc_i2; A.dc_level_off = c->dc_level_off; A.dc_rest = c->dc_rest;
+        A.ops = c->fused_ops;
+        A.n = n; A.nops = c->fused_nops; A.nbodies = c->nbodies; A.ndist = c->dc_total; A.window_base = c->scalars_host[4];
+        A.stabilization_iterations = P.stabilization_iterations; A.solver_iterations = P.solver_iterations;
+        A.any_solid = c->any_solid;
+        A.prof = c->fused_prof;
+        c->fused_ticks++;
+        A.dt = dt; A.gx = P.gravity[0]; A.gy = P.gravity[1];
+        A.x0 = P.x_bounds[0]; A.x1 = P.x_bounds[1]; A.y0 = P.y_bounds[0]; A.y1 = P.y_bounds[1];
+        k2d_tick_fused<<<1, kFusedBlock, stage, s>>>(A);
+        c->launches = 1;
+    } else if (no_graph) {
         c->launches = issue_tick(c, dt);
     } else {
         Ps2dCtx::TickKey key;
