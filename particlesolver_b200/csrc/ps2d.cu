@@ -14,6 +14,7 @@
 // the host when the list changes.  Fluid / gas constraints are Jacobi inside and run as whole kernels at their place in
 // the STANDARD list; their all-pairs neighbour loops (totalfluidconstraint.cpp:52-76) run one warp per particle.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <cmath>
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__rest
 __device__ void d_fluid_delta(u32 i, u32 lane, const double2 *ep, const double *imass, u32 n, double p0, const FluidConsts &K, const double *lambda,
                               const u32 *nbcount, const u32 *counts, double2 *delta, const double2 *v, double2 *f) {
     const double2 pi = ep[i];
-    const double li = lambda[i];
+    const double li = __ldcg(lambda + i);
     const double base6 = poly6(K.dq_p * K.dq_p * kH * kH);
     double dx = 0., dy = 0., fvx = 0., fvy = 0.;
     for (u32 j = lane; j < n; j += 32) {
@@ -651,7 +652,7 @@ __device__ void d_fluid_delta(u32 i, u32 lane, const double2 *ep, const double *
             const double2 sg = spiky_grad(rx, ry, rlen);
             const double q = poly6(rlen * rlen) / base6, q2 = q * q;
             const double corr = -K.k_p * (q2 * q2);  // pow(q, E_P), E_P = 4, as two squarings (within 1 ulp of libm's pow)
-            const double s = (li + lambda[j]) + corr;
+            const double s = (li + __ldcg(lambda + j)) + corr;  // (.cg: in the fused tick another CTA of the cluster may have written it)
             dx += s * sg.x; dy += s * sg.y;
             if (K.gas) {
                 const double2 g = spiky_grad(rx, ry, r2);  // [sic] the squared length as the length
@@ -667,7 +668,7 @@ __device__ void d_fluid_delta(u32 i, u32 lane, const double2 *ep, const double *
     dx = warp_sum_d(dx); dy = warp_sum_d(dy);
     if (K.gas) { fvx = warp_sum_d(fvx); fvy = warp_sum_d(fvy); }
     if (lane != 0) return;
-    const double div = (double)nbcount[i] + (double)counts[i];
+    const double div = (double)__ldcg(nbcount + i) + (double)counts[i];
     delta[i] = make_double2((dx / p0) / div, (dy / p0) / div);
     if (K.gas) {
         double2 fi = f[i];
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restr
 }
 __device__ __forceinline__ void d_fluid_apply(u32 i, double2 *ep, const double2 *delta) {
     double2 e = ep[i];
-    const double2 d = delta[i];
+    const double2 d = __ldcg(delta + i);
     e.x += d.x; e.y += d.y;
     ep[i] = e;
 }
@@ -766,83 +767,125 @@ __device__ __noinline__ void fused_distance_cta(double2 *ep, const DistSlot *slo
     d_distance_levels<false>(ep, slots, 0u, level_off, levels, threadIdx.x, blockDim.x);
 }
 constexpr u32 kFusedTickMaxN = 160;   // measured: profiles/r2zz_2d_fused_tick.txt
+constexpr u32 kFusedCluster = 8;    // CTAs of the one cluster (the portable maximum)
 constexpr u32 kFusedBlock = 512;      // registers: 128 per thread, the serial chains of a tick must not spill
 constexpr u32 kFusedTickCapN = 2048;
 constexpr size_t kFusedStageMax = 160 * 1024;  // shared memory of the fused tick: 64 B per distance constraint + 20 B per particle  // what the kernel's shared memory is sized for at most (PS2D_FUSED_MAX_N for measurements)
 
+// Launched as ONE thread-block cluster of kFusedCluster CTAs: CTA 0 runs the tick; the others join it for the all-pairs loops (contact
+// search, fluid lambda and delta), which are double-precision throughput on one SM otherwise (2 sqrt + 4 divides per pair in range).
+// They read the predicted positions out of CTA 0's shared memory (distributed shared memory) and meet CTA 0 at cluster barriers
+// (release / acquire at cluster scope: what one side wrote to global memory before the barrier the other side reads after it).
 __global__ void __launch_bounds__(kFusedBlock, 1) k2d_tick_fused(const FusedTick A) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char fused_stage[];
     DistSlot *s_slots = reinterpret_cast<DistSlot *>(fused_stage);           // ndist: every distance constraint of the STANDARD list
     double2 *s_ep = reinterpret_cast<double2 *>(s_slots + A.ndist);          // n
     u32 *s_cur = reinterpret_cast<u32 *>(s_ep + A.n);                        // n
+    const u32 rank = cluster.block_rank(), nranks = cluster.num_blocks();
+    const bool lead = rank == 0;
+    const double2 *all_ep = lead ? s_ep : cluster.map_shared_rank(s_ep, 0);  // CTA 0's positions, as every CTA of the cluster reads them
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = kFusedBlock / 32, n = A.n;
+    const u32 cwarp = rank * nwarps + warp, cwarps = nranks * nwarps;        // this warp among the cluster's
     long long t_mark = A.prof ? clock64() : 0;
-#define PS2D_PHASE(k) do { if (A.prof && tid == 0) { const long long t_ = clock64(); A.prof[k] += (unsigned long long)(t_ - t_mark); t_mark = t_; } } while (0)
-    for (u32 i = tid; i < n; i += kFusedBlock) d_predict(i, A.v, s_ep, A.f, A.tmass, A.p, A.imass, A.phase, A.dt, A.gx, A.gy);
-    __syncthreads();
-    for (u32 i = warp; i < n; i += nwarps)
-        d_find_contacts(i, lane, s_ep, A.imass, A.phase, A.bod, A.static_counts, n, A.x0, A.x1, A.y0, A.y1, A.nb, A.cnt, A.flags, A.counts, A.draws, A.scalars + 3,
+#define PS2D_PHASE(k) do { if (A.prof && lead && tid == 0) { const long long t_ = clock64(); A.prof[k] += (unsigned long long)(t_ - t_mark); t_mark = t_; } } while (0)
+    if (lead)
+        for (u32 i = tid; i < n; i += kFusedBlock) d_predict(i, A.v, s_ep, A.f, A.tmass, A.p, A.imass, A.phase, A.dt, A.gx, A.gy);
+    cluster.sync();
+    for (u32 i = cwarp; i < n; i += cwarps)
+        d_find_contacts(i, lane, all_ep, A.imass, A.phase, A.bod, A.static_counts, n, A.x0, A.x1, A.y0, A.y1, A.nb, A.cnt, A.flags, A.counts, A.draws, A.scalars + 3,
                         A.any_solid);
-    __syncthreads();
-    d_scan_counts(A.draws, A.rank, n, A.scalars);
-    __syncthreads();
-    d_contact_levels(A.nb, A.cnt, A.flags, n, A.nbq, A.lvl, A.scalars + 1);
-    d_distance_prepare(s_slots, 0u, A.ndist, A.imass, A.counts, A.dc_i1, A.dc_i2, A.dc_rest, tid, kFusedBlock);  // counts are final since the contact search
-    __syncthreads();
-    PS2D_PHASE(0);
+    cluster.sync();
     const Particles2D V{s_ep, A.p, A.tmass, A.sfric, A.kfric, A.phase, A.bod, A.counts, A.sdf_grad, A.sdf_dist, A.b_angle};
-    for (u32 st = 0; st < A.stabilization_iterations; st++) {
-        d_contact_project(V, A.nb, A.cnt, A.flags, A.lvl, A.rank, A.scalars + 1, s_cur, n, A.raw, A.window_base, st, A.x0, A.x1, A.y0, A.y1, true);
+    if (lead) {
+        d_scan_counts(A.draws, A.rank, n, A.scalars);
         __syncthreads();
+        d_contact_levels(A.nb, A.cnt, A.flags, n, A.nbq, A.lvl, A.scalars + 1);
+        d_distance_prepare(s_slots, 0u, A.ndist, A.imass, A.counts, A.dc_i1, A.dc_i2, A.dc_rest, tid, kFusedBlock);  // counts are final since the contact search
+        __syncthreads();
+        PS2D_PHASE(0);
+        for (u32 st = 0; st < A.stabilization_iterations; st++) {
+            d_contact_project(V, A.nb, A.cnt, A.flags, A.lvl, A.rank, A.scalars + 1, s_cur, n, A.raw, A.window_base, st, A.x0, A.x1, A.y0, A.y1, true);
+            __syncthreads();
+        }
     }
     for (u32 it = 0; it < A.solver_iterations; it++) {
-        d_contact_project(V, A.nb, A.cnt, A.flags, A.lvl, A.rank, A.scalars + 1, s_cur, n, A.raw, A.window_base, A.stabilization_iterations + it, A.x0, A.x1, A.y0,
-                          A.y1, false);
-        __syncthreads();
-        PS2D_PHASE(1);
+        if (lead) {
+            d_contact_project(V, A.nb, A.cnt, A.flags, A.lvl, A.rank, A.scalars + 1, s_cur, n, A.raw, A.window_base, A.stabilization_iterations + it, A.x0, A.x1,
+                              A.y0, A.y1, false);
+            __syncthreads();
+            PS2D_PHASE(1);
+        }
         for (u32 o = 0; o < A.nops; o++) {
             const FusedOp op = A.ops[o];
             if (op.kind == STD_DISTANCE) {
-                const u32 *lo = A.dc_level_off + op.level_first;
-                if (op.width <= 32u) {
-                    if (warp == 0) fused_distance_warp(s_ep, s_slots, lo, op.levels, lane);
-                } else {
-                    fused_distance_cta(s_ep, s_slots, lo, op.levels);
+                if (lead) {
+                    const u32 *lo = A.dc_level_off + op.level_first;
+                    if (op.width <= 32u) {
+                        if (warp == 0) fused_distance_warp(s_ep, s_slots, lo, op.levels, lane);
+                    } else {
+                        fused_distance_cta(s_ep, s_slots, lo, op.levels);
+                    }
+                    __syncthreads();
+                    PS2D_PHASE(2);
                 }
-                __syncthreads();
-                PS2D_PHASE(2);
                 continue;
             }
             const FluidConsts K = op.kind == STD_GAS ? FluidConsts{.2, .25, .5, 1, (int)op.open} : FluidConsts{.1, .2, 0., 0, 0};
-            for (u32 i = warp; i < n; i += nwarps) d_fluid_lambda(i, lane, s_ep, A.imass, A.phase, A.group, n, (int)op.index, op.p0, K, A.lambda, A.nbcount, A.v, A.f);
-            __syncthreads();
+            cluster.sync();  // CTA 0's positions are those this constraint sees
+            for (u32 i = cwarp; i < n; i += cwarps) d_fluid_lambda(i, lane, all_ep, A.imass, A.phase, A.group, n, (int)op.index, op.p0, K, A.lambda, A.nbcount, A.v, A.f);
+            cluster.sync();  // every lambda is written
             PS2D_PHASE(3);
-            if (op.keep && it + 1 == A.solver_iterations)
-                for (u32 i = tid; i < n; i += kFusedBlock) A.lambda_keep[i] = A.lambda[i];
-            for (u32 i = warp; i < n; i += nwarps)
-                if (A.group[i] == (int)op.index) d_fluid_delta(i, lane, s_ep, A.imass, n, op.p0, K, A.lambda, A.nbcount, A.counts, A.delta, A.v, A.f);
-            __syncthreads();
-            for (u32 i = tid; i < n; i += kFusedBlock)
-                if (A.group[i] == (int)op.index) d_fluid_apply(i, s_ep, A.delta);
-            __syncthreads();
-            PS2D_PHASE(4);
+            if (lead && op.keep && it + 1 == A.solver_iterations)
+                for (u32 i = tid; i < n; i += kFusedBlock) A.lambda_keep[i] = __ldcg(A.lambda + i);
+            for (u32 i = cwarp; i < n; i += cwarps)
+                if (A.group[i] == (int)op.index) d_fluid_delta(i, lane, all_ep, A.imass, n, op.p0, K, A.lambda, A.nbcount, A.counts, A.delta, A.v, A.f);
+            cluster.sync();  // every delta is written, nobody reads the positions any more
+            if (lead) {
+                for (u32 i = tid; i < n; i += kFusedBlock)
+                    if (A.group[i] == (int)op.index) d_fluid_apply(i, s_ep, A.delta);
+                __syncthreads();
+                PS2D_PHASE(4);
+            }
         }
-        if (A.nbodies) {
+        if (lead && A.nbodies) {
             for (u32 b = tid; b < A.nbodies; b += kFusedBlock) d_shape(b, s_ep, A.imass, A.rs, A.b_first, A.b_count, A.b_imass, A.b_stiff, A.b_center, A.b_angle);
             __syncthreads();
             PS2D_PHASE(5);
         }
     }
+    if (!lead) return;
     for (u32 i = tid; i < n; i += kFusedBlock) {
         A.ep[i] = s_ep[i];
         d_finish(i, A.p, A.v, s_ep, A.dt);
     }
     if (tid == 0) {  // the tick's four scalars, straight into the host's (mapped, pinned) words
-        for (int k = 0; k < 4; k++) A.scalars_out[k] = A.scalars[k];
-        __threadfence_system();
+        for (int k = 0; k < 4; k++) A.scalars_out[k] = A.scalars[k];  // visible to the host when the kernel has ended (ps2d_tick waits for the stream)
     }
     PS2D_PHASE(6);
 #undef PS2D_PHASE
+}
+
+// New particles arrive as one record each in a pinned staging buffer and are scattered to the arrays by one small kernel: an emitter
+// that adds a particle every few ticks costs one asynchronous copy and one launch, not sixteen synchronous uploads.
+struct AppendRec { double px, py, vx, vy, im, sf, kf; int phase, bod, group, pad; };
+__global__ void k2d_append(const AppendRec *__restrict__ rec, u32 at, u32 n, double2 *p, double2 *ep, double2 *v, double2 *f, double2 *rs, double2 *sdf_grad,
+                           double *sdf_dist, double *imass, double *tmass, double *sfric, double *kfric, double *lambda, int *phase, int *bod, int *group,
+                           u32 *static_counts) {
+    const u32 k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= n) return;
+    const AppendRec r = rec[k];
+    const u32 i = at + k;
+    p[i] = ep[i] = make_double2(r.px, r.py);
+    v[i] = make_double2(r.vx, r.vy);
+    f[i] = rs[i] = sdf_grad[i] = make_double2(0., 0.);
+    sdf_dist[i] = -1.;
+    imass[i] = tmass[i] = r.im;
+    sfric[i] = r.sf; kfric[i] = r.kf;
+    lambda[i] = 0.;
+    phase[i] = r.phase; bod[i] = r.bod; group[i] = r.group;
+    static_counts[i] = 0u;
 }
 
 // glibc rand() = random(), TYPE_3: r[i] = r[i-31] + r[i-3], output r[i] >> 1 (after 310 discarded words)
@@ -923,6 +966,10 @@ struct Ps2dCtx {
     u32 dc_total = 0;                  // distance constraints in the STANDARD list
     u32 *scalars_out = nullptr;        // scalars_host as the device sees it (mapped pinned memory), or null
     bool last_tick_fused = false;
+    AppendRec *append_host = nullptr, *append_dev = nullptr;  // staging of ps2d_add_particles
+    size_t append_cap = 0;
+    cudaEvent_t append_done = nullptr;
+    bool append_pending = false;
     unsigned long long *fused_prof = nullptr;  // PS2D_FUSED_PROFILE=1: per-phase cycles of k2d_tick_fused, printed by ps2d_destroy
     uint64_t fused_ticks = 0;
     bool standard_dirty = true;
@@ -1011,6 +1058,9 @@ extern "C" int ps2d_destroy(Ps2dCtx *c) {
     if (!c) return PS_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->append_host) cudaFreeHost(c->append_host);
+    if (c->append_dev) cudaFree(c->append_dev);
+    if (c->append_done) cudaEventDestroy(c->append_done);
     if (c->fused_prof && c->fused_ticks) {
         unsigned long long h[8] = {};
         cudaMemcpy(h, c->fused_prof, sizeof h, cudaMemcpyDeviceToHost);
@@ -1038,46 +1088,59 @@ static cudaError_t upload(Ps2dCtx *c, T *dst, const T *src, size_t count) {
     return cudaStreamSynchronize(c->stream);  // callers pass temporaries
 }
 
-extern "C" int ps2d_add_particles(Ps2dCtx *c, const double *p2, const double *v2, const double *inv_mass, const int32_t *phase, const int32_t *bod,
-                                  const double *s_friction, const double *k_friction, uint64_t n, uint64_t *first) {
+static int append_particles(Ps2dCtx *c, const double *p2, const double *v2, const double *inv_mass, const int32_t *phase, const int32_t *bod,
+                            const double *s_friction, const double *k_friction, const int32_t *group, uint64_t n, uint64_t *first) {
     if (!c || !p2 || !inv_mass || !phase) { ps_set_error("ps2d_add_particles: null argument"); return PS_ERR_INVALID; }
     if (c->n + n > c->cap) { ps_set_error("ps2d_add_particles: %llu + %llu exceeds max_particles", (unsigned long long)c->n, (unsigned long long)n); return PS_ERR_CAPACITY; }
     for (uint64_t k = 0; k < n; k++) {
         if (phase[k] < PS2D_PHASE_SOLID || phase[k] > PS2D_PHASE_GAS) { ps_set_error("ps2d_add_particles: unknown phase %d", phase[k]); return PS_ERR_INVALID; }
         if (!(inv_mass[k] >= 0.)) { ps_set_error("ps2d_add_particles: negative inverse mass"); return PS_ERR_INVALID; }
     }
-    CU2(cudaSetDevice(c->device));
     const u32 at = c->n;
-    std::vector<double> zeros2(2 * n, 0.), zeros(n, 0.), minus(n, -1.);
-    std::vector<int> none(n, -1);
-    std::vector<u32> zc(n, 0u);
-    CU2(upload(c, (double *)(c->p + at), p2, 2 * n));
-    CU2(upload(c, (double *)(c->ep + at), p2, 2 * n));
-    CU2(upload(c, (double *)(c->v + at), v2 ? v2 : zeros2.data(), 2 * n));
-    CU2(upload(c, (double *)(c->f + at), zeros2.data(), 2 * n));
-    CU2(upload(c, (double *)(c->rs + at), zeros2.data(), 2 * n));
-    CU2(upload(c, (double *)(c->sdf_grad + at), zeros2.data(), 2 * n));
-    CU2(upload(c, c->sdf_dist + at, minus.data(), n));
-    CU2(upload(c, c->imass + at, inv_mass, n));
-    CU2(upload(c, c->tmass + at, inv_mass, n));
-    CU2(upload(c, c->sfric + at, s_friction ? s_friction : zeros.data(), n));
-    CU2(upload(c, c->kfric + at, k_friction ? k_friction : zeros.data(), n));
-    CU2(upload(c, c->lambda + at, zeros.data(), n));
-    CU2(upload(c, c->phase + at, (const int *)phase, n));
-    CU2(upload(c, c->bod + at, bod ? (const int *)bod : none.data(), n));
-    CU2(upload(c, c->group + at, none.data(), n));
-    CU2(upload(c, c->static_counts + at, zc.data(), n));
+    if (first) *first = at;
+    if (!n) return PS_OK;
+    CU2(cudaSetDevice(c->device));
+    if (!c->append_done) CU2(cudaEventCreateWithFlags(&c->append_done, cudaEventDisableTiming));
+    if (c->append_pending) { CU2(cudaEventSynchronize(c->append_done)); c->append_pending = false; }  // the staging buffer is free again
+    if (n > c->append_cap) {
+        CU2(cudaStreamSynchronize(c->stream));
+        if (c->append_host) cudaFreeHost(c->append_host);
+        if (c->append_dev) cudaFree(c->append_dev);
+        c->append_host = nullptr; c->append_dev = nullptr;
+        c->append_cap = std::max<size_t>(n, 64);
+        if (cudaMallocHost((void **)&c->append_host, c->append_cap * sizeof(AppendRec)) != cudaSuccess || !dev_alloc(&c->append_dev, c->append_cap)) {
+            c->append_cap = 0;
+            ps_set_error("ps2d_add_particles: staging allocation failed"); return PS_ERR_CUDA;
+        }
+    }
+    for (uint64_t k = 0; k < n; k++) {
+        AppendRec &r = c->append_host[k];
+        r.px = p2[2 * k]; r.py = p2[2 * k + 1];
+        r.vx = v2 ? v2[2 * k] : 0.; r.vy = v2 ? v2[2 * k + 1] : 0.;
+        r.im = inv_mass[k];
+        r.sf = s_friction ? s_friction[k] : 0.; r.kf = k_friction ? k_friction[k] : 0.;
+        r.phase = phase[k]; r.bod = bod ? bod[k] : -1; r.group = group ? group[k] : -1; r.pad = 0;
+    }
+    CU2(cudaMemcpyAsync(c->append_dev, c->append_host, n * sizeof(AppendRec), cudaMemcpyHostToDevice, c->stream));
+    k2d_append<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, c->stream>>>(c->append_dev, at, (u32)n, c->p, c->ep, c->v, c->f, c->rs, c->sdf_grad, c->sdf_dist, c->imass,
+                                                                                 c->tmass, c->sfric, c->kfric, c->lambda, c->phase, c->bod, c->group, c->static_counts);
+    CU2(cudaGetLastError());
+    CU2(cudaEventRecord(c->append_done, c->stream));
+    c->append_pending = true;
     for (uint64_t k = 0; k < n; k++) {
         c->h_imass.push_back(inv_mass[k]);
         c->h_phase.push_back(phase[k]);
         c->h_static_counts.push_back(0);
-        c->h_group.push_back(-1);
+        c->h_group.push_back(group ? group[k] : -1);
         c->h_t.push_back(4.);
         if (phase[k] == PS2D_PHASE_SOLID) c->any_solid = 1; else c->any_jitter = 1;
     }
     c->n += (u32)n;
-    if (first) *first = at;
     return PS_OK;
+}
+extern "C" int ps2d_add_particles(Ps2dCtx *c, const double *p2, const double *v2, const double *inv_mass, const int32_t *phase, const int32_t *bod,
+                                  const double *s_friction, const double *k_friction, uint64_t n, uint64_t *first) {
+    return append_particles(c, p2, v2, inv_mass, phase, bod, s_friction, k_friction, nullptr, n, first);
 }
 
 static int bump_static_counts(Ps2dCtx *c, u32 i) {
@@ -1092,6 +1155,7 @@ extern "C" int ps2d_add_distance_constraint(Ps2dCtx *c, uint32_t i1, uint32_t i2
     CU2(cudaSetDevice(c->device));
     if (d < 0.) {  // DistanceConstraint(first, second, particles): d = length(p1 - p2)
         double a[2], b[2];
+        CU2(cudaStreamSynchronize(c->stream));  // particles are appended on the context's stream
         CU2(cudaMemcpy(a, c->p + i1, 16, cudaMemcpyDeviceToHost));
         CU2(cudaMemcpy(b, c->p + i2, 16, cudaMemcpyDeviceToHost));
         const double x = a[0] - b[0], y = a[1] - b[1];
@@ -1440,10 +1504,8 @@ static int fluid_emitters_tick(Ps2dCtx *c, double dt) {
             const double vel[2] = {(double)(float)((double)c->rng.next() / (double)2147483647), 1.};  // glm::dvec2(frand(), 1)
             const int32_t ph = PS2D_PHASE_FLUID;
             uint64_t at = 0;
-            int r = ps2d_add_particles(c, pos, vel, &im, &ph, nullptr, nullptr, nullptr, 1, &at);
+            int r = append_particles(c, pos, vel, &im, &ph, nullptr, nullptr, nullptr, &id, 1, &at);  // a member of the emitter's fluid from the start
             if (r != PS_OK) return r;
-            CU2(upload(c, c->group + at, &id, 1));
-            c->h_group[at] = id;
         }
     }
     return PS_OK;
@@ -1622,7 +1684,14 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
         c->fused_ticks++;
         A.dt = dt; A.gx = P.gravity[0]; A.gy = P.gravity[1];
         A.x0 = P.x_bounds[0]; A.x1 = P.x_bounds[1]; A.y0 = P.y_bounds[0]; A.y1 = P.y_bounds[1];
-        k2d_tick_fused<<<1, kFusedBlock, stage, s>>>(A);
+        static const u32 cluster_ctas = [] { const char *e = getenv("PS2D_FUSED_CLUSTER"); return e ? std::max<u32>(1u, std::min<u32>((u32)strtoul(e, nullptr, 10), kFusedCluster)) : kFusedCluster; }();
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cluster_ctas); cfg.blockDim = dim3(kFusedBlock); cfg.dynamicSmemBytes = stage; cfg.stream = s;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cluster_ctas; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        CU2(cudaLaunchKernelEx(&cfg, k2d_tick_fused, A));
         c->launches = 1;
     } else if (no_graph) {
         c->launches = issue_tick(c, dt);
@@ -1681,11 +1750,9 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
             const double pos[2] = {em.x, em.y}, im = 1. / 1.;
             const int32_t ph = PS2D_PHASE_GAS;
             uint64_t at = 0;
-            int r = ps2d_add_particles(c, pos, nullptr, &im, &ph, nullptr, nullptr, nullptr, 1, &at);
-            if (r != PS_OK) return r;
             const int id = (int)em.standard_index;
-            CU2(upload(c, c->group + at, &id, 1));
-            c->h_group[at] = id;
+            int r = append_particles(c, pos, nullptr, &im, &ph, nullptr, nullptr, nullptr, &id, 1, &at);  // a member of the gas from the start
+            if (r != PS_OK) return r;
         }
     }
     return fluid_emitters_tick(c, dt);

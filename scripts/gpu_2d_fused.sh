@@ -1,22 +1,29 @@
 #!/bin/bash
-# the fused 2-D tick against the launch sequence: parity test, then ms per tick per scene at thresholds 0 (never) / 2048 (always, where it fits)
+# the fused 2-D tick (one cluster of CTAs) against the launch sequence: parity tests, then ms per tick per scene
+#   PS2D_FUSED_MAX_N: 0 = never fused, 2048 = always (where it fits); PS2D_FUSED_CLUSTER: CTAs of the cluster (default 8)
 mkdir -p gpurun_out
 python -m pytest tests/test_gpu_2d_fused.py tests/test_gpu_2d.py tests/test_gpu_2d_full.py -x -q -m gpu 2>&1 | tail -5
 CLI=particlesolver_b200/psolver_cli
 OUT=gpurun_out/r2zz_2d_fused_tick.jsonl
 : > $OUT
+for cl in 1 2 4 8; do
+  for rep in 1 2; do
+    PS2D_FUSED_CLUSTER=$cl timeout 300 $CLI --app cpu --scene 8 --ticks 200 --json | sed "s/^{/{\"cluster\": $cl, /" >> $OUT
+  done
+done
+PS2D_FUSED_PROFILE=1 $CLI --app cpu --scene 8 --ticks 200 --json > /dev/null 2> gpurun_out/r2zz_2d_fused_phases.txt
 for key in 8 7 6 2 1 0 w v; do
   for thr in 0 2048; do
     for rep in 1 2; do
-      PS2D_FUSED_MAX_N=$thr timeout 300 $CLI --app cpu --scene $key --ticks 400 --json | sed "s/^{/{\"fused_max_n\": $thr, /" >> $OUT
+      PS2D_FUSED_MAX_N=$thr timeout 300 $CLI --app cpu --scene $key --ticks 200 --json | sed "s/^{/{\"fused_max_n\": $thr, /" >> $OUT
     done
   done
 done
-timeout 300 oracle/_ref/ref_cpu --scene 8 --ticks 400 --json | grep '^{' >> $OUT
-timeout 300 oracle/_ref/ref_cpu --scene 8 --ticks 400 --json | grep '^{' >> $OUT
+for rep in 1 2; do timeout 300 oracle/_ref/ref_cpu --scene 8 --ticks 200 --json | grep '^{' >> $OUT; done
+cat gpurun_out/r2zz_2d_fused_phases.txt
 python - <<'PY'
 import json
 for l in open('gpurun_out/r2zz_2d_fused_tick.jsonl'):
     d = json.loads(l)
-    print(d.get('impl', 'ours'), d.get('scene'), d.get('fused_max_n'), d.get('particles', d.get('n')), d.get('wall_ms_per_tick', d.get('ms_per_tick')), d.get('launches_per_tick'))
+    print(d.get('impl', 'ours'), 'scene', d.get('scene'), 'cluster', d.get('cluster'), 'max_n', d.get('fused_max_n'), 'n', d.get('particles', d.get('n')), 'ms', d.get('wall_ms_per_tick', d.get('ms_per_tick')), 'launches', d.get('launches_per_tick'))
 PY
