@@ -766,7 +766,7 @@ __device__ __noinline__ void fused_distance_warp(double2 *ep, const DistSlot *sl
 __device__ __noinline__ void fused_distance_cta(double2 *ep, const DistSlot *slots, const u32 *level_off, u32 levels) {
     d_distance_levels<false>(ep, slots, 0u, level_off, levels, threadIdx.x, blockDim.x);
 }
-constexpr u32 kFusedTickMaxN = 160;   // measured: profiles/r2zz_2d_fused_tick.txt
+constexpr u32 kFusedTickMaxN = 128;   // measured break-even ~130-200 particles: profiles/r2zz_2d_fused_tick.txt
 constexpr u32 kFusedCluster = 8;    // CTAs of the one cluster (the portable maximum)
 constexpr u32 kFusedBlock = 512;      // registers: 128 per thread, the serial chains of a tick must not spill
 constexpr u32 kFusedTickCapN = 2048;
