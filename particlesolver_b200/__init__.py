@@ -126,6 +126,7 @@ def lib():
         L.ps_slab_set_lambda_range.argtypes = [vp, f32, f32]
         L.ps_slab_pack_lambda.argtypes = [vp, vp, vp, u64, C.POINTER(u32 * 2)]
         L.ps_slab_set_ghost_lambda.argtypes = [vp, vp, u64, vp, u64]
+        L.ps_slab_set_lambda_sinks.argtypes = [vp, vp, vp, u64]
         L.ps_slab_x_histogram.argtypes = [vp, f32, f32, u32, vp]
         L.ps_comm_get_unique_id.argtypes = [vp]
         L.ps_comm_init.argtypes = [vp, vp, i32, i32]
@@ -559,6 +560,10 @@ class Solver:
 
     def slab_set_ghost_lambda(self, left_ptr, n_left, right_ptr, n_right):
         _check(lib().ps_slab_set_ghost_lambda(self._h, left_ptr, n_left, right_ptr, n_right))
+
+    def slab_set_lambda_sinks(self, left_ptr, right_ptr, capacity):
+        """all-FLUID contexts: the lambda pass writes the halo members' lambda straight into these two message buffers (None, None: off)"""
+        _check(lib().ps_slab_set_lambda_sinks(self._h, left_ptr, right_ptr, capacity))
 
     def download_owned(self, which):
         """The owned particles' part of a per-particle array (ghosts follow them)."""

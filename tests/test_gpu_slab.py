@@ -112,6 +112,56 @@ def test_lambda_exchange_kernels():
     sol.close()
 
 
+def test_lambda_sinks_fill_the_messages_from_the_lambda_pass():
+    """ps_slab_set_lambda_sinks: the fused lambda kernel writes the lambda of every halo member into the outgoing messages itself, and
+    ps_slab_pack_lambda on the same buffers only reports the counts — same bytes as the separate pack pass; other buffers, the queue
+    walk or a cleared sink fall back to the pack kernel"""
+    p_or, pos, vel, w, phase, ros = _scene()
+    rng = np.random.default_rng(2)
+    pos[:, 0] += rng.uniform(-0.3, 0.3, pos.shape[0]).astype(np.float32)
+    assert (phase == 0).all()                                              # all fluid: what the sinks are for
+    eng = _ctx_engine(_params(p_or), (pos, vel, w, phase, ros))
+    sol = eng.sol
+    x_lo, x_hi, width = 8.0, 15.0, 2.25
+    gl, gr = eng.pack_halo(x_lo, x_hi, width)
+    nl, nr = gl.shape[0], gr.shape[0]
+    eng.set_ghosts(gr, gl)
+    sol.build_grid()
+    sol.solve_fluid_lambda()
+    ll, lr = eng.pack_lambda()
+    sol.sync()
+    want_l, want_r = ll.cpu().numpy().copy(), lr.cpu().numpy().copy()      # the pack kernel's messages
+    assert nl > 0 and nr > 0 and want_l.shape[0] == nl
+    # now as sinks: poison the buffers, run the lambda pass, "pack" without a launch
+    for buf in eng.lam_send:
+        buf.fill_(0xFF)
+    sol.slab_set_lambda_sinks(eng.lam_send[0].data_ptr(), eng.lam_send[1].data_ptr(), eng.halo_cap)
+    sol.solve_fluid_lambda()
+    sol.sync()
+    assert np.array_equal(eng.lam_send[0][:nl].cpu().numpy(), want_l) and np.array_equal(eng.lam_send[1][:nr].cpu().numpy(), want_r)
+    assert (eng.lam_send[0][nl:nl + 4].cpu().numpy() == 0xFF).all()        # nothing beyond the records
+    ll2, lr2 = eng.pack_lambda()                                           # counts only; the bytes stay
+    sol.sync()
+    assert (ll2.shape[0], lr2.shape[0]) == (nl, nr) and np.array_equal(ll2.cpu().numpy(), want_l) and np.array_equal(lr2.cpu().numpy(), want_r)
+    # a different destination is packed by the kernel as before
+    other = [torch.full_like(b, 0xEE) for b in eng.lam_send]
+    sol.solve_fluid_lambda()
+    c = sol.slab_pack_lambda(other[0].data_ptr(), other[1].data_ptr(), eng.halo_cap)
+    sol.sync()
+    assert c == (nl, nr) and np.array_equal(other[0][:nl].cpu().numpy(), want_l) and np.array_equal(other[1][:nr].cpu().numpy(), want_r)
+    # sinks cleared: the lambda pass leaves the buffers alone
+    sol.slab_set_lambda_sinks(None, None, 0)
+    for buf in eng.lam_send:
+        buf.fill_(0xFF)
+    sol.solve_fluid_lambda()
+    sol.sync()
+    assert (eng.lam_send[0][:nl].cpu().numpy() == 0xFF).all()
+    ll3, _ = eng.pack_lambda()
+    sol.sync()
+    assert np.array_equal(ll3.cpu().numpy(), want_l)
+    sol.close()
+
+
 @pytest.mark.parametrize("exchange_lambda", [True, False], ids=["lambda-exchanged", "lambda-local"])
 @pytest.mark.parametrize("nranks", [2, 3])
 def test_slabs_on_one_gpu_match_one_context(nranks, exchange_lambda):
