@@ -143,6 +143,7 @@ struct LambdaSinks {
     const uint2 *ranks = nullptr;
     float *left = nullptr, *right = nullptr;
     u32 cap = 0;
+    float left_below = 0.f, right_from = 0.f;  // the pack's membership test (x < left_below | x >= right_from): only members look their rank up
 };
 size_t ps_neighbor_list_elems(unsigned long long capacity, u32 rows_per_warp);
 size_t ps_neighbor_record_elems(unsigned long long capacity);

@@ -537,6 +537,7 @@ static int issue_fluid(PsCtx *c, const char *what, bool do_lambda, bool do_delta
         if (c->lam_sink[0] && c->slab_ranks_valid && c->slab_halo_counts[0] <= c->lam_sink_cap && c->slab_halo_counts[1] <= c->lam_sink_cap) {
             sinks.ranks = reinterpret_cast<const uint2 *>(c->slab_ranks); sinks.left = c->lam_sink[0]; sinks.right = c->lam_sink[1];
             sinks.cap = (u32)std::min<uint64_t>(c->lam_sink_cap, 0xfffffffeu);
+            sinks.left_below = c->slab_left_below; sinks.right_from = c->slab_right_from;
         }
         ps_launch_find_lambdas(c->lambda, c->num_neighbors, c->spos, c->sw, c->sphase, c->index, c->cell_begin, c->ros, c->n, c->n - c->n_ghost,
                                c->lambda_xmin, c->lambda_xmax, c->grid, c->stencil, (c->params.flags & PS_FLAG_ZERO_NONFLUID_LAMBDA) != 0, c->nbr_list,
@@ -900,6 +901,7 @@ extern "C" int ps_slab_pack_halo(PsCtx *c, float x_lo, float x_hi, float width, 
     c->slab_halo_counts[0] = counts[0];
     c->slab_halo_counts[1] = counts[1];
     c->slab_ranks_valid = true;
+    c->slab_left_below = left_below; c->slab_right_from = right_from;
     if (counts[0] > cap || counts[1] > cap) { ps_set_error("ps_slab_pack_halo: %u / %u records exceed the buffer capacity %llu", counts[0], counts[1], (unsigned long long)cap); return PS_ERR_CAPACITY; }
     return PS_OK;
 }

@@ -135,6 +135,7 @@ struct PsCtx {
     float *lam_sink[2] = {nullptr, nullptr};
     uint64_t lam_sink_cap = 0;
     bool lam_sinks_written = false;
+    float slab_left_below = 0.f, slab_right_from = 0.f;  // membership thresholds of the last halo pack
     bool slab_used = false;           // a slab call has compacted / appended particles: index-based constraints and bodies are refused from then on
     float lambda_xmin = -3.0e38f, lambda_xmax = 3.0e38f;
     PsStreamIo io;

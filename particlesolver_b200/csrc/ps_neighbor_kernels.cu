@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(kBlock, PS_FUSED_MINB) k_find_lambdas_fused(fl
     num_neighbors[i] = woff >> 7;
     // slab contexts: a particle of the last halo pack hands its lambda straight to the outgoing messages (what k_slab_pack_lambda would
     // collect in a pass of its own over all sorted slots)
-    if (sinks.ranks && orig < n_owned) {
+    if (sinks.ranks && orig < n_owned && (pi.x < sinks.left_below || pi.x >= sinks.right_from)) {  // positions are those the pack classified
         const uint2 r = __ldg(sinks.ranks + orig);
         if (r.x < sinks.cap) sinks.left[r.x] = lam;
         if (r.y < sinks.cap) sinks.right[r.y] = lam;
