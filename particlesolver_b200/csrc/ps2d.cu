@@ -13,6 +13,10 @@
 // found by parallel relaxation (k2d_contact_levels).  Distance constraints are static: their schedule is built once on
 // the host when the list changes.  Fluid / gas constraints are Jacobi inside and run as whole kernels at their place in
 // the STANDARD list; their all-pairs neighbour loops (totalfluidconstraint.cpp:52-76) run one warp per particle.
+//
+// Two ways to issue a tick, same device functions (d_*) and therefore the same bits: the LAUNCH SEQUENCE (issue_tick: 11-29
+// kernels, replayed as a CUDA graph) and, for scenes of up to kFusedTickMaxN particles, ONE KERNEL on one thread-block cluster
+// (k2d_tick_fused) — see the comment above it for when each wins.
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <nvtx3/nvToolsExt.h>
