@@ -112,7 +112,11 @@ __device__ __forceinline__ void d_find_contacts(u32 i, u32 lane, const double2 *
                 if ((solid2 || ph == PS2D_PHASE_SOLID || phj == PS2D_PHASE_SOLID) && !(im == 0. && imass[j] == 0.) && !(solid2 && bd == bod[j] && bd != -1)) {
                     const double2 q = ep[j];
                     const double dx = q.x - e.x, dy = q.y - e.y;
-                    hit = sqrt(dx * dx + dy * dy) < kDiam - kEps;
+                    // the reference's test is sqrt(d2) < DIAM - EPS; the square root is only taken where d2 is within 1e-9 of the
+                    // threshold's square (sqrt is monotone and correctly rounded, so the answer is the same everywhere else)
+                    constexpr double kT = kDiam - kEps, kT2 = kT * kT;
+                    const double d2 = dx * dx + dy * dy;
+                    hit = d2 < kT2 * (1. - 1e-9) ? true : (d2 > kT2 * (1. + 1e-9) ? false : sqrt(d2) < kT);
                 }
             }
             const u32 m = __ballot_sync(0xffffffffu, hit);
@@ -573,47 +577,77 @@ __global__ void __launch_bounds__(kBlock) k2d_shape(double2 *__restrict__ ep, co
 // TotalFluidConstraint / GasConstraint::project, first loop (totalfluidconstraint.cpp:45-93, gasconstraint.cpp:33-85): lambda
 // of every particle of STANDARD constraint `op`, 0 for everybody else (the constraint's lambdas is a QHash cleared per
 // call: any other particle reads 0, :106).  SOLID neighbours count S_SOLID-fold, immovable ones not at all.
-// One WARP per particle: lane l takes the candidates j = l, l + 32, ... of the reference's all-pairs loop and the partial
-// sums meet in a butterfly of xor-shuffles (deterministic; the summation order differs from the reference's sequential
-// one, i.e. the result agrees to rounding, ~1e-16 relative, instead of bit for bit — measured in tests/test_gpu_2d_full.py).
-// The serial form of this loop (one thread per particle) cost 115 + 177 us per constraint at N = 432: 96 % of a tick.
+// One WARP per particle, in two kinds of trips over the reference's all-pairs loop: a CHEAP one per 32 candidates (distance test
+// only; a ballot compacts the hits, in ascending index, into a 64-entry ring in shared memory) and a HEAVY one per 32 neighbours
+// found (one neighbour per lane: the 2 sqrt + 4 divides of the kernel terms) — a particle has some 25 neighbours among hundreds of
+// candidates, and with the terms evaluated inside the candidate trip every trip paid for them (14 heavy trips per particle at
+// N = 432; now 1).  Lane partial sums meet in a butterfly of xor-shuffles: deterministic; the summation order differs from the
+// reference's sequential one, i.e. the result agrees to rounding, ~1e-16 relative, instead of bit for bit (measured in
+// tests/test_gpu_2d_full.py).  The serial form of this loop (one thread per particle) cost 115 + 177 us per constraint at N = 432.
+constexpr u32 kRing = 64;  // entries per warp: fewer than 32 wait when up to 32 arrive
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ void d_fluid_lambda(u32 i, u32 lane, const double2 *ep, const double *imass, const int *phase, const int *group, u32 n, int op, double p0,
+// the candidates of particle i within H (and i itself when with_self), 32 at a time in ascending index, handed to visit(j)
+// one per lane; returns how many there were.  ring: this warp's kRing words of shared memory.
+template <class Visit>
+__device__ __forceinline__ u32 for_each_neighbor_2d(u32 i, u32 lane, u32 *ring, const double2 &pi, const double2 *ep, const double *imass, u32 n, bool with_self,
+                                                    Visit visit) {
+    const u32 lt = (1u << lane) - 1u;
+    u32 head = 0, cnt = 0, total = 0;
+    for (u32 base = 0; base < n; base += 32) {
+        const u32 j = base + lane;
+        bool hit = false;
+        if (j < n) {
+            if (j == i) hit = with_self;
+            else if (imass[j] != 0.) {  // fixed particles are ignored
+                const double2 pj = ep[j];
+                const double rx = pi.x - pj.x, ry = pi.y - pj.y;
+                hit = rx * rx + ry * ry < kH2;
+            }
+        }
+        const u32 m = __ballot_sync(0xffffffffu, hit);
+        if (!m) continue;
+        if (hit) ring[(head + cnt + __popc(m & lt)) & (kRing - 1)] = j;
+        cnt += __popc(m); total += __popc(m);
+        __syncwarp();
+        if (cnt >= 32u) {
+            visit(ring[(head + lane) & (kRing - 1)]);
+            head = (head + 32u) & (kRing - 1); cnt -= 32u;
+            __syncwarp();
+        }
+    }
+    if (lane < cnt) visit(ring[(head + lane) & (kRing - 1)]);
+    __syncwarp();
+    return total;
+}
+__device__ void d_fluid_lambda(u32 i, u32 lane, u32 *ring, const double2 *ep, const double *imass, const int *phase, const int *group, u32 n, int op, double p0,
                                const FluidConsts &K, double *lambda, u32 *nbcount, const double2 *v, double2 *f) {
     if (group[i] != op) { if (lane == 0) lambda[i] = 0.; return; }
     const double2 pi = ep[i];
     double rho = 0., denom = 0., ox = 0., oy = 0.;
-    u32 nbc = 0;
-    for (u32 j = lane; j < n; j += 32) {
+    const u32 nbc = for_each_neighbor_2d(i, lane, ring, pi, ep, imass, n, true, [&](u32 j) {
         const double im = imass[j];
         if (j == i) {  // the particle itself (:78-81)
-            nbc++;
             rho += poly6(0.) / im;
-            continue;
+            return;
         }
-        if (im == 0.) continue;  // fixed particles are ignored
         const double2 pj = ep[j];
         const double rx = pi.x - pj.x, ry = pi.y - pj.y;
         const double r2 = rx * rx + ry * ry;
-        if (r2 < kH2) {
-            nbc++;
-            double incr = poly6(r2) / im;
-            const bool solid = phase[j] == PS2D_PHASE_SOLID;
-            if (solid) incr *= K.s_solid;
-            rho += incr;
-            const double2 sg = spiky_grad(rx, ry, sqrt(r2));
-            const double gx = -sg.x / p0, gy = -sg.y / p0;  // grad(k, j) = -spikyGrad / p0 (:137-144)
-            denom += gx * gx + gy * gy;
-            const double w = solid ? K.s_solid : 1.;       // grad(k, i) = sum_j w_j spikyGrad / p0 (:146-157)
-            ox += w * sg.x; oy += w * sg.y;
-        }
-    }
+        double incr = poly6(r2) / im;
+        const bool solid = phase[j] == PS2D_PHASE_SOLID;
+        if (solid) incr *= K.s_solid;
+        rho += incr;
+        const double2 sg = spiky_grad(rx, ry, sqrt(r2));
+        const double gx = -sg.x / p0, gy = -sg.y / p0;  // grad(k, j) = -spikyGrad / p0 (:137-144)
+        denom += gx * gx + gy * gy;
+        const double w = solid ? K.s_solid : 1.;       // grad(k, i) = sum_j w_j spikyGrad / p0 (:146-157)
+        ox += w * sg.x; oy += w * sg.y;
+    });
     rho = warp_sum_d(rho); denom = warp_sum_d(denom); ox = warp_sum_d(ox); oy = warp_sum_d(oy);
-    nbc = __reduce_add_sync(0xffffffffu, nbc);
     if (lane != 0) return;
     ox = ox / p0; oy = oy / p0;
     denom += ox * ox + oy * oy;
@@ -632,43 +666,42 @@ __device__ void d_fluid_lambda(u32 i, u32 lane, const double2 *ep, const double 
 __global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ phase,
                                                            const int *__restrict__ group, u32 n, int op, double p0, FluidConsts K, double *__restrict__ lambda,
                                                            u32 *__restrict__ nbcount, const double2 *__restrict__ v, double2 *__restrict__ f) {
+    __shared__ u32 rings[kBlock / 32][kRing];
     const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     if (i >= n) return;  // warp-uniform
-    d_fluid_lambda(i, threadIdx.x & 31, ep, imass, phase, group, n, op, p0, K, lambda, nbcount, v, f);
+    d_fluid_lambda(i, threadIdx.x & 31, rings[threadIdx.x >> 5], ep, imass, phase, group, n, op, p0, K, lambda, nbcount, v, f);
 }
 
 // second loop (:95-111): delta_i = sum_j (lambda_i + lambda_j + s_corr) spikyGrad / p0, divided by (#neighbours incl. self +
 // constraint count) (:113-115).  Written to `delta`, applied by k2d_fluid_apply: all deltas of a constraint come from the
-// same ep.  Gas: the pseudo-vorticity force of gasconstraint.cpp:99-107 goes to the force accumulator.  One warp per particle.
-__device__ void d_fluid_delta(u32 i, u32 lane, const double2 *ep, const double *imass, u32 n, double p0, const FluidConsts &K, const double *lambda,
+// same ep.  Gas: the pseudo-vorticity force of gasconstraint.cpp:99-107 goes to the force accumulator.  One warp per particle,
+// the same two kinds of trips.
+__device__ void d_fluid_delta(u32 i, u32 lane, u32 *ring, const double2 *ep, const double *imass, u32 n, double p0, const FluidConsts &K, const double *lambda,
                               const u32 *nbcount, const u32 *counts, double2 *delta, const double2 *v, double2 *f) {
     const double2 pi = ep[i];
-    const double li = __ldcg(lambda + i);
+    const double li = __ldcg(lambda + i);  // (.cg: in the fused tick another CTA of the cluster may have written it)
     const double base6 = poly6(K.dq_p * K.dq_p * kH * kH);
     double dx = 0., dy = 0., fvx = 0., fvy = 0.;
-    for (u32 j = lane; j < n; j += 32) {
-        if (j == i || imass[j] == 0.) continue;
+    for_each_neighbor_2d(i, lane, ring, pi, ep, imass, n, false, [&](u32 j) {
         const double2 pj = ep[j];
         const double rx = pi.x - pj.x, ry = pi.y - pj.y;
         const double r2 = rx * rx + ry * ry;
-        if (r2 < kH2) {
-            const double rlen = sqrt(r2);
-            const double2 sg = spiky_grad(rx, ry, rlen);
-            const double q = poly6(rlen * rlen) / base6, q2 = q * q;
-            const double corr = -K.k_p * (q2 * q2);  // pow(q, E_P), E_P = 4, as two squarings (within 1 ulp of libm's pow)
-            const double s = (li + __ldcg(lambda + j)) + corr;  // (.cg: in the fused tick another CTA of the cluster may have written it)
-            dx += s * sg.x; dy += s * sg.y;
-            if (K.gas) {
-                const double2 g = spiky_grad(rx, ry, r2);  // [sic] the squared length as the length
-                const double2 vj = v[j];
-                const double wx = g.x * vj.x, wy = g.y * vj.y;
-                const double L = sqrt(wx * wx + wy * wy);
-                const double cx = 0. * 0. - ry * L, cy = L * rx - 0. * 0.;  // cross((0,0,L), (rx,ry,0))
-                const double p6 = poly6(r2);
-                fvx += cx * p6; fvy += cy * p6;
-            }
+        const double rlen = sqrt(r2);
+        const double2 sg = spiky_grad(rx, ry, rlen);
+        const double q = poly6(rlen * rlen) / base6, q2 = q * q;
+        const double corr = -K.k_p * (q2 * q2);  // pow(q, E_P), E_P = 4, as two squarings (within 1 ulp of libm's pow)
+        const double s = (li + __ldcg(lambda + j)) + corr;
+        dx += s * sg.x; dy += s * sg.y;
+        if (K.gas) {
+            const double2 g = spiky_grad(rx, ry, r2);  // [sic] the squared length as the length
+            const double2 vj = v[j];
+            const double wx = g.x * vj.x, wy = g.y * vj.y;
+            const double L = sqrt(wx * wx + wy * wy);
+            const double cx = 0. * 0. - ry * L, cy = L * rx - 0. * 0.;  // cross((0,0,L), (rx,ry,0))
+            const double p6 = poly6(r2);
+            fvx += cx * p6; fvy += cy * p6;
         }
-    }
+    });
     dx = warp_sum_d(dx); dy = warp_sum_d(dy);
     if (K.gas) { fvx = warp_sum_d(fvx); fvy = warp_sum_d(fvy); }
     if (lane != 0) return;
@@ -684,9 +717,10 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restr
                                                           int op, double p0, FluidConsts K, const double *__restrict__ lambda, const u32 *__restrict__ nbcount,
                                                           const u32 *__restrict__ counts, double2 *__restrict__ delta, const double2 *__restrict__ v,
                                                           double2 *__restrict__ f) {
+    __shared__ u32 rings[kBlock / 32][kRing];
     const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     if (i >= n || group[i] != op) return;  // warp-uniform
-    d_fluid_delta(i, threadIdx.x & 31, ep, imass, n, p0, K, lambda, nbcount, counts, delta, v, f);
+    d_fluid_delta(i, threadIdx.x & 31, rings[threadIdx.x >> 5], ep, imass, n, p0, K, lambda, nbcount, counts, delta, v, f);
 }
 __device__ __forceinline__ void d_fluid_apply(u32 i, double2 *ep, const double2 *delta) {
     double2 e = ep[i];
@@ -770,35 +804,52 @@ __device__ __noinline__ void fused_distance_warp(double2 *ep, const DistSlot *sl
 __device__ __noinline__ void fused_distance_cta(double2 *ep, const DistSlot *slots, const u32 *level_off, u32 levels) {
     d_distance_levels<false>(ep, slots, 0u, level_off, levels, threadIdx.x, blockDim.x);
 }
-constexpr u32 kFusedTickMaxN = 128;   // measured break-even ~130-200 particles: profiles/r2zz_2d_fused_tick.txt
-constexpr u32 kFusedCluster = 8;    // CTAs of the one cluster (the portable maximum)
+constexpr u32 kFusedTickMaxN = 800;   // measured break-even between 765 and 931 particles (16-CTA cluster): profiles/r2zz_2d_fused_tick.txt
+constexpr u32 kFusedCluster = 16;   // CTAs of the one cluster wanted (8 is the portable maximum; 16 is asked for and halved until the device accepts)
+constexpr u32 kFusedClusterMax = 16;
 constexpr u32 kFusedBlock = 512;      // registers: 128 per thread, the serial chains of a tick must not spill
 constexpr u32 kFusedTickCapN = 2048;
-constexpr size_t kFusedStageMax = 160 * 1024;  // shared memory of the fused tick: 64 B per distance constraint + 20 B per particle  // what the kernel's shared memory is sized for at most (PS2D_FUSED_MAX_N for measurements)
+constexpr size_t kFusedStageMax = 160 * 1024;  // shared memory of the fused tick: 64 B per distance constraint + 36 B per particle
 
 // Launched as ONE thread-block cluster of kFusedCluster CTAs: CTA 0 runs the tick; the others join it for the all-pairs loops (contact
 // search, fluid lambda and delta), which are double-precision throughput on one SM otherwise (2 sqrt + 4 divides per pair in range).
-// They read the predicted positions out of CTA 0's shared memory (distributed shared memory) and meet CTA 0 at cluster barriers
-// (release / acquire at cluster scope: what one side wrote to global memory before the barrier the other side reads after it).
+// They read the predicted positions from the copy CTA 0 publishes in global memory and meet CTA 0 at cluster barriers (release /
+// acquire at cluster scope: what one side wrote to global memory before the barrier the other side reads after it).
 __global__ void __launch_bounds__(kFusedBlock, 1) k2d_tick_fused(const FusedTick A) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char fused_stage[];
     DistSlot *s_slots = reinterpret_cast<DistSlot *>(fused_stage);           // ndist: every distance constraint of the STANDARD list
     double2 *s_ep = reinterpret_cast<double2 *>(s_slots + A.ndist);          // n
-    u32 *s_cur = reinterpret_cast<u32 *>(s_ep + A.n);                        // n
+    __shared__ u32 s_ring[kFusedBlock / 32][kRing];                          // the warps' neighbour rings (d_fluid_lambda / d_fluid_delta)
     const u32 rank = cluster.block_rank(), nranks = cluster.num_blocks();
     const bool lead = rank == 0;
-    const double2 *all_ep = lead ? s_ep : cluster.map_shared_rank(s_ep, 0);  // CTA 0's positions, as every CTA of the cluster reads them
+    // every CTA keeps its own copies, in shared memory, of what the all-pairs loops read: inverse masses, phases and groups (constant
+    // during a tick) and the predicted positions — CTA 0's are the tick's state, the others refresh theirs from the copy CTA 0
+    // publishes in global memory before each cluster barrier that opens an all-pairs phase (one coalesced burst per phase instead of
+    // dependent L2 misses per trip: cluster.sync flushes L1.  Reading CTA 0's shared memory directly — distributed shared memory —
+    // makes its one shared-memory port serve n x n x 16 bytes per phase: measured 77 k cycles per lambda pass at 432 particles)
+    double *c_imass = reinterpret_cast<double *>(s_ep + A.n);                // n (before s_cur: 8-byte aligned)
+    u32 *s_cur = reinterpret_cast<u32 *>(c_imass + A.n);                     // n: the contact cursors (CTA 0)
+    int *c_phase = reinterpret_cast<int *>(s_cur + A.n);                     // n
+    int *c_group = c_phase + A.n;                                            // n
+    const double2 *all_ep = s_ep;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = kFusedBlock / 32, n = A.n;
     const u32 cwarp = rank * nwarps + warp, cwarps = nranks * nwarps;        // this warp among the cluster's
     long long t_mark = A.prof ? clock64() : 0;
 #define PS2D_PHASE(k) do { if (A.prof && lead && tid == 0) { const long long t_ = clock64(); A.prof[k] += (unsigned long long)(t_ - t_mark); t_mark = t_; } } while (0)
+    for (u32 i = tid; i < n; i += kFusedBlock) { c_imass[i] = A.imass[i]; c_phase[i] = A.phase[i]; c_group[i] = A.group[i]; }
     if (lead)
-        for (u32 i = tid; i < n; i += kFusedBlock) d_predict(i, A.v, s_ep, A.f, A.tmass, A.p, A.imass, A.phase, A.dt, A.gx, A.gy);
+        for (u32 i = tid; i < n; i += kFusedBlock) {
+            d_predict(i, A.v, s_ep, A.f, A.tmass, A.p, A.imass, A.phase, A.dt, A.gx, A.gy);
+            A.ep[i] = s_ep[i];
+        }
     cluster.sync();
+    if (!lead)
+        for (u32 i = tid; i < n; i += kFusedBlock) s_ep[i] = A.ep[i];
+    __syncthreads();
     for (u32 i = cwarp; i < n; i += cwarps)
-        d_find_contacts(i, lane, all_ep, A.imass, A.phase, A.bod, A.static_counts, n, A.x0, A.x1, A.y0, A.y1, A.nb, A.cnt, A.flags, A.counts, A.draws, A.scalars + 3,
+        d_find_contacts(i, lane, all_ep, c_imass, c_phase, A.bod, A.static_counts, n, A.x0, A.x1, A.y0, A.y1, A.nb, A.cnt, A.flags, A.counts, A.draws, A.scalars + 3,
                         A.any_solid);
     cluster.sync();
     const Particles2D V{s_ep, A.p, A.tmass, A.sfric, A.kfric, A.phase, A.bod, A.counts, A.sdf_grad, A.sdf_dist, A.b_angle};
@@ -837,18 +888,24 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k2d_tick_fused(const FusedTick
                 continue;
             }
             const FluidConsts K = op.kind == STD_GAS ? FluidConsts{.2, .25, .5, 1, (int)op.open} : FluidConsts{.1, .2, 0., 0, 0};
+            if (lead)
+                for (u32 i = tid; i < n; i += kFusedBlock) A.ep[i] = s_ep[i];
             cluster.sync();  // CTA 0's positions are those this constraint sees
-            for (u32 i = cwarp; i < n; i += cwarps) d_fluid_lambda(i, lane, all_ep, A.imass, A.phase, A.group, n, (int)op.index, op.p0, K, A.lambda, A.nbcount, A.v, A.f);
+            if (!lead) {
+                for (u32 i = tid; i < n; i += kFusedBlock) s_ep[i] = A.ep[i];
+                __syncthreads();
+            }
+            for (u32 i = cwarp; i < n; i += cwarps) d_fluid_lambda(i, lane, s_ring[warp], all_ep, c_imass, c_phase, c_group, n, (int)op.index, op.p0, K, A.lambda, A.nbcount, A.v, A.f);
             cluster.sync();  // every lambda is written
             PS2D_PHASE(3);
             if (lead && op.keep && it + 1 == A.solver_iterations)
                 for (u32 i = tid; i < n; i += kFusedBlock) A.lambda_keep[i] = __ldcg(A.lambda + i);
             for (u32 i = cwarp; i < n; i += cwarps)
-                if (A.group[i] == (int)op.index) d_fluid_delta(i, lane, all_ep, A.imass, n, op.p0, K, A.lambda, A.nbcount, A.counts, A.delta, A.v, A.f);
+                if (c_group[i] == (int)op.index) d_fluid_delta(i, lane, s_ring[warp], all_ep, c_imass, n, op.p0, K, A.lambda, A.nbcount, A.counts, A.delta, A.v, A.f);
             cluster.sync();  // every delta is written, nobody reads the positions any more
             if (lead) {
                 for (u32 i = tid; i < n; i += kFusedBlock)
-                    if (A.group[i] == (int)op.index) d_fluid_apply(i, s_ep, A.delta);
+                    if (c_group[i] == (int)op.index) d_fluid_apply(i, s_ep, A.delta);
                 __syncthreads();
                 PS2D_PHASE(4);
             }
@@ -1648,7 +1705,7 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
     // draws of this tick start at window[window_base]; the kernels read it from a device word
     // scenes of a few dozen particles: the whole tick as one kernel (k2d_tick_fused); PS2D_FUSED_MAX_N moves the threshold (0: never)
     static const u32 fused_max_n = [] { const char *e = getenv("PS2D_FUSED_MAX_N"); return e ? std::min<u32>((u32)strtoul(e, nullptr, 10), kFusedTickCapN) : kFusedTickMaxN; }();
-    const size_t fused_stage = (size_t)c->dc_total * sizeof(DistSlot) + (size_t)n * (sizeof(double2) + sizeof(u32));
+    const size_t fused_stage = (size_t)c->dc_total * sizeof(DistSlot) + (size_t)n * (sizeof(double2) + sizeof(double) + sizeof(u32) + 2 * sizeof(int));
     c->last_tick_fused = n <= fused_max_n && c->scalars_out != nullptr && fused_stage <= kFusedStageMax;
     c->scalars_host[4] = (u32)(c->rng.calls - c->win_pos);
     if (!c->last_tick_fused) CU2(cudaMemcpyAsync(c->window_base_dev, c->scalars_host + 4, 4, cudaMemcpyHostToDevice, s));  // the fused kernel takes it as an argument
@@ -1688,13 +1745,25 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
         c->fused_ticks++;
         A.dt = dt; A.gx = P.gravity[0]; A.gy = P.gravity[1];
         A.x0 = P.x_bounds[0]; A.x1 = P.x_bounds[1]; A.y0 = P.y_bounds[0]; A.y1 = P.y_bounds[1];
-        static const u32 cluster_ctas = [] { const char *e = getenv("PS2D_FUSED_CLUSTER"); return e ? std::max<u32>(1u, std::min<u32>((u32)strtoul(e, nullptr, 10), kFusedCluster)) : kFusedCluster; }();
+        static const u32 cluster_want = [] { const char *e = getenv("PS2D_FUSED_CLUSTER"); return e ? std::max<u32>(1u, std::min<u32>((u32)strtoul(e, nullptr, 10), kFusedClusterMax)) : kFusedCluster; }();
+        static u32 cluster_ok[64] = {};  // per device: the largest cluster of this kernel the device schedules (0 = not asked yet)
+        u32 &cluster_ctas = cluster_ok[(c->device >= 0 && c->device < 64) ? c->device : 0];
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(cluster_ctas); cfg.blockDim = dim3(kFusedBlock); cfg.dynamicSmemBytes = stage; cfg.stream = s;
+        cfg.blockDim = dim3(kFusedBlock); cfg.dynamicSmemBytes = kFusedStageMax; cfg.stream = s;
         cudaLaunchAttribute attr{};
         attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = cluster_ctas; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
+        if (!cluster_ctas) {
+            if (cluster_want > 8) CU2(cudaFuncSetAttribute(k2d_tick_fused, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            for (cluster_ctas = cluster_want; cluster_ctas > 1; cluster_ctas /= 2) {  // sizes above 8 are not portable: ask, halve if refused
+                int fits = 0;
+                cfg.gridDim = dim3(cluster_ctas); attr.val.clusterDim.x = cluster_ctas;
+                if (cudaOccupancyMaxActiveClusters(&fits, k2d_tick_fused, &cfg) == cudaSuccess && fits > 0) break;
+                cudaGetLastError();
+            }
+        }
+        cfg.gridDim = dim3(cluster_ctas); attr.val.clusterDim.x = cluster_ctas; cfg.dynamicSmemBytes = stage;
         CU2(cudaLaunchKernelEx(&cfg, k2d_tick_fused, A));
         c->launches = 1;
     } else if (no_graph) {

@@ -40,4 +40,4 @@ def test_small_scenes_are_fused_by_default():
     r = subprocess.run([CLI, "--app", "cpu", "--scene", "8", "--ticks", "30", "--json"], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     out = json.loads(r.stdout.strip().splitlines()[-1])
-    assert out["particles"] <= 128 and out["launches_per_tick"] == 1
+    assert out["particles"] <= 800 and out["launches_per_tick"] == 1
