@@ -761,13 +761,13 @@ __global__ void k2d_impulse(double2 *__restrict__ v, const double2 *__restrict__
 
 enum StdKind { STD_FLUID, STD_GAS, STD_DISTANCE };
 
-// ---- the whole tick as ONE kernel, for scenes of a few dozen particles ------------------------------------------------
-// A tick of such a scene is 11-29 dependent launches whose kernels run for a microsecond or two each: even replayed as a graph, the
-// gaps between dependent nodes (2-3 us each) are most of the tick.  k2d_tick_fused runs the same device functions in the same order
-// inside one CTA of 512 threads, with a CTA barrier where the launch boundaries were, the predicted positions and the contact
-// cursors in shared memory for the whole tick, and the STANDARD list as a device-side op table.  Same functions, same arithmetic:
-// bit-identical to the launch sequence (tests/test_gpu_2d_fused.py).  It stops paying where the all-pairs loops of the fluid / contact
-// search want more than one SM: above kFusedTickMaxN particles the launch sequence (148 SMs) is used.
+// ---- the whole tick as ONE kernel, for scenes of up to a few hundred particles ----------------------------------------
+// A tick of such a scene is 8-29 dependent launches whose kernels run for a few microseconds each: even replayed as a graph, the
+// gaps between dependent nodes (2-3 us each) are a large part of the tick.  k2d_tick_fused runs the same device functions in the same
+// order inside one thread-block cluster (see the kernel), with a barrier where the launch boundaries were, the predicted positions and
+// the contact cursors in shared memory for the whole tick, and the STANDARD list as a device-side op table.  Same functions, same
+// arithmetic: bit-identical to the launch sequence (tests/test_gpu_2d_fused.py).  It stops paying where the all-pairs loops of the
+// fluid / contact search want more SMs than a cluster has: above kFusedTickMaxN particles the launch sequence (148 SMs) is used.
 struct FusedOp {  // one entry of the STANDARD list, distance constraints as whole runs
     u32 kind;      // STD_FLUID / STD_GAS / STD_DISTANCE
     u32 open;      // gas: open boundary
@@ -811,7 +811,7 @@ constexpr u32 kFusedBlock = 512;      // registers: 128 per thread, the serial c
 constexpr u32 kFusedTickCapN = 2048;
 constexpr size_t kFusedStageMax = 160 * 1024;  // shared memory of the fused tick: 64 B per distance constraint + 36 B per particle
 
-// Launched as ONE thread-block cluster of kFusedCluster CTAs: CTA 0 runs the tick; the others join it for the all-pairs loops (contact
+// Launched as ONE thread-block cluster of up to kFusedCluster CTAs: CTA 0 runs the tick; the others join it for the all-pairs loops (contact
 // search, fluid lambda and delta), which are double-precision throughput on one SM otherwise (2 sqrt + 4 divides per pair in range).
 // They read the predicted positions from the copy CTA 0 publishes in global memory and meet CTA 0 at cluster barriers (release /
 // acquire at cluster scope: what one side wrote to global memory before the barrier the other side reads after it).
@@ -1702,11 +1702,11 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
         c->win_pos = c->rng.calls;
         c->win_len = want;
     }
-    // draws of this tick start at window[window_base]; the kernels read it from a device word
-    // scenes of a few dozen particles: the whole tick as one kernel (k2d_tick_fused); PS2D_FUSED_MAX_N moves the threshold (0: never)
+    // scenes of up to kFusedTickMaxN particles: the whole tick as one kernel (k2d_tick_fused); PS2D_FUSED_MAX_N moves the threshold (0: never)
     static const u32 fused_max_n = [] { const char *e = getenv("PS2D_FUSED_MAX_N"); return e ? std::min<u32>((u32)strtoul(e, nullptr, 10), kFusedTickCapN) : kFusedTickMaxN; }();
     const size_t fused_stage = (size_t)c->dc_total * sizeof(DistSlot) + (size_t)n * (sizeof(double2) + sizeof(double) + sizeof(u32) + 2 * sizeof(int));
     c->last_tick_fused = n <= fused_max_n && c->scalars_out != nullptr && fused_stage <= kFusedStageMax;
+    // draws of this tick start at window[window_base]; the kernels of the launch sequence read it from a device word
     c->scalars_host[4] = (u32)(c->rng.calls - c->win_pos);
     if (!c->last_tick_fused) CU2(cudaMemcpyAsync(c->window_base_dev, c->scalars_host + 4, 4, cudaMemcpyHostToDevice, s));  // the fused kernel takes it as an argument
     static const bool no_graph = getenv("PS_NO_GRAPH") != nullptr;
