@@ -591,12 +591,14 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 // the candidates of particle i within H (and i itself when with_self), 32 at a time in ascending index, handed to visit(j)
-// one per lane; returns how many there were.  ring: this warp's kRing words of shared memory.
+// one per lane; returns how many there were.  ring: this warp's kRing words of shared memory.  keep != nullptr: the first kNbrKeep
+// of them are also written there, for the second loop of the constraint (the reference reuses its neighbour lists the same way, :96).
+constexpr u32 kNbrKeep = 128;  // list entries kept per particle (2-D fluids at rest have ~25-50 neighbours within H; more: the second loop searches again)
 template <class Visit>
 __device__ __forceinline__ u32 for_each_neighbor_2d(u32 i, u32 lane, u32 *ring, const double2 &pi, const double2 *ep, const double *imass, u32 n, bool with_self,
-                                                    Visit visit) {
+                                                    u32 *keep, Visit visit) {
     const u32 lt = (1u << lane) - 1u;
-    u32 head = 0, cnt = 0, total = 0;
+    u32 head = 0, cnt = 0, total = 0, kept = 0;
     for (u32 base = 0; base < n; base += 32) {
         const u32 j = base + lane;
         bool hit = false;
@@ -614,21 +616,28 @@ __device__ __forceinline__ u32 for_each_neighbor_2d(u32 i, u32 lane, u32 *ring, 
         cnt += __popc(m); total += __popc(m);
         __syncwarp();
         if (cnt >= 32u) {
-            visit(ring[(head + lane) & (kRing - 1)]);
+            const u32 jj = ring[(head + lane) & (kRing - 1)];
+            if (keep && kept + lane < kNbrKeep) keep[kept + lane] = jj;
+            kept += 32u;
+            visit(jj);
             head = (head + 32u) & (kRing - 1); cnt -= 32u;
             __syncwarp();
         }
     }
-    if (lane < cnt) visit(ring[(head + lane) & (kRing - 1)]);
+    if (lane < cnt) {
+        const u32 jj = ring[(head + lane) & (kRing - 1)];
+        if (keep && kept + lane < kNbrKeep) keep[kept + lane] = jj;
+        visit(jj);
+    }
     __syncwarp();
     return total;
 }
 __device__ void d_fluid_lambda(u32 i, u32 lane, u32 *ring, const double2 *ep, const double *imass, const int *phase, const int *group, u32 n, int op, double p0,
-                               const FluidConsts &K, double *lambda, u32 *nbcount, const double2 *v, double2 *f) {
+                               const FluidConsts &K, double *lambda, u32 *nbcount, u32 *nbr_keep, const double2 *v, double2 *f) {
     if (group[i] != op) { if (lane == 0) lambda[i] = 0.; return; }
     const double2 pi = ep[i];
     double rho = 0., denom = 0., ox = 0., oy = 0.;
-    const u32 nbc = for_each_neighbor_2d(i, lane, ring, pi, ep, imass, n, true, [&](u32 j) {
+    const u32 nbc = for_each_neighbor_2d(i, lane, ring, pi, ep, imass, n, true, nbr_keep ? nbr_keep + (size_t)i * kNbrKeep : nullptr, [&](u32 j) {
         const double im = imass[j];
         if (j == i) {  // the particle itself (:78-81)
             rho += poly6(0.) / im;
@@ -665,11 +674,12 @@ __device__ void d_fluid_lambda(u32 i, u32 lane, u32 *ring, const double2 *ep, co
 
 __global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ phase,
                                                            const int *__restrict__ group, u32 n, int op, double p0, FluidConsts K, double *__restrict__ lambda,
-                                                           u32 *__restrict__ nbcount, const double2 *__restrict__ v, double2 *__restrict__ f) {
+                                                           u32 *__restrict__ nbcount, u32 *__restrict__ nbr_keep, const double2 *__restrict__ v,
+                                                           double2 *__restrict__ f) {
     __shared__ u32 rings[kBlock / 32][kRing];
     const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     if (i >= n) return;  // warp-uniform
-    d_fluid_lambda(i, threadIdx.x & 31, rings[threadIdx.x >> 5], ep, imass, phase, group, n, op, p0, K, lambda, nbcount, v, f);
+    d_fluid_lambda(i, threadIdx.x & 31, rings[threadIdx.x >> 5], ep, imass, phase, group, n, op, p0, K, lambda, nbcount, nbr_keep, v, f);
 }
 
 // second loop (:95-111): delta_i = sum_j (lambda_i + lambda_j + s_corr) spikyGrad / p0, divided by (#neighbours incl. self +
@@ -677,12 +687,12 @@ __global__ void __launch_bounds__(kBlock) k2d_fluid_lambda(const double2 *__rest
 // same ep.  Gas: the pseudo-vorticity force of gasconstraint.cpp:99-107 goes to the force accumulator.  One warp per particle,
 // the same two kinds of trips.
 __device__ void d_fluid_delta(u32 i, u32 lane, u32 *ring, const double2 *ep, const double *imass, u32 n, double p0, const FluidConsts &K, const double *lambda,
-                              const u32 *nbcount, const u32 *counts, double2 *delta, const double2 *v, double2 *f) {
+                              const u32 *nbcount, const u32 *nbr_keep, const u32 *counts, double2 *delta, const double2 *v, double2 *f) {
     const double2 pi = ep[i];
     const double li = __ldcg(lambda + i);  // (.cg: in the fused tick another CTA of the cluster may have written it)
     const double base6 = poly6(K.dq_p * K.dq_p * kH * kH);
     double dx = 0., dy = 0., fvx = 0., fvy = 0.;
-    for_each_neighbor_2d(i, lane, ring, pi, ep, imass, n, false, [&](u32 j) {
+    auto visit = [&](u32 j) {
         const double2 pj = ep[j];
         const double rx = pi.x - pj.x, ry = pi.y - pj.y;
         const double r2 = rx * rx + ry * ry;
@@ -701,11 +711,21 @@ __device__ void d_fluid_delta(u32 i, u32 lane, u32 *ring, const double2 *ep, con
             const double p6 = poly6(r2);
             fvx += cx * p6; fvy += cy * p6;
         }
-    });
+    };
+    const u32 nbc = __ldcg(nbcount + i);  // neighbours the first loop found, the particle itself included
+    if (nbr_keep && nbc <= kNbrKeep) {  // the first loop's list is complete: no second search (positions have not moved since)
+        const u32 *list = nbr_keep + (size_t)i * kNbrKeep;
+        for (u32 k = lane; k < nbc; k += 32) {
+            const u32 j = __ldcg(list + k);
+            if (j != i) visit(j);
+        }
+    } else {
+        for_each_neighbor_2d(i, lane, ring, pi, ep, imass, n, false, nullptr, visit);
+    }
     dx = warp_sum_d(dx); dy = warp_sum_d(dy);
     if (K.gas) { fvx = warp_sum_d(fvx); fvy = warp_sum_d(fvy); }
     if (lane != 0) return;
-    const double div = (double)__ldcg(nbcount + i) + (double)counts[i];
+    const double div = (double)nbc + (double)counts[i];
     delta[i] = make_double2((dx / p0) / div, (dy / p0) / div);
     if (K.gas) {
         double2 fi = f[i];
@@ -715,12 +735,12 @@ __device__ void d_fluid_delta(u32 i, u32 lane, u32 *ring, const double2 *ep, con
 }
 __global__ void __launch_bounds__(kBlock) k2d_fluid_delta(const double2 *__restrict__ ep, const double *__restrict__ imass, const int *__restrict__ group, u32 n,
                                                           int op, double p0, FluidConsts K, const double *__restrict__ lambda, const u32 *__restrict__ nbcount,
-                                                          const u32 *__restrict__ counts, double2 *__restrict__ delta, const double2 *__restrict__ v,
-                                                          double2 *__restrict__ f) {
+                                                          const u32 *nbr_keep, const u32 *__restrict__ counts, double2 *__restrict__ delta,
+                                                          const double2 *__restrict__ v, double2 *__restrict__ f) {
     __shared__ u32 rings[kBlock / 32][kRing];
     const u32 i = (blockIdx.x * kBlock + threadIdx.x) >> 5;
     if (i >= n || group[i] != op) return;  // warp-uniform
-    d_fluid_delta(i, threadIdx.x & 31, rings[threadIdx.x >> 5], ep, imass, n, p0, K, lambda, nbcount, counts, delta, v, f);
+    d_fluid_delta(i, threadIdx.x & 31, rings[threadIdx.x >> 5], ep, imass, n, p0, K, lambda, nbcount, nbr_keep, counts, delta, v, f);
 }
 __device__ __forceinline__ void d_fluid_apply(u32 i, double2 *ep, const double2 *delta) {
     double2 e = ep[i];
@@ -783,7 +803,7 @@ struct FusedTick {
     const double2 *sdf_grad, *rs;
     const int *phase, *bod, *group, *raw;
     const u32 *static_counts;
-    u32 *nb, *cnt, *flags, *counts, *draws, *rank, *lvl, *nbcount, *scalars, *scalars_out;
+    u32 *nb, *cnt, *flags, *counts, *draws, *rank, *lvl, *nbcount, *nbr_keep, *scalars, *scalars_out;
     unsigned char *nbq;
     const u32 *b_first, *b_count;
     const double *b_imass, *b_stiff;
@@ -895,13 +915,13 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k2d_tick_fused(const FusedTick
                 for (u32 i = tid; i < n; i += kFusedBlock) s_ep[i] = A.ep[i];
                 __syncthreads();
             }
-            for (u32 i = cwarp; i < n; i += cwarps) d_fluid_lambda(i, lane, s_ring[warp], all_ep, c_imass, c_phase, c_group, n, (int)op.index, op.p0, K, A.lambda, A.nbcount, A.v, A.f);
+            for (u32 i = cwarp; i < n; i += cwarps) d_fluid_lambda(i, lane, s_ring[warp], all_ep, c_imass, c_phase, c_group, n, (int)op.index, op.p0, K, A.lambda, A.nbcount, A.nbr_keep, A.v, A.f);
             cluster.sync();  // every lambda is written
             PS2D_PHASE(3);
             if (lead && op.keep && it + 1 == A.solver_iterations)
                 for (u32 i = tid; i < n; i += kFusedBlock) A.lambda_keep[i] = __ldcg(A.lambda + i);
             for (u32 i = cwarp; i < n; i += cwarps)
-                if (c_group[i] == (int)op.index) d_fluid_delta(i, lane, s_ring[warp], all_ep, c_imass, n, op.p0, K, A.lambda, A.nbcount, A.counts, A.delta, A.v, A.f);
+                if (c_group[i] == (int)op.index) d_fluid_delta(i, lane, s_ring[warp], all_ep, c_imass, n, op.p0, K, A.lambda, A.nbcount, A.nbr_keep, A.counts, A.delta, A.v, A.f);
             cluster.sync();  // every delta is written, nobody reads the positions any more
             if (lead) {
                 for (u32 i = tid; i < n; i += kFusedBlock)
@@ -1026,6 +1046,7 @@ struct Ps2dCtx {
     u32 fused_nops = 0;
     u32 dc_total = 0;                  // distance constraints in the STANDARD list
     u32 *scalars_out = nullptr;        // scalars_host as the device sees it (mapped pinned memory), or null
+    u32 *nbr_keep = nullptr;           // kNbrKeep neighbour indices per particle, first loop -> second loop of a fluid / gas constraint (null: max_particles too large)
     bool last_tick_fused = false;
     AppendRec *append_host = nullptr, *append_dev = nullptr;  // staging of ps2d_add_particles
     size_t append_cap = 0;
@@ -1102,6 +1123,7 @@ extern "C" int ps2d_create(int device, const Ps2dParams *params, uint64_t max_pa
          dev_alloc(&c->nbcount, n) && dev_alloc(&c->nb, n * kMaxC) && dev_alloc(&c->cnt, n) && dev_alloc(&c->lvl, n * kEntries) && dev_alloc(&c->cur, n) &&
          dev_alloc(&c->nbq, n * kMaxC) && dev_alloc(&c->scalars, 8) && cudaMallocHost((void **)&c->scalars_host, 32) == cudaSuccess;
     if (ok) c->window_base_dev = c->scalars + 4;
+    if (ok && n <= (1u << 20) && !dev_alloc(&c->nbr_keep, n * kNbrKeep)) { c->nbr_keep = nullptr; cudaGetLastError(); }  // optional: 512 B per particle
     if (ok && getenv("PS2D_FUSED_PROFILE")) ok = dev_alloc(&c->fused_prof, 8) && cudaMemset(c->fused_prof, 0, 64) == cudaSuccess;
     if (ok && cudaHostGetDevicePointer((void **)&c->scalars_out, c->scalars_host, 0) != cudaSuccess) { c->scalars_out = nullptr; cudaGetLastError(); }
     if (ok) ok = cudaMemsetAsync(c->f, 0, n * 16, c->stream) == cudaSuccess && cudaMemsetAsync(c->lambda, 0, n * 8, c->stream) == cudaSuccess &&
@@ -1132,7 +1154,7 @@ extern "C" int ps2d_destroy(Ps2dCtx *c) {
     }
     void *ptrs[] = {c->p, c->v, c->ep, c->f, c->delta, c->rs, c->sdf_grad, c->imass, c->tmass, c->sfric, c->kfric, c->lambda, c->sdf_dist, c->phase, c->bod,
                     c->group, c->raw, c->static_counts, c->flags, c->counts, c->draws, c->rank, c->nbcount, c->nb, c->cnt, c->lvl, c->cur, c->nbq, c->scalars,
-                    c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center, c->dc_i1, c->dc_i2, c->dc_level_off, c->dc_rest, c->lambda_keep, c->fused_ops};
+                    c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center, c->dc_i1, c->dc_i2, c->dc_level_off, c->dc_rest, c->lambda_keep, c->fused_ops, c->nbr_keep};
     for (void *q : ptrs) if (q) cudaFree(q);
     if (c->scalars_host) cudaFreeHost(c->scalars_host);
     if (c->tick_graph) cudaGraphExecDestroy(c->tick_graph);
@@ -1647,11 +1669,11 @@ static u32 issue_tick(Ps2dCtx *c, double dt) {
             }
             const FluidConsts K = op.kind == STD_GAS ? FluidConsts{.2, .25, .5, 1, op.open} : FluidConsts{.1, .2, 0., 0, 0};
             const u32 wblocks = (n + kBlock / 32 - 1) / (kBlock / 32);  // one warp per particle
-            k2d_fluid_lambda<<<wblocks, kBlock, 0, s>>>(c->ep, c->imass, c->phase, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->v, c->f);
+            k2d_fluid_lambda<<<wblocks, kBlock, 0, s>>>(c->ep, c->imass, c->phase, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->nbr_keep, c->v, c->f);
             if (it + 1 == P.solver_iterations)
                 for (const FluidEmitterRec &fe : c->fluid_emitters)
                     if (fe.standard_index == k) CU2(cudaMemcpyAsync(c->lambda_keep, c->lambda, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
-            k2d_fluid_delta<<<wblocks, kBlock, 0, s>>>(c->ep, c->imass, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->counts, c->delta, c->v, c->f);
+            k2d_fluid_delta<<<wblocks, kBlock, 0, s>>>(c->ep, c->imass, c->group, n, (int)k, op.p0, K, c->lambda, c->nbcount, c->nbr_keep, c->counts, c->delta, c->v, c->f);
             k2d_fluid_apply<<<blocks, kBlock, 0, s>>>(c->ep, c->delta, c->group, n, (int)k);
             launches += 3;
             k++;
@@ -1732,7 +1754,7 @@ extern "C" int ps2d_tick(Ps2dCtx *c, double dt) {
         A.sdf_grad = c->sdf_grad; A.rs = c->rs;
         A.phase = c->phase; A.bod = c->bod; A.group = c->group; A.raw = c->raw;
         A.static_counts = c->static_counts;
-        A.nb = c->nb; A.cnt = c->cnt; A.flags = c->flags; A.counts = c->counts; A.draws = c->draws; A.rank = c->rank; A.lvl = c->lvl; A.nbcount = c->nbcount;
+        A.nb = c->nb; A.cnt = c->cnt; A.flags = c->flags; A.counts = c->counts; A.draws = c->draws; A.rank = c->rank; A.lvl = c->lvl; A.nbcount = c->nbcount; A.nbr_keep = c->nbr_keep;
         A.scalars = c->scalars; A.scalars_out = c->scalars_out;
         A.nbq = c->nbq;
         A.b_first = c->b_first; A.b_count = c->b_count; A.b_imass = c->b_imass; A.b_stiff = c->b_stiff; A.b_center = c->b_center; A.b_angle = c->b_angle;
