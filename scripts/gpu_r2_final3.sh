@@ -3,6 +3,7 @@
 mkdir -p gpurun_out
 T=r2zz
 ( time timeout 1800 python -m pytest tests -m gpu -q --durations=8 ) > gpurun_out/${T}_pytest_all.log 2>&1; echo "pytest rc=$?"; tail -14 gpurun_out/${T}_pytest_all.log
+rm -f gpurun_out/${T}_ps2d_parity.txt; PS2D_REPORT=gpurun_out/${T}_ps2d_parity.txt timeout 600 python -m pytest tests/test_gpu_2d_full.py -m gpu -q > /dev/null 2>&1; echo "parity report rc=$?"; cat gpurun_out/${T}_ps2d_parity.txt | cut -c1-200
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${T}_smoke.log
 ( time timeout 900 python bench.py --steps 20 --warmup 3 ) > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$?"
 python - <<'PY'

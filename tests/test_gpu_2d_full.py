@@ -5,8 +5,8 @@ each started from a full restart state of the reference.
 
 Tolerances (double precision; the level-scheduled lists execute the reference's update sequence per particle, so the GPU
 differs from the x86-64 reference only in the last bits of exp / sin / cos / atan2 / pow): |dp| <= 1e-12 for the first
-three kept ticks after the restart state, 1e-9 for the later ones.  Measured on B200 (profiles/r1h_ps2d_parity.txt):
-0 (bit-identical) for the scenes without fluid or gas over (nearly) all kept ticks, <= 4e-13 for the others (their neighbour
+three kept ticks after the restart state, 1e-9 for the later ones.  Measured on B200 (profiles/r2zz_ps2d_parity.txt):
+0 (bit-identical) for the scenes without fluid or gas over (nearly) all kept ticks, <= 5e-13 after 20 ticks for the others (their neighbour
 sums run as a warp-wide tree instead of the reference's sequential loop)."""
 import json
 import os
