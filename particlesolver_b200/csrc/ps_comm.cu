@@ -207,7 +207,8 @@ extern "C" int ps_comm_set_slab(PsCtx *c, float x_lo, float x_hi, float drift, i
     m->contact_sources_seen = c->contact_sources;
     m->nonfluid_sources_seen = c->nonfluid_sources;
     // an all-fluid run: K6 fills the outgoing lambda messages itself (ps_slab_set_lambda_sinks), no pack pass over the sorted slots
-    if (m->exchange_lambda && census[1] == 0.) OK(ps_slab_set_lambda_sinks(c, m->lam_send[0], m->lam_send[1], m->halo_cap));
+    static const bool no_sinks = getenv("PS_NO_LAMBDA_SINKS") != nullptr;  // (measurements: the separate pack pass instead)
+    if (m->exchange_lambda && census[1] == 0. && !no_sinks) OK(ps_slab_set_lambda_sinks(c, m->lam_send[0], m->lam_send[1], m->halo_cap));
     else OK(ps_slab_set_lambda_sinks(c, nullptr, nullptr, 0));
     m->slab_set = true;
     return PS_OK;
