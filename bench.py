@@ -703,6 +703,16 @@ def run_slabs(args, rank, world, local_rank):
     # (+ lambda pack / unpack 2 per iteration when the ghost lambdas are exchanged)
     launches_per_step = 1 + ITERS * (4 + passes + 3 + ((4 + 2 * exchange_lambda) if world > 1 else 0)) + (2 if world > 1 else 0) + 1
 
+    # ---- correctness of the decomposed run: particles conserved, density error and kinetic energy of the global state ----
+    # taken HERE, after exactly warmup + steps physical steps from the initial lattice (the end-to-end leg below re-submits captured host
+    # frames, which restarts the physics from those frames while nothing migrates: its steps are timing steps, not simulation time).
+    # `psolver_cli --app gpu --scene c5 --planes <nx> --ranks 1 --steps <warmup + steps> --json` is the same scene undecomposed.
+    mde, xde, ke = sol.fluid_stats()          # over this rank's owned particles, ghosts as neighbours
+    owned_now = sol.n_owned
+    g_count = reduce(float(owned_now), dist.ReduceOp.SUM)
+    g_mde = reduce(mde * owned_now, dist.ReduceOp.SUM) / max(g_count, 1.0)
+    g_xde = reduce(xde, dist.ReduceOp.MAX)
+    g_ke = reduce(ke, dist.ReduceOp.SUM)
     # ---- end to end: the step's inputs come from pinned host memory, its result goes back to it ----
     # ps_io_begin / ps_io_end (include/psolver.h) around the slab step: the owned particles' positions + velocities are taken from
     # pinned host memory before every step and delivered to pinned host memory after it, double-buffered on the context's copy
@@ -773,13 +783,6 @@ def run_slabs(args, rank, world, local_rank):
         else:
             step()
     dom.eng = eng
-    # ---- correctness of the decomposed run: particles conserved, density error and kinetic energy of the global state ----
-    mde, xde, ke = sol.fluid_stats()          # over this rank's owned particles, ghosts as neighbours
-    owned_now = sol.n_owned
-    g_count = reduce(float(owned_now), dist.ReduceOp.SUM)
-    g_mde = reduce(mde * owned_now, dist.ReduceOp.SUM) / max(g_count, 1.0)
-    g_xde = reduce(xde, dist.ReduceOp.MAX)
-    g_ke = reduce(ke, dist.ReduceOp.SUM)
     peak, peak_kind = measured_peaks()
     n_local = sol.n  # owned + ghosts: what the kernels process
     fluid_ms = (acc.get("solve_fluid", 0.0) + acc.get("solve_fluid_lambda", 0.0) + acc.get("solve_fluid_delta", 0.0)) / prof_steps / ITERS
@@ -810,9 +813,12 @@ def run_slabs(args, rank, world, local_rank):
                 "roofline": roofline, "stage_ms_per_step_rank0": stage_ms,
                 "state_check": {"particles_total_now": int(g_count), "particles_conserved": int(g_count) == total, "mean_density_error": g_mde,
                                 "max_density_error": g_xde, "kinetic_energy": g_ke,
-                                "after_steps": max(args.warmup, 3) + args.steps + 1 + e2e_steps + prof_steps,
-                                "note": "global statistics over the owned particles of all ranks (ps_fluid_stats per rank, all-reduced); the same scene "
-                                        "undecomposed gives the same figures up to summation order (tests/test_gpu_slab*.py compare per particle)"},
+                                "after_steps": max(args.warmup, 3) + args.steps,
+                                "kinetic_energy_per_particle": g_ke / max(g_count, 1.0),
+                                "note": "global statistics over the owned particles of all ranks (ps_fluid_stats per rank, all-reduced) after warmup + steps "
+                                        "steps from the initial lattice, before the end-to-end leg; the same scene undecomposed (psolver_cli --app gpu --scene c5 "
+                                        f"--planes {nx} --ranks 1 --steps {max(args.warmup, 3) + args.steps}) gives the same figures up to summation order "
+                                        "(profiles/r2zz_state_check_vs_undecomposed.txt; tests/test_gpu_slab*.py compare per particle)"},
                 "cpu_baseline": None if world > 1 else "see the c3 line (bench.py without --workload)",
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
