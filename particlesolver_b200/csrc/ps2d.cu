@@ -1150,8 +1150,8 @@ extern "C" int ps2d_destroy(Ps2dCtx *c) {
         const double t = (double)c->fused_ticks;
         fprintf(stderr, "ps2d fused tick, cycles per tick over %.0f ticks: set-up %.0f, contacts %.0f, distance runs %.0f, fluid lambda %.0f, fluid delta+apply %.0f, shape %.0f, finish %.0f\n",
                 t, h[0] / t, h[1] / t, h[2] / t, h[3] / t, h[4] / t, h[5] / t, h[6] / t);
-        cudaFree(c->fused_prof);
     }
+    if (c->fused_prof) cudaFree(c->fused_prof);
     void *ptrs[] = {c->p, c->v, c->ep, c->f, c->delta, c->rs, c->sdf_grad, c->imass, c->tmass, c->sfric, c->kfric, c->lambda, c->sdf_dist, c->phase, c->bod,
                     c->group, c->raw, c->static_counts, c->flags, c->counts, c->draws, c->rank, c->nbcount, c->nb, c->cnt, c->lvl, c->cur, c->nbq, c->scalars,
                     c->b_first, c->b_count, c->b_imass, c->b_stiff, c->b_angle, c->b_center, c->dc_i1, c->dc_i2, c->dc_level_off, c->dc_rest, c->lambda_keep, c->fused_ops, c->nbr_keep};
