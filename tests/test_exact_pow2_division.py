@@ -41,3 +41,16 @@ def test_division_by_a_power_of_two_equals_multiplication_by_its_reciprocal_bit_
             same = (q.view(np.uint64) == p.view(np.uint64)) | (np.isnan(q) & np.isnan(p))
             assert same.all(), (e, x[~same][:3])
             assert np.array_equal(np.isfinite(q[finite]), np.isfinite(p[finite]))
+
+
+def test_contact_search_square_root_is_only_needed_near_the_threshold():
+    """d_find_contacts decides sqrt(d2) < DIAM - EPS from d2 alone outside a 1e-9 band around the threshold's square (csrc/ps2d.cu)"""
+    T = 0.5 - 1e-4
+    T2 = T * T
+    rng = np.random.default_rng(2)
+    rel = np.concatenate([rng.uniform(-1e-6, 1e-6, 400_000), rng.uniform(-3e-9, 3e-9, 400_000), np.array([-1e-9, 1e-9, 0.0])])
+    d2 = T2 * (1.0 + rel)
+    exact = np.sqrt(d2) < T
+    fast = np.where(d2 < T2 * (1.0 - 1e-9), True, np.where(d2 > T2 * (1.0 + 1e-9), False, exact))
+    assert np.array_equal(fast, exact)
+    assert (d2 < T2 * (1.0 - 1e-9)).sum() > 100_000 and (d2 > T2 * (1.0 + 1e-9)).sum() > 100_000   # both shortcuts exercised
