@@ -131,11 +131,13 @@ def test_cli_switches_the_optional_contact_rules_on():
 def test_2d_tick_graph_replay_equals_eager_issue():
     """the 2-D tick is replayed as a CUDA graph once its key has stood still for a few ticks; PS_NO_GRAPH=1 issues every launch
     eagerly — the two must be the same computation (scenes with walls + jitter draws, rigid bodies, an emitter that changes n)"""
+    seq = dict(os.environ, PS2D_FUSED_MAX_N="0")   # the launch sequence (these scenes would otherwise run their tick as one fused kernel)
     for key in ("6", "w", "s"):
-        a = subprocess.run([CLI, "--app", "cpu", "--scene", key, "--ticks", "120", "--json"], capture_output=True, text=True, check=True).stdout
+        a = subprocess.run([CLI, "--app", "cpu", "--scene", key, "--ticks", "120", "--json"], capture_output=True, text=True, check=True, env=seq).stdout
         b = subprocess.run([CLI, "--app", "cpu", "--scene", key, "--ticks", "120", "--json"], capture_output=True, text=True, check=True,
-                           env=dict(os.environ, PS_NO_GRAPH="1")).stdout
+                           env=dict(seq, PS_NO_GRAPH="1")).stdout
         a, b = json.loads(a), json.loads(b)
+        assert a["launches_per_tick"] > 1 and b["launches_per_tick"] > 1
         assert a["kinetic_energy"] == b["kinetic_energy"] and a["rand_calls"] == b["rand_calls"] and a["particles"] == b["particles"], key
 
 
